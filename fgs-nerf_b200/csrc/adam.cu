@@ -1,0 +1,189 @@
+// Masked / dense / per-voxel-lr Adam as bandwidth-bound streaming kernels (sm_100a).
+//
+// Replaces model/cuda/adam_upd_kernel.cu:8-58 (three scalar one-thread-per-element kernels)
+// and the host step_size of :72,:94,:117.  Here: 128-bit loads/stores, grid sized to the 148
+// SMs with a grid-stride loop, and a multi-tensor variant that updates all MLP tensors in one
+// launch (the reference's MaskedAdam.step issues one launch per tensor, model/adam.py:190-221).
+// Algorithmic traffic: dense 28 B/param (p,g,m,v read; p,m,v written); masked 4 B/param where
+// grad==0 (only g is read) -- the masked kernel loads p/m/v only inside the taken branch.
+//
+// Arithmetic is the reference's SASS sequence (so p,m,v are bit-identical):
+//   m = fma(beta1, m, (1-beta1)*g);  v = fma(beta2, v, ((1-beta2)*g)*g);
+//   p = p - (step_size*m) / (sqrt(v) + eps)        (IEEE sqrt and divide)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct AdamConst {
+  float step_size, beta1, beta2, omb1, omb2, eps;
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamConst& c,
+                                          float lr_scale) {
+  m = __fmaf_rn(m, c.beta1, __fmul_rn(g, c.omb1));
+  v = __fmaf_rn(v, c.beta2, __fmul_rn(g, __fmul_rn(g, c.omb2)));
+  const float num = __fmul_rn(lr_scale, m);
+  p = __fsub_rn(p, __fdiv_rn(num, __fadd_rn(__fsqrt_rn(v), c.eps)));
+}
+
+// MODE 0 dense, 1 masked (skip g==0), 2 per-voxel lr (dense)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
+            float* __restrict__ exp_avg_sq, const float* __restrict__ perlr, long long n,
+            AdamConst c) {
+  const long long n4 = n >> 2;
+  const long long tid = blockIdx.x * (long long)kBlock + threadIdx.x;
+  const long long nth = (long long)gridDim.x * kBlock;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 g = ld_stream4(grad + 4 * i);
+    if (MODE == 1 && g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    float4 p = ld4(param + 4 * i), m = ld4(exp_avg + 4 * i), v = ld4(exp_avg_sq + 4 * i);
+    float4 l = make_float4(c.step_size, c.step_size, c.step_size, c.step_size);
+    if (MODE == 2) {
+      // kernel.cu:56: step_size * perlr[index] * exp_avg[index] -> (step_size*perlr)*m
+      const float4 q = ld_stream4(perlr + 4 * i);
+      l.x = __fmul_rn(c.step_size, q.x); l.y = __fmul_rn(c.step_size, q.y);
+      l.z = __fmul_rn(c.step_size, q.z); l.w = __fmul_rn(c.step_size, q.w);
+    }
+    if (MODE != 1 || g.x != 0.f) adam_elem(p.x, g.x, m.x, v.x, c, l.x);
+    if (MODE != 1 || g.y != 0.f) adam_elem(p.y, g.y, m.y, v.y, c, l.y);
+    if (MODE != 1 || g.z != 0.f) adam_elem(p.z, g.z, m.z, v.z, c, l.z);
+    if (MODE != 1 || g.w != 0.f) adam_elem(p.w, g.w, m.w, v.w, c, l.w);
+    st4(param + 4 * i, p);
+    st4(exp_avg + 4 * i, m);
+    st4(exp_avg_sq + 4 * i, v);
+  }
+  // tail (< 4 elements)
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) {
+    const float g = grad[i];
+    if (MODE == 1 && g == 0.f) continue;
+    float p = param[i], m = exp_avg[i], v = exp_avg_sq[i];
+    const float l = (MODE == 2) ? __fmul_rn(c.step_size, perlr[i]) : c.step_size;
+    adam_elem(p, g, m, v, c, l);
+    param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+  }
+}
+
+// Scalar fallback for pointers that are not 16-byte aligned (tensor views).
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+adam_kernel_scalar(float* __restrict__ param, const float* __restrict__ grad,
+                   float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                   const float* __restrict__ perlr, long long n, AdamConst c) {
+  for (long long i = blockIdx.x * (long long)kBlock + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kBlock) {
+    const float g = grad[i];
+    if (MODE == 1 && g == 0.f) continue;
+    float p = param[i], m = exp_avg[i], v = exp_avg_sq[i];
+    const float l = (MODE == 2) ? __fmul_rn(c.step_size, perlr[i]) : c.step_size;
+    adam_elem(p, g, m, v, c, l);
+    param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+  }
+}
+
+struct MultiArgs {
+  float* p[FGS_MAX_MT];
+  const float* g[FGS_MAX_MT];
+  float* m[FGS_MAX_MT];
+  float* v[FGS_MAX_MT];
+  long long n[FGS_MAX_MT];
+  float step_size[FGS_MAX_MT];
+  int blk_start[FGS_MAX_MT + 1];  // first CTA of each tensor
+  int count;
+  float beta1, beta2, omb1, omb2, eps;
+};
+
+constexpr int kMtChunk = kBlock * 4;  // elements per CTA in the multi-tensor kernel
+
+__global__ void __launch_bounds__(kBlock) adam_multi_kernel(const __grid_constant__ MultiArgs a) {
+  int t = 0;
+  while (t + 1 < a.count && (int)blockIdx.x >= a.blk_start[t + 1]) ++t;
+  const long long base = (long long)(blockIdx.x - a.blk_start[t]) * kMtChunk;
+  AdamConst c{a.step_size[t], a.beta1, a.beta2, a.omb1, a.omb2, a.eps};
+  float* __restrict__ P = a.p[t];
+  const float* __restrict__ G = a.g[t];
+  float* __restrict__ M = a.m[t];
+  float* __restrict__ V = a.v[t];
+  const long long n = a.n[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * kBlock + threadIdx.x;
+    if (i < n) {
+      float p = P[i], m = M[i], v = V[i];
+      adam_elem(p, G[i], m, v, c, c.step_size);
+      P[i] = p; M[i] = m; V[i] = v;
+    }
+  }
+}
+
+// adam_upd_kernel.cu:72 -- all in float, as the reference's host code evaluates it
+inline float host_step_size(float lr, float beta1, float beta2, int step) {
+  return lr * sqrtf(1 - powf(beta2, (float)step)) / (1 - powf(beta1, (float)step));
+}
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <int MODE>
+int launch_adam(float* param, const float* grad, float* m, float* v, const float* perlr,
+                int64_t n, const AdamConst& c, cudaStream_t st) {
+  const bool vec = aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v) &&
+                   (MODE != 2 || aligned16(perlr));
+  if (vec) {
+    const int grid = fgs::stream_grid((n + 3) / 4, kBlock, 8);
+    adam_kernel<MODE><<<grid, kBlock, 0, st>>>(param, grad, m, v, perlr, n, c);
+  } else {
+    const int grid = fgs::stream_grid(n, kBlock, 8);
+    adam_kernel_scalar<MODE><<<grid, kBlock, 0, st>>>(param, grad, m, v, perlr, n, c);
+  }
+  return fgs::check_launch("adam_upd");
+}
+
+}  // namespace
+
+extern "C" {
+
+int fgs_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                 const float* perlr, int64_t n, int step, float beta1, float beta2, float lr,
+                 float eps, int mode, fgs_stream_t stream) {
+  FGS_REQUIRE(n >= 0, "n < 0");
+  FGS_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0,1,2");
+  FGS_REQUIRE(mode != 2 || perlr != nullptr, "perlr is NULL");
+  if (n == 0) return 0;
+  AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case 0: return launch_adam<0>(param, grad, exp_avg, exp_avg_sq, perlr, n, c, st);
+    case 1: return launch_adam<1>(param, grad, exp_avg, exp_avg_sq, perlr, n, c, st);
+    default: return launch_adam<2>(param, grad, exp_avg, exp_avg_sq, perlr, n, c, st);
+  }
+}
+
+int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* grads,
+                       float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
+                       const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                       fgs_stream_t stream) {
+  FGS_REQUIRE(n_tensors >= 0 && n_tensors <= FGS_MAX_MT, "n_tensors out of range");
+  if (n_tensors == 0) return 0;
+  MultiArgs a;
+  a.count = n_tensors;
+  a.beta1 = beta1; a.beta2 = beta2; a.omb1 = 1 - beta1; a.omb2 = 1 - beta2; a.eps = eps;
+  int blk = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    a.p[t] = params[t]; a.g[t] = grads[t]; a.m[t] = exp_avgs[t]; a.v[t] = exp_avg_sqs[t];
+    a.n[t] = numels[t];
+    a.step_size[t] = host_step_size(lrs[t], beta1, beta2, steps[t]);
+    a.blk_start[t] = blk;
+    blk += fgs::cdiv(numels[t] > 0 ? numels[t] : 0, kMtChunk);
+  }
+  a.blk_start[n_tensors] = blk;
+  if (blk == 0) return 0;
+  adam_multi_kernel<<<blk, kBlock, 0, (cudaStream_t)stream>>>(a);
+  return fgs::check_launch("adam_upd_multi");
+}
+
+}  // extern "C"
