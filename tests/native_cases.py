@@ -30,9 +30,10 @@ def alpha_case(n_rays=97, seed=1, max_len=70):
     rs = np.random.RandomState(seed)
     lens = rs.randint(0, max_len, size=n_rays)
     lens[rs.rand(n_rays) < 0.15] = 0
-    lens[5] = 0
+    if n_rays > 8:
+        lens[5] = 0
+        lens[7] = 1
     lens[n_rays - 1] = 0          # trailing empty ray
-    lens[7] = 1
     ray_id = np.repeat(np.arange(n_rays), lens).astype(np.int64)
     kind = rs.randint(0, 3, size=n_rays)
     alpha = np.empty(ray_id.shape[0], np.float32)
