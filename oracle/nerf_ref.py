@@ -9,7 +9,7 @@ is the reference's arithmetic.  The three native ops it needs (sample_pts_on_ray
 alpha2weight_backward; plus adam / TV for the step) are injected through `native`:
   * on the CPU: oracle.native_ref (the C restatement)  -> CPU baseline and golden fixtures,
   * on the GPU box: the reference's own compiled kernels (oracle/_ref via oracle.ref_ext).
-Pinned by tests/golden/fine_golden.pt, which tests/golden/make_fine_golden.py produces by
+Pinned by tests/golden/fine_golden.npz, which tests/golden/make_fine_golden.py produces by
 importing the REAL model/nerf.py from /root/reference (with stubs for its missing third-party
 imports) and running it on the same inputs.
 
