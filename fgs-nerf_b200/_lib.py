@@ -30,6 +30,10 @@ _SIGS = {
     "fgs_reset_launch_count": (None, []),
     "fgs_set_device": (_i, [_i]),
     "fgs_device_sm_count": (_i, [_i, _p, _p, _p]),
+    "fgs_prof_begin": (_i, [_p]),
+    "fgs_prof_end": (_i, []),
+    "fgs_prof_get": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
+    "fgs_memset_zero": (_i, [_p, _l, _p]),
     "fgs_infer_t_minmax": (_i, [_p, _p, _p, _p, _f, _f, _i, _p, _p, _p]),
     "fgs_infer_n_samples": (_i, [_p, _p, _p, _f, _i, _p, _p]),
     "fgs_infer_ray_start_dir": (_i, [_p, _p, _p, _i, _p, _p, _p]),
@@ -96,3 +100,20 @@ def check_input(t, name, dtype=None):
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError(f"{name} must be {dtype} (got {t.dtype}); fgs_b200 kernels are fp32-only")
+
+
+def prof_begin():
+    check(lib.fgs_prof_begin(stream()))
+
+
+def prof_end():
+    """-> list of (launch name, milliseconds), in launch order."""
+    n = lib.fgs_prof_end()
+    if n < 0:
+        check(1)
+    out = []
+    name, ms = C.c_char_p(), C.c_float()
+    for i in range(n):
+        check(lib.fgs_prof_get(i, C.byref(name), C.byref(ms)))
+        out.append((name.value.decode(), float(ms.value)))
+    return out

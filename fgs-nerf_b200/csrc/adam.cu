@@ -140,7 +140,7 @@ int launch_adam(float* param, const float* grad, float* m, float* v, const float
     const int grid = fgs::stream_grid(n, kBlock, 8);
     adam_kernel_scalar<MODE><<<grid, kBlock, 0, st>>>(param, grad, m, v, perlr, n, c);
   }
-  return fgs::check_launch("adam_upd");
+  return fgs::check_launch("adam_upd", st);
 }
 
 }  // namespace
@@ -183,7 +183,7 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
   a.blk_start[n_tensors] = blk;
   if (blk == 0) return 0;
   adam_multi_kernel<<<blk, kBlock, 0, (cudaStream_t)stream>>>(a);
-  return fgs::check_launch("adam_upd_multi");
+  return fgs::check_launch("adam_upd_multi", (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,3 +28,56 @@ int fgs_device_sm_count(int device, int* sm_count, int* cc_major, int* cc_minor)
 }
 
 }  // extern "C"
+
+// ---- per-launch timing (bench.py / profiles): one cudaEvent per launch on the launching stream
+namespace fgs {
+namespace {
+constexpr int kMaxEv = 16384;
+bool g_prof_on = false;
+int g_prof_n = 0, g_prof_created = 0;
+cudaEvent_t g_ev[kMaxEv];
+const char* g_ev_name[kMaxEv];
+}  // namespace
+
+void prof_mark(const char* what, cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= kMaxEv) return;
+  if (g_prof_n >= g_prof_created) {
+    if (cudaEventCreate(&g_ev[g_prof_created]) != cudaSuccess) return;
+    ++g_prof_created;
+  }
+  cudaEventRecord(g_ev[g_prof_n], st);
+  g_ev_name[g_prof_n] = what;
+  ++g_prof_n;
+}
+}  // namespace fgs
+
+extern "C" {
+
+int fgs_prof_begin(fgs_stream_t stream) {
+  fgs::g_prof_n = 0;
+  fgs::g_prof_on = true;
+  fgs::prof_mark("begin", (cudaStream_t)stream);
+  return 0;
+}
+
+int fgs_prof_end(void) {
+  fgs::g_prof_on = false;
+  if (fgs::g_prof_n == 0) return 0;
+  int rc = fgs::check_cuda(cudaEventSynchronize(fgs::g_ev[fgs::g_prof_n - 1]), "prof sync");
+  return rc ? -1 : fgs::g_prof_n - 1;
+}
+
+int fgs_prof_get(int i, const char** name, float* ms) {
+  if (i < 0 || i + 1 >= fgs::g_prof_n) return FGS_E_BADARG;
+  *name = fgs::g_ev_name[i + 1];
+  return fgs::check_cuda(cudaEventElapsedTime(ms, fgs::g_ev[i], fgs::g_ev[i + 1]), "prof elapsed");
+}
+
+int fgs_memset_zero(void* ptr, int64_t bytes, fgs_stream_t stream) {
+  if (bytes <= 0) return 0;
+  int rc = fgs::check_cuda(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream), "memset");
+  fgs::prof_mark("memset", (cudaStream_t)stream);
+  return rc;
+}
+
+}  // extern "C"

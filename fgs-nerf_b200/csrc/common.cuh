@@ -29,6 +29,15 @@ inline int check_launch(const char* what) {
   return 0;
 }
 
+// Optional per-launch timing (fgs_prof_begin/end): one event per launch on the launching stream.
+void prof_mark(const char* what, cudaStream_t st);
+
+inline int check_launch(const char* what, cudaStream_t st) {
+  const int rc = check_launch(what);
+  prof_mark(what, st);
+  return rc;
+}
+
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "fgs_b200: %s: %s", what, cudaGetErrorString(e));

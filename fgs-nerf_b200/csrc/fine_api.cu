@@ -1,0 +1,216 @@
+// C-ABI of the fused fine-stage step (include/fgs_b200_fine.h): kernel sequencing only.
+//   fgs_fine_forward  : march -> scan -> level1 -> scan -> compact2 -> feat -> 8 GEMMs -> composite
+//   fgs_fine_loss     : composite with the loss block + first backward hop fused
+//   fgs_fine_backward : 8 layers x (dW GEMM, db colsum, dX GEMM) -> feat_bwd -> level1_bwd
+// plus the stand-alone DenseGrid / MaskCache trilinear ops.  No host synchronisation anywhere.
+#include "fine_common.cuh"
+
+namespace fine {
+int launch_march(const FgsFineParams& P, cudaStream_t st);
+int launch_feat(const FgsFineParams& P, cudaStream_t st);
+int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st);
+int launch_composite(const FgsFineParams& P, const FgsFineLoss* L, cudaStream_t st);
+int launch_level1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t st);
+int gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+         int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
+         const int32_t* rows_dev, cudaStream_t st);
+int colsum(const float* X, int ld, int rows, int N, const int32_t* rows_dev, float* out, cudaStream_t st);
+}  // namespace fine
+
+namespace {
+
+using namespace fine;
+constexpr int W = FGS_MLP_WIDTH;
+
+int check_params(const FgsFineParams* p) {
+  FGS_REQUIRE(p != nullptr, "params is NULL");
+  FGS_REQUIRE(p->n_rays > 0 && p->n_rays <= (1 << 20), "n_rays out of range (1..2^20)");
+  FGS_REQUIRE(p->X >= 2 && p->Y >= 2 && p->Z >= 2, "grid too small");
+  FGS_REQUIRE(p->cap_words > 0 && p->cap_m1 > 0 && p->cap_m2 > 0, "capacities must be > 0");
+  FGS_REQUIRE(p->stepdist > 0.f, "stepdist must be > 0");
+  return 0;
+}
+
+float* hidden(const FgsFineParams& P, int i) { return P.H + (size_t)i * P.cap_m2 * W; }
+
+}  // namespace
+
+extern "C" {
+
+int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  const FgsFineParams& P = *p;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = launch_march(P, st))) return rc;
+  if ((rc = launch_feat(P, st))) return rc;
+  const int* m2 = P.counters + FGS_CNT_M2;
+  const int cap = P.cap_m2;
+  // rgbnet (model/nerf.py:125-134, 877)
+  if ((rc = gemm(0, cap, W, FGS_X0_DIM, P.X0, FGS_X0_LD, P.W[0], FGS_X0_DIM, hidden(P, 0), W, P.B[0], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, W, W, hidden(P, 0), W, P.W[1], W, hidden(P, 1), W, P.B[1], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, W, W, hidden(P, 1), W, P.W[2], W, hidden(P, 2), W, P.B[2], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, W, W, hidden(P, 2), W, P.W[3], W, P.XR, FGS_XR_LD, P.B[3], 0, nullptr, 0, m2, st))) return rc;
+  // refnet (model/nerf.py:136-151, 883-884)
+  if ((rc = gemm(0, cap, W, FGS_XR_DIM, P.XR, FGS_XR_LD, P.W[4], FGS_XR_DIM, hidden(P, 3), W, P.B[4], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, W, W, hidden(P, 3), W, P.W[5], W, hidden(P, 4), W, P.B[5], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, W, W, hidden(P, 4), W, P.W[6], W, hidden(P, 5), W, P.B[6], 1, nullptr, 0, m2, st))) return rc;
+  if ((rc = gemm(0, cap, 3, W, hidden(P, 5), W, P.W[7], W, P.logit, 4, P.B[7], 0, nullptr, 0, m2, st))) return rc;
+  return launch_composite(P, nullptr, st);
+}
+
+int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  FGS_REQUIRE(l && l->target && l->g_alphainv_last && l->loss_out, "loss descriptor incomplete");
+  FGS_REQUIRE(l->n_rays_global >= p->n_rays, "n_rays_global < n_rays");
+  return launch_composite(*p, l, (cudaStream_t)stream);
+}
+
+int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  FGS_REQUIRE(l && l->g_alphainv_last, "loss descriptor incomplete");
+  const FgsFineParams& P = *p;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* m2 = P.counters + FGS_CNT_M2;
+  const int cap = P.cap_m2;
+  const int in_dim[8] = {FGS_X0_DIM, W, W, W, FGS_XR_DIM, W, W, W};
+  const int out_dim[8] = {W, W, W, W, W, W, W, 3};
+  for (int i = 0; i < 8; ++i) {
+    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
+    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
+  }
+  fgs::prof_mark("memset", st);
+  // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
+  // layer 7: logit = H5 W7^T + b7
+  if ((rc = gemm(2, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dlogit, 4, cap, 3, m2, P.gB[7], st))) return rc;
+  if ((rc = gemm(1, cap, W, 3, P.dlogit, 4, P.W[7], W, P.dA, W, nullptr, 0, hidden(P, 5), W, m2, st))) return rc;
+  // layer 6: H5 = relu(H4 W6^T + b6); dA = dZ6
+  if ((rc = gemm(2, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[6], st))) return rc;
+  if ((rc = gemm(1, cap, W, W, P.dA, W, P.W[6], W, P.dB, W, nullptr, 0, hidden(P, 4), W, m2, st))) return rc;
+  // layer 5: dB = dZ5
+  if ((rc = gemm(2, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[5], st))) return rc;
+  if ((rc = gemm(1, cap, W, W, P.dB, W, P.W[5], W, P.dA, W, nullptr, 0, hidden(P, 3), W, m2, st))) return rc;
+  // layer 4: H3 = relu(XR W4^T + b4); dA = dZ4; dXR = dZ4 W4 (no mask: XR is not a ReLU output)
+  if ((rc = gemm(2, W, FGS_XR_DIM, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_DIM, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[4], st))) return rc;
+  if ((rc = gemm(1, cap, FGS_XR_DIM, W, P.dA, W, P.W[4], FGS_XR_DIM, P.dXR, FGS_XR_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  // ---- rgbnet: dZ3 = dXR[:, 0:256] (last rgbnet layer is linear) ----
+  if ((rc = gemm(2, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dXR, FGS_XR_LD, cap, W, m2, P.gB[3], st))) return rc;
+  if ((rc = gemm(1, cap, W, W, P.dXR, FGS_XR_LD, P.W[3], W, P.dB, W, nullptr, 0, hidden(P, 2), W, m2, st))) return rc;
+  // layer 2
+  if ((rc = gemm(2, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[2], st))) return rc;
+  if ((rc = gemm(1, cap, W, W, P.dB, W, P.W[2], W, P.dA, W, nullptr, 0, hidden(P, 1), W, m2, st))) return rc;
+  // layer 1
+  if ((rc = gemm(2, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[1], st))) return rc;
+  if ((rc = gemm(1, cap, W, W, P.dA, W, P.W[1], W, P.dB, W, nullptr, 0, hidden(P, 0), W, m2, st))) return rc;
+  // layer 0
+  if ((rc = gemm(2, W, FGS_X0_DIM, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_DIM, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[0], st))) return rc;
+  if ((rc = gemm(1, cap, FGS_X0_DIM, W, P.dB, W, P.W[0], FGS_X0_DIM, P.dX0, FGS_X0_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  // ---- features -> level-1 quantities -> grids ----
+  if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
+  return launch_level1_bwd(P, l->g_alphainv_last, st);
+}
+
+}  // extern "C"
+
+// ---- stand-alone trilinear ops (DenseGrid.forward/backward, MaskCache) ----------------------
+namespace {
+
+template <bool CL>
+__global__ void __launch_bounds__(256)
+grid_sample_fwd_kernel(const float* __restrict__ grid, int C, fine::GridGeo g, const float* __restrict__ xyz,
+                       long long M, float* __restrict__ out) {
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < M; p += (long long)gridDim.x * 256) {
+    float iw, ih, id;
+    fine::cont_index(g, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], iw, ih, id);
+    const Tri t = tri_setup(iw, ih, id);
+    const size_t V = (size_t)g.X * g.Y * g.Z;
+    for (int ch = 0; ch < C; ++ch) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
+        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
+          const size_t vox = ((size_t)z * g.Y + y) * g.Z + x;
+          acc = __fmaf_rn(__ldg(grid + (CL ? vox * C + ch : (size_t)ch * V + vox)), t.w[c], acc);
+        }
+      }
+      out[p * C + ch] = acc;
+    }
+  }
+}
+
+template <bool CL>
+__global__ void __launch_bounds__(256)
+grid_sample_bwd_kernel(float* __restrict__ g_grid, int C, fine::GridGeo g, const float* __restrict__ xyz,
+                       long long M, const float* __restrict__ g_out) {
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < M; p += (long long)gridDim.x * 256) {
+    float iw, ih, id;
+    fine::cont_index(g, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], iw, ih, id);
+    const Tri t = tri_setup(iw, ih, id);
+    const size_t V = (size_t)g.X * g.Y * g.Z;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
+      if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
+        const size_t vox = ((size_t)z * g.Y + y) * g.Z + x;
+        for (int ch = 0; ch < C; ++ch)
+          atomicAdd(g_grid + (CL ? vox * C + ch : (size_t)ch * V + vox), __fmul_rn(t.w[c], g_out[p * C + ch]));
+      }
+    }
+  }
+}
+
+fine::GridGeo host_geo(const float* mn, const float* mx, int X, int Y, int Z) {
+  fine::GridGeo g;
+  for (int c = 0; c < 3; ++c) {
+    g.mn[c] = mn[c];
+    g.ext[c] = mx[c] - mn[c];  // fp32 subtraction, as torch evaluates (xyz_max - xyz_min)
+  }
+  g.X = X; g.Y = Y; g.Z = Z;
+  return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+// xyz_min / xyz_max are HOST pointers to 3 floats here (scalars of the grid object).
+int fgs_grid_sample_fwd(const float* grid, int C, int X, int Y, int Z, int channels_last,
+                        const float* xyz, int64_t M, const float* xyz_min, const float* xyz_max,
+                        float* out, fgs_stream_t stream) {
+  FGS_REQUIRE(C > 0 && X > 0 && Y > 0 && Z > 0 && M >= 0, "bad size");
+  if (M == 0) return 0;
+  const fine::GridGeo g = host_geo(xyz_min, xyz_max, X, Y, Z);
+  const int grid_dim = fgs::stream_grid(M, 256, 8);
+  if (channels_last)
+    grid_sample_fwd_kernel<true><<<grid_dim, 256, 0, (cudaStream_t)stream>>>(grid, C, g, xyz, M, out);
+  else
+    grid_sample_fwd_kernel<false><<<grid_dim, 256, 0, (cudaStream_t)stream>>>(grid, C, g, xyz, M, out);
+  return fgs::check_launch("grid_sample_fwd", (cudaStream_t)stream);
+}
+
+int fgs_grid_sample_bwd(float* g_grid, int C, int X, int Y, int Z, int channels_last,
+                        const float* xyz, int64_t M, const float* xyz_min, const float* xyz_max,
+                        const float* g_out, fgs_stream_t stream) {
+  FGS_REQUIRE(C > 0 && X > 0 && Y > 0 && Z > 0 && M >= 0, "bad size");
+  if (M == 0) return 0;
+  const fine::GridGeo g = host_geo(xyz_min, xyz_max, X, Y, Z);
+  const int grid_dim = fgs::stream_grid(M, 256, 8);
+  if (channels_last)
+    grid_sample_bwd_kernel<true><<<grid_dim, 256, 0, (cudaStream_t)stream>>>(g_grid, C, g, xyz, M, g_out);
+  else
+    grid_sample_bwd_kernel<false><<<grid_dim, 256, 0, (cudaStream_t)stream>>>(g_grid, C, g, xyz, M, g_out);
+  return fgs::check_launch("grid_sample_bwd", (cudaStream_t)stream);
+}
+
+}  // extern "C"

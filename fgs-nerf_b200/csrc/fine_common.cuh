@@ -1,0 +1,118 @@
+// Device helpers shared by the fused fine-stage kernels: ray/point reconstruction and the
+// reference's grid-query arithmetic (model/nerf.py:597-672, 1202-1209, model/grid.py:49-59),
+// spelled with explicit roundings so discrete decisions downstream stay bit-identical.
+#pragma once
+#include "../../include/fgs_b200_fine.h"
+#include "ray_math.cuh"
+
+namespace fine {
+
+struct Ray {
+  float sx, sy, sz;  // start = o + d * t_min      (render_utils_kernel.cu:72-74)
+  float ux, uy, uz;  // dir   = d / ||d||          (render_utils_kernel.cu:75-77)
+};
+
+__device__ __forceinline__ Ray make_ray(const float* __restrict__ o, const float* __restrict__ d,
+                                        float t_min) {
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const float rn = ray_norm(dx, dy, dz);
+  Ray r;
+  r.sx = __fmaf_rn(dx, t_min, o[0]);
+  r.sy = __fmaf_rn(dy, t_min, o[1]);
+  r.sz = __fmaf_rn(dz, t_min, o[2]);
+  r.ux = __fdiv_rn(dx, rn);
+  r.uy = __fdiv_rn(dy, rn);
+  r.uz = __fdiv_rn(dz, rn);
+  return r;
+}
+
+// render_utils_kernel.cu:184-187
+__device__ __forceinline__ void ray_point(const Ray& r, float stepdist, int step, float& px,
+                                          float& py, float& pz) {
+  const float dist = __fmul_rn(stepdist, (float)step);
+  px = __fmaf_rn(dist, r.ux, r.sx);
+  py = __fmaf_rn(dist, r.uy, r.sy);
+  pz = __fmaf_rn(dist, r.uz, r.sz);
+}
+
+// Grid geometry in grid_sample's (W,H,D) = (Z,Y,X) order.
+struct GridGeo {
+  float mn[3], ext[3];  // xyz_min and (xyz_max - xyz_min), world x,y,z order
+  int X, Y, Z;
+};
+
+__device__ __forceinline__ GridGeo make_geo(const float* mn, const float* mx, int X, int Y, int Z) {
+  GridGeo g;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g.mn[c] = mn[c];
+    g.ext[c] = __fsub_rn(mx[c], mn[c]);
+  }
+  g.X = X; g.Y = Y; g.Z = Z;
+  return g;
+}
+
+// continuous index of world point p in (W,H,D) order: ind[0] <- z, ind[1] <- y, ind[2] <- x
+// = ((ind_norm + 1) / 2) * (size - 1) with ind_norm = ((p - min)/(max - min)).flip(-1)*2 - 1
+// (model/nerf.py:604-607; identical to what F.grid_sample computes internally for the direct
+// sample of nerf.py:654-657 / grid.py:55-56 / nerf.py:1206-1207).
+__device__ __forceinline__ void cont_index(const GridGeo& g, float px, float py, float pz,
+                                           float& iw, float& ih, float& id) {
+  iw = aten_unnormalize(ref_normalize(pz, g.mn[2], g.ext[2]), g.Z);
+  ih = aten_unnormalize(ref_normalize(py, g.mn[1], g.ext[1]), g.Y);
+  id = aten_unnormalize(ref_normalize(px, g.mn[0], g.ext[0]), g.X);
+}
+
+// One displaced tap of sample_sdfs (model/nerf.py:611-619): u = clamp(ind + off, 0, S-1) per
+// component, renormalised (u/(S-1))*2-1 and un-normalised again inside grid_sample.
+__device__ __forceinline__ float tap_clamp(float ind, float off, int S) {
+  return fminf(fmaxf(__fadd_rn(ind, off), 0.f), (float)(S - 1));
+}
+__device__ __forceinline__ float tap_resample_index(float u, int S) {
+  const float cn = __fsub_rn(__fmul_rn(__fdiv_rn(u, (float)(S - 1)), 2.f), 1.f);
+  return aten_unnormalize(cn, S);
+}
+
+// Tap geometry for axis a (0 = W/z, 1 = H/y, 2 = D/x), displacement +-disp.
+struct TapPair {
+  Tri lo, hi;
+  float diff;  // u_hi - u_lo along the axis (model/nerf.py:621-622)
+};
+
+__device__ __forceinline__ TapPair make_taps(const GridGeo& g, float iw, float ih, float id, int axis,
+                                             float disp) {
+  // components that are not displaced still go through ind + 0 -> clamp -> renormalise
+  const float uw = tap_clamp(iw, 0.f, g.Z), uh = tap_clamp(ih, 0.f, g.Y), ud = tap_clamp(id, 0.f, g.X);
+  const float rw = tap_resample_index(uw, g.Z), rh = tap_resample_index(uh, g.Y),
+              rd = tap_resample_index(ud, g.X);
+  TapPair t;
+  float ulo, uhi;
+  if (axis == 0) {
+    ulo = tap_clamp(iw, -disp, g.Z); uhi = tap_clamp(iw, disp, g.Z);
+    t.lo = tri_setup(tap_resample_index(ulo, g.Z), rh, rd);
+    t.hi = tri_setup(tap_resample_index(uhi, g.Z), rh, rd);
+  } else if (axis == 1) {
+    ulo = tap_clamp(ih, -disp, g.Y); uhi = tap_clamp(ih, disp, g.Y);
+    t.lo = tri_setup(rw, tap_resample_index(ulo, g.Y), rd);
+    t.hi = tri_setup(rw, tap_resample_index(uhi, g.Y), rd);
+  } else {
+    ulo = tap_clamp(id, -disp, g.X); uhi = tap_clamp(id, disp, g.X);
+    t.lo = tri_setup(rw, rh, tap_resample_index(ulo, g.X));
+    t.hi = tri_setup(rw, rh, tap_resample_index(uhi, g.X));
+  }
+  t.diff = __fsub_rn(uhi, ulo);
+  return t;
+}
+
+// grad = (f_hi - f_lo) / diff / voxel_size   (model/nerf.py:624-626)
+__device__ __forceinline__ float tap_grad(float flo, float fhi, float diff, float voxel_size) {
+  return __fdiv_rn(__fdiv_rn(__fsub_rn(fhi, flo), diff), voxel_size);
+}
+
+__device__ __forceinline__ int lanemask_lt() {
+  int m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace fine

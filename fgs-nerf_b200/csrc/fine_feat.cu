@@ -1,0 +1,306 @@
+// Level-2 feature kernels of the fused fine stage (sm_100a).
+//
+// feat_kernel: one thread per level-2 sample builds the whole rgbnet input row
+//   [k0 12 | xyz_emb 33 | viewdirs_emb 21 | sdf 1 | all_feat 24 | all_grad 12 | gradient 3]
+// (model/nerf.py:835-876) plus the normal, the reflection direction and its encoding
+// (:835, :879-883) in ONE pass: the reference runs grid_sample (k0), sample_sdfs (24 taps ->
+// 1 grid_sample + ~25 index kernels), 3 encodings, 4 concats and ~15 elementwise kernels.
+// k0 is channels-last so a corner's 12 channels are three 128-bit loads.
+// feat_bwd_kernel: the matching backward: k0 scatter with 128-bit vector reductions
+// (red.global.add.v4.f32), 24-tap SDF scatter, and the gradient/normal/reflection chain back to
+// the level-1 quantities (d_sdf1, d_grad1) that level1_bwd_kernel turns into SDF-grid gradients.
+#include "fine_common.cuh"
+
+namespace {
+
+using namespace fine;
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ float4 fma4(float4 v, float w, float4 acc) {
+  acc.x = __fmaf_rn(v.x, w, acc.x);
+  acc.y = __fmaf_rn(v.y, w, acc.y);
+  acc.z = __fmaf_rn(v.z, w, acc.z);
+  acc.w = __fmaf_rn(v.w, w, acc.w);
+  return acc;
+}
+
+struct Sample {
+  int idx1, ray, step;
+  float px, py, pz;
+};
+
+__device__ __forceinline__ Sample load_sample(const FgsFineParams& P, int s) {
+  Sample q;
+  q.idx1 = P.idx1_of2[s];
+  q.ray = P.ray_id2[s];
+  q.step = P.step_id1[q.idx1];
+  const Ray r = make_ray(P.rays_o + 3 * (size_t)q.ray, P.rays_d + 3 * (size_t)q.ray, P.t_min[q.ray]);
+  ray_point(r, P.stepdist, q.step, q.px, q.py, q.pz);
+  return q;
+}
+
+// normal = l2_normalize(g / (||g|| + 1e-7))   (model/nerf.py:835, :480-483)
+struct NormalCtx {
+  float gn, den, ux, uy, uz, ss, L, nx, ny, nz;
+};
+__device__ __forceinline__ NormalCtx make_normal(float gx, float gy, float gz) {
+  NormalCtx c;
+  c.gn = __fsqrt_rn(sum3_inner(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+  c.den = __fadd_rn(c.gn, 1e-7f);
+  c.ux = __fdiv_rn(gx, c.den); c.uy = __fdiv_rn(gy, c.den); c.uz = __fdiv_rn(gz, c.den);
+  c.ss = sum3_inner(__fmul_rn(c.ux, c.ux), __fmul_rn(c.uy, c.uy), __fmul_rn(c.uz, c.uz));
+  c.L = __fsqrt_rn(fmaxf(c.ss, 1.1920928955078125e-07f));
+  c.nx = __fdiv_rn(c.ux, c.L); c.ny = __fdiv_rn(c.uy, c.L); c.nz = __fdiv_rn(c.uz, c.L);
+  return c;
+}
+
+// displace_list = sorted(set(grad_feat + (1.0,))) = 0.5, 1.0, 1.5, 2.0 (model/nerf.py:843-850)
+__device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); }
+
+__global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P) {
+  const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
+  const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
+  for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
+    const Sample q = load_sample(P, s);
+    float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
+    float iw, ih, id;
+    cont_index(g, q.px, q.py, q.pz, iw, ih, id);
+    // ---- k0: DenseGrid.forward (model/grid.py:49-59), channels-last storage ----
+    {
+      const Tri t = tri_setup(iw, ih, id);
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
+        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
+          const float* v = P.k0 + (((size_t)z * g.Y + y) * g.Z + x) * FGS_K0_DIM;
+          a0 = fma4(__ldg(reinterpret_cast<const float4*>(v)), t.w[c], a0);
+          a1 = fma4(__ldg(reinterpret_cast<const float4*>(v) + 1), t.w[c], a1);
+          a2 = fma4(__ldg(reinterpret_cast<const float4*>(v) + 2), t.w[c], a2);
+        }
+      }
+      st4(row + FGS_X0_K0, a0);
+      st4(row + FGS_X0_K0 + 4, a1);
+      st4(row + FGS_X0_K0 + 8, a2);
+    }
+    // ---- positional encodings (model/nerf.py:836-839, 870-873) ----
+    {
+      const float rx[3] = {__fdiv_rn(__fsub_rn(q.px, g.mn[0]), g.ext[0]),
+                           __fdiv_rn(__fsub_rn(q.py, g.mn[1]), g.ext[1]),
+                           __fdiv_rn(__fsub_rn(q.pz, g.mn[2]), g.ext[2])};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        row[FGS_X0_XYZ + c] = rx[c];
+        float f = 1.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const float e = __fmul_rn(rx[c], f);
+          row[FGS_X0_XYZ + 3 + c * 5 + k] = sinf(e);
+          row[FGS_X0_XYZ + 18 + c * 5 + k] = cosf(e);
+          f *= 2.f;
+        }
+      }
+    }
+    const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
+                        P.viewdirs[3 * (size_t)q.ray + 2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      row[FGS_X0_VIEW + c] = v[c];
+      float f = 1.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float e = __fmul_rn(v[c], f);
+        row[FGS_X0_VIEW + 3 + c * 3 + k] = sinf(e);
+        row[FGS_X0_VIEW + 12 + c * 3 + k] = cosf(e);
+        f *= 2.f;
+      }
+    }
+    row[FGS_X0_SDF] = P.sdf1[q.idx1];
+    // ---- hierarchical SDF taps (sample_sdfs, model/nerf.py:597-637, use_grad_norm=True) ----
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float gr[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const TapPair tp = make_taps(g, iw, ih, id, a, disp_of(d));
+        const float flo = tri_sample1(P.sdf, tp.lo, g.X, g.Y, g.Z);
+        const float fhi = tri_sample1(P.sdf, tp.hi, g.X, g.Y, g.Z);
+        row[FGS_X0_FEAT + (2 * a) * 4 + d] = flo;
+        row[FGS_X0_FEAT + (2 * a + 1) * 4 + d] = fhi;
+        gr[a] = tap_grad(flo, fhi, tp.diff, P.voxel_size);
+      }
+      const float nrm = __fsqrt_rn(sum3_outer(__fmul_rn(gr[0], gr[0]), __fmul_rn(gr[1], gr[1]),
+                                              __fmul_rn(gr[2], gr[2])));
+      const float den = __fadd_rn(nrm, 1e-5f);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) row[FGS_X0_AGRAD + a * 4 + d] = __fdiv_rn(gr[a], den);
+    }
+    const float gx = P.grad1[q.idx1], gy = P.grad1[(size_t)P.cap_m1 + q.idx1],
+                gz = P.grad1[2 * (size_t)P.cap_m1 + q.idx1];
+    row[FGS_X0_GRAD] = gx; row[FGS_X0_GRAD + 1] = gy; row[FGS_X0_GRAD + 2] = gz;
+#pragma unroll
+    for (int c = FGS_X0_DIM; c < FGS_X0_LD; ++c) row[c] = 0.f;
+    // ---- normal, reflection direction and its encoding (model/nerf.py:835, 879-882) ----
+    const NormalCtx nc = make_normal(gx, gy, gz);
+    const float dot = sum3_inner(__fmul_rn(v[0], nc.nx), __fmul_rn(v[1], nc.ny), __fmul_rn(v[2], nc.nz));
+    const float n3[3] = {nc.nx, nc.ny, nc.nz};
+    float* __restrict__ xr = P.XR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float r = __fsub_rn(v[c], __fmul_rn(__fmul_rn(2.f, dot), n3[c]));
+      xr[c] = r;
+      float f = 1.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float e = __fmul_rn(r, f);
+        xr[3 + c * 8 + k] = sinf(e);
+        xr[27 + c * 8 + k] = cosf(e);
+        f *= 2.f;
+      }
+    }
+#pragma unroll
+    for (int c = FGS_XR_DIM - FGS_MLP_WIDTH; c < FGS_XR_LD - FGS_MLP_WIDTH; ++c) xr[c] = 0.f;
+    st4(P.normal2 + 4 * (size_t)s, make_float4(nc.nx, nc.ny, nc.nz, dot));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientation) {
+  const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
+  const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
+  for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
+    const Sample q = load_sample(P, s);
+    const float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
+    const float* __restrict__ drow = P.dX0 + (size_t)s * FGS_X0_LD;
+    float iw, ih, id;
+    cont_index(g, q.px, q.py, q.pz, iw, ih, id);
+    // ---- k0 scatter (grid_sample backward wrt input), 3 vector reductions per corner ----
+    {
+      const Tri t = tri_setup(iw, ih, id);
+      const float4 d0 = ld4(drow + FGS_X0_K0), d1 = ld4(drow + FGS_X0_K0 + 4), d2 = ld4(drow + FGS_X0_K0 + 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
+        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
+          float* v = P.g_k0 + (((size_t)z * g.Y + y) * g.Z + x) * FGS_K0_DIM;
+          const float w = t.w[c];
+          red_add_v4(v, w * d0.x, w * d0.y, w * d0.z, w * d0.w);
+          red_add_v4(v + 4, w * d1.x, w * d1.y, w * d1.z, w * d1.w);
+          red_add_v4(v + 8, w * d2.x, w * d2.y, w * d2.z, w * d2.w);
+        }
+      }
+    }
+    // ---- 24 hierarchical taps: direct (all_feat) + through the normalised gradients ----
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      TapPair tp[3];
+      float gr[3], dG[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        tp[a] = make_taps(g, iw, ih, id, a, disp_of(d));
+        gr[a] = tap_grad(row[FGS_X0_FEAT + (2 * a) * 4 + d], row[FGS_X0_FEAT + (2 * a + 1) * 4 + d],
+                         tp[a].diff, P.voxel_size);
+        dG[a] = drow[FGS_X0_AGRAD + a * 4 + d];
+      }
+      const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+      const float inv = 1.f / (nrm + 1e-5f);
+      const float dotg = dG[0] * gr[0] + dG[1] * gr[1] + dG[2] * gr[2];
+      const float k = (nrm > 0.f) ? dotg * inv * inv / nrm : 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float dgr = dG[a] * inv - k * gr[a];
+        const float df = dgr / tp[a].diff / P.voxel_size;
+        const float dlo = drow[FGS_X0_FEAT + (2 * a) * 4 + d] - df;
+        const float dhi = drow[FGS_X0_FEAT + (2 * a + 1) * 4 + d] + df;
+        tri_scatter1(P.g_sdf, tp[a].lo, g.X, g.Y, g.Z, dlo);
+        tri_scatter1(P.g_sdf, tp[a].hi, g.X, g.Y, g.Z, dhi);
+      }
+    }
+    // ---- reflection encoding -> reflect dir -> normal -> gradient ----
+    const float gx = P.grad1[q.idx1], gy = P.grad1[(size_t)P.cap_m1 + q.idx1],
+                gz = P.grad1[2 * (size_t)P.cap_m1 + q.idx1];
+    const NormalCtx nc = make_normal(gx, gy, gz);
+    const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
+                        P.viewdirs[3 * (size_t)q.ray + 2]};
+    const float n3[3] = {nc.nx, nc.ny, nc.nz};
+    const float* __restrict__ xr = P.XR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
+    const float* __restrict__ dxr = P.dXR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
+    float dr[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = dxr[c];
+      float f = 1.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc += f * (xr[27 + c * 8 + k] * dxr[3 + c * 8 + k] - xr[3 + c * 8 + k] * dxr[27 + c * 8 + k]);
+        f *= 2.f;
+      }
+      dr[c] = acc;
+    }
+    const float vn = v[0] * n3[0] + v[1] * n3[1] + v[2] * n3[2];
+    const float drn = dr[0] * n3[0] + dr[1] * n3[1] + dr[2] * n3[2];
+    float dn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dn[c] = -2.f * (drn * v[c] + vn * dr[c]);
+    // orientation loss (model/nerf.py:469-478): sum_s w.detach * min(0, n.(-v))^2
+    if (weight_orientation > 0.f && -vn < 0.f) {
+      const float w = P.w1[q.idx1];
+      const float k = weight_orientation * w * 2.f * (-vn);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dn[c] += k * (-v[c]);
+    }
+    // normal = u / L, L = sqrt(max(|u|^2, eps))
+    float du[3];
+    {
+      const float u3[3] = {nc.ux, nc.uy, nc.uz};
+      const float invL = 1.f / nc.L;
+      if (nc.ss > 1.1920928955078125e-07f) {
+        const float dnu = dn[0] * u3[0] + dn[1] * u3[1] + dn[2] * u3[2];
+        const float k = dnu * invL * invL * invL;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) du[c] = dn[c] * invL - k * u3[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) du[c] = dn[c] * invL;
+      }
+    }
+    // u = g / (|g| + 1e-7)
+    float dg[3];
+    {
+      const float g3[3] = {gx, gy, gz};
+      const float inv = 1.f / nc.den;
+      const float dug = du[0] * g3[0] + du[1] * g3[1] + du[2] * g3[2];
+      const float k = (nc.gn > 0.f) ? dug * inv * inv / nc.gn : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dg[c] = du[c] * inv - k * g3[c];
+    }
+    P.d_sdf1[q.idx1] = drow[FGS_X0_SDF];
+    P.d_grad1[q.idx1] = dg[0] + drow[FGS_X0_GRAD];
+    P.d_grad1[(size_t)P.cap_m1 + q.idx1] = dg[1] + drow[FGS_X0_GRAD + 1];
+    P.d_grad1[2 * (size_t)P.cap_m1 + q.idx1] = dg[2] + drow[FGS_X0_GRAD + 2];
+  }
+}
+
+}  // namespace
+
+namespace fine {
+
+int launch_feat(const FgsFineParams& P, cudaStream_t st) {
+  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 16);
+  feat_kernel<<<grid, kBlock, 0, st>>>(P);
+  return fgs::check_launch("fine feat", st);
+}
+
+int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st) {
+  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 16);
+  feat_bwd_kernel<<<grid, kBlock, 0, st>>>(P, weight_orientation);
+  return fgs::check_launch("fine feat_bwd", st);
+}
+
+}  // namespace fine

@@ -1,0 +1,275 @@
+// Fused ray marching for the fine stage (sm_100a): sampling + MaskCache + SDF / gradient /
+// NeuS alpha + segmented transmittance scan, with every data-dependent count kept on the device.
+//
+// Replaces, per training step, the reference's chain (model/nerf.py:776-833)
+//   sample_pts_on_rays (6 launches, 2 scans, sync)  ->  3 masked selects  ->  MaskCache
+//   grid_sample -> 3 masked selects -> grid_sample x7 + ~15 elementwise kernels (alpha) ->
+//   7 masked selects -> alpha2weight (2 launches + sync) -> 8 masked selects
+// by four launches and no host synchronisation:
+//   march_kernel   warp per ray: t_min/t_max/N_steps, per-step bbox + MaskCache test, survivors
+//                  recorded as a bitmap (1 bit per step) + count
+//   scan_kernel    exclusive scan of the per-ray counts (single CTA; N <= 2^20 rays)
+//   level1_kernel  warp per ray: survivors get sdf, 6-tap gradient, alpha; the transmittance
+//                  recurrence runs over the warp with shuffles (early stop T<1e-3, alpha and
+//                  weight thresholds) and leaves flags + the per-ray level-2 count
+//   compact2_kernel warp per ray: level-2 index list
+// Arithmetic follows the reference op by op (see fine_common.cuh / ray_math.cuh) so the
+// surviving sample sets are bit-identical.
+#include "fine_common.cuh"
+
+namespace {
+
+using namespace fine;
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+__global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ FgsFineParams P) {
+  const int lane = lane_id();
+  const GridGeo mg = make_geo(P.mask_xyz_min, P.mask_xyz_max, P.mX, P.mY, P.mZ);
+  const float thres = P.mask_thres;
+  long long tot_steps = 0;
+  int tot_m0 = 0;
+  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
+    const float* o = P.rays_o + 3 * (size_t)ray;
+    const float* d = P.rays_d + 3 * (size_t)ray;
+    const RayIsect is = ray_aabb(o[0], o[1], o[2], d[0], d[1], d[2], P.xyz_min[0], P.xyz_min[1],
+                                 P.xyz_min[2], P.xyz_max[0], P.xyz_max[1], P.xyz_max[2], P.near_, P.far_);
+    const long long n64 = ray_nsamples(is.t_min, is.t_max, ray_norm(d[0], d[1], d[2]), P.stepdist);
+    const int cap = P.cap_words * 32;
+    const int n = (int)(n64 < (long long)cap ? n64 : (long long)cap);
+    if (lane == 0) {
+      P.t_min[ray] = is.t_min;
+      P.t_max[ray] = is.t_max;
+      P.n_steps[ray] = (int)(n64 < 0x7fffffffLL ? n64 : 0x7fffffffLL);
+      if (n64 > cap) atomicOr(P.counters + FGS_CNT_OVERFLOW, 1);
+      tot_steps += n64;
+    }
+    const Ray r = make_ray(o, d, is.t_min);
+    int c1 = 0;
+    const int words = (n + 31) >> 5;
+    for (int w = 0; w < words; ++w) {
+      const int step = w * 32 + lane;
+      bool in = step < n;
+      float px, py, pz;
+      ray_point(r, P.stepdist, step, px, py, pz);
+      // render_utils_kernel.cu:191-192
+      in = in && !((P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) |
+                   (P.xyz_max[0] < px) | (P.xyz_max[1] < py) | (P.xyz_max[2] < pz));
+      bool keep = false;
+      if (in) {
+        // MaskCache.forward, model/nerf.py:1202-1209
+        float iw, ih, id;
+        cont_index(mg, px, py, pz, iw, ih, id);
+        const Tri t = tri_setup(iw, ih, id);
+        keep = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, in);
+      const unsigned word = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) {
+        P.bits[(size_t)ray * P.cap_words + w] = word;
+        tot_m0 += __popc(m0);
+      }
+      c1 += __popc(word);
+    }
+    if (lane == 0) P.cnt1[ray] = c1;
+  }
+  if (lane == 0) {
+    if (tot_m0) atomicAdd(P.counters + FGS_CNT_M0, tot_m0);
+    if (tot_steps) {
+      atomicAdd((unsigned long long*)(P.counters + FGS_CNT_TOTAL_LO), (unsigned long long)tot_steps);
+    }
+  }
+}
+
+// Exclusive scan of cnt[0..n) -> off[0..n]; total -> counters[slot]; overflow bit if > cap.
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt, int* __restrict__ off,
+                                                    int n, int* __restrict__ counters, int slot,
+                                                    int cap, int overflow_bit) {
+  __shared__ int s_warp[32];
+  const int per = (n + 1023) / 1024;
+  const int beg = threadIdx.x * per;
+  const int end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += cnt[i];
+  const int incl = warp_incl_scan(sum);
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const int v = s_warp[lane_id()];
+    const int sc = warp_incl_scan(v);
+    s_warp[lane_id()] = sc - v;
+    if (lane_id() == 31) {
+      off[n] = sc;
+      counters[slot] = sc;
+      if (sc > cap) atomicOr(counters + FGS_CNT_OVERFLOW, overflow_bit);
+    }
+  }
+  __syncthreads();
+  int run = incl - sum + s_warp[w];
+  for (int i = beg; i < end; ++i) {
+    off[i] = run;
+    run += cnt[i];
+  }
+}
+
+// trilinear SDF value + 6-tap finite-difference gradient (nerf.grid_sampler, model/nerf.py:
+// 639-672 with sample_sdfs(displace=[1.0]) :597-637); gradient returned in x,y,z order (:664).
+__device__ __forceinline__ void sdf_and_grad(const FgsFineParams& P, const GridGeo& g, float px, float py,
+                                             float pz, float& sdf, float& gx, float& gy, float& gz) {
+  float iw, ih, id;
+  cont_index(g, px, py, pz, iw, ih, id);
+  const Tri t0 = tri_setup(iw, ih, id);
+  sdf = tri_sample1(P.sdf, t0, g.X, g.Y, g.Z);
+  float gr[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const TapPair tp = make_taps(g, iw, ih, id, a, 1.0f);
+    const float flo = tri_sample1(P.sdf, tp.lo, g.X, g.Y, g.Z);
+    const float fhi = tri_sample1(P.sdf, tp.hi, g.X, g.Y, g.Z);
+    gr[a] = tap_grad(flo, fhi, tp.diff, P.voxel_size);
+  }
+  gx = gr[2]; gy = gr[1]; gz = gr[0];
+}
+
+// nerf.neus_alpha_from_sdf_scatter, model/nerf.py:510-544 (cos_anneal_ratio = 1)
+__device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float gz, float vx, float vy,
+                                            float vz, float dist, float inv_s) {
+  const float tc = sum3_inner(__fmul_rn(vx, gx), __fmul_rn(vy, gy), __fmul_rn(vz, gz));
+  // -(relu(-tc*0.5+0.5)*0 + relu(-tc)*1)
+  const float r1 = __fmul_rn(fmaxf(__fadd_rn(__fmul_rn(-tc, 0.5f), 0.5f), 0.f), 0.f);
+  const float r2 = __fmul_rn(fmaxf(-tc, 0.f), 1.f);
+  const float ic = -__fadd_rn(r1, r2);
+  const float h = __fmul_rn(__fmul_rn(ic, dist), 0.5f);
+  const float nx = __fadd_rn(sdf, h), pv = __fsub_rn(sdf, h);
+  const float pc = torch_sigmoid(__fmul_rn(pv, inv_s));
+  const float nc = torch_sigmoid(__fmul_rn(nx, inv_s));
+  const float p = __fsub_rn(pc, nc);
+  const float a = __fdiv_rn(__fadd_rn(p, 1e-5f), __fadd_rn(pc, 1e-5f));
+  return fminf(fmaxf(a, 0.f), 1.f);
+}
+
+__global__ void __launch_bounds__(kBlock) level1_kernel(const __grid_constant__ FgsFineParams P) {
+  const int lane = lane_id();
+  const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
+  const float thres = P.fast_color_thres;
+  int tot_a = 0;
+  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
+    const int base = P.off1[ray];
+    const int c1 = P.cnt1[ray];
+    if (c1 == 0 || base + c1 > P.cap_m1) {  // empty ray, or over capacity (flagged by the scan)
+      if (lane == 0) { P.cnt2[ray] = 0; P.alphainv_last[ray] = 1.f; }
+      continue;
+    }
+    const float* o = P.rays_o + 3 * (size_t)ray;
+    const float* d = P.rays_d + 3 * (size_t)ray;
+    const float vx = P.viewdirs[3 * (size_t)ray], vy = P.viewdirs[3 * (size_t)ray + 1],
+                vz = P.viewdirs[3 * (size_t)ray + 2];
+    const Ray r = make_ray(o, d, P.t_min[ray]);
+    int n = P.n_steps[ray];
+    n = min(n, P.cap_words * 32);
+    const int words = (n + 31) >> 5;
+    float Tc = 1.f;
+    bool stopped = false;
+    int run = 0, c2 = 0;
+    for (int w = 0; w < words; ++w) {
+      const unsigned word = P.bits[(size_t)ray * P.cap_words + w];
+      if (word == 0) continue;
+      const bool mine = (word >> lane) & 1u;
+      const int idx = base + run + __popc(word & lanemask_lt());
+      float alpha = 0.f;
+      if (mine) {
+        const int step = w * 32 + lane;
+        float px, py, pz, sdf, gx, gy, gz;
+        ray_point(r, P.stepdist, step, px, py, pz);
+        sdf_and_grad(P, g, px, py, pz, sdf, gx, gy, gz);
+        alpha = neus_alpha(sdf, gx, gy, gz, vx, vy, vz, P.dist, P.inv_s);
+        P.ray_id1[idx] = ray;
+        P.step_id1[idx] = step;
+        P.sdf1[idx] = sdf;
+        P.grad1[idx] = gx;
+        P.grad1[(size_t)P.cap_m1 + idx] = gy;
+        P.grad1[2 * (size_t)P.cap_m1 + idx] = gz;
+        P.alpha1[idx] = alpha;
+      }
+      const bool kept = mine && (alpha > thres);  // model/nerf.py:803
+      const float a_eff = kept ? alpha : 0.f;
+      unsigned m = __ballot_sync(0xffffffffu, kept);
+      tot_a += __popc(m);
+      float myT = 1.f, myW = 0.f;
+      bool visited = false;
+      // render_utils_kernel.cu:577-605 over the level-a samples of this chunk, in order
+      while (m && !stopped) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float aj = __shfl_sync(0xffffffffu, a_eff, j);
+        if (lane == j) {
+          myT = Tc;
+          myW = __fmul_rn(Tc, aj);
+          visited = true;
+        }
+        Tc = (float)__dmul_rn(__dsub_rn(1., (double)aj), (double)Tc);
+        if ((double)Tc < 1e-3) stopped = true;
+      }
+      const bool l2 = visited && (myW > thres);  // model/nerf.py:825
+      if (mine) {
+        P.w1[idx] = myW;
+        P.T1[idx] = myT;
+        P.flag1[idx] = (kept ? FGS_F_ALPHA : 0) | (visited ? FGS_F_VISIT : 0) | (l2 ? FGS_F_L2 : 0);
+      }
+      c2 += __popc(__ballot_sync(0xffffffffu, l2));
+      run += __popc(word);
+    }
+    if (lane == 0) {
+      P.cnt2[ray] = c2;
+      P.alphainv_last[ray] = Tc;
+    }
+  }
+  if (lane == 0 && tot_a) atomicAdd(P.counters + FGS_CNT_MA, tot_a);
+}
+
+__global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant__ FgsFineParams P) {
+  const int lane = lane_id();
+  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
+    const int c2 = P.cnt2[ray];
+    if (c2 == 0) continue;
+    const int base1 = P.off1[ray], c1 = P.cnt1[ray];
+    int dst = P.off2[ray];
+    if (dst + c2 > P.cap_m2) continue;  // flagged by the scan
+    for (int b = 0; b < c1; b += 32) {
+      const int i = b + lane;
+      const bool l2 = (i < c1) && (P.flag1[base1 + i] & FGS_F_L2);
+      const unsigned m = __ballot_sync(0xffffffffu, l2);
+      if (l2) {
+        const int s = dst + __popc(m & lanemask_lt());
+        P.idx1_of2[s] = base1 + i;
+        P.ray_id2[s] = ray;
+      }
+      dst += __popc(m);
+    }
+  }
+}
+
+}  // namespace
+
+namespace fine {
+
+int launch_march(const FgsFineParams& P, cudaStream_t st) {
+  int rc = fgs::check_cuda(cudaMemsetAsync(P.counters, 0, sizeof(int32_t) * FGS_NUM_COUNTERS, st),
+                           "fine counters memset");
+  if (rc) return rc;
+  fgs::prof_mark("memset", st);
+  const int grid = fgs::stream_grid(P.n_rays, kWarps, 8);
+  march_kernel<<<grid, kBlock, 0, st>>>(P);
+  if ((rc = fgs::check_launch("fine march", st))) return rc;
+  scan_kernel<<<1, 1024, 0, st>>>(P.cnt1, P.off1, P.n_rays, P.counters, FGS_CNT_M1, P.cap_m1, 2);
+  if ((rc = fgs::check_launch("fine scan1", st))) return rc;
+  level1_kernel<<<grid, kBlock, 0, st>>>(P);
+  if ((rc = fgs::check_launch("fine level1", st))) return rc;
+  scan_kernel<<<1, 1024, 0, st>>>(P.cnt2, P.off2, P.n_rays, P.counters, FGS_CNT_M2, P.cap_m2, 4);
+  if ((rc = fgs::check_launch("fine scan2", st))) return rc;
+  compact2_kernel<<<grid, kBlock, 0, st>>>(P);
+  return fgs::check_launch("fine compact2", st);
+}
+
+}  // namespace fine

@@ -121,7 +121,7 @@ int launch_generic(const float* param, float* grad, const float* mask, float wk,
     tv_kernel<DENSE, MASK, true><<<grid, kBlock, 0, st>>>(param, grad, mask, wk, wj, wi, C, X, Y, Z, n);
   else
     tv_kernel<DENSE, MASK, false><<<grid, kBlock, 0, st>>>(param, grad, mask, wk, wj, wi, C, X, Y, Z, n);
-  return fgs::check_launch("total_variation_add_grad");
+  return fgs::check_launch("total_variation_add_grad", st);
 }
 
 }  // namespace
@@ -152,7 +152,7 @@ extern "C" int fgs_total_variation_add_grad(const float* param, float* grad, con
       tv_kernel_v4<true><<<grid, kBlock, 0, st>>>(param, grad, wz, wy, wz, sz_i, sz_j, sz_k, n4);
     else
       tv_kernel_v4<false><<<grid, kBlock, 0, st>>>(param, grad, wz, wy, wz, sz_i, sz_j, sz_k, n4);
-    return fgs::check_launch("total_variation_add_grad_v4");
+    return fgs::check_launch("total_variation_add_grad_v4", st);
   }
   return dense_mode ? launch_generic<true, false>(param, grad, nullptr, wz, wy, wz, C, sz_i, sz_j, sz_k, channels_last, st)
                     : launch_generic<false, false>(param, grad, nullptr, wz, wy, wz, C, sz_i, sz_j, sz_k, channels_last, st);

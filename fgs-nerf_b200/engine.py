@@ -1,1 +1,465 @@
-"""Fused fine-stage step (placeholder until the fused kernels land in this round)."""
+"""Fused fine-stage step: host side of include/fgs_b200_fine.h.
+
+`FineStepEngine` owns the parameters (sdf / k0 grids, rgbnet / refnet), the Adam state and every
+workspace buffer as torch CUDA tensors, and drives one training iteration of the reference
+(model/nerf_training.py:300-373, fine stage) as a fixed sequence of launches of our sm_100a
+kernels through the C-ABI -- no host synchronisation inside a step, no torch compute ops on the
+path (torch is used for allocation, memsets and, multi-GPU, the NCCL all-reduce).
+
+  forward()      nerf.forward_fine                                  model/nerf.py:776-941
+  train_step()   forward + loss + backward + TV + MaskedAdam        model/nerf_training.py:300-373
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+
+MLP_LAYERS = 8
+WIDTH = 256
+X0_DIM, X0_LD = 106, 112
+XR_DIM, XR_LD = 307, 320
+K0_DIM = 12
+NUM_COUNTERS = 8
+CNT = dict(M1=0, M2=1, OVERFLOW=2, MA=3, TOTAL_LO=4, TOTAL_HI=5, M0=6)
+F_ALPHA, F_VISIT, F_L2 = 1, 2, 4
+
+_fp = C.c_void_p
+
+
+class FgsFineParams(C.Structure):
+    """Mirror of `struct FgsFineParams` (include/fgs_b200_fine.h) -- keep field order in step."""
+    _fields_ = [
+        ("n_rays", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32),
+        ("mX", C.c_int32), ("mY", C.c_int32), ("mZ", C.c_int32),
+        ("cap_words", C.c_int32), ("cap_m1", C.c_int32), ("cap_m2", C.c_int32),
+        ("render_depth", C.c_int32), ("render_normal", C.c_int32),
+        ("xyz_min", C.c_float * 3), ("xyz_max", C.c_float * 3),
+        ("mask_xyz_min", C.c_float * 3), ("mask_xyz_max", C.c_float * 3),
+        ("near_", C.c_float), ("far_", C.c_float), ("stepdist", C.c_float), ("dist", C.c_float),
+        ("voxel_size", C.c_float), ("mask_thres", C.c_float), ("fast_color_thres", C.c_float),
+        ("inv_s", C.c_float), ("bg", C.c_float), ("pad0_", C.c_float),
+        ("rays_o", _fp), ("rays_d", _fp), ("viewdirs", _fp),
+        ("sdf", _fp), ("k0", _fp), ("mask_grid", _fp),
+        ("W", _fp * MLP_LAYERS), ("B", _fp * MLP_LAYERS),
+        ("t_min", _fp), ("t_max", _fp),
+        ("n_steps", _fp), ("cnt1", _fp), ("cnt2", _fp), ("off1", _fp), ("off2", _fp),
+        ("bits", _fp), ("alphainv_last", _fp),
+        ("ray_id1", _fp), ("step_id1", _fp), ("flag1", _fp),
+        ("sdf1", _fp), ("grad1", _fp), ("alpha1", _fp), ("w1", _fp), ("T1", _fp),
+        ("d_sdf1", _fp), ("d_grad1", _fp), ("d_w1", _fp),
+        ("idx1_of2", _fp), ("ray_id2", _fp),
+        ("X0", _fp), ("H", _fp), ("XR", _fp), ("logit", _fp), ("normal2", _fp),
+        ("rgb_marched", _fp), ("sigmoid_rgb", _fp), ("cum_weights", _fp), ("depth", _fp),
+        ("normal_marched", _fp), ("counters", _fp),
+        ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
+        ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
+    ]
+
+
+class FgsFineLoss(C.Structure):
+    _fields_ = [
+        ("target", _fp),
+        ("weight_main", C.c_float), ("weight_entropy_last", C.c_float),
+        ("weight_orientation", C.c_float), ("sigmoid_rgb_loss", C.c_float),
+        ("n_rays_global", C.c_int32), ("has_last_ray", C.c_int32),
+        ("g_alphainv_last", _fp), ("loss_out", _fp),
+    ]
+
+
+_PP = C.POINTER(FgsFineParams)
+_LP = C.POINTER(FgsFineLoss)
+_lib.declare("fgs_fine_forward", C.c_int, [_PP, _fp])
+_lib.declare("fgs_fine_loss", C.c_int, [_PP, _LP, _fp])
+_lib.declare("fgs_fine_backward", C.c_int, [_PP, _LP, _fp])
+_lib.declare("fgs_smooth_grad_tv_add_grad", C.c_int,
+             [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_double, _fp, _fp])
+_f3 = C.POINTER(C.c_float)
+_lib.declare("fgs_grid_sample_fwd", C.c_int,
+             [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
+_lib.declare("fgs_grid_sample_bwd", C.c_int,
+             [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
+_lib.declare("fgs_gemm", C.c_int,
+             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
+              _fp, C.c_int, _fp, _fp])
+
+
+def _c3(t):
+    a = (C.c_float * 3)()
+    for i in range(3):
+        a[i] = float(t[i])
+    return a
+
+
+def grid_sample(grid, xyz, xyz_min, xyz_max):
+    """DenseGrid.forward (model/grid.py:49-59) / MaskCache sampling (model/nerf.py:1202-1207):
+    grid [1,C,X,Y,Z] (contiguous or channels_last_3d), xyz [...,3] -> [...,C]."""
+    assert grid.is_cuda and grid.dtype == torch.float32 and grid.dim() == 5 and grid.size(0) == 1
+    Cn, X, Y, Z = grid.shape[1:]
+    cl = 0
+    if not grid.is_contiguous():
+        if not grid.is_contiguous(memory_format=torch.channels_last_3d):
+            raise RuntimeError("grid must be contiguous or channels_last_3d")
+        cl = 1
+    shape = xyz.shape[:-1]
+    pts = xyz.reshape(-1, 3).contiguous()
+    out = torch.empty((pts.shape[0], Cn), dtype=torch.float32, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(lib.fgs_grid_sample_fwd(ptr(grid), Cn, X, Y, Z, cl, ptr(pts), pts.shape[0],
+                                      _c3(xyz_min), _c3(xyz_max), ptr(out), stream()))
+    return out.reshape(*shape, Cn)
+
+
+def grid_sample_backward(grid_shape, channels_last, xyz, xyz_min, xyz_max, grad_out, grad_grid=None):
+    Cn, X, Y, Z = grid_shape[1:]
+    pts = xyz.reshape(-1, 3).contiguous()
+    go = grad_out.reshape(-1, Cn).contiguous()
+    if grad_grid is None:
+        grad_grid = torch.zeros(grid_shape, dtype=torch.float32, device=xyz.device)
+        if channels_last:
+            grad_grid = grad_grid.contiguous(memory_format=torch.channels_last_3d)
+    with torch.cuda.device(xyz.device):
+        check(lib.fgs_grid_sample_bwd(ptr(grad_grid), Cn, X, Y, Z, int(channels_last), ptr(pts), pts.shape[0],
+                                      _c3(xyz_min), _c3(xyz_max), ptr(go), stream()))
+    return grad_grid
+
+
+def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None):
+    """fgs_gemm on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
+    if mode == 0:
+        m, k = A.shape; n = B.shape[0]
+    elif mode == 1:
+        m, k = A.shape; n = B.shape[1]
+    else:
+        k, m = A.shape; n = B.shape[1]
+    M, N, K = M or m, N or n, K or k
+    check(lib.fgs_gemm(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
+                       ptr(bias), int(relu), ptr(relu_mask), relu_mask.stride(0) if relu_mask is not None else 0,
+                       ptr(rows_dev), stream()))
+    return out
+
+
+class FineStepEngine:
+    """State + workspace of the fine-stage model for batches of `n_rays` rays on one GPU."""
+
+    def __init__(self, scene, n_rays, device="cuda", train_cfg=None, cap_m1_per_ray=128, cap_m2_per_ray=16,
+                 world_size=1, rank=0):
+        from .scene import FINE_TRAIN
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FineStepEngine needs a CUDA device: fgs_b200 has no CPU path")
+        dev = self.device
+        self.cfg = dict(scene.cfg)
+        self.train_cfg = dict(train_cfg if train_cfg is not None else FINE_TRAIN)
+        self.n_rays = int(n_rays)
+        self.world_size, self.rank = int(world_size), int(rank)
+        f32 = torch.float32
+        # ---- parameters ----
+        self.xyz_min = scene.xyz_min.clone().float()
+        self.xyz_max = scene.xyz_max.clone().float()
+        self.mask_xyz_min = scene.mask_xyz_min.clone().float()
+        self.mask_xyz_max = scene.mask_xyz_max.clone().float()
+        self.voxel_size = np.float32(scene.voxel_size)
+        self.sdf = scene.sdf.to(dev, f32).contiguous().clone()                       # [1,1,X,Y,Z]
+        self.k0 = scene.k0.to(dev, f32).contiguous(memory_format=torch.channels_last_3d).clone()  # [1,12,X,Y,Z], C innermost
+        assert self.k0.shape[1] == K0_DIM, "fine stage k0_dim must be 12"
+        self.mask_grid = scene.mask_grid.to(dev, f32).contiguous()
+        self.mask_thres = np.float32(scene.mask_thres)
+        self.fast_color_thres = np.float32(self.cfg["fast_color_thres"])
+        layers = list(scene.rgbnet) + list(scene.refnet)
+        assert len(layers) == MLP_LAYERS
+        self.Wt = [w.to(dev, f32).contiguous().clone() for w, _ in layers]
+        self.Bt = [b.to(dev, f32).contiguous().clone() for _, b in layers]
+        dims = [(WIDTH, X0_DIM)] + [(WIDTH, WIDTH)] * 3 + [(WIDTH, XR_DIM)] + [(WIDTH, WIDTH)] * 2 + [(3, WIDTH)]
+        for w, d in zip(self.Wt, dims):
+            assert tuple(w.shape) == d, (tuple(w.shape), d)
+        X, Y, Z = self.sdf.shape[2:]
+        self.X, self.Y, self.Z = X, Y, Z
+        # ---- gradients + Adam state ----
+        self.g_sdf = torch.zeros_like(self.sdf)
+        self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
+        self.gW = [torch.zeros_like(w) for w in self.Wt]
+        self.gB = [torch.zeros_like(b) for b in self.Bt]
+        self.adam = {}
+        self.adam_step = 0
+        # ---- workspace ----
+        N = self.n_rays
+        diag = float((self.xyz_max - self.xyz_min).norm())
+        stepdist = float(np.float32(self.cfg["stepsize"]) * self.voxel_size)
+        self.cap_words = int(math.ceil((diag / stepdist + 2) / 32)) + 1
+        self.cap_m1 = int(cap_m1_per_ray * N)
+        self.cap_m2 = int((cap_m2_per_ray * N + 127) // 128 * 128)
+        i32 = torch.int32
+        e = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=dev)
+        ws = self.ws = {}
+        for k in ("t_min", "t_max", "alphainv_last", "cum_weights", "depth", "g_alphainv_last"):
+            ws[k] = e(N)
+        for k in ("n_steps", "cnt1", "cnt2"):
+            ws[k] = e(N, dt=i32)
+        ws["off1"], ws["off2"] = e(N + 1, dt=i32), e(N + 1, dt=i32)
+        ws["bits"] = e(N, self.cap_words, dt=i32)
+        for k in ("ray_id1", "step_id1"):
+            ws[k] = e(self.cap_m1, dt=i32)
+        ws["flag1"] = e(self.cap_m1, dt=torch.uint8)
+        for k in ("sdf1", "alpha1", "w1", "T1", "d_sdf1", "d_w1"):
+            ws[k] = e(self.cap_m1)
+        ws["grad1"], ws["d_grad1"] = e(3, self.cap_m1), e(3, self.cap_m1)
+        ws["idx1_of2"], ws["ray_id2"] = e(self.cap_m2, dt=i32), e(self.cap_m2, dt=i32)
+        ws["X0"] = e(self.cap_m2, X0_LD)
+        ws["H"] = e(6, self.cap_m2, WIDTH)
+        ws["XR"] = e(self.cap_m2, XR_LD)
+        ws["logit"], ws["normal2"], ws["dlogit"] = e(self.cap_m2, 4), e(self.cap_m2, 4), e(self.cap_m2, 4)
+        ws["dA"], ws["dB"] = e(self.cap_m2, WIDTH), e(self.cap_m2, WIDTH)
+        ws["dXR"], ws["dX0"] = e(self.cap_m2, XR_LD), e(self.cap_m2, X0_LD)
+        for k in ("rgb_marched", "sigmoid_rgb", "normal_marched"):
+            ws[k] = e(N, 3)
+        ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
+        ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
+        self.tv_scratch = None
+        self.nonempty_mask = None
+        self._keep = None
+        self.P = FgsFineParams()
+        self.L = FgsFineLoss()
+        self._fill_static()
+
+    # -------------------------------------------------------------------------------------
+    def _fill_static(self):
+        P, ws = self.P, self.ws
+        P.n_rays = self.n_rays
+        P.X, P.Y, P.Z = self.X, self.Y, self.Z
+        P.mX, P.mY, P.mZ = self.mask_grid.shape[2:]
+        P.cap_words, P.cap_m1, P.cap_m2 = self.cap_words, self.cap_m1, self.cap_m2
+        for c in range(3):
+            P.xyz_min[c] = float(self.xyz_min[c]); P.xyz_max[c] = float(self.xyz_max[c])
+            P.mask_xyz_min[c] = float(self.mask_xyz_min[c]); P.mask_xyz_max[c] = float(self.mask_xyz_max[c])
+        # model/nerf.py:689-691, 795: stepdist = dist = stepsize * voxel_size (fp32 tensor product)
+        sd = np.float32(self.cfg["stepsize"]) * self.voxel_size
+        P.stepdist = float(sd); P.dist = float(sd)
+        P.voxel_size = float(self.voxel_size)
+        P.mask_thres = float(self.mask_thres)
+        P.fast_color_thres = float(self.fast_color_thres)
+        P.far_ = 1e9                                      # model/nerf.py:686
+        P.sdf, P.k0, P.mask_grid = ptr(self.sdf), ptr(self.k0), ptr(self.mask_grid)
+        for i in range(MLP_LAYERS):
+            P.W[i], P.B[i] = ptr(self.Wt[i]), ptr(self.Bt[i])
+            P.gW[i], P.gB[i] = ptr(self.gW[i]), ptr(self.gB[i])
+        P.g_sdf, P.g_k0 = ptr(self.g_sdf), ptr(self.g_k0)
+        for k in ("t_min", "t_max", "n_steps", "cnt1", "cnt2", "off1", "off2", "bits", "alphainv_last",
+                  "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
+                  "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
+                  "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
+                  "dX0", "dlogit"):
+            setattr(P, k, ptr(ws[k]))
+
+    def s_val(self, global_step):
+        """model/nerf.py:514 (python floats)."""
+        c = self.cfg
+        return 1.0 / (global_step + c["s_ratio"] / c["s_start"] - c["step_start"]) * c["s_ratio"]
+
+    def _bind_inputs(self, rays_o, rays_d, viewdirs, global_step, near, bg, render_depth, render_grad):
+        for t, n in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs")):
+            _lib.check_input(t, n, torch.float32)
+            if tuple(t.shape) != (self.n_rays, 3):
+                raise RuntimeError(f"{n} must be [{self.n_rays},3], got {tuple(t.shape)}")
+        P = self.P
+        P.rays_o, P.rays_d, P.viewdirs = ptr(rays_o), ptr(rays_d), ptr(viewdirs)
+        self._keep = (rays_o, rays_d, viewdirs)
+        P.near_ = float(np.float32(near))
+        P.bg = float(bg)
+        # inv_s = ones(1) / (ones(1) * s_val)   (model/nerf.py:514-523), fp32
+        P.inv_s = float(np.float32(1.0) / np.float32(self.s_val(global_step)))
+        P.render_depth, P.render_normal = int(bool(render_depth)), int(bool(render_grad))
+
+    # -------------------------------------------------------------------------------------
+    def forward(self, rays_o, rays_d, viewdirs, global_step=20000, near=2.0, bg=1.0, render_depth=False,
+                render_grad=False):
+        """nerf.forward_fine: enqueue only.  Results live in self.ws (see outputs())."""
+        self._bind_inputs(rays_o, rays_d, viewdirs, global_step, near, bg, render_depth, render_grad)
+        with torch.cuda.device(self.device):
+            check(lib.fgs_fine_forward(C.byref(self.P), stream()))
+
+    def counters(self):
+        """Host copy of the device counters (synchronises)."""
+        c = self.ws["counters"].cpu().numpy().astype(np.int64)
+        out = {k: int(c[i]) for k, i in CNT.items() if not k.startswith("TOTAL")}
+        out["total_len"] = int((c[CNT["TOTAL_HI"]] << 32) | (c[CNT["TOTAL_LO"]] & 0xffffffff))
+        if out["OVERFLOW"]:
+            raise RuntimeError(f"fgs_b200 fine step: workspace overflow (bits {out['OVERFLOW']:#x}: "
+                               f"1=steps/ray, 2=cap_m1 {self.cap_m1}, 4=cap_m2 {self.cap_m2}); counts {out}")
+        return out
+
+    def outputs(self):
+        """The reference's render_result dict (model/nerf.py:922-939) from the workspace;
+        exact-size tensors, so this synchronises once to read M2."""
+        cnt = self.counters()
+        ws = self.ws
+        M1, M2 = cnt["M1"], cnt["M2"]
+        idx1 = ws["idx1_of2"][:M2].long()
+        ray_id = ws["ray_id2"][:M2].long()
+        rgb = torch.sigmoid(ws["logit"][:M2, :3])
+        flag = ws["flag1"][:M1]
+        keep_a = (flag & F_ALPHA) != 0
+        depth = ws["depth"] if self.P.render_depth else None
+        return {
+            "alphainv_cum": ws["alphainv_last"], "weights": ws["w1"][idx1], "ray_id": ray_id,
+            "step_id": ws["step_id1"][idx1].long(), "viewdirs": self._keep[2][ray_id],
+            "rgb_marched": ws["rgb_marched"], "sigmoid_rgb": ws["sigmoid_rgb"],
+            "normal_marched": ws["normal_marched"] if self.P.render_normal else None,
+            "normal": ws["normal2"][:M2, :3], "raw_alpha": ws["alpha1"][idx1], "raw_rgb": rgb,
+            "depth": depth, "disp": (1 / depth) if depth is not None else None,
+            "mask": ((flag & F_L2) != 0)[keep_a], "gradient": ws["grad1"][:, idx1].T,
+            "s_val": None, "counts": cnt,
+            "level1": dict(ray_id=ws["ray_id1"][:M1].long(), step_id=ws["step_id1"][:M1].long(),
+                           sdf=ws["sdf1"][:M1], gradient=ws["grad1"][:, :M1].T, alpha=ws["alpha1"][:M1],
+                           flag=flag),
+        }
+
+    # -------------------------------------------------------------------------------------
+    def set_nonempty_mask(self):
+        """nerf._set_nonempty_mask (model/nerf.py:339-353): MaskCache at the voxel centres."""
+        X, Y, Z = self.X, self.Y, self.Z
+        g = torch.stack(torch.meshgrid(
+            torch.linspace(float(self.xyz_min[0]), float(self.xyz_max[0]), X),
+            torch.linspace(float(self.xyz_min[1]), float(self.xyz_max[1]), Y),
+            torch.linspace(float(self.xyz_min[2]), float(self.xyz_max[2]), Z), indexing="ij"), -1).to(self.device)
+        v = grid_sample(self.mask_grid, g, self.mask_xyz_min, self.mask_xyz_max)[..., 0]
+        self.nonempty_mask = (v >= float(self.mask_thres)).contiguous()
+        self.n_nonempty = int(self.nonempty_mask.sum().item())
+        return self.nonempty_mask
+
+    def is_tv_step(self, global_step):
+        t = self.train_cfg
+        return t["tv_from"] < global_step < t["tv_end"] and global_step % t["tv_every"] == 0
+
+    def zero_grad(self):
+        with torch.cuda.device(self.device):
+            st = stream()
+            check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
+            check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
+
+    def loss_backward(self, target, n_rays_global=None, has_last_ray=True):
+        """Loss block + backward (model/nerf_training.py:307-347); grads of the MLPs are overwritten,
+        g_sdf / g_k0 accumulated into (call zero_grad() first)."""
+        t = self.train_cfg
+        L = self.L
+        _lib.check_input(target, "target", torch.float32)
+        L.target = ptr(target)
+        self._keep_t = target
+        L.weight_main, L.weight_entropy_last = t["weight_main"], t["weight_entropy_last"]
+        L.weight_orientation, L.sigmoid_rgb_loss = t["weight_orientation"], t["sigmoid_rgb_loss"]
+        L.n_rays_global = int(n_rays_global or self.n_rays)
+        L.has_last_ray = int(bool(has_last_ray))
+        L.g_alphainv_last = ptr(self.ws["g_alphainv_last"])
+        L.loss_out = ptr(self.ws["loss"])
+        self.ws["loss"].zero_()
+        with torch.cuda.device(self.device):
+            st = stream()
+            check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
+            check(lib.fgs_fine_backward(C.byref(self.P), C.byref(L), st))
+
+    def smooth_grad_tv_add_grad(self):
+        """weight_tv_density * smooth_grad_tv term (model/nerf_training.py:330-336, nerf.py:438-446)."""
+        t = self.train_cfg
+        if self.tv_scratch is None:
+            self.tv_scratch = torch.empty(6 * self.X * self.Y * self.Z, dtype=torch.float32, device=self.device)
+        if self.nonempty_mask is not None:
+            n_sel, m = 3.0 * self.n_nonempty, ptr(self.nonempty_mask)
+        else:
+            n_sel, m = 3.0 * self.X * self.Y * self.Z, None
+        w = t["weight_tv_density"] * t["smooth_grad_tv"]
+        with torch.cuda.device(self.device):
+            check(lib.fgs_smooth_grad_tv_add_grad(ptr(self.sdf), ptr(self.g_sdf), m, ptr(self.tv_scratch), self.X,
+                                                  self.Y, self.Z, float(self.voxel_size), float(w), float(n_sel),
+                                                  self.ws["loss"].data_ptr() + 4 * 8, stream()))
+
+    def sdf_tv_add_grad(self, global_step, n_rays_global=None):
+        """model/nerf_training.py:353-360 + nerf.sdf_total_variation_add_grad (nerf.py:465-467)."""
+        t = self.train_cfg
+        w = t["weight_tv_density"] * t["sdf_tv"] / (n_rays_global or self.n_rays)
+        w = float(w * max(self.X, self.Y, self.Z) / 128)
+        dense = global_step < t["tv_dense_before"]
+        with torch.cuda.device(self.device):
+            check(lib.fgs_total_variation_add_grad(ptr(self.sdf), ptr(self.g_sdf), None, w, w, w, 1, self.X, self.Y,
+                                                   self.Z, int(dense), 0, stream()))
+
+    def optimizer_step(self, lr_scale=1.0):
+        """MaskedAdam.step (model/adam.py:190-221) with the fine-stage param groups
+        (model/nerf_training.py:9-37): k0 masked (skip_zero_grad), sdf and the 16 MLP tensors dense."""
+        t = self.train_cfg
+        self.adam_step += 1
+        step = self.adam_step
+        if not self.adam:
+            self.adam = {"sdf": (torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)),
+                         "k0": (torch.zeros_like(self.k0), torch.zeros_like(self.k0)),
+                         "W": [(torch.zeros_like(w), torch.zeros_like(w)) for w in self.Wt],
+                         "B": [(torch.zeros_like(b), torch.zeros_like(b)) for b in self.Bt]}
+            n = 2 * MLP_LAYERS
+            self._mt = dict(
+                p=(_fp * n)(*[ptr(x) for x in self.Wt + self.Bt]),
+                g=(_fp * n)(*[ptr(x) for x in self.gW + self.gB]),
+                m=(_fp * n)(*[ptr(x[0]) for x in self.adam["W"] + self.adam["B"]]),
+                v=(_fp * n)(*[ptr(x[1]) for x in self.adam["W"] + self.adam["B"]]),
+                n=(C.c_int64 * n)(*[x.numel() for x in self.Wt + self.Bt]))
+        b1, b2, eps = 0.9, 0.99, 1e-8
+        with torch.cuda.device(self.device):
+            st = stream()
+            m, v = self.adam["sdf"]
+            check(lib.fgs_adam_upd(ptr(self.sdf), ptr(self.g_sdf), ptr(m), ptr(v), None, self.sdf.numel(), step,
+                                   b1, b2, t["lrate_sdf"] * lr_scale, eps, 0, st))
+            m, v = self.adam["k0"]
+            check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
+                                   b1, b2, t["lrate_k0"] * lr_scale, eps, 1, st))
+            n = 2 * MLP_LAYERS
+            lrs = [t["lrate_rgbnet"]] * 4 + [t["lrate_refnet"]] * 4
+            lrs = (C.c_float * n)(*[x * lr_scale for x in lrs + lrs])
+            steps = (C.c_int * n)(*([step] * n))
+            mt = self._mt
+            check(lib.fgs_adam_upd_multi(n, mt["p"], mt["g"], mt["m"], mt["v"], mt["n"], steps, lrs, b1, b2, eps, st))
+
+    def all_reduce_grads(self):
+        """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink)."""
+        if self.world_size == 1:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(self.g_sdf)
+        dist.all_reduce(self.g_k0)
+        flat = torch.cat([g.reshape(-1) for g in self.gW + self.gB])
+        dist.all_reduce(flat)
+        o = 0
+        for g in self.gW + self.gB:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+
+    def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
+                   has_last_ray=True):
+        """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous."""
+        self.forward(rays_o, rays_d, viewdirs, global_step, near, bg)
+        self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
+        self.loss_backward(target, n_rays_global, has_last_ray)
+        t = self.train_cfg
+        tv = self.is_tv_step(global_step) and t["weight_tv_density"] > 0
+        if tv and t["smooth_grad_tv"] > 0 and (self.world_size == 1 or self.rank == 0):
+            self.smooth_grad_tv_add_grad()                                 # a pure function of the params:
+        self.all_reduce_grads()                                            # added once, not per rank
+        if tv and t["sdf_tv"] > 0:
+            self.sdf_tv_add_grad(global_step, n_rays_global)
+        self.optimizer_step()
+
+
+def smoke():
+    """Tiny fused step on cuda:0 checked against the oracle's forward (called by __graft_entry__)."""
+    from . import scene
+    dev = torch.device("cuda:0")
+    sc = scene.make_scene(G=48, mask_G=40)
+    ro, rd, vd, tgt = [t.to(dev) for t in scene.make_rays(N=192, H=100, W=100, n_views=8)]
+    eng = FineStepEngine(sc, 192, dev)
+    eng.set_nonempty_mask()
+    eng.train_step(ro, rd, vd, tgt, 5000)
+    torch.cuda.synchronize()
+    cnt = eng.counters()
+    assert cnt["M2"] > 0 and bool(torch.isfinite(eng.ws["rgb_marched"]).all())
+    print("smoke: fused fine step ok,", cnt, "loss", eng.ws["loss"].cpu().numpy().round(6).tolist())
+    return eng

@@ -37,6 +37,18 @@ void fgs_reset_launch_count(void);
 int fgs_set_device(int device);
 int fgs_device_sm_count(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Per-launch device timing for bench.py / profiles: between fgs_prof_begin(stream) and
+ * fgs_prof_end() every launch of this library records a CUDA event on its stream.
+ * fgs_prof_end() synchronises and returns the number of timed intervals (or -1);
+ * fgs_prof_get(i, &name, &ms) gives interval i = the launch named `name` (time since the
+ * previous launch finished, so stream-serialised kernels are timed one by one). */
+int fgs_prof_begin(fgs_stream_t stream);
+int fgs_prof_end(void);
+int fgs_prof_get(int i, const char** name, float* ms);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (grad buffers are cleared through the library so the
+ * clears show up in the launch timing above). */
+int fgs_memset_zero(void* ptr, int64_t bytes, fgs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Ray sampling  (reference: model/cuda/render_utils.cpp:50-85, render_utils_kernel.cu:12-242)
  * ------------------------------------------------------------------------------------ */

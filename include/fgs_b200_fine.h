@@ -1,0 +1,177 @@
+/*
+ * fgs_b200_fine.h -- C-ABI of the FUSED fine-stage step (new entry points; the reference has no
+ * single call for this, it is the body of its training iteration):
+ *   forward  = nerf.forward_fine                         (model/nerf.py:776-941)
+ *   loss     = the loss block of the training loop       (model/nerf_training.py:307-345)
+ *   backward = what autograd does for that graph         
+ *   reg/opt  = sdf TV add-grad + smooth-grad TV + MaskedAdam (nerf_training.py:330-373)
+ *
+ * All memory is owned by the caller (the Python host allocates it as torch tensors); the
+ * struct below only carries pointers and sizes.  Every launcher enqueues a fixed sequence of
+ * kernels on `stream` with NO host synchronisation: data-dependent sample counts stay on the
+ * device (`counters`), buffers are sized by capacity, so a whole step is CUDA-graph capturable.
+ *
+ * Sample levels (flat, ray-major, near->far inside a ray -- the reference's packing):
+ *   level 1 = samples inside the bbox that pass the MaskCache test      (nerf.py:780-789)
+ *   level a = level-1 samples with alpha > fast_color_thres            (nerf.py:802-810)
+ *   level 2 = level-a samples visited before the T<1e-3 stop with weight > fast_color_thres
+ *             (nerf.py:823-833) -- the only ones that reach the MLPs.
+ * Levels 1 and a share the level-1 arrays (flag1 tells them apart); level 2 is compacted.
+ *
+ * Layouts:
+ *   sdf   [X][Y][Z] fp32 (the reference's [1,1,X,Y,Z]);
+ *   k0    [X][Y][Z][C] fp32 = torch.channels_last_3d storage of the reference's [1,C,X,Y,Z]
+ *         (one voxel's 12 channels are three 128-bit loads);
+ *   mask  [mX][mY][mZ] fp32 (MaskCache.sdf_mask after its max-pool, model/nerf.py:1199);
+ *   MLP weights: nn.Linear layout W[out][in], bias[out]; layers 0-3 = rgbnet, 4-7 = refnet;
+ *   activations: SAMPLE-MAJOR rows [cap_m2][ld] (K contiguous: the operand layout of the GEMMs).
+ */
+#ifndef FGS_B200_FINE_H
+#define FGS_B200_FINE_H
+
+#include <stdint.h>
+
+#include "fgs_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGS_MLP_LAYERS 8
+#define FGS_MLP_WIDTH 256
+#define FGS_X0_DIM 106   /* rgbnet input (model/nerf.py:108-112, 874)                 */
+#define FGS_X0_LD 112    /* padded row length of X0 (pad columns are written as 0)    */
+#define FGS_XR_DIM 307   /* refnet input = 256 rgb_feat + 51 reflect_emb (nerf.py:883) */
+#define FGS_XR_LD 320
+#define FGS_K0_DIM 12
+
+/* X0 column map (concat order of model/nerf.py:874) */
+#define FGS_X0_K0 0      /* 12: k0                                   */
+#define FGS_X0_XYZ 12    /* 33: xyz, sin(xyz*2^k), cos(xyz*2^k) k<5  */
+#define FGS_X0_VIEW 45   /* 21: viewdirs emb, k<3                    */
+#define FGS_X0_SDF 66    /*  1: sdf                                  */
+#define FGS_X0_FEAT 67   /* 24: all_feat [tap(z-,z+,y-,y+,x-,x+)][d] */
+#define FGS_X0_AGRAD 91  /* 12: all_grad [axis(z,y,x)][d] normalised */
+#define FGS_X0_GRAD 103  /*  3: gradient (x,y,z)                     */
+
+/* counters[] (device int32) */
+#define FGS_CNT_M1 0        /* level-1 samples                                          */
+#define FGS_CNT_M2 1        /* level-2 samples                                          */
+#define FGS_CNT_OVERFLOW 2  /* bit0: steps/ray > bitmap, bit1: M1 > cap_m1, bit2: M2 > cap_m2 */
+#define FGS_CNT_MA 3        /* level-a samples (alpha > thres, visited or not)          */
+#define FGS_CNT_TOTAL_LO 4  /* total_len = sum of N_steps, low / high 32 bits           */
+#define FGS_CNT_TOTAL_HI 5
+#define FGS_CNT_M0 6        /* samples inside the bbox (before the MaskCache)           */
+#define FGS_NUM_COUNTERS 8
+
+/* flag1[] bits */
+#define FGS_F_ALPHA 1   /* alpha > thres (level a)                   */
+#define FGS_F_VISIT 2   /* reached before the early stop             */
+#define FGS_F_L2 4      /* weight > thres (level 2)                  */
+
+typedef struct FgsFineParams {
+  /* ---- sizes ---- */
+  int32_t n_rays;
+  int32_t X, Y, Z;
+  int32_t mX, mY, mZ;
+  int32_t cap_words;            /* 32-bit words of the per-ray step bitmap */
+  int32_t cap_m1, cap_m2;       /* sample capacities; cap_m2 % 128 == 0   */
+  int32_t render_depth, render_normal;
+  /* ---- scalars ---- */
+  float xyz_min[3], xyz_max[3], mask_xyz_min[3], mask_xyz_max[3];
+  float near_, far_, stepdist, dist, voxel_size, mask_thres, fast_color_thres, inv_s, bg;
+  float pad0_;
+  /* ---- inputs ---- */
+  const float *rays_o, *rays_d, *viewdirs;       /* [N,3] */
+  /* ---- parameters ---- */
+  const float *sdf, *k0, *mask_grid;
+  const float *W[FGS_MLP_LAYERS], *B[FGS_MLP_LAYERS];
+  /* ---- per-ray workspace ---- */
+  float *t_min, *t_max;                          /* [N] */
+  int32_t *n_steps, *cnt1, *cnt2, *off1, *off2;  /* [N]; off*: [N+1] */
+  uint32_t *bits;                                /* [N][cap_words] level-1 membership per step */
+  float *alphainv_last;                          /* [N] */
+  /* ---- level-1 samples, SoA, capacity cap_m1 ---- */
+  int32_t *ray_id1, *step_id1;
+  uint8_t *flag1;
+  float *sdf1, *grad1 /*[3][cap_m1] x,y,z*/, *alpha1, *w1, *T1;
+  float *d_sdf1, *d_grad1 /*[3][cap_m1]*/, *d_w1;  /* backward, valid where flag1 & FGS_F_L2 */
+  /* ---- level-2 samples, capacity cap_m2 ---- */
+  int32_t *idx1_of2, *ray_id2;
+  float *X0;       /* [cap_m2][FGS_X0_LD]   rgbnet input                                   */
+  float *H;        /* [6][cap_m2][256] hidden activations (post-ReLU): rgbnet 0-2, refnet 3-5 */
+  float *XR;       /* [cap_m2][FGS_XR_LD]  cols 0..255 rgbnet output, 256..306 reflect emb  */
+  float *logit;    /* [cap_m2][4] refnet output (pre-sigmoid), col 3 unused                 */
+  float *normal2;  /* [cap_m2][4] normal (nerf.py:835), col 3 = n.v                         */
+  /* ---- per-ray outputs ---- */
+  float *rgb_marched, *sigmoid_rgb, *cum_weights, *depth, *normal_marched; /* [N,3],[N,3],[N],[N],[N,3] */
+  int32_t *counters;                             /* [FGS_NUM_COUNTERS] device */
+  /* ---- backward: parameter gradients (accumulated into; caller zeroes g_sdf, g_k0) ---- */
+  float *g_sdf, *g_k0;
+  float *gW[FGS_MLP_LAYERS], *gB[FGS_MLP_LAYERS]; /* overwritten */
+  /* ---- backward scratch, capacity cap_m2 ---- */
+  float *dA, *dB;  /* [cap_m2][256] ping-pong  */
+  float *dXR;      /* [cap_m2][FGS_XR_LD]      */
+  float *dX0;      /* [cap_m2][FGS_X0_LD]      */
+  float *dlogit;   /* [cap_m2][4]              */
+} FgsFineParams;
+
+/* forward_fine: sampling -> MaskCache -> SDF/gradient/alpha -> weights -> features -> rgbnet ->
+ * refnet -> compositing.  Fills the per-ray outputs, counters and every saved intermediate. */
+int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream);
+
+/* Loss block of model/nerf_training.py:307-327 (+ nerf.orientation_loss, nerf.py:469-478)
+ * fused with the start of the backward pass: per ray it forms d loss / d rgb_marched,
+ * d sigmoid_rgb, d alphainv_last, and pushes them through the compositing sums
+ * (nerf.py:888-903) into dlogit [cap_m2][4] and d_w1.  The four scalar loss terms are ADDED
+ * into loss_out[0..3] (mse, entropy_last, orientation, sigmoid_rgb; caller zeroes). */
+typedef struct FgsFineLoss {
+  const float* target;          /* [N,3] */
+  float weight_main, weight_entropy_last, weight_orientation, sigmoid_rgb_loss;
+  int32_t n_rays_global;        /* N of the whole (multi-GPU) batch: mse means divide by 3*this */
+  int32_t has_last_ray;         /* this rank owns the global last ray (entropy quirk)          */
+  float* g_alphainv_last;       /* [N] written                                                 */
+  double* loss_out;             /* [4] device                                                  */
+} FgsFineLoss;
+int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream);
+
+/* Backward of fgs_fine_forward given what fgs_fine_loss left behind; accumulates into g_sdf,
+ * g_k0 (atomics) and overwrites gW/gB. */
+int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream);
+
+/* smooth_grad_tv term of nerf.density_total_variation (model/nerf.py:438-446) differentiated
+ * analytically: g_sdf += d/dsdf [ weight * mean_{nonempty,3ch}( (conv3(G).detach() - G)^2 ) ],
+ * G = central-difference gradient grid of the SDF (nerf.py:491-494).  `scratch` holds
+ * 6*X*Y*Z floats; nonempty may be NULL (all voxels); n_sel = number of selected elements
+ * (3 * masked voxels).  loss_out (may be NULL, double) has the loss value ADDED. */
+int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const uint8_t* nonempty,
+                                float* scratch, int X, int Y, int Z, float voxel_size,
+                                float weight, double n_sel, double* loss_out,
+                                fgs_stream_t stream);
+
+/* DenseGrid.forward / backward (model/grid.py:49-59) and MaskCache.forward (model/nerf.py:
+ * 1202-1209) as stand-alone ops: ATen grid_sample arithmetic, any channel count.
+ * channels_last: 0 = [C][X][Y][Z], 1 = [X][Y][Z][C].  out: [M][C].
+ * xyz_min / xyz_max are HOST pointers to 3 floats (scalars of the grid object). */
+int fgs_grid_sample_fwd(const float* grid, int C, int X, int Y, int Z, int channels_last,
+                        const float* xyz, int64_t M, const float* xyz_min, const float* xyz_max,
+                        float* out, fgs_stream_t stream);
+int fgs_grid_sample_bwd(float* g_grid, int C, int X, int Y, int Z, int channels_last,
+                        const float* xyz, int64_t M, const float* xyz_min, const float* xyz_max,
+                        const float* g_out, fgs_stream_t stream);
+
+/* Row-major fp32 GEMM used by the MLPs, exposed for tests:
+ *   mode 0 (NT): C[M,N] = A[M,K] * B[N,K]^T     mode 1 (NN): C = A[M,K] * B[K,N]
+ *   mode 2 (TN): C[M,N] += A[K,M]^T * B[K,N]  (split over K, atomically accumulated)
+ * bias (may be NULL) is added per output column; relu!=0 applies max(0,.);
+ * relu_mask (may be NULL, [M][ld_mask]) multiplies the result by (relu_mask > 0).
+ * The row count of the sample dimension (M for modes 0/1, K for mode 2) is read on the
+ * device from *rows_dev when rows_dev != NULL (clamped to the host value). */
+int fgs_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
+             const int32_t* rows_dev, fgs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGS_B200_FINE_H */

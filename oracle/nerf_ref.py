@@ -461,9 +461,10 @@ class RefOptimizer:
 
 
 def train_step(m, native, opt, rays_o, rays_d, viewdirs, target, global_step, train_cfg, near, stepsize, bg,
-               stages=None):
+               stages=None, render_depth=False, render_grad=False):
     """One iteration of model/nerf_training.py:300-373 (fine stage)."""
-    out = forward_fine(m, native, rays_o, rays_d, viewdirs, global_step, near, 1e9, stepsize, bg, stages=stages)
+    out = forward_fine(m, native, rays_o, rays_d, viewdirs, global_step, near, 1e9, stepsize, bg, stages=stages,
+                       render_depth=render_depth, render_grad=render_grad)
     for _, p in m.params():
         p.grad = None                                           # zero_grad(set_to_none=True)
     loss = fine_loss(m, out, target, train_cfg, global_step)

@@ -1,0 +1,252 @@
+"""GPU parity of the fused fine-stage step (fgs_nerf_b200.engine, through the C-ABI of
+include/fgs_b200_fine.h) against the oracle: oracle/nerf_ref.py running the reference's own
+arithmetic on the same device -- torch CUDA ops (F.grid_sample, F.linear, sigmoid, index_add_) plus
+the reference's compiled kernels from oracle/_ref (sample_pts_on_rays, alpha2weight[_backward],
+adam, total_variation).
+
+Bars (BASELINE.json north_star): ray_id / step_id / masks BIT-EXACT; rendered RGB, depth, weights
+and gradients within 1e-4 relative (fp32)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fine_case  # noqa: E402
+from oracle import nerf_ref as R  # noqa: E402
+from oracle import ref_ext  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _native():
+    return R.RefCudaNative() if ref_ext.available() else None
+
+
+def _rel(a, b):
+    """max |a-b| / max|b|: the 1e-4-relative bar on a whole tensor."""
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _close(a, b, what, rtol=RTOL, atol_frac=1e-5):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    atol = atol_frac * float(b.abs().max())
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{a.numel()} outside rtol {rtol}; "
+                                 f"max abs err {float((a - b).abs().max()):.3e}, ref max {float(b.abs().max()):.3e}")
+
+
+class Case:
+    def __init__(self, cuda, G, mask_G, N, H, W, n_views, step, tv_every=1):
+        from fgs_nerf_b200 import engine, scene
+        native = _native()
+        if native is None:
+            pytest.skip("oracle/_ref not built")
+        self.sc = scene.make_scene(G=G, mask_G=mask_G)
+        self.rays = [t.to(cuda) for t in scene.make_rays(N=N, H=H, W=W, n_views=n_views)]
+        self.step = step
+        self.train_cfg = dict(scene.FINE_TRAIN, tv_every=tv_every)
+        # ---- oracle ----
+        self.m = R.FineModel(self.sc, device=cuda)
+        self.m.set_nonempty_mask()
+        self.stages = {}
+        ro, rd, vd, tgt = self.rays
+        self.opt = R.RefOptimizer(self.m, self.train_cfg, native)
+        self.p_before = {k: v.detach().clone() for k, v in self.m.params()}
+        self.out, self.loss = R.train_step(self.m, native, self.opt, ro, rd, vd, tgt, step, self.train_cfg,
+                                           near=2.0, stepsize=0.5, bg=1.0, stages=self.stages,
+                                           render_depth=True, render_grad=True)
+        # ---- ours ----
+        self.eng = engine.FineStepEngine(self.sc, N, cuda, train_cfg=self.train_cfg)
+        self.eng.set_nonempty_mask()
+        self.eng.forward(ro, rd, vd, step, near=2.0, bg=1.0, render_depth=True, render_grad=True)
+        self.mine = self.eng.outputs()
+        self.eng.zero_grad()
+        self.eng.loss_backward(tgt)
+        torch.cuda.synchronize()
+
+
+@pytest.fixture(scope="module")
+def small(cuda):
+    return Case(cuda, G=48, mask_G=40, N=192, H=100, W=100, n_views=8, step=5000)
+
+
+@pytest.fixture(scope="module")
+def config1(cuda):
+    """BASELINE.json configs[0]: 96^3 SDF + 12-ch feature grid, 4096 rays."""
+    return Case(cuda, G=96, mask_G=120, N=4096, H=800, W=800, n_views=40, step=5000)
+
+
+@pytest.mark.parametrize("case", ["small", "config1"])
+def test_sample_sets_bit_exact(case, request):
+    c = request.getfixturevalue(case)
+    st, mine = c.stages, c.mine
+    cnt = mine["counts"]
+    assert cnt["total_len"] == st["total_len"]
+    assert cnt["M0"] == st["M0"]
+    assert cnt["M1"] == st["M1"], (cnt, st["M1"])
+    l1 = mine["level1"]
+    assert torch.equal(l1["ray_id"], st["ray_id_1"])
+    assert torch.equal(l1["step_id"], st["step_id_1"])
+    assert cnt["MA"] == st["Ma"]
+    assert cnt["M2"] == st["M2"]
+    assert torch.equal(mine["ray_id"], c.out["ray_id"])
+    assert torch.equal(mine["step_id"], c.out["step_id"])
+    assert torch.equal(mine["mask"], c.out["mask"])
+
+
+@pytest.mark.parametrize("case", ["small", "config1"])
+def test_level1_values(case, request):
+    c = request.getfixturevalue(case)
+    l1, st = c.mine["level1"], c.stages
+    for k, ref in (("sdf", st["sdf_1"]), ("gradient", st["gradient_1"]), ("alpha", st["alpha_1"])):
+        exact = float((l1[k] == ref).float().mean())
+        print(f"{case} level1 {k}: bit-equal fraction {exact:.6f}")
+        _close(l1[k], ref, k, rtol=1e-5)
+        assert exact > 0.99, f"{k}: only {exact:.4f} bit-equal"
+
+
+@pytest.mark.parametrize("case", ["small", "config1"])
+def test_forward_outputs(case, request):
+    c = request.getfixturevalue(case)
+    for k in ("weights", "raw_alpha", "alphainv_cum", "gradient", "normal", "raw_rgb", "rgb_marched",
+              "sigmoid_rgb", "normal_marched", "depth"):
+        _close(c.mine[k], c.out[k], k)
+    _close(c.eng.ws["X0"][:c.mine["counts"]["M2"], :106], c.stages["rgb_feat_in"], "rgb_feat_in")
+    _close(c.eng.ws["XR"][:c.mine["counts"]["M2"], 256:307], c.stages["reflect_emb"], "reflect_emb")
+
+
+@pytest.mark.parametrize("case", ["small", "config1"])
+def test_loss_and_gradients(case, request):
+    c = request.getfixturevalue(case)
+    eng = c.eng
+    # our loss terms (mse, entropy, orientation, sigmoid_rgb) + smooth TV vs the oracle's total
+    eng.smooth_grad_tv_add_grad()
+    torch.cuda.synchronize()
+    total = float(eng.ws["loss"].sum())
+    ref_total = float(c.loss.detach())
+    assert abs(total - ref_total) <= 1e-4 * abs(ref_total), (total, ref_total, eng.ws["loss"].tolist())
+    eng.sdf_tv_add_grad(c.step)
+    torch.cuda.synchronize()
+    ref = dict(c.m.params())
+    names = [f"rgbnet.{i}" for i in range(4)] + [f"refnet.{i}" for i in range(4)]
+    for i, n in enumerate(names):
+        _close(eng.gW[i], ref[n + ".weight"].grad, n + ".weight.grad")
+        _close(eng.gB[i], ref[n + ".bias"].grad, n + ".bias.grad")
+    _close(eng.g_k0, ref["k0"].grad, "k0.grad")
+    _close(eng.g_sdf, ref["sdf"].grad, "sdf.grad (after TV add-grad)")
+    for i, n in enumerate(names):
+        print(case, n, "weight grad rel err", _rel(eng.gW[i], ref[n + ".weight"].grad))
+    print(case, "k0 grad rel err", _rel(eng.g_k0, ref["k0"].grad), " sdf grad rel err", _rel(eng.g_sdf, ref["sdf"].grad))
+
+
+def test_full_train_step_matches_reference_optimizer(cuda):
+    """forward + loss + backward + both TV terms + MaskedAdam in one call vs the oracle's step."""
+    from fgs_nerf_b200 import engine, scene
+    c = Case(cuda, G=48, mask_G=40, N=192, H=100, W=100, n_views=8, step=5000)
+    eng = engine.FineStepEngine(c.sc, 192, cuda, train_cfg=c.train_cfg)
+    eng.set_nonempty_mask()
+    ro, rd, vd, tgt = c.rays
+    eng.train_step(ro, rd, vd, tgt, c.step)
+    torch.cuda.synchronize()
+    ref = dict(c.m.params())
+    t = c.train_cfg
+    # Adam's first step moves every touched parameter by ~lr * sign(g): compare the UPDATE, with an
+    # absolute tolerance of 1e-3 * lr for entries whose gradient is at rounding-noise level
+    def upd(name, mine, lr, before):
+        d_ref = (ref[name].detach() - before).float()
+        d_mine = (mine.detach() - before).float()
+        bad = (d_ref - d_mine).abs() > 1e-3 * lr + 1e-4 * d_ref.abs()
+        frac = float(bad.float().mean())
+        assert frac < 1e-3, f"{name}: {frac:.5f} of the updates differ"
+    upd("sdf", eng.sdf, t["lrate_sdf"], c.p_before["sdf"])
+    upd("k0", eng.k0, t["lrate_k0"], c.p_before["k0"])
+    names = [f"rgbnet.{i}" for i in range(4)] + [f"refnet.{i}" for i in range(4)]
+    for i, n in enumerate(names):
+        upd(n + ".weight", eng.Wt[i], 1e-3, c.p_before[n + ".weight"])
+        upd(n + ".bias", eng.Bt[i], 1e-3, c.p_before[n + ".bias"])
+    # masked Adam: untouched k0 voxels must be bit-identical to before
+    untouched = ref["k0"].grad == 0
+    assert torch.equal(eng.k0[untouched], c.p_before["k0"][untouched])
+
+
+def test_golden_fixture_from_reference_python(cuda):
+    """tests/golden/fine_golden.npz was produced by the reference's own model/nerf.py on the CPU.
+    CPU and CUDA F.grid_sample round differently and the MaskCache test `trilinear(1e-3 field) >=
+    1e-3` sits on that rounding by construction (hard part 1), so the CPU run keeps a
+    slightly different sample set than ANY CUDA run (the reference's included).  Rays whose
+    level-2 sample count agrees with the fixture must match to 2e-4; they must be the majority."""
+    from fgs_nerf_b200 import engine
+    gold = fine_case.load_golden()
+    sc, (ro, rd, vd, tgt), step = fine_case.golden_inputs(gold)
+    N = ro.shape[0]
+    eng = engine.FineStepEngine(sc, N, cuda)
+    eng.forward(ro.to(cuda), rd.to(cuda), vd.to(cuda), step, near=2.0, bg=1.0, render_depth=True, render_grad=True)
+    out = eng.outputs()
+    mine_cnt = torch.bincount(out["ray_id"].cpu(), minlength=N)
+    gold_cnt = torch.bincount(torch.from_numpy(gold["out_ray_id"]), minlength=N)
+    same = mine_cnt == gold_cnt
+    assert float(same.float().mean()) > 0.6, float(same.float().mean())
+    _close(out["rgb_marched"].cpu()[same], torch.from_numpy(gold["out_rgb_marched"])[same], "rgb_marched vs golden", rtol=2e-4)
+    _close(out["alphainv_cum"].cpu()[same], torch.from_numpy(gold["out_alphainv_cum"])[same], "alphainv_cum vs golden",
+           rtol=2e-4)
+
+
+@pytest.mark.parametrize("mode,M,N,K", [(0, 300, 256, 106), (0, 129, 3, 256), (1, 257, 307, 256), (1, 100, 256, 3),
+                                        (2, 256, 307, 1000), (2, 3, 256, 777)])
+def test_gemm_modes(cuda, mode, M, N, K):
+    from fgs_nerf_b200 import engine
+    g = torch.Generator(device="cpu").manual_seed(mode * 1000 + M)
+    r = lambda *s: torch.randn(*s, generator=g).to(cuda)
+    if mode == 0:
+        A, B = r(M, K), r(N, K)
+        want = A.double() @ B.double().T
+    elif mode == 1:
+        A, B = r(M, K), r(K, N)
+        want = A.double() @ B.double()
+    else:
+        A, B = r(K, M), r(K, N)
+        want = A.double().T @ B.double()
+    out = torch.zeros(M, N, device=cuda)
+    rows = torch.tensor([K if mode == 2 else M], dtype=torch.int32, device=cuda)
+    engine.gemm(mode, A, B, out, rows_dev=rows)
+    assert _rel(out, want) < 1e-5
+    if mode != 2:
+        bias = r(N)
+        mask = r(M, N)
+        engine.gemm(mode, A, B, out, bias=bias, relu=True, relu_mask=mask, rows_dev=rows)
+        want2 = torch.relu(want + bias.double()) * (mask > 0)
+        assert _rel(out, want2) < 1e-5
+        # device-side row count smaller than the launch extent: rows beyond it stay untouched
+        out.fill_(7.0)
+        rows.fill_(M // 2)
+        engine.gemm(mode, A, B, out, rows_dev=rows)
+        assert bool((out[M // 2:] == 7.0).all()) and _rel(out[:M // 2], want[:M // 2]) < 1e-5
+
+
+@pytest.mark.parametrize("C,cl", [(1, False), (12, True), (3, False)])
+def test_grid_sample_matches_aten(cuda, C, cl):
+    """DenseGrid.forward arithmetic = F.grid_sample(align_corners=True) on CUDA: bit-exact forward."""
+    import torch.nn.functional as F
+    from fgs_nerf_b200 import engine
+    g = torch.Generator().manual_seed(5)
+    grid = torch.randn(1, C, 20, 17, 23, generator=g).to(cuda)
+    mn, mx = torch.tensor([-1.0, -0.5, -2.0]), torch.tensor([1.0, 1.5, 0.5])
+    xyz = (torch.rand(5000, 3, generator=g) * 1.2 - 0.1) * (mx - mn) + mn     # some points outside
+    xyz = xyz.to(cuda)
+    ind = ((xyz - mn.to(cuda)) / (mx.to(cuda) - mn.to(cuda))).flip((-1,)) * 2 - 1
+    want = F.grid_sample(grid, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True)
+    want = want.reshape(C, -1).T
+    gg = grid.contiguous(memory_format=torch.channels_last_3d) if cl else grid
+    got = engine.grid_sample(gg, xyz, mn, mx)
+    assert torch.equal(got, want), f"{int((got != want).sum())} of {got.numel()} differ"
+    go = torch.randn(5000, C, generator=g).to(cuda)
+    grid_r = grid.clone().requires_grad_(True)
+    F.grid_sample(grid_r, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True).reshape(C, -1).T.backward(go)
+    mine = engine.grid_sample_backward(tuple(grid.shape), cl, xyz, mn, mx, go)
+    _close(mine, grid_r.grad, "grid_sample backward")
