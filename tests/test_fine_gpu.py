@@ -179,8 +179,8 @@ def test_golden_fixture_from_reference_python(cuda):
     """tests/golden/fine_golden.npz was produced by the reference's own model/nerf.py on the CPU.
     CPU and CUDA F.grid_sample round differently and the MaskCache test `trilinear(1e-3 field) >=
     1e-3` sits on that rounding by construction (hard part 1), so the CPU run keeps a
-    slightly different sample set than ANY CUDA run (the reference's included).  Rays whose
-    level-2 sample count agrees with the fixture must match to 2e-4; they must be the majority."""
+    slightly different sample set than ANY CUDA run (the reference's included): >90% of the rays
+    must still match the fixture to 2e-4 (the bit-exact bar is against the CUDA oracle above)."""
     from fgs_nerf_b200 import engine
     gold = fine_case.load_golden()
     sc, (ro, rd, vd, tgt), step = fine_case.golden_inputs(gold)
@@ -188,13 +188,12 @@ def test_golden_fixture_from_reference_python(cuda):
     eng = engine.FineStepEngine(sc, N, cuda)
     eng.forward(ro.to(cuda), rd.to(cuda), vd.to(cuda), step, near=2.0, bg=1.0, render_depth=True, render_grad=True)
     out = eng.outputs()
-    mine_cnt = torch.bincount(out["ray_id"].cpu(), minlength=N)
-    gold_cnt = torch.bincount(torch.from_numpy(gold["out_ray_id"]), minlength=N)
-    same = mine_cnt == gold_cnt
-    assert float(same.float().mean()) > 0.6, float(same.float().mean())
-    _close(out["rgb_marched"].cpu()[same], torch.from_numpy(gold["out_rgb_marched"])[same], "rgb_marched vs golden", rtol=2e-4)
-    _close(out["alphainv_cum"].cpu()[same], torch.from_numpy(gold["out_alphainv_cum"])[same], "alphainv_cum vs golden",
-           rtol=2e-4)
+    for k in ("rgb_marched", "alphainv_cum"):
+        a, b = out[k].cpu().reshape(N, -1), torch.from_numpy(gold["out_" + k]).reshape(N, -1)
+        ok = ((a - b).abs() <= 2e-4 * b.abs() + 1e-5).all(dim=1)
+        frac = float(ok.float().mean())
+        print(f"golden {k}: {frac:.4f} of the rays within 2e-4")
+        assert frac > 0.9, f"{k}: only {frac:.3f} of the rays agree with the CPU fixture"
 
 
 @pytest.mark.parametrize("mode,M,N,K", [(0, 300, 256, 106), (0, 129, 3, 256), (1, 257, 307, 256), (1, 100, 256, 3),
