@@ -82,9 +82,16 @@ _lib.declare("fgs_grid_sample_fwd", C.c_int,
              [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
 _lib.declare("fgs_grid_sample_bwd", C.c_int,
              [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
-_lib.declare("fgs_gemm", C.c_int,
-             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
-              _fp, C.c_int, _fp, _fp])
+_GEMM_SIG = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
+             _fp, C.c_int, _fp, _fp]
+_lib.declare("fgs_gemm", C.c_int, _GEMM_SIG)
+_lib.declare("fgs_gemm_tc", C.c_int, _GEMM_SIG)
+_lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
+
+
+def set_gemm_backend(tensor_core=True):
+    """MLP GEMMs of the fused step: tcgen05 3xTF32 tensor cores (default) or the fp32 SIMT kernel."""
+    check(lib.fgs_set_gemm_backend(int(bool(tensor_core))))
 
 
 def _c3(t):
@@ -127,8 +134,8 @@ def grid_sample_backward(grid_shape, channels_last, xyz, xyz_min, xyz_max, grad_
     return grad_grid
 
 
-def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None):
-    """fgs_gemm on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
+def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None, tc=False):
+    """fgs_gemm / fgs_gemm_tc on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
     if mode == 0:
         m, k = A.shape; n = B.shape[0]
     elif mode == 1:
@@ -136,7 +143,7 @@ def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, 
     else:
         k, m = A.shape; n = B.shape[1]
     M, N, K = M or m, N or n, K or k
-    check(lib.fgs_gemm(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
+    check((lib.fgs_gemm_tc if tc else lib.fgs_gemm)(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
                        ptr(bias), int(relu), ptr(relu_mask), relu_mask.stride(0) if relu_mask is not None else 0,
                        ptr(rows_dev), stream()))
     return out
@@ -171,17 +178,25 @@ class FineStepEngine:
         self.fast_color_thres = np.float32(self.cfg["fast_color_thres"])
         layers = list(scene.rgbnet) + list(scene.refnet)
         assert len(layers) == MLP_LAYERS
-        self.Wt = [w.to(dev, f32).contiguous().clone() for w, _ in layers]
-        self.Bt = [b.to(dev, f32).contiguous().clone() for _, b in layers]
         dims = [(WIDTH, X0_DIM)] + [(WIDTH, WIDTH)] * 3 + [(WIDTH, XR_DIM)] + [(WIDTH, WIDTH)] * 2 + [(3, WIDTH)]
-        for w, d in zip(self.Wt, dims):
+        lds = [X0_LD, WIDTH, WIDTH, WIDTH, XR_LD, WIDTH, WIDTH, WIDTH]
+        # storage: input layers zero-padded to the activation row length ([256,112], [256,320]);
+        # self.weights[i] are the nn.Linear-shaped views ([out,in]) of the same memory
+        self.Wt, self.weights = [], []
+        for (w, _), d, ld in zip(layers, dims, lds):
             assert tuple(w.shape) == d, (tuple(w.shape), d)
+            st = torch.zeros(d[0], ld, dtype=f32, device=dev)
+            st[:, :d[1]] = w.to(dev, f32)
+            self.Wt.append(st)
+            self.weights.append(st[:, :d[1]])
+        self.Bt = [b.to(dev, f32).contiguous().clone() for _, b in layers]
         X, Y, Z = self.sdf.shape[2:]
         self.X, self.Y, self.Z = X, Y, Z
         # ---- gradients + Adam state ----
         self.g_sdf = torch.zeros_like(self.sdf)
         self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
         self.gW = [torch.zeros_like(w) for w in self.Wt]
+        self.weight_grads = [g[:, :d[1]] for g, d in zip(self.gW, dims)]
         self.gB = [torch.zeros_like(b) for b in self.Bt]
         self.adam = {}
         self.adam_step = 0

@@ -23,7 +23,10 @@
  *   k0    [X][Y][Z][C] fp32 = torch.channels_last_3d storage of the reference's [1,C,X,Y,Z]
  *         (one voxel's 12 channels are three 128-bit loads);
  *   mask  [mX][mY][mZ] fp32 (MaskCache.sdf_mask after its max-pool, model/nerf.py:1199);
- *   MLP weights: nn.Linear layout W[out][in], bias[out]; layers 0-3 = rgbnet, 4-7 = refnet;
+ *   MLP weights: nn.Linear layout W[out][in], bias[out]; layers 0-3 = rgbnet, 4-7 = refnet; the two
+ *         input layers are stored zero-padded to the activation row length: W[0] is [256][112]
+ *         (106 used), W[4] is [256][320] (307 used), so every GEMM operand row is 16-byte aligned
+ *         (pad columns stay exactly 0 under Adam: their gradient is 0);
  *   activations: SAMPLE-MAJOR rows [cap_m2][ld] (K contiguous: the operand layout of the GEMMs).
  */
 #ifndef FGS_B200_FINE_H
@@ -170,6 +173,16 @@ int fgs_grid_sample_bwd(float* g_grid, int C, int X, int Y, int Z, int channels_
 int fgs_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
              const int32_t* rows_dev, fgs_stream_t stream);
+
+/* Same contract on the tcgen05 tensor cores (3xTF32 split, fp32-grade accuracy).  Operands must be
+ * 16-byte aligned with leading dimensions % 4 == 0, and readable up to the next multiple of 4
+ * along their contiguous dimension. */
+int fgs_gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
+                const int32_t* rows_dev, fgs_stream_t stream);
+
+/* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
+int fgs_set_gemm_backend(int tensor_core);
 
 #ifdef __cplusplus
 }

@@ -136,12 +136,12 @@ def test_loss_and_gradients(case, request):
     ref = dict(c.m.params())
     names = [f"rgbnet.{i}" for i in range(4)] + [f"refnet.{i}" for i in range(4)]
     for i, n in enumerate(names):
-        _close(eng.gW[i], ref[n + ".weight"].grad, n + ".weight.grad")
+        _close(eng.weight_grads[i], ref[n + ".weight"].grad, n + ".weight.grad")
         _close(eng.gB[i], ref[n + ".bias"].grad, n + ".bias.grad")
     _close(eng.g_k0, ref["k0"].grad, "k0.grad")
     _close(eng.g_sdf, ref["sdf"].grad, "sdf.grad (after TV add-grad)")
     for i, n in enumerate(names):
-        print(case, n, "weight grad rel err", _rel(eng.gW[i], ref[n + ".weight"].grad))
+        print(case, n, "weight grad rel err", _rel(eng.weight_grads[i], ref[n + ".weight"].grad))
     print(case, "k0 grad rel err", _rel(eng.g_k0, ref["k0"].grad), " sdf grad rel err", _rel(eng.g_sdf, ref["sdf"].grad))
 
 
@@ -168,7 +168,7 @@ def test_full_train_step_matches_reference_optimizer(cuda):
     upd("k0", eng.k0, t["lrate_k0"], c.p_before["k0"])
     names = [f"rgbnet.{i}" for i in range(4)] + [f"refnet.{i}" for i in range(4)]
     for i, n in enumerate(names):
-        upd(n + ".weight", eng.Wt[i], 1e-3, c.p_before[n + ".weight"])
+        upd(n + ".weight", eng.weights[i], 1e-3, c.p_before[n + ".weight"])
         upd(n + ".bias", eng.Bt[i], 1e-3, c.p_before[n + ".bias"])
     # masked Adam: untouched k0 voxels must be bit-identical to before
     untouched = ref["k0"].grad == 0
@@ -249,3 +249,75 @@ def test_grid_sample_matches_aten(cuda, C, cl):
     F.grid_sample(grid_r, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True).reshape(C, -1).T.backward(go)
     mine = engine.grid_sample_backward(tuple(grid.shape), cl, xyz, mn, mx, go)
     _close(mine, grid_r.grad, "grid_sample backward")
+
+
+def _tc_case(cuda, mode, M, N, K, seed):
+    """Operands laid out the way the fused step feeds the tensor-core kernel: leading dimensions
+    rounded up to 4 floats, pad entries zero."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    pad4 = lambda n: (n + 3) // 4 * 4
+
+    def mat(r, c):
+        t = torch.zeros(r, pad4(c))
+        t[:, :c] = torch.randn(r, c, generator=g)
+        return t.to(cuda)
+    if mode == 0:
+        A, B = mat(M, K), mat(N, K)
+        want = A[:, :K].double() @ B[:, :K].double().T
+    elif mode == 1:
+        A, B = mat(M, K), mat(K, N)
+        want = A[:, :K].double() @ B[:, :N].double()
+    else:
+        A, B = mat(K, M), mat(K, N)
+        want = A[:, :M].double().T @ B[:, :N].double()
+    return A, B, want
+
+
+@pytest.mark.parametrize("mode,M,N,K", [
+    (0, 300, 256, 112), (0, 129, 3, 256), (0, 1000, 256, 320), (0, 128, 256, 16), (0, 5, 16, 4),
+    (1, 257, 320, 256), (1, 100, 256, 3), (1, 640, 112, 256),
+    (2, 256, 320, 1000), (2, 3, 256, 777), (2, 256, 112, 40000), (2, 256, 256, 130)])
+def test_gemm_tensor_core_3xtf32(cuda, mode, M, N, K):
+    """tcgen05 kind::tf32 with the 3xTF32 split must be fp32-grade (the reference's MLPs are true
+    fp32 SGEMMs): max error relative to the largest output < 2e-6, far inside the 1e-4 bar."""
+    from fgs_nerf_b200 import engine
+    A, B, want = _tc_case(cuda, mode, M, N, K, mode * 7919 + M + N + K)
+    out = torch.full((M, (N + 3) // 4 * 4), 0.0, device=cuda)
+    rows = torch.tensor([K if mode == 2 else M], dtype=torch.int32, device=cuda)
+    engine.gemm(mode, A, B, out, rows_dev=rows, M=M, N=N, K=K, tc=True)
+    torch.cuda.synchronize()
+    err = _rel(out[:, :N], want)
+    print(f"tc gemm mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
+    assert err < 1e-5, err
+    if mode != 2:
+        g = torch.Generator(device="cpu").manual_seed(1)
+        bias = torch.randn(N, generator=g).to(cuda)
+        mask = torch.randn(M, (N + 3) // 4 * 4, generator=g).to(cuda)
+        out.fill_(7.0)
+        rows.fill_(M // 2)
+        engine.gemm(mode, A, B, out, bias=bias, relu=True, relu_mask=mask, rows_dev=rows, M=M, N=N, K=K, tc=True)
+        want2 = torch.relu(want + bias.double()) * (mask[:, :N] > 0)
+        assert bool((out[M // 2:, :N] == 7.0).all()), "rows beyond the device-side row count were written"
+        if M // 2 > 0:
+            assert _rel(out[:M // 2, :N], want2[:M // 2]) < 1e-5
+
+
+def test_simt_backend_agrees_with_tensor_core_backend(cuda):
+    """The fp32 SIMT GEMM path stays selectable; both backends must give the same step."""
+    from fgs_nerf_b200 import engine, scene
+    sc = scene.make_scene(G=48, mask_G=40)
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=192, H=100, W=100, n_views=8)]
+    res = []
+    try:
+        for tc in (True, False):
+            engine.set_gemm_backend(tc)
+            eng = engine.FineStepEngine(sc, 192, cuda)
+            eng.forward(ro, rd, vd, 5000)
+            eng.zero_grad()
+            eng.loss_backward(tgt)
+            torch.cuda.synchronize()
+            res.append((eng.ws["rgb_marched"].clone(), eng.g_sdf.clone(), eng.g_k0.clone(), eng.gW[0].clone(), eng.gW[4].clone()))
+    finally:
+        engine.set_gemm_backend(True)
+    for a, b, n in zip(res[0], res[1], ("rgb_marched", "g_sdf", "g_k0", "gW0", "gW4")):
+        assert _rel(a, b) < 2e-5, (n, _rel(a, b))
