@@ -4,8 +4,8 @@
 // Why 3xTF32: the reference runs its nn.Linear layers as true-fp32 SGEMMs (TF32 off,
 // model/nerf.py:125-151) and the parity bar is 1e-4 relative on colours AND gradients; a single
 // TF32 pass (10-bit mantissa) misses it.  Each fp32 operand x is split on the fly into
-//   hi = x with the low 13 mantissa bits cleared (exactly what the tensor core would read),
-//   lo = x - hi  (exact in fp32; its own TF32 truncation leaves a 2^-22 relative residue),
+//   hi = rn_tf32(x)          (cvt.rna: 10-bit mantissa, round to nearest),
+//   lo = rn_tf32(x - hi)     (the residue, again rounded to TF32: split error <= 2^-23 |x|),
 // and D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi is issued as three MMAs per k-step into the same fp32
 // TMEM accumulator (the dropped A_lo*B_lo term is ~2^-22 relative).
 //
@@ -34,6 +34,7 @@ constexpr uint32_t kATile = BM * BK * 4;        // 8 KB
 constexpr uint32_t kBTile = 256 * BK * 4;       // 16 KB
 constexpr uint32_t kStage = 2 * kATile + 2 * kBTile;  // 48 KB: A_hi, A_lo, B_hi, B_lo
 constexpr int kStages = 2;
+constexpr float kReluRefine = 1e-4f;  // |pre-activation| below this is recomputed in fp64 before ReLU
 constexpr uint32_t kSmemBytes = kStages * kStage + 64;
 
 struct TcArgs {
@@ -79,12 +80,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
+// hi = rn_tf32(x), lo = rn_tf32(x - hi): both exactly representable in TF32, so the tensor core's
+// operand truncation is a no-op and the split error is <= 2^-23 |x|, unbiased (a truncating split
+// leaves a one-sided 2^-21 error that flips ReLU masks near zero ~30x more often than fp32 does)
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float4 split_lo(float4 x, float4& hi) {
-  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-  return make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+  hi.x = rn_tf32(x.x); hi.y = rn_tf32(x.y); hi.z = rn_tf32(x.z); hi.w = rn_tf32(x.w);
+  return make_float4(rn_tf32(x.x - hi.x), rn_tf32(x.y - hi.y), rn_tf32(x.z - hi.z), rn_tf32(x.w - hi.w));
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
@@ -283,7 +289,22 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(const TcArgs a) {
           for (int q = 0; q < 4; ++q) {
             float x = __uint_as_float(r[j4 + q]);
             if (a.bias && j4 + q < nvalid) x += __ldg(a.bias + n0 + c0 + j4 + q);
-            if (a.relu) x = fmaxf(x, 0.f);
+            if (a.relu) {
+              // The TMEM accumulator truncates (round-toward-zero) at every MMA, which leaves a
+              // ~1e-6-relative bias after the 3*K/8 accumulations of a layer.  Harmless for the
+              // value, but a pre-activation that close to 0 could take the other ReLU branch than
+              // an fp32 SGEMM does, and one switched unit moves its sample's gradients by O(1).
+              // The (rare: ~1e-4 of the units) near-zero pre-activations are therefore recomputed
+              // exactly -- an fp64 dot product of the two fp32 rows -- before the ReLU decides.
+              if (!A_MN && !B_MN && fabsf(x) < kReluRefine && j4 + q < nvalid) {
+                const float* ar = a.A + (size_t)m * a.lda;
+                const float* br = a.B + (size_t)(n0 + c0 + j4 + q) * a.ldb;
+                double acc = a.bias ? (double)__ldg(a.bias + n0 + c0 + j4 + q) : 0.;
+                for (int k = 0; k < K; ++k) acc = fma((double)__ldg(ar + k), (double)__ldg(br + k), acc);
+                x = (float)acc;
+              }
+              x = fmaxf(x, 0.f);
+            }
             v[q] = x;
           }
           if (vec) {
