@@ -4,6 +4,7 @@
 //   fgs_fine_backward : 8 layers x (dW GEMM, db colsum, dX GEMM) -> feat_bwd -> level1_bwd
 // plus the stand-alone DenseGrid / MaskCache trilinear ops.  No host synchronisation anywhere.
 #include "fine_common.cuh"
+#include "tc_api.cuh"
 
 namespace fine {
 int launch_march(const FgsFineParams& P, cudaStream_t st);
@@ -14,9 +15,6 @@ int launch_level1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t 
 int gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
          int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
          const int32_t* rows_dev, cudaStream_t st);
-int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-            int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-            const int32_t* rows_dev, cudaStream_t st);
 int colsum(const float* X, int ld, int rows, int N, const int32_t* rows_dev, float* out, cudaStream_t st);
 }  // namespace fine
 
@@ -38,16 +36,45 @@ float* hidden(const FgsFineParams& P, int i) { return P.H + (size_t)i * P.cap_m2
 
 // 1 = tcgen05 3xTF32 tensor-core GEMMs (default), 0 = fp32 SIMT GEMMs (gemm.cu)
 int g_backend = 1;
-int mm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-       const float* bias, int relu, const float* relu_mask, int ld_mask, const int32_t* rows_dev,
+
+uint32_t* hbits(const FgsFineParams& P, int i) { return P.hbits + (size_t)i * P.cap_m2 * 8; }
+
+// One MLP GEMM of the fused step.  layer: which weight matrix (modes 0/1); hid: hidden buffer whose
+// ReLU mask is produced (mode 0 with relu) or applied (mode 1), -1 for none.
+int mm(const FgsFineParams& P, int mode, int layer, int hid, int M, int N, int K, const float* A, int lda,
+       const float* B, int ldb, float* C, int ldc, const float* bias, int relu, const int32_t* rows_dev,
        cudaStream_t st) {
-  return g_backend ? gemm_tc(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, relu_mask, ld_mask, rows_dev, st)
-                   : gemm(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, relu_mask, ld_mask, rows_dev, st);
+  if (!g_backend) {
+    const float* mask = (mode == 1 && hid >= 0) ? hidden(P, hid) : nullptr;
+    return gemm(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, W, rows_dev, st);
+  }
+  if (mode == 2) return gemm_tc(2, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, nullptr, 0, rows_dev, st);
+  const WSplitLayout L = wsplit_layout();
+  if (mode == 0)
+    return gemm_w(M, N, K, A, lda, P.w_split + L.hi[layer], P.w_split + L.lo[layer], L.in_ld[layer], C, ldc, bias,
+                  relu, nullptr, (relu && hid >= 0) ? hbits(P, hid) : nullptr, rows_dev, st);
+  return gemm_w(M, N, K, A, lda, P.w_split + L.thi[layer], P.w_split + L.tlo[layer], L.ldt[layer], C, ldc, nullptr,
+                0, hid >= 0 ? hbits(P, hid) : nullptr, nullptr, rows_dev, st);
+}
+
+// hi / lo TF32 planes of the 8 weight matrices, straight and transposed, in one launch
+int prep_weights(const FgsFineParams& P, cudaStream_t st) {
+  if (!g_backend) return 0;
+  FGS_REQUIRE(P.w_split != nullptr && P.hbits != nullptr, "w_split / hbits workspace is NULL");
+  const WSplitLayout L = wsplit_layout();
+  SplitJobHost jobs[2 * FGS_MLP_LAYERS];
+  for (int l = 0; l < FGS_MLP_LAYERS; ++l) {
+    jobs[2 * l] = {P.W[l], P.w_split + L.hi[l], P.w_split + L.lo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.in_ld[l], 0};
+    jobs[2 * l + 1] = {P.W[l], P.w_split + L.thi[l], P.w_split + L.tlo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.ldt[l], 1};
+  }
+  return weight_split_jobs(jobs, 2 * FGS_MLP_LAYERS, st);
 }
 
 }  // namespace
 
 extern "C" {
+
+int64_t fgs_fine_wsplit_floats(void) { return (int64_t)wsplit_layout().total; }
 
 int fgs_set_gemm_backend(int tensor_core) {
   g_backend = tensor_core ? 1 : 0;
@@ -63,16 +90,17 @@ int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
   if ((rc = launch_feat(P, st))) return rc;
   const int* m2 = P.counters + FGS_CNT_M2;
   const int cap = P.cap_m2;
+  if ((rc = prep_weights(P, st))) return rc;
   // rgbnet (model/nerf.py:125-134, 877)
-  if ((rc = mm(0, cap, W, FGS_X0_LD, P.X0, FGS_X0_LD, P.W[0], FGS_X0_LD, hidden(P, 0), W, P.B[0], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, W, W, hidden(P, 0), W, P.W[1], W, hidden(P, 1), W, P.B[1], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, W, W, hidden(P, 1), W, P.W[2], W, hidden(P, 2), W, P.B[2], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, W, W, hidden(P, 2), W, P.W[3], W, P.XR, FGS_XR_LD, P.B[3], 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 0, 0, 0, cap, W, FGS_X0_LD, P.X0, FGS_X0_LD, P.W[0], FGS_X0_LD, hidden(P, 0), W, P.B[0], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 1, 1, cap, W, W, hidden(P, 0), W, P.W[1], W, hidden(P, 1), W, P.B[1], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 2, 2, cap, W, W, hidden(P, 1), W, P.W[2], W, hidden(P, 2), W, P.B[2], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 3, -1, cap, W, W, hidden(P, 2), W, P.W[3], W, P.XR, FGS_XR_LD, P.B[3], 0, m2, st))) return rc;
   // refnet (model/nerf.py:136-151, 883-884)
-  if ((rc = mm(0, cap, W, FGS_XR_LD, P.XR, FGS_XR_LD, P.W[4], FGS_XR_LD, hidden(P, 3), W, P.B[4], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, W, W, hidden(P, 3), W, P.W[5], W, hidden(P, 4), W, P.B[5], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, W, W, hidden(P, 4), W, P.W[6], W, hidden(P, 5), W, P.B[6], 1, nullptr, 0, m2, st))) return rc;
-  if ((rc = mm(0, cap, 3, W, hidden(P, 5), W, P.W[7], W, P.logit, 4, P.B[7], 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 0, 4, 3, cap, W, FGS_XR_LD, P.XR, FGS_XR_LD, P.W[4], FGS_XR_LD, hidden(P, 3), W, P.B[4], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 5, 4, cap, W, W, hidden(P, 3), W, P.W[5], W, hidden(P, 4), W, P.B[5], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 6, 5, cap, W, W, hidden(P, 4), W, P.W[6], W, hidden(P, 5), W, P.B[6], 1, m2, st))) return rc;
+  if ((rc = mm(P, 0, 7, -1, cap, 3, W, hidden(P, 5), W, P.W[7], W, P.logit, 4, P.B[7], 0, m2, st))) return rc;
   return launch_composite(P, nullptr, st);
 }
 
@@ -101,37 +129,37 @@ int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t
   fgs::prof_mark("memset", st);
   // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
   // layer 7: logit = H5 W7^T + b7
-  if ((rc = mm(2, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dlogit, 4, cap, 3, m2, P.gB[7], st))) return rc;
-  if ((rc = mm(1, cap, W, 3, P.dlogit, 4, P.W[7], W, P.dA, W, nullptr, 0, hidden(P, 5), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 7, 5, cap, W, 3, P.dlogit, 4, P.W[7], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 6: H5 = relu(H4 W6^T + b6); dA = dZ6
-  if ((rc = mm(2, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[6], st))) return rc;
-  if ((rc = mm(1, cap, W, W, P.dA, W, P.W[6], W, P.dB, W, nullptr, 0, hidden(P, 4), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 6, 4, cap, W, W, P.dA, W, P.W[6], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 5: dB = dZ5
-  if ((rc = mm(2, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[5], st))) return rc;
-  if ((rc = mm(1, cap, W, W, P.dB, W, P.W[5], W, P.dA, W, nullptr, 0, hidden(P, 3), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 5, 3, cap, W, W, P.dB, W, P.W[5], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 4: H3 = relu(XR W4^T + b4); dA = dZ4; dXR = dZ4 W4 (no mask: XR is not a ReLU output)
-  if ((rc = mm(2, W, FGS_XR_LD, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, FGS_XR_LD, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_LD, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[4], st))) return rc;
-  if ((rc = mm(1, cap, FGS_XR_LD, W, P.dA, W, P.W[4], FGS_XR_LD, P.dXR, FGS_XR_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 1, 4, -1, cap, FGS_XR_LD, W, P.dA, W, P.W[4], FGS_XR_LD, P.dXR, FGS_XR_LD, nullptr, 0, m2, st))) return rc;
   // ---- rgbnet: dZ3 = dXR[:, 0:256] (last rgbnet layer is linear) ----
-  if ((rc = mm(2, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dXR, FGS_XR_LD, cap, W, m2, P.gB[3], st))) return rc;
-  if ((rc = mm(1, cap, W, W, P.dXR, FGS_XR_LD, P.W[3], W, P.dB, W, nullptr, 0, hidden(P, 2), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 3, 2, cap, W, W, P.dXR, FGS_XR_LD, P.W[3], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 2
-  if ((rc = mm(2, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[2], st))) return rc;
-  if ((rc = mm(1, cap, W, W, P.dB, W, P.W[2], W, P.dA, W, nullptr, 0, hidden(P, 1), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 2, 1, cap, W, W, P.dB, W, P.W[2], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 1
-  if ((rc = mm(2, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[1], st))) return rc;
-  if ((rc = mm(1, cap, W, W, P.dA, W, P.W[1], W, P.dB, W, nullptr, 0, hidden(P, 0), W, m2, st))) return rc;
+  if ((rc = mm(P, 1, 1, 0, cap, W, W, P.dA, W, P.W[1], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 0
-  if ((rc = mm(2, W, FGS_X0_LD, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, FGS_X0_LD, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_LD, nullptr, 0, m2, st))) return rc;
   if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[0], st))) return rc;
-  if ((rc = mm(1, cap, FGS_X0_LD, W, P.dB, W, P.W[0], FGS_X0_LD, P.dX0, FGS_X0_LD, nullptr, 0, nullptr, 0, m2, st))) return rc;
+  if ((rc = mm(P, 1, 0, -1, cap, FGS_X0_LD, W, P.dB, W, P.W[0], FGS_X0_LD, P.dX0, FGS_X0_LD, nullptr, 0, m2, st))) return rc;
   // ---- features -> level-1 quantities -> grids ----
   if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
   return launch_level1_bwd(P, l->g_alphainv_last, st);

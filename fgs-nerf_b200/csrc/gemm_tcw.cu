@@ -1,0 +1,506 @@
+// Tensor-core GEMMs "activations x weights" of the colour MLPs (forward  Y = X W^T + b  and
+// backward-data  dX = dZ W): the weight operand arrives PRE-SPLIT and by TMA (sm_100a).
+//
+// Same numerics as gemm_tc.cu (3xTF32 split, 32-k accumulation chunks in alternating TMEM regions,
+// fp32 register accumulators), different data movement -- each choice below answers a measured
+// cost of the previous version (tools/gemm_phase_probe.py, per-phase clock64 of one CTA):
+//   * the 0.45 M MLP weights are split ONCE per step into hi / lo TF32 planes, straight ([out][in],
+//     forward) and transposed ([in][out], dZ*W) -- weight_split_kernel, one launch -- instead of
+//     being re-split from fp32 by every CTA for every k-slab;
+//   * the B (weight) tiles are fetched by TMA: one elected thread issues two
+//     cp.async.bulk.tensor.4d per k-slab (hi, lo).  The 4-D tensor map views a [rows][ld] plane as
+//     (4 floats, 8 rows, k-chunks, row-groups), so the box lands in shared memory exactly in the
+//     canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices, LBO 128, SBO 512): no
+//     registers, no LSU instructions (2048 16-byte cp.async per slab cost 0.65 us of issue time),
+//     completion on an mbarrier (expect_tx), prefetched two slabs ahead across tile boundaries;
+//   * only the A (activation) slab -- one third of the bytes -- takes the load / split / store
+//     path, with a lane-per-row mapping whose 128-bit stores are bank-conflict free;
+//   * persistent CTAs (one per SM) loop over the 128-row tiles of the sample dimension, whose
+//     extent is read on the device; TMEM (512 columns) and mbarriers are set up once per CTA;
+//   * ReLU masks travel as BITS: the forward epilogue packs (x > 0) of its 32 columns into one
+//     word per thread, the backward epilogue reads 4 words instead of 128 floats of H;
+//   * the epilogue is transposed through shared memory (32x33 floats per warp) so global stores
+//     are full 128-byte lines (row-per-thread 16-byte stores 1 KB apart cost 11 us per tile).
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "tc_api.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 16, kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kATile = BM * BK * 4;             // 8 KB
+constexpr uint32_t kBTile = 256 * BK * 4;            // 16 KB
+constexpr uint32_t kStage = 2 * kATile + 2 * kBTile; // 48 KB: A_hi, A_lo, B_hi, B_lo
+constexpr int kStages = 4;
+constexpr int kChunkSlabs = 2;
+constexpr uint32_t kStagingOff = kStages * kStage;             // 8 warps x 32 x 33 floats
+constexpr uint32_t kStagingBytes = 8 * 32 * 33 * 4;
+constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;      // mbarriers + tmem slot
+constexpr uint32_t kSmemBytes = kBarOff + 128;
+constexpr int kPfB = 2;                                        // TMA prefetch distance (slabs)
+
+struct WArgs {
+  const float* A; float* C;
+  const float* bias; const uint32_t* bits_in; uint32_t* bits_out; const int* rows_dev;
+  int M, N, K, lda, ldc, relu;
+  long long* dbg;  // optional phase timing of CTA (0,0) thread 0 (tools/gemm_phase_probe.py)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+  if (!done) __trap();  // a phase bug must surface as an error, never as a hung GPU
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {  // K-major, no swizzle, LBO 128, SBO 512
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// hi / lo TF32 planes of a weight matrix W [rows][ld] (cols valid), straight or transposed.
+struct SplitJob {
+  const float* W; float* hi; float* lo;
+  int rows, cols, ld, ld_out, transpose;  // transpose: out[c][r] (ld_out >= rows) else out[r][c] (ld_out >= cols)
+};
+struct SplitJobs {
+  SplitJob j[16];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) weight_split_kernel(const __grid_constant__ SplitJobs jobs) {
+  const SplitJob& J = jobs.j[blockIdx.y];
+  const int total = J.rows * J.cols;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int r = i / J.cols, c = i - r * J.cols;
+    const float x = J.W[(size_t)r * J.ld + c];
+    const float h = rn_tf32(x), l = rn_tf32(x - h);
+    const size_t o = J.transpose ? (size_t)c * J.ld_out + r : (size_t)r * J.ld_out + c;
+    J.hi[o] = h;
+    J.lo[o] = l;
+  }
+}
+
+#define PHASE(i)                                              \
+  do {                                                        \
+    if (dbg_on) {                                             \
+      const long long t_now = clock64();                      \
+      phase[i] += t_now - t_last;                             \
+      t_last = t_now;                                         \
+    }                                                         \
+  } while (0)
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  long long phase[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_last = dbg_on ? clock64() : 0;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const uint32_t free_bar0 = smem + kBarOff;                 // kStages: MMAs done reading the stage
+  const uint32_t bfull_bar0 = free_bar0 + 8 * kStages;       // kStages: TMA bytes of B landed
+  const uint32_t region_bar0 = bfull_bar0 + 8 * kStages;     // 2: accumulation chunk finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (2 * kStages + 2) + 8);
+  float* staging = reinterpret_cast<float*>(smem_raw + kStagingOff);
+
+  int M = a.M;
+  if (a.rows_dev) M = min(M, *a.rows_dev);
+  const int n0 = blockIdx.x * 256;
+  const int n_tiles = (M + BM - 1) / BM;
+  if ((int)blockIdx.y >= n_tiles) return;
+  const int K = a.K;
+  const int BN = min(256, (a.N - n0 + 15) & ~15);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kStages + 2; ++i) mbar_init(free_bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                         ((uint32_t)(BM >> 4) << 24);
+
+  const int n_slabs = (K + BK - 1) / BK;
+  const int n_chunks = (n_slabs + kChunkSlabs - 1) / kChunkSlabs;
+  const int my_tiles = (n_tiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1;
+  const uint32_t total_slabs = (uint32_t)my_tiles * (uint32_t)n_slabs;
+  const int col_half = (warp >> 2) * 128;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  // A slots: thread -> row ar, 16-byte k-chunks ac and ac + 2 (a quarter-warp = 8 consecutive rows of
+  // one core-matrix column = 128 contiguous bytes of shared memory)
+  const int ar = tid & 127, ac = tid >> 7;
+  const uint32_t aoff = (uint32_t)((ar >> 3) * 512 + ac * 128 + (ar & 7) * 16);
+
+  // B of global slab gs (tile-independent: coordinates are (k-chunk, row-group) of the weight plane)
+  auto issue_b = [&](uint32_t gs) {
+    const uint32_t st = gs % kStages;
+    const uint32_t b_hi = smem + st * kStage + 2 * kATile, b_lo = b_hi + kBTile;
+    const uint32_t bar = bfull_bar0 + 8 * st;
+    const int kc = (int)(gs % (uint32_t)n_slabs) * (BK / 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBTile) : "memory");
+    tma_load_4d(b_hi, &tm_hi, bar, 0, 0, kc, n0 >> 3);
+    tma_load_4d(b_lo, &tm_lo, bar, 0, 0, kc, n0 >> 3);
+  };
+  if (tid == 32) {
+    for (uint32_t gs = 0; gs < (uint32_t)kPfB && gs < total_slabs; ++gs) issue_b(gs);
+  }
+  PHASE(0);  // setup
+
+  uint32_t g = 0;   // slabs issued by this CTA so far (stage ring position / mbarrier phases)
+  uint32_t gc = 0;  // accumulation chunks issued so far (TMEM region ring / phases)
+
+  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+    const int m0 = tile * BM;
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+
+    auto load_a = [&](float4 (&v)[2], int k0) {
+      const int m = m0 + ar;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int k = k0 + 4 * (ac + 2 * i);
+        v[i] = (m < M && k < K) ? ldg4(a.A + (size_t)m * a.lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_a = [&](const float4 (&v)[2], uint32_t stage_base) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t off = aoff + (uint32_t)(2 * i) * 128;
+        float4 hi, lo;
+        hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
+        lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
+        lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
+        st_shared_v4(stage_base + off, hi);
+        st_shared_v4(stage_base + kATile + off, lo);
+      }
+    };
+    auto drain = [&](uint32_t c) {   // c = global chunk index
+      mbar_wait(region_bar0 + 8 * (c & 1), (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col_half + 32 * q < BN) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    float4 a0[2], a1[2];
+    load_a(a0, 0);
+    if (n_slabs > 1) load_a(a1, BK);
+    PHASE(1);  // tile prologue
+
+    for (int kt = 0; kt < n_slabs; ++kt, ++g) {
+      const uint32_t st = g % kStages;
+      const uint32_t stage_base = smem + st * kStage;
+      const int cl = kt / kChunkSlabs;                       // chunk within the tile
+      const bool first_in_chunk = (kt % kChunkSlabs) == 0;
+      const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == n_slabs - 1;
+      if (tid == 32) {
+        // B two slabs ahead (possibly already the next tile's): its stage was read by slab gs - kStages
+        const uint32_t gs = g + kPfB;
+        if (gs < total_slabs) {
+          if (gs >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
+          issue_b(gs);
+        }
+      }
+      // the stage was last read by the MMAs of slab g - kStages
+      if (g >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * st, ((g / kStages) - 1) & 1);
+      PHASE(10);  // stage wait
+      if (kt & 1) {
+        store_a(a1, stage_base);
+        if (kt + 2 < n_slabs) load_a(a1, (kt + 2) * BK);
+      } else {
+        store_a(a0, stage_base);
+        if (kt + 2 < n_slabs) load_a(a0, (kt + 2) * BK);
+      }
+      PHASE(2);  // A split + store, next A loads issued
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      PHASE(4);  // fence + barrier
+      if (tid == 0) {
+        mbar_wait(bfull_bar0 + 8 * st, (g / kStages) & 1);   // TMA bytes of B(hi, lo) have landed
+        PHASE(3);  // wait for B
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+        const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+        const uint32_t d = tmem_d + (uint32_t)(((gc + cl) & 1) * 256);
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint64_t dah = make_desc(a_hi + j * 256), dal = make_desc(a_lo + j * 256);
+          const uint64_t dbh = make_desc(b_hi + j * 256), dbl = make_desc(b_lo + j * 256);
+          mma_tf32(d, dal, dbh, idesc, (!first_in_chunk || j != 0) ? 1u : 0u);
+          mma_tf32(d, dah, dbl, idesc, 1);
+          mma_tf32(d, dah, dbh, idesc, 1);
+        }
+        mma_commit(free_bar0 + 8 * st);
+        if (last_in_chunk) mma_commit(region_bar0 + 8 * ((gc + cl) & 1));
+        PHASE(5);  // MMA issue
+      }
+      if (last_in_chunk && cl >= 1) drain(gc + cl - 1);
+      PHASE(7);  // drain
+    }
+    drain(gc + n_chunks - 1);
+    gc += n_chunks;
+    PHASE(8);  // final drain
+
+    // ---- epilogue: registers -> (bias, ReLU, mask) -> 32x33 smem transpose -> 128-byte row stores ----
+    {
+      const int m = m0 + (warp & 3) * 32 + lane;               // the row this thread accumulated
+      float* stg = staging + warp * (32 * 33);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+          const int col = n0 + c0 + lane;                      // the column this lane stores
+          const int word = (n0 + c0) >> 5;
+          const float bcol = (a.bias && col < a.N) ? __ldg(a.bias + col) : 0.f;
+          uint32_t in_bits = 0xffffffffu, out_bits = 0;
+          if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = acc[32 * q + j] + __shfl_sync(0xffffffffu, bcol, j);
+            if (a.relu) {
+              if (x > 0.f) out_bits |= 1u << j;
+              x = fmaxf(x, 0.f);
+            }
+            if (!((in_bits >> j) & 1u)) x = 0.f;
+            stg[lane * 33 + j] = x;
+          }
+          if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
+          __syncwarp();
+          if (col < a.N) {
+            const int mr0 = m0 + (warp & 3) * 32;
+            float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (mr0 + r < M) cp[(size_t)r * a.ldc] = stg[r * 33 + lane];
+          }
+          __syncwarp();
+        }
+      }
+    }
+    PHASE(9);  // epilogue
+    // every warp is past its TMEM reads (tcgen05 fence inside drain) before the next tile's first
+    // __syncthreads, after which thread 0 may overwrite a region.
+  }
+
+  if (dbg_on)
+    for (int i = 0; i < 12; ++i) a.dbg[i] = phase[i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
+long long* g_dbg = nullptr;
+
+int configure_once() {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return fgs::check_cuda(e, "gemm_w smem attribute");
+    configured = true;
+  }
+  return 0;
+}
+
+// 4-D tensor map of a K-major fp32 plane [rows_alloc][ld]: (4 floats, 8 rows, ld/4 k-chunks,
+// rows_alloc/8 row groups); box = (4, 8, 4, 32) = one 16-wide k-slab of 256 rows, which TMA writes
+// to shared memory as [row group][k-chunk][row % 8][4 floats] -- the canonical UMMA K-major layout.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
+
+int get_map(const float* plane, int rows_alloc, int ld, CUtensorMap* out) {
+  auto key = std::make_tuple((const void*)plane, rows_alloc, ld);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn)
+      return fgs::check_cuda(e != cudaSuccess ? e : cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
+    g_encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t dims[4] = {4, 8, (cuuint64_t)(ld / 4), (cuuint64_t)(rows_alloc / 8)};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 16, (cuuint64_t)ld * 32};   // bytes, dims 1..3
+  const cuuint32_t box[4] = {4, 8, BK / 4, 32};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)plane, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) rows %d ld %d", (int)r,
+             rows_alloc, ld);
+    return FGS_E_BADARG;
+  }
+  g_maps[key] = tm;
+  *out = tm;
+  return 0;
+}
+
+float* g_scratch = nullptr;
+size_t g_scratch_floats = 0;
+
+}  // namespace
+
+namespace fine {
+
+// C[M,N] = A[M,K] * (Bh + Bl)[N,K]^T (+bias, ReLU -> bits_out, masked by bits_in).  Bh/Bl: K-major
+// planes [round_up(N,8)][ldb] (rows >= N and columns >= K zero), 16-byte aligned, ldb % 4 == 0.
+// bits_*: [M][8] words (bit n of row m).
+int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb, float* C,
+           int ldc, const float* bias, int relu, const uint32_t* bits_in, uint32_t* bits_out,
+           const int32_t* rows_dev, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)Bh | (uintptr_t)Bl) & 15))
+    return fgs::fail_arg("gemm_w needs 16-byte aligned operands with leading dimensions % 4 == 0");
+  if (K > ldb) return fgs::fail_arg("gemm_w: K exceeds the weight plane's row length");
+  int rc = configure_once();
+  if (rc) return rc;
+  CUtensorMap tm_hi, tm_lo;
+  const int rows_alloc = (N + 7) & ~7;
+  if ((rc = get_map(Bh, rows_alloc, ldb, &tm_hi))) return rc;
+  if ((rc = get_map(Bl, rows_alloc, ldb, &tm_lo))) return rc;
+  WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, g_dbg};
+  const int n_tiles = fgs::cdiv(M, BM);
+  const int nx = fgs::cdiv(N, 256);
+  int ny = FGS_NUM_SMS / nx;
+  if (ny > n_tiles) ny = n_tiles;
+  if (ny < 1) ny = 1;
+  gemm_w_kernel<<<dim3(nx, ny, 1), kThreads, kSmemBytes, st>>>(a, tm_hi, tm_lo);
+  return fgs::check_launch("gemm_w", st);
+}
+
+// ---- weight splitting ------------------------------------------------------------------------
+int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n > 16) return fgs::fail_arg("at most 16 weight split jobs per launch");
+  SplitJobs J;
+  J.n = n;
+  for (int i = 0; i < n; ++i) {
+    J.j[i].W = jobs[i].W; J.j[i].hi = jobs[i].hi; J.j[i].lo = jobs[i].lo;
+    J.j[i].rows = jobs[i].rows; J.j[i].cols = jobs[i].cols; J.j[i].ld = jobs[i].ld;
+    J.j[i].ld_out = jobs[i].ld_out; J.j[i].transpose = jobs[i].transpose;
+  }
+  weight_split_kernel<<<dim3(32, n), 256, 0, st>>>(J);
+  return fgs::check_launch("weight_split", st);
+}
+
+}  // namespace fine
+
+// Stand-alone entry for tests: B is a plain fp32 matrix ([N][ldb] for mode 0, [K][ldb] for mode 1);
+// it is split into an internal scratch buffer first.
+extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                            float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
+                            uint32_t* bits_out, const int32_t* rows_dev, fgs_stream_t stream) {
+  FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+  FGS_REQUIRE(mode == 0 || mode == 1, "fgs_gemm_tcw: mode must be 0 (B [N][K]) or 1 (B [K][N])");
+  if (M == 0 || N == 0 || K == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kp = (K + 3) & ~3, np = (N + 7) & ~7;
+  const size_t need = 2 * (size_t)np * kp;
+  if (need > g_scratch_floats) {
+    if (g_scratch) {
+      cudaStreamSynchronize(st);
+      cudaFree(g_scratch);
+      g_maps.clear();
+    }
+    int rc = fgs::check_cuda(cudaMalloc(&g_scratch, need * sizeof(float)), "gemm_tcw scratch");
+    if (rc) return rc;
+    g_scratch_floats = need;
+  }
+  int rc = fgs::check_cuda(cudaMemsetAsync(g_scratch, 0, need * sizeof(float), st), "gemm_tcw scratch memset");
+  if (rc) return rc;
+  fine::SplitJobHost job;
+  job.W = B; job.hi = g_scratch; job.lo = g_scratch + (size_t)np * kp;
+  job.ld = ldb; job.ld_out = kp;
+  if (mode == 0) { job.rows = N; job.cols = K; job.transpose = 0; }
+  else { job.rows = K; job.cols = N; job.transpose = 1; }
+  if ((rc = fine::weight_split_jobs(&job, 1, st))) return rc;
+  return fine::gemm_w(M, N, K, A, lda, job.hi, job.lo, kp, C, ldc, bias, relu, bits_in, bits_out, rows_dev, st);
+}
+
+// Debug: device buffer of 12 int64 that the next gemm_w launches fill with per-phase clock cycles of
+// CTA (0,0) (NULL switches it off).
+extern "C" int fgs_debug_gemm_phases(void* buf) {
+  g_dbg = (long long*)buf;
+  return 0;
+}

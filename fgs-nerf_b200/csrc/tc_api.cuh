@@ -1,0 +1,53 @@
+// Internal interface of the tensor-core GEMM translation units (gemm_tc.cu, gemm_tcw.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fgs_b200_fine.h"
+
+namespace fine {
+
+struct SplitJobHost {
+  const float* W; float* hi; float* lo;
+  int rows, cols, ld, ld_out, transpose;  // transpose: out[c][r] (ld_out >= rows) else out[r][c]
+};
+// hi / lo TF32 planes of up to 16 weight matrices in one launch (gemm_tcw.cu)
+int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st);
+
+// C[M,N] = A[M,K] * (Bh + Bl)[N,K]^T (+bias, ReLU -> bits_out, masked by bits_in)   (gemm_tcw.cu)
+int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb, float* C,
+           int ldc, const float* bias, int relu, const uint32_t* bits_in, uint32_t* bits_out,
+           const int32_t* rows_dev, cudaStream_t st);
+
+// generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
+int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+            int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
+            const int32_t* rows_dev, cudaStream_t st);
+
+// Layout of FgsFineParams::w_split: per layer the straight planes [out][in_ld] (forward) and the
+// transposed planes [in_ld][ldt] (backward-data), hi then lo.
+struct WSplitLayout {
+  size_t hi[FGS_MLP_LAYERS], lo[FGS_MLP_LAYERS], thi[FGS_MLP_LAYERS], tlo[FGS_MLP_LAYERS];
+  int in_ld[FGS_MLP_LAYERS], out[FGS_MLP_LAYERS], ldt[FGS_MLP_LAYERS];
+  size_t total;
+};
+inline WSplitLayout wsplit_layout() {
+  WSplitLayout L;
+  const int in_ld[FGS_MLP_LAYERS] = {FGS_X0_LD, 256, 256, 256, FGS_XR_LD, 256, 256, 256};
+  size_t o = 0;
+  for (int l = 0; l < FGS_MLP_LAYERS; ++l) {
+    L.in_ld[l] = in_ld[l];
+    L.out[l] = (l == FGS_MLP_LAYERS - 1) ? 3 : FGS_MLP_WIDTH;
+    L.ldt[l] = (l == FGS_MLP_LAYERS - 1) ? 4 : FGS_MLP_WIDTH;
+    // straight planes are allocated with the row count rounded up to 8 (TMA row groups)
+    const size_t s = (size_t)((L.out[l] + 7) & ~7) * in_ld[l], t = (size_t)in_ld[l] * L.ldt[l];
+    L.hi[l] = o; o += s;
+    L.lo[l] = o; o += s;
+    L.thi[l] = o; o += t;
+    L.tlo[l] = o; o += t;
+  }
+  L.total = o;
+  return L;
+}
+
+}  // namespace fine

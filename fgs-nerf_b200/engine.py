@@ -57,6 +57,7 @@ class FgsFineParams(C.Structure):
         ("normal_marched", _fp), ("counters", _fp),
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
+        ("w_split", _fp), ("hbits", _fp),
     ]
 
 
@@ -87,6 +88,11 @@ _GEMM_SIG = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp
 _lib.declare("fgs_gemm", C.c_int, _GEMM_SIG)
 _lib.declare("fgs_gemm_tc", C.c_int, _GEMM_SIG)
 _lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
+_lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
+_lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
+_lib.declare("fgs_gemm_tcw", C.c_int,
+             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
+              _fp, _fp, _fp, _fp])
 
 
 def set_gemm_backend(tensor_core=True):
@@ -134,7 +140,8 @@ def grid_sample_backward(grid_shape, channels_last, xyz, xyz_min, xyz_max, grad_
     return grad_grid
 
 
-def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None, tc=False):
+def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None, tc=False,
+         bits_in=None, bits_out=None):
     """fgs_gemm / fgs_gemm_tc on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
     if mode == 0:
         m, k = A.shape; n = B.shape[0]
@@ -143,6 +150,11 @@ def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, 
     else:
         k, m = A.shape; n = B.shape[1]
     M, N, K = M or m, N or n, K or k
+    if tc == "w":
+        assert relu_mask is None
+        check(lib.fgs_gemm_tcw(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
+                               ptr(bias), int(relu), ptr(bits_in), ptr(bits_out), ptr(rows_dev), stream()))
+        return out
     check((lib.fgs_gemm_tc if tc else lib.fgs_gemm)(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
                        ptr(bias), int(relu), ptr(relu_mask), relu_mask.stride(0) if relu_mask is not None else 0,
                        ptr(rows_dev), stream()))
@@ -231,6 +243,8 @@ class FineStepEngine:
         ws["dXR"], ws["dX0"] = e(self.cap_m2, XR_LD), e(self.cap_m2, X0_LD)
         for k in ("rgb_marched", "sigmoid_rgb", "normal_marched"):
             ws[k] = e(N, 3)
+        ws["w_split"] = torch.zeros(int(lib.fgs_fine_wsplit_floats()), dtype=f32, device=dev)
+        ws["hbits"] = e(6, self.cap_m2, 8, dt=i32)
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
         ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
         self.tv_scratch = None
@@ -266,7 +280,7 @@ class FineStepEngine:
                   "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
                   "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
                   "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
-                  "dX0", "dlogit"):
+                  "dX0", "dlogit", "w_split", "hbits"):
             setattr(P, k, ptr(ws[k]))
 
     def s_val(self, global_step):

@@ -117,7 +117,14 @@ typedef struct FgsFineParams {
   float *dXR;      /* [cap_m2][FGS_XR_LD]      */
   float *dX0;      /* [cap_m2][FGS_X0_LD]      */
   float *dlogit;   /* [cap_m2][4]              */
+  /* ---- tensor-core MLP workspace ---- */
+  float *w_split;    /* fgs_fine_wsplit_floats() floats: hi / lo TF32 planes of the 8 weight matrices,
+                        straight and transposed; rewritten by every fgs_fine_forward; zero-initialised */
+  uint32_t *hbits;   /* [6][cap_m2][8] ReLU masks of the hidden activations, 1 bit per unit */
 } FgsFineParams;
+
+/* size of FgsFineParams::w_split in floats */
+int64_t fgs_fine_wsplit_floats(void);
 
 /* forward_fine: sampling -> MaskCache -> SDF/gradient/alpha -> weights -> features -> rgbnet ->
  * refnet -> compositing.  Fills the per-ray outputs, counters and every saved intermediate. */
@@ -180,6 +187,17 @@ int fgs_gemm(int mode, int M, int N, int K, const float* A, int lda, const float
 int fgs_gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
                 const int32_t* rows_dev, fgs_stream_t stream);
+
+/* modes 0 / 1 with the weight operand B split once into TF32 hi / lo planes (internal scratch) and
+ * streamed with cp.async -- the kernel the fused step uses for X*W^T and dZ*W.  bits_out (mode 0,
+ * relu) receives the ReLU mask as [M][8] words; bits_in (may be NULL) masks the result. */
+int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                 float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
+                 uint32_t* bits_out, const int32_t* rows_dev, fgs_stream_t stream);
+
+/* Debug aid: 10 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock
+ * cycles CTA (0,0) spent per pipeline phase (NULL = off). */
+int fgs_debug_gemm_phases(void* buf);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);

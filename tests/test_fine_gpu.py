@@ -43,20 +43,19 @@ def _close(a, b, what, rtol=RTOL, atol_frac=1e-5):
 
 
 def _close_grad(a, b, what, rtol=RTOL):
-    """Gradient tensors: the 1e-4 bar is on the tensor, ||a-b||_2 <= 1e-4 ||b||_2, and 99.9% of the
-    entries must agree element-wise.  Why not max-norm: a ReLU unit whose pre-activation is within
-    fp32 rounding noise of 0 legitimately takes different branches in two fp32 GEMM implementations
-    (cuBLAS vs ours, or cuBLAS on another GPU); one such unit among the ~2e7 of a batch moves ONE
-    sample's contribution to a heavily cancelling gradient sum, i.e. a few entries by ~1e-3 of the
-    tensor maximum (tools/tc_diag.py measures exactly one switched unit at config 1)."""
+    """Gradient tensors: the 1e-4 bar is on the tensor, ||a-b||_2 <= 1e-4 ||b||_2.
+    Why not element-wise / max-norm: a ReLU unit whose pre-activation is within fp32 rounding
+    noise of 0 legitimately takes different branches in two fp32 GEMM implementations (cuBLAS vs
+    ours, or cuBLAS on another GPU).  One such unit among the ~2e7 of a batch changes ONE sample's
+    back-propagated signal through every earlier layer, i.e. it perturbs every entry of the
+    earlier weight gradients by about 1/M2 of their scale (tools/tc_diag.py finds exactly one
+    switched unit at config 1, between our own SIMT-fp32 and tensor-core backends as well).  So:
+    relative L2 <= 1e-4, and no entry off by more than 2e-3 of the tensor's largest entry."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     l2 = float((a - b).norm() / b.norm().clamp_min(1e-300))
-    assert l2 <= rtol, f"{what}: relative L2 error {l2:.3e} > {rtol}"
-    scale = float(b.abs().max())
-    bad = (a - b).abs() > 1e-5 * scale + rtol * b.abs()
-    assert float(bad.double().mean()) < 1e-3, f"{what}: {int(bad.sum())}/{a.numel()} entries outside rtol {rtol}"
-    mx = float((a - b).abs().max()) / scale
+    mx = float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    assert l2 <= rtol, f"{what}: relative L2 error {l2:.3e} > {rtol} (max-norm {mx:.3e})"
     assert mx < 2e-3, f"{what}: max abs err {mx:.3e} of max|ref|"
 
 
@@ -310,7 +309,7 @@ def test_gemm_tensor_core_3xtf32(cuda, mode, M, N, K):
     torch.cuda.synchronize()
     err = _rel(out[:, :N], want)
     print(f"tc gemm mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
-    assert err < 1e-5, err
+    assert err < 2e-6, err
     if mode != 2:
         g = torch.Generator(device="cpu").manual_seed(1)
         bias = torch.randn(N, generator=g).to(cuda)
@@ -343,3 +342,48 @@ def test_simt_backend_agrees_with_tensor_core_backend(cuda):
         engine.set_gemm_backend(True)
     for a, b, n in zip(res[0], res[1], ("rgb_marched", "g_sdf", "g_k0", "gW0", "gW4")):
         assert _rel(a, b) < 2e-5, (n, _rel(a, b))
+
+
+@pytest.mark.parametrize("mode,M,N,K", [
+    (0, 300, 256, 112), (0, 129, 3, 256), (0, 40000, 256, 320), (0, 128, 256, 16), (0, 5, 16, 4),
+    (1, 257, 320, 256), (1, 100, 256, 3), (1, 30000, 112, 256), (0, 19000, 256, 256)])
+def test_gemm_presplit_weights_kernel(cuda, mode, M, N, K):
+    """fgs_gemm_tcw = the kernel the fused step runs for X*W^T and dZ*W: weights pre-split into TF32
+    hi/lo planes and streamed with cp.async, persistent CTAs over the sample tiles, ReLU masks as bits."""
+    from fgs_nerf_b200 import engine
+    A, B, want = _tc_case(cuda, mode, M, N, K, mode * 104729 + M + N + K)
+    ldc = (N + 3) // 4 * 4
+    out = torch.zeros(M, ldc, device=cuda)
+    rows = torch.tensor([M], dtype=torch.int32, device=cuda)
+    engine.gemm(mode, A, B, out, rows_dev=rows, M=M, N=N, K=K, tc="w")
+    torch.cuda.synchronize()
+    err = _rel(out[:, :N], want)
+    print(f"tcw gemm mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
+    assert err < 2e-6, err
+    # bias + ReLU with mask bits out, device-side row count below the launch extent
+    g = torch.Generator(device="cpu").manual_seed(2)
+    bias = torch.randn(N, generator=g).to(cuda)
+    half = M // 2
+    rows.fill_(half)
+    out.fill_(7.0)
+    if N == 256:
+        bits = torch.zeros(M, 8, dtype=torch.int32, device=cuda)
+        engine.gemm(mode, A, B, out, bias=bias, relu=True, rows_dev=rows, M=M, N=N, K=K, tc="w", bits_out=bits)
+        torch.cuda.synchronize()
+        pre = want + bias.double()
+        assert bool((out[half:, :N] == 7.0).all()), "rows beyond the device-side row count were written"
+        assert _rel(out[:half, :N], torch.relu(pre[:half])) < 2e-6
+        # mask bits == (out > 0)
+        unpacked = ((bits[:half].long().unsqueeze(-1) >> torch.arange(32, device=cuda)) & 1).reshape(half, 256).bool()
+        assert torch.equal(unpacked, out[:half, :N] > 0)
+        # and applied as an input mask
+        out2 = torch.zeros(M, ldc, device=cuda)
+        engine.gemm(mode, A, B, out2, rows_dev=rows, M=M, N=N, K=K, tc="w", bits_in=bits)
+        torch.cuda.synchronize()
+        assert _rel(out2[:half, :N], want[:half] * unpacked) < 2e-6
+    else:
+        engine.gemm(mode, A, B, out, bias=bias, rows_dev=rows, M=M, N=N, K=K, tc="w")
+        torch.cuda.synchronize()
+        assert bool((out[half:, :N] == 7.0).all())
+        if half:
+            assert _rel(out[:half, :N], (want + bias.double())[:half]) < 2e-6
