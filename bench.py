@@ -225,15 +225,17 @@ def run_ours(args):
 
     # ---- per-launch timing of one more K steps (device events between launches) ----
     prof = {}
-    if rank == 0:
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()                 # every rank runs these steps (they contain the all-reduce);
+    if rank == 0:                            # only rank 0 records the per-launch events
         _lib.prof_begin()
-        for i in range(args.steps):
-            step_resident(it + i)
+    for i in range(args.steps):
+        step_resident(it + i)
+    if rank == 0:
         rows = _lib.prof_end()
         for name, t in rows:
             a = prof.setdefault(name, [0.0, 0])
             a[0] += t; a[1] += 1
+    torch.cuda.synchronize()
     it += args.steps
     if world > 1:
         dist.barrier()

@@ -34,6 +34,7 @@ _SIGS = {
     "fgs_prof_end": (_i, []),
     "fgs_prof_get": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "fgs_memset_zero": (_i, [_p, _l, _p]),
+    "fgs_prof_mark": (_i, [_i, _p]),
     "fgs_infer_t_minmax": (_i, [_p, _p, _p, _p, _f, _f, _i, _p, _p, _p]),
     "fgs_infer_n_samples": (_i, [_p, _p, _p, _f, _i, _p, _p]),
     "fgs_infer_ray_start_dir": (_i, [_p, _p, _p, _i, _p, _p, _p]),

@@ -73,6 +73,13 @@ int fgs_prof_get(int i, const char** name, float* ms) {
   return fgs::check_cuda(cudaEventElapsedTime(ms, fgs::g_ev[i], fgs::g_ev[i + 1]), "prof elapsed");
 }
 
+// mark a non-library launch (e.g. an NCCL collective enqueued by the host) in the timing stream
+int fgs_prof_mark(int what, fgs_stream_t stream) {
+  static const char* names[] = {"other", "allreduce", "h2d copy", "d2h copy"};
+  fgs::prof_mark(names[(what >= 0 && what < 4) ? what : 0], (cudaStream_t)stream);
+  return 0;
+}
+
 int fgs_memset_zero(void* ptr, int64_t bytes, fgs_stream_t stream) {
   if (bytes <= 0) return 0;
   int rc = fgs::check_cuda(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream), "memset");

@@ -452,15 +452,9 @@ class FineStepEngine:
         """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink)."""
         if self.world_size == 1:
             return
-        import torch.distributed as dist
-        dist.all_reduce(self.g_sdf)
-        dist.all_reduce(self.g_k0)
-        flat = torch.cat([g.reshape(-1) for g in self.gW + self.gB])
-        dist.all_reduce(flat)
-        o = 0
-        for g in self.gW + self.gB:
-            g.copy_(flat[o:o + g.numel()].view_as(g))
-            o += g.numel()
+        from .dist import all_reduce_sum_
+        all_reduce_sum_([self.g_sdf, self.g_k0] + self.gW + self.gB)
+        lib.fgs_prof_mark(1, stream())
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True):

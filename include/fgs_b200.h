@@ -45,6 +45,9 @@ int fgs_device_sm_count(int device, int* sm_count, int* cc_major, int* cc_minor)
 int fgs_prof_begin(fgs_stream_t stream);
 int fgs_prof_end(void);
 int fgs_prof_get(int i, const char** name, float* ms);
+/* record a host-enqueued, non-library operation in the same timing stream: what = 1 all-reduce,
+ * 2 H2D copy, 3 D2H copy, 0 other */
+int fgs_prof_mark(int what, fgs_stream_t stream);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (grad buffers are cleared through the library so the
  * clears show up in the launch timing above). */
 int fgs_memset_zero(void* ptr, int64_t bytes, fgs_stream_t stream);
