@@ -160,6 +160,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from fgs_nerf_b200 import _lib, engine, scene
 

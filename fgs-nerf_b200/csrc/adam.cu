@@ -187,3 +187,143 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
 }
 
 }  // extern "C"
+
+// ---- fused-step optimiser kernels ---------------------------------------------------------------
+// Same arithmetic as above (adam_elem), different traffic:
+//  * adam_dense_zero_kernel: dense Adam that also clears the gradient it has just consumed, so the
+//    next step needs no separate memset pass over the grid (32 B/param instead of 28 + 4 + launch).
+//  * adam_bricks_kernel: MASKED Adam driven by the touched-brick flags that the backward scatter
+//    leaves behind (1 byte per 4x4x4-voxel brick).  The reference's masked_adam_upd reads the whole
+//    gradient grid to find the few percent of voxels with grad != 0 (model/adam.py:211-214,
+//    adam_upd_kernel.cu:25-40) after a full-size zero fill; here only flagged bricks are read, the
+//    per-element `grad != 0` test of the reference is kept inside them (bit-identical p, m, v), and
+//    the consumed gradients and flags are cleared on the way out.
+namespace {
+
+__global__ void __launch_bounds__(kBlock)
+adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ exp_avg,
+                       float* __restrict__ exp_avg_sq, long long n, AdamConst c) {
+  const long long n4 = n >> 2;
+  const long long tid = blockIdx.x * (long long)kBlock + threadIdx.x;
+  const long long nth = (long long)gridDim.x * kBlock;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 g = ld_stream4(grad + 4 * i);
+    float4 p = ld4(param + 4 * i), m = ld4(exp_avg + 4 * i), v = ld4(exp_avg_sq + 4 * i);
+    adam_elem(p.x, g.x, m.x, v.x, c, c.step_size);
+    adam_elem(p.y, g.y, m.y, v.y, c, c.step_size);
+    adam_elem(p.z, g.z, m.z, v.z, c, c.step_size);
+    adam_elem(p.w, g.w, m.w, v.w, c, c.step_size);
+    st4(param + 4 * i, p);
+    st4(exp_avg + 4 * i, m);
+    st4(exp_avg_sq + 4 * i, v);
+    st4(grad + 4 * i, z4);
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) {
+    float p = param[i], m = exp_avg[i], v = exp_avg_sq[i];
+    adam_elem(p, grad[i], m, v, c, c.step_size);
+    param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v; grad[i] = 0.f;
+  }
+}
+
+// touched-brick list: one thread per brick flag, warp-aggregated append, flags cleared on the way.
+// list[0] = count, list[1..] = brick ids (order irrelevant).
+__global__ void __launch_bounds__(kBlock)
+brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ list) {
+  const int b = blockIdx.x * kBlock + threadIdx.x;
+  const bool f = (b < n_bricks) && flags[b];
+  if (f) flags[b] = 0;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (m == 0) return;
+  int base = 0;
+  if (lane_id() == __ffs(m) - 1) base = atomicAdd(list, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (f) list[1 + base + __popc(m & ((1u << lane_id()) - 1))] = b;
+}
+
+// grid layout [X][Y][Z][12] (channels-last); brick b = ((x>>2)*nbY + (y>>2))*nbZ + (z>>2).
+// One warp per listed brick: 16 (x,y) rows of 4 z-voxels x 12 channels = 192 float4 = 6 per lane,
+// all gradient loads issued before any dependent work.
+__global__ void __launch_bounds__(kBlock)
+adam_bricks_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ exp_avg,
+                   float* __restrict__ exp_avg_sq, const int* __restrict__ list, int X, int Y, int Z, AdamConst c) {
+  const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
+  const int lane = lane_id();
+  const int wpb = kBlock / 32;
+  const int count = list[0];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < count; e += gridDim.x * wpb) {
+    const int br = list[1 + e];
+    const int bz = br % nbZ, by = (br / nbZ) % nbY, bx = br / (nbZ * nbY);
+    size_t off[6];
+    float4 g[6];
+    bool ok[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int q = lane + 32 * i;
+      const int row = q / 12, f4 = q - row * 12;
+      const int x = 4 * bx + (row >> 2), y = 4 * by + (row & 3), z = 4 * bz + f4 / 3;
+      ok[i] = x < X && y < Y && z < Z;
+      off[i] = (((size_t)x * Y + y) * Z + 4 * bz) * 12 + 4 * f4;
+      g[i] = ok[i] ? ld4(grad + off[i]) : z4;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (ok[i] && (g[i].x != 0.f || g[i].y != 0.f || g[i].z != 0.f || g[i].w != 0.f)) {
+        float4 p = ld4(param + off[i]), m = ld4(exp_avg + off[i]), v = ld4(exp_avg_sq + off[i]);
+        if (g[i].x != 0.f) adam_elem(p.x, g[i].x, m.x, v.x, c, c.step_size);
+        if (g[i].y != 0.f) adam_elem(p.y, g[i].y, m.y, v.y, c, c.step_size);
+        if (g[i].z != 0.f) adam_elem(p.z, g[i].z, m.z, v.z, c, c.step_size);
+        if (g[i].w != 0.f) adam_elem(p.w, g[i].w, m.w, v.w, c, c.step_size);
+        st4(param + off[i], p);
+        st4(exp_avg + off[i], m);
+        st4(exp_avg_sq + off[i], v);
+        st4(grad + off[i], z4);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
+                           float beta1, float beta2, float lr, float eps, fgs_stream_t stream) {
+  FGS_REQUIRE(n >= 0, "n < 0");
+  FGS_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq),
+              "fgs_adam_upd_zero_grad needs 16-byte aligned tensors");
+  if (n == 0) return 0;
+  AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
+  adam_dense_zero_kernel<<<fgs::stream_grid((n + 3) / 4, kBlock, 8), kBlock, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, c);
+  return fgs::check_launch("adam_dense_zero", (cudaStream_t)stream);
+}
+
+int64_t fgs_brick_list_ints(int X, int Y, int Z) {
+  return 1 + (int64_t)((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
+}
+
+// brick_flags -> brick_list (count + ids), flags cleared
+int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_list, fgs_stream_t stream) {
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "bad grid size");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_bricks = ((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
+  int rc = fgs::check_cuda(cudaMemsetAsync(brick_list, 0, sizeof(int32_t), st), "brick list memset");
+  if (rc) return rc;
+  brick_list_kernel<<<fgs::cdiv(n_bricks, kBlock), kBlock, 0, st>>>(brick_flags, n_bricks, brick_list);
+  return fgs::check_launch("brick_list", st);
+}
+
+int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int32_t* brick_list,
+                        int X, int Y, int Z, int channels, int step, float beta1, float beta2, float lr,
+                        float eps, fgs_stream_t stream) {
+  FGS_REQUIRE(channels == 12, "brick Adam is specialised for the 12-channel channels-last k0 grid");
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick Adam needs Z % 4 == 0");
+  AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
+  adam_bricks_kernel<<<FGS_NUM_SMS * 8, kBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
+                                                                          brick_list, X, Y, Z, c);
+  return fgs::check_launch("adam_bricks", (cudaStream_t)stream);
+}
+
+}  // extern "C"

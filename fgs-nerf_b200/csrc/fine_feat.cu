@@ -184,10 +184,17 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
     {
       const Tri t = tri_setup(iw, ih, id);
       const float4 d0 = ld4(drow + FGS_X0_K0), d1 = ld4(drow + FGS_X0_K0 + 4), d2 = ld4(drow + FGS_X0_K0 + 8);
+      const int nbY = (g.Y + 3) >> 2, nbZ = (g.Z + 3) >> 2;
+      int last_brick = -1;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
         if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
+          if (P.k0_brick_flags) {   // touched-brick flag for the sparse masked Adam / gradient exchange
+            const int brick = ((z >> 2) * nbY + (y >> 2)) * nbZ + (x >> 2);
+            if (brick != last_brick) P.k0_brick_flags[brick] = 1;
+            last_brick = brick;
+          }
           float* v = P.g_k0 + (((size_t)z * g.Y + y) * g.Z + x) * FGS_K0_DIM;
           const float w = t.w[c];
           red_add_v4(v, w * d0.x, w * d0.y, w * d0.z, w * d0.w);

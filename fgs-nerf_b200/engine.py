@@ -57,7 +57,7 @@ class FgsFineParams(C.Structure):
         ("normal_marched", _fp), ("counters", _fp),
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
-        ("w_split", _fp), ("hbits", _fp),
+        ("w_split", _fp), ("hbits", _fp), ("k0_brick_flags", _fp),
     ]
 
 
@@ -245,6 +245,11 @@ class FineStepEngine:
             ws[k] = e(N, 3)
         ws["w_split"] = torch.zeros(int(lib.fgs_fine_wsplit_floats()), dtype=f32, device=dev)
         ws["hbits"] = e(6, self.cap_m2, 8, dt=i32)
+        nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
+        ws["k0_brick_flags"] = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        ws["k0_brick_list"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)), dtype=i32, device=dev)
+        self.sparse_k0 = (Z % 4 == 0)      # brick-driven masked Adam (else the dense reference-style scan)
+        self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
         ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
         self.tv_scratch = None
@@ -280,7 +285,7 @@ class FineStepEngine:
                   "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
                   "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
                   "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
-                  "dX0", "dlogit", "w_split", "hbits"):
+                  "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags"):
             setattr(P, k, ptr(ws[k]))
 
     def s_val(self, global_step):
@@ -364,10 +369,15 @@ class FineStepEngine:
         return t["tv_from"] < global_step < t["tv_end"] and global_step % t["tv_every"] == 0
 
     def zero_grad(self):
+        """optimizer.zero_grad(): a no-op when the optimiser kernels already cleared what they consumed."""
+        if self._grads_clean:
+            return
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
             check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
+            check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
+        self._grads_clean = True
 
     def loss_backward(self, target, n_rays_global=None, has_last_ray=True):
         """Loss block + backward (model/nerf_training.py:307-347); grads of the MLPs are overwritten,
@@ -384,6 +394,7 @@ class FineStepEngine:
         L.g_alphainv_last = ptr(self.ws["g_alphainv_last"])
         L.loss_out = ptr(self.ws["loss"])
         self.ws["loss"].zero_()
+        self._grads_clean = False
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
@@ -436,11 +447,23 @@ class FineStepEngine:
         with torch.cuda.device(self.device):
             st = stream()
             m, v = self.adam["sdf"]
-            check(lib.fgs_adam_upd(ptr(self.sdf), ptr(self.g_sdf), ptr(m), ptr(v), None, self.sdf.numel(), step,
-                                   b1, b2, t["lrate_sdf"] * lr_scale, eps, 0, st))
+            # sdf: dense Adam (not in skip_zero_grad_fields), gradient cleared by the same kernel
+            check(lib.fgs_adam_upd_zero_grad(ptr(self.sdf), ptr(self.g_sdf), ptr(m), ptr(v), self.sdf.numel(), step,
+                                             b1, b2, t["lrate_sdf"] * lr_scale, eps, st))
             m, v = self.adam["k0"]
-            check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
-                                   b1, b2, t["lrate_k0"] * lr_scale, eps, 1, st))
+            if self.sparse_k0:
+                # k0: masked Adam over the touched bricks only; clears the gradients / flags it consumed
+                check(lib.fgs_brick_list(ptr(self.ws["k0_brick_flags"]), self.X, self.Y, self.Z,
+                                         ptr(self.ws["k0_brick_list"]), st))
+                check(lib.fgs_adam_upd_bricks(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), ptr(self.ws["k0_brick_list"]),
+                                              self.X, self.Y, self.Z, K0_DIM, step, b1, b2, t["lrate_k0"] * lr_scale,
+                                              eps, st))
+            else:
+                check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
+                                       b1, b2, t["lrate_k0"] * lr_scale, eps, 1, st))
+                check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
+                check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
+            self._grads_clean = True
             n = 2 * MLP_LAYERS
             lrs = [t["lrate_rgbnet"]] * 4 + [t["lrate_refnet"]] * 4
             lrs = (C.c_float * n)(*[x * lr_scale for x in lrs + lrs])
@@ -452,8 +475,10 @@ class FineStepEngine:
         """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink)."""
         if self.world_size == 1:
             return
+        import torch.distributed as dist
         from .dist import all_reduce_sum_
         all_reduce_sum_([self.g_sdf, self.g_k0] + self.gW + self.gB)
+        dist.all_reduce(self.ws["k0_brick_flags"], op=dist.ReduceOp.MAX)   # union of the touched bricks
         lib.fgs_prof_mark(1, stream())
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,

@@ -145,6 +145,23 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
                        const int* steps, const float* lrs, float beta1, float beta2, float eps,
                        fgs_stream_t stream);
 
+/* Fused-step variants (same arithmetic, less traffic):
+ *  fgs_adam_upd_zero_grad : dense adam_upd that also clears the consumed gradient (no memset pass);
+ *  fgs_brick_list         : compacts the touched-brick flags that fgs_fine_backward leaves behind (one
+ *      byte per 4x4x4-voxel brick of k0, [ceil(X/4)*ceil(Y/4)*ceil(Z/4)]) into brick_list
+ *      (fgs_brick_list_ints() ints: count, then brick ids) and clears the flags;
+ *  fgs_adam_upd_bricks    : masked_adam_upd of a channels-last [X][Y][Z][12] grid restricted to the
+ *      listed bricks, one warp per brick; clears the gradients it consumed.  Identical p, m, v to
+ *      masked_adam_upd provided every voxel with grad != 0 lies in a listed brick. */
+int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           int step, float beta1, float beta2, float lr, float eps,
+                           fgs_stream_t stream);
+int64_t fgs_brick_list_ints(int X, int Y, int Z);
+int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_list, fgs_stream_t stream);
+int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                        const int32_t* brick_list, int X, int Y, int Z, int channels, int step,
+                        float beta1, float beta2, float lr, float eps, fgs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Total variation  (reference: model/cuda/total_variation.cpp:16-32, _kernel.cu:13-133)
  * param/grad: [1,C,X,Y,Z]; channels_last=0 is the reference's contiguous NCDHW layout,

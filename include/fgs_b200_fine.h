@@ -121,6 +121,8 @@ typedef struct FgsFineParams {
   float *w_split;    /* fgs_fine_wsplit_floats() floats: hi / lo TF32 planes of the 8 weight matrices,
                         straight and transposed; rewritten by every fgs_fine_forward; zero-initialised */
   uint32_t *hbits;   /* [6][cap_m2][8] ReLU masks of the hidden activations, 1 bit per unit */
+  uint8_t *k0_brick_flags; /* [ceil(X/4)*ceil(Y/4)*ceil(Z/4)] set to 1 by the backward scatter for every
+                        4x4x4 brick of k0 that received a gradient (may be NULL); see fgs_adam_upd_bricks */
 } FgsFineParams;
 
 /* size of FgsFineParams::w_split in floats */
