@@ -31,18 +31,18 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 16, kThreads = 256;
+constexpr int BM = 128, BK = 32;                    // one k-slab = 32 floats = one 128-byte swizzle row
 constexpr int kTmemCols = 512;
-constexpr uint32_t kATile = BM * BK * 4;             // 8 KB
-constexpr uint32_t kBTile = 256 * BK * 4;            // 16 KB
-constexpr uint32_t kStage = 2 * kATile + 2 * kBTile; // 48 KB: A_hi, A_lo, B_hi, B_lo
-constexpr int kStages = 4;
-constexpr int kChunkSlabs = 2;
+constexpr uint32_t kATile = BM * BK * 4;             // 16 KB
+constexpr uint32_t kBTile = 256 * BK * 4;            // 32 KB
+constexpr uint32_t kStage = 2 * kATile + 2 * kBTile; // 96 KB: A_hi, A_lo, B_hi, B_lo
+constexpr int kStages = 2;
+constexpr int kChunkSlabs = 1;                       // accumulation chunk = one 32-k slab
 constexpr uint32_t kStagingOff = kStages * kStage;             // 8 warps x 32 x 33 floats
 constexpr uint32_t kStagingBytes = 8 * 32 * 33 * 4;
 constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;      // mbarriers + tmem slot
-constexpr uint32_t kSmemBytes = kBarOff + 128;
-constexpr int kPfB = 2;                                        // TMA prefetch distance (slabs)
+constexpr uint32_t kSmemBytes = kBarOff + 256;
+constexpr int kPfB = 1;                                        // TMA prefetch distance (slabs)
 
 struct WArgs {
   const float* A; float* C;
@@ -68,8 +68,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   if (!done) __trap();  // a phase bug must surface as an error, never as a hung GPU
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {  // K-major, no swizzle, LBO 128, SBO 512
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row (1024-byte) swizzle
+// atoms (SBO 1024), 16-byte chunk c of row r stored at chunk position c ^ (r % 8); layout_type = 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -93,11 +96,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
                : "memory");
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -124,26 +126,32 @@ __global__ void __launch_bounds__(256) weight_split_kernel(const __grid_constant
   }
 }
 
-#define PHASE(i)                                              \
-  do {                                                        \
-    if (dbg_on) {                                             \
-      const long long t_now = clock64();                      \
-      phase[i] += t_now - t_last;                             \
-      t_last = t_now;                                         \
-    }                                                         \
-  } while (0)
+constexpr int kWorkers = 256;            // warps 0-7: A producers, TMEM drain, epilogue
+constexpr int kThreadsWS = kWorkers + 128; // third warpgroup: warp 8 lane 0 issues TMA (B) and tcgen05.mma;
+                                           // registers are re-balanced with setmaxnreg (40 vs 232 per thread)
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised: the MMA/TMA thread and the 256 workers only meet at mbarriers
+//   a_full[st]   workers -> MMA   (256 arrivals: the A hi/lo slab is stored and proxy-fenced)
+//   b_full[st]   TMA     -> MMA   (expect_tx: B hi/lo bytes landed)
+//   free[st]     MMA     -> all   (tcgen05.commit: the MMAs reading the stage are done)
+//   r_full[r]    MMA     -> workers (tcgen05.commit at the end of a 32-k chunk)
+//   r_empty[r]   workers -> MMA   (256 arrivals: the chunk has been added into registers)
+// so the blocking MMA issue never stalls the producers, and the producers run up to kStages slabs
+// ahead of the tensor core.
+__global__ void __launch_bounds__(kThreadsWS, 1)
 gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
-  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-  long long phase[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long t_last = dbg_on ? clock64() : 0;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
-  const uint32_t free_bar0 = smem + kBarOff;                 // kStages: MMAs done reading the stage
-  const uint32_t bfull_bar0 = free_bar0 + 8 * kStages;       // kStages: TMA bytes of B landed
-  const uint32_t region_bar0 = bfull_bar0 + 8 * kStages;     // 2: accumulation chunk finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (2 * kStages + 2) + 8);
+  const uint32_t free_bar0 = smem + kBarOff;
+  const uint32_t bfull_bar0 = free_bar0 + 8 * kStages;
+  const uint32_t afull_bar0 = bfull_bar0 + 8 * kStages;
+  const uint32_t rfull_bar0 = afull_bar0 + 8 * kStages;
+  const uint32_t rempty_bar0 = rfull_bar0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (3 * kStages + 4) + 8);
   float* staging = reinterpret_cast<float*>(smem_raw + kStagingOff);
 
   int M = a.M;
@@ -162,7 +170,15 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int i = 0; i < 2 * kStages + 2; ++i) mbar_init(free_bar0 + 8 * i, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(free_bar0 + 8 * i, 1);
+      mbar_init(bfull_bar0 + 8 * i, 1);
+      mbar_init(afull_bar0 + 8 * i, kWorkers);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(rfull_bar0 + 8 * i, 1);
+      mbar_init(rempty_bar0 + 8 * i, kWorkers);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -176,185 +192,181 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
   const int n_chunks = (n_slabs + kChunkSlabs - 1) / kChunkSlabs;
   const int my_tiles = (n_tiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1;
   const uint32_t total_slabs = (uint32_t)my_tiles * (uint32_t)n_slabs;
-  const int col_half = (warp >> 2) * 128;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  // A slots: thread -> row ar, 16-byte k-chunks ac and ac + 2 (a quarter-warp = 8 consecutive rows of
-  // one core-matrix column = 128 contiguous bytes of shared memory)
-  const int ar = tid & 127, ac = tid >> 7;
-  const uint32_t aoff = (uint32_t)((ar >> 3) * 512 + ac * 128 + (ar & 7) * 16);
 
-  // B of global slab gs (tile-independent: coordinates are (k-chunk, row-group) of the weight plane)
-  auto issue_b = [&](uint32_t gs) {
-    const uint32_t st = gs % kStages;
-    const uint32_t b_hi = smem + st * kStage + 2 * kATile, b_lo = b_hi + kBTile;
-    const uint32_t bar = bfull_bar0 + 8 * st;
-    const int kc = (int)(gs % (uint32_t)n_slabs) * (BK / 4);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBTile) : "memory");
-    tma_load_4d(b_hi, &tm_hi, bar, 0, 0, kc, n0 >> 3);
-    tma_load_4d(b_lo, &tm_lo, bar, 0, 0, kc, n0 >> 3);
-  };
-  if (tid == 32) {
-    for (uint32_t gs = 0; gs < (uint32_t)kPfB && gs < total_slabs; ++gs) issue_b(gs);
-  }
-  PHASE(0);  // setup
-
-  uint32_t g = 0;   // slabs issued by this CTA so far (stage ring position / mbarrier phases)
-  uint32_t gc = 0;  // accumulation chunks issued so far (TMEM region ring / phases)
-
-  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-    const int m0 = tile * BM;
-    float acc[128];
-#pragma unroll
-    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-
-    auto load_a = [&](float4 (&v)[2], int k0) {
-      const int m = m0 + ar;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int k = k0 + 4 * (ac + 2 * i);
-        v[i] = (m < M && k < K) ? ldg4(a.A + (size_t)m * a.lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto store_a = [&](const float4 (&v)[2], uint32_t stage_base) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t off = aoff + (uint32_t)(2 * i) * 128;
-        float4 hi, lo;
-        hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
-        lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
-        lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
-        st_shared_v4(stage_base + off, hi);
-        st_shared_v4(stage_base + kATile + off, lo);
-      }
-    };
-    auto drain = [&](uint32_t c) {   // c = global chunk index
-      mbar_wait(region_bar0 + 8 * (c & 1), (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (col_half + 32 * q < BN) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-
-    float4 a0[2], a1[2];
-    load_a(a0, 0);
-    if (n_slabs > 1) load_a(a1, BK);
-    PHASE(1);  // tile prologue
-
-    for (int kt = 0; kt < n_slabs; ++kt, ++g) {
-      const uint32_t st = g % kStages;
-      const uint32_t stage_base = smem + st * kStage;
-      const int cl = kt / kChunkSlabs;                       // chunk within the tile
-      const bool first_in_chunk = (kt % kChunkSlabs) == 0;
-      const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == n_slabs - 1;
-      if (tid == 32) {
-        // B two slabs ahead (possibly already the next tile's): its stage was read by slab gs - kStages
-        const uint32_t gs = g + kPfB;
-        if (gs < total_slabs) {
-          if (gs >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
-          issue_b(gs);
-        }
-      }
-      // the stage was last read by the MMAs of slab g - kStages
-      if (g >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * st, ((g / kStages) - 1) & 1);
-      PHASE(10);  // stage wait
-      if (kt & 1) {
-        store_a(a1, stage_base);
-        if (kt + 2 < n_slabs) load_a(a1, (kt + 2) * BK);
-      } else {
-        store_a(a0, stage_base);
-        if (kt + 2 < n_slabs) load_a(a0, (kt + 2) * BK);
-      }
-      PHASE(2);  // A split + store, next A loads issued
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      PHASE(4);  // fence + barrier
-      if (tid == 0) {
-        mbar_wait(bfull_bar0 + 8 * st, (g / kStages) & 1);   // TMA bytes of B(hi, lo) have landed
-        PHASE(3);  // wait for B
+  if (warp >= kWorkers / 32) {
+    // ================= MMA + TMA issuer (one thread of the third warpgroup) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == kWorkers / 32 && lane == 0) {
+      auto issue_b = [&](uint32_t gs) {
+        const uint32_t st = gs % kStages;
+        const uint32_t b_hi = smem + st * kStage + 2 * kATile, b_lo = b_hi + kBTile;
+        const uint32_t bar = bfull_bar0 + 8 * st;
+        const int k0 = (int)(gs % (uint32_t)n_slabs) * BK;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBTile) : "memory");
+        tma_load_2d(b_hi, &tm_hi, bar, k0, n0);
+        tma_load_2d(b_lo, &tm_lo, bar, k0, n0);
+      };
+      for (uint32_t gs = 0; gs < (uint32_t)kPfB && gs < total_slabs; ++gs) issue_b(gs);
+      for (uint32_t g = 0; g < total_slabs; ++g) {
+        const uint32_t st = g % kStages;
+        const uint32_t par = (g / kStages) & 1;
+        const uint32_t kt = g % (uint32_t)n_slabs;
+        const uint32_t cg = (g / (uint32_t)n_slabs) * (uint32_t)n_chunks + kt / kChunkSlabs;  // global chunk
+        const bool first_in_chunk = (kt % kChunkSlabs) == 0;
+        const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == (uint32_t)n_slabs - 1;
+        mbar_wait(afull_bar0 + 8 * st, par);
+        mbar_wait(bfull_bar0 + 8 * st, par);
+        if (first_in_chunk && cg >= 2) mbar_wait(rempty_bar0 + 8 * (cg & 1), ((cg >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t stage_base = smem + st * kStage;
         const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
         const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
-        const uint32_t d = tmem_d + (uint32_t)(((gc + cl) & 1) * 256);
+        const uint32_t d = tmem_d + (cg & 1) * 256;
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * 256), dal = make_desc(a_lo + j * 256);
-          const uint64_t dbh = make_desc(b_hi + j * 256), dbl = make_desc(b_lo + j * 256);
+          // k-step j = bytes [32 j, 32 j + 32) of every 128-byte row (the swizzle is a function of the address)
+          const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+          const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
           mma_tf32(d, dal, dbh, idesc, (!first_in_chunk || j != 0) ? 1u : 0u);
           mma_tf32(d, dah, dbl, idesc, 1);
           mma_tf32(d, dah, dbh, idesc, 1);
         }
         mma_commit(free_bar0 + 8 * st);
-        if (last_in_chunk) mma_commit(region_bar0 + 8 * ((gc + cl) & 1));
-        PHASE(5);  // MMA issue
-      }
-      if (last_in_chunk && cl >= 1) drain(gc + cl - 1);
-      PHASE(7);  // drain
-    }
-    drain(gc + n_chunks - 1);
-    gc += n_chunks;
-    PHASE(8);  // final drain
-
-    // ---- epilogue: registers -> (bias, ReLU, mask) -> 32x33 smem transpose -> 128-byte row stores ----
-    {
-      const int m = m0 + (warp & 3) * 32 + lane;               // the row this thread accumulated
-      float* stg = staging + warp * (32 * 33);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c0 = col_half + 32 * q;
-        if (c0 < BN) {
-          const int col = n0 + c0 + lane;                      // the column this lane stores
-          const int word = (n0 + c0) >> 5;
-          const float bcol = (a.bias && col < a.N) ? __ldg(a.bias + col) : 0.f;
-          uint32_t in_bits = 0xffffffffu, out_bits = 0;
-          if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = acc[32 * q + j] + __shfl_sync(0xffffffffu, bcol, j);
-            if (a.relu) {
-              if (x > 0.f) out_bits |= 1u << j;
-              x = fmaxf(x, 0.f);
-            }
-            if (!((in_bits >> j) & 1u)) x = 0.f;
-            stg[lane * 33 + j] = x;
-          }
-          if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
-          __syncwarp();
-          if (col < a.N) {
-            const int mr0 = m0 + (warp & 3) * 32;
-            float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-              if (mr0 + r < M) cp[(size_t)r * a.ldc] = stg[r * 33 + lane];
-          }
-          __syncwarp();
+        if (last_in_chunk) mma_commit(rfull_bar0 + 8 * (cg & 1));
+        const uint32_t gs = g + kPfB;   // B two slabs ahead; its stage was read by slab gs - kStages
+        if (gs < total_slabs) {
+          if (gs >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
+          issue_b(gs);
         }
       }
     }
-    PHASE(9);  // epilogue
-    // every warp is past its TMEM reads (tcgen05 fence inside drain) before the next tile's first
-    // __syncthreads, after which thread 0 may overwrite a region.
+  } else {
+    // ================= workers: A slabs, TMEM drain, epilogue =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    const int col_half = (warp >> 2) * 128;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // A slots: thread -> row ar, 16-byte k-chunks ac, ac + 2, ac + 4, ac + 6 of the 128-byte row; chunk c
+    // of row r lives at chunk position c ^ (r % 8), so the 8 rows of a quarter-warp hit 8 distinct
+    // bank groups
+    const int ar = tid & 127, ac = tid >> 7;
+    const uint32_t arow = (uint32_t)(ar * 128);
+    uint32_t g = 0, gc = 0;
+    long long t_main = 0, t_epi = 0, t0 = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+
+    for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+      const int m0 = tile * BM;
+      if (dbg_on) t0 = clock64();
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+
+      auto load_a = [&](float4 (&v)[4], int k0) {
+        const int m = m0 + ar;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = k0 + 4 * (ac + 2 * i);
+          v[i] = (m < M && k < K) ? ldg4(a.A + (size_t)m * a.lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto store_a = [&](const float4 (&v)[4], uint32_t stage_base) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = arow + (uint32_t)(((ac + 2 * i) ^ (ar & 7)) * 16);
+          float4 hi, lo;
+          hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
+          lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
+          lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
+          st_shared_v4(stage_base + off, hi);
+          st_shared_v4(stage_base + kATile + off, lo);
+        }
+      };
+      auto drain = [&](uint32_t c) {   // c = global chunk index
+        mbar_wait(rfull_bar0 + 8 * (c & 1), (c >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (col_half + 32 * q < BN) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(rempty_bar0 + 8 * (c & 1));   // the region may be overwritten by chunk c + 2
+      };
+
+      float4 a0[4];
+      load_a(a0, 0);
+      for (int kt = 0; kt < n_slabs; ++kt, ++g) {
+        const uint32_t st = g % kStages;
+        const uint32_t stage_base = smem + st * kStage;
+        const int cl = kt / kChunkSlabs;
+        const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == n_slabs - 1;
+        if (g >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * st, ((g / kStages) - 1) & 1);
+        store_a(a0, stage_base);
+        if (kt + 1 < n_slabs) load_a(a0, (kt + 1) * BK);   // in flight during the drain below
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(afull_bar0 + 8 * st);
+        if (last_in_chunk && cl >= 1) drain(gc + cl - 1);
+      }
+      drain(gc + n_chunks - 1);
+      gc += n_chunks;
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+
+      // ---- epilogue: registers -> (bias, ReLU, mask) -> 32x33 smem transpose -> 128-byte row stores ----
+      {
+        const int m = m0 + (warp & 3) * 32 + lane;               // the row this thread accumulated
+        float* stg = staging + warp * (32 * 33);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = col_half + 32 * q;
+          if (c0 < BN) {
+            const int col = n0 + c0 + lane;                      // the column this lane stores
+            const int word = (n0 + c0) >> 5;
+            const float bcol = (a.bias && col < a.N) ? __ldg(a.bias + col) : 0.f;
+            uint32_t in_bits = 0xffffffffu, out_bits = 0;
+            if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = acc[32 * q + j] + __shfl_sync(0xffffffffu, bcol, j);
+              if (a.relu) {
+                if (x > 0.f) out_bits |= 1u << j;
+                x = fmaxf(x, 0.f);
+              }
+              if (!((in_bits >> j) & 1u)) x = 0.f;
+              stg[lane * 33 + j] = x;
+            }
+            if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
+            __syncwarp();
+            if (col < a.N) {
+              const int mr0 = m0 + (warp & 3) * 32;
+              float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r)
+                if (mr0 + r < M) cp[(size_t)r * a.ldc] = stg[r * 33 + lane];
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
+    }
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
   }
 
-  if (dbg_on)
-    for (int i = 0; i < 12; ++i) a.dbg[i] = phase[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -374,9 +386,10 @@ int configure_once() {
   return 0;
 }
 
-// 4-D tensor map of a K-major fp32 plane [rows_alloc][ld]: (4 floats, 8 rows, ld/4 k-chunks,
-// rows_alloc/8 row groups); box = (4, 8, 4, 32) = one 16-wide k-slab of 256 rows, which TMA writes
-// to shared memory as [row group][k-chunk][row % 8][4 floats] -- the canonical UMMA K-major layout.
+// 2-D tensor map of a K-major fp32 plane [rows_alloc][ld]; box = (32 floats, 256 rows) = one k-slab of
+// 256 rows, written to shared memory as 128-byte rows with the 128B swizzle -- the UMMA K-major
+// SWIZZLE_128B layout.  (A first version used a 4-D map producing the no-swizzle core-matrix layout;
+// its 16-byte inner box made TMA the bottleneck: ~1.4 us per 32 KB slab.)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -398,13 +411,13 @@ int get_map(const float* plane, int rows_alloc, int ld, CUtensorMap* out) {
       return fgs::check_cuda(e != cudaSuccess ? e : cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
     g_encode = (EncodeTiledFn)fn;
   }
-  const cuuint64_t dims[4] = {4, 8, (cuuint64_t)(ld / 4), (cuuint64_t)(rows_alloc / 8)};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 16, (cuuint64_t)ld * 32};   // bytes, dims 1..3
-  const cuuint32_t box[4] = {4, 8, BK / 4, 32};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_alloc};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};                           // bytes, dim 1
+  const cuuint32_t box[2] = {BK, 256};
+  const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
-  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)plane, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) rows %d ld %d", (int)r,
@@ -445,7 +458,7 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   int ny = FGS_NUM_SMS / nx;
   if (ny > n_tiles) ny = n_tiles;
   if (ny < 1) ny = 1;
-  gemm_w_kernel<<<dim3(nx, ny, 1), kThreads, kSmemBytes, st>>>(a, tm_hi, tm_lo);
+  gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo);
   return fgs::check_launch("gemm_w", st);
 }
 
@@ -498,8 +511,8 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
   return fine::gemm_w(M, N, K, A, lda, job.hi, job.lo, kp, C, ldc, bias, relu, bits_in, bits_out, rows_dev, st);
 }
 
-// Debug: device buffer of 12 int64 that the next gemm_w launches fill with per-phase clock cycles of
-// CTA (0,0) (NULL switches it off).
+// Debug: device buffer of 2 int64 that the next gemm_w launches fill with the clock cycles worker 0 of
+// CTA (0,0) spent in main loops and in epilogues (NULL switches it off).
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
   return 0;

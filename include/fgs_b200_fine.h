@@ -197,8 +197,8 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
                  float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
                  uint32_t* bits_out, const int32_t* rows_dev, fgs_stream_t stream);
 
-/* Debug aid: 10 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock
- * cycles CTA (0,0) spent per pipeline phase (NULL = off). */
+/* Debug aid: 2 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
+ * worker 0 of CTA (0,0) spent in its main loops and in its epilogues (NULL = off). */
 int fgs_debug_gemm_phases(void* buf);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */

@@ -9,9 +9,8 @@ M, N, K = int(sys.argv[1]) if len(sys.argv) > 1 else 27000, 256, 256
 A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); out = torch.zeros(M, N, device=dev)
 bias = torch.randn(N, device=dev); bits = torch.zeros(M, 8, dtype=torch.int32, device=dev)
 rows = torch.tensor([M], dtype=torch.int32, device=dev)
-dbg = torch.zeros(12, dtype=torch.int64, device=dev)
-names = ["setup", "tile prologue", "A split+store (+next A loads)", "wait B (cp.async)", "fence+barrier", "MMA issue",
-         "B cp.async issue", "drain (in loop)", "final drain", "epilogue", "stage wait (MMAs of slab g-2)", "-"]
+dbg = torch.zeros(2, dtype=torch.int64, device=dev)
+names = ["main loops (A slabs + drains)", "epilogues"]
 for rep in range(3):
     check(lib.fgs_debug_gemm_phases(dbg.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
