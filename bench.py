@@ -250,7 +250,17 @@ def run_ours(args):
     K = args.steps
     M1, M2 = cnt1["M1"], cnt1["M2"]
     V = args.grid ** 3
-    touched = int((eng.g_k0 != 0).any(dim=1).sum().item())      # voxels of k0 with a gradient (last step)
+    # k0 voxels / 4^3 bricks that receive a gradient in a step (one extra forward + backward, untimed;
+    # the optimiser clears the gradient it consumes, so it cannot be read back after a full step)
+    ro, rd, vd, tgt = resident[0]
+    eng.forward(ro, rd, vd, args.global_step + it)
+    eng.zero_grad()
+    eng.loss_backward(tgt, n_glob, rank == world - 1)
+    torch.cuda.synchronize()
+    touched = int((eng.g_k0 != 0).any(dim=1).sum().item())
+    bricks = int(eng.ws["k0_brick_flags"].sum().item())
+    eng._grads_clean = False
+    eng.zero_grad()
     tv_steps = sum(1 for i in range(K) if eng.is_tv_step(args.global_step + args.warmup + i))
     step_ms_prof = sum(v[0] for v in prof.values()) / K
     kern = []
@@ -258,10 +268,21 @@ def run_ours(args):
         kern.append({"name": name, "ms_per_step": round(t / K, 5), "launches_per_step": round(n / K, 2),
                      "share": round(t / K / step_ms_prof, 4)})
     # algorithmic work per step of the kernels that have a simple model ("byte model")
-    gemm_flops = 2.0 * MLP_MACS * M2 * 3                                   # fwd + dX + dW
-    alg = {"gemm": ("tensor", gemm_flops / 1e12, "TFLOP/s"),
-           "adam_upd": ("hbm", (28.0 * V + 4.0 * 12 * V + 24.0 * 12 * touched) / 1e9, "GB/s"),   # sdf dense + k0 masked
-           "memset": ("hbm", (4.0 * V + 48.0 * V) / 1e9, "GB/s"),                                   # grad clears
+    # MLP GEMMs: forward and backward-data (gemm_w: X*W^T, dZ*W) and backward-weight (gemm_tc: dZ^T*X);
+    # algorithmic FLOPs = 2 * MACs per product, fp32 semantics (the 3xTF32 split issues 3x that on the
+    # tensor cores; the roofline below counts the algorithmic FLOPs only)
+    mac = 2.0 * MLP_MACS * M2
+    V_t = touched
+    alg = {"gemm_w": ("tensor", 2 * mac / 1e12, "TFLOP/s"),
+           "gemm_tc": ("tensor", mac / 1e12, "TFLOP/s"),
+           "gemm": ("tensor", 3 * mac / 1e12, "TFLOP/s"),
+           "adam_dense_zero": ("hbm", 32.0 * V / 1e9, "GB/s"),                          # p,g,m,v read; p,m,v,g written
+           "adam_bricks": ("hbm", 12.0 * V_t * 32.0 / 1e9, "GB/s"),                    # touched voxels x 12 ch x 32 B
+           "adam_upd": ("hbm", (28.0 * V + 4.0 * 12 * V + 24.0 * 12 * touched) / 1e9, "GB/s"),
+           "memset": ("hbm", (4.0 * V + 48.0 * V) / 1e9, "GB/s"),
+           "smooth_tv err": ("hbm", 24.0 * V / 1e9 * tv_steps / K, "GB/s"),               # G read, E written (3 ch)
+           "smooth_tv grad grid": ("hbm", 16.0 * V / 1e9 * tv_steps / K, "GB/s"),         # sdf read, G written
+           "smooth_tv scatter": ("hbm", 20.0 * V / 1e9 * tv_steps / K, "GB/s"),           # E read, g_sdf RMW
            "total_variation_add_grad_v4": ("hbm", 12.0 * V / 1e9 * tv_steps / K, "GB/s")}
     for k in kern:
         if k["name"] in alg:
@@ -275,14 +296,16 @@ def run_ours(args):
             "unit": top.get("unit", "GB/s"), "frac": top.get("frac"), "traffic": None, "peak_source": pk["src"],
             "launches_per_step": top["launches_per_step"], "avg_launch_ms": round(top["ms_per_step"] / max(top["launches_per_step"], 1e-9), 5),
             "share_of_step": top["share"],
-            "note": "fp32 SIMT GEMMs of the colour MLPs measured against the bf16 tensor peak"}
+            "note": "3xTF32 tcgen05 GEMMs of the colour MLPs: algorithmic fp32 FLOPs against the measured bf16 tensor "
+                    "peak (kind::tf32 runs at half the bf16 rate and the split issues 3 MMAs per product, so the "
+                    "ceiling of this formulation is 1/6 of that peak)"}
     line = {"metric": METRIC, "value": n_glob * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": dict(workload(args), parallelism=f"ray-sharded dp{world}", global_rays_per_step=n_glob,
                            samples_per_ray={"total_len": cnt1["total_len"] / N, "M0": cnt1["M0"] / N, "M1": M1 / N,
                                             "Ma": cnt1["MA"] / N, "M2": M2 / N, "M2_at_start": cnt0["M2"] / N},
-                           k0_voxels_touched=touched),
+                           k0_voxels_touched=touched, k0_bricks_touched=bricks),
             "clocks": clocks,
             "e2e": {"value": n_glob * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host[0])),

@@ -43,12 +43,14 @@ uint32_t* hbits(const FgsFineParams& P, int i) { return P.hbits + (size_t)i * P.
 // ReLU mask is produced (mode 0 with relu) or applied (mode 1), -1 for none.
 int mm(const FgsFineParams& P, int mode, int layer, int hid, int M, int N, int K, const float* A, int lda,
        const float* B, int ldb, float* C, int ldc, const float* bias, int relu, const int32_t* rows_dev,
-       cudaStream_t st) {
+       cudaStream_t st, float* gbias = nullptr) {
   if (!g_backend) {
     const float* mask = (mode == 1 && hid >= 0) ? hidden(P, hid) : nullptr;
-    return gemm(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, W, rows_dev, st);
+    int rc = gemm(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, W, rows_dev, st);
+    if (!rc && mode == 2 && gbias) rc = colsum(A, lda, K, M, rows_dev, gbias, st);   // bias gradient
+    return rc;
   }
-  if (mode == 2) return gemm_tc(2, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, nullptr, 0, rows_dev, st);
+  if (mode == 2) return gemm_tc(2, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, nullptr, 0, rows_dev, st, gbias);
   const WSplitLayout L = wsplit_layout();
   if (mode == 0)
     return gemm_w(M, N, K, A, lda, P.w_split + L.hi[layer], P.w_split + L.lo[layer], L.in_ld[layer], C, ldc, bias,
@@ -122,6 +124,10 @@ int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t
   const int cap = P.cap_m2;
   const int in_dim[8] = {FGS_X0_LD, W, W, W, FGS_XR_LD, W, W, W};
   const int out_dim[8] = {W, W, W, W, W, W, W, 3};
+  if (P.g_mlp_flat && P.g_mlp_floats > 0) {
+    // all 16 MLP gradient tensors are views of one buffer: one clear instead of 16
+    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
+  } else
   for (int i = 0; i < 8; ++i) {
     if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
     if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
@@ -129,36 +135,28 @@ int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t
   fgs::prof_mark("memset", st);
   // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
   // layer 7: logit = H5 W7^T + b7
-  if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dlogit, 4, cap, 3, m2, P.gB[7], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st, P.gB[7]))) return rc;
   if ((rc = mm(P, 1, 7, 5, cap, W, 3, P.dlogit, 4, P.W[7], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 6: H5 = relu(H4 W6^T + b6); dA = dZ6
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[6], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, m2, st, P.gB[6]))) return rc;
   if ((rc = mm(P, 1, 6, 4, cap, W, W, P.dA, W, P.W[6], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 5: dB = dZ5
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[5], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, m2, st, P.gB[5]))) return rc;
   if ((rc = mm(P, 1, 5, 3, cap, W, W, P.dB, W, P.W[5], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 4: H3 = relu(XR W4^T + b4); dA = dZ4; dXR = dZ4 W4 (no mask: XR is not a ReLU output)
-  if ((rc = mm(P, 2, -1, -1, W, FGS_XR_LD, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_LD, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[4], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, FGS_XR_LD, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_LD, nullptr, 0, m2, st, P.gB[4]))) return rc;
   if ((rc = mm(P, 1, 4, -1, cap, FGS_XR_LD, W, P.dA, W, P.W[4], FGS_XR_LD, P.dXR, FGS_XR_LD, nullptr, 0, m2, st))) return rc;
   // ---- rgbnet: dZ3 = dXR[:, 0:256] (last rgbnet layer is linear) ----
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dXR, FGS_XR_LD, cap, W, m2, P.gB[3], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, m2, st, P.gB[3]))) return rc;
   if ((rc = mm(P, 1, 3, 2, cap, W, W, P.dXR, FGS_XR_LD, P.W[3], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 2
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[2], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, m2, st, P.gB[2]))) return rc;
   if ((rc = mm(P, 1, 2, 1, cap, W, W, P.dB, W, P.W[2], W, P.dA, W, nullptr, 0, m2, st))) return rc;
   // layer 1
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dA, W, cap, W, m2, P.gB[1], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, m2, st, P.gB[1]))) return rc;
   if ((rc = mm(P, 1, 1, 0, cap, W, W, P.dA, W, P.W[1], W, P.dB, W, nullptr, 0, m2, st))) return rc;
   // layer 0
-  if ((rc = mm(P, 2, -1, -1, W, FGS_X0_LD, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_LD, nullptr, 0, m2, st))) return rc;
-  if ((rc = colsum(P.dB, W, cap, W, m2, P.gB[0], st))) return rc;
+  if ((rc = mm(P, 2, -1, -1, W, FGS_X0_LD, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_LD, nullptr, 0, m2, st, P.gB[0]))) return rc;
   if ((rc = mm(P, 1, 0, -1, cap, FGS_X0_LD, W, P.dB, W, P.W[0], FGS_X0_LD, P.dX0, FGS_X0_LD, nullptr, 0, m2, st))) return rc;
   // ---- features -> level-1 quantities -> grids ----
   if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;

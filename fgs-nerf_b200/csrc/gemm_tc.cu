@@ -50,6 +50,7 @@ struct TcArgs {
   const float* A; const float* B; float* C;
   const float* bias; const float* relu_mask; const int* rows_dev;
   int M, N, K, lda, ldb, ldc, ld_mask, relu;
+  float* colsum;  // SPLITK only (may be NULL): colsum[m] += sum_k A[k][m]  (bias gradients ride along)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs a) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)(BM >> 4) << 24);
 
+  float csum = 0.f;
   // slot idx -> (row = tile row, c = 16-byte k-chunk): K-major operands take one 128-bit load per
   // slot; transposed operands take four coalesced 32-bit loads (k .. k+3 of one row)
   auto load_slab = [&](Slab& s, int k0) {
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs a) {
           if (k + 2 < kend) v.z = __ldg(p + 2 * (size_t)a.lda);
           if (k + 3 < kend) v.w = __ldg(p + 3 * (size_t)a.lda);
         }
+        if (SPLITK) csum += (v.x + v.y) + (v.z + v.w);   // both slots of a thread belong to row idx & 127
       }
       s.a[i] = v;
     }
@@ -310,6 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcArgs a) {
   }
   drain(n_chunks - 1);
 
+  if (SPLITK && a.colsum && blockIdx.x == 0) {
+    const int mr = m0 + (tid & 127);
+    if (mr < M && csum != 0.f) atomicAdd(a.colsum + mr, csum);
+  }
   // ---- epilogue from registers ----
   const int m = m0 + (warp & 3) * 32 + lane;
   if (m < M) {
@@ -391,12 +398,12 @@ namespace fine {
 // up to the next multiple of 4 along k (the fused step pads its rows with zeros).
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-            const int32_t* rows_dev, cudaStream_t st) {
+            const int32_t* rows_dev, cudaStream_t st, float* colsum) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const bool a_vec = (mode != 2), b_vec = (mode == 0);   // operands read with 128-bit loads
   if ((a_vec && ((lda & 3) || ((uintptr_t)A & 15))) || (b_vec && ((ldb & 3) || ((uintptr_t)B & 15))))
     return fgs::fail_arg("gemm_tc needs 16-byte aligned K-major operands with leading dimension % 4 == 0");
-  TcArgs a{A, B, C, bias, relu_mask, rows_dev, M, N, K, lda, ldb, ldc, ld_mask, relu};
+  TcArgs a{A, B, C, bias, relu_mask, rows_dev, M, N, K, lda, ldb, ldc, ld_mask, relu, colsum};
   dim3 grid(fgs::cdiv(N, 256), fgs::cdiv(M, BM), 1);
   switch (mode) {
     case 0: return launch<false, false, false>(a, grid, st);
@@ -421,5 +428,5 @@ extern "C" int fgs_gemm_tc(int mode, int M, int N, int K, const float* A, int ld
                            int ld_mask, const int32_t* rows_dev, fgs_stream_t stream) {
   FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
   return fine::gemm_tc(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, relu_mask, ld_mask, rows_dev,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, nullptr);
 }

@@ -34,15 +34,22 @@ namespace {
 constexpr int BM = 128, BK = 32;                    // one k-slab = 32 floats = one 128-byte swizzle row
 constexpr int kTmemCols = 512;
 constexpr uint32_t kATile = BM * BK * 4;             // 16 KB
-constexpr uint32_t kBTile = 256 * BK * 4;            // 32 KB
-constexpr uint32_t kStage = 2 * kATile + 2 * kBTile; // 96 KB: A_hi, A_lo, B_hi, B_lo
-constexpr int kStages = 2;
-constexpr int kChunkSlabs = 1;                       // accumulation chunk = one 32-k slab
-constexpr uint32_t kStagingOff = kStages * kStage;             // 8 warps x 32 x 33 floats
-constexpr uint32_t kStagingBytes = 8 * 32 * 33 * 4;
-constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;      // mbarriers + tmem slot
-constexpr uint32_t kSmemBytes = kBarOff + 256;
-constexpr int kPfB = 1;                                        // TMA prefetch distance (slabs)
+// Tile width TN (output columns per CTA) is a template parameter: 256 (2 stages of 96 KB) or 128
+// (3 stages of 64 KB, 64 accumulator registers per thread, 2x the CTAs -> finer wave quantisation).
+constexpr int kChunkSlabs = 1;  // accumulation chunk = one 32-k slab (12 MMAs) per TMEM region
+
+template <int TN>
+struct Cfg {
+  static constexpr uint32_t kBTile = TN * BK * 4;
+  static constexpr uint32_t kStage = 2 * kATile + 2 * kBTile;      // A_hi, A_lo, B_hi, B_lo
+  static constexpr int kStages = (TN == 256) ? 2 : 3;
+  static constexpr uint32_t kStagingOff = kStages * kStage;       // 8 warps x 32 x 33 floats
+  static constexpr uint32_t kStagingBytes = 8 * 32 * 33 * 4;
+  static constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;  // mbarriers + tmem slot
+  static constexpr uint32_t kSmemBytes = kBarOff + 256;
+  static constexpr int kAcc = TN / 2;                               // accumulator registers per worker thread
+};
+
 
 struct WArgs {
   const float* A; float* C;
@@ -142,8 +149,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   r_empty[r]   workers -> MMA   (256 arrivals: the chunk has been added into registers)
 // so the blocking MMA issue never stalls the producers, and the producers run up to kStages slabs
 // ahead of the tensor core.
+template <int TN>
 __global__ void __launch_bounds__(kThreadsWS, 1)
 gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
+  constexpr uint32_t kBTile = Cfg<TN>::kBTile, kStage = Cfg<TN>::kStage, kStagingOff = Cfg<TN>::kStagingOff,
+                     kBarOff = Cfg<TN>::kBarOff;
+  constexpr int kStages = Cfg<TN>::kStages, kAcc = Cfg<TN>::kAcc, kPfB = kStages - 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
   const uint32_t free_bar0 = smem + kBarOff;
@@ -156,11 +167,11 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
 
   int M = a.M;
   if (a.rows_dev) M = min(M, *a.rows_dev);
-  const int n0 = blockIdx.x * 256;
+  const int n0 = blockIdx.x * TN;
   const int n_tiles = (M + BM - 1) / BM;
   if ((int)blockIdx.y >= n_tiles) return;
   const int K = a.K;
-  const int BN = min(256, (a.N - n0 + 15) & ~15);
+  const int BN = min(TN, (a.N - n0 + 15) & ~15);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) {
@@ -243,7 +254,7 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
   } else {
     // ================= workers: A slabs, TMEM drain, epilogue =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-    const int col_half = (warp >> 2) * 128;
+    const int col_half = (warp >> 2) * kAcc;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     // A slots: thread -> row ar, 16-byte k-chunks ac, ac + 2, ac + 4, ac + 6 of the 128-byte row; chunk c
     // of row r lives at chunk position c ^ (r % 8), so the 8 rows of a quarter-warp hit 8 distinct
@@ -257,9 +268,9 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
     for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
       const int m0 = tile * BM;
       if (dbg_on) t0 = clock64();
-      float acc[128];
+      float acc[kAcc];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
 
       auto load_a = [&](float4 (&v)[4], int k0) {
         const int m = m0 + ar;
@@ -285,7 +296,7 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
         mbar_wait(rfull_bar0 + 8 * (c & 1), (c >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kAcc / 32; ++q) {
           if (col_half + 32 * q < BN) {
             uint32_t r[32];
             const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
@@ -331,7 +342,7 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
         const int m = m0 + (warp & 3) * 32 + lane;               // the row this thread accumulated
         float* stg = staging + warp * (32 * 33);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kAcc / 32; ++q) {
           const int c0 = col_half + 32 * q;
           if (c0 < BN) {
             const int col = n0 + c0 + lane;                      // the column this lane stores
@@ -375,11 +386,14 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
 }
 
 long long* g_dbg = nullptr;
+int g_tile_n = 128;   // 128 or 256 (fgs_debug_gemm_tile_n)
 
+template <int TN>
 int configure_once() {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_w_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg<TN>::kSmemBytes);
     if (e != cudaSuccess) return fgs::check_cuda(e, "gemm_w smem attribute");
     configured = true;
   }
@@ -394,10 +408,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
+std::map<std::tuple<const void*, int, int, int>, CUtensorMap> g_maps;
 
-int get_map(const float* plane, int rows_alloc, int ld, CUtensorMap* out) {
-  auto key = std::make_tuple((const void*)plane, rows_alloc, ld);
+int get_map(const float* plane, int rows_alloc, int ld, int tn, CUtensorMap* out) {
+  auto key = std::make_tuple((const void*)plane, rows_alloc, ld, tn);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -413,7 +427,7 @@ int get_map(const float* plane, int rows_alloc, int ld, CUtensorMap* out) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_alloc};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};                           // bytes, dim 1
-  const cuuint32_t box[2] = {BK, 256};
+  const cuuint32_t box[2] = {BK, (cuuint32_t)tn};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
   CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
@@ -446,19 +460,24 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)Bh | (uintptr_t)Bl) & 15))
     return fgs::fail_arg("gemm_w needs 16-byte aligned operands with leading dimensions % 4 == 0");
   if (K > ldb) return fgs::fail_arg("gemm_w: K exceeds the weight plane's row length");
-  int rc = configure_once();
+  // tile width: 128-wide tiles double the CTA count; pick them when that fills the last wave better
+  const int n_tiles = fgs::cdiv(M, BM);
+  const int tn = (N > 128 && g_tile_n != 256) ? 128 : 256;
+  int rc = (tn == 128) ? configure_once<128>() : configure_once<256>();
   if (rc) return rc;
   CUtensorMap tm_hi, tm_lo;
   const int rows_alloc = (N + 7) & ~7;
-  if ((rc = get_map(Bh, rows_alloc, ldb, &tm_hi))) return rc;
-  if ((rc = get_map(Bl, rows_alloc, ldb, &tm_lo))) return rc;
+  if ((rc = get_map(Bh, rows_alloc, ldb, tn, &tm_hi))) return rc;
+  if ((rc = get_map(Bl, rows_alloc, ldb, tn, &tm_lo))) return rc;
   WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, g_dbg};
-  const int n_tiles = fgs::cdiv(M, BM);
-  const int nx = fgs::cdiv(N, 256);
+  const int nx = fgs::cdiv(N, tn);
   int ny = FGS_NUM_SMS / nx;
   if (ny > n_tiles) ny = n_tiles;
   if (ny < 1) ny = 1;
-  gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo);
+  if (tn == 128)
+    gemm_w_kernel<128><<<dim3(nx, ny, 1), kThreadsWS, Cfg<128>::kSmemBytes, st>>>(a, tm_hi, tm_lo);
+  else
+    gemm_w_kernel<256><<<dim3(nx, ny, 1), kThreadsWS, Cfg<256>::kSmemBytes, st>>>(a, tm_hi, tm_lo);
   return fgs::check_launch("gemm_w", st);
 }
 
@@ -515,5 +534,12 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 // CTA (0,0) spent in main loops and in epilogues (NULL switches it off).
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
+  return 0;
+}
+
+// Debug / tuning: output-tile width of the pre-split GEMM (128 or 256 columns per CTA).
+extern "C" int fgs_debug_gemm_tile_n(int tn) {
+  FGS_REQUIRE(tn == 128 || tn == 256, "tile width must be 128 or 256");
+  g_tile_n = tn;
   return 0;
 }

@@ -22,7 +22,7 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
 // generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-            const int32_t* rows_dev, cudaStream_t st);
+            const int32_t* rows_dev, cudaStream_t st, float* colsum = nullptr);
 
 // Layout of FgsFineParams::w_split: per layer the straight planes [out][in_ld] (forward) and the
 // transposed planes [in_ld][ldt] (backward-data), hi then lo.

@@ -57,7 +57,7 @@ class FgsFineParams(C.Structure):
         ("normal_marched", _fp), ("counters", _fp),
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
-        ("w_split", _fp), ("hbits", _fp), ("k0_brick_flags", _fp),
+        ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
     ]
 
 
@@ -90,6 +90,7 @@ _lib.declare("fgs_gemm_tc", C.c_int, _GEMM_SIG)
 _lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
 _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
+_lib.declare("fgs_debug_gemm_tile_n", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
@@ -207,9 +208,16 @@ class FineStepEngine:
         # ---- gradients + Adam state ----
         self.g_sdf = torch.zeros_like(self.sdf)
         self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
-        self.gW = [torch.zeros_like(w) for w in self.Wt]
+        # all 16 MLP gradient tensors are views of one flat buffer (one clear, one all-reduce bucket)
+        sizes = [w.numel() for w in self.Wt] + [b.numel() for b in self.Bt]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)         # keep every view 16-byte aligned
+        self.g_mlp_flat = torch.zeros(offs[-1], dtype=f32, device=dev)
+        views = [self.g_mlp_flat[o:o + n] for o, n in zip(offs, sizes)]
+        self.gW = [v.view_as(w) for v, w in zip(views[:MLP_LAYERS], self.Wt)]
         self.weight_grads = [g[:, :d[1]] for g, d in zip(self.gW, dims)]
-        self.gB = [torch.zeros_like(b) for b in self.Bt]
+        self.gB = [v.view_as(b) for v, b in zip(views[MLP_LAYERS:], self.Bt)]
         self.adam = {}
         self.adam_step = 0
         # ---- workspace ----
@@ -281,6 +289,7 @@ class FineStepEngine:
             P.W[i], P.B[i] = ptr(self.Wt[i]), ptr(self.Bt[i])
             P.gW[i], P.gB[i] = ptr(self.gW[i]), ptr(self.gB[i])
         P.g_sdf, P.g_k0 = ptr(self.g_sdf), ptr(self.g_k0)
+        P.g_mlp_flat, P.g_mlp_floats = ptr(self.g_mlp_flat), self.g_mlp_flat.numel()
         for k in ("t_min", "t_max", "n_steps", "cnt1", "cnt2", "off1", "off2", "bits", "alphainv_last",
                   "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
                   "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
@@ -477,7 +486,7 @@ class FineStepEngine:
             return
         import torch.distributed as dist
         from .dist import all_reduce_sum_
-        all_reduce_sum_([self.g_sdf, self.g_k0] + self.gW + self.gB)
+        all_reduce_sum_([self.g_sdf, self.g_k0, self.g_mlp_flat])
         dist.all_reduce(self.ws["k0_brick_flags"], op=dist.ReduceOp.MAX)   # union of the touched bricks
         lib.fgs_prof_mark(1, stream())
 

@@ -121,6 +121,8 @@ typedef struct FgsFineParams {
   float *w_split;    /* fgs_fine_wsplit_floats() floats: hi / lo TF32 planes of the 8 weight matrices,
                         straight and transposed; rewritten by every fgs_fine_forward; zero-initialised */
   uint32_t *hbits;   /* [6][cap_m2][8] ReLU masks of the hidden activations, 1 bit per unit */
+  float *g_mlp_flat;   /* optional: one buffer that contains every gW[i] / gB[i] (cleared with one memset) */
+  int64_t g_mlp_floats;
   uint8_t *k0_brick_flags; /* [ceil(X/4)*ceil(Y/4)*ceil(Z/4)] set to 1 by the backward scatter for every
                         4x4x4 brick of k0 that received a gradient (may be NULL); see fgs_adam_upd_bricks */
 } FgsFineParams;
@@ -200,6 +202,8 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
 /* Debug aid: 2 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
  * worker 0 of CTA (0,0) spent in its main loops and in its epilogues (NULL = off). */
 int fgs_debug_gemm_phases(void* buf);
+/* Tuning aid: output-tile width (128 or 256 columns per CTA) of the pre-split GEMM. */
+int fgs_debug_gemm_tile_n(int tn);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);
