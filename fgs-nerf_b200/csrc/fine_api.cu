@@ -50,7 +50,7 @@ int mm(const FgsFineParams& P, int mode, int layer, int hid, int M, int N, int K
     if (!rc && mode == 2 && gbias) rc = colsum(A, lda, K, M, rows_dev, gbias, st);   // bias gradient
     return rc;
   }
-  if (mode == 2) return gemm_tc(2, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, nullptr, 0, rows_dev, st, gbias);
+  if (mode == 2) return gemm_tn(M, N, K, A, lda, B, ldb, C, ldc, gbias, rows_dev, st);
   const WSplitLayout L = wsplit_layout();
   if (mode == 0)
     return gemm_w(M, N, K, A, lda, P.w_split + L.hi[layer], P.w_split + L.lo[layer], L.in_ld[layer], C, ldc, bias,

@@ -385,6 +385,213 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
   }
 }
 
+// ---- backward-weight GEMM:  C[M,N] += A[K,M]^T B[K,N]  (dW = dZ^T X), split over the samples ----------
+// Same machinery (warp-specialised, SWIZZLE_128B tiles, 32-k accumulation chunks, register
+// accumulators), but the reduction index is the SAMPLE dimension, which is the slow dimension of both
+// row-major operands.  kind::tf32 cannot read MN-major tiles without the 128B_BASE32B swizzle, so the
+// 256 workers transpose both operands on the fly: coalesced 32-bit loads along the feature dimension
+// (a warp reads 128 contiguous bytes of one sample row), four consecutive samples of one feature form
+// the 16-byte chunk that is split into hi / lo and stored to the swizzled K-major tile.  The bias
+// gradient (column sums of dZ) rides along with the A loads.  Partial products of the K-splits are
+// combined with 128-byte red.global.add rows (epilogue transposed through shared memory).
+struct TnArgs {
+  const float* A; const float* B; float* C; float* colsum; const int* rows_dev;
+  int M, N, K, lda, ldb, ldc;
+};
+
+__global__ void __launch_bounds__(kThreadsWS, 1) gemm_tn_kernel(const TnArgs a) {
+  constexpr int TN = 128;
+  constexpr uint32_t kBTile = Cfg<TN>::kBTile, kStage = Cfg<TN>::kStage, kStagingOff = Cfg<TN>::kStagingOff,
+                     kBarOff = Cfg<TN>::kBarOff;
+  constexpr int kStages = Cfg<TN>::kStages, kAcc = Cfg<TN>::kAcc;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const uint32_t free_bar0 = smem + kBarOff;
+  const uint32_t afull_bar0 = free_bar0 + 8 * kStages;
+  const uint32_t rfull_bar0 = afull_bar0 + 8 * kStages;
+  const uint32_t rempty_bar0 = rfull_bar0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (2 * kStages + 4) + 8);
+  float* staging = reinterpret_cast<float*>(smem_raw + kStagingOff);
+
+  int K = a.K;
+  if (a.rows_dev) K = min(K, *a.rows_dev);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * TN;
+  int chunk = (K + gridDim.z - 1) / gridDim.z;
+  chunk = (chunk + BK - 1) / BK * BK;
+  const int kbeg = blockIdx.z * chunk;
+  const int kend = min(K, kbeg + chunk);
+  if (kbeg >= kend) return;
+  const int BN = min(TN, (a.N - n0 + 15) & ~15);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(free_bar0 + 8 * i, 1);
+      mbar_init(afull_bar0 + 8 * i, kWorkers);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(rfull_bar0 + 8 * i, 1);
+      mbar_init(rempty_bar0 + 8 * i, kWorkers);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                         ((uint32_t)(BM >> 4) << 24);
+  const int n_slabs = (kend - kbeg + BK - 1) / BK;
+
+  if (warp >= kWorkers / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == kWorkers / 32 && lane == 0) {
+      for (int kt = 0; kt < n_slabs; ++kt) {
+        const uint32_t st = (uint32_t)kt % kStages;
+        mbar_wait(afull_bar0 + 8 * st, ((uint32_t)kt / kStages) & 1);
+        if (kt >= 2) mbar_wait(rempty_bar0 + 8 * (kt & 1), ((kt >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t stage_base = smem + st * kStage;
+        const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+        const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+        const uint32_t d = tmem_d + (uint32_t)(kt & 1) * 256;
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+          const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+          mma_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
+          mma_tf32(d, dah, dbl, idesc, 1);
+          mma_tf32(d, dah, dbh, idesc, 1);
+        }
+        mma_commit(free_bar0 + 8 * st);
+        mma_commit(rfull_bar0 + 8 * (kt & 1));
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    const int col_half = (warp >> 2) * kAcc;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int ar = tid & 127, ac = tid >> 7;           // tile row (feature) and first 16-byte chunk
+    const uint32_t arow = (uint32_t)(ar * 128);
+    float acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+    float csum = 0.f;
+
+    // 4 consecutive samples k .. k+3 of feature (f0 + ar): one 16-byte chunk of the K-major tile
+    auto load_t = [&](float4 (&v)[4], const float* __restrict__ src, int ld, int f0, int fmax, int k0) {
+      const int f = f0 + ar;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + 4 * (ac + 2 * i);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < fmax) {
+          const float* p = src + (size_t)k * ld + f;
+          if (k < kend) x.x = __ldg(p);
+          if (k + 1 < kend) x.y = __ldg(p + ld);
+          if (k + 2 < kend) x.z = __ldg(p + 2 * (size_t)ld);
+          if (k + 3 < kend) x.w = __ldg(p + 3 * (size_t)ld);
+        }
+        v[i] = x;
+      }
+    };
+    auto store_t = [&](const float4 (&v)[4], uint32_t hi_base, uint32_t lo_base) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = arow + (uint32_t)(((ac + 2 * i) ^ (ar & 7)) * 16);
+        float4 hi, lo;
+        hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
+        lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
+        lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
+        st_shared_v4(hi_base + off, hi);
+        st_shared_v4(lo_base + off, lo);
+      }
+    };
+    auto drain = [&](uint32_t c) {
+      mbar_wait(rfull_bar0 + 8 * (c & 1), (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < kAcc / 32; ++q) {
+        if (col_half + 32 * q < BN) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(rempty_bar0 + 8 * (c & 1));
+    };
+
+    float4 va[4], vb[4];
+    load_t(va, a.A, a.lda, m0, a.M, kbeg);
+    load_t(vb, a.B, a.ldb, n0, a.N, kbeg);
+    for (int kt = 0; kt < n_slabs; ++kt) {
+      const uint32_t st = (uint32_t)kt % kStages;
+      const uint32_t stage_base = smem + st * kStage;
+      if (kt >= kStages) mbar_wait(free_bar0 + 8 * st, (((uint32_t)kt / kStages) - 1) & 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) csum += (va[i].x + va[i].y) + (va[i].z + va[i].w);
+      store_t(va, stage_base, stage_base + kATile);
+      store_t(vb, stage_base + 2 * kATile, stage_base + 2 * kATile + kBTile);
+      if (kt + 1 < n_slabs) {
+        load_t(va, a.A, a.lda, m0, a.M, kbeg + (kt + 1) * BK);
+        load_t(vb, a.B, a.ldb, n0, a.N, kbeg + (kt + 1) * BK);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(afull_bar0 + 8 * st);
+      if (kt >= 1) drain((uint32_t)kt - 1);
+    }
+    drain((uint32_t)n_slabs - 1);
+
+    if (a.colsum && blockIdx.x == 0 && m0 + ar < a.M && csum != 0.f) atomicAdd(a.colsum + m0 + ar, csum);
+
+    // ---- epilogue: registers -> 32x33 smem transpose -> 128-byte red.global.add rows ----
+    float* stg = staging + warp * (32 * 33);
+#pragma unroll
+    for (int q = 0; q < kAcc / 32; ++q) {
+      const int c0 = col_half + 32 * q;
+      if (c0 < BN) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = acc[32 * q + j];
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        if (col < a.N) {
+          const int mr0 = m0 + (warp & 3) * 32;
+          float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r)
+            if (mr0 + r < a.M) atomicAdd(cp + (size_t)r * a.ldc, stg[r * 33 + lane]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
 long long* g_dbg = nullptr;
 int g_tile_n = 128;   // 128 or 256 (fgs_debug_gemm_tile_n)
 
@@ -481,6 +688,29 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   return fgs::check_launch("gemm_w", st);
 }
 
+// C[M,N] += A[K,M]^T B[K,N] over the first min(K, *rows_dev) rows; colsum[m] += sum_k A[k][m] (may be NULL)
+int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            float* colsum, const int32_t* rows_dev, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg<128>::kSmemBytes);
+    if (e != cudaSuccess) return fgs::check_cuda(e, "gemm_tn smem attribute");
+    configured = true;
+  }
+  TnArgs a{A, B, C, colsum, rows_dev, M, N, K, lda, ldb, ldc};
+  dim3 grid(fgs::cdiv(N, 128), fgs::cdiv(M, BM), 1);
+  const int tiles = grid.x * grid.y;
+  int splits = (FGS_NUM_SMS + tiles - 1) / tiles;
+  const int max_splits = fgs::cdiv(K, 4 * BK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  grid.z = splits;
+  gemm_tn_kernel<<<grid, kThreadsWS, Cfg<128>::kSmemBytes, st>>>(a);
+  return fgs::check_launch("gemm_tn", st);
+}
+
 // ---- weight splitting ------------------------------------------------------------------------
 int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {
   if (n <= 0) return 0;
@@ -542,4 +772,11 @@ extern "C" int fgs_debug_gemm_tile_n(int tn) {
   FGS_REQUIRE(tn == 128 || tn == 256, "tile width must be 128 or 256");
   g_tile_n = tn;
   return 0;
+}
+
+// Stand-alone entry for tests: C[M,N] += A[K,M]^T B[K,N] (warp-specialised split-K kernel).
+extern "C" int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                           int ldc, float* colsum, const int32_t* rows_dev, fgs_stream_t stream) {
+  FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+  return fine::gemm_tn(M, N, K, A, lda, B, ldb, C, ldc, colsum, rows_dev, (cudaStream_t)stream);
 }

@@ -19,6 +19,10 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
            int ldc, const float* bias, int relu, const uint32_t* bits_in, uint32_t* bits_out,
            const int32_t* rows_dev, cudaStream_t st);
 
+// C[M,N] += A[K,M]^T B[K,N], split over K; colsum[m] += sum_k A[k][m]   (gemm_tcw.cu)
+int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            float* colsum, const int32_t* rows_dev, cudaStream_t st);
+
 // generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,

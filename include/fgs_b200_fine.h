@@ -199,6 +199,11 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
                  float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
                  uint32_t* bits_out, const int32_t* rows_dev, fgs_stream_t stream);
 
+/* C[M,N] += A[K,M]^T B[K,N] (3xTF32, split over K, atomically accumulated) with colsum[m] += sum_k A[k][m]
+ * (may be NULL): the kernel the fused step runs for the weight / bias gradients. */
+int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
+
 /* Debug aid: 2 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
  * worker 0 of CTA (0,0) spent in its main loops and in its epilogues (NULL = off). */
 int fgs_debug_gemm_phases(void* buf);

@@ -441,3 +441,27 @@ def test_brick_adam_equals_dense_masked_adam(cuda):
         assert torch.equal(flat(eng.adam["k0"][0]), m_ref) and torch.equal(flat(eng.adam["k0"][1]), v_ref)
         assert int(eng.g_k0.count_nonzero()) == 0 and int(eng.g_sdf.count_nonzero()) == 0
         assert int(eng.ws["k0_brick_flags"].sum()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 320, 1000), (3, 256, 777), (256, 112, 40000), (256, 256, 130), (256, 256, 27000)])
+def test_gemm_weight_gradient_kernel(cuda, M, N, K):
+    """fgs_gemm_tn = the warp-specialised split-K kernel of the weight / bias gradients (dW = dZ^T X)."""
+    from fgs_nerf_b200 import engine
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    A, B, want = _tc_case(cuda, 2, M, N, K, 31 * M + N + K)
+    out = torch.zeros(M, (N + 3) // 4 * 4, device=cuda)
+    csum = torch.zeros(M, device=cuda)
+    rows = torch.tensor([K], dtype=torch.int32, device=cuda)
+    check(lib.fgs_gemm_tn(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), ptr(csum),
+                          ptr(rows), stream()))
+    torch.cuda.synchronize()
+    err = _rel(out[:, :N], want)
+    cerr = _rel(csum, A[:, :M].double().sum(0))
+    print(f"tn gemm {M}x{N}x{K}: rel err {err:.3e}, colsum rel err {cerr:.3e}")
+    assert err < 2e-6 and cerr < 2e-6
+    # device-side row count: only the first K/2 samples contribute
+    out.zero_(); csum.zero_(); rows.fill_(K // 2)
+    check(lib.fgs_gemm_tn(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), ptr(csum),
+                          ptr(rows), stream()))
+    torch.cuda.synchronize()
+    assert _rel(out[:, :N], A[:K // 2, :M].double().T @ B[:K // 2, :N].double()) < 2e-6
