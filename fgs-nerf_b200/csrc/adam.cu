@@ -226,19 +226,62 @@ adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, floa
   }
 }
 
-// touched-brick list: one thread per brick flag, warp-aggregated append, flags cleared on the way.
-// list[0] = count, list[1..] = brick ids (order irrelevant).
-__global__ void __launch_bounds__(kBlock)
+// touched-brick list in ASCENDING brick order (deterministic, identical on every rank that holds the
+// same flags): single CTA, each thread counts a contiguous run of flags, block scan, ordered write;
+// the flags are cleared on the way.  list[0] = count, list[1..] = brick ids.
+__global__ void __launch_bounds__(1024)
 brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ list) {
-  const int b = blockIdx.x * kBlock + threadIdx.x;
-  const bool f = (b < n_bricks) && flags[b];
-  if (f) flags[b] = 0;
-  const unsigned m = __ballot_sync(0xffffffffu, f);
-  if (m == 0) return;
-  int base = 0;
-  if (lane_id() == __ffs(m) - 1) base = atomicAdd(list, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (f) list[1 + base + __popc(m & ((1u << lane_id()) - 1))] = b;
+  __shared__ int s_warp[32];
+  const int per = (n_bricks + 1023) / 1024;
+  const int beg = threadIdx.x * per, end = min(beg + per, n_bricks);
+  int cnt = 0;
+  for (int b = beg; b < end; ++b) cnt += flags[b] ? 1 : 0;
+  const int incl = warp_incl_scan(cnt);
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const int v = s_warp[lane_id()];
+    const int sc = warp_incl_scan(v);
+    s_warp[lane_id()] = sc - v;
+    if (lane_id() == 31) list[0] = sc;
+  }
+  __syncthreads();
+  int o = 1 + incl - cnt + s_warp[w];
+  for (int b = beg; b < end; ++b) {
+    if (flags[b]) {
+      list[o++] = b;
+      flags[b] = 0;
+    }
+  }
+}
+
+// gather / scatter of listed k0 gradient bricks (768 floats each, channels-last [X][Y][Z][12]) to and
+// from a compact [count][768] buffer: the payload of the sparse multi-GPU gradient exchange.
+template <bool PACK>
+__global__ void __launch_bounds__(kBlock)
+brick_copy_kernel(float* __restrict__ grid, float* __restrict__ compact, const int* __restrict__ list, int max_bricks,
+                  int X, int Y, int Z) {
+  const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
+  const int lane = lane_id();
+  const int wpb = kBlock / 32;
+  const int count = min(list[0], max_bricks);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < count; e += gridDim.x * wpb) {
+    const int br = list[1 + e];
+    const int bz = br % nbZ, by = (br / nbZ) % nbY, bx = br / (nbZ * nbY);
+    float* __restrict__ c = compact + (size_t)e * 768;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int q = lane + 32 * i;
+      const int row = q / 12, f4 = q - row * 12;
+      const int x = 4 * bx + (row >> 2), y = 4 * by + (row & 3), z = 4 * bz + f4 / 3;
+      const bool ok = x < X && y < Y && z < Z;
+      const size_t off = (((size_t)x * Y + y) * Z + 4 * bz) * 12 + 4 * f4;
+      if (PACK) st4(c + 4 * q, ok ? ld4(grid + off) : z4);
+      else if (ok) st4(grid + off, ld4(c + 4 * q));
+    }
+  }
 }
 
 // grid layout [X][Y][Z][12] (channels-last); brick b = ((x>>2)*nbY + (y>>2))*nbZ + (z>>2).
@@ -309,10 +352,20 @@ int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_lis
   FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "bad grid size");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_bricks = ((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
-  int rc = fgs::check_cuda(cudaMemsetAsync(brick_list, 0, sizeof(int32_t), st), "brick list memset");
-  if (rc) return rc;
-  brick_list_kernel<<<fgs::cdiv(n_bricks, kBlock), kBlock, 0, st>>>(brick_flags, n_bricks, brick_list);
+  brick_list_kernel<<<1, 1024, 0, st>>>(brick_flags, n_bricks, brick_list);
   return fgs::check_launch("brick_list", st);
+}
+
+// compact[e][768] <- grad bricks list[1+e] (pack != 0), or grad bricks <- compact (pack == 0); e < max_bricks
+int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int max_bricks, int X, int Y, int Z,
+                   int channels, int pack, fgs_stream_t stream) {
+  FGS_REQUIRE(channels == 12 && X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick copy: 12-channel grid, Z % 4 == 0");
+  if (max_bricks <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid_dim = fgs::stream_grid(max_bricks, kBlock / 32, 8);
+  if (pack) brick_copy_kernel<true><<<grid_dim, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
+  else brick_copy_kernel<false><<<grid_dim, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
+  return fgs::check_launch(pack ? "brick_pack" : "brick_unpack", st);
 }
 
 int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int32_t* brick_list,

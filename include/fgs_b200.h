@@ -149,7 +149,9 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
  *  fgs_adam_upd_zero_grad : dense adam_upd that also clears the consumed gradient (no memset pass);
  *  fgs_brick_list         : compacts the touched-brick flags that fgs_fine_backward leaves behind (one
  *      byte per 4x4x4-voxel brick of k0, [ceil(X/4)*ceil(Y/4)*ceil(Z/4)]) into brick_list
- *      (fgs_brick_list_ints() ints: count, then brick ids) and clears the flags;
+ *      (fgs_brick_list_ints() ints: count, then brick ids in ascending order) and clears the flags;
+ *  fgs_brick_copy         : gathers (pack != 0) / scatters the listed gradient bricks (768 floats each)
+ *      to / from a compact [count][768] buffer -- the payload of the sparse multi-GPU exchange;
  *  fgs_adam_upd_bricks    : masked_adam_upd of a channels-last [X][Y][Z][12] grid restricted to the
  *      listed bricks, one warp per brick; clears the gradients it consumed.  Identical p, m, v to
  *      masked_adam_upd provided every voxel with grad != 0 lies in a listed brick. */
@@ -158,6 +160,8 @@ int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp
                            fgs_stream_t stream);
 int64_t fgs_brick_list_ints(int X, int Y, int Z);
 int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_list, fgs_stream_t stream);
+int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int max_bricks, int X, int Y,
+                   int Z, int channels, int pack, fgs_stream_t stream);
 int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                         const int32_t* brick_list, int X, int Y, int Z, int channels, int step,
                         float beta1, float beta2, float lr, float eps, fgs_stream_t stream);
