@@ -103,6 +103,7 @@ int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
   if ((rc = mm(P, 0, 5, 4, cap, W, W, hidden(P, 3), W, P.W[5], W, hidden(P, 4), W, P.B[5], 1, m2, st))) return rc;
   if ((rc = mm(P, 0, 6, 5, cap, W, W, hidden(P, 4), W, P.W[6], W, hidden(P, 5), W, P.B[6], 1, m2, st))) return rc;
   if ((rc = mm(P, 0, 7, -1, cap, 3, W, hidden(P, 5), W, P.W[7], W, P.logit, 4, P.B[7], 0, m2, st))) return rc;
+  if (P.skip_composite) return 0;   // training: fgs_fine_loss runs the compositing with the loss fused
   return launch_composite(P, nullptr, st);
 }
 

@@ -149,7 +149,7 @@ __device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float
   return fminf(fmaxf(a, 0.f), 1.f);
 }
 
-__global__ void __launch_bounds__(kBlock) level1_kernel(const __grid_constant__ FgsFineParams P) {
+__global__ void __launch_bounds__(kBlock, 3) level1_kernel(const __grid_constant__ FgsFineParams P) {
   const int lane = lane_id();
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const float thres = P.fast_color_thres;

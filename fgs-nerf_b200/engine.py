@@ -37,6 +37,7 @@ class FgsFineParams(C.Structure):
         ("mX", C.c_int32), ("mY", C.c_int32), ("mZ", C.c_int32),
         ("cap_words", C.c_int32), ("cap_m1", C.c_int32), ("cap_m2", C.c_int32),
         ("render_depth", C.c_int32), ("render_normal", C.c_int32),
+        ("skip_composite", C.c_int32), ("pad1_", C.c_int32),
         ("xyz_min", C.c_float * 3), ("xyz_max", C.c_float * 3),
         ("mask_xyz_min", C.c_float * 3), ("mask_xyz_max", C.c_float * 3),
         ("near_", C.c_float), ("far_", C.c_float), ("stepdist", C.c_float), ("dist", C.c_float),
@@ -261,6 +262,8 @@ class FineStepEngine:
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         self._brick_list_ready = False
         self._compact = None
+        self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._count_evt = torch.cuda.Event()
         self.exchange_bricks = 0
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
         ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
@@ -322,9 +325,10 @@ class FineStepEngine:
 
     # -------------------------------------------------------------------------------------
     def forward(self, rays_o, rays_d, viewdirs, global_step=20000, near=2.0, bg=1.0, render_depth=False,
-                render_grad=False):
+                render_grad=False, _skip_composite=False):
         """nerf.forward_fine: enqueue only.  Results live in self.ws (see outputs())."""
         self._bind_inputs(rays_o, rays_d, viewdirs, global_step, near, bg, render_depth, render_grad)
+        self.P.skip_composite = int(bool(_skip_composite))
         with torch.cuda.device(self.device):
             check(lib.fgs_fine_forward(C.byref(self.P), stream()))
 
@@ -502,12 +506,17 @@ class FineStepEngine:
             dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)
             lib.fgs_prof_mark(1, stream())
             return
-        all_reduce_sum_([self.g_sdf, self.g_mlp_flat])
         dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
-            n = int(ws["k0_brick_list"][0].item())                              # the one host sync of a DP step
+            self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
+            self._count_evt.record()
+            # the dense reductions run while the host waits for the brick count (the one host sync of a
+            # DP step) and enqueues the sparse exchange behind them
+            all_reduce_sum_([self.g_sdf, self.g_mlp_flat])
+            self._count_evt.synchronize()
+            n = int(self._count_host[0])
             if n > 0:
                 if self._compact is None or self._compact.numel() < n * 768:
                     self._compact = torch.empty(int(n * 1.5) * 768, dtype=torch.float32, device=self.device)
@@ -524,7 +533,7 @@ class FineStepEngine:
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True):
         """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous."""
-        self.forward(rays_o, rays_d, viewdirs, global_step, near, bg)
+        self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
         self.loss_backward(target, n_rays_global, has_last_ray)
         t = self.train_cfg

@@ -80,6 +80,8 @@ typedef struct FgsFineParams {
   int32_t cap_words;            /* 32-bit words of the per-ray step bitmap */
   int32_t cap_m1, cap_m2;       /* sample capacities; cap_m2 % 128 == 0   */
   int32_t render_depth, render_normal;
+  int32_t skip_composite;       /* fgs_fine_forward stops after the MLPs (fgs_fine_loss composites) */
+  int32_t pad1_;
   /* ---- scalars ---- */
   float xyz_min[3], xyz_max[3], mask_xyz_min[3], mask_xyz_max[3];
   float near_, far_, stepdist, dist, voxel_size, mask_thres, fast_color_thres, inv_s, bg;
