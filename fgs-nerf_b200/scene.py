@@ -132,6 +132,10 @@ def make_rays(N=8192, H=800, W=800, n_views=40, seed=777, inverse_y=False, radiu
         dirs = np.stack([(col - cx) / f, -(row - cy) / f, -np.ones_like(col)], -1)
     poses = np.stack([_pose_spherical(t, elev, radius) for t in np.linspace(-180, 180, n_views + 1)[:-1]])
     R = poses[view, :3, :3]                       # [N,3,3]
+    if inverse_y:
+        # OpenCV-convention cameras (DTU, model/nerf_ray.py:24-25: x right, y down, z forward): the same
+        # viewpoints expressed in that convention, c2w = c2w_gl @ diag(1, -1, -1)
+        R = R * np.array([1.0, -1.0, -1.0], dtype=np.float32)[None, None, :]
     rays_d = np.einsum("nij,nj->ni", R, dirs.astype(np.float32)).astype(np.float32)
     rays_o = poses[view, :3, 3].astype(np.float32)
     viewdirs = rays_d / np.linalg.norm(rays_d, axis=-1, keepdims=True)
