@@ -369,6 +369,53 @@ class FineStepEngine:
         }
 
     # -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, viewdirs, global_step=20000, near=2.0, bg=1.0, render_depth=True,
+               render_grad=True, world_size=1, rank=0):
+        """Full-image rendering (model/utils.py:249-441, render_viewpoints): the rays [R,3] are cut into
+        chunks of self.n_rays (the reference uses 8192, utils.py:296-299), each chunk runs the fused
+        forward, per-ray results are gathered on the device.  With world_size > 1 the chunks are dealt
+        round-robin to the ranks and the results all-gathered (rendering needs no other exchange).
+        Returns rgb_marched, sigmoid_rgb, depth, disp, normal_marched, alphainv_cum, cum_weights."""
+        R = rays_o.shape[0]
+        N = self.n_rays
+        n_chunks = (R + N - 1) // N
+        dev = self.device
+        keys = [("rgb_marched", 3), ("sigmoid_rgb", 3), ("alphainv_last", 1), ("cum_weights", 1)]
+        if render_depth:
+            keys.append(("depth", 1))
+        if render_grad:
+            keys.append(("normal_marched", 3))
+        out = {k: torch.zeros((n_chunks * N, c), dtype=torch.float32, device=dev) for k, c in keys}
+        ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        for ci in range(rank, n_chunks, world_size):
+            a, b = ci * N, min(R, (ci + 1) * N)
+            chunk = []
+            for t in (rays_o, rays_d, viewdirs):
+                c = t[a:b].contiguous()
+                if b - a < N:                                   # last chunk: pad by repeating its last ray
+                    c = torch.cat([c, c[-1:].expand(N - (b - a), 3)]).contiguous()
+                chunk.append(c)
+            self.forward(*chunk, global_step=global_step, near=near, bg=bg, render_depth=render_depth,
+                         render_grad=render_grad)
+            for k, c in keys:
+                out[k][a:a + N] = self.ws[k].reshape(N, c)
+            ovf |= self.ws["counters"][CNT["OVERFLOW"]]
+        if world_size > 1:
+            import torch.distributed as dist
+            for k in out:
+                dist.all_reduce(out[k])                         # chunks are disjoint across ranks: sum = gather
+            dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
+        if int(ovf.item()):
+            raise RuntimeError(f"fgs_b200 render: workspace overflow (bits {int(ovf.item()):#x}); raise cap_m1/cap_m2")
+        res = {k: v[:R] for k, v in out.items()}
+        res["alphainv_cum"] = res.pop("alphainv_last")[:, 0]
+        res["cum_weights"] = res["cum_weights"][:, 0]
+        if render_depth:
+            res["depth"] = res["depth"][:, 0]
+            res["disp"] = 1 / res["depth"]
+        return res
+
     def set_nonempty_mask(self):
         """nerf._set_nonempty_mask (model/nerf.py:339-353): MaskCache at the voxel centres."""
         X, Y, Z = self.X, self.Y, self.Z

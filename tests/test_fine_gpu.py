@@ -492,3 +492,23 @@ def test_gemm_weight_gradient_kernel(cuda, M, N, K):
                           ptr(rows), stream()))
     torch.cuda.synchronize()
     assert _rel(out[:, :N], A[:K // 2, :M].double().T @ B[:K // 2, :N].double()) < 2e-6
+
+
+def test_chunked_render_matches_oracle_forward(cuda):
+    """engine.render (the render_viewpoints chunk loop, model/utils.py:296-299) over a ragged ray set
+    (2 full chunks + a short one) equals the oracle's forward_fine on the same rays."""
+    from fgs_nerf_b200 import engine, scene
+    native = _native()
+    if native is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scene.make_scene(G=48, mask_G=40)
+    R_total = 2 * 256 + 77
+    ro, rd, vd, _ = [t.to(cuda) for t in scene.make_rays(N=R_total, H=100, W=100, n_views=8)]
+    eng = engine.FineStepEngine(sc, 256, cuda)
+    got = eng.render(ro, rd, vd, global_step=20000, near=2.0, bg=1.0)
+    m = R.FineModel(sc, device=cuda, requires_grad=False)
+    with torch.no_grad():
+        want = R.forward_fine(m, native, ro, rd, vd, 20000, 2.0, 1e9, 0.5, 1.0, render_depth=True, render_grad=True)
+    for k in ("rgb_marched", "sigmoid_rgb", "depth", "normal_marched", "alphainv_cum"):
+        _close(got[k], want[k], "render " + k)
+    assert got["rgb_marched"].shape == (R_total, 3)
