@@ -1,26 +1,31 @@
 // Tensor-core GEMMs "activations x weights" of the colour MLPs (forward  Y = X W^T + b  and
 // backward-data  dX = dZ W): the weight operand arrives PRE-SPLIT and by TMA (sm_100a).
 //
-// Same numerics as gemm_tc.cu (3xTF32 split, 32-k accumulation chunks in alternating TMEM regions,
+// Same numerics as gemm_tc.cu (3xTF32 split, 32-k accumulation chunks in rotating TMEM regions,
 // fp32 register accumulators), different data movement -- each choice below answers a measured
-// cost of the previous version (tools/gemm_phase_probe.py, per-phase clock64 of one CTA):
+// cost of an earlier version (tools/gemm_phase_probe.py, per-phase clock64 of one CTA):
 //   * the 0.45 M MLP weights are split ONCE per step into hi / lo TF32 planes, straight ([out][in],
 //     forward) and transposed ([in][out], dZ*W) -- weight_split_kernel, one launch -- instead of
 //     being re-split from fp32 by every CTA for every k-slab;
-//   * the B (weight) tiles are fetched by TMA: one elected thread issues two
-//     cp.async.bulk.tensor.4d per k-slab (hi, lo).  The 4-D tensor map views a [rows][ld] plane as
-//     (4 floats, 8 rows, k-chunks, row-groups), so the box lands in shared memory exactly in the
-//     canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices, LBO 128, SBO 512): no
-//     registers, no LSU instructions (2048 16-byte cp.async per slab cost 0.65 us of issue time),
-//     completion on an mbarrier (expect_tx), prefetched two slabs ahead across tile boundaries;
-//   * only the A (activation) slab -- one third of the bytes -- takes the load / split / store
-//     path, with a lane-per-row mapping whose 128-bit stores are bank-conflict free;
+//   * the B (weight) tiles are fetched by TMA: one elected thread issues two 2-D
+//     cp.async.bulk.tensor per k-slab (hi, lo planes; box 32 floats x 128 rows, SWIZZLE_128B), no
+//     registers, no LSU instructions, completion on an mbarrier (expect_tx), prefetched two slabs
+//     ahead across tile boundaries;
+//   * THREE roles that only meet at mbarriers: 4 producer warps (activation slab: 128-bit loads, two
+//     slabs in flight -> hi / lo split -> XOR-swizzled st.shared), one issuer thread (TMA + all
+//     tcgen05.mma), 8 consumer warps (drain each finished chunk into registers, then the epilogue).
+//     With producers == consumers (the previous version) the tensor core idled during every drain and
+//     every epilogue: 42 % MMA occupancy inside a tile, 53 us per 27 K x 256 x 256 GEMM;
+//   * four 128-column TMEM regions rotate, so the tensor core runs up to 4 chunks ahead of the drain
+//     and the epilogue of tile t overlaps the MMAs of tile t + 1;
 //   * persistent CTAs (one per SM) loop over the 128-row tiles of the sample dimension, whose
 //     extent is read on the device; TMEM (512 columns) and mbarriers are set up once per CTA;
 //   * ReLU masks travel as BITS: the forward epilogue packs (x > 0) of its 32 columns into one
 //     word per thread, the backward epilogue reads 4 words instead of 128 floats of H;
-//   * the epilogue is transposed through shared memory (32x33 floats per warp) so global stores
-//     are full 128-byte lines (row-per-thread 16-byte stores 1 KB apart cost 11 us per tile).
+//   * the epilogue leaves through TMA: each consumer warp writes its 32 rows x 32 columns as swizzled
+//     128-byte rows (conflict-free 16-byte st.shared) and one lane issues a bulk tensor store
+//     (row-per-thread 16-byte global stores 1 KB apart cost 11 us per tile; a smem transpose with
+//     scalar readback cost 15 K cycles per tile at one warp per scheduler).
 #include <cuda.h>
 
 #include <map>
@@ -32,30 +37,39 @@
 namespace {
 
 constexpr int BM = 128, BK = 32;                    // one k-slab = 32 floats = one 128-byte swizzle row
+constexpr int TN = 128;                              // output columns per CTA (N = 256 -> two column CTAs)
 constexpr int kTmemCols = 512;
+constexpr int kRegions = 4;                          // 4 accumulation regions of 128 TMEM columns
 constexpr uint32_t kATile = BM * BK * 4;             // 16 KB
-// Tile width TN (output columns per CTA) is a template parameter: 256 (2 stages of 96 KB) or 128
-// (3 stages of 64 KB, 64 accumulator registers per thread, 2x the CTAs -> finer wave quantisation).
-constexpr int kChunkSlabs = 1;  // accumulation chunk = one 32-k slab (12 MMAs) per TMEM region
+constexpr uint32_t kBTile = TN * BK * 4;             // 16 KB
+constexpr uint32_t kStage = 2 * kATile + 2 * kBTile; // A_hi, A_lo, B_hi, B_lo = 64 KB
+constexpr int kStages = 3;
+constexpr uint32_t kStagingOff = kStages * kStage;   // 8 consumer warps x (32 rows x 128 bytes), 1024-byte aligned
+constexpr uint32_t kStagingWarp = 32 * 128;
+constexpr uint32_t kStagingBytes = 8 * kStagingWarp;
+constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;  // mbarriers + tmem slot, then the bias slice
+constexpr uint32_t kBiasOff = kBarOff + 256;
+constexpr uint32_t kSmemBytes = kBiasOff + TN * 4;
+constexpr int kAcc = TN / 2;                         // accumulator registers per consumer thread (half a row)
 
-template <int TN>
-struct Cfg {
-  static constexpr uint32_t kBTile = TN * BK * 4;
-  static constexpr uint32_t kStage = 2 * kATile + 2 * kBTile;      // A_hi, A_lo, B_hi, B_lo
-  static constexpr int kStages = (TN == 256) ? 2 : 3;
-  static constexpr uint32_t kStagingOff = kStages * kStage;       // 8 warps x 32 x 33 floats
-  static constexpr uint32_t kStagingBytes = 8 * 32 * 33 * 4;
-  static constexpr uint32_t kBarOff = kStagingOff + kStagingBytes;  // mbarriers + tmem slot
-  static constexpr uint32_t kSmemBytes = kBarOff + 256;
-  static constexpr int kAcc = TN / 2;                               // accumulator registers per worker thread
-};
-
+// Thread roles (13 warps, 128 registers per thread; ptxas does not raise a role's allocation above the
+// kernel-wide cap after setmaxnreg, so the roles are sized to fit it):
+//   warps 0-7    consumers (warp w: TMEM lanes 32 (w % 4).., columns 64 (w / 4)..): drain every finished
+//                32-k chunk from TMEM into fp32 register accumulators (round-to-nearest adds), then the
+//                bias / ReLU / mask epilogue, swizzled st.shared and one TMA store per 32x32 block
+//   warps 8-11   producers: activation slab global -> registers (two slabs in flight) -> hi / lo TF32
+//                split -> swizzled st.shared
+//   warp 12      lane 0 issues TMA (weight planes) and every tcgen05.mma
+constexpr int kConsumers = 256;
+constexpr int kProducers = 128;
+constexpr int kIssuerWarp = (kConsumers + kProducers) / 32;
+constexpr int kThreadsWS = kConsumers + kProducers + 32;
 
 struct WArgs {
   const float* A; float* C;
   const float* bias; const uint32_t* bits_in; uint32_t* bits_out; const int* rows_dev;
-  int M, N, K, lda, ldc, relu;
-  long long* dbg;  // optional phase timing of CTA (0,0) thread 0 (tools/gemm_phase_probe.py)
+  int M, N, K, lda, ldc, relu, c_tma;
+  long long* dbg;  // optional per-role phase timing of CTA (0,0) (tools/gemm_phase_probe.py), 10 values
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,37 +147,189 @@ __global__ void __launch_bounds__(256) weight_split_kernel(const __grid_constant
   }
 }
 
-constexpr int kWorkers = 256;            // warps 0-7: A producers, TMEM drain, epilogue
-constexpr int kThreadsWS = kWorkers + 128; // third warpgroup: warp 8 lane 0 issues TMA (B) and tcgen05.mma;
-                                           // registers are re-balanced with setmaxnreg (40 vs 232 per thread)
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Warp-specialised: the MMA/TMA thread and the 256 workers only meet at mbarriers
-//   a_full[st]   workers -> MMA   (256 arrivals: the A hi/lo slab is stored and proxy-fenced)
-//   b_full[st]   TMA     -> MMA   (expect_tx: B hi/lo bytes landed)
-//   free[st]     MMA     -> all   (tcgen05.commit: the MMAs reading the stage are done)
-//   r_full[r]    MMA     -> workers (tcgen05.commit at the end of a 32-k chunk)
-//   r_empty[r]   workers -> MMA   (256 arrivals: the chunk has been added into registers)
-// so the blocking MMA issue never stalls the producers, and the producers run up to kStages slabs
-// ahead of the tensor core.
-template <int TN>
+// Consumer side of the accumulation: chunk c (one 32-k slab = 12 MMAs) has been committed into TMEM region
+// c % kRegions; add this warp's 64 columns of it into the thread's fp32 register accumulators (its row) and
+// hand the region back.  tmem_row = base + (lane quarter << 16) + column half.
+template <bool PAIRED>
+__device__ __forceinline__ void drain_chunk(float (&acc)[kAcc], uint32_t tmem_row, int col_half, uint32_t c, int BN,
+                                            uint32_t rfull_bar0, uint32_t rempty_bar0) {
+  const uint32_t rg = c % kRegions;
+  mbar_wait(rfull_bar0 + 8 * rg, (c / kRegions) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < kAcc / 32; ++q) {
+    if (col_half + 32 * q < BN) {
+      if (PAIRED) {                         // two 16-column loads in flight
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tmem_row + rg * TN + 32 * q, r0);
+        tmem_ld16(tmem_row + rg * TN + 32 * q + 16, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r0[j]));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[32 * q + 16 + j] = __fadd_rn(acc[32 * q + 16 + j], __uint_as_float(r1[j]));
+      } else {                              // tighter register budget: one load at a time
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[16];
+          tmem_ld16(tmem_row + rg * TN + 32 * q + 16 * h, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            acc[32 * q + 16 * h + j] = __fadd_rn(acc[32 * q + 16 * h + j], __uint_as_float(r0[j]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  mbar_arrive(rempty_bar0 + 8 * rg);   // the region may be overwritten by chunk c + kRegions
+}
+
+// TMA store of one swizzled 32-row x 128-byte block (issued by one lane; completion tracked per thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// hi / lo TF32 split of one 16-byte chunk, stored at the same (swizzled) offset of the hi and lo tiles
+__device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, const float4& v) {
+  float4 hi, lo;
+  hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
+  lo.x = rn_tf32(v.x - hi.x); lo.y = rn_tf32(v.y - hi.y);
+  lo.z = rn_tf32(v.z - hi.z); lo.w = rn_tf32(v.w - hi.w);
+  st_shared_v4(hi_addr, hi);
+  st_shared_v4(lo_addr, lo);
+}
+
+struct Bars {
+  uint32_t free0, bfull0, afull0, rfull0, rempty0;
+};
+__device__ __forceinline__ Bars make_bars(uint32_t smem) {
+  Bars b;
+  b.free0 = smem + kBarOff;
+  b.bfull0 = b.free0 + 8 * kStages;
+  b.afull0 = b.bfull0 + 8 * kStages;
+  b.rfull0 = b.afull0 + 8 * kStages;
+  b.rempty0 = b.rfull0 + 8 * kRegions;
+  return b;
+}
+constexpr uint32_t kTmemSlotOff = kBarOff + 8 * (3 * kStages + 2 * kRegions) + 8;
+
+// TMEM allocation + mbarrier initialisation, common to both kernels; returns the TMEM base address
+__device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const Bars& B, int warp, int tid,
+                                               int n_producers) {
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(B.free0 + 8 * i, 1);
+      mbar_init(B.bfull0 + 8 * i, 1);
+      mbar_init(B.afull0 + 8 * i, n_producers);
+    }
+    for (int i = 0; i < kRegions; ++i) {
+      mbar_init(B.rfull0 + 8 * i, 1);
+      mbar_init(B.rempty0 + 8 * i, kConsumers);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *tmem_slot;
+}
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_d, int warp) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
+// 12 MMAs of one 32-k slab: D (+)= A_lo B_hi + A_hi B_lo + A_hi B_hi per 8-wide k-step, small terms first
+__device__ __forceinline__ void mma_slab(uint32_t d, uint32_t stage_base, uint32_t idesc) {
+  const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+  const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+  for (int j = 0; j < BK / 8; ++j) {
+    // k-step j = bytes [32 j, 32 j + 32) of every 128-byte row (the swizzle is a function of the address)
+    const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+    const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+    mma_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);   // every slab starts a fresh accumulation region
+    mma_tf32(d, dah, dbl, idesc, 1);
+    mma_tf32(d, dah, dbh, idesc, 1);
+  }
+}
+
+// Epilogue arithmetic on one 32-column block of a consumer thread's row, in place.
+template <bool RELU, bool MASK>
+__device__ __forceinline__ uint32_t epilogue_block(float* v, uint32_t bias_addr, bool has_bias, uint32_t in_bits) {
+  uint32_t out_bits = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bias) b = lds4(bias_addr + 16 * j4);           // same address in every lane: a broadcast
+    float x[4] = {v[4 * j4] + b.x, v[4 * j4 + 1] + b.y, v[4 * j4 + 2] + b.z, v[4 * j4 + 3] + b.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = 4 * j4 + t;
+      if (RELU) {
+        if (x[t] > 0.f) out_bits |= 1u << j;
+        x[t] = fmaxf(x[t], 0.f);
+      }
+      if (MASK && !((in_bits >> j) & 1u)) x[t] = 0.f;
+      v[j] = x[t];
+    }
+  }
+  return out_bits;
+}
+
+// Warp-specialised: issuer, producers and consumers only meet at mbarriers
+//   a_full[st]   producers -> MMA     (128 arrivals: the A hi/lo slab is stored and proxy-fenced)
+//   b_full[st]   TMA       -> MMA     (expect_tx: B hi/lo bytes landed)
+//   free[st]     MMA       -> producers, TMA (tcgen05.commit: the MMAs reading the stage are done)
+//   r_full[r]    MMA       -> consumers (tcgen05.commit at the end of a 32-k chunk)
+//   r_empty[r]   consumers -> MMA     (256 arrivals: the chunk has been added into registers)
+// The producers run up to kStages slabs ahead of the tensor core (across tile boundaries), the tensor
+// core up to kRegions chunks ahead of the consumers, so the epilogue of tile t overlaps the MMAs of
+// tile t + 1 and nobody waits for a block-wide barrier.
 __global__ void __launch_bounds__(kThreadsWS, 1)
-gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
-  constexpr uint32_t kBTile = Cfg<TN>::kBTile, kStage = Cfg<TN>::kStage, kStagingOff = Cfg<TN>::kStagingOff,
-                     kBarOff = Cfg<TN>::kBarOff;
-  constexpr int kStages = Cfg<TN>::kStages, kAcc = Cfg<TN>::kAcc, kPfB = kStages - 1;
+gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+              const __grid_constant__ CUtensorMap tm_c) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
-  const uint32_t free_bar0 = smem + kBarOff;
-  const uint32_t bfull_bar0 = free_bar0 + 8 * kStages;
-  const uint32_t afull_bar0 = bfull_bar0 + 8 * kStages;
-  const uint32_t rfull_bar0 = afull_bar0 + 8 * kStages;
-  const uint32_t rempty_bar0 = rfull_bar0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (3 * kStages + 4) + 8);
-  float* staging = reinterpret_cast<float*>(smem_raw + kStagingOff);
+  const Bars B = make_bars(smem);
 
   int M = a.M;
   if (a.rows_dev) M = min(M, *a.rows_dev);
@@ -174,96 +340,111 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
   const int BN = min(TN, (a.N - n0 + 15) & ~15);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(free_bar0 + 8 * i, 1);
-      mbar_init(bfull_bar0 + 8 * i, 1);
-      mbar_init(afull_bar0 + 8 * i, kWorkers);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(rfull_bar0 + 8 * i, 1);
-      mbar_init(rempty_bar0 + 8 * i, kWorkers);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
+  if (tid < TN) reinterpret_cast<float*>(smem_raw + kBiasOff)[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
+  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducers);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)(BM >> 4) << 24);
 
-  const int n_slabs = (K + BK - 1) / BK;
-  const int n_chunks = (n_slabs + kChunkSlabs - 1) / kChunkSlabs;
+  const uint32_t n_slabs = (uint32_t)((K + BK - 1) / BK);
   const int my_tiles = (n_tiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1;
-  const uint32_t total_slabs = (uint32_t)my_tiles * (uint32_t)n_slabs;
+  const uint32_t total_slabs = (uint32_t)my_tiles * n_slabs;
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
-  if (warp >= kWorkers / 32) {
-    // ================= MMA + TMA issuer (one thread of the third warpgroup) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-    if (warp == kWorkers / 32 && lane == 0) {
+  if (warp >= kIssuerWarp) {
+    // ================= MMA + TMA issuer (one thread of warp 12) =================
+    if (warp == kIssuerWarp && lane == 0) {
+      constexpr uint32_t kPfB = kStages - 1;
+      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
       auto issue_b = [&](uint32_t gs) {
         const uint32_t st = gs % kStages;
         const uint32_t b_hi = smem + st * kStage + 2 * kATile, b_lo = b_hi + kBTile;
-        const uint32_t bar = bfull_bar0 + 8 * st;
-        const int k0 = (int)(gs % (uint32_t)n_slabs) * BK;
+        const uint32_t bar = B.bfull0 + 8 * st;
+        const int k0 = (int)(gs % n_slabs) * BK;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBTile) : "memory");
         tma_load_2d(b_hi, &tm_hi, bar, k0, n0);
         tma_load_2d(b_lo, &tm_lo, bar, k0, n0);
       };
-      for (uint32_t gs = 0; gs < (uint32_t)kPfB && gs < total_slabs; ++gs) issue_b(gs);
-      for (uint32_t g = 0; g < total_slabs; ++g) {
+      for (uint32_t gs = 0; gs < kPfB && gs < total_slabs; ++gs) issue_b(gs);
+      for (uint32_t g = 0; g < total_slabs; ++g) {      // global slab index = global chunk index
         const uint32_t st = g % kStages;
         const uint32_t par = (g / kStages) & 1;
-        const uint32_t kt = g % (uint32_t)n_slabs;
-        const uint32_t cg = (g / (uint32_t)n_slabs) * (uint32_t)n_chunks + kt / kChunkSlabs;  // global chunk
-        const bool first_in_chunk = (kt % kChunkSlabs) == 0;
-        const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == (uint32_t)n_slabs - 1;
-        mbar_wait(afull_bar0 + 8 * st, par);
-        mbar_wait(bfull_bar0 + 8 * st, par);
-        if (first_in_chunk && cg >= 2) mbar_wait(rempty_bar0 + 8 * (cg & 1), ((cg >> 1) - 1) & 1);
+        if (dbg_cta) t0 = clock64();
+        mbar_wait(B.afull0 + 8 * st, par);
+        if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+        mbar_wait(B.bfull0 + 8 * st, par);
+        if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
+        if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
+        if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t stage_base = smem + st * kStage;
-        const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
-        const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
-        const uint32_t d = tmem_d + (cg & 1) * 256;
-#pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {
-          // k-step j = bytes [32 j, 32 j + 32) of every 128-byte row (the swizzle is a function of the address)
-          const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
-          const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-          mma_tf32(d, dal, dbh, idesc, (!first_in_chunk || j != 0) ? 1u : 0u);
-          mma_tf32(d, dah, dbl, idesc, 1);
-          mma_tf32(d, dah, dbh, idesc, 1);
-        }
-        mma_commit(free_bar0 + 8 * st);
-        if (last_in_chunk) mma_commit(rfull_bar0 + 8 * (cg & 1));
+        mma_slab(tmem_d + (g % kRegions) * TN, smem + st * kStage, idesc);
+        mma_commit(B.free0 + 8 * st);
+        mma_commit(B.rfull0 + 8 * (g % kRegions));
         const uint32_t gs = g + kPfB;   // B two slabs ahead; its stage was read by slab gs - kStages
         if (gs < total_slabs) {
-          if (gs >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
+          if (dbg_cta) t0 = clock64();
+          if (gs >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
+          if (dbg_cta) t_f += clock64() - t0;
           issue_b(gs);
         }
       }
+      if (dbg_cta) {
+        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
+      }
     }
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers: activation slabs -> hi / lo TF32 tiles =================
+    // warp pw owns tile rows [32 pw, 32 pw + 32); load i (0..7) covers rows 4 i + lane / 8 with lane % 8 =
+    // 16-byte k-chunk: 8 lanes read one full 128-byte row (coalesced), and since chunk c of row r lives at
+    // chunk position c ^ (r % 8) the quarter-warp's stores fill one permuted 128-byte row (conflict-free)
+    const int pw = warp - kConsumers / 32;
+    const int prow = pw * 32 + (lane >> 3), pc = lane & 7;
+    const bool dbg_on = dbg_cta && tid == kConsumers;
+    long long t_wait = 0, t_work = 0, t0 = 0;
+    auto load_a = [&](float4 (&v)[8], uint32_t gs) {
+      if (gs >= total_slabs) return;
+      const int tile = (int)blockIdx.y + (int)(gs / n_slabs) * (int)gridDim.y;
+      const int k = (int)(gs % n_slabs) * BK + 4 * pc;
+      const float* __restrict__ src = a.A + (size_t)(tile * BM + prow) * a.lda + k;
+      const int mleft = M - (tile * BM + prow);          // rows 4 i with 4 i < mleft are valid
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = (4 * i < mleft && k < K) ? ldg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto produce = [&](float4 (&v)[8], uint32_t g) {
+      const uint32_t st = g % kStages;
+      const uint32_t stage_base = smem + st * kStage;
+      if (dbg_on) t0 = clock64();
+      if (g >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
+      if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = prow + 4 * i;
+        const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+        split_store(stage_base + off, stage_base + kATile + off, v[i]);
+      }
+      load_a(v, g + 2);                                  // two slabs stay in flight
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(B.afull0 + 8 * st);
+      if (dbg_on) t_work += clock64() - t0;
+    };
+    float4 v0[8], v1[8];
+    load_a(v0, 0);
+    load_a(v1, 1);
+    for (uint32_t g = 0; g < total_slabs; g += 2) {
+      produce(v0, g);
+      if (g + 1 < total_slabs) produce(v1, g + 1);
+    }
+    if (dbg_on) { a.dbg[3] = t_wait; a.dbg[4] = t_work; }
   } else {
-    // ================= workers: A slabs, TMEM drain, epilogue =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-    const int col_half = (warp >> 2) * kAcc;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    // A slots: thread -> row ar, 16-byte k-chunks ac, ac + 2, ac + 4, ac + 6 of the 128-byte row; chunk c
-    // of row r lives at chunk position c ^ (r % 8), so the 8 rows of a quarter-warp hit 8 distinct
-    // bank groups
-    const int ar = tid & 127, ac = tid >> 7;
-    const uint32_t arow = (uint32_t)(ar * 128);
-    uint32_t g = 0, gc = 0;
+    // ================= consumers: TMEM drain, epilogue =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
+    const uint32_t bias_s = smem + kBiasOff;
+    uint32_t gc = 0;
     long long t_main = 0, t_epi = 0, t0 = 0;
-    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    const bool dbg_on = dbg_cta && tid == 0;
 
     for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
       const int m0 = tile * BM;
@@ -271,125 +452,59 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
       float acc[kAcc];
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-
-      auto load_a = [&](float4 (&v)[4], int k0) {
-        const int m = m0 + ar;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + 4 * (ac + 2 * i);
-          v[i] = (m < M && k < K) ? ldg4(a.A + (size_t)m * a.lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      auto store_a = [&](const float4 (&v)[4], uint32_t stage_base) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t off = arow + (uint32_t)(((ac + 2 * i) ^ (ar & 7)) * 16);
-          float4 hi, lo;
-          hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
-          lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
-          lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
-          st_shared_v4(stage_base + off, hi);
-          st_shared_v4(stage_base + kATile + off, lo);
-        }
-      };
-      auto drain = [&](uint32_t c) {   // c = global chunk index
-        mbar_wait(rfull_bar0 + 8 * (c & 1), (c >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < kAcc / 32; ++q) {
-          if (col_half + 32 * q < BN) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(rempty_bar0 + 8 * (c & 1));   // the region may be overwritten by chunk c + 2
-      };
-
-      float4 a0[4];
-      load_a(a0, 0);
-      for (int kt = 0; kt < n_slabs; ++kt, ++g) {
-        const uint32_t st = g % kStages;
-        const uint32_t stage_base = smem + st * kStage;
-        const int cl = kt / kChunkSlabs;
-        const bool last_in_chunk = (kt % kChunkSlabs) == kChunkSlabs - 1 || kt == n_slabs - 1;
-        if (g >= (uint32_t)kStages) mbar_wait(free_bar0 + 8 * st, ((g / kStages) - 1) & 1);
-        store_a(a0, stage_base);
-        if (kt + 1 < n_slabs) load_a(a0, (kt + 1) * BK);   // in flight during the drain below
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(afull_bar0 + 8 * st);
-        if (last_in_chunk && cl >= 1) drain(gc + cl - 1);
-      }
-      drain(gc + n_chunks - 1);
-      gc += n_chunks;
+      for (uint32_t c = 0; c < n_slabs; ++c) drain_chunk<true>(acc, tmem_row, col_half, gc + c, BN, B.rfull0, B.rempty0);
+      gc += n_slabs;
       if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
 
-      // ---- epilogue: registers -> (bias, ReLU, mask) -> 32x33 smem transpose -> 128-byte row stores ----
-      {
-        const int m = m0 + (warp & 3) * 32 + lane;               // the row this thread accumulated
-        float* stg = staging + warp * (32 * 33);
+      // ---- epilogue: (bias, ReLU, mask) in registers -> swizzled 32 x 128-byte block -> one TMA store ----
+      const int mr0 = m0 + quarter * 32;
+      const int m = mr0 + lane;                                  // the row this thread accumulated
 #pragma unroll
-        for (int q = 0; q < kAcc / 32; ++q) {
-          const int c0 = col_half + 32 * q;
-          if (c0 < BN) {
-            const int col = n0 + c0 + lane;                      // the column this lane stores
-            const int word = (n0 + c0) >> 5;
-            const float bcol = (a.bias && col < a.N) ? __ldg(a.bias + col) : 0.f;
-            uint32_t in_bits = 0xffffffffu, out_bits = 0;
-            if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
+      for (int q = 0; q < kAcc / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+          const int word = (n0 + c0) >> 5;
+          uint32_t in_bits = 0xffffffffu, out_bits = 0;
+          if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
+          float* v = acc + 32 * q;
+          const uint32_t baddr = bias_s + 4 * c0;
+          const bool hb = a.bias != nullptr;
+          if (a.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
+          else if (a.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
+          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
+          if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
+          if (a.c_tma && mr0 + 32 <= M) {
+            if (lane == 0) tma_store_wait_read();                // the previous block has left the staging tile
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = acc[32 * q + j] + __shfl_sync(0xffffffffu, bcol, j);
-              if (a.relu) {
-                if (x > 0.f) out_bits |= 1u << j;
-                x = fmaxf(x, 0.f);
-              }
-              if (!((in_bits >> j) & 1u)) x = 0.f;
-              stg[lane * 33 + j] = x;
-            }
-            if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
+            for (int j4 = 0; j4 < 8; ++j4)
+              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
+                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (col < a.N) {
-              const int mr0 = m0 + (warp & 3) * 32;
-              float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r)
-                if (mr0 + r < M) cp[(size_t)r * a.ldc] = stg[r * 33 + lane];
-            }
-            __syncwarp();
+            if (lane == 0) tma_store_2d(&tm_c, stg, n0 + c0, mr0);   // columns >= N are clipped by the map
+          } else if (m < M) {
+            // the 32-row block straddles the device-side row count (or C is not TMA-addressable): row stores
+            float* __restrict__ cp = a.C + (size_t)m * a.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < a.N) cp[j] = v[j];
           }
         }
       }
       if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
     }
-    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
+    if (lane == 0) tma_store_wait_all();
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; a.dbg[2] = 0; }
   }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
-  }
+  cta_teardown(tmem_d, warp);
 }
 
 // ---- backward-weight GEMM:  C[M,N] += A[K,M]^T B[K,N]  (dW = dZ^T X), split over the samples ----------
 // Same machinery (warp-specialised, SWIZZLE_128B tiles, 32-k accumulation chunks, register
 // accumulators), but the reduction index is the SAMPLE dimension, which is the slow dimension of both
 // row-major operands.  kind::tf32 cannot read MN-major tiles without the 128B_BASE32B swizzle, so the
-// 256 workers transpose both operands on the fly: coalesced 32-bit loads along the feature dimension
+// 256 producers transpose both operands on the fly: coalesced 32-bit loads along the feature dimension
 // (a warp reads 128 contiguous bytes of one sample row), four consecutive samples of one feature form
 // the 16-byte chunk that is split into hi / lo and stored to the swizzled K-major tile.  The bias
 // gradient (column sums of dZ) rides along with the A loads.  Partial products of the K-splits are
@@ -399,19 +514,15 @@ struct TnArgs {
   int M, N, K, lda, ldb, ldc;
 };
 
-__global__ void __launch_bounds__(kThreadsWS, 1) gemm_tn_kernel(const TnArgs a) {
-  constexpr int TN = 128;
-  constexpr uint32_t kBTile = Cfg<TN>::kBTile, kStage = Cfg<TN>::kStage, kStagingOff = Cfg<TN>::kStagingOff,
-                     kBarOff = Cfg<TN>::kBarOff;
-  constexpr int kStages = Cfg<TN>::kStages, kAcc = Cfg<TN>::kAcc;
+// 8 consumer warps + 8 producer warps (the transposing loads are 32-bit: twice the producers of gemm_w) + issuer
+constexpr int kProducersTn = 256;
+constexpr int kIssuerWarpTn = (kConsumers + kProducersTn) / 32;
+constexpr int kThreadsTn = kConsumers + kProducersTn + 32;
+
+__global__ void __launch_bounds__(kThreadsTn, 1) gemm_tn_kernel(const TnArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
-  const uint32_t free_bar0 = smem + kBarOff;
-  const uint32_t afull_bar0 = free_bar0 + 8 * kStages;
-  const uint32_t rfull_bar0 = afull_bar0 + 8 * kStages;
-  const uint32_t rempty_bar0 = rfull_bar0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBarOff + 8 * (2 * kStages + 4) + 8);
-  float* staging = reinterpret_cast<float*>(smem_raw + kStagingOff);
+  const Bars B = make_bars(smem);
 
   int K = a.K;
   if (a.rows_dev) K = min(K, *a.rows_dev);
@@ -424,67 +535,31 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gemm_tn_kernel(const TnArgs a) 
   const int BN = min(TN, (a.N - n0 + 15) & ~15);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(free_bar0 + 8 * i, 1);
-      mbar_init(afull_bar0 + 8 * i, kWorkers);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(rfull_bar0 + 8 * i, 1);
-      mbar_init(rempty_bar0 + 8 * i, kWorkers);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersTn);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)(BM >> 4) << 24);
-  const int n_slabs = (kend - kbeg + BK - 1) / BK;
+  const uint32_t n_slabs = (uint32_t)((kend - kbeg + BK - 1) / BK);
 
-  if (warp >= kWorkers / 32) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-    if (warp == kWorkers / 32 && lane == 0) {
-      for (int kt = 0; kt < n_slabs; ++kt) {
-        const uint32_t st = (uint32_t)kt % kStages;
-        mbar_wait(afull_bar0 + 8 * st, ((uint32_t)kt / kStages) & 1);
-        if (kt >= 2) mbar_wait(rempty_bar0 + 8 * (kt & 1), ((kt >> 1) - 1) & 1);
+  if (warp >= kIssuerWarpTn) {
+    if (warp == kIssuerWarpTn && lane == 0) {
+      for (uint32_t g = 0; g < n_slabs; ++g) {
+        const uint32_t st = g % kStages;
+        mbar_wait(B.afull0 + 8 * st, (g / kStages) & 1);
+        if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t stage_base = smem + st * kStage;
-        const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
-        const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
-        const uint32_t d = tmem_d + (uint32_t)(kt & 1) * 256;
-#pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
-          const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-          mma_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
-          mma_tf32(d, dah, dbl, idesc, 1);
-          mma_tf32(d, dah, dbh, idesc, 1);
-        }
-        mma_commit(free_bar0 + 8 * st);
-        mma_commit(rfull_bar0 + 8 * (kt & 1));
+        mma_slab(tmem_d + (g % kRegions) * TN, smem + st * kStage, idesc);
+        mma_commit(B.free0 + 8 * st);
+        mma_commit(B.rfull0 + 8 * (g % kRegions));
       }
     }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-    const int col_half = (warp >> 2) * kAcc;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int ar = tid & 127, ac = tid >> 7;           // tile row (feature) and first 16-byte chunk
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers: transpose + split both operands =================
+    // thread -> tile row (feature) ar and 16-byte chunks ac, ac + 2, ac + 4, ac + 6 (4 consecutive samples
+    // each); a warp's 32-bit loads of one sample row are 128 contiguous bytes
+    const int ptid = tid - kConsumers;
+    const int ar = ptid & 127, ac = ptid >> 7;
     const uint32_t arow = (uint32_t)(ar * 128);
-    float acc[kAcc];
-#pragma unroll
-    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
     float csum = 0.f;
-
-    // 4 consecutive samples k .. k+3 of feature (f0 + ar): one 16-byte chunk of the K-major tile
     auto load_t = [&](float4 (&v)[4], const float* __restrict__ src, int ld, int f0, int fmax, int k0) {
       const int f = f0 + ar;
 #pragma unroll
@@ -501,124 +576,93 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gemm_tn_kernel(const TnArgs a) 
         v[i] = x;
       }
     };
-    auto store_t = [&](const float4 (&v)[4], uint32_t hi_base, uint32_t lo_base) {
+    auto load_ab = [&](float4 (&va)[4], float4 (&vb)[4], uint32_t g) {
+      if (g >= n_slabs) return;
+      load_t(va, a.A, a.lda, m0, a.M, kbeg + (int)g * BK);
+      load_t(vb, a.B, a.ldb, n0, a.N, kbeg + (int)g * BK);
+    };
+    auto produce = [&](float4 (&va)[4], float4 (&vb)[4], uint32_t g) {
+      const uint32_t st = g % kStages;
+      const uint32_t stage_base = smem + st * kStage;
+      if (g >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        csum += (va[i].x + va[i].y) + (va[i].z + va[i].w);
         const uint32_t off = arow + (uint32_t)(((ac + 2 * i) ^ (ar & 7)) * 16);
-        float4 hi, lo;
-        hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
-        lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y);
-        lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
-        st_shared_v4(hi_base + off, hi);
-        st_shared_v4(lo_base + off, lo);
+        split_store(stage_base + off, stage_base + kATile + off, va[i]);
+        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBTile + off, vb[i]);
       }
-    };
-    auto drain = [&](uint32_t c) {
-      mbar_wait(rfull_bar0 + 8 * (c & 1), (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int q = 0; q < kAcc / 32; ++q) {
-        if (col_half + 32 * q < BN) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_d + lane_base + (uint32_t)((c & 1) * 256 + col_half + 32 * q);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[32 * q + j] = __fadd_rn(acc[32 * q + j], __uint_as_float(r[j]));
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(rempty_bar0 + 8 * (c & 1));
-    };
-
-    float4 va[4], vb[4];
-    load_t(va, a.A, a.lda, m0, a.M, kbeg);
-    load_t(vb, a.B, a.ldb, n0, a.N, kbeg);
-    for (int kt = 0; kt < n_slabs; ++kt) {
-      const uint32_t st = (uint32_t)kt % kStages;
-      const uint32_t stage_base = smem + st * kStage;
-      if (kt >= kStages) mbar_wait(free_bar0 + 8 * st, (((uint32_t)kt / kStages) - 1) & 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) csum += (va[i].x + va[i].y) + (va[i].z + va[i].w);
-      store_t(va, stage_base, stage_base + kATile);
-      store_t(vb, stage_base + 2 * kATile, stage_base + 2 * kATile + kBTile);
-      if (kt + 1 < n_slabs) {
-        load_t(va, a.A, a.lda, m0, a.M, kbeg + (kt + 1) * BK);
-        load_t(vb, a.B, a.ldb, n0, a.N, kbeg + (kt + 1) * BK);
-      }
+      load_ab(va, vb, g + 2);                            // two slabs stay in flight
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(afull_bar0 + 8 * st);
-      if (kt >= 1) drain((uint32_t)kt - 1);
+      mbar_arrive(B.afull0 + 8 * st);
+    };
+    float4 va0[4], vb0[4], va1[4], vb1[4];
+    load_ab(va0, vb0, 0);
+    load_ab(va1, vb1, 1);
+    for (uint32_t g = 0; g < n_slabs; g += 2) {
+      produce(va0, vb0, g);
+      if (g + 1 < n_slabs) produce(va1, vb1, g + 1);
     }
-    drain((uint32_t)n_slabs - 1);
-
     if (a.colsum && blockIdx.x == 0 && m0 + ar < a.M && csum != 0.f) atomicAdd(a.colsum + m0 + ar, csum);
+  } else {
+    // ================= consumers: TMEM drain, red.global.add epilogue =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    float acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+    for (uint32_t c = 0; c < n_slabs; ++c) drain_chunk<false>(acc, tmem_row, col_half, c, BN, B.rfull0, B.rempty0);
 
-    // ---- epilogue: registers -> 32x33 smem transpose -> 128-byte red.global.add rows ----
-    float* stg = staging + warp * (32 * 33);
+    // ---- epilogue: registers -> 32x32 smem transpose (XOR-swizzled columns) -> 128-byte red.global.add rows ----
+    float* stg = reinterpret_cast<float*>(smem_raw + kStagingOff + warp * kStagingWarp);
 #pragma unroll
     for (int q = 0; q < kAcc / 32; ++q) {
       const int c0 = col_half + 32 * q;
       if (c0 < BN) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = acc[32 * q + j];
+        for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = acc[32 * q + j];
         __syncwarp();
         const int col = n0 + c0 + lane;
         if (col < a.N) {
-          const int mr0 = m0 + (warp & 3) * 32;
+          const int mr0 = m0 + quarter * 32;
           float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
 #pragma unroll 8
           for (int r = 0; r < 32; ++r)
-            if (mr0 + r < a.M) atomicAdd(cp + (size_t)r * a.ldc, stg[r * 33 + lane]);
+            if (mr0 + r < a.M) atomicAdd(cp + (size_t)r * a.ldc, stg[r * 32 + (lane ^ r)]);
         }
         __syncwarp();
       }
     }
   }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
-  }
+  cta_teardown(tmem_d, warp);
 }
 
 long long* g_dbg = nullptr;
-int g_tile_n = 128;   // 128 or 256 (fgs_debug_gemm_tile_n)
 
-template <int TN>
-int configure_once() {
-  static bool configured = false;
+template <typename Kern>
+int configure_once(Kern kern, bool& configured, const char* what) {
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_w_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg<TN>::kSmemBytes);
-    if (e != cudaSuccess) return fgs::check_cuda(e, "gemm_w smem attribute");
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return fgs::check_cuda(e, what);
     configured = true;
   }
   return 0;
 }
 
-// 2-D tensor map of a K-major fp32 plane [rows_alloc][ld]; box = (32 floats, 256 rows) = one k-slab of
-// 256 rows, written to shared memory as 128-byte rows with the 128B swizzle -- the UMMA K-major
+// 2-D tensor map of a K-major fp32 plane [rows_alloc][ld]; box = (32 floats, 128 rows) = one k-slab of
+// 128 rows, written to shared memory as 128-byte rows with the 128B swizzle -- the UMMA K-major
 // SWIZZLE_128B layout.  (A first version used a 4-D map producing the no-swizzle core-matrix layout;
 // its 16-byte inner box made TMA the bottleneck: ~1.4 us per 32 KB slab.)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-std::map<std::tuple<const void*, int, int, int>, CUtensorMap> g_maps;
+std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
 
-int get_map(const float* plane, int rows_alloc, int ld, int tn, CUtensorMap* out) {
-  auto key = std::make_tuple((const void*)plane, rows_alloc, ld, tn);
+// 2-D map of a row-major fp32 matrix: `cols` valid columns (dim 0), `rows` rows of pitch ld floats; box =
+// (32 floats, box_rows rows), SWIZZLE_128B.  Out-of-range box elements read as zero / are not written.
+int get_map(const float* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out) {
+  auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -632,19 +676,20 @@ int get_map(const float* plane, int rows_alloc, int ld, int tn, CUtensorMap* out
       return fgs::check_cuda(e != cudaSuccess ? e : cudaErrorUnknown, "cuTensorMapEncodeTiled lookup");
     g_encode = (EncodeTiledFn)fn;
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_alloc};
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};                           // bytes, dim 1
-  const cuuint32_t box[2] = {BK, (cuuint32_t)tn};
+  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
   CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) rows %d ld %d", (int)r,
-             rows_alloc, ld);
+    snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) cols %d rows %d ld %d",
+             (int)r, cols, rows, ld);
     return FGS_E_BADARG;
   }
+  if (g_maps.size() > 4096) g_maps.clear();   // the fused step uses ~50 distinct maps; tests may churn through more
   g_maps[key] = tm;
   *out = tm;
   return 0;
@@ -667,24 +712,25 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)Bh | (uintptr_t)Bl) & 15))
     return fgs::fail_arg("gemm_w needs 16-byte aligned operands with leading dimensions % 4 == 0");
   if (K > ldb) return fgs::fail_arg("gemm_w: K exceeds the weight plane's row length");
-  // tile width: 128-wide tiles double the CTA count; pick them when that fills the last wave better
   const int n_tiles = fgs::cdiv(M, BM);
-  const int tn = (N > 128 && g_tile_n != 256) ? 128 : 256;
-  int rc = (tn == 128) ? configure_once<128>() : configure_once<256>();
+  static bool configured = false;
+  int rc = configure_once(gemm_w_kernel, configured, "gemm_w smem attribute");
   if (rc) return rc;
   CUtensorMap tm_hi, tm_lo;
   const int rows_alloc = (N + 7) & ~7;
-  if ((rc = get_map(Bh, rows_alloc, ldb, tn, &tm_hi))) return rc;
-  if ((rc = get_map(Bl, rows_alloc, ldb, tn, &tm_lo))) return rc;
-  WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, g_dbg};
-  const int nx = fgs::cdiv(N, tn);
+  if ((rc = get_map(Bh, ldb, rows_alloc, ldb, TN, &tm_hi))) return rc;
+  if ((rc = get_map(Bl, ldb, rows_alloc, ldb, TN, &tm_lo))) return rc;
+  // C leaves through TMA when its rows are 16-byte aligned (always, inside the fused step)
+  const int c_tma = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0) ? 1 : 0;
+  CUtensorMap tm_c = tm_hi;
+  if (c_tma && (rc = get_map(C, N, M, ldc, 32, &tm_c))) return rc;
+  WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, c_tma, g_dbg};
+  // persistent CTAs: one per SM, nx column blocks x ny row-tile walkers
+  const int nx = fgs::cdiv(N, TN);
   int ny = FGS_NUM_SMS / nx;
   if (ny > n_tiles) ny = n_tiles;
   if (ny < 1) ny = 1;
-  if (tn == 128)
-    gemm_w_kernel<128><<<dim3(nx, ny, 1), kThreadsWS, Cfg<128>::kSmemBytes, st>>>(a, tm_hi, tm_lo);
-  else
-    gemm_w_kernel<256><<<dim3(nx, ny, 1), kThreadsWS, Cfg<256>::kSmemBytes, st>>>(a, tm_hi, tm_lo);
+  gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo, tm_c);
   return fgs::check_launch("gemm_w", st);
 }
 
@@ -693,21 +739,17 @@ int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ld
             float* colsum, const int32_t* rows_dev, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg<128>::kSmemBytes);
-    if (e != cudaSuccess) return fgs::check_cuda(e, "gemm_tn smem attribute");
-    configured = true;
-  }
+  int rc = configure_once(gemm_tn_kernel, configured, "gemm_tn smem attribute");
+  if (rc) return rc;
   TnArgs a{A, B, C, colsum, rows_dev, M, N, K, lda, ldb, ldc};
-  dim3 grid(fgs::cdiv(N, 128), fgs::cdiv(M, BM), 1);
+  dim3 grid(fgs::cdiv(N, TN), fgs::cdiv(M, BM), 1);
   const int tiles = grid.x * grid.y;
-  int splits = (FGS_NUM_SMS + tiles - 1) / tiles;
+  int splits = FGS_NUM_SMS / tiles;                 // one wave: every CTA owns an SM (smem, 512 TMEM columns)
   const int max_splits = fgs::cdiv(K, 4 * BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   grid.z = splits;
-  gemm_tn_kernel<<<grid, kThreadsWS, Cfg<128>::kSmemBytes, st>>>(a);
+  gemm_tn_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
   return fgs::check_launch("gemm_tn", st);
 }
 
@@ -760,17 +802,10 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
   return fine::gemm_w(M, N, K, A, lda, job.hi, job.lo, kp, C, ldc, bias, relu, bits_in, bits_out, rows_dev, st);
 }
 
-// Debug: device buffer of 2 int64 that the next gemm_w launches fill with the clock cycles worker 0 of
-// CTA (0,0) spent in main loops and in epilogues (NULL switches it off).
+// Debug: device buffer of 2 int64 that the next gemm_w launches fill with the clock cycles consumer 0 of
+// CTA (0,0) spent draining chunks (incl. waiting for the tensor core) and in epilogues (NULL switches it off).
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
-  return 0;
-}
-
-// Debug / tuning: output-tile width of the pre-split GEMM (128 or 256 columns per CTA).
-extern "C" int fgs_debug_gemm_tile_n(int tn) {
-  FGS_REQUIRE(tn == 128 || tn == 256, "tile width must be 128 or 256");
-  g_tile_n = tn;
   return 0;
 }
 

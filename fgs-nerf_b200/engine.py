@@ -92,7 +92,6 @@ _lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
 _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
-_lib.declare("fgs_debug_gemm_tile_n", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])

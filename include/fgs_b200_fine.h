@@ -195,7 +195,7 @@ int fgs_gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const fl
                 const int32_t* rows_dev, fgs_stream_t stream);
 
 /* modes 0 / 1 with the weight operand B split once into TF32 hi / lo planes (internal scratch) and
- * streamed with cp.async -- the kernel the fused step uses for X*W^T and dZ*W.  bits_out (mode 0,
+ * streamed by TMA -- the kernel the fused step uses for X*W^T and dZ*W.  bits_out (mode 0,
  * relu) receives the ReLU mask as [M][8] words; bits_in (may be NULL) masks the result. */
 int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                  float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
@@ -206,11 +206,10 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
 int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
 
-/* Debug aid: 2 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
- * worker 0 of CTA (0,0) spent in its main loops and in its epilogues (NULL = off). */
+/* Debug aid: 10 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
+ * the roles of CTA (0,0) spent per phase (consumer drain / epilogue, producer wait / work, issuer waits on
+ * a_full / b_full / r_empty / free, issuer total; tools/gemm_phase_probe.py).  NULL = off. */
 int fgs_debug_gemm_phases(void* buf);
-/* Tuning aid: output-tile width (128 or 256 columns per CTA) of the pre-split GEMM. */
-int fgs_debug_gemm_tile_n(int tn);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);

@@ -8,7 +8,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
-__global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int iters, int kind_f16, long long* out) {
+__global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int iters, int kind_f16, int a_tmem, long long* out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 200000);
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + 200016);
@@ -39,7 +39,13 @@ __global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int it
       for (int j = 0; j < 6; ++j) {
         const uint64_t da = make_desc(base + (j & 1) * 320 + (j >> 1) * 16384, lbo, sbo, layout);
         const uint64_t db = make_desc(base + 65536 + (j & 1) * 320 + (j >> 1) * 32768, lbo, sbo, layout);
-        if (kind_f16)
+        if (a_tmem) {   // A operand from TMEM (lane = row, 8 columns = one K8 step), D in columns [0, N)
+          const uint32_t ta = tmem + 256 + (uint32_t)j * 8;
+          if (kind_f16)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(ta), "l"(db), "r"(idesc), "r"(1u) : "memory");
+          else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(ta), "l"(db), "r"(idesc), "r"(1u) : "memory");
+        } else if (kind_f16)
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (it & 1) * 256), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
         else
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (it & 1) * 256), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
@@ -61,17 +67,24 @@ int main() {
   long long* d; cudaMalloc(&d, 64); long long h[3];
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 201000);
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
-  struct V { int N; uint32_t lbo, sbo, layout; int f16; const char* name; } vs[] = {
+  struct V { int N; uint32_t lbo, sbo, layout; int f16; const char* name; int a_tmem; } vs[] = {
     {256, 128, 512, 0, 0, "tf32 N=256 no-swizzle lbo128 sbo512"},
     {256, 160, 640, 0, 0, "tf32 N=256 no-swizzle lbo160 sbo640"},
     {128, 160, 640, 0, 0, "tf32 N=128 no-swizzle lbo160 sbo640"},
     {256, 16, 1024, 2, 0, "tf32 N=256 swizzle128B (sbo 1024)"},
     {256, 128, 512, 0, 1, "bf16 N=256 K16 no-swizzle lbo128 sbo512"},
     {256, 16, 1024, 2, 1, "bf16 N=256 K16 swizzle128B"},
+    {128, 16, 1024, 2, 0, "tf32 N=128 swizzle128B"},
+    {64, 16, 1024, 2, 0, "tf32 N=64 swizzle128B"},
+    {256, 16, 1024, 2, 0, "tf32 N=256 swizzle128B, A from TMEM", 1},
+    {128, 16, 1024, 2, 0, "tf32 N=128 swizzle128B, A from TMEM", 1},
+    {256, 16, 1024, 2, 1, "bf16 N=256 K16 swizzle128B, A from TMEM", 1},
+    {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B, A from TMEM", 1},
+    {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B"},
   };
   for (auto& v : vs) {
     const int iters = 2000;
-    bench<<<1, 128, 201000>>>(v.N, v.lbo, v.sbo, v.layout, iters, v.f16, d);
+    bench<<<1, 128, 201000>>>(v.N, v.lbo, v.sbo, v.layout, iters, v.f16, v.a_tmem, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", v.name, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
