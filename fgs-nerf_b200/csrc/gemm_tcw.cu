@@ -500,6 +500,220 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
   cta_teardown(tmem_d, warp);
 }
 
+// ---- fast variant: whole-K accumulation in TMEM, 256-column tiles --------------------------------------
+// gemm_w_kernel keeps the tensor core's accumulation chains short (12 MMAs, then a round-to-nearest add on
+// the CUDA cores) because the TMEM accumulator truncates at every MMA; that costs 128-column tiles (the
+// register accumulators), a TMEM drain per 32 k and half-rate-sized MMAs (M128 N128 K8 takes 107 cycles,
+// N256 171: tools/umma_bench).  This variant lets one accumulator take all K (96-120 MMAs: error ~3e-6
+// of max|out| instead of 3e-7, both far inside the 1e-4 bar), which frees the structure:
+//   * 128 x 256 output tiles, one M128 N256 K8 MMA per product: 25 % fewer tensor-core cycles per FLOP and
+//     the activation slab is loaded / split once instead of once per column half;
+//   * two 256-column TMEM regions ping-pong between TILES: the consumers' only job is the epilogue of
+//     tile t (TMEM -> bias / ReLU / mask -> swizzled smem -> TMA store) while tile t + 1 multiplies;
+//   * 8 producer warps, 8 consumer warps, 1 issuer warp (96 registers each, nobody holds accumulators).
+constexpr int TNF = 256;
+constexpr uint32_t kBTileF = TNF * BK * 4;                  // 32 KB
+constexpr uint32_t kStageF = 2 * kATile + 2 * kBTileF;      // 96 KB
+constexpr int kStagesF = 2;
+static_assert(kStagesF * kStageF == kStagingOff, "staging / barrier offsets are shared with gemm_w_kernel");
+constexpr uint32_t kSmemBytesF = kBiasOff + TNF * 4;
+constexpr int kProducersF = 256;
+constexpr int kIssuerWarpF = (kConsumers + kProducersF) / 32;
+constexpr int kThreadsF = kConsumers + kProducersF + 32;
+
+__global__ void __launch_bounds__(kThreadsF, 1)
+gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const __grid_constant__ CUtensorMap tm_c) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const Bars B = make_bars(smem);
+
+  int M = a.M;
+  if (a.rows_dev) M = min(M, *a.rows_dev);
+  const int n0 = blockIdx.x * TNF;
+  const int n_tiles = (M + BM - 1) / BM;
+  if ((int)blockIdx.y >= n_tiles) return;
+  const int K = a.K;
+  const int BN = min(TNF, (a.N - n0 + 15) & ~15);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < TNF) reinterpret_cast<float*>(smem_raw + kBiasOff)[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
+  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersF);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                         ((uint32_t)(BM >> 4) << 24);
+
+  const uint32_t n_slabs = (uint32_t)((K + BK - 1) / BK);
+  const int my_tiles = (n_tiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1;
+  const uint32_t total_slabs = (uint32_t)my_tiles * n_slabs;
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+
+  if (warp >= kIssuerWarpF) {
+    // ================= MMA + TMA issuer =================
+    if (warp == kIssuerWarpF && lane == 0) {
+      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
+      const int n_boxes = BN > 128 ? 2 : 1;               // weight rows arrive in boxes of 128
+      auto issue_b = [&](uint32_t gs) {
+        const uint32_t st = gs % kStagesF;
+        const uint32_t b_hi = smem + st * kStageF + 2 * kATile, b_lo = b_hi + kBTileF;
+        const uint32_t bar = B.bfull0 + 8 * st;
+        const int k0 = (int)(gs % n_slabs) * BK;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_boxes * 2 * kBTile) : "memory");
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          tma_load_2d(b_hi + bx * kBTile, &tm_hi, bar, k0, n0 + 128 * bx);
+          tma_load_2d(b_lo + bx * kBTile, &tm_lo, bar, k0, n0 + 128 * bx);
+        }
+      };
+      issue_b(0);
+      for (uint32_t g = 0; g < total_slabs; ++g) {
+        const uint32_t st = g % kStagesF;
+        const uint32_t par = (g / kStagesF) & 1;
+        const uint32_t lt = g / n_slabs, kt = g % n_slabs, rg = lt & 1;   // local tile, slab, TMEM region
+        if (dbg_cta) t0 = clock64();
+        mbar_wait(B.afull0 + 8 * st, par);
+        if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+        mbar_wait(B.bfull0 + 8 * st, par);
+        if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
+        if (kt == 0 && lt >= 2) mbar_wait(B.rempty0 + 8 * rg, ((lt >> 1) - 1) & 1);
+        if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+          const uint32_t stage_base = smem + st * kStageF, d = tmem_d + rg * TNF;
+          const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTileF;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+            const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+            mma_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);   // a tile starts a fresh accumulator
+            mma_tf32(d, dah, dbl, idesc, 1);
+            mma_tf32(d, dah, dbh, idesc, 1);
+          }
+        }
+        mma_commit(B.free0 + 8 * st);
+        if (kt == n_slabs - 1) mma_commit(B.rfull0 + 8 * rg);
+        const uint32_t gs = g + 1;     // next slab's weights; its stage was read by slab g - 1
+        if (gs < total_slabs) {
+          if (dbg_cta) t0 = clock64();
+          if (gs >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * (gs % kStagesF), ((gs / kStagesF) - 1) & 1);
+          if (dbg_cta) t_f += clock64() - t0;
+          issue_b(gs);
+        }
+      }
+      if (dbg_cta) {
+        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
+      }
+    }
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers: activation slabs -> hi / lo TF32 tiles =================
+    // warp pw owns tile rows [16 pw, 16 pw + 16); load i (0..3) covers rows 4 i + lane / 8, lane % 8 = k-chunk
+    const int pw = warp - kConsumers / 32;
+    const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
+    const bool dbg_on = dbg_cta && tid == kConsumers;
+    long long t_wait = 0, t_work = 0, t0 = 0;
+    auto load_a = [&](float4 (&v)[4], uint32_t gs) {
+      if (gs >= total_slabs) return;
+      const int tile = (int)blockIdx.y + (int)(gs / n_slabs) * (int)gridDim.y;
+      const int k = (int)(gs % n_slabs) * BK + 4 * pc;
+      const float* __restrict__ src = a.A + (size_t)(tile * BM + prow) * a.lda + k;
+      const int mleft = M - (tile * BM + prow);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        v[i] = (4 * i < mleft && k < K) ? ldg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto produce = [&](float4 (&v)[4], uint32_t g) {
+      const uint32_t st = g % kStagesF;
+      const uint32_t stage_base = smem + st * kStageF;
+      if (dbg_on) t0 = clock64();
+      if (g >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
+      if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = prow + 4 * i;
+        const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+        split_store(stage_base + off, stage_base + kATile + off, v[i]);
+      }
+      load_a(v, g + 2);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(B.afull0 + 8 * st);
+      if (dbg_on) t_work += clock64() - t0;
+    };
+    float4 v0[4], v1[4];
+    load_a(v0, 0);
+    load_a(v1, 1);
+    for (uint32_t g = 0; g < total_slabs; g += 2) {
+      produce(v0, g);
+      if (g + 1 < total_slabs) produce(v1, g + 1);
+    }
+    if (dbg_on) { a.dbg[3] = t_wait; a.dbg[4] = t_work; }
+  } else {
+    // ================= consumers: epilogue of tile t while tile t + 1 multiplies =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * (TNF / 2);
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
+    const uint32_t bias_s = smem + kBiasOff;
+    long long t_main = 0, t_epi = 0, t0 = 0;
+    const bool dbg_on = dbg_cta && tid == 0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y, ++lt) {
+      const int m0 = tile * BM;
+      const uint32_t rg = lt & 1;
+      if (dbg_on) t0 = clock64();
+      mbar_wait(B.rfull0 + 8 * rg, (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+      const int mr0 = m0 + quarter * 32;
+      const int m = mr0 + lane;
+#pragma unroll 1
+      for (int q = 0; q < TNF / 2 / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+          float v[32];
+          {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
+            tmem_ld16(tmem_row + rg * TNF + 32 * q + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
+          }
+          const int word = (n0 + c0) >> 5;
+          uint32_t in_bits = 0xffffffffu, out_bits = 0;
+          if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
+          const uint32_t baddr = bias_s + 4 * c0;
+          const bool hb = a.bias != nullptr;
+          if (a.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
+          else if (a.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
+          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
+          if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
+          if (a.c_tma && mr0 + 32 <= M) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
+                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&tm_c, stg, n0 + c0, mr0);
+          } else if (m < M) {
+            float* __restrict__ cp = a.C + (size_t)m * a.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < a.N) cp[j] = v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(B.rempty0 + 8 * rg);                 // tile t + 2 may overwrite the region
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; a.dbg[2] = 0; }
+  }
+  cta_teardown(tmem_d, warp);
+}
+
 // ---- backward-weight GEMM:  C[M,N] += A[K,M]^T B[K,N]  (dW = dZ^T X), split over the samples ----------
 // Same machinery (warp-specialised, SWIZZLE_128B tiles, 32-k accumulation chunks, register
 // accumulators), but the reduction index is the SAMPLE dimension, which is the slow dimension of both
@@ -638,11 +852,12 @@ __global__ void __launch_bounds__(kThreadsTn, 1) gemm_tn_kernel(const TnArgs a) 
 }
 
 long long* g_dbg = nullptr;
+int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
 template <typename Kern>
-int configure_once(Kern kern, bool& configured, const char* what) {
+int configure_once(Kern kern, bool& configured, const char* what, uint32_t smem_bytes) {
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return fgs::check_cuda(e, what);
     configured = true;
   }
@@ -713,8 +928,10 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
     return fgs::fail_arg("gemm_w needs 16-byte aligned operands with leading dimensions % 4 == 0");
   if (K > ldb) return fgs::fail_arg("gemm_w: K exceeds the weight plane's row length");
   const int n_tiles = fgs::cdiv(M, BM);
-  static bool configured = false;
-  int rc = configure_once(gemm_w_kernel, configured, "gemm_w smem attribute");
+  const bool fast = g_tmem_accumulate != 0;
+  static bool configured = false, configured_f = false;
+  int rc = fast ? configure_once(gemm_wf_kernel, configured_f, "gemm_wf smem attribute", kSmemBytesF)
+                : configure_once(gemm_w_kernel, configured, "gemm_w smem attribute", kSmemBytes);
   if (rc) return rc;
   CUtensorMap tm_hi, tm_lo;
   const int rows_alloc = (N + 7) & ~7;
@@ -726,11 +943,14 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   if (c_tma && (rc = get_map(C, N, M, ldc, 32, &tm_c))) return rc;
   WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, c_tma, g_dbg};
   // persistent CTAs: one per SM, nx column blocks x ny row-tile walkers
-  const int nx = fgs::cdiv(N, TN);
+  const int nx = fgs::cdiv(N, fast ? TNF : TN);
   int ny = FGS_NUM_SMS / nx;
   if (ny > n_tiles) ny = n_tiles;
   if (ny < 1) ny = 1;
-  gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo, tm_c);
+  if (fast)
+    gemm_wf_kernel<<<dim3(nx, ny, 1), kThreadsF, kSmemBytesF, st>>>(a, tm_hi, tm_lo, tm_c);
+  else
+    gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo, tm_c);
   return fgs::check_launch("gemm_w", st);
 }
 
@@ -739,7 +959,7 @@ int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ld
             float* colsum, const int32_t* rows_dev, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   static bool configured = false;
-  int rc = configure_once(gemm_tn_kernel, configured, "gemm_tn smem attribute");
+  int rc = configure_once(gemm_tn_kernel, configured, "gemm_tn smem attribute", kSmemBytes);
   if (rc) return rc;
   TnArgs a{A, B, C, colsum, rows_dev, M, N, K, lda, ldb, ldc};
   dim3 grid(fgs::cdiv(N, TN), fgs::cdiv(M, BM), 1);
@@ -806,6 +1026,13 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 // CTA (0,0) spent draining chunks (incl. waiting for the tensor core) and in epilogues (NULL switches it off).
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
+  return 0;
+}
+
+// Accumulation mode of the pre-split GEMMs: 1 = whole K in one TMEM accumulator (fast, ~3e-6 of max|out|),
+// 0 = 32-k chunks added into fp32 registers with round-to-nearest (~3e-7).
+extern "C" int fgs_set_gemm_tmem_accumulate(int on) {
+  g_tmem_accumulate = on ? 1 : 0;
   return 0;
 }
 

@@ -92,6 +92,7 @@ _lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
 _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
+_lib.declare("fgs_set_gemm_tmem_accumulate", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
@@ -100,6 +101,12 @@ _lib.declare("fgs_gemm_tcw", C.c_int,
 def set_gemm_backend(tensor_core=True):
     """MLP GEMMs of the fused step: tcgen05 3xTF32 tensor cores (default) or the fp32 SIMT kernel."""
     check(lib.fgs_set_gemm_backend(int(bool(tensor_core))))
+
+
+def set_gemm_tmem_accumulate(on=True):
+    """Pre-split tensor-core GEMMs: whole-K TMEM accumulation (fast, default) or 32-k chunks + fp32 register
+    accumulators (the most accurate mode)."""
+    check(lib.fgs_set_gemm_tmem_accumulate(int(bool(on))))
 
 
 def _c3(t):

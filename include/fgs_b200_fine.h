@@ -211,6 +211,12 @@ int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, in
  * a_full / b_full / r_empty / free, issuer total; tools/gemm_phase_probe.py).  NULL = off. */
 int fgs_debug_gemm_phases(void* buf);
 
+/* Accumulation mode of the pre-split tensor-core GEMMs (fgs_gemm_tcw and the fused step):
+ * 1 (default) = the whole K dimension accumulates in one TMEM accumulator (128 x 256 tiles; the accumulator
+ * truncates at every MMA: error ~3e-6 of max|out|); 0 = 32-k chunks are added into fp32 registers with
+ * round-to-nearest (128 x 128 tiles, ~3e-7, about 2x slower).  Both are far inside the 1e-4 parity bar. */
+int fgs_set_gemm_tmem_accumulate(int on);
+
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);
 

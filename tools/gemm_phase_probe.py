@@ -6,6 +6,7 @@ from fgs_nerf_b200 import engine
 from fgs_nerf_b200._lib import lib, check
 dev = torch.device("cuda:0")
 M, N, K = int(sys.argv[1]) if len(sys.argv) > 1 else 27000, 256, 256
+engine.set_gemm_tmem_accumulate(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); out = torch.zeros(M, N, device=dev)
 bias = torch.randn(N, device=dev); bits = torch.zeros(M, 8, dtype=torch.int32, device=dev)
 rows = torch.tensor([M], dtype=torch.int32, device=dev)
