@@ -274,6 +274,8 @@ def run_ours(args):
     mac = 2.0 * MLP_MACS * M2
     V_t = touched
     alg = {"gemm_w": ("tensor", 2 * mac / 1e12, "TFLOP/s"),
+           "mlp_chain": ("tensor", 2 * mac / 1e12, "TFLOP/s"),      # forward chain + backward-data chain
+           "gemm_tn": ("tensor", mac / 1e12, "TFLOP/s"),
            "gemm_tc": ("tensor", mac / 1e12, "TFLOP/s"),
            "gemm": ("tensor", 3 * mac / 1e12, "TFLOP/s"),
            "adam_dense_zero": ("hbm", 32.0 * V / 1e9, "GB/s"),                          # p,g,m,v read; p,m,v,g written

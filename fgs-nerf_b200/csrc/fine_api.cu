@@ -59,6 +59,32 @@ int mm(const FgsFineParams& P, int mode, int layer, int hid, int M, int N, int K
                 0, hid >= 0 ? hbits(P, hid) : nullptr, nullptr, rows_dev, st);
 }
 
+int g_fusion = 1;
+bool use_chain() { return g_backend && g_fusion && tmem_accumulate_enabled(); }
+
+// forward step `layer`: C = act(A W_layer^T + b_layer) (straight planes)
+ChainStepHost fwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer, const float* A, int lda, int K,
+                       float* C, int ldc, int N, int relu, int hid) {
+  ChainStepHost s{};
+  s.A = A; s.lda = lda; s.K = K;
+  s.Bh = P.w_split + L.hi[layer]; s.Bl = P.w_split + L.lo[layer]; s.ldb = L.in_ld[layer];
+  s.C = C; s.ldc = ldc; s.N = N; s.n0 = 0;
+  s.bias = P.B[layer]; s.relu = relu;
+  s.bits_in = nullptr; s.bits_out = (relu && hid >= 0) ? hbits(P, hid) : nullptr;
+  return s;
+}
+// backward-data step through `layer`: C = (A W_layer) masked by the ReLU bits of hidden buffer `hid`
+ChainStepHost bwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer, const float* A, int lda, int K,
+                       float* C, int ldc, int N, int n0, int hid) {
+  ChainStepHost s{};
+  s.A = A; s.lda = lda; s.K = K;
+  s.Bh = P.w_split + L.thi[layer]; s.Bl = P.w_split + L.tlo[layer]; s.ldb = L.ldt[layer];
+  s.C = C; s.ldc = ldc; s.N = N; s.n0 = n0;
+  s.bias = nullptr; s.relu = 0;
+  s.bits_in = hid >= 0 ? hbits(P, hid) : nullptr; s.bits_out = nullptr;
+  return s;
+}
+
 // hi / lo TF32 planes of the 8 weight matrices, straight and transposed, in one launch
 int prep_weights(const FgsFineParams& P, cudaStream_t st) {
   if (!g_backend) return 0;
@@ -78,6 +104,11 @@ extern "C" {
 
 int64_t fgs_fine_wsplit_floats(void) { return (int64_t)wsplit_layout().total; }
 
+int fgs_set_mlp_fusion(int on) {
+  g_fusion = on ? 1 : 0;
+  return 0;
+}
+
 int fgs_set_gemm_backend(int tensor_core) {
   g_backend = tensor_core ? 1 : 0;
   return 0;
@@ -93,6 +124,22 @@ int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
   const int* m2 = P.counters + FGS_CNT_M2;
   const int cap = P.cap_m2;
   if ((rc = prep_weights(P, st))) return rc;
+  if (use_chain()) {
+    // rgbnet (model/nerf.py:125-134, 877) and refnet (:136-151, 883-884) as one persistent launch
+    const WSplitLayout L = wsplit_layout();
+    const ChainStepHost steps[8] = {
+        fwd_step(P, L, 0, P.X0, FGS_X0_LD, FGS_X0_LD, hidden(P, 0), W, W, 1, 0),
+        fwd_step(P, L, 1, hidden(P, 0), W, W, hidden(P, 1), W, W, 1, 1),
+        fwd_step(P, L, 2, hidden(P, 1), W, W, hidden(P, 2), W, W, 1, 2),
+        fwd_step(P, L, 3, hidden(P, 2), W, W, P.XR, FGS_XR_LD, W, 0, -1),
+        fwd_step(P, L, 4, P.XR, FGS_XR_LD, FGS_XR_LD, hidden(P, 3), W, W, 1, 3),
+        fwd_step(P, L, 5, hidden(P, 3), W, W, hidden(P, 4), W, W, 1, 4),
+        fwd_step(P, L, 6, hidden(P, 4), W, W, hidden(P, 5), W, W, 1, 5),
+        fwd_step(P, L, 7, hidden(P, 5), W, W, P.logit, 4, 3, 0, -1)};
+    if ((rc = mlp_chain(steps, 8, cap, m2, st))) return rc;
+    if (P.skip_composite) return 0;
+    return launch_composite(P, nullptr, st);
+  }
   // rgbnet (model/nerf.py:125-134, 877)
   if ((rc = mm(P, 0, 0, 0, cap, W, FGS_X0_LD, P.X0, FGS_X0_LD, P.W[0], FGS_X0_LD, hidden(P, 0), W, P.B[0], 1, m2, st))) return rc;
   if ((rc = mm(P, 0, 1, 1, cap, W, W, hidden(P, 0), W, P.W[1], W, hidden(P, 1), W, P.B[1], 1, m2, st))) return rc;
@@ -134,6 +181,31 @@ int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t
     if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
   }
   fgs::prof_mark("memset", st);
+  if (use_chain() && P.dZ) {
+    // ---- backward-data chain in one launch: dZ_l = (dZ_{l+1} W_{l+1}) masked by relu'(H_l) ----
+    const WSplitLayout L = wsplit_layout();
+    auto dz = [&](int i) { return P.dZ + (size_t)i * P.cap_m2 * W; };   // dZ6, dZ5, dZ4, dZ2, dZ1, dZ0
+    const ChainStepHost steps[9] = {
+        bwd_step(P, L, 7, P.dlogit, 4, 3, dz(0), W, W, 0, 5),
+        bwd_step(P, L, 6, dz(0), W, W, dz(1), W, W, 0, 4),
+        bwd_step(P, L, 5, dz(1), W, W, dz(2), W, W, 0, 3),
+        bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 0, -1),      // dXR[:, 0:256] = dZ3 (linear layer)
+        bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 256, -1),    // dXR[:, 256:320] -> feat_bwd
+        bwd_step(P, L, 3, P.dXR, FGS_XR_LD, W, dz(3), W, W, 0, 2),
+        bwd_step(P, L, 2, dz(3), W, W, dz(4), W, W, 0, 1),
+        bwd_step(P, L, 1, dz(4), W, W, dz(5), W, W, 0, 0),
+        bwd_step(P, L, 0, dz(5), W, W, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1)};
+    if ((rc = mlp_chain(steps, 9, cap, m2, st))) return rc;
+    // ---- weight / bias gradients: dW_l = dZ_l^T X_l ----
+    const float* dzl[8] = {dz(5), dz(4), dz(3), P.dXR, dz(2), dz(1), dz(0), P.dlogit};
+    const int dz_ld[8] = {W, W, W, FGS_XR_LD, W, W, W, 4};
+    const float* xin[8] = {P.X0, hidden(P, 0), hidden(P, 1), hidden(P, 2), P.XR, hidden(P, 3), hidden(P, 4), hidden(P, 5)};
+    for (int l = 7; l >= 0; --l)
+      if ((rc = gemm_tn(out_dim[l], in_dim[l], cap, dzl[l], dz_ld[l], xin[l], in_dim[l], P.gW[l], in_dim[l], P.gB[l], m2, st)))
+        return rc;
+    if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
+    return launch_level1_bwd(P, l->g_alphainv_last, st);
+  }
   // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
   // layer 7: logit = H5 W7^T + b7
   if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st, P.gB[7]))) return rc;

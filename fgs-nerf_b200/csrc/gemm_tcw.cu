@@ -28,6 +28,7 @@
 //     scalar readback cost 15 K cycles per tile at one warp per scheduler).
 #include <cuda.h>
 
+#include <cstring>
 #include <map>
 #include <tuple>
 
@@ -714,6 +715,267 @@ gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const _
   cta_teardown(tmem_d, warp);
 }
 
+// ---- fused MLP chain: all layers of one direction in ONE persistent launch ------------------------------
+// A layer's 128-row output tile depends only on the same 128 rows of the previous layer, so a CTA can
+// walk a row tile through the whole chain (forward: X0 -> H0 -> H1 -> H2 -> XR -> H3 -> H4 -> H5 -> logit;
+// backward-data: dlogit -> dZ6 -> ... -> dX0) without any grid-wide dependency.  Per launch of gemm_wf_kernel
+// about 10 us are not tensor-core time (launch, TMEM / barrier setup, pipeline fill, the last epilogue);
+// 16 such launches per step are replaced by 2.  Work items = (step, local tile), step-major over the CTA's
+// tiles, so the epilogue + TMA store of (tile, step) overlaps the MMAs of the CTA's other tile(s) before
+// (tile, step + 1) needs it; completion travels through one mbarrier per local tile (c_done: the storing
+// lanes arrive after cp.async.bulk.wait_group 0), the dependent loads are ld.global.cg.
+constexpr int kChainMaxSteps = 10;
+constexpr int kChainMaxTiles = 16;                         // local tiles per CTA (c_done barriers)
+constexpr uint32_t kCDoneOff = kBiasOff + 2 * TNF * 4;     // bias slices are double-buffered by item parity
+constexpr uint32_t kSmemBytesChain = kCDoneOff + 8 * kChainMaxTiles;
+
+struct ChainStep {
+  const float* A; float* C; const float* bias; const uint32_t* bits_in; uint32_t* bits_out;
+  int lda, ldc, K, N, n0, relu, c_tma, pad_;
+};
+struct ChainArgs {
+  ChainStep s[kChainMaxSteps];
+  const int* rows_dev;
+  long long* dbg;
+  int n_steps, M;
+};
+struct ChainMaps {
+  CUtensorMap hi[kChainMaxSteps], lo[kChainMaxSteps], c[kChainMaxSteps];
+};
+
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreadsF, 1)
+mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const Bars B = make_bars(smem);
+  const uint32_t cdone0 = smem + kCDoneOff;
+
+  int M = a.M;
+  if (a.rows_dev) M = min(M, *a.rows_dev);
+  const int n_tiles = (M + BM - 1) / BM;
+  if ((int)blockIdx.x >= n_tiles) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0)
+    for (int i = 0; i < kChainMaxTiles; ++i) mbar_init(cdone0 + 8 * i, 8);   // lane 0 of the 8 consumer warps
+  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersF);
+
+  const int my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+  const int n_items = a.n_steps * my_tiles;                  // item w: step w / my_tiles, local tile w % my_tiles
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
+
+  if (warp >= kIssuerWarpF) {
+    // ================= MMA + TMA issuer =================
+    if (warp == kIssuerWarpF && lane == 0) {
+      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
+      auto issue_b = [&](int step, int kt, uint32_t gs) {
+        const ChainStep& S = a.s[step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const int n_boxes = BN > 128 ? 2 : 1;
+        const uint32_t st = gs % kStagesF;
+        const uint32_t b_hi = smem + st * kStageF + 2 * kATile, b_lo = b_hi + kBTileF;
+        const uint32_t bar = B.bfull0 + 8 * st;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_boxes * 2 * kBTile) : "memory");
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          tma_load_2d(b_hi + bx * kBTile, &maps.hi[step], bar, kt * BK, S.n0 + 128 * bx);
+          tma_load_2d(b_lo + bx * kBTile, &maps.lo[step], bar, kt * BK, S.n0 + 128 * bx);
+        }
+      };
+      issue_b(0, 0, 0);
+      uint32_t g = 0;
+      for (int w = 0; w < n_items; ++w) {
+        const int step = w / my_tiles;
+        const ChainStep& S = a.s[step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const int n_slabs = (S.K + BK - 1) / BK;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+        const uint32_t rg = (uint32_t)w & 1;
+        for (int kt = 0; kt < n_slabs; ++kt, ++g) {
+          const uint32_t st = g % kStagesF;
+          const uint32_t par = (g / kStagesF) & 1;
+          if (dbg_cta) t0 = clock64();
+          mbar_wait(B.afull0 + 8 * st, par);
+          if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+          mbar_wait(B.bfull0 + 8 * st, par);
+          if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
+          if (kt == 0 && w >= 2) mbar_wait(B.rempty0 + 8 * rg, (((uint32_t)w >> 1) - 1) & 1);
+          if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          {
+            const uint32_t stage_base = smem + st * kStageF, d = tmem_d + rg * TNF;
+            const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+            const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTileF;
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+              const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+              mma_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);
+              mma_tf32(d, dah, dbl, idesc, 1);
+              mma_tf32(d, dah, dbh, idesc, 1);
+            }
+          }
+          mma_commit(B.free0 + 8 * st);
+          if (kt == n_slabs - 1) mma_commit(B.rfull0 + 8 * rg);
+          // weights of the next slab (possibly the first slab of the next item: weights have no dependency)
+          int nstep = step, nkt = kt + 1;
+          if (nkt == n_slabs) { nkt = 0; nstep = (w + 1) / my_tiles; }
+          if (nkt != 0 || w + 1 < n_items) {
+            const uint32_t gs = g + 1;
+            if (dbg_cta) t0 = clock64();
+            if (gs >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * (gs % kStagesF), ((gs / kStagesF) - 1) & 1);
+            if (dbg_cta) t_f += clock64() - t0;
+            issue_b(nstep, nkt, gs);
+          }
+        }
+      }
+      if (dbg_cta) {
+        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
+      }
+    }
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers: activation slabs -> hi / lo TF32 tiles =================
+    const int pw = warp - kConsumers / 32;
+    const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
+    const bool dbg_on = dbg_cta && tid == kConsumers;
+    long long t_wait = 0, t_work = 0, t_dep = 0, t0 = 0;
+    uint32_t g = 0;
+    for (int w = 0; w < n_items; ++w) {
+      const int step = w / my_tiles, lt = w - step * my_tiles;
+      const ChainStep& S = a.s[step];
+      const int K = S.K, lda = S.lda;
+      const int n_slabs = (K + BK - 1) / BK;
+      const int row = ((int)blockIdx.x + lt * (int)gridDim.x) * BM + prow;
+      const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
+      const int mleft = M - row;
+      if (step > 0) {
+        // the tile's rows of this step's input were stored by the consumers of (tile, step - 1)
+        if (dbg_on) t0 = clock64();
+        mbar_wait(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (dbg_on) t_dep += clock64() - t0;
+      }
+      auto load_a = [&](float4 (&v)[4], int kt) {
+        if (kt >= n_slabs) return;
+        const int k = kt * BK + 4 * pc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto produce = [&](float4 (&v)[4], int kt) {
+        const uint32_t st = g % kStagesF;
+        const uint32_t stage_base = smem + st * kStageF;
+        if (dbg_on) t0 = clock64();
+        if (g >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
+        if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = prow + 4 * i;
+          const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+          split_store(stage_base + off, stage_base + kATile + off, v[i]);
+        }
+        load_a(v, kt + 2);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(B.afull0 + 8 * st);
+        ++g;
+        if (dbg_on) t_work += clock64() - t0;
+      };
+      float4 v0[4], v1[4];
+      load_a(v0, 0);
+      load_a(v1, 1);
+      for (int kt = 0; kt < n_slabs; kt += 2) {
+        produce(v0, kt);
+        if (kt + 1 < n_slabs) produce(v1, kt + 1);
+      }
+    }
+    if (dbg_on) { a.dbg[2] = t_dep; a.dbg[3] = t_wait; a.dbg[4] = t_work; }
+  } else {
+    // ================= consumers: epilogue of item w while item w + 1 multiplies =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * (TNF / 2);
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
+    long long t_main = 0, t_epi = 0, t0 = 0;
+    const bool dbg_on = dbg_cta && tid == 0;
+    for (int w = 0; w < n_items; ++w) {
+      const int step = w / my_tiles, lt = w - step * my_tiles;
+      const ChainStep& S = a.s[step];
+      const int n0 = S.n0, N = S.N;
+      const int BN = min(TNF, (N - n0 + 15) & ~15);
+      const uint32_t rg = (uint32_t)w & 1;
+      const uint32_t bias_s = smem + kBiasOff + rg * (TNF * 4);
+      // bias slice of this item (the other buffer may still be read by a slower warp of item w - 1)
+      reinterpret_cast<float*>(smem_raw + kBiasOff)[rg * TNF + tid] = (S.bias && n0 + tid < N) ? S.bias[n0 + tid] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (dbg_on) t0 = clock64();
+      mbar_wait(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+      const int m0 = ((int)blockIdx.x + lt * (int)gridDim.x) * BM;
+      const int mr0 = m0 + quarter * 32;
+      const int m = mr0 + lane;
+#pragma unroll 1
+      for (int q = 0; q < TNF / 2 / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+          float v[32];
+          {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
+            tmem_ld16(tmem_row + rg * TNF + 32 * q + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
+          }
+          const int word = (n0 + c0) >> 5;
+          uint32_t in_bits = 0xffffffffu, out_bits = 0;
+          if (S.bits_in && m < M) in_bits = S.bits_in[(size_t)m * 8 + word];
+          const uint32_t baddr = bias_s + 4 * c0;
+          const bool hb = S.bias != nullptr;
+          if (S.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
+          else if (S.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
+          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
+          if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + word] = out_bits;
+          if (S.c_tma && mr0 + 32 <= M) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
+                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&maps.c[step], stg, n0 + c0, mr0);
+          } else if (m < M) {
+            float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) cp[j] = v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(B.rempty0 + 8 * rg);                 // item w + 2 may overwrite the region
+      // the tile's rows of this step are complete in global memory -> (tile, step + 1) may load them
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        mbar_arrive(cdone0 + 8 * lt);
+      }
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
+    }
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
+  }
+  cta_teardown(tmem_d, warp);
+}
+
 // ---- backward-weight GEMM:  C[M,N] += A[K,M]^T B[K,N]  (dW = dZ^T X), split over the samples ----------
 // Same machinery (warp-specialised, SWIZZLE_128B tiles, 32-k accumulation chunks, register
 // accumulators), but the reduction index is the SAMPLE dimension, which is the slow dimension of both
@@ -954,6 +1216,42 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   return fgs::check_launch("gemm_w", st);
 }
 
+// The MLP chain in one launch (see mlp_chain_kernel).  steps[i]: C_i = act(A_i W_i^T + b_i) on the column
+// block [n0, n0 + 256) with pre-split weight planes Bh / Bl ([round_up(N,8)][ldb], K-major).
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st) {
+  if (M <= 0 || n_steps <= 0) return 0;
+  if (n_steps > kChainMaxSteps) return fgs::fail_arg("mlp_chain: too many steps");
+  const int n_tiles = fgs::cdiv(M, BM);
+  int grid = FGS_NUM_SMS;
+  if (grid > n_tiles) grid = n_tiles;
+  if (fgs::cdiv(n_tiles, grid) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
+  static bool configured = false;
+  int rc = configure_once(mlp_chain_kernel, configured, "mlp_chain smem attribute", kSmemBytesChain);
+  if (rc) return rc;
+  ChainArgs a;
+  ChainMaps maps;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < n_steps; ++i) {
+    const ChainStepHost& h = steps[i];
+    if ((h.lda & 3) || (h.ldb & 3) || (((uintptr_t)h.A | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
+      return fgs::fail_arg("mlp_chain needs 16-byte aligned operands with leading dimensions % 4 == 0");
+    if (h.K > h.ldb) return fgs::fail_arg("mlp_chain: K exceeds the weight plane's row length");
+    const int rows_alloc = (h.N + 7) & ~7;
+    if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.hi[i]))) return rc;
+    if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.lo[i]))) return rc;
+    const int c_tma = ((h.ldc & 3) == 0 && ((uintptr_t)h.C & 15) == 0) ? 1 : 0;
+    maps.c[i] = maps.hi[i];
+    if (c_tma && (rc = get_map(h.C, h.N, M, h.ldc, 32, &maps.c[i]))) return rc;
+    ChainStep& s = a.s[i];
+    s.A = h.A; s.C = h.C; s.bias = h.bias; s.bits_in = h.bits_in; s.bits_out = h.bits_out;
+    s.lda = h.lda; s.ldc = h.ldc; s.K = h.K; s.N = h.N; s.n0 = h.n0; s.relu = h.relu; s.c_tma = c_tma;
+  }
+  for (int i = n_steps; i < kChainMaxSteps; ++i) { maps.hi[i] = maps.hi[0]; maps.lo[i] = maps.lo[0]; maps.c[i] = maps.c[0]; }
+  a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = M;
+  mlp_chain_kernel<<<grid, kThreadsF, kSmemBytesChain, st>>>(a, maps);
+  return fgs::check_launch("mlp_chain", st);
+}
+
 // C[M,N] += A[K,M]^T B[K,N] over the first min(K, *rows_dev) rows; colsum[m] += sum_k A[k][m] (may be NULL)
 int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             float* colsum, const int32_t* rows_dev, cudaStream_t st) {
@@ -972,6 +1270,8 @@ int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ld
   gemm_tn_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
   return fgs::check_launch("gemm_tn", st);
 }
+
+bool tmem_accumulate_enabled() { return g_tmem_accumulate != 0; }
 
 // ---- weight splitting ------------------------------------------------------------------------
 int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {

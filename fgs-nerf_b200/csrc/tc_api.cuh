@@ -23,6 +23,18 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
 int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             float* colsum, const int32_t* rows_dev, cudaStream_t st);
 
+// One step of the fused MLP chain (gemm_tcw.cu: mlp_chain_kernel): C = act(A W^T + b) on output columns
+// [n0, n0 + 256) with pre-split weight planes Bh / Bl.
+struct ChainStepHost {
+  const float* A; int lda; int K;
+  const float* Bh; const float* Bl; int ldb;
+  float* C; int ldc; int N; int n0;
+  const float* bias; int relu;
+  const uint32_t* bits_in; uint32_t* bits_out;
+};
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
+bool tmem_accumulate_enabled();
+
 // generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,

@@ -59,6 +59,7 @@ class FgsFineParams(C.Structure):
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
         ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
+        ("dZ", _fp),
     ]
 
 
@@ -93,6 +94,7 @@ _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
 _lib.declare("fgs_set_gemm_tmem_accumulate", C.c_int, [C.c_int])
+_lib.declare("fgs_set_mlp_fusion", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
@@ -107,6 +109,11 @@ def set_gemm_tmem_accumulate(on=True):
     """Pre-split tensor-core GEMMs: whole-K TMEM accumulation (fast, default) or 32-k chunks + fp32 register
     accumulators (the most accurate mode)."""
     check(lib.fgs_set_gemm_tmem_accumulate(int(bool(on))))
+
+
+def set_mlp_fusion(on=True):
+    """Fused step: run each direction of the MLPs as one persistent launch (default) or one launch per layer."""
+    check(lib.fgs_set_mlp_fusion(int(bool(on))))
 
 
 def _c3(t):
@@ -256,6 +263,7 @@ class FineStepEngine:
         ws["XR"] = e(self.cap_m2, XR_LD)
         ws["logit"], ws["normal2"], ws["dlogit"] = e(self.cap_m2, 4), e(self.cap_m2, 4), e(self.cap_m2, 4)
         ws["dA"], ws["dB"] = e(self.cap_m2, WIDTH), e(self.cap_m2, WIDTH)
+        ws["dZ"] = e(6, self.cap_m2, WIDTH)      # per-layer pre-activation gradients (one-launch backward chain)
         ws["dXR"], ws["dX0"] = e(self.cap_m2, XR_LD), e(self.cap_m2, X0_LD)
         for k in ("rgb_marched", "sigmoid_rgb", "normal_marched"):
             ws[k] = e(N, 3)
@@ -307,7 +315,7 @@ class FineStepEngine:
                   "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
                   "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
                   "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
-                  "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags"):
+                  "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ"):
             setattr(P, k, ptr(ws[k]))
 
     def s_val(self, global_step):

@@ -127,6 +127,9 @@ typedef struct FgsFineParams {
   int64_t g_mlp_floats;
   uint8_t *k0_brick_flags; /* [ceil(X/4)*ceil(Y/4)*ceil(Z/4)] set to 1 by the backward scatter for every
                         4x4x4 brick of k0 that received a gradient (may be NULL); see fgs_adam_upd_bricks */
+  float *dZ;         /* optional [6][cap_m2][256]: one buffer per hidden layer's pre-activation gradient, so the
+                        backward-data chain runs as ONE launch and the 8 weight-gradient GEMMs follow it
+                        (NULL: per-layer launches through the dA / dB ping-pong) */
 } FgsFineParams;
 
 /* size of FgsFineParams::w_split in floats */
@@ -216,6 +219,11 @@ int fgs_debug_gemm_phases(void* buf);
  * truncates at every MMA: error ~3e-6 of max|out|); 0 = 32-k chunks are added into fp32 registers with
  * round-to-nearest (128 x 128 tiles, ~3e-7, about 2x slower).  Both are far inside the 1e-4 parity bar. */
 int fgs_set_gemm_tmem_accumulate(int on);
+
+/* 1 (default): the 8 forward GEMMs and the 8 backward-data GEMMs of the fused step each run as one
+ * persistent launch (mlp_chain_kernel; needs the tcgen05 backend with TMEM accumulation); 0: one launch per
+ * layer. */
+int fgs_set_mlp_fusion(int on);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);
