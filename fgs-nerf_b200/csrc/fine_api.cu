@@ -200,9 +200,10 @@ int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t
     const float* dzl[8] = {dz(5), dz(4), dz(3), P.dXR, dz(2), dz(1), dz(0), P.dlogit};
     const int dz_ld[8] = {W, W, W, FGS_XR_LD, W, W, W, 4};
     const float* xin[8] = {P.X0, hidden(P, 0), hidden(P, 1), hidden(P, 2), P.XR, hidden(P, 3), hidden(P, 4), hidden(P, 5)};
-    for (int l = 7; l >= 0; --l)
-      if ((rc = gemm_tn(out_dim[l], in_dim[l], cap, dzl[l], dz_ld[l], xin[l], in_dim[l], P.gW[l], in_dim[l], P.gB[l], m2, st)))
-        return rc;
+    DwProblemHost dw[8];
+    for (int l = 0; l < 8; ++l)
+      dw[l] = DwProblemHost{dzl[l], xin[l], P.gW[l], P.gB[l], out_dim[l], in_dim[l], dz_ld[l], in_dim[l], in_dim[l]};
+    if ((rc = mlp_dw(dw, 8, cap, m2, st))) return rc;
     if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
     return launch_level1_bwd(P, l->g_alphainv_last, st);
   }

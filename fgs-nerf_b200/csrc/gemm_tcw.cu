@@ -90,6 +90,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   if (!done) __trap();  // a phase bug must surface as an error, never as a hung GPU
 }
+// The same wait for the roles that are not on the critical hand-off path (producers waiting for a free stage,
+// consumers waiting for a finished accumulator): back off between polls, so the waiting warps do not take issue
+// slots from the working warps of their scheduler (a producer warp sharing its scheduler with two spinning
+// consumer warps needed 1.8 K cycles for an EMPTY slab iteration).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(40);
+  }
+  __trap();
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row (1024-byte) swizzle
 // atoms (SBO 1024), 16-byte chunk c of row r stored at chunk position c ^ (r % 8); layout_type = 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
@@ -108,16 +127,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Round-to-nearest (ties away from zero) to TF32 = cvt.rna.tf32.f32, but on the integer pipe: the conversion
+// instruction issues at 16 lanes / clock / SM and made the operand producers the bottleneck of every GEMM here
+// (2 cvt per element: 2 K cycles per 64 KB slab against 1.3 K cycles of MMAs); add-half-ulp-and-mask is two
+// full-rate ALU ops and bit-identical for finite inputs.
 __device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streamed operands bypass L1: with ~210 KB of the SM's 256 KB carved out as shared memory the remaining L1 tracks too
+// few outstanding lines to keep 32-64 KB of loads in flight (ld.global.nc ran the dW producers at 4 K cycles per slab)
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -169,7 +196,7 @@ template <bool PAIRED>
 __device__ __forceinline__ void drain_chunk(float (&acc)[kAcc], uint32_t tmem_row, int col_half, uint32_t c, int BN,
                                             uint32_t rfull_bar0, uint32_t rempty_bar0) {
   const uint32_t rg = c % kRegions;
-  mbar_wait(rfull_bar0 + 8 * rg, (c / kRegions) & 1);
+  mbar_wait_relaxed(rfull_bar0 + 8 * rg, (c / kRegions) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
   for (int q = 0; q < kAcc / 32; ++q) {
@@ -197,7 +224,8 @@ __device__ __forceinline__ void drain_chunk(float (&acc)[kAcc], uint32_t tmem_ro
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  mbar_arrive(rempty_bar0 + 8 * rg);   // the region may be overwritten by chunk c + kRegions
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(rempty_bar0 + 8 * rg);   // the region may be overwritten by chunk c + kRegions
 }
 
 // TMA store of one swizzled 32-row x 128-byte block (issued by one lane; completion tracked per thread)
@@ -257,11 +285,11 @@ __device__ __forceinline__ uint32_t cta_setup(unsigned char* smem_raw, const Bar
     for (int i = 0; i < kStages; ++i) {
       mbar_init(B.free0 + 8 * i, 1);
       mbar_init(B.bfull0 + 8 * i, 1);
-      mbar_init(B.afull0 + 8 * i, n_producers);
+      mbar_init(B.afull0 + 8 * i, n_producers / 32);       // one arrival per producer warp
     }
     for (int i = 0; i < kRegions; ++i) {
       mbar_init(B.rfull0 + 8 * i, 1);
-      mbar_init(B.rempty0 + 8 * i, kConsumers);
+      mbar_init(B.rempty0 + 8 * i, kConsumers / 32);       // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -410,13 +438,13 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
       const int mleft = M - (tile * BM + prow);          // rows 4 i with 4 i < mleft are valid
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        v[i] = (4 * i < mleft && k < K) ? ldg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto produce = [&](float4 (&v)[8], uint32_t g) {
       const uint32_t st = g % kStages;
       const uint32_t stage_base = smem + st * kStage;
       if (dbg_on) t0 = clock64();
-      if (g >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
+      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
       if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -426,7 +454,8 @@ gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __
       }
       load_a(v, g + 2);                                  // two slabs stay in flight
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(B.afull0 + 8 * st);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
       if (dbg_on) t_work += clock64() - t0;
     };
     float4 v0[8], v1[8];
@@ -620,13 +649,13 @@ gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const _
       const int mleft = M - (tile * BM + prow);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        v[i] = (4 * i < mleft && k < K) ? ldg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto produce = [&](float4 (&v)[4], uint32_t g) {
       const uint32_t st = g % kStagesF;
       const uint32_t stage_base = smem + st * kStageF;
       if (dbg_on) t0 = clock64();
-      if (g >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
+      if (g >= (uint32_t)kStagesF) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
       if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -636,7 +665,8 @@ gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const _
       }
       load_a(v, g + 2);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(B.afull0 + 8 * st);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
       if (dbg_on) t_work += clock64() - t0;
     };
     float4 v0[4], v1[4];
@@ -660,7 +690,7 @@ gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const _
       const int m0 = tile * BM;
       const uint32_t rg = lt & 1;
       if (dbg_on) t0 = clock64();
-      mbar_wait(B.rfull0 + 8 * rg, (lt >> 1) & 1);
+      mbar_wait_relaxed(B.rfull0 + 8 * rg, (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
       const int mr0 = m0 + quarter * 32;
@@ -706,7 +736,8 @@ gemm_wf_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const _
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(B.rempty0 + 8 * rg);                 // tile t + 2 may overwrite the region
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.rempty0 + 8 * rg);                 // tile t + 2 may overwrite the region
       if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
     }
     if (lane == 0) tma_store_wait_all();
@@ -742,12 +773,6 @@ struct ChainArgs {
 struct ChainMaps {
   CUtensorMap hi[kChainMaxSteps], lo[kChainMaxSteps], c[kChainMaxSteps];
 };
-
-__device__ __forceinline__ float4 ldcg4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(kThreadsF, 1)
 mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
@@ -857,7 +882,7 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
       if (step > 0) {
         // the tile's rows of this step's input were stored by the consumers of (tile, step - 1)
         if (dbg_on) t0 = clock64();
-        mbar_wait(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
+        mbar_wait_relaxed(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (dbg_on) t_dep += clock64() - t0;
       }
@@ -872,7 +897,7 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
         const uint32_t st = g % kStagesF;
         const uint32_t stage_base = smem + st * kStageF;
         if (dbg_on) t0 = clock64();
-        if (g >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
+        if (g >= (uint32_t)kStagesF) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
         if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -882,7 +907,8 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
         }
         load_a(v, kt + 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(B.afull0 + 8 * st);
+        __syncwarp();
+      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
         ++g;
         if (dbg_on) t_work += clock64() - t0;
       };
@@ -913,7 +939,7 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
       reinterpret_cast<float*>(smem_raw + kBiasOff)[rg * TNF + tid] = (S.bias && n0 + tid < N) ? S.bias[n0 + tid] : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (dbg_on) t0 = clock64();
-      mbar_wait(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
+      mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
       const int m0 = ((int)blockIdx.x + lt * (int)gridDim.x) * BM;
@@ -960,7 +986,8 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(B.rempty0 + 8 * rg);                 // item w + 2 may overwrite the region
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.rempty0 + 8 * rg);                 // item w + 2 may overwrite the region
       // the tile's rows of this step are complete in global memory -> (tile, step + 1) may load them
       __syncwarp();
       if (lane == 0) {
@@ -976,144 +1003,215 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
   cta_teardown(tmem_d, warp);
 }
 
-// ---- backward-weight GEMM:  C[M,N] += A[K,M]^T B[K,N]  (dW = dZ^T X), split over the samples ----------
-// Same machinery (warp-specialised, SWIZZLE_128B tiles, 32-k accumulation chunks, register
-// accumulators), but the reduction index is the SAMPLE dimension, which is the slow dimension of both
-// row-major operands.  kind::tf32 cannot read MN-major tiles without the 128B_BASE32B swizzle, so the
-// 256 producers transpose both operands on the fly: coalesced 32-bit loads along the feature dimension
-// (a warp reads 128 contiguous bytes of one sample row), four consecutive samples of one feature form
-// the 16-byte chunk that is split into hi / lo and stored to the swizzled K-major tile.  The bias
-// gradient (column sums of dZ) rides along with the A loads.  Partial products of the K-splits are
-// combined with 128-byte red.global.add rows (epilogue transposed through shared memory).
-struct TnArgs {
-  const float* A; const float* B; float* C; float* colsum; const int* rows_dev;
-  int M, N, K, lda, ldb, ldc;
+// ---- backward-weight GEMMs:  C_l[M_l,N_l] += A_l[K,M_l]^T B_l[K,N_l]  (dW_l = dZ_l^T X_l) for ALL layers in one launch --
+// The reduction index is the SAMPLE dimension, the slow dimension of both row-major operands, i.e. both tiles
+// are MN-major.  kind::tf32 reads MN-major tiles in the SWIZZLE_128B_BASE32B layout (tools/umma_probe.cu):
+//   addr(mn, k) = (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + (((mn % 32) / 8) ^ (k % 4)) * 32 + (mn % 8) * 4
+// With LBO = 4096, SBO = 512 a slab is four blocks of [32 samples][32 features], one 128-byte row per sample:
+// a producer warp reads one sample row of 128 features with one coalesced 128-bit load per lane, splits it
+// into hi / lo and stores 16 bytes per lane -- no transposition anywhere (an earlier version transposed with
+// 32-bit loads and ran at 2.3x the tensor-core time).  The bias gradient (column sums of dZ) rides along.
+// Work is the flattened (tile, 32-sample slab) space of all 8 layers' 128 x 128 output tiles, cut into equal
+// contiguous ranges, one per CTA (stream-K): every SM gets the same number of MMAs, a CTA crosses at most a
+// few tile boundaries, each costing one 128 x 128 red.global.add epilogue.  Accumulation: 32-k chunks in
+// rotating TMEM regions, fp32 register accumulators (thousands of MMAs per range -- the TMEM accumulator's
+// per-MMA truncation would reach 1e-4 if it took them all).
+constexpr int kDwMaxProblems = 8, kDwMaxTiles = 32;
+struct DwProblem {
+  const float* A; const float* B; float* C; float* colsum;
+  int M, N, lda, ldb, ldc, pad_;
 };
-
-// 8 consumer warps + 8 producer warps (the transposing loads are 32-bit: twice the producers of gemm_w) + issuer
+struct DwArgs {
+  DwProblem p[kDwMaxProblems];
+  unsigned char tile_prob[kDwMaxTiles], tile_m[kDwMaxTiles], tile_n[kDwMaxTiles];
+  const int* rows_dev;
+  long long* dbg;
+  int n_tiles, K;
+};
 constexpr int kProducersTn = 256;
 constexpr int kIssuerWarpTn = (kConsumers + kProducersTn) / 32;
 constexpr int kThreadsTn = kConsumers + kProducersTn + 32;
 
-__global__ void __launch_bounds__(kThreadsTn, 1) gemm_tn_kernel(const TnArgs a) {
+// MN-major SWIZZLE_128B_BASE32B descriptor (layout_type 1): LBO 4096 between 32-wide MN blocks, SBO 512
+// between groups of 4 k-rows
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_constant__ DwArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
   const Bars B = make_bars(smem);
 
   int K = a.K;
   if (a.rows_dev) K = min(K, *a.rows_dev);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * TN;
-  int chunk = (K + gridDim.z - 1) / gridDim.z;
-  chunk = (chunk + BK - 1) / BK * BK;
-  const int kbeg = blockIdx.z * chunk;
-  const int kend = min(K, kbeg + chunk);
-  if (kbeg >= kend) return;
-  const int BN = min(TN, (a.N - n0 + 15) & ~15);
+  const int n_slabs = (K + BK - 1) / BK;
+  const long long units = (long long)a.n_tiles * n_slabs;
+  const int u_beg = (int)(units * blockIdx.x / gridDim.x), u_end = (int)(units * (blockIdx.x + 1) / gridDim.x);
+  if (u_beg >= u_end) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
   const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersTn);
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                         ((uint32_t)(BM >> 4) << 24);
-  const uint32_t n_slabs = (uint32_t)((kend - kbeg + BK - 1) / BK);
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
 
   if (warp >= kIssuerWarpTn) {
     if (warp == kIssuerWarpTn && lane == 0) {
-      for (uint32_t g = 0; g < n_slabs; ++g) {
-        const uint32_t st = g % kStages;
-        mbar_wait(B.afull0 + 8 * st, (g / kStages) & 1);
-        if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma_slab(tmem_d + (g % kRegions) * TN, smem + st * kStage, idesc);
-        mma_commit(B.free0 + 8 * st);
-        mma_commit(B.rfull0 + 8 * (g % kRegions));
+      uint32_t g = 0;
+      long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
+      for (int u = u_beg; u < u_end;) {
+        const int tile = u / n_slabs, s0 = u - tile * n_slabs;
+        const int len = min(n_slabs - s0, u_end - u);
+        const DwProblem& P = a.p[a.tile_prob[tile]];
+        const int BN = min(TN, (P.N - a.tile_n[tile] * TN + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // A and B MN-major
+        for (int i = 0; i < len; ++i, ++g) {
+          const uint32_t st = g % kStages;
+          if (dbg_cta) t0 = clock64();
+          mbar_wait(B.afull0 + 8 * st, (g / kStages) & 1);
+          if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+          if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
+          if (dbg_cta) t_r += clock64() - t0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t stage_base = smem + st * kStage, d = tmem_d + (g % kRegions) * TN;
+          const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {            // k-step j = sample rows [8 j, 8 j + 8) of every block
+            const uint64_t dah = make_desc_mn(a_hi + j * 1024), dal = make_desc_mn(a_lo + j * 1024);
+            const uint64_t dbh = make_desc_mn(b_hi + j * 1024), dbl = make_desc_mn(b_lo + j * 1024);
+            mma_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
+            mma_tf32(d, dah, dbl, idesc, 1);
+            mma_tf32(d, dah, dbh, idesc, 1);
+          }
+          mma_commit(B.free0 + 8 * st);
+          mma_commit(B.rfull0 + 8 * (g % kRegions));
+        }
+        u += len;
       }
+      if (dbg_cta) { a.dbg[5] = t_a; a.dbg[6] = 0; a.dbg[7] = t_r; a.dbg[8] = g; a.dbg[9] = clock64() - t_all; }
     }
   } else if (warp >= kConsumers / 32) {
-    // ================= producers: transpose + split both operands =================
-    // thread -> tile row (feature) ar and 16-byte chunks ac, ac + 2, ac + 4, ac + 6 (4 consecutive samples
-    // each); a warp's 32-bit loads of one sample row are 128 contiguous bytes
-    const int ptid = tid - kConsumers;
-    const int ar = ptid & 127, ac = ptid >> 7;
-    const uint32_t arow = (uint32_t)(ar * 128);
-    float csum = 0.f;
-    auto load_t = [&](float4 (&v)[4], const float* __restrict__ src, int ld, int f0, int fmax, int k0) {
-      const int f = f0 + ar;
+    // ================= producers: split both operands, no transposition =================
+    // warp pw owns sample rows 4 pw .. 4 pw + 3 of every slab; lane l owns features 4 l .. 4 l + 3 of the tile
+    const int pw = warp - kConsumers / 32;
+    // smem offset of (features 4 l.., sample row r): block l / 8, row r, 32-byte chunk ((l % 8) / 2) ^ (r % 4)
+    const uint32_t lane_blk = (uint32_t)(lane >> 3) * 4096u + (uint32_t)(lane & 1) * 16u;
+    const uint32_t lane_c32 = (uint32_t)((lane & 7) >> 1);
+    uint32_t g = 0;
+    // flattened walk over the CTA's (tile, slab) units with two slabs in flight
+    struct Cur { int u, tile, s; };
+    auto advance = [&](Cur& c) {                       // next unit
+      ++c.u; ++c.s;
+      if (c.s == n_slabs) { c.s = 0; ++c.tile; }
+    };
+    auto load_ab = [&](float4 (&va)[4], float4 (&vb)[4], const Cur& c) {
+      if (c.u >= u_end) return;
+      const DwProblem& P = a.p[a.tile_prob[c.tile]];
+      const int fa = a.tile_m[c.tile] * BM + 4 * lane, fb = a.tile_n[c.tile] * TN + 4 * lane;
+      const int k0 = c.s * BK + 4 * pw;
+      const bool in_a = fa < P.M, in_b = fb < P.N;     // (rows are padded to 4 floats: lda, ldb % 4 == 0)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int k = k0 + 4 * (ac + 2 * i);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < fmax) {
-          const float* p = src + (size_t)k * ld + f;
-          if (k < kend) x.x = __ldg(p);
-          if (k + 1 < kend) x.y = __ldg(p + ld);
-          if (k + 2 < kend) x.z = __ldg(p + 2 * (size_t)ld);
-          if (k + 3 < kend) x.w = __ldg(p + 3 * (size_t)ld);
-        }
-        v[i] = x;
+        const bool kin = k0 + i < K;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+        // (features M .. round_up(M, 4) - 1 of a row are read too: they only reach output rows / columns >= M / N,
+        // which are never stored)
+        if (kin && in_a) x = ldcg4(P.A + (size_t)(k0 + i) * P.lda + fa);
+        if (kin && in_b) y = ldcg4(P.B + (size_t)(k0 + i) * P.ldb + fb);
+        va[i] = x; vb[i] = y;
       }
     };
-    auto load_ab = [&](float4 (&va)[4], float4 (&vb)[4], uint32_t g) {
-      if (g >= n_slabs) return;
-      load_t(va, a.A, a.lda, m0, a.M, kbeg + (int)g * BK);
-      load_t(vb, a.B, a.ldb, n0, a.N, kbeg + (int)g * BK);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);     // bias-gradient partial sums of this lane's 4 features
+    auto flush_colsum = [&](int tile) {
+      const DwProblem& P = a.p[a.tile_prob[tile]];
+      if (P.colsum && a.tile_n[tile] == 0) {
+        const int f = a.tile_m[tile] * BM + 4 * lane;
+        if (f < P.M && cs.x != 0.f) atomicAdd(P.colsum + f, cs.x);
+        if (f + 1 < P.M && cs.y != 0.f) atomicAdd(P.colsum + f + 1, cs.y);
+        if (f + 2 < P.M && cs.z != 0.f) atomicAdd(P.colsum + f + 2, cs.z);
+        if (f + 3 < P.M && cs.w != 0.f) atomicAdd(P.colsum + f + 3, cs.w);
+      }
+      cs = make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto produce = [&](float4 (&va)[4], float4 (&vb)[4], uint32_t g) {
+    auto produce = [&](float4 (&va)[4], float4 (&vb)[4], const Cur& c, Cur& pf) {
       const uint32_t st = g % kStages;
       const uint32_t stage_base = smem + st * kStage;
-      if (g >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
+      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        csum += (va[i].x + va[i].y) + (va[i].z + va[i].w);
-        const uint32_t off = arow + (uint32_t)(((ac + 2 * i) ^ (ar & 7)) * 16);
+        cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
+        const uint32_t r = (uint32_t)(4 * pw + i);
+        const uint32_t off = lane_blk + r * 128u + ((lane_c32 ^ (r & 3u)) * 32u);
         split_store(stage_base + off, stage_base + kATile + off, va[i]);
         split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBTile + off, vb[i]);
       }
-      load_ab(va, vb, g + 2);                            // two slabs stay in flight
+      if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);   // last slab of this tile in the range
+      load_ab(va, vb, pf);                               // two slabs stay in flight
+      advance(pf);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(B.afull0 + 8 * st);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
+      ++g;
     };
+    Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs}, pf = c;
     float4 va0[4], vb0[4], va1[4], vb1[4];
-    load_ab(va0, vb0, 0);
-    load_ab(va1, vb1, 1);
-    for (uint32_t g = 0; g < n_slabs; g += 2) {
-      produce(va0, vb0, g);
-      if (g + 1 < n_slabs) produce(va1, vb1, g + 1);
+    load_ab(va0, vb0, pf); advance(pf);
+    load_ab(va1, vb1, pf); advance(pf);
+    while (c.u < u_end) {
+      produce(va0, vb0, c, pf); advance(c);
+      if (c.u < u_end) { produce(va1, vb1, c, pf); advance(c); }
     }
-    if (a.colsum && blockIdx.x == 0 && m0 + ar < a.M && csum != 0.f) atomicAdd(a.colsum + m0 + ar, csum);
   } else {
-    // ================= consumers: TMEM drain, red.global.add epilogue =================
+    // ================= consumers: TMEM drain, red.global.add epilogue per tile segment =================
     const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
     const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
-    float acc[kAcc];
-#pragma unroll
-    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-    for (uint32_t c = 0; c < n_slabs; ++c) drain_chunk<false>(acc, tmem_row, col_half, c, BN, B.rfull0, B.rempty0);
-
-    // ---- epilogue: registers -> 32x32 smem transpose (XOR-swizzled columns) -> 128-byte red.global.add rows ----
     float* stg = reinterpret_cast<float*>(smem_raw + kStagingOff + warp * kStagingWarp);
+    uint32_t g = 0;
+    const bool dbg_c = dbg_cta && tid == 0;
+    long long t_main = 0, t_epi = 0, t0c = 0;
+    for (int u = u_beg; u < u_end;) {
+      const int tile = u / n_slabs, s0 = u - tile * n_slabs;
+      const int len = min(n_slabs - s0, u_end - u);
+      const DwProblem& P = a.p[a.tile_prob[tile]];
+      const int m0 = a.tile_m[tile] * BM, n0 = a.tile_n[tile] * TN;
+      const int BN = min(TN, (P.N - n0 + 15) & ~15);
+      float acc[kAcc];
 #pragma unroll
-    for (int q = 0; q < kAcc / 32; ++q) {
-      const int c0 = col_half + 32 * q;
-      if (c0 < BN) {
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+      if (dbg_c) t0c = clock64();
+      for (int i = 0; i < len; ++i, ++g) drain_chunk<false>(acc, tmem_row, col_half, g, BN, B.rfull0, B.rempty0);
+      if (dbg_c) { const long long t1 = clock64(); t_main += t1 - t0c; t0c = t1; }
+      // ---- registers -> 32x32 smem transpose (XOR-swizzled columns) -> 128-byte red.global.add rows ----
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = acc[32 * q + j];
-        __syncwarp();
-        const int col = n0 + c0 + lane;
-        if (col < a.N) {
-          const int mr0 = m0 + quarter * 32;
-          float* __restrict__ cp = a.C + (size_t)mr0 * a.ldc + col;
+      for (int q = 0; q < kAcc / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = acc[32 * q + j];
+          __syncwarp();
+          const int col = n0 + c0 + lane;
+          if (col < P.N) {
+            const int mr0 = m0 + quarter * 32;
+            float* __restrict__ cp = P.C + (size_t)mr0 * P.ldc + col;
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r)
-            if (mr0 + r < a.M) atomicAdd(cp + (size_t)r * a.ldc, stg[r * 32 + (lane ^ r)]);
+            for (int r = 0; r < 32; ++r)
+              if (mr0 + r < P.M) atomicAdd(cp + (size_t)r * P.ldc, stg[r * 32 + (lane ^ r)]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      u += len;
+      if (dbg_c) t_epi += clock64() - t0c;
     }
+    if (dbg_c) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
   }
   cta_teardown(tmem_d, warp);
 }
 
 long long* g_dbg = nullptr;
+long long* g_dbg_dw = nullptr;
 int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
 template <typename Kern>
@@ -1252,23 +1350,51 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   return fgs::check_launch("mlp_chain", st);
 }
 
+// All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first
+// min(K, *rows_dev) rows, colsum_i[m] += sum_k A_i[k][m] (may be NULL).  Rows of A / B must be readable in whole
+// float4s (lda, ldb % 4 == 0, 16-byte aligned bases).
+int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st) {
+  if (n <= 0 || K <= 0) return 0;
+  if (n > kDwMaxProblems) return fgs::fail_arg("mlp_dw: too many problems");
+  DwArgs a;
+  memset(&a, 0, sizeof(a));
+  int nt = 0;
+  for (int i = 0; i < n; ++i) {
+    const DwProblemHost& h = probs[i];
+    if (h.M <= 0 || h.N <= 0) continue;
+    if ((h.lda & 3) || (h.ldb & 3) || (((uintptr_t)h.A | (uintptr_t)h.B) & 15))
+      return fgs::fail_arg("mlp_dw needs 16-byte aligned operands with leading dimensions % 4 == 0");
+    if (((h.M + 3) & ~3) > h.lda || ((h.N + 3) & ~3) > h.ldb) return fgs::fail_arg("mlp_dw: operand rows must be padded to 4 floats");
+    DwProblem& p = a.p[i];
+    p.A = h.A; p.B = h.B; p.C = h.C; p.colsum = h.colsum;
+    p.M = h.M; p.N = h.N; p.lda = h.lda; p.ldb = h.ldb; p.ldc = h.ldc;
+    for (int m = 0; m < fgs::cdiv(h.M, BM); ++m)
+      for (int c = 0; c < fgs::cdiv(h.N, TN); ++c) {
+        if (nt >= kDwMaxTiles) return fgs::fail_arg("mlp_dw: more than 32 output tiles");
+        a.tile_prob[nt] = (unsigned char)i; a.tile_m[nt] = (unsigned char)m; a.tile_n[nt] = (unsigned char)c;
+        ++nt;
+      }
+  }
+  if (nt == 0) return 0;
+  a.n_tiles = nt; a.K = K; a.rows_dev = rows_dev; a.dbg = g_dbg_dw;
+  static bool configured = false;
+  int rc = configure_once(mlp_dw_kernel, configured, "mlp_dw smem attribute", kSmemBytes);
+  if (rc) return rc;
+  // every CTA should own at least ~8 slabs, else the epilogues dominate
+  const long long units = (long long)nt * fgs::cdiv(K, BK);
+  int grid = FGS_NUM_SMS;
+  if (units < 8LL * grid) grid = (int)((units + 7) / 8);
+  if (grid < 1) grid = 1;
+  mlp_dw_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
+  return fgs::check_launch("mlp_dw", st);
+}
+
 // C[M,N] += A[K,M]^T B[K,N] over the first min(K, *rows_dev) rows; colsum[m] += sum_k A[k][m] (may be NULL)
 int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             float* colsum, const int32_t* rows_dev, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  static bool configured = false;
-  int rc = configure_once(gemm_tn_kernel, configured, "gemm_tn smem attribute", kSmemBytes);
-  if (rc) return rc;
-  TnArgs a{A, B, C, colsum, rows_dev, M, N, K, lda, ldb, ldc};
-  dim3 grid(fgs::cdiv(N, TN), fgs::cdiv(M, BM), 1);
-  const int tiles = grid.x * grid.y;
-  int splits = FGS_NUM_SMS / tiles;                 // one wave: every CTA owns an SM (smem, 512 TMEM columns)
-  const int max_splits = fgs::cdiv(K, 4 * BK);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  grid.z = splits;
-  gemm_tn_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
-  return fgs::check_launch("gemm_tn", st);
+  DwProblemHost p{A, B, C, colsum, M, N, lda, ldb, ldc};
+  return mlp_dw(&p, 1, K, rows_dev, st);
 }
 
 bool tmem_accumulate_enabled() { return g_tmem_accumulate != 0; }
@@ -1326,6 +1452,7 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 // CTA (0,0) spent draining chunks (incl. waiting for the tensor core) and in epilogues (NULL switches it off).
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
+  g_dbg_dw = buf ? (long long*)buf + 10 : nullptr;    // slots 10..19: the weight-gradient kernel
   return 0;
 }
 

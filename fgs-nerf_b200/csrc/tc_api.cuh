@@ -35,6 +35,13 @@ struct ChainStepHost {
 int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
 bool tmem_accumulate_enabled();
 
+// One weight-gradient problem of mlp_dw (gemm_tcw.cu: mlp_dw_kernel): C[M,N] += A[K,M]^T B[K,N], colsum[m] += sum_k A[k][m]
+struct DwProblemHost {
+  const float* A; const float* B; float* C; float* colsum;
+  int M, N, lda, ldb, ldc;
+};
+int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st);
+
 // generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,

@@ -209,7 +209,7 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
 int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
 
-/* Debug aid: 10 x int64 device buffer that subsequent pre-split GEMM launches fill with the clock cycles
+/* Debug aid: 20 x int64 device buffer (slots 10..19: the same phases of the weight-gradient kernel) that subsequent pre-split GEMM launches fill with the clock cycles
  * the roles of CTA (0,0) spent per phase (consumer drain / epilogue, producer wait / work, issuer waits on
  * a_full / b_full / r_empty / free, issuer total; tools/gemm_phase_probe.py).  NULL = off. */
 int fgs_debug_gemm_phases(void* buf);

@@ -10,7 +10,7 @@ engine.set_gemm_tmem_accumulate(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); out = torch.zeros(M, N, device=dev)
 bias = torch.randn(N, device=dev); bits = torch.zeros(M, 8, dtype=torch.int32, device=dev)
 rows = torch.tensor([M], dtype=torch.int32, device=dev)
-dbg = torch.zeros(10, dtype=torch.int64, device=dev)
+dbg = torch.zeros(20, dtype=torch.int64, device=dev)
 names = ["consumer: chunk wait + drain", "consumer: epilogues", "-", "producer: wait stage free", "producer: split/store/load issue",
          "issuer: wait a_full", "issuer: wait b_full", "issuer: wait r_empty", "issuer: wait free (B prefetch)", "issuer: total"]
 for rep in range(3):

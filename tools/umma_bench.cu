@@ -8,7 +8,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
-__global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int iters, int kind_f16, int a_tmem, long long* out) {
+__global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int iters, int kind_f16, int a_tmem, int mn, long long* out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 200000);
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + 200016);
@@ -31,7 +31,8 @@ __global__ void bench(int N, uint32_t lbo, uint32_t sbo, uint32_t layout, int it
   long long t0 = 0, t1 = 0, t2 = 0;
   if (tid == 0) {
     const uint32_t fmt = kind_f16 ? 1u : 2u;   // bf16 : tf32
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) |
+                           ((mn & 1) ? (1u << 15) : 0u) | ((mn & 2) ? (1u << 16) : 0u);
     const uint32_t base = smem_u32(sm);
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
@@ -67,7 +68,7 @@ int main() {
   long long* d; cudaMalloc(&d, 64); long long h[3];
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 201000);
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
-  struct V { int N; uint32_t lbo, sbo, layout; int f16; const char* name; int a_tmem; } vs[] = {
+  struct V { int N; uint32_t lbo, sbo, layout; int f16; const char* name; int a_tmem; int mn; } vs[] = {
     {256, 128, 512, 0, 0, "tf32 N=256 no-swizzle lbo128 sbo512"},
     {256, 160, 640, 0, 0, "tf32 N=256 no-swizzle lbo160 sbo640"},
     {128, 160, 640, 0, 0, "tf32 N=128 no-swizzle lbo160 sbo640"},
@@ -81,10 +82,14 @@ int main() {
     {256, 16, 1024, 2, 1, "bf16 N=256 K16 swizzle128B, A from TMEM", 1},
     {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B, A from TMEM", 1},
     {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B"},
+    {128, 4096, 512, 1, 0, "tf32 N=128 A+B MN-major SW128_BASE32B", 0, 3},
+    {256, 4096, 512, 1, 0, "tf32 N=256 A+B MN-major SW128_BASE32B", 0, 3},
+    {128, 4096, 512, 1, 0, "tf32 N=128 A MN-major only", 0, 1},
+    {128, 4096, 512, 1, 0, "tf32 N=128 B MN-major only", 0, 2},
   };
   for (auto& v : vs) {
     const int iters = 2000;
-    bench<<<1, 128, 201000>>>(v.N, v.lbo, v.sbo, v.layout, iters, v.f16, v.a_tmem, d);
+    bench<<<1, 128, 201000>>>(v.N, v.lbo, v.sbo, v.layout, iters, v.f16, v.a_tmem, v.mn, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", v.name, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);

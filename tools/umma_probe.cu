@@ -7,14 +7,14 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout = 0) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 
 // which: 0 = probe B, 1 = probe A (then B is the identity: D[m][n] = A(m, k=n) for n < 8)
-__global__ void probe(int which, int mn_major, uint32_t lbo, uint32_t sbo, int div, float* out) {
-  extern __shared__ __align__(128) unsigned char sm[];
+__global__ void probe(int which, int mn_major, uint32_t lbo, uint32_t sbo, int div, float* out, uint32_t layout) {
+  extern __shared__ __align__(1024) unsigned char sm[];
   float* At = reinterpret_cast<float*>(sm);            // 16 KB
   float* Bt = reinterpret_cast<float*>(sm + 16384);    // 16 KB
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 32768);
@@ -48,7 +48,7 @@ __global__ void probe(int which, int mn_major, uint32_t lbo, uint32_t sbo, int d
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (a_major << 15) | (b_major << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t d_id = make_desc(smem_u32(ident), 128, 512);
-    const uint64_t d_pr = make_desc(smem_u32(probed), lbo, sbo);
+    const uint64_t d_pr = make_desc(smem_u32(probed), lbo, sbo, layout);
     const uint64_t da = which ? d_pr : d_id, db = which ? d_id : d_pr;
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db),
@@ -79,7 +79,7 @@ int main() {
   cudaMalloc(&d, 128 * 16 * 4);
   float h[128 * 16], h2[128 * 16];
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-  struct V { int which, mn; uint32_t lbo, sbo; const char* name; } vs[] = {
+  struct V { int which, mn; uint32_t lbo, sbo; const char* name; uint32_t layout; } vs[] = {
       {0, 0, 128, 512, "B K-major  lbo=128 sbo=512 (known good)"},
       {0, 1, 2048, 128, "B MN-major lbo=2048 sbo=128"},
       {0, 1, 128, 2048, "B MN-major lbo=128 sbo=2048"},
@@ -87,10 +87,17 @@ int main() {
       {0, 1, 256, 1024, "B MN-major lbo=256 sbo=1024"},
       {1, 1, 4096, 128, "A MN-major lbo=4096 sbo=128"},
       {1, 1, 128, 4096, "A MN-major lbo=128 sbo=4096"},
+      {0, 1, 4096, 1024, "B MN-major SW128 (layout 2) lbo=4096 sbo=1024", 2},
+      {0, 1, 1024, 4096, "B MN-major SW128 (layout 2) lbo=1024 sbo=4096", 2},
+      {0, 1, 4096, 1024, "B MN-major SW128_BASE32B (layout 1) lbo=4096 sbo=1024", 1},
+      {1, 1, 4096, 1024, "A MN-major SW128 (layout 2) lbo=4096 sbo=1024", 2},
+      {1, 1, 1024, 4096, "A MN-major SW128 (layout 2) lbo=1024 sbo=4096", 2},
+      {1, 1, 4096, 1024, "A MN-major SW128_BASE32B (layout 1) lbo=4096 sbo=1024", 1},
+      {0, 0, 16, 1024, "B K-major SW128 (layout 2) sbo=1024 (known good)", 2},
   };
   for (auto& v : vs) {
     for (int pass = 0; pass < 2; ++pass) {
-      probe<<<1, 128, 40000>>>(v.which, v.mn, v.lbo, v.sbo, pass ? 2048 : 1, d);
+      probe<<<1, 128, 40000>>>(v.which, v.mn, v.lbo, v.sbo, pass ? 2048 : 1, d, v.layout);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s: CUDA error %s\n", v.name, cudaGetErrorString(e)); return 1; }
       cudaMemcpy(pass ? h2 : h, d, sizeof(h), cudaMemcpyDeviceToHost);
