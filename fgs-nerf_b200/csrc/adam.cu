@@ -232,28 +232,77 @@ adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, floa
 __global__ void __launch_bounds__(1024)
 brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ list) {
   __shared__ int s_warp[32];
-  const int per = (n_bricks + 1023) / 1024;
-  const int beg = threadIdx.x * per, end = min(beg + per, n_bricks);
-  int cnt = 0;
-  for (int b = beg; b < end; ++b) cnt += flags[b] ? 1 : 0;
-  const int incl = warp_incl_scan(cnt);
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
   const int w = threadIdx.x >> 5;
-  if (lane_id() == 31) s_warp[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    const int v = s_warp[lane_id()];
-    const int sc = warp_incl_scan(v);
-    s_warp[lane_id()] = sc - v;
-    if (lane_id() == 31) list[0] = sc;
-  }
-  __syncthreads();
-  int o = 1 + incl - cnt + s_warp[w];
-  for (int b = beg; b < end; ++b) {
-    if (flags[b]) {
-      list[o++] = b;
-      flags[b] = 0;
+  const bool vec = (((uintptr_t)flags) & 15) == 0;
+  // passes of 1024 threads x 64 flags; a thread's run is read as four 16-byte words, all loads in flight
+  // (the byte-by-byte dependent loop took 23 us for 64 K flags)
+  for (int base = 0; base < n_bricks; base += 1024 * 64) {
+    const int beg = base + threadIdx.x * 64;
+    uint32_t m[16];                                   // bit 8 j + 7 of word i set <=> flag 4 i + j nonzero
+    const bool full = vec && beg + 64 <= n_bricks;
+    if (full) {
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(flags + beg);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = src[q];
+        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = beg + 4 * i + j;
+          if (b < n_bricks) x |= (uint32_t)flags[b] << (8 * j);
+        }
+        m[i] = x;
+      }
     }
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      m[i] = ((((m[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m[i]) & 0x80808080u);
+      cnt += __popc(m[i]);
+    }
+    const int incl = warp_incl_scan(cnt);
+    const int carry = s_carry;                        // total of the previous passes (rewritten below by warp 0)
+    if (lane_id() == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const int v = s_warp[lane_id()];
+      const int sc = warp_incl_scan(v);
+      s_warp[lane_id()] = sc - v;
+      __syncwarp();
+      if (lane_id() == 31) s_carry = carry + sc;
+    }
+    __syncthreads();
+    if (cnt) {
+      int o = 1 + carry + incl - cnt + s_warp[w];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t x = m[i];
+        while (x) {
+          const int bit = __ffs(x) - 1;               // 7, 15, 23 or 31
+          x &= x - 1;
+          list[o++] = beg + 4 * i + (bit >> 3);
+        }
+      }
+      if (full) {
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(flags + beg);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = z;
+      } else {
+        for (int b = beg; b < min(beg + 64, n_bricks); ++b) flags[b] = 0;
+      }
+    }
+    __syncthreads();                                  // s_warp / s_carry are reused by the next pass
   }
+  if (threadIdx.x == 0) list[0] = s_carry;
 }
 
 // gather / scatter of listed k0 gradient bricks (768 floats each, channels-last [X][Y][Z][12]) to and

@@ -89,8 +89,20 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
   const int per = (n + 1023) / 1024;
   const int beg = threadIdx.x * per;
   const int end = min(beg + per, n);
+  // per <= 8 (n <= 8192 rays, the usual batch): the thread's run lives in registers, read once with all loads in
+  // flight (the dependent `sum += cnt[i]` loop paid one memory latency per element, twice)
+  constexpr int kReg = 8;
+  int r[kReg];
+  const bool in_regs = per <= kReg;
   int sum = 0;
-  for (int i = beg; i < end; ++i) sum += cnt[i];
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kReg; ++i) r[i] = (i < per && beg + i < n) ? cnt[beg + i] : 0;
+#pragma unroll
+    for (int i = 0; i < kReg; ++i) sum += r[i];
+  } else {
+    for (int i = beg; i < end; ++i) sum += cnt[i];
+  }
   const int incl = warp_incl_scan(sum);
   const int w = threadIdx.x >> 5;
   if (lane_id() == 31) s_warp[w] = incl;
@@ -107,9 +119,17 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
   }
   __syncthreads();
   int run = incl - sum + s_warp[w];
-  for (int i = beg; i < end; ++i) {
-    off[i] = run;
-    run += cnt[i];
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kReg; ++i) {
+      if (i < per && beg + i < n) off[beg + i] = run;
+      run += r[i];
+    }
+  } else {
+    for (int i = beg; i < end; ++i) {
+      off[i] = run;
+      run += cnt[i];
+    }
   }
 }
 
