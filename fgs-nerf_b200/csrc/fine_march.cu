@@ -9,9 +9,9 @@
 //   march_kernel   warp per ray: t_min/t_max/N_steps, per-step bbox + MaskCache test, survivors
 //                  recorded as a bitmap (1 bit per step) + count
 //   scan_kernel    exclusive scan of the per-ray counts (single CTA; N <= 2^20 rays)
-//   level1_kernel  warp per ray: survivors get sdf, 6-tap gradient, alpha; the transmittance
-//                  recurrence runs over the warp with shuffles (early stop T<1e-3, alpha and
-//                  weight thresholds) and leaves flags + the per-ray level-2 count
+//   expand1 / sample1 / weights1  survivors get sdf, 6-tap gradient, alpha (thread per sample); the
+//                  transmittance recurrence runs over a warp per ray with shuffles (early stop T<1e-3,
+//                  alpha and weight thresholds) and leaves flags + the per-ray level-2 count
 //   compact2_kernel warp per ray: level-2 index list
 // Arithmetic follows the reference op by op (see fine_common.cuh / ray_math.cuh) so the
 // surviving sample sets are bit-identical.
@@ -169,9 +169,66 @@ __device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float
   return fminf(fmaxf(a, 0.f), 1.f);
 }
 
-__global__ void __launch_bounds__(kBlock, 3) level1_kernel(const __grid_constant__ FgsFineParams P) {
+// Level 1 runs as three kernels so that the expensive part is balanced over SAMPLES, not rays (rays keep
+// between 0 and ~200 samples after the MaskCache; with a warp walking one ray's step bitmap the longest rays
+// set the kernel time while 90 % of the warp slots sat empty: 85 us, sm__warps_active 11 %):
+//   expand1_kernel   warp per ray: step bitmap -> (ray_id1, step_id1) at off1[ray] + rank
+//   sample1_kernel   thread per level-1 sample: point, SDF, 6-tap gradient, NeuS alpha (56 gathers)
+//   weights1_kernel  warp per ray: transmittance recurrence over the ray's alphas (early stop T < 1e-3,
+//                    alpha / weight thresholds), flags, level-2 count
+// The arithmetic per sample and the order of the recurrence are unchanged.
+__global__ void __launch_bounds__(kBlock) expand1_kernel(const __grid_constant__ FgsFineParams P) {
   const int lane = lane_id();
+  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
+    const int base = P.off1[ray];
+    const int c1 = P.cnt1[ray];
+    if (c1 == 0) continue;
+    if (base + c1 > P.cap_m1) {           // over capacity (flagged by the scan): mark the slots that exist
+      for (int i = base + lane; i < min(base + c1, P.cap_m1); i += 32) P.ray_id1[i] = -1;
+      continue;
+    }
+    int n = P.n_steps[ray];
+    n = min(n, P.cap_words * 32);
+    const int words = (n + 31) >> 5;
+    int run = 0;
+    for (int w = 0; w < words; ++w) {
+      const unsigned word = P.bits[(size_t)ray * P.cap_words + w];
+      if (word == 0) continue;
+      if ((word >> lane) & 1u) {
+        const int idx = base + run + __popc(word & lanemask_lt());
+        P.ray_id1[idx] = ray;
+        P.step_id1[idx] = w * 32 + lane;
+      }
+      run += __popc(word);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) sample1_kernel(const __grid_constant__ FgsFineParams P) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
+  const int M1 = min(P.counters[FGS_CNT_M1], P.cap_m1);
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < M1; i += gridDim.x * kBlock) {
+    const int ray = P.ray_id1[i];
+    if (ray < 0) continue;
+    const int step = P.step_id1[i];
+    const float* o = P.rays_o + 3 * (size_t)ray;
+    const float* d = P.rays_d + 3 * (size_t)ray;
+    const float vx = P.viewdirs[3 * (size_t)ray], vy = P.viewdirs[3 * (size_t)ray + 1],
+                vz = P.viewdirs[3 * (size_t)ray + 2];
+    const Ray r = make_ray(o, d, P.t_min[ray]);
+    float px, py, pz, sdf, gx, gy, gz;
+    ray_point(r, P.stepdist, step, px, py, pz);
+    sdf_and_grad(P, g, px, py, pz, sdf, gx, gy, gz);
+    P.sdf1[i] = sdf;
+    P.grad1[i] = gx;
+    P.grad1[(size_t)P.cap_m1 + i] = gy;
+    P.grad1[2 * (size_t)P.cap_m1 + i] = gz;
+    P.alpha1[i] = neus_alpha(sdf, gx, gy, gz, vx, vy, vz, P.dist, P.inv_s);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) weights1_kernel(const __grid_constant__ FgsFineParams P) {
+  const int lane = lane_id();
   const float thres = P.fast_color_thres;
   int tot_a = 0;
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
@@ -181,37 +238,13 @@ __global__ void __launch_bounds__(kBlock, 3) level1_kernel(const __grid_constant
       if (lane == 0) { P.cnt2[ray] = 0; P.alphainv_last[ray] = 1.f; }
       continue;
     }
-    const float* o = P.rays_o + 3 * (size_t)ray;
-    const float* d = P.rays_d + 3 * (size_t)ray;
-    const float vx = P.viewdirs[3 * (size_t)ray], vy = P.viewdirs[3 * (size_t)ray + 1],
-                vz = P.viewdirs[3 * (size_t)ray + 2];
-    const Ray r = make_ray(o, d, P.t_min[ray]);
-    int n = P.n_steps[ray];
-    n = min(n, P.cap_words * 32);
-    const int words = (n + 31) >> 5;
     float Tc = 1.f;
     bool stopped = false;
-    int run = 0, c2 = 0;
-    for (int w = 0; w < words; ++w) {
-      const unsigned word = P.bits[(size_t)ray * P.cap_words + w];
-      if (word == 0) continue;
-      const bool mine = (word >> lane) & 1u;
-      const int idx = base + run + __popc(word & lanemask_lt());
-      float alpha = 0.f;
-      if (mine) {
-        const int step = w * 32 + lane;
-        float px, py, pz, sdf, gx, gy, gz;
-        ray_point(r, P.stepdist, step, px, py, pz);
-        sdf_and_grad(P, g, px, py, pz, sdf, gx, gy, gz);
-        alpha = neus_alpha(sdf, gx, gy, gz, vx, vy, vz, P.dist, P.inv_s);
-        P.ray_id1[idx] = ray;
-        P.step_id1[idx] = step;
-        P.sdf1[idx] = sdf;
-        P.grad1[idx] = gx;
-        P.grad1[(size_t)P.cap_m1 + idx] = gy;
-        P.grad1[2 * (size_t)P.cap_m1 + idx] = gz;
-        P.alpha1[idx] = alpha;
-      }
+    int c2 = 0;
+    for (int b = 0; b < c1; b += 32) {
+      const bool mine = b + lane < c1;
+      const int idx = base + b + lane;
+      const float alpha = mine ? P.alpha1[idx] : 0.f;
       const bool kept = mine && (alpha > thres);  // model/nerf.py:803
       const float a_eff = kept ? alpha : 0.f;
       unsigned m = __ballot_sync(0xffffffffu, kept);
@@ -238,7 +271,6 @@ __global__ void __launch_bounds__(kBlock, 3) level1_kernel(const __grid_constant
         P.flag1[idx] = (kept ? FGS_F_ALPHA : 0) | (visited ? FGS_F_VISIT : 0) | (l2 ? FGS_F_L2 : 0);
       }
       c2 += __popc(__ballot_sync(0xffffffffu, l2));
-      run += __popc(word);
     }
     if (lane == 0) {
       P.cnt2[ray] = c2;
@@ -284,8 +316,14 @@ int launch_march(const FgsFineParams& P, cudaStream_t st) {
   if ((rc = fgs::check_launch("fine march", st))) return rc;
   scan_kernel<<<1, 1024, 0, st>>>(P.cnt1, P.off1, P.n_rays, P.counters, FGS_CNT_M1, P.cap_m1, 2);
   if ((rc = fgs::check_launch("fine scan1", st))) return rc;
-  level1_kernel<<<grid, kBlock, 0, st>>>(P);
+  expand1_kernel<<<grid, kBlock, 0, st>>>(P);
+  if ((rc = fgs::check_launch("fine expand1", st))) return rc;
+  // the sample count lives on the device: size the grid for the capacity, capped at a few waves (grid-stride loop)
+  const int grid_s = fgs::stream_grid(P.cap_m1, kBlock, 8);
+  sample1_kernel<<<grid_s, kBlock, 0, st>>>(P);
   if ((rc = fgs::check_launch("fine level1", st))) return rc;
+  weights1_kernel<<<grid, kBlock, 0, st>>>(P);
+  if ((rc = fgs::check_launch("fine weights1", st))) return rc;
   scan_kernel<<<1, 1024, 0, st>>>(P.cnt2, P.off2, P.n_rays, P.counters, FGS_CNT_M2, P.cap_m2, 4);
   if ((rc = fgs::check_launch("fine scan2", st))) return rc;
   compact2_kernel<<<grid, kBlock, 0, st>>>(P);

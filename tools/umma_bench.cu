@@ -82,6 +82,7 @@ int main() {
     {256, 16, 1024, 2, 1, "bf16 N=256 K16 swizzle128B, A from TMEM", 1},
     {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B, A from TMEM", 1},
     {128, 16, 1024, 2, 1, "bf16 N=128 K16 swizzle128B"},
+    {256, 16, 512, 4, 0, "tf32 N=256 swizzle64B (sbo 512) A and B", 0, 0},
     {128, 4096, 512, 1, 0, "tf32 N=128 A+B MN-major SW128_BASE32B", 0, 3},
     {256, 4096, 512, 1, 0, "tf32 N=256 A+B MN-major SW128_BASE32B", 0, 3},
     {128, 4096, 512, 1, 0, "tf32 N=128 A MN-major only", 0, 1},
