@@ -63,16 +63,22 @@ __device__ __forceinline__ NormalCtx make_normal(float gx, float gy, float gz) {
 // displace_list = sorted(set(grad_feat + (1.0,))) = 0.5, 1.0, 1.5, 2.0 (model/nerf.py:843-850)
 __device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); }
 
+// independent parts of a level-2 row (blockIdx.y of feat_kernel / feat_bwd_kernel)
+constexpr int kTaskK0 = 0, kTaskPE = 1, kTaskRefl = 2, kTaskTap0 = 3, kNumTasks = 7;
+
 __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
+  // blockIdx.y = which independent part of the row this CTA builds (uniform per CTA: no divergence).  With one
+  // thread building a whole row only ~1300 warps existed for ~40 K samples (sm__warps_active 14 %, 79 us).
+  const int task = blockIdx.y;
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
     float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
     float iw, ih, id;
     cont_index(g, q.px, q.py, q.pz, iw, ih, id);
     // ---- k0: DenseGrid.forward (model/grid.py:49-59), channels-last storage ----
-    {
+    if (task == kTaskK0) {
       const Tri t = tri_setup(iw, ih, id);
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
 #pragma unroll
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
       st4(row + FGS_X0_K0 + 8, a2);
     }
     // ---- positional encodings (model/nerf.py:836-839, 870-873) ----
-    {
+    if (task == kTaskPE) {
       const float rx[3] = {__fdiv_rn(__fsub_rn(q.px, g.mn[0]), g.ext[0]),
                            __fdiv_rn(__fsub_rn(q.py, g.mn[1]), g.ext[1]),
                            __fdiv_rn(__fsub_rn(q.pz, g.mn[2]), g.ext[2])};
@@ -109,22 +115,24 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
     }
     const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
                         P.viewdirs[3 * (size_t)q.ray + 2]};
+    if (task == kTaskPE) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      row[FGS_X0_VIEW + c] = v[c];
-      float f = 1.f;
+      for (int c = 0; c < 3; ++c) {
+        row[FGS_X0_VIEW + c] = v[c];
+        float f = 1.f;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float e = __fmul_rn(v[c], f);
-        row[FGS_X0_VIEW + 3 + c * 3 + k] = sinf(e);
-        row[FGS_X0_VIEW + 12 + c * 3 + k] = cosf(e);
-        f *= 2.f;
+        for (int k = 0; k < 3; ++k) {
+          const float e = __fmul_rn(v[c], f);
+          row[FGS_X0_VIEW + 3 + c * 3 + k] = sinf(e);
+          row[FGS_X0_VIEW + 12 + c * 3 + k] = cosf(e);
+          f *= 2.f;
+        }
       }
+      row[FGS_X0_SDF] = P.sdf1[q.idx1];
     }
-    row[FGS_X0_SDF] = P.sdf1[q.idx1];
     // ---- hierarchical SDF taps (sample_sdfs, model/nerf.py:597-637, use_grad_norm=True) ----
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
+    if (task >= kTaskTap0 && task < kTaskTap0 + 4) {
+      const int d = task - kTaskTap0;
       float gr[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
 #pragma unroll
       for (int a = 0; a < 3; ++a) row[FGS_X0_AGRAD + a * 4 + d] = __fdiv_rn(gr[a], den);
     }
+    if (task != kTaskRefl) continue;
     const float gx = P.grad1[q.idx1], gy = P.grad1[(size_t)P.cap_m1 + q.idx1],
                 gz = P.grad1[2 * (size_t)P.cap_m1 + q.idx1];
     row[FGS_X0_GRAD] = gx; row[FGS_X0_GRAD + 1] = gy; row[FGS_X0_GRAD + 2] = gz;
@@ -174,6 +183,8 @@ __global__ void __launch_bounds__(kBlock)
 feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientation) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
+  const int task = blockIdx.y;     // k0 scatter | (unused) | reflection chain | 4 displacement levels
+  if (task == kTaskPE) return;     // the encodings of xyz / viewdirs have no trainable inputs
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
     const float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
@@ -181,7 +192,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
     float iw, ih, id;
     cont_index(g, q.px, q.py, q.pz, iw, ih, id);
     // ---- k0 scatter (grid_sample backward wrt input), 3 vector reductions per corner ----
-    {
+    if (task == kTaskK0) {
       const Tri t = tri_setup(iw, ih, id);
       const float4 d0 = ld4(drow + FGS_X0_K0), d1 = ld4(drow + FGS_X0_K0 + 4), d2 = ld4(drow + FGS_X0_K0 + 8);
       const int nbY = (g.Y + 3) >> 2, nbZ = (g.Z + 3) >> 2;
@@ -204,8 +215,8 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
       }
     }
     // ---- 24 hierarchical taps: direct (all_feat) + through the normalised gradients ----
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
+    if (task >= kTaskTap0 && task < kTaskTap0 + 4) {
+      const int d = task - kTaskTap0;
       TapPair tp[3];
       float gr[3], dG[3];
 #pragma unroll
@@ -229,6 +240,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
         tri_scatter1(P.g_sdf, tp[a].hi, g.X, g.Y, g.Z, dhi);
       }
     }
+    if (task != kTaskRefl) continue;
     // ---- reflection encoding -> reflect dir -> normal -> gradient ----
     const float gx = P.grad1[q.idx1], gy = P.grad1[(size_t)P.cap_m1 + q.idx1],
                 gz = P.grad1[2 * (size_t)P.cap_m1 + q.idx1];
@@ -299,14 +311,14 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
 namespace fine {
 
 int launch_feat(const FgsFineParams& P, cudaStream_t st) {
-  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 16);
-  feat_kernel<<<grid, kBlock, 0, st>>>(P);
+  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 4);
+  feat_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P);
   return fgs::check_launch("fine feat", st);
 }
 
 int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st) {
-  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 16);
-  feat_bwd_kernel<<<grid, kBlock, 0, st>>>(P, weight_orientation);
+  const int grid = fgs::stream_grid(P.cap_m2, kBlock, 4);
+  feat_bwd_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P, weight_orientation);
   return fgs::check_launch("fine feat_bwd", st);
 }
 
