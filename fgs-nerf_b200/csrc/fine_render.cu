@@ -6,9 +6,9 @@
 // model/nerf_training.py:307-327 together with the first backward hop: d rgb_marched and
 // d sigmoid_rgb are pushed straight back through the sums into dlogit and d_w1, so neither the
 // per-ray gradients nor the per-sample rgb ever round-trip through HBM.
-// level1_bwd_kernel (warp per ray): alpha2weight backward (render_utils_kernel.cu:654-677) as a
-// reverse warp-shuffle recurrence, the NeuS alpha backward (model/nerf.py:510-544) and the
-// 1 + 6 trilinear scatters into the SDF gradient grid.
+// weights1_bwd_kernel (warp per ray) + sample1_bwd_kernel (thread per level-1 sample): alpha2weight
+// backward (render_utils_kernel.cu:654-677) as a reverse warp-shuffle recurrence, then the NeuS alpha
+// backward (model/nerf.py:510-544) and the 1 + 6 trilinear scatters into the SDF gradient grid.
 #include "fine_common.cuh"
 
 namespace {
@@ -128,17 +128,18 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
   }
 }
 
+// Backward of level 1 in two kernels (as the forward: the recurrence is per ray, the expensive part per sample):
+//   weights1_bwd_kernel  warp per ray: alpha2weight backward (render_utils_kernel.cu:654-677) as a reverse
+//                        warp-shuffle recurrence; leaves d_alpha of every visited sample in d_w1
+//   sample1_bwd_kernel   thread per level-1 sample: NeuS alpha backward (model/nerf.py:510-544) and the 1 + 6
+//                        trilinear scatters into the SDF gradient grid
 __global__ void __launch_bounds__(kBlock)
-level1_bwd_kernel(const __grid_constant__ FgsFineParams P, const float* __restrict__ g_last) {
+weights1_bwd_kernel(const __grid_constant__ FgsFineParams P, const float* __restrict__ g_last) {
   const int lane = lane_id();
-  const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
     const int base = P.off1[ray];
     const int c1 = P.cnt1[ray];
     if (c1 == 0 || base + c1 > P.cap_m1) continue;
-    const float vx = P.viewdirs[3 * (size_t)ray], vy = P.viewdirs[3 * (size_t)ray + 1],
-                vz = P.viewdirs[3 * (size_t)ray + 2];
-    const Ray r = make_ray(P.rays_o + 3 * (size_t)ray, P.rays_d + 3 * (size_t)ray, P.t_min[ray]);
     float back = __fmul_rn(g_last ? g_last[ray] : 0.f, P.alphainv_last[ray]);
     for (int top = c1; top > 0; top -= 32) {
       const int i = top - 1 - lane;
@@ -162,47 +163,63 @@ level1_bwd_kernel(const __grid_constant__ FgsFineParams P, const float* __restri
       if (!part) continue;
       const float a = P.alpha1[idx];
       const double den = __dadd_rn((double)__fsub_rn(1.f, a), 1e-10);
-      const float d_alpha = (float)__dsub_rn((double)__fmul_rn(gw, P.T1[idx]), __ddiv_rn((double)myBack, den));
-      // ---- NeuS alpha backward (model/nerf.py:510-544) ----
-      const float sdf = P.sdf1[idx];
-      const float gx = P.grad1[idx], gy = P.grad1[(size_t)P.cap_m1 + idx], gz = P.grad1[2 * (size_t)P.cap_m1 + idx];
-      const float tc = vx * gx + vy * gy + vz * gz;
-      const float ic = -fmaxf(-tc, 0.f);
-      const float h = ic * P.dist * 0.5f;
-      const float pc = sigm((sdf - h) * P.inv_s), nc = sigm((sdf + h) * P.inv_s);
-      const float u = pc - nc + 1e-5f, q = pc + 1e-5f;
-      const float a_raw = u / q;
-      float d_sdf = 0.f, d_g[3] = {0.f, 0.f, 0.f};
-      if (a_raw >= 0.f && a_raw <= 1.f) {
-        const float d_pc = d_alpha * (q - u) / (q * q);
-        const float d_nc = -d_alpha / q;
-        const float d_prev = d_pc * pc * (1.f - pc) * P.inv_s;
-        const float d_next = d_nc * nc * (1.f - nc) * P.inv_s;
-        d_sdf = d_prev + d_next;
-        const float d_ic = (d_next - d_prev) * P.dist * 0.5f;
-        const float d_tc = (tc < 0.f) ? d_ic : 0.f;
-        d_g[0] = d_tc * vx; d_g[1] = d_tc * vy; d_g[2] = d_tc * vz;
-      }
-      if (l2) {
-        d_sdf += P.d_sdf1[idx];
-        d_g[0] += P.d_grad1[idx];
-        d_g[1] += P.d_grad1[(size_t)P.cap_m1 + idx];
-        d_g[2] += P.d_grad1[2 * (size_t)P.cap_m1 + idx];
-      }
-      // ---- scatter: direct sample + 6 finite-difference taps (model/nerf.py:639-672) ----
-      float px, py, pz, iw, ih, id;
-      ray_point(r, P.stepdist, P.step_id1[idx], px, py, pz);
-      cont_index(g, px, py, pz, iw, ih, id);
-      if (d_sdf != 0.f) tri_scatter1(P.g_sdf, tri_setup(iw, ih, id), g.X, g.Y, g.Z, d_sdf);
+      P.d_w1[idx] = (float)__dsub_rn((double)__fmul_rn(gw, P.T1[idx]), __ddiv_rn((double)myBack, den));   // d_alpha
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) sample1_bwd_kernel(const __grid_constant__ FgsFineParams P) {
+  const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
+  const int M1 = min(P.counters[FGS_CNT_M1], P.cap_m1);
+  for (int idx = blockIdx.x * kBlock + threadIdx.x; idx < M1; idx += gridDim.x * kBlock) {
+    const int ray = P.ray_id1[idx];
+    if (ray < 0) continue;
+    const int fl = P.flag1[idx];
+    if (!(fl & FGS_F_VISIT)) continue;
+    const bool l2 = fl & FGS_F_L2;
+    const float vx = P.viewdirs[3 * (size_t)ray], vy = P.viewdirs[3 * (size_t)ray + 1],
+                vz = P.viewdirs[3 * (size_t)ray + 2];
+    const float d_alpha = P.d_w1[idx];
+    // ---- NeuS alpha backward (model/nerf.py:510-544) ----
+    const float sdf = P.sdf1[idx];
+    const float gx = P.grad1[idx], gy = P.grad1[(size_t)P.cap_m1 + idx], gz = P.grad1[2 * (size_t)P.cap_m1 + idx];
+    const float tc = vx * gx + vy * gy + vz * gz;
+    const float ic = -fmaxf(-tc, 0.f);
+    const float h = ic * P.dist * 0.5f;
+    const float pc = sigm((sdf - h) * P.inv_s), nc = sigm((sdf + h) * P.inv_s);
+    const float u = pc - nc + 1e-5f, q = pc + 1e-5f;
+    const float a_raw = u / q;
+    float d_sdf = 0.f, d_g[3] = {0.f, 0.f, 0.f};
+    if (a_raw >= 0.f && a_raw <= 1.f) {
+      const float d_pc = d_alpha * (q - u) / (q * q);
+      const float d_nc = -d_alpha / q;
+      const float d_prev = d_pc * pc * (1.f - pc) * P.inv_s;
+      const float d_next = d_nc * nc * (1.f - nc) * P.inv_s;
+      d_sdf = d_prev + d_next;
+      const float d_ic = (d_next - d_prev) * P.dist * 0.5f;
+      const float d_tc = (tc < 0.f) ? d_ic : 0.f;
+      d_g[0] = d_tc * vx; d_g[1] = d_tc * vy; d_g[2] = d_tc * vz;
+    }
+    if (l2) {
+      d_sdf += P.d_sdf1[idx];
+      d_g[0] += P.d_grad1[idx];
+      d_g[1] += P.d_grad1[(size_t)P.cap_m1 + idx];
+      d_g[2] += P.d_grad1[2 * (size_t)P.cap_m1 + idx];
+    }
+    // ---- scatter: direct sample + 6 finite-difference taps (model/nerf.py:639-672) ----
+    const Ray r = make_ray(P.rays_o + 3 * (size_t)ray, P.rays_d + 3 * (size_t)ray, P.t_min[ray]);
+    float px, py, pz, iw, ih, id;
+    ray_point(r, P.stepdist, P.step_id1[idx], px, py, pz);
+    cont_index(g, px, py, pz, iw, ih, id);
+    if (d_sdf != 0.f) tri_scatter1(P.g_sdf, tri_setup(iw, ih, id), g.X, g.Y, g.Z, d_sdf);
 #pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        const float dgr = d_g[2 - ax];  // axis 0 = z, 1 = y, 2 = x
-        if (dgr == 0.f) continue;
-        const TapPair tp = make_taps(g, iw, ih, id, ax, 1.0f);
-        const float df = dgr / tp.diff / P.voxel_size;
-        tri_scatter1(P.g_sdf, tp.lo, g.X, g.Y, g.Z, -df);
-        tri_scatter1(P.g_sdf, tp.hi, g.X, g.Y, g.Z, df);
-      }
+    for (int ax = 0; ax < 3; ++ax) {
+      const float dgr = d_g[2 - ax];  // axis 0 = z, 1 = y, 2 = x
+      if (dgr == 0.f) continue;
+      const TapPair tp = make_taps(g, iw, ih, id, ax, 1.0f);
+      const float df = dgr / tp.diff / P.voxel_size;
+      tri_scatter1(P.g_sdf, tp.lo, g.X, g.Y, g.Z, -df);
+      tri_scatter1(P.g_sdf, tp.hi, g.X, g.Y, g.Z, df);
     }
   }
 }
@@ -224,7 +241,10 @@ int launch_composite(const FgsFineParams& P, const FgsFineLoss* L, cudaStream_t 
 
 int launch_level1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t st) {
   const int grid = fgs::stream_grid(P.n_rays, kWarps, 8);
-  level1_bwd_kernel<<<grid, kBlock, 0, st>>>(P, g_last);
+  weights1_bwd_kernel<<<grid, kBlock, 0, st>>>(P, g_last);
+  int rc = fgs::check_launch("fine weights1_bwd", st);
+  if (rc) return rc;
+  sample1_bwd_kernel<<<fgs::stream_grid(P.cap_m1, kBlock, 8), kBlock, 0, st>>>(P);
   return fgs::check_launch("fine level1_bwd", st);
 }
 
