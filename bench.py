@@ -161,8 +161,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: anything the communicator set-up prints ("NCCL version ...")
+        # goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))      # communicators are created lazily
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from fgs_nerf_b200 import _lib, engine, scene
 
     N = args.rays

@@ -104,6 +104,12 @@ extern "C" {
 
 int64_t fgs_fine_wsplit_floats(void) { return (int64_t)wsplit_layout().total; }
 
+int fgs_set_dw_sm_reserve(int n_sms) {
+  FGS_REQUIRE(n_sms >= 0 && n_sms < FGS_NUM_SMS, "reserve must be in [0, number of SMs)");
+  set_dw_sm_reserve(n_sms);
+  return 0;
+}
+
 int fgs_set_mlp_fusion(int on) {
   g_fusion = on ? 1 : 0;
   return 0;
@@ -163,50 +169,74 @@ int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t str
 }
 
 int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream) {
+  return fgs_fine_backward_phase(p, l, 0, stream);
+}
+
+int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int phase, fgs_stream_t stream) {
   int rc = check_params(p);
   if (rc) return rc;
   FGS_REQUIRE(l && l->g_alphainv_last, "loss descriptor incomplete");
+  FGS_REQUIRE(phase >= 0 && phase <= 2, "phase must be 0 (all), 1 (data path) or 2 (weight gradients)");
+  const bool chain = use_chain() && p->dZ;
+  if (phase == 2 && !chain) return 0;      // per-layer path: everything ran in phase 1
   const FgsFineParams& P = *p;
   cudaStream_t st = (cudaStream_t)stream;
   const int* m2 = P.counters + FGS_CNT_M2;
   const int cap = P.cap_m2;
   const int in_dim[8] = {FGS_X0_LD, W, W, W, FGS_XR_LD, W, W, W};
   const int out_dim[8] = {W, W, W, W, W, W, W, 3};
-  if (P.g_mlp_flat && P.g_mlp_floats > 0) {
-    // all 16 MLP gradient tensors are views of one buffer: one clear instead of 16
-    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
-  } else
-  for (int i = 0; i < 8; ++i) {
-    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
-    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
-  }
-  fgs::prof_mark("memset", st);
-  if (use_chain() && P.dZ) {
-    // ---- backward-data chain in one launch: dZ_l = (dZ_{l+1} W_{l+1}) masked by relu'(H_l) ----
+  if (chain) {
     const WSplitLayout L = wsplit_layout();
     auto dz = [&](int i) { return P.dZ + (size_t)i * P.cap_m2 * W; };   // dZ6, dZ5, dZ4, dZ2, dZ1, dZ0
-    const ChainStepHost steps[9] = {
-        bwd_step(P, L, 7, P.dlogit, 4, 3, dz(0), W, W, 0, 5),
-        bwd_step(P, L, 6, dz(0), W, W, dz(1), W, W, 0, 4),
-        bwd_step(P, L, 5, dz(1), W, W, dz(2), W, W, 0, 3),
-        bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 0, -1),      // dXR[:, 0:256] = dZ3 (linear layer)
-        bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 256, -1),    // dXR[:, 256:320] -> feat_bwd
-        bwd_step(P, L, 3, P.dXR, FGS_XR_LD, W, dz(3), W, W, 0, 2),
-        bwd_step(P, L, 2, dz(3), W, W, dz(4), W, W, 0, 1),
-        bwd_step(P, L, 1, dz(4), W, W, dz(5), W, W, 0, 0),
-        bwd_step(P, L, 0, dz(5), W, W, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1)};
-    if ((rc = mlp_chain(steps, 9, cap, m2, st))) return rc;
-    // ---- weight / bias gradients: dW_l = dZ_l^T X_l ----
-    const float* dzl[8] = {dz(5), dz(4), dz(3), P.dXR, dz(2), dz(1), dz(0), P.dlogit};
-    const int dz_ld[8] = {W, W, W, FGS_XR_LD, W, W, W, 4};
-    const float* xin[8] = {P.X0, hidden(P, 0), hidden(P, 1), hidden(P, 2), P.XR, hidden(P, 3), hidden(P, 4), hidden(P, 5)};
-    DwProblemHost dw[8];
-    for (int l = 0; l < 8; ++l)
-      dw[l] = DwProblemHost{dzl[l], xin[l], P.gW[l], P.gB[l], out_dim[l], in_dim[l], dz_ld[l], in_dim[l], in_dim[l]};
-    if ((rc = mlp_dw(dw, 8, cap, m2, st))) return rc;
-    if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
-    return launch_level1_bwd(P, l->g_alphainv_last, st);
+    if (phase != 2) {
+      // ---- data path: backward-data chain in one launch, dZ_l = (dZ_{l+1} W_{l+1}) masked by relu'(H_l),
+      // then the scatters into the grids.  The weight gradients (phase 2) only read what this phase wrote, so a
+      // data-parallel caller can exchange the grid gradients while they run. ----
+      const ChainStepHost steps[9] = {
+          bwd_step(P, L, 7, P.dlogit, 4, 3, dz(0), W, W, 0, 5),
+          bwd_step(P, L, 6, dz(0), W, W, dz(1), W, W, 0, 4),
+          bwd_step(P, L, 5, dz(1), W, W, dz(2), W, W, 0, 3),
+          bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 0, -1),      // dXR[:, 0:256] = dZ3 (linear layer)
+          bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 256, -1),    // dXR[:, 256:320] -> feat_bwd
+          bwd_step(P, L, 3, P.dXR, FGS_XR_LD, W, dz(3), W, W, 0, 2),
+          bwd_step(P, L, 2, dz(3), W, W, dz(4), W, W, 0, 1),
+          bwd_step(P, L, 1, dz(4), W, W, dz(5), W, W, 0, 0),
+          bwd_step(P, L, 0, dz(5), W, W, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1)};
+      if ((rc = mlp_chain(steps, 9, cap, m2, st))) return rc;
+      if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
+      if ((rc = launch_level1_bwd(P, l->g_alphainv_last, st))) return rc;
+    }
+    if (phase != 1) {
+      // ---- weight / bias gradients: dW_l = dZ_l^T X_l, all layers in one launch ----
+      if (P.g_mlp_flat && P.g_mlp_floats > 0) {
+        // all 16 MLP gradient tensors are views of one buffer: one clear instead of 16
+        if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
+      } else {
+        for (int i = 0; i < 8; ++i) {
+          if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
+          if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
+        }
+      }
+      fgs::prof_mark("memset", st);
+      const float* dzl[8] = {dz(5), dz(4), dz(3), P.dXR, dz(2), dz(1), dz(0), P.dlogit};
+      const int dz_ld[8] = {W, W, W, FGS_XR_LD, W, W, W, 4};
+      const float* xin[8] = {P.X0, hidden(P, 0), hidden(P, 1), hidden(P, 2), P.XR, hidden(P, 3), hidden(P, 4), hidden(P, 5)};
+      DwProblemHost dw[8];
+      for (int i = 0; i < 8; ++i)
+        dw[i] = DwProblemHost{dzl[i], xin[i], P.gW[i], P.gB[i], out_dim[i], in_dim[i], dz_ld[i], in_dim[i], in_dim[i]};
+      if ((rc = mlp_dw(dw, 8, cap, m2, st))) return rc;
+    }
+    return 0;
   }
+  if (P.g_mlp_flat && P.g_mlp_floats > 0) {
+    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
+  } else {
+    for (int i = 0; i < 8; ++i) {
+      if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
+      if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
+    }
+  }
+  fgs::prof_mark("memset", st);
   // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
   // layer 7: logit = H5 W7^T + b7
   if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st, P.gB[7]))) return rc;

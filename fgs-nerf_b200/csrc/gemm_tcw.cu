@@ -1212,6 +1212,7 @@ __global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_cons
 
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
+int g_dw_sm_reserve = 0;
 int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
 template <typename Kern>
@@ -1382,7 +1383,7 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   if (rc) return rc;
   // every CTA should own at least ~8 slabs, else the epilogues dominate
   const long long units = (long long)nt * fgs::cdiv(K, BK);
-  int grid = FGS_NUM_SMS;
+  int grid = FGS_NUM_SMS - g_dw_sm_reserve;
   if (units < 8LL * grid) grid = (int)((units + 7) / 8);
   if (grid < 1) grid = 1;
   mlp_dw_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
@@ -1398,6 +1399,7 @@ int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ld
 }
 
 bool tmem_accumulate_enabled() { return g_tmem_accumulate != 0; }
+void set_dw_sm_reserve(int n_sms) { g_dw_sm_reserve = n_sms; }
 
 // ---- weight splitting ------------------------------------------------------------------------
 int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {

@@ -41,6 +41,8 @@ struct DwProblemHost {
   int M, N, lda, ldb, ldc;
 };
 int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st);
+// leave n SMs free while mlp_dw runs (a data-parallel step overlaps the gradient exchange with it)
+void set_dw_sm_reserve(int n_sms);
 
 // generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
 int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,

@@ -78,6 +78,8 @@ _LP = C.POINTER(FgsFineLoss)
 _lib.declare("fgs_fine_forward", C.c_int, [_PP, _fp])
 _lib.declare("fgs_fine_loss", C.c_int, [_PP, _LP, _fp])
 _lib.declare("fgs_fine_backward", C.c_int, [_PP, _LP, _fp])
+_lib.declare("fgs_fine_backward_phase", C.c_int, [_PP, _LP, C.c_int, _fp])
+_lib.declare("fgs_set_dw_sm_reserve", C.c_int, [C.c_int])
 _lib.declare("fgs_smooth_grad_tv_add_grad", C.c_int,
              [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_double, _fp, _fp])
 _f3 = C.POINTER(C.c_float)
@@ -279,6 +281,8 @@ class FineStepEngine:
         self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._count_evt = torch.cuda.Event()
         self.exchange_bricks = 0
+        self._side = None                  # side stream of the overlapped gradient exchange (data parallel)
+        self.dw_sm_reserve = 16            # SMs the weight-gradient kernel leaves to the collectives
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
         ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
         self.tv_scratch = None
@@ -457,9 +461,10 @@ class FineStepEngine:
             check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
         self._grads_clean = True
 
-    def loss_backward(self, target, n_rays_global=None, has_last_ray=True):
+    def loss_backward(self, target, n_rays_global=None, has_last_ray=True, phase=0):
         """Loss block + backward (model/nerf_training.py:307-347); grads of the MLPs are overwritten,
-        g_sdf / g_k0 accumulated into (call zero_grad() first)."""
+        g_sdf / g_k0 accumulated into (call zero_grad() first).  phase=1 stops after the grid gradients are
+        complete (the weight gradients follow with backward_weights())."""
         t = self.train_cfg
         L = self.L
         _lib.check_input(target, "target", torch.float32)
@@ -476,7 +481,12 @@ class FineStepEngine:
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
-            check(lib.fgs_fine_backward(C.byref(self.P), C.byref(L), st))
+            check(lib.fgs_fine_backward_phase(C.byref(self.P), C.byref(L), int(phase), st))
+
+    def backward_weights(self):
+        """Second phase of loss_backward(phase=1): the MLP weight / bias gradients."""
+        with torch.cuda.device(self.device):
+            check(lib.fgs_fine_backward_phase(C.byref(self.P), C.byref(self.L), 2, stream()))
 
     def smooth_grad_tv_add_grad(self):
         """weight_tv_density * smooth_grad_tv term (model/nerf_training.py:330-336, nerf.py:438-446)."""
@@ -559,13 +569,20 @@ class FineStepEngine:
         brick count crosses to the host once per step to size the collective."""
         if self.world_size == 1:
             return
-        import torch.distributed as dist
+        self._exchange_grids_begin()
         from .dist import all_reduce_sum_
+        all_reduce_sum_([self.g_mlp_flat])
+        self._exchange_grids_finish()
+
+    def _exchange_grids_begin(self):
+        """Grid-gradient exchange, part 1 (everything that does not need the host): union of the touched
+        bricks, ordered brick list, its count on the way to the host, dense reduction of g_sdf."""
+        import torch.distributed as dist
         ws = self.ws
         if not self.sparse_k0:
-            all_reduce_sum_([self.g_sdf, self.g_k0, self.g_mlp_flat])
+            from .dist import all_reduce_sum_
+            all_reduce_sum_([self.g_sdf, self.g_k0])
             dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)
-            lib.fgs_prof_mark(1, stream())
             return
         dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
         with torch.cuda.device(self.device):
@@ -573,9 +590,18 @@ class FineStepEngine:
             check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
             self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
             self._count_evt.record()
-            # the dense reductions run while the host waits for the brick count (the one host sync of a
-            # DP step) and enqueues the sparse exchange behind them
-            all_reduce_sum_([self.g_sdf, self.g_mlp_flat])
+        dist.all_reduce(self.g_sdf)
+
+    def _exchange_grids_finish(self):
+        """Part 2: the one host sync of a DP step (brick count -> size of the collective), then pack ->
+        all-reduce of the packed bricks -> unpack."""
+        import torch.distributed as dist
+        ws = self.ws
+        if not self.sparse_k0:
+            lib.fgs_prof_mark(1, stream())
+            return
+        with torch.cuda.device(self.device):
+            st = stream()
             self._count_evt.synchronize()
             n = int(self._count_host[0])
             if n > 0:
@@ -593,15 +619,38 @@ class FineStepEngine:
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True):
-        """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous."""
+        """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous.
+        Data-parallel (world_size > 1): the backward runs in two phases -- the grid gradients first -- and the
+        exchange of g_sdf / the touched k0 bricks is issued on a side stream while the weight-gradient kernel
+        (which leaves a few SMs free for the collectives) runs on the main one."""
         self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
-        self.loss_backward(target, n_rays_global, has_last_ray)
         t = self.train_cfg
         tv = self.is_tv_step(global_step) and t["weight_tv_density"] > 0
-        if tv and t["smooth_grad_tv"] > 0 and (self.world_size == 1 or self.rank == 0):
-            self.smooth_grad_tv_add_grad()                                 # a pure function of the params:
-        self.all_reduce_grads()                                            # added once, not per rank
+        if self.world_size == 1:
+            self.loss_backward(target, n_rays_global, has_last_ray)
+            if tv and t["smooth_grad_tv"] > 0:
+                self.smooth_grad_tv_add_grad()
+        else:
+            from .dist import all_reduce_sum_
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
+                check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve))
+            main = torch.cuda.current_stream(self.device)
+            self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
+            if tv and t["smooth_grad_tv"] > 0 and self.rank == 0:
+                self.smooth_grad_tv_add_grad()                             # a pure function of the params:
+            self._ev_grids.record(main)                                    # added once, not per rank
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_grids)
+                self._exchange_grids_begin()
+            self.backward_weights()                                        # main stream, overlaps the exchange
+            with torch.cuda.stream(self._side):
+                self._exchange_grids_finish()
+                self._ev_exch.record(self._side)
+            all_reduce_sum_([self.g_mlp_flat])
+            main.wait_event(self._ev_exch)
         if tv and t["sdf_tv"] > 0:
             self.sdf_tv_add_grad(global_step, n_rays_global)
         self.optimizer_step()

@@ -158,6 +158,15 @@ int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t str
  * g_k0 (atomics) and overwrites gW/gB. */
 int fgs_fine_backward(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream);
 
+/* The same in two phases for data-parallel callers: phase 1 = everything that produces g_sdf / g_k0 (the
+ * backward-data chain and the grid scatters), phase 2 = the weight / bias gradients gW / gB, which only read
+ * what phase 1 left behind -- so the grid-gradient exchange can run while phase 2 does.  phase 0 = both. */
+int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int phase, fgs_stream_t stream);
+
+/* Leave n_sms SMs free while the weight-gradient kernel of phase 2 runs (room for the collectives of an
+ * overlapping gradient exchange); 0 = use the whole GPU (default). */
+int fgs_set_dw_sm_reserve(int n_sms);
+
 /* smooth_grad_tv term of nerf.density_total_variation (model/nerf.py:438-446) differentiated
  * analytically: g_sdf += d/dsdf [ weight * mean_{nonempty,3ch}( (conv3(G).detach() - G)^2 ) ],
  * G = central-difference gradient grid of the SDF (nerf.py:491-494).  `scratch` holds
