@@ -513,27 +513,38 @@ class FineStepEngine:
             check(lib.fgs_total_variation_add_grad(ptr(self.sdf), ptr(self.g_sdf), None, w, w, w, 1, self.X, self.Y,
                                                    self.Z, int(dense), 0, stream()))
 
-    def optimizer_step(self, lr_scale=1.0):
+    def _ensure_adam(self):
+        """Adam state (allocated and zeroed on the calling stream, before any side-stream use)."""
+        if self.adam:
+            return
+        self.adam = {"sdf": (torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)),
+                     "k0": (torch.zeros_like(self.k0), torch.zeros_like(self.k0)),
+                     "W": [(torch.zeros_like(w), torch.zeros_like(w)) for w in self.Wt],
+                     "B": [(torch.zeros_like(b), torch.zeros_like(b)) for b in self.Bt]}
+        n = 2 * MLP_LAYERS
+        self._mt = dict(
+            p=(_fp * n)(*[ptr(x) for x in self.Wt + self.Bt]),
+            g=(_fp * n)(*[ptr(x) for x in self.gW + self.gB]),
+            m=(_fp * n)(*[ptr(x[0]) for x in self.adam["W"] + self.adam["B"]]),
+            v=(_fp * n)(*[ptr(x[1]) for x in self.adam["W"] + self.adam["B"]]),
+            n=(C.c_int64 * n)(*[x.numel() for x in self.Wt + self.Bt]))
+
+    def optimizer_step(self, lr_scale=1.0, parts="all"):
         """MaskedAdam.step (model/adam.py:190-221) with the fine-stage param groups
-        (model/nerf_training.py:9-37): k0 masked (skip_zero_grad), sdf and the 16 MLP tensors dense."""
+        (model/nerf_training.py:9-37): k0 masked (skip_zero_grad), sdf and the 16 MLP tensors dense.
+        parts: "all", or "grids" followed by "mlp" (train_step runs the grid part on a side stream while the
+        weight gradients are still being computed)."""
         t = self.train_cfg
-        self.adam_step += 1
+        if parts != "mlp":
+            self.adam_step += 1
         step = self.adam_step
-        if not self.adam:
-            self.adam = {"sdf": (torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)),
-                         "k0": (torch.zeros_like(self.k0), torch.zeros_like(self.k0)),
-                         "W": [(torch.zeros_like(w), torch.zeros_like(w)) for w in self.Wt],
-                         "B": [(torch.zeros_like(b), torch.zeros_like(b)) for b in self.Bt]}
-            n = 2 * MLP_LAYERS
-            self._mt = dict(
-                p=(_fp * n)(*[ptr(x) for x in self.Wt + self.Bt]),
-                g=(_fp * n)(*[ptr(x) for x in self.gW + self.gB]),
-                m=(_fp * n)(*[ptr(x[0]) for x in self.adam["W"] + self.adam["B"]]),
-                v=(_fp * n)(*[ptr(x[1]) for x in self.adam["W"] + self.adam["B"]]),
-                n=(C.c_int64 * n)(*[x.numel() for x in self.Wt + self.Bt]))
+        self._ensure_adam()
         b1, b2, eps = 0.9, 0.99, 1e-8
         with torch.cuda.device(self.device):
             st = stream()
+            if parts == "mlp":
+                self._adam_mlp(step, lr_scale, b1, b2, eps, st)
+                return
             m, v = self.adam["sdf"]
             # sdf: dense Adam (not in skip_zero_grad_fields), gradient cleared by the same kernel
             check(lib.fgs_adam_upd_zero_grad(ptr(self.sdf), ptr(self.g_sdf), ptr(m), ptr(v), self.sdf.numel(), step,
@@ -554,12 +565,17 @@ class FineStepEngine:
                 check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
                 check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
             self._grads_clean = True
-            n = 2 * MLP_LAYERS
-            lrs = [t["lrate_rgbnet"]] * 4 + [t["lrate_refnet"]] * 4
-            lrs = (C.c_float * n)(*[x * lr_scale for x in lrs + lrs])
-            steps = (C.c_int * n)(*([step] * n))
-            mt = self._mt
-            check(lib.fgs_adam_upd_multi(n, mt["p"], mt["g"], mt["m"], mt["v"], mt["n"], steps, lrs, b1, b2, eps, st))
+            if parts == "all":
+                self._adam_mlp(step, lr_scale, b1, b2, eps, st)
+
+    def _adam_mlp(self, step, lr_scale, b1, b2, eps, st):
+        t = self.train_cfg
+        n = 2 * MLP_LAYERS
+        lrs = [t["lrate_rgbnet"]] * 4 + [t["lrate_refnet"]] * 4
+        lrs = (C.c_float * n)(*[x * lr_scale for x in lrs + lrs])
+        steps = (C.c_int * n)(*([step] * n))
+        mt = self._mt
+        check(lib.fgs_adam_upd_multi(n, mt["p"], mt["g"], mt["m"], mt["v"], mt["n"], steps, lrs, b1, b2, eps, st))
 
     def all_reduce_grads(self):
         """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink).
@@ -627,17 +643,33 @@ class FineStepEngine:
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
         t = self.train_cfg
         tv = self.is_tv_step(global_step) and t["weight_tv_density"] > 0
+        self._ensure_adam()
+        if tv and self.tv_scratch is None:
+            self.tv_scratch = torch.empty(6 * self.X * self.Y * self.Z, dtype=torch.float32, device=self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
+            check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve if self.world_size > 1 else 0))
+        main = torch.cuda.current_stream(self.device)
         if self.world_size == 1:
-            self.loss_backward(target, n_rays_global, has_last_ray)
-            if tv and t["smooth_grad_tv"] > 0:
-                self.smooth_grad_tv_add_grad()
+            # the grid gradients are final after phase 1: their regularisers and optimiser kernels (HBM-bound, small
+            # CTAs) run on the side stream next to the tensor-core-bound weight-gradient kernel
+            self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
+            self._ev_grids.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_grids)
+                if tv and t["smooth_grad_tv"] > 0:
+                    self.smooth_grad_tv_add_grad()
+                if tv and t["sdf_tv"] > 0:
+                    self.sdf_tv_add_grad(global_step, n_rays_global)
+                self.optimizer_step(parts="grids")
+                self._ev_exch.record(self._side)
+            self.backward_weights()
+            self.optimizer_step(parts="mlp")
+            main.wait_event(self._ev_exch)
+            return
         else:
             from .dist import all_reduce_sum_
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-                self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
-                check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve))
-            main = torch.cuda.current_stream(self.device)
             self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
             if tv and t["smooth_grad_tv"] > 0 and self.rank == 0:
                 self.smooth_grad_tv_add_grad()                             # a pure function of the params:
