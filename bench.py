@@ -247,6 +247,8 @@ def run_ours(args):
     if rank == 0:
         rows = _lib.prof_end()
         for name, t in rows:
+            if name == "fork":          # stream-segment marker, not a launch (its interval spans the previous step)
+                continue
             a = prof.setdefault(name, [0.0, 0])
             a[0] += t; a[1] += 1
     torch.cuda.synchronize()

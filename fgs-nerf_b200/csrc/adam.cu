@@ -182,6 +182,7 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
   }
   a.blk_start[n_tensors] = blk;
   if (blk == 0) return 0;
+  FGS_PREFER_MAX_SHARED(adam_multi_kernel);
   adam_multi_kernel<<<blk, kBlock, 0, (cudaStream_t)stream>>>(a);
   return fgs::check_launch("adam_upd_multi", (cudaStream_t)stream);
 }
@@ -229,17 +230,19 @@ adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, floa
 // touched-brick list in ASCENDING brick order (deterministic, identical on every rank that holds the
 // same flags): single CTA, each thread counts a contiguous run of flags, block scan, ordered write;
 // the flags are cleared on the way.  list[0] = count, list[1..] = brick ids.
-__global__ void __launch_bounds__(1024)
+constexpr int kListThreads = 256;
+// (256 threads, <= 40 registers: the CTA fits next to a resident tensor-core CTA when the optimiser runs on a side stream)
+__global__ void __launch_bounds__(kListThreads)
 brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ list) {
-  __shared__ int s_warp[32];
+  __shared__ int s_warp[kListThreads / 32];
   __shared__ int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5;
   const bool vec = (((uintptr_t)flags) & 15) == 0;
-  // passes of 1024 threads x 64 flags; a thread's run is read as four 16-byte words, all loads in flight
+  // passes of 256 threads x 64 flags; a thread's run is read as four 16-byte words, all loads in flight
   // (the byte-by-byte dependent loop took 23 us for 64 K flags)
-  for (int base = 0; base < n_bricks; base += 1024 * 64) {
+  for (int base = 0; base < n_bricks; base += kListThreads * 64) {
     const int beg = base + threadIdx.x * 64;
     uint32_t m[16];                                   // bit 8 j + 7 of word i set <=> flag 4 i + j nonzero
     const bool full = vec && beg + 64 <= n_bricks;
@@ -273,9 +276,9 @@ brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restri
     if (lane_id() == 31) s_warp[w] = incl;
     __syncthreads();
     if (w == 0) {
-      const int v = s_warp[lane_id()];
+      const int v = lane_id() < kListThreads / 32 ? s_warp[lane_id()] : 0;
       const int sc = warp_incl_scan(v);
-      s_warp[lane_id()] = sc - v;
+      if (lane_id() < kListThreads / 32) s_warp[lane_id()] = sc - v;
       __syncwarp();
       if (lane_id() == 31) s_carry = carry + sc;
     }
@@ -336,12 +339,14 @@ brick_copy_kernel(float* __restrict__ grid, float* __restrict__ compact, const i
 // grid layout [X][Y][Z][12] (channels-last); brick b = ((x>>2)*nbY + (y>>2))*nbZ + (z>>2).
 // One warp per listed brick: 16 (x,y) rows of 4 z-voxels x 12 channels = 192 float4 = 6 per lane,
 // all gradient loads issued before any dependent work.
-__global__ void __launch_bounds__(kBlock)
+constexpr int kBrickBlock = 128;
+// (128 threads x ~98 registers: small enough to be resident next to a tensor-core CTA on a side stream)
+__global__ void __launch_bounds__(kBrickBlock)
 adam_bricks_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ exp_avg,
                    float* __restrict__ exp_avg_sq, const int* __restrict__ list, int X, int Y, int Z, AdamConst c) {
   const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
   const int lane = lane_id();
-  const int wpb = kBlock / 32;
+  const int wpb = kBrickBlock / 32;
   const int count = list[0];
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < count; e += gridDim.x * wpb) {
@@ -387,6 +392,7 @@ int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp
               "fgs_adam_upd_zero_grad needs 16-byte aligned tensors");
   if (n == 0) return 0;
   AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
+  FGS_PREFER_MAX_SHARED(adam_dense_zero_kernel);
   adam_dense_zero_kernel<<<fgs::stream_grid((n + 3) / 4, kBlock, 8), kBlock, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, n, c);
   return fgs::check_launch("adam_dense_zero", (cudaStream_t)stream);
@@ -401,7 +407,8 @@ int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_lis
   FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "bad grid size");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_bricks = ((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
-  brick_list_kernel<<<1, 1024, 0, st>>>(brick_flags, n_bricks, brick_list);
+  FGS_PREFER_MAX_SHARED(brick_list_kernel);
+  brick_list_kernel<<<1, kListThreads, 0, st>>>(brick_flags, n_bricks, brick_list);
   return fgs::check_launch("brick_list", st);
 }
 
@@ -412,6 +419,8 @@ int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int m
   if (max_bricks <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid_dim = fgs::stream_grid(max_bricks, kBlock / 32, 8);
+  FGS_PREFER_MAX_SHARED(brick_copy_kernel<true>);
+  FGS_PREFER_MAX_SHARED(brick_copy_kernel<false>);
   if (pack) brick_copy_kernel<true><<<grid_dim, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
   else brick_copy_kernel<false><<<grid_dim, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
   return fgs::check_launch(pack ? "brick_pack" : "brick_unpack", st);
@@ -423,7 +432,8 @@ int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_av
   FGS_REQUIRE(channels == 12, "brick Adam is specialised for the 12-channel channels-last k0 grid");
   FGS_REQUIRE(X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick Adam needs Z % 4 == 0");
   AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
-  adam_bricks_kernel<<<FGS_NUM_SMS * 8, kBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
+  FGS_PREFER_MAX_SHARED(adam_bricks_kernel);
+  adam_bricks_kernel<<<FGS_NUM_SMS * 16, kBrickBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
                                                                           brick_list, X, Y, Z, c);
   return fgs::check_launch("adam_bricks", (cudaStream_t)stream);
 }

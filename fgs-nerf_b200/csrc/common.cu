@@ -37,6 +37,7 @@ bool g_prof_on = false;
 int g_prof_n = 0, g_prof_created = 0;
 cudaEvent_t g_ev[kMaxEv];
 const char* g_ev_name[kMaxEv];
+cudaStream_t g_ev_stream[kMaxEv];
 }  // namespace
 
 void prof_mark(const char* what, cudaStream_t st) {
@@ -47,6 +48,7 @@ void prof_mark(const char* what, cudaStream_t st) {
   }
   cudaEventRecord(g_ev[g_prof_n], st);
   g_ev_name[g_prof_n] = what;
+  g_ev_stream[g_prof_n] = st;
   ++g_prof_n;
 }
 }  // namespace fgs
@@ -70,13 +72,18 @@ int fgs_prof_end(void) {
 int fgs_prof_get(int i, const char** name, float* ms) {
   if (i < 0 || i + 1 >= fgs::g_prof_n) return FGS_E_BADARG;
   *name = fgs::g_ev_name[i + 1];
-  return fgs::check_cuda(cudaEventElapsedTime(ms, fgs::g_ev[i], fgs::g_ev[i + 1]), "prof elapsed");
+  // duration of launch i + 1 = time since the previous event on the SAME stream (callers that fork work onto
+  // another stream mark the fork / join points, fgs_prof_mark(4 | 5), so every stream segment starts with one)
+  int prev = i;
+  for (int j = i; j >= 0; --j)
+    if (fgs::g_ev_stream[j] == fgs::g_ev_stream[i + 1]) { prev = j; break; }
+  return fgs::check_cuda(cudaEventElapsedTime(ms, fgs::g_ev[prev], fgs::g_ev[i + 1]), "prof elapsed");
 }
 
 // mark a non-library launch (e.g. an NCCL collective enqueued by the host) in the timing stream
 int fgs_prof_mark(int what, fgs_stream_t stream) {
-  static const char* names[] = {"other", "allreduce", "h2d copy", "d2h copy"};
-  fgs::prof_mark(names[(what >= 0 && what < 4) ? what : 0], (cudaStream_t)stream);
+  static const char* names[] = {"other", "allreduce", "h2d copy", "d2h copy", "fork", "join"};
+  fgs::prof_mark(names[(what >= 0 && what < 6) ? what : 0], (cudaStream_t)stream);
   return 0;
 }
 

@@ -38,6 +38,20 @@ inline int check_launch(const char* what, cudaStream_t st) {
   return rc;
 }
 
+// Kernels that may run on a side stream NEXT TO the persistent tensor-core CTAs (which carve ~214 KB of the SM's
+// 256 KB out as shared memory) ask for the same carve-out: an SM cannot change its L1 / shared split while CTAs are
+// resident, so a kernel with the default preference waited until the tensor-core kernel had drained (a 12 us
+// brick-list scan took 137 us).  Streaming kernels lose nothing with a small L1.
+template <typename Kern>
+inline void prefer_max_shared(Kern kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define FGS_PREFER_MAX_SHARED(kern)                \
+  do {                                             \
+    static bool done_ = false;                     \
+    if (!done_) { fgs::prefer_max_shared(kern); done_ = true; } \
+  } while (0)
+
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "fgs_b200: %s: %s", what, cudaGetErrorString(e));

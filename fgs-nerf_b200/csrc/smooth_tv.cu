@@ -128,6 +128,9 @@ extern "C" int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const
   float* G = scratch;
   float* E = scratch + 3 * V;
   const int grid = fgs::stream_grid(V, kBlock, 8);
+  FGS_PREFER_MAX_SHARED(tv_grad_grid_kernel);
+  FGS_PREFER_MAX_SHARED(tv_err_kernel);
+  FGS_PREFER_MAX_SHARED(tv_scatter_kernel);
   tv_grad_grid_kernel<<<grid, kBlock, 0, st>>>(sdf, G, X, Y, Z, voxel_size);
   int rc = fgs::check_launch("smooth_tv grad grid", st);
   if (rc) return rc;

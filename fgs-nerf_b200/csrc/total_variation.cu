@@ -148,6 +148,8 @@ extern "C" int fgs_total_variation_add_grad(const float* param, float* grad, con
     const int grid = fgs::stream_grid(n4, kBlock, 8);
     // a [C,X,Y,Z] tensor is C stacked [X,Y,Z] volumes: fold C into the i decode via X only
     // (i = (q / (Z4*Y)) % X is per-channel correct because the channel index is the next digit)
+    FGS_PREFER_MAX_SHARED(tv_kernel_v4<true>);
+    FGS_PREFER_MAX_SHARED(tv_kernel_v4<false>);
     if (dense_mode)
       tv_kernel_v4<true><<<grid, kBlock, 0, st>>>(param, grad, wz, wy, wz, sz_i, sz_j, sz_k, n4);
     else

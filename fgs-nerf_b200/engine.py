@@ -647,7 +647,7 @@ class FineStepEngine:
         if tv and self.tv_scratch is None:
             self.tv_scratch = torch.empty(6 * self.X * self.Y * self.Z, dtype=torch.float32, device=self.device)
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # its small CTAs go first when an SM has room
             self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
             check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve if self.world_size > 1 else 0))
         main = torch.cuda.current_stream(self.device)
@@ -658,6 +658,7 @@ class FineStepEngine:
             self._ev_grids.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_grids)
+                lib.fgs_prof_mark(4, stream())
                 if tv and t["smooth_grad_tv"] > 0:
                     self.smooth_grad_tv_add_grad()
                 if tv and t["sdf_tv"] > 0:
@@ -667,6 +668,7 @@ class FineStepEngine:
             self.backward_weights()
             self.optimizer_step(parts="mlp")
             main.wait_event(self._ev_exch)
+            lib.fgs_prof_mark(5, stream())
             return
         else:
             from .dist import all_reduce_sum_
@@ -676,13 +678,16 @@ class FineStepEngine:
             self._ev_grids.record(main)                                    # added once, not per rank
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_grids)
+                lib.fgs_prof_mark(4, stream())
                 self._exchange_grids_begin()
             self.backward_weights()                                        # main stream, overlaps the exchange
             with torch.cuda.stream(self._side):
                 self._exchange_grids_finish()
                 self._ev_exch.record(self._side)
             all_reduce_sum_([self.g_mlp_flat])
+            lib.fgs_prof_mark(1, stream())
             main.wait_event(self._ev_exch)
+            lib.fgs_prof_mark(5, stream())
         if tv and t["sdf_tv"] > 0:
             self.sdf_tv_add_grad(global_step, n_rays_global)
         self.optimizer_step()
