@@ -524,3 +524,81 @@ def test_chunked_render_matches_oracle_forward(cuda):
     for k in ("rgb_marched", "sigmoid_rgb", "depth", "normal_marched", "alphainv_cum"):
         _close(got[k], want[k], "render " + k)
     assert got["rgb_marched"].shape == (R_total, 3)
+
+
+def _one_step(cuda, setup=None, phase_split=False, rays=None, N=192, G=48):
+    """forward + loss + backward of a small scene; returns the tensors a step produces."""
+    from fgs_nerf_b200 import engine, scene
+    sc = scene.make_scene(G=G, mask_G=40)
+    ro, rd, vd, tgt = rays if rays is not None else [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
+    if setup:
+        setup(engine)
+    eng = engine.FineStepEngine(sc, ro.shape[0], cuda)
+    eng.forward(ro, rd, vd, 5000)
+    eng.zero_grad()
+    if phase_split:
+        eng.loss_backward(tgt, phase=1)
+        torch.cuda.synchronize()
+        grids = (eng.g_sdf.clone(), eng.g_k0.clone())       # final after phase 1
+        eng.backward_weights()
+        torch.cuda.synchronize()
+        assert torch.equal(grids[0], eng.g_sdf) and torch.equal(grids[1], eng.g_k0), "phase 2 touched the grid gradients"
+    else:
+        eng.loss_backward(tgt)
+    torch.cuda.synchronize()
+    out = dict(rgb=eng.ws["rgb_marched"].clone(), g_sdf=eng.g_sdf.clone(), g_k0=eng.g_k0.clone(),
+               g_mlp=eng.g_mlp_flat.clone(), loss=eng.ws["loss"].clone(), cnt=eng.counters())
+    return out
+
+
+def test_fused_mlp_chain_equals_per_layer_launches(cuda):
+    """mlp_chain_kernel (8 forward layers / 9 backward-data steps per launch) + the batched weight-gradient
+    kernel against one launch per layer: same kernels' arithmetic, so the step must agree to rounding of the
+    atomics' order (bar 1e-4; observed ~1e-6)."""
+    from fgs_nerf_b200 import engine
+    try:
+        a = _one_step(cuda, lambda e: e.set_mlp_fusion(True))
+        b = _one_step(cuda, lambda e: e.set_mlp_fusion(False))
+    finally:
+        engine.set_mlp_fusion(True)
+    assert a["cnt"] == b["cnt"]
+    assert torch.equal(a["rgb"], b["rgb"]), "the fused forward chain runs the same MMAs in the same order"
+    for k in ("g_sdf", "g_k0", "g_mlp"):
+        assert _rel(a[k], b[k]) < 2e-5, (k, _rel(a[k], b[k]))
+
+
+def test_backward_in_two_phases_equals_one_call(cuda):
+    """fgs_fine_backward_phase: 1 (grid gradients final) then 2 (weight gradients) == phase 0; phase 2 must
+    not touch g_sdf / g_k0 (the data-parallel step exchanges them while it runs)."""
+    a = _one_step(cuda, phase_split=False)
+    b = _one_step(cuda, phase_split=True)
+    for k in ("g_sdf", "g_k0", "g_mlp"):
+        assert _rel(a[k], b[k]) < 2e-5, (k, _rel(a[k], b[k]))
+
+
+def test_weight_gradient_kernel_with_reserved_sms(cuda):
+    """fgs_set_dw_sm_reserve only changes how the (tile, slab) space is cut across CTAs."""
+    from fgs_nerf_b200._lib import lib, check
+    import ctypes
+    lib.fgs_set_dw_sm_reserve.argtypes = [ctypes.c_int]
+    try:
+        a = _one_step(cuda)
+        check(lib.fgs_set_dw_sm_reserve(16))
+        b = _one_step(cuda)
+    finally:
+        check(lib.fgs_set_dw_sm_reserve(0))
+    assert _rel(a["g_mlp"], b["g_mlp"]) < 2e-6
+
+
+def test_batch_that_misses_the_volume(cuda):
+    """Every ray points away from the bounding box: no samples anywhere.  All kernels must cope with
+    M1 = M2 = 0 (persistent MLP kernels exit before touching TMEM), the image is the background colour
+    and every gradient is exactly zero."""
+    from fgs_nerf_b200 import scene
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=64, H=100, W=100, n_views=8)]
+    rays = (ro, (-rd).contiguous(), (-vd).contiguous(), tgt)
+    out = _one_step(cuda, rays=rays)
+    assert out["cnt"]["M1"] == 0 and out["cnt"]["M2"] == 0
+    assert bool((out["rgb"] == 1.0).all())
+    assert int(out["g_sdf"].count_nonzero()) == 0 and int(out["g_k0"].count_nonzero()) == 0
+    assert int(out["g_mlp"].count_nonzero()) == 0
