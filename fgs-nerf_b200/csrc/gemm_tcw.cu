@@ -1003,6 +1003,355 @@ mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ Ch
   cta_teardown(tmem_d, warp);
 }
 
+// ---- the same chain on CTA PAIRS (tcgen05 cta_group::2): M = 256 per MMA, each SM holds half of the weights -----
+// In the single-CTA chain every SM streams the whole 64 KB weight slab per 32 k and its tensor core reads 12 KB
+// of operands per MMA through one shared-memory port (measured: 178-200 cycles per M128 N256 K8 MMA against 138
+// when less is read, and ~600 cycles per slab waiting for the weight TMA with room for only two stages).  A CTA
+// pair multiplies a 256-row tile with ONE MMA stream issued by the leader CTA: each CTA contributes its own 128
+// activation rows (A) and HALF of the weight rows (B: 128 of 256), so per SM the weight traffic, the weight
+// footprint (32 KB per stage -> three stages fit) and the operand reads per MMA (8 KB) all drop.
+// Cross-CTA signalling: tcgen05.commit multicasts `free` / `r_full` to both CTAs; the follower's producers and
+// consumers arrive on the LEADER's a_full / r_empty barriers (mapa + mbarrier.arrive.release.cluster), and its half of
+// the weight slab completes its bytes directly on the leader's b_full (cp.async.bulk.tensor .cta_group::2).
+// Measured (tools/chain_phase_probe.py, M2 = 42.5 K): the pair issues an M256 N256 K8 MMA every ~108 cycles (178 for
+// the single-CTA M128 MMA), b_full waits drop from 620 to 210 cycles per slab; what remains is the follower's
+// a_full round trip (commit multicast -> fill -> remote arrive, ~550 cycles per slab with three stages).  Everything else (producers, epilogue, per-tile completion barriers) is
+// per CTA and identical to mlp_chain_kernel.
+constexpr int kStages2 = 3;
+constexpr uint32_t kBHalf2 = 128 * BK * 4;                       // 16 KB: one plane of this CTA's half of a slab
+constexpr uint32_t kStage2 = 2 * kATile + 2 * kBHalf2;           // A_hi, A_lo, B_hi, B_lo = 64 KB
+static_assert(kStages2 * kStage2 == kStagingOff, "staging / barrier offsets are shared");
+constexpr uint32_t kSmemBytesChain2 = kCDoneOff + 8 * kChainMaxTiles;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+  if (!done) __trap();
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_commit(uint32_t bar) {    // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
+mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const Bars B = make_bars(smem);
+  const uint32_t cdone0 = smem + kCDoneOff;
+
+  int M = a.M;
+  if (a.rows_dev) M = min(M, *a.rows_dev);
+  const int n_pair_tiles = (M + 2 * BM - 1) / (2 * BM);        // 256-row tiles
+  const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+  if (pair >= n_pair_tiles) return;                            // both CTAs of the pair leave together
+  const uint32_t rank = cluster_ctarank();                     // 0 = leader (issues the MMAs)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- set-up: barriers (the leader's a_full / b_full / r_empty also count the follower's arrivals), TMEM ----
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
+  if (tid == 0) {
+    for (int i = 0; i < kChainMaxTiles; ++i) mbar_init(cdone0 + 8 * i, 8);
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(B.free0 + 8 * i, 1);                                     // one multicast commit
+      mbar_init(B.bfull0 + 8 * i, 1);                                    // the leader's expect_tx arrive; bytes from both CTAs
+      mbar_init(B.afull0 + 8 * i, 2 * (kProducersF / 32));               // producer warps of both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(B.rfull0 + 8 * i, 1);
+      mbar_init(B.rempty0 + 8 * i, 2 * (kConsumers / 32));               // consumer warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();                                          // barriers of both CTAs exist before anyone signals
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (n_pair_tiles - 1 - pair) / n_pairs + 1;
+  const int n_items = a.n_steps * my_tiles;                    // item w: step w / my_tiles, local tile w % my_tiles
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
+  // leader-side addresses of the barriers the follower signals
+  const uint32_t l_afull0 = map_to_cta(B.afull0, 0), l_bfull0 = map_to_cta(B.bfull0, 0), l_rempty0 = map_to_cta(B.rempty0, 0);
+  auto tile_row0 = [&](int lt) { return ((pair + lt * n_pairs) * 2 + (int)rank) * BM; };   // this CTA's 128 rows
+
+  if (warp >= kIssuerWarpF) {
+    if (warp == kIssuerWarpF && lane == 0) {
+      // both CTAs: TMA of THIS CTA's half of the weight rows; leader: also every MMA
+      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
+      struct Cursor { int w, step, kt, n_slabs; };
+      auto cur_next = [&](Cursor& c) {
+        if (++c.kt == c.n_slabs) {
+          c.kt = 0;
+          ++c.w;
+          if (c.w < n_items) { c.step = c.w / my_tiles; c.n_slabs = (a.s[c.step].K + BK - 1) / BK; }
+        }
+      };
+      auto issue_b = [&](const Cursor& c, uint32_t gs) {
+        const ChainStep& S = a.s[c.step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const uint32_t st = gs % kStages2;
+        const uint32_t b_hi = smem + st * kStage2 + 2 * kATile, b_lo = b_hi + kBHalf2;
+        // both halves complete their bytes on the LEADER's b_full (cta_group::2 form of the bulk tensor copy: the
+        // mbarrier may live in the peer CTA), which the leader arms for the whole 64 KB
+        if (rank == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(B.bfull0 + 8 * st), "r"(4 * kBHalf2) : "memory");
+        const uint32_t bar = l_bfull0 + 8 * st;
+        const int row0 = S.n0 + (int)rank * (BN >> 1);          // B is split along N between the two CTAs
+        tma2_load_2d(b_hi, &maps.hi[c.step], bar, c.kt * BK, row0);
+        tma2_load_2d(b_lo, &maps.lo[c.step], bar, c.kt * BK, row0);
+      };
+      Cursor lc{0, 0, 0, (a.s[0].K + BK - 1) / BK};
+      uint32_t lg = 0;
+      constexpr uint32_t kPf = kStages2 - 1;                   // weight slabs in flight ahead of the MMAs
+      for (; lg < kPf && lc.w < n_items; ++lg) { issue_b(lc, lg); cur_next(lc); }
+      uint32_t g = 0;
+      for (int w = 0; w < n_items; ++w) {
+        const int step = w / my_tiles;
+        const ChainStep& S = a.s[step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const int n_slabs = (S.K + BK - 1) / BK;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)((2 * BM) >> 4) << 24);          // M = 256 across the pair
+        const uint32_t rg = (uint32_t)w & 1;
+        for (int kt = 0; kt < n_slabs; ++kt, ++g) {
+          const uint32_t st = g % kStages2;
+          const uint32_t par = (g / kStages2) & 1;
+          if (rank == 0) {
+            if (dbg_cta) t0 = clock64();
+            mbar_wait_cluster(B.afull0 + 8 * st, par);
+            if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+            mbar_wait_cluster(B.bfull0 + 8 * st, par);
+            if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
+            if (kt == 0 && w >= 2) mbar_wait_cluster(B.rempty0 + 8 * rg, (((uint32_t)w >> 1) - 1) & 1);
+            if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t stage_base = smem + st * kStage2, d = tmem_d + rg * TNF;
+            const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+            const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBHalf2;
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+              const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+              mma2_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);
+              mma2_tf32(d, dah, dbl, idesc, 1);
+              mma2_tf32(d, dah, dbh, idesc, 1);
+            }
+            mma2_commit(B.free0 + 8 * st);
+            if (kt == n_slabs - 1) mma2_commit(B.rfull0 + 8 * rg);
+          }
+          // next weight slab of this CTA's half (its stage was last read by slab lg - kStages2)
+          if (lc.w < n_items) {
+            if (dbg_cta) t0 = clock64();
+            if (lg >= (uint32_t)kStages2) mbar_wait(B.free0 + 8 * (lg % kStages2), ((lg / kStages2) - 1) & 1);
+            if (dbg_cta) t_f += clock64() - t0;
+            issue_b(lc, lg);
+            cur_next(lc);
+            ++lg;
+          }
+        }
+      }
+      if (dbg_cta) {
+        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
+      }
+    }
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers: this CTA's 128 activation rows -> hi / lo TF32 tiles =================
+    const int pw = warp - kConsumers / 32;
+    const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
+    const bool dbg_on = dbg_cta && tid == kConsumers;
+    long long t_wait = 0, t_work = 0, t_dep = 0, t0 = 0;
+    uint32_t g = 0;
+    for (int w = 0; w < n_items; ++w) {
+      const int step = w / my_tiles, lt = w - step * my_tiles;
+      const ChainStep& S = a.s[step];
+      const int K = S.K, lda = S.lda;
+      const int n_slabs = (K + BK - 1) / BK;
+      const int row = tile_row0(lt) + prow;
+      const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
+      const int mleft = M - row;
+      if (step > 0) {
+        if (dbg_on) t0 = clock64();
+        mbar_wait_relaxed(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (dbg_on) t_dep += clock64() - t0;
+      }
+      auto load_a = [&](float4 (&v)[4], int kt) {
+        if (kt >= n_slabs) return;
+        const int k = kt * BK + 4 * pc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto produce = [&](float4 (&v)[4], int kt) {
+        const uint32_t st = g % kStages2;
+        const uint32_t stage_base = smem + st * kStage2;
+        if (dbg_on) t0 = clock64();
+        if (g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
+        if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = prow + 4 * i;
+          const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+          split_store(stage_base + off, stage_base + kATile + off, v[i]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {                                          // the LEADER's barrier
+          if (rank == 0) mbar_arrive(B.afull0 + 8 * st);
+          else mbar_arrive_cluster(l_afull0 + 8 * st);
+        }
+        // (the prefetch is issued AFTER the arrive: a cluster-scope release waits for every load in flight --
+        // with the loads in front of it each slab iteration took 2.2 K cycles instead of 0.8 K)
+        load_a(v, kt + 2);
+        ++g;
+        if (dbg_on) t_work += clock64() - t0;
+      };
+      float4 v0[4], v1[4];
+      load_a(v0, 0);
+      load_a(v1, 1);
+      for (int kt = 0; kt < n_slabs; kt += 2) {
+        produce(v0, kt);
+        if (kt + 1 < n_slabs) produce(v1, kt + 1);
+      }
+    }
+    if (dbg_on) { a.dbg[2] = t_dep; a.dbg[3] = t_wait; a.dbg[4] = t_work; }
+  } else {
+    // ================= consumers: epilogue of this CTA's 128 rows of item w =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * (TNF / 2);
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
+    long long t_main = 0, t_epi = 0, t0 = 0;
+    const bool dbg_on = dbg_cta && tid == 0;
+    for (int w = 0; w < n_items; ++w) {
+      const int step = w / my_tiles, lt = w - step * my_tiles;
+      const ChainStep& S = a.s[step];
+      const int n0 = S.n0, N = S.N;
+      const int BN = min(TNF, (N - n0 + 15) & ~15);
+      const uint32_t rg = (uint32_t)w & 1;
+      const uint32_t bias_s = smem + kBiasOff + rg * (TNF * 4);
+      reinterpret_cast<float*>(smem_raw + kBiasOff)[rg * TNF + tid] = (S.bias && n0 + tid < N) ? S.bias[n0 + tid] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (dbg_on) t0 = clock64();
+      mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+      const int m0 = tile_row0(lt);
+      const int mr0 = m0 + quarter * 32;
+      const int m = mr0 + lane;
+#pragma unroll 1
+      for (int q = 0; q < TNF / 2 / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+          float v[32];
+          {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
+            tmem_ld16(tmem_row + rg * TNF + 32 * q + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
+          }
+          const int word = (n0 + c0) >> 5;
+          uint32_t in_bits = 0xffffffffu, out_bits = 0;
+          if (S.bits_in && m < M) in_bits = S.bits_in[(size_t)m * 8 + word];
+          const uint32_t baddr = bias_s + 4 * c0;
+          const bool hb = S.bias != nullptr;
+          if (S.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
+          else if (S.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
+          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
+          if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + word] = out_bits;
+          if (S.c_tma && mr0 + 32 <= M) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
+                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&maps.c[step], stg, n0 + c0, mr0);
+          } else if (m < M) {
+            float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) cp[j] = v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {                                          // the leader may overwrite the region in BOTH CTAs
+        if (rank == 0) mbar_arrive(B.rempty0 + 8 * rg);
+        else mbar_arrive_cluster(l_rempty0 + 8 * rg);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        mbar_arrive(cdone0 + 8 * lt);
+      }
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
+  }
+  // ---- teardown: nobody may leave (or free TMEM) while the partner can still signal it or multiply into it ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
 // ---- backward-weight GEMMs:  C_l[M_l,N_l] += A_l[K,M_l]^T B_l[K,N_l]  (dW_l = dZ_l^T X_l) for ALL layers in one launch --
 // The reduction index is the SAMPLE dimension, the slow dimension of both row-major operands, i.e. both tiles
 // are MN-major.  kind::tf32 reads MN-major tiles in the SWIZZLE_128B_BASE32B layout (tools/umma_probe.cu):
@@ -1212,6 +1561,7 @@ __global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_cons
 
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
+int g_chain_pairs = 1;     // 1: mlp_chain2_kernel (CTA pairs, tcgen05 cta_group::2)
 int g_dw_sm_reserve = 0;
 int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
@@ -1324,8 +1674,10 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   int grid = FGS_NUM_SMS;
   if (grid > n_tiles) grid = n_tiles;
   if (fgs::cdiv(n_tiles, grid) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
-  static bool configured = false;
-  int rc = configure_once(mlp_chain_kernel, configured, "mlp_chain smem attribute", kSmemBytesChain);
+  static bool configured = false, configured2 = false;
+  const bool pairs = g_chain_pairs != 0;
+  int rc = pairs ? configure_once(mlp_chain2_kernel, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2)
+                 : configure_once(mlp_chain_kernel, configured, "mlp_chain smem attribute", kSmemBytesChain);
   if (rc) return rc;
   ChainArgs a;
   ChainMaps maps;
@@ -1347,7 +1699,16 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   }
   for (int i = n_steps; i < kChainMaxSteps; ++i) { maps.hi[i] = maps.hi[0]; maps.lo[i] = maps.lo[0]; maps.c[i] = maps.c[0]; }
   a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = M;
-  mlp_chain_kernel<<<grid, kThreadsF, kSmemBytesChain, st>>>(a, maps);
+  if (pairs) {
+    // CTA pairs (static cluster size 2): the grid is a whole number of pairs
+    const int n_pair_tiles = fgs::cdiv(M, 2 * BM);
+    int pairs_n = FGS_NUM_SMS / 2;
+    if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
+    if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
+    mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+  } else {
+    mlp_chain_kernel<<<grid, kThreadsF, kSmemBytesChain, st>>>(a, maps);
+  }
   return fgs::check_launch("mlp_chain", st);
 }
 
@@ -1455,6 +1816,12 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
   g_dbg_dw = buf ? (long long*)buf + 10 : nullptr;    // slots 10..19: the weight-gradient kernel
+  return 0;
+}
+
+// MLP chain on CTA pairs (cta_group::2) instead of single CTAs.
+extern "C" int fgs_set_mlp_chain_pairs(int on) {
+  g_chain_pairs = on ? 1 : 0;
   return 0;
 }
 

@@ -97,6 +97,7 @@ _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
 _lib.declare("fgs_set_gemm_tmem_accumulate", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_fusion", C.c_int, [C.c_int])
+_lib.declare("fgs_set_mlp_chain_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
@@ -111,6 +112,11 @@ def set_gemm_tmem_accumulate(on=True):
     """Pre-split tensor-core GEMMs: whole-K TMEM accumulation (fast, default) or 32-k chunks + fp32 register
     accumulators (the most accurate mode)."""
     check(lib.fgs_set_gemm_tmem_accumulate(int(bool(on))))
+
+
+def set_mlp_chain_pairs(on=True):
+    """MLP chains on CTA pairs (tcgen05 cta_group::2) or on single CTAs."""
+    check(lib.fgs_set_mlp_chain_pairs(int(bool(on))))
 
 
 def set_mlp_fusion(on=True):

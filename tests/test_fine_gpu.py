@@ -602,3 +602,19 @@ def test_batch_that_misses_the_volume(cuda):
     assert bool((out["rgb"] == 1.0).all())
     assert int(out["g_sdf"].count_nonzero()) == 0 and int(out["g_k0"].count_nonzero()) == 0
     assert int(out["g_mlp"].count_nonzero()) == 0
+
+
+def test_mlp_chain_on_cta_pairs(cuda):
+    """mlp_chain2_kernel (tcgen05 cta_group::2: 256-row tiles across two SMs, each holding half of the weight rows)
+    against the single-CTA chain: the same products accumulate in the same order per output element, so the
+    forward must be identical and the gradients agree to the order of the atomics."""
+    from fgs_nerf_b200 import engine
+    try:
+        a = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(False), N=512)
+        b = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(True), N=512)
+    finally:
+        engine.set_mlp_chain_pairs(False)
+    assert a["cnt"] == b["cnt"] and a["cnt"]["M2"] > 256
+    assert torch.equal(a["rgb"], b["rgb"])
+    for k in ("g_sdf", "g_k0", "g_mlp"):
+        assert _rel(a[k], b[k]) < 2e-5, (k, _rel(a[k], b[k]))
