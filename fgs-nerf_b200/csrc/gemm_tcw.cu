@@ -192,9 +192,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Consumer side of the accumulation: chunk c (one 32-k slab = 12 MMAs) has been committed into TMEM region
 // c % kRegions; add this warp's 64 columns of it into the thread's fp32 register accumulators (its row) and
 // hand the region back.  tmem_row = base + (lane quarter << 16) + column half.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr);
+// rempty_cluster0 != 0: r_empty lives in the leader CTA of a pair (shared::cluster address), arrive there
 template <bool PAIRED>
 __device__ __forceinline__ void drain_chunk(float (&acc)[kAcc], uint32_t tmem_row, int col_half, uint32_t c, int BN,
-                                            uint32_t rfull_bar0, uint32_t rempty_bar0) {
+                                            uint32_t rfull_bar0, uint32_t rempty_bar0, uint32_t rempty_cluster0 = 0) {
   const uint32_t rg = c % kRegions;
   mbar_wait_relaxed(rfull_bar0 + 8 * rg, (c / kRegions) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -225,7 +227,10 @@ __device__ __forceinline__ void drain_chunk(float (&acc)[kAcc], uint32_t tmem_ro
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(rempty_bar0 + 8 * rg);   // the region may be overwritten by chunk c + kRegions
+  if ((threadIdx.x & 31) == 0) {   // the region may be overwritten by chunk c + kRegions
+    if (rempty_cluster0) mbar_arrive_cluster(rempty_cluster0 + 8 * rg);
+    else mbar_arrive(rempty_bar0 + 8 * rg);
+  }
 }
 
 // TMA store of one swizzled 32-row x 128-byte block (issued by one lane; completion tracked per thread)
@@ -1559,9 +1564,240 @@ __global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_cons
   cta_teardown(tmem_d, warp);
 }
 
+// ---- the same on CTA pairs (cta_group::2): a pair owns a 256 (all out-features) x 128 output tile ----------------
+// Each CTA produces the MN-major tile of ITS 128 out-features of dZ (A) and of ITS half of the tile's input features
+// of X (B): per slab 48 KB of st.shared per SM instead of 64 KB, for twice the output, and one M256 N128 K8 MMA
+// stream issued by the leader (~92 cycles per MMA).  Signalling as in mlp_chain2_kernel.  Measured: NOT faster
+// (259 vs 237 us per step): this kernel is bound by its producers, and the follower's producers now sit on a longer
+// loop (commit multicast -> fill -> remote arrive); selectable with fgs_set_mlp_dw_pairs(1), off by default.
+struct Dw2Args {
+  DwProblem p[kDwMaxProblems];
+  unsigned char tile_prob[kDwMaxTiles], tile_n[kDwMaxTiles];
+  const int* rows_dev;
+  long long* dbg;
+  int n_tiles, K;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_dw2_kernel(const __grid_constant__ Dw2Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const Bars B = make_bars(smem);
+
+  int K = a.K;
+  if (a.rows_dev) K = min(K, *a.rows_dev);
+  const int n_slabs = (K + BK - 1) / BK;
+  const long long units = (long long)a.n_tiles * n_slabs;
+  const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+  const int u_beg = (int)(units * pair / n_pairs), u_end = (int)(units * (pair + 1) / n_pairs);
+  if (u_beg >= u_end) return;                                  // both CTAs of the pair
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(B.free0 + 8 * i, 1);
+      mbar_init(B.afull0 + 8 * i, 2 * (kProducersTn / 32));    // producer warps of both CTAs
+    }
+    for (int i = 0; i < kRegions; ++i) {
+      mbar_init(B.rfull0 + 8 * i, 1);
+      mbar_init(B.rempty0 + 8 * i, 2 * (kConsumers / 32));     // consumer warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
+  const uint32_t l_afull0 = map_to_cta(B.afull0, 0), l_rempty0 = map_to_cta(B.rempty0, 0);
+
+  if (warp >= kIssuerWarpTn) {
+    if (rank == 0 && warp == kIssuerWarpTn && lane == 0) {
+      uint32_t g = 0;
+      long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
+      if (dbg_cta) t_all = clock64();
+      for (int u = u_beg; u < u_end;) {
+        const int tile = u / n_slabs, s0 = u - tile * n_slabs;
+        const int len = min(n_slabs - s0, u_end - u);
+        const DwProblem& P = a.p[a.tile_prob[tile]];
+        const int BN = min(TN, (P.N - a.tile_n[tile] * TN + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256, MN-major
+        for (int i = 0; i < len; ++i, ++g) {
+          const uint32_t st = g % kStages;
+          if (dbg_cta) t0 = clock64();
+          mbar_wait_cluster(B.afull0 + 8 * st, (g / kStages) & 1);
+          if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
+          if (g >= (uint32_t)kRegions) mbar_wait_cluster(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
+          if (dbg_cta) t_r += clock64() - t0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t stage_base = smem + st * kStage, d = tmem_d + (g % kRegions) * TN;
+          const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
+          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = make_desc_mn(a_hi + j * 1024), dal = make_desc_mn(a_lo + j * 1024);
+            const uint64_t dbh = make_desc_mn(b_hi + j * 1024), dbl = make_desc_mn(b_lo + j * 1024);
+            mma2_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
+            mma2_tf32(d, dah, dbl, idesc, 1);
+            mma2_tf32(d, dah, dbh, idesc, 1);
+          }
+          mma2_commit(B.free0 + 8 * st);
+          mma2_commit(B.rfull0 + 8 * (g % kRegions));
+        }
+        u += len;
+      }
+      if (dbg_cta) { a.dbg[5] = t_a; a.dbg[6] = 0; a.dbg[7] = t_r; a.dbg[8] = g; a.dbg[9] = clock64() - t_all; }
+    }
+  } else if (warp >= kConsumers / 32) {
+    // ================= producers =================
+    // A: warp pw owns sample rows 4 pw .. 4 pw + 3; lane l owns out-features 128 rank + 4 l .. + 3
+    // B: this CTA's half (h = BN / 2 <= 64 input features): 16 lanes per sample row, two rows per load
+    const int pw = warp - kConsumers / 32;
+    const uint32_t a_blk = (uint32_t)(lane >> 3) * 4096u + (uint32_t)(lane & 1) * 16u;
+    const uint32_t a_c32 = (uint32_t)((lane & 7) >> 1);
+    const int bq = lane & 15, bsub = lane >> 4;                 // feature quad and row-in-pair of the B loads
+    const uint32_t b_blk = (uint32_t)(bq >> 3) * 4096u + (uint32_t)(bq & 1) * 16u;
+    const uint32_t b_c32 = (uint32_t)((bq & 7) >> 1);
+    uint32_t g = 0;
+    struct Cur { int u, tile, s; };
+    auto advance = [&](Cur& c) {
+      ++c.u; ++c.s;
+      if (c.s == n_slabs) { c.s = 0; ++c.tile; }
+    };
+    auto load_ab = [&](float4 (&va)[4], float4 (&vb)[2], const Cur& c) {
+      if (c.u >= u_end) return;
+      const DwProblem& P = a.p[a.tile_prob[c.tile]];
+      const int n0 = a.tile_n[c.tile] * TN;
+      const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;        // input features per CTA
+      const int fa = (int)rank * BM + 4 * lane, fb = n0 + (int)rank * h + 4 * bq;
+      const int k0 = c.s * BK + 4 * pw;
+      const bool in_a = fa < P.M, in_b = 4 * bq < h && fb < P.N;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + i < K && in_a) x = ldcg4(P.A + (size_t)(k0 + i) * P.lda + fa);
+        va[i] = x;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int k = k0 + 2 * i + bsub;
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K && in_b) y = ldcg4(P.B + (size_t)k * P.ldb + fb);
+        vb[i] = y;
+      }
+    };
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush_colsum = [&](int tile) {
+      const DwProblem& P = a.p[a.tile_prob[tile]];
+      if (P.colsum && a.tile_n[tile] == 0) {
+        const int f = (int)rank * BM + 4 * lane;
+        if (f < P.M && cs.x != 0.f) atomicAdd(P.colsum + f, cs.x);
+        if (f + 1 < P.M && cs.y != 0.f) atomicAdd(P.colsum + f + 1, cs.y);
+        if (f + 2 < P.M && cs.z != 0.f) atomicAdd(P.colsum + f + 2, cs.z);
+        if (f + 3 < P.M && cs.w != 0.f) atomicAdd(P.colsum + f + 3, cs.w);
+      }
+      cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto produce = [&](float4 (&va)[4], float4 (&vb)[2], const Cur& c, Cur& pf) {
+      const uint32_t st = g % kStages;
+      const uint32_t stage_base = smem + st * kStage;
+      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
+        const uint32_t r = (uint32_t)(4 * pw + i);
+        const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 3u)) * 32u);
+        split_store(stage_base + off, stage_base + kATile + off, va[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t r = (uint32_t)(4 * pw + 2 * i + bsub);
+        const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 3u)) * 32u);
+        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBTile + off, vb[i]);
+      }
+      if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(B.afull0 + 8 * st);
+        else mbar_arrive_cluster(l_afull0 + 8 * st);
+      }
+      load_ab(va, vb, pf);                               // after the (cluster-scope) arrive: see mlp_chain2_kernel
+      advance(pf);
+      ++g;
+    };
+    Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs}, pf = c;
+    float4 va0[4], vb0[2], va1[4], vb1[2];
+    load_ab(va0, vb0, pf); advance(pf);
+    load_ab(va1, vb1, pf); advance(pf);
+    while (c.u < u_end) {
+      produce(va0, vb0, c, pf); advance(c);
+      if (c.u < u_end) { produce(va1, vb1, c, pf); advance(c); }
+    }
+  } else {
+    // ================= consumers: this CTA's 128 out-features x BN =================
+    const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
+    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
+    float* stg = reinterpret_cast<float*>(smem_raw + kStagingOff + warp * kStagingWarp);
+    uint32_t g = 0;
+    const bool dbg_c = dbg_cta && tid == 0;
+    long long t_main = 0, t_epi = 0, t0c = 0;
+    for (int u = u_beg; u < u_end;) {
+      const int tile = u / n_slabs, s0 = u - tile * n_slabs;
+      const int len = min(n_slabs - s0, u_end - u);
+      const DwProblem& P = a.p[a.tile_prob[tile]];
+      const int m0 = (int)rank * BM, n0 = a.tile_n[tile] * TN;
+      const int BN = min(TN, (P.N - n0 + 15) & ~15);
+      float acc[kAcc];
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+      if (dbg_c) t0c = clock64();
+      for (int i = 0; i < len; ++i, ++g)
+        drain_chunk<false>(acc, tmem_row, col_half, g, BN, B.rfull0, B.rempty0, rank == 0 ? 0u : l_rempty0);
+      if (dbg_c) { const long long t1 = clock64(); t_main += t1 - t0c; t0c = t1; }
+#pragma unroll
+      for (int q = 0; q < kAcc / 32; ++q) {
+        const int c0 = col_half + 32 * q;
+        if (c0 < BN) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = acc[32 * q + j];
+          __syncwarp();
+          const int col = n0 + c0 + lane;
+          if (col < P.N) {
+            const int mr0 = m0 + quarter * 32;
+            float* __restrict__ cp = P.C + (size_t)mr0 * P.ldc + col;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (mr0 + r < P.M) atomicAdd(cp + (size_t)r * P.ldc, stg[r * 32 + (lane ^ r)]);
+          }
+          __syncwarp();
+        }
+      }
+      u += len;
+      if (dbg_c) t_epi += clock64() - t0c;
+    }
+    if (dbg_c) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
 int g_chain_pairs = 1;     // 1: mlp_chain2_kernel (CTA pairs, tcgen05 cta_group::2)
+int g_dw_pairs = 0;        // 1: mlp_dw2_kernel (correct, but its producers sit on the longer cross-CTA loop: 259 vs 237 us)
 int g_dw_sm_reserve = 0;
 int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
@@ -1738,6 +1974,34 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
       }
   }
   if (nt == 0) return 0;
+  if (g_dw_pairs) {
+    // CTA pairs: a pair owns all (<= 256) out-features x one 128-wide block of input features
+    bool fits = true;
+    for (int i = 0; i < n; ++i) fits = fits && probs[i].M <= 2 * BM;
+    if (fits) {
+      Dw2Args b;
+      memset(&b, 0, sizeof(b));
+      int nt2 = 0;
+      for (int i = 0; i < n; ++i) {
+        b.p[i] = a.p[i];
+        if (probs[i].M <= 0 || probs[i].N <= 0) continue;
+        for (int c = 0; c < fgs::cdiv(probs[i].N, TN); ++c) {
+          b.tile_prob[nt2] = (unsigned char)i; b.tile_n[nt2] = (unsigned char)c;
+          ++nt2;
+        }
+      }
+      b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
+      static bool configured2 = false;
+      int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytes);
+      if (rc2) return rc2;
+      const long long units2 = (long long)nt2 * fgs::cdiv(K, BK);
+      int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
+      if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
+      if (pairs_n < 1) pairs_n = 1;
+      mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytes, st>>>(b);
+      return fgs::check_launch("mlp_dw", st);
+    }
+  }
   a.n_tiles = nt; a.K = K; a.rows_dev = rows_dev; a.dbg = g_dbg_dw;
   static bool configured = false;
   int rc = configure_once(mlp_dw_kernel, configured, "mlp_dw smem attribute", kSmemBytes);
@@ -1822,6 +2086,12 @@ extern "C" int fgs_debug_gemm_phases(void* buf) {
 // MLP chain on CTA pairs (cta_group::2) instead of single CTAs.
 extern "C" int fgs_set_mlp_chain_pairs(int on) {
   g_chain_pairs = on ? 1 : 0;
+  return 0;
+}
+
+// Weight-gradient kernel on CTA pairs (off by default: measured slower, see mlp_dw2_kernel).
+extern "C" int fgs_set_mlp_dw_pairs(int on) {
+  g_dw_pairs = on ? 1 : 0;
   return 0;
 }
 

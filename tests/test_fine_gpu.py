@@ -483,9 +483,20 @@ def test_brick_adam_equals_dense_masked_adam(cuda):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 320, 1000), (3, 256, 777), (256, 112, 40000), (256, 256, 130), (256, 256, 27000)])
-def test_gemm_weight_gradient_kernel(cuda, M, N, K):
-    """fgs_gemm_tn = the warp-specialised split-K kernel of the weight / bias gradients (dW = dZ^T X)."""
+@pytest.mark.parametrize("pairs", [0, 1])
+def test_gemm_weight_gradient_kernel(cuda, M, N, K, pairs):
+    """fgs_gemm_tn = the stream-K kernel of the weight / bias gradients (dW = dZ^T X, MN-major operand tiles);
+    pairs=1: the CTA-pair (cta_group::2) variant."""
     from fgs_nerf_b200 import engine
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    check(lib.fgs_set_mlp_dw_pairs(pairs))
+    try:
+        _dw_case(cuda, M, N, K)
+    finally:
+        check(lib.fgs_set_mlp_dw_pairs(0))
+
+
+def _dw_case(cuda, M, N, K):
     from fgs_nerf_b200._lib import lib, check, ptr, stream
     A, B, want = _tc_case(cuda, 2, M, N, K, 31 * M + N + K)
     out = torch.zeros(M, (N + 3) // 4 * 4, device=cuda)
