@@ -308,12 +308,12 @@ def run_ours(args):
                      frac=round(ach / (pk["tensor"] if bound == "tensor" else pk["hbm"]), 4))
     top = kern[0]
     # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture of this command
-    # (profiles/r01_ncu_full_mlp_chain_dw.txt: dram__bytes_read.sum + dram__bytes_write.sum, taken at M2 = 42.5 K)
-    ncu_traffic = {"mlp_chain": 37.04e6 + 264.62e6, "mlp_dw": 1071.7e6 + 9.89e6}
+    # (profiles/r01_ncu_full_mlp_chain2_dw.txt: dram__bytes_read.sum + dram__bytes_write.sum, taken at M2 = 42.5 K)
+    ncu_traffic = {"mlp_chain": 37.42e6 + 263.94e6, "mlp_dw": 1051.6e6 + 7.32e6}
     roof = {"kernel": top["name"], "bound": top.get("bound", "hbm"), "achieved": top.get("achieved"),
             "peak": pk["tensor"] if top.get("bound") == "tensor" else pk["hbm"],
             "unit": top.get("unit", "GB/s"), "frac": top.get("frac"), "traffic": ncu_traffic.get(top["name"]),
-            "traffic_source": "profiles/r01_ncu_full_mlp_chain_dw.txt (bytes per launch at M2 = 42.5 K samples)",
+            "traffic_source": "profiles/r01_ncu_full_mlp_chain2_dw.txt (bytes per launch at M2 = 42.5 K samples)",
             "peak_source": pk["src"],
             "launches_per_step": top["launches_per_step"], "avg_launch_ms": round(top["ms_per_step"] / max(top["launches_per_step"], 1e-9), 5),
             "share_of_step": top["share"],

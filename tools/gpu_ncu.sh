@@ -2,7 +2,7 @@
 # ncu evidence for the current bench command: (1) launch list with device times, (2) full capture
 # of the kernels matching $1 (default mlp_chain_kernel) and $2 (default mlp_dw_kernel).  Each ncu run
 # directly follows a plain run of the same command.
-PAT=${1:-mlp_chain_kernel}
+PAT=${1:-mlp_chain2_kernel}
 PAT2=${2:-mlp_dw_kernel}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 mkdir -p gpurun_out
