@@ -662,14 +662,16 @@ class FineStepEngine:
             # the grid gradients are final after phase 1: their regularisers and optimiser kernels (HBM-bound, small
             # CTAs) run on the side stream next to the tensor-core-bound weight-gradient kernel
             self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
+            # the TV regularisers stay on the main stream: full-grid stencils run 4x slower squeezed in beside the
+            # weight-gradient CTAs than alone (75 us), and the join would wait for them
+            if tv and t["smooth_grad_tv"] > 0:
+                self.smooth_grad_tv_add_grad()
+            if tv and t["sdf_tv"] > 0:
+                self.sdf_tv_add_grad(global_step, n_rays_global)
             self._ev_grids.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_grids)
                 lib.fgs_prof_mark(4, stream())
-                if tv and t["smooth_grad_tv"] > 0:
-                    self.smooth_grad_tv_add_grad()
-                if tv and t["sdf_tv"] > 0:
-                    self.sdf_tv_add_grad(global_step, n_rays_global)
                 self.optimizer_step(parts="grids")
                 self._ev_exch.record(self._side)
             self.backward_weights()
