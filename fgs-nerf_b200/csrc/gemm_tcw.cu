@@ -1095,13 +1095,16 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- set-up: barriers (the leader's a_full / b_full / r_empty also count the follower's arrivals), TMEM ----
+  // a_full: every CTA's producers arrive on their OWN barrier (CTA scope); the follower's otherwise idle issuer
+  // thread forwards each completed phase to the leader.  A cluster-scope release issued by a producer itself waits
+  // for that thread's prefetch loads in flight -- one memory latency per slab.
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
   if (tid == 0) {
     for (int i = 0; i < kChainMaxTiles; ++i) mbar_init(cdone0 + 8 * i, 8);
     for (int i = 0; i < kStages2; ++i) {
       mbar_init(B.free0 + 8 * i, 1);                                     // one multicast commit
       mbar_init(B.bfull0 + 8 * i, 1);                                    // the leader's expect_tx arrive; bytes from both CTAs
-      mbar_init(B.afull0 + 8 * i, 2 * (kProducersF / 32));               // producer warps of both CTAs
+      mbar_init(B.afull0 + 8 * i, kProducersF / 32 + (rank == 0 ? 1 : 0));   // own producer warps (+ the follower's relay)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(B.rfull0 + 8 * i, 1);
@@ -1193,6 +1196,9 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
             }
             mma2_commit(B.free0 + 8 * st);
             if (kt == n_slabs - 1) mma2_commit(B.rfull0 + 8 * rg);
+          } else {
+            mbar_wait(B.afull0 + 8 * st, par);                   // this CTA's activation slab g is in place
+            mbar_arrive_cluster(l_afull0 + 8 * st);              // -> tell the leader
           }
           // next weight slab of this CTA's half (its stage was last read by slab lg - kStages2)
           if (lc.w < n_items) {
@@ -1251,12 +1257,7 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {                                          // the LEADER's barrier
-          if (rank == 0) mbar_arrive(B.afull0 + 8 * st);
-          else mbar_arrive_cluster(l_afull0 + 8 * st);
-        }
-        // (the prefetch is issued AFTER the arrive: a cluster-scope release waits for every load in flight --
-        // with the loads in front of it each slab iteration took 2.2 K cycles instead of 0.8 K)
+        if (lane == 0) mbar_arrive(B.afull0 + 8 * st);            // own CTA's barrier (the follower's is relayed)
         load_a(v, kt + 2);
         ++g;
         if (dbg_on) t_work += clock64() - t0;
@@ -1569,9 +1570,19 @@ __global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_cons
 // ---- the same on CTA pairs (cta_group::2): a pair owns a 256 (all out-features) x 128 output tile ----------------
 // Each CTA produces the MN-major tile of ITS 128 out-features of dZ (A) and of ITS half of the tile's input features
 // of X (B): per slab 48 KB of st.shared per SM instead of 64 KB, for twice the output, and one M256 N128 K8 MMA
-// stream issued by the leader (~92 cycles per MMA).  Signalling as in mlp_chain2_kernel.  Measured: NOT faster
-// (259 vs 237 us per step): this kernel is bound by its producers, and the follower's producers now sit on a longer
-// loop (commit multicast -> fill -> remote arrive); selectable with fgs_set_mlp_dw_pairs(1), off by default.
+// stream issued by the leader (~92 cycles per MMA).  Signalling as in mlp_chain2_kernel, four 48-KB stages.
+// Measured: 230 -> 187 us per step once the follower's a_full went through the relay thread (with its producers
+// arriving on the leader's barrier themselves -- a cluster-scope release behind their prefetch loads -- it was
+// SLOWER than the single-CTA kernel: 259 us).  At 187 us the kernel reads its ~1 GB of operands at 5.6 TB/s.
+// stage = A_hi, A_lo (16 KB each: this CTA's 128 out-features) + B_hi, B_lo (8 KB each: its <= 64 input features):
+// 48 KB, so FOUR stages fit -- the follower's producers sit on a longer loop than in the single-CTA kernel
+constexpr int kStagesD2 = 4;
+constexpr uint32_t kBHalfD2 = 64 * BK * 4;                       // 8 KB
+constexpr uint32_t kStageD2 = 2 * kATile + 2 * kBHalfD2;         // 48 KB
+static_assert(kStagesD2 * kStageD2 == kStagingOff, "staging / barrier offsets are shared");
+constexpr uint32_t kBarD2Off = kCDoneOff;                        // its own barrier block (4 stages do not fit Bars)
+constexpr uint32_t kSmemBytesDw2 = kBarD2Off + 8 * (2 * kStagesD2 + 2 * kRegions);
+
 struct Dw2Args {
   DwProblem p[kDwMaxProblems];
   unsigned char tile_prob[kDwMaxTiles], tile_n[kDwMaxTiles];
@@ -1583,7 +1594,12 @@ struct Dw2Args {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_dw2_kernel(const __grid_constant__ Dw2Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
-  const Bars B = make_bars(smem);
+  Bars B;                                                       // free[4], afull[4], rfull[4], rempty[4]
+  B.free0 = smem + kBarD2Off;
+  B.afull0 = B.free0 + 8 * kStagesD2;
+  B.rfull0 = B.afull0 + 8 * kStagesD2;
+  B.rempty0 = B.rfull0 + 8 * kRegions;
+  B.bfull0 = 0;
 
   int K = a.K;
   if (a.rows_dev) K = min(K, *a.rows_dev);
@@ -1597,9 +1613,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kStagesD2; ++i) {
       mbar_init(B.free0 + 8 * i, 1);
-      mbar_init(B.afull0 + 8 * i, 2 * (kProducersTn / 32));    // producer warps of both CTAs
+      mbar_init(B.afull0 + 8 * i, kProducersTn / 32 + (rank == 0 ? 1 : 0));   // own producer warps (+ the follower's relay)
     }
     for (int i = 0; i < kRegions; ++i) {
       mbar_init(B.rfull0 + 8 * i, 1);
@@ -1622,6 +1638,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
   const uint32_t l_afull0 = map_to_cta(B.afull0, 0), l_rempty0 = map_to_cta(B.rempty0, 0);
 
   if (warp >= kIssuerWarpTn) {
+    if (rank != 0 && warp == kIssuerWarpTn && lane == 0) {
+      // follower: forward "my operand tiles of slab g are in place" to the leader (see mlp_chain2_kernel)
+      const uint32_t total = (uint32_t)(u_end - u_beg);
+      for (uint32_t g = 0; g < total; ++g) {
+        const uint32_t st = g % kStagesD2;
+        mbar_wait(B.afull0 + 8 * st, (g / kStagesD2) & 1);
+        mbar_arrive_cluster(l_afull0 + 8 * st);
+      }
+    }
     if (rank == 0 && warp == kIssuerWarpTn && lane == 0) {
       uint32_t g = 0;
       long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
@@ -1634,16 +1659,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256, MN-major
         for (int i = 0; i < len; ++i, ++g) {
-          const uint32_t st = g % kStages;
+          const uint32_t st = g % kStagesD2;
           if (dbg_cta) t0 = clock64();
-          mbar_wait_cluster(B.afull0 + 8 * st, (g / kStages) & 1);
+          mbar_wait_cluster(B.afull0 + 8 * st, (g / kStagesD2) & 1);
           if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
           if (g >= (uint32_t)kRegions) mbar_wait_cluster(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
           if (dbg_cta) t_r += clock64() - t0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t stage_base = smem + st * kStage, d = tmem_d + (g % kRegions) * TN;
+          const uint32_t stage_base = smem + st * kStageD2, d = tmem_d + (g % kRegions) * TN;
           const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
-          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
+          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBHalfD2;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t dah = make_desc_mn(a_hi + j * 1024), dal = make_desc_mn(a_lo + j * 1024);
@@ -1710,9 +1735,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
       cs = make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto produce = [&](float4 (&va)[4], float4 (&vb)[2], const Cur& c, Cur& pf) {
-      const uint32_t st = g % kStages;
-      const uint32_t stage_base = smem + st * kStage;
-      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
+      const uint32_t st = g % kStagesD2;
+      const uint32_t stage_base = smem + st * kStageD2;
+      if (g >= (uint32_t)kStagesD2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesD2) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
@@ -1724,16 +1749,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
       for (int i = 0; i < 2; ++i) {
         const uint32_t r = (uint32_t)(4 * pw + 2 * i + bsub);
         const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 3u)) * 32u);
-        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBTile + off, vb[i]);
+        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
       }
       if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(B.afull0 + 8 * st);
-        else mbar_arrive_cluster(l_afull0 + 8 * st);
-      }
-      load_ab(va, vb, pf);                               // after the (cluster-scope) arrive: see mlp_chain2_kernel
+      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);     // own CTA's barrier (the follower's is relayed)
+      load_ab(va, vb, pf);
       advance(pf);
       ++g;
     };
@@ -1799,7 +1821,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
 int g_chain_pairs = 1;     // 1: mlp_chain2_kernel (CTA pairs, tcgen05 cta_group::2)
-int g_dw_pairs = 0;        // 1: mlp_dw2_kernel (correct, but its producers sit on the longer cross-CTA loop: 259 vs 237 us)
+int g_dw_pairs = 1;        // 1: mlp_dw2_kernel (CTA pairs)
 int g_dw_sm_reserve = 0;
 int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
@@ -1994,13 +2016,13 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
       }
       b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
       static bool configured2 = false;
-      int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytes);
+      int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
       if (rc2) return rc2;
       const long long units2 = (long long)nt2 * fgs::cdiv(K, BK);
       int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
       if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
       if (pairs_n < 1) pairs_n = 1;
-      mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytes, st>>>(b);
+      mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
       return fgs::check_launch("mlp_dw", st);
     }
   }
@@ -2091,7 +2113,7 @@ extern "C" int fgs_set_mlp_chain_pairs(int on) {
   return 0;
 }
 
-// Weight-gradient kernel on CTA pairs (off by default: measured slower, see mlp_dw2_kernel).
+// Weight-gradient kernel on CTA pairs (default) or single CTAs.
 extern "C" int fgs_set_mlp_dw_pairs(int on) {
   g_dw_pairs = on ? 1 : 0;
   return 0;

@@ -237,7 +237,7 @@ int fgs_set_mlp_fusion(int on);
 /* 1: the MLP chains run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each SM of a pair holds half of the
  * weight rows); 0: one CTA per 128-row tile. */
 int fgs_set_mlp_chain_pairs(int on);
-/* The same for the weight-gradient kernel (default 0: measured slower, its operand producers are the bottleneck). */
+/* The same for the weight-gradient kernel (default 1). */
 int fgs_set_mlp_dw_pairs(int on);
 
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
