@@ -230,14 +230,23 @@ class FineStepEngine:
         X, Y, Z = self.sdf.shape[2:]
         self.X, self.Y, self.Z = X, Y, Z
         # ---- gradients + Adam state ----
-        self.g_sdf = torch.zeros_like(self.sdf)
         self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
         # all 16 MLP gradient tensors are views of one flat buffer (one clear, one all-reduce bucket)
         sizes = [w.numel() for w in self.Wt] + [b.numel() for b in self.Bt]
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + (n + 3) // 4 * 4)         # keep every view 16-byte aligned
-        self.g_mlp_flat = torch.zeros(offs[-1], dtype=f32, device=dev)
+        # one allocation [ g_sdf | MLP gradient bucket | packed touched k0 bricks ]: a data-parallel step reduces
+        # everything with ONE all-reduce over a prefix of it (the packed part exists only when world_size > 1)
+        V = self.sdf.numel()
+        Vp = (V + 3) // 4 * 4
+        nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
+        self._xcap_bricks = min(nb, 32768) if self.world_size > 1 else 0
+        self._xbuf = torch.zeros(Vp + offs[-1] + self._xcap_bricks * 768, dtype=f32, device=dev)
+        self.g_sdf = self._xbuf[:V].view_as(self.sdf)
+        self.g_mlp_flat = self._xbuf[Vp:Vp + offs[-1]]
+        self._compact = self._xbuf[Vp + offs[-1]:]
+        self._xdense = Vp + offs[-1]
         views = [self.g_mlp_flat[o:o + n] for o, n in zip(offs, sizes)]
         self.gW = [v.view_as(w) for v, w in zip(views[:MLP_LAYERS], self.Wt)]
         self.weight_grads = [g[:, :d[1]] for g, d in zip(self.gW, dims)]
@@ -284,7 +293,6 @@ class FineStepEngine:
         self.sparse_k0 = (Z % 4 == 0)      # brick-driven masked Adam (else the dense reference-style scan)
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         self._brick_list_ready = False
-        self._compact = None
         self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._count_evt = torch.cuda.Event()
         self.exchange_bricks = 0
@@ -585,67 +593,80 @@ class FineStepEngine:
         check(lib.fgs_adam_upd_multi(n, mt["p"], mt["g"], mt["m"], mt["v"], mt["n"], steps, lrs, b1, b2, eps, st))
 
     def all_reduce_grads(self):
-        """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink).
-        g_sdf and the MLP bucket are reduced densely (16 MB + 1.8 MB at 160^3).  g_k0 (197 MB, ~2 %
-        non-zero) is exchanged SPARSELY: union of the touched-brick flags (MAX all-reduce of one byte
-        per 4^3 brick), ordered brick list, pack -> all-reduce of the packed bricks -> unpack.  The
-        brick count crosses to the host once per step to size the collective."""
+        """Ray-sharded data parallelism: sum the per-rank gradients (NCCL over NVLink), not overlapped with anything
+        (train_step overlaps the first two parts with the weight-gradient kernel).
+        g_sdf and the MLP bucket are dense (16 MB + 1.8 MB at 160^3).  g_k0 (197 MB, ~2 % non-zero) is exchanged
+        SPARSELY: union of the touched-brick flags (MAX all-reduce of one byte per 4^3 brick), ordered brick list,
+        pack.  Then ONE all-reduce over [g_sdf | MLP bucket | packed bricks] and the unpack.  The brick count
+        crosses to the host once per step to size the collective."""
         if self.world_size == 1:
             return
-        self._exchange_grids_begin()
-        from .dist import all_reduce_sum_
-        all_reduce_sum_([self.g_mlp_flat])
-        self._exchange_grids_finish()
+        self._exchange_begin()
+        self._exchange_pack()
+        self._exchange_reduce()
 
-    def _exchange_grids_begin(self):
-        """Grid-gradient exchange, part 1 (everything that does not need the host): union of the touched
-        bricks, ordered brick list, its count on the way to the host, dense reduction of g_sdf."""
+    def _exchange_begin(self):
+        """Part 1 (needs only the grid gradients): union of the touched bricks, ordered brick list, its count on
+        the way to the host."""
         import torch.distributed as dist
         ws = self.ws
-        if not self.sparse_k0:
-            from .dist import all_reduce_sum_
-            all_reduce_sum_([self.g_sdf, self.g_k0])
-            dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)
-            return
         dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
+        if not self.sparse_k0:
+            return
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
             self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
             self._count_evt.record()
-        dist.all_reduce(self.g_sdf)
 
-    def _exchange_grids_finish(self):
-        """Part 2: the one host sync of a DP step (brick count -> size of the collective), then pack ->
-        all-reduce of the packed bricks -> unpack."""
-        import torch.distributed as dist
-        ws = self.ws
+    def _exchange_pack(self):
+        """Part 2: the one host sync of a DP step (brick count -> size of the collective) and the pack of the
+        union bricks behind the dense gradients."""
         if not self.sparse_k0:
-            lib.fgs_prof_mark(1, stream())
             return
         with torch.cuda.device(self.device):
-            st = stream()
             self._count_evt.synchronize()
             n = int(self._count_host[0])
+            self.exchange_bricks = n
+            self._xbuf_overflow = None
+            if n > self._xcap_bricks:                               # rare: more bricks than the shared buffer holds
+                self._xbuf_overflow = torch.empty(n * 768, dtype=torch.float32, device=self.device)
             if n > 0:
-                if self._compact is None or self._compact.numel() < n * 768:
-                    self._compact = torch.empty(int(n * 1.5) * 768, dtype=torch.float32, device=self.device)
-                buf = self._compact[:n * 768]
-                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(ws["k0_brick_list"]), n, self.X, self.Y, self.Z,
-                                         K0_DIM, 1, st))
-                dist.all_reduce(buf)
-                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(ws["k0_brick_list"]), n, self.X, self.Y, self.Z,
-                                         K0_DIM, 0, st))
-            lib.fgs_prof_mark(1, st)
+                buf = self._xbuf_overflow if self._xbuf_overflow is not None else self._compact
+                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
+                                         self.Z, K0_DIM, 1, stream()))
         self._brick_list_ready = True
-        self.exchange_bricks = n
+
+    def _exchange_reduce(self):
+        """Part 3 (needs the MLP gradients too): one all-reduce over [g_sdf | MLP bucket | packed bricks], unpack."""
+        import torch.distributed as dist
+        if not self.sparse_k0:
+            dist.all_reduce(self._xbuf[:self._xdense])
+            g = self.g_k0
+            dist.all_reduce(torch.as_strided(g, (g.numel(),), (1,), g.storage_offset()))
+            lib.fgs_prof_mark(1, stream())
+            return
+        n = self.exchange_bricks
+        with torch.cuda.device(self.device):
+            if self._xbuf_overflow is not None:
+                dist.all_reduce(self._xbuf[:self._xdense])
+                dist.all_reduce(self._xbuf_overflow)
+                buf = self._xbuf_overflow
+            else:
+                dist.all_reduce(self._xbuf[:self._xdense + n * 768])
+                buf = self._compact
+            lib.fgs_prof_mark(1, stream())
+            if n > 0:
+                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
+                                         self.Z, K0_DIM, 0, stream()))
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True):
         """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous.
-        Data-parallel (world_size > 1): the backward runs in two phases -- the grid gradients first -- and the
-        exchange of g_sdf / the touched k0 bricks is issued on a side stream while the weight-gradient kernel
-        (which leaves a few SMs free for the collectives) runs on the main one."""
+        Data-parallel (world_size > 1): the backward runs in two phases -- the grid gradients first; the union of
+        the touched k0 bricks, its count (the one host sync) and the pack run on a side stream while the
+        weight-gradient kernel (which leaves a few SMs free for them) runs on the main one; then ONE all-reduce over
+        [g_sdf | MLP bucket | packed bricks]."""
         self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
         t = self.train_cfg
@@ -680,7 +701,6 @@ class FineStepEngine:
             lib.fgs_prof_mark(5, stream())
             return
         else:
-            from .dist import all_reduce_sum_
             self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
             if tv and t["smooth_grad_tv"] > 0 and self.rank == 0:
                 self.smooth_grad_tv_add_grad()                             # a pure function of the params:
@@ -688,15 +708,14 @@ class FineStepEngine:
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_grids)
                 lib.fgs_prof_mark(4, stream())
-                self._exchange_grids_begin()
+                self._exchange_begin()                                     # flags, brick list, count -> host
             self.backward_weights()                                        # main stream, overlaps the exchange
             with torch.cuda.stream(self._side):
-                self._exchange_grids_finish()
+                self._exchange_pack()                                      # host sync + pack, still beside phase 2
                 self._ev_exch.record(self._side)
-            all_reduce_sum_([self.g_mlp_flat])
-            lib.fgs_prof_mark(1, stream())
             main.wait_event(self._ev_exch)
             lib.fgs_prof_mark(5, stream())
+            self._exchange_reduce()                                        # ONE all-reduce of everything, unpack
         if tv and t["sdf_tv"] > 0:
             self.sdf_tv_add_grad(global_step, n_rays_global)
         self.optimizer_step()
