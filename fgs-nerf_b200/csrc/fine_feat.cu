@@ -66,12 +66,13 @@ __device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); 
 // independent parts of a level-2 row (blockIdx.y of feat_kernel / feat_bwd_kernel)
 constexpr int kTaskK0 = 0, kTaskPE = 1, kTaskRefl = 2, kTaskTap0 = 3, kNumTasks = 7;
 
-__global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P) {
+__global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P, int only_task) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
   // blockIdx.y = which independent part of the row this CTA builds (uniform per CTA: no divergence).  With one
   // thread building a whole row only ~1300 warps existed for ~40 K samples (sm__warps_active 14 %, 79 us).
   const int task = blockIdx.y;
+  if (only_task >= 0 && task != only_task) return;    // timing experiments (fgs_debug_feat_task)
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
     float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
@@ -96,40 +97,52 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
       st4(row + FGS_X0_K0 + 8, a2);
     }
     // ---- positional encodings (model/nerf.py:836-839, 870-873) ----
+    // (sincosf shares the argument reduction of the sinf / cosf pair it replaces; the 54 values + sdf are assembled
+    // in registers and leave as 16-byte stores: columns 12..63 are 13 float4, 64..66 scalars)
     if (task == kTaskPE) {
+      float e54[56];
       const float rx[3] = {__fdiv_rn(__fsub_rn(q.px, g.mn[0]), g.ext[0]),
                            __fdiv_rn(__fsub_rn(q.py, g.mn[1]), g.ext[1]),
                            __fdiv_rn(__fsub_rn(q.pz, g.mn[2]), g.ext[2])};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        row[FGS_X0_XYZ + c] = rx[c];
+        e54[c] = rx[c];
         float f = 1.f;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-          const float e = __fmul_rn(rx[c], f);
-          row[FGS_X0_XYZ + 3 + c * 5 + k] = sinf(e);
-          row[FGS_X0_XYZ + 18 + c * 5 + k] = cosf(e);
+          float sn, cs;
+          sincosf(__fmul_rn(rx[c], f), &sn, &cs);
+          e54[3 + c * 5 + k] = sn;
+          e54[18 + c * 5 + k] = cs;
           f *= 2.f;
         }
       }
-    }
-    const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
-                        P.viewdirs[3 * (size_t)q.ray + 2]};
-    if (task == kTaskPE) {
+      const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
+                          P.viewdirs[3 * (size_t)q.ray + 2]};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        row[FGS_X0_VIEW + c] = v[c];
+        e54[33 + c] = v[c];
         float f = 1.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float e = __fmul_rn(v[c], f);
-          row[FGS_X0_VIEW + 3 + c * 3 + k] = sinf(e);
-          row[FGS_X0_VIEW + 12 + c * 3 + k] = cosf(e);
+          float sn, cs;
+          sincosf(__fmul_rn(v[c], f), &sn, &cs);
+          e54[33 + 3 + c * 3 + k] = sn;
+          e54[33 + 12 + c * 3 + k] = cs;
           f *= 2.f;
         }
       }
-      row[FGS_X0_SDF] = P.sdf1[q.idx1];
+      e54[54] = P.sdf1[q.idx1];
+      static_assert(FGS_X0_XYZ % 4 == 0 && FGS_X0_VIEW == FGS_X0_XYZ + 33 && FGS_X0_SDF == FGS_X0_XYZ + 54, "row layout");
+#pragma unroll
+      for (int j = 0; j < 13; ++j)
+        st4(row + FGS_X0_XYZ + 4 * j, make_float4(e54[4 * j], e54[4 * j + 1], e54[4 * j + 2], e54[4 * j + 3]));
+      row[FGS_X0_XYZ + 52] = e54[52];
+      row[FGS_X0_XYZ + 53] = e54[53];
+      row[FGS_X0_SDF] = e54[54];
     }
+    const float v[3] = {P.viewdirs[3 * (size_t)q.ray], P.viewdirs[3 * (size_t)q.ray + 1],
+                        P.viewdirs[3 * (size_t)q.ray + 2]};
     // ---- hierarchical SDF taps (sample_sdfs, model/nerf.py:597-637, use_grad_norm=True) ----
     if (task >= kTaskTap0 && task < kTaskTap0 + 4) {
       const int d = task - kTaskTap0;
@@ -160,31 +173,39 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
     const float dot = sum3_inner(__fmul_rn(v[0], nc.nx), __fmul_rn(v[1], nc.ny), __fmul_rn(v[2], nc.nz));
     const float n3[3] = {nc.nx, nc.ny, nc.nz};
     float* __restrict__ xr = P.XR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
+    {
+      float e64[FGS_XR_LD - FGS_MLP_WIDTH];             // 51 values + zero pad, assembled in registers, 16 float4 stores
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float r = __fsub_rn(v[c], __fmul_rn(__fmul_rn(2.f, dot), n3[c]));
-      xr[c] = r;
-      float f = 1.f;
+      for (int c = FGS_XR_DIM - FGS_MLP_WIDTH; c < FGS_XR_LD - FGS_MLP_WIDTH; ++c) e64[c] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float e = __fmul_rn(r, f);
-        xr[3 + c * 8 + k] = sinf(e);
-        xr[27 + c * 8 + k] = cosf(e);
-        f *= 2.f;
+      for (int c = 0; c < 3; ++c) {
+        const float r = __fsub_rn(v[c], __fmul_rn(__fmul_rn(2.f, dot), n3[c]));
+        e64[c] = r;
+        float f = 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float sn, cs;
+          sincosf(__fmul_rn(r, f), &sn, &cs);
+          e64[3 + c * 8 + k] = sn;
+          e64[27 + c * 8 + k] = cs;
+          f *= 2.f;
+        }
       }
-    }
 #pragma unroll
-    for (int c = FGS_XR_DIM - FGS_MLP_WIDTH; c < FGS_XR_LD - FGS_MLP_WIDTH; ++c) xr[c] = 0.f;
+      for (int j = 0; j < (FGS_XR_LD - FGS_MLP_WIDTH) / 4; ++j)
+        st4(xr + 4 * j, make_float4(e64[4 * j], e64[4 * j + 1], e64[4 * j + 2], e64[4 * j + 3]));
+    }
     st4(P.normal2 + 4 * (size_t)s, make_float4(nc.nx, nc.ny, nc.nz, dot));
   }
 }
 
 __global__ void __launch_bounds__(kBlock)
-feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientation) {
+feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientation, int only_task) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
   const int task = blockIdx.y;     // k0 scatter | (unused) | reflection chain | 4 displacement levels
   if (task == kTaskPE) return;     // the encodings of xyz / viewdirs have no trainable inputs
+  if (only_task >= 0 && task != only_task) return;
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
     const float* __restrict__ row = P.X0 + (size_t)s * FGS_X0_LD;
@@ -251,16 +272,25 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
     const float* __restrict__ xr = P.XR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
     const float* __restrict__ dxr = P.dXR + (size_t)s * FGS_XR_LD + FGS_MLP_WIDTH;
     float dr[3];
+    {
+      float xl[52], dl[52];                              // the 51 encoding values / their gradients: 13 float4 loads each
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float acc = dxr[c];
-      float f = 1.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc += f * (xr[27 + c * 8 + k] * dxr[3 + c * 8 + k] - xr[3 + c * 8 + k] * dxr[27 + c * 8 + k]);
-        f *= 2.f;
+      for (int j = 0; j < 13; ++j) {
+        const float4 a4 = ld4(xr + 4 * j), b4 = ld4(dxr + 4 * j);
+        xl[4 * j] = a4.x; xl[4 * j + 1] = a4.y; xl[4 * j + 2] = a4.z; xl[4 * j + 3] = a4.w;
+        dl[4 * j] = b4.x; dl[4 * j + 1] = b4.y; dl[4 * j + 2] = b4.z; dl[4 * j + 3] = b4.w;
       }
-      dr[c] = acc;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = dl[c];
+        float f = 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc += f * (xl[27 + c * 8 + k] * dl[3 + c * 8 + k] - xl[3 + c * 8 + k] * dl[27 + c * 8 + k]);
+          f *= 2.f;
+        }
+        dr[c] = acc;
+      }
     }
     const float vn = v[0] * n3[0] + v[1] * n3[1] + v[2] * n3[2];
     const float drn = dr[0] * n3[0] + dr[1] * n3[1] + dr[2] * n3[2];
@@ -310,16 +340,24 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
 
 namespace fine {
 
+int g_only_task = -1;
+
 int launch_feat(const FgsFineParams& P, cudaStream_t st) {
   const int grid = fgs::stream_grid(P.cap_m2, kBlock, 4);
-  feat_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P);
+  feat_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P, g_only_task);
   return fgs::check_launch("fine feat", st);
 }
 
 int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st) {
   const int grid = fgs::stream_grid(P.cap_m2, kBlock, 4);
-  feat_bwd_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P, weight_orientation);
+  feat_bwd_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P, weight_orientation, g_only_task);
   return fgs::check_launch("fine feat_bwd", st);
 }
 
 }  // namespace fine
+
+// Timing aid: run only one of the independent row parts of feat_kernel / feat_bwd_kernel (-1 = all).
+extern "C" int fgs_debug_feat_task(int task) {
+  fine::g_only_task = task;
+  return 0;
+}

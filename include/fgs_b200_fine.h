@@ -240,6 +240,10 @@ int fgs_set_mlp_chain_pairs(int on);
 /* The same for the weight-gradient kernel (default 1). */
 int fgs_set_mlp_dw_pairs(int on);
 
+/* Timing aid: run only row part `task` (0 k0, 1 encodings, 2 reflection chain, 3..6 displacement levels) of the
+ * level-2 feature kernels; -1 = all (default).  Results are incomplete while it is set. */
+int fgs_debug_feat_task(int task);
+
 /* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
 int fgs_set_gemm_backend(int tensor_core);
 
