@@ -317,6 +317,10 @@ def run_ours(args):
             "peak_source": pk["src"],
             "launches_per_step": top["launches_per_step"], "avg_launch_ms": round(top["ms_per_step"] / max(top["launches_per_step"], 1e-9), 5),
             "share_of_step": top["share"],
+            # the same achieved rate against what this formulation can reach at best: kind::tf32 issues at half the
+            # bf16 rate and 3xTF32 spends three MMAs per product
+            "frac_of_3xtf32_ceiling": (round(top["achieved"] / (pk["tensor"] / 6.0), 4)
+                                       if top.get("bound") == "tensor" and top.get("achieved") else None),
             "note": "3xTF32 tcgen05 GEMMs of the colour MLPs: algorithmic fp32 FLOPs against the measured bf16 tensor "
                     "peak (kind::tf32 runs at half the bf16 rate and the split issues 3 MMAs per product, so the "
                     "ceiling of this formulation is 1/6 of that peak)"}
