@@ -99,6 +99,7 @@ _lib.declare("fgs_set_gemm_tmem_accumulate", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_fusion", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_chain_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_dw_pairs", C.c_int, [C.c_int])
+_lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])

@@ -4,7 +4,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fgs_nerf_b200 import engine, scene, _lib
 from fgs_nerf_b200._lib import lib, check
-lib.fgs_debug_feat_task.argtypes = [ctypes.c_int]
 dev = torch.device("cuda:0")
 sc = scene.make_scene(G=160)
 ro, rd, vd, tgt = [t.to(dev) for t in scene.make_rays(N=8192)]
