@@ -52,6 +52,9 @@ _SIGS = {
     "fgs_adam_upd_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p]),
     "fgs_adam_upd_zero_grad": (_i, [_p, _p, _p, _p, _l, _i, _f, _f, _f, _f, _p]),
     "fgs_brick_list_ints": (_l, [_i, _i, _i]),
+    "fgs_voxel_list_ints": (_l, [_l]),
+    "fgs_voxel_list": (_i, [_p, _l, _p, _p]),
+    "fgs_voxel_copy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "fgs_brick_list": (_i, [_p, _i, _i, _i, _p, _p]),
     "fgs_brick_copy": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fgs_adam_upd_bricks": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _p]),

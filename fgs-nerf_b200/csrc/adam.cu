@@ -381,6 +381,120 @@ adam_bricks_kernel(float* __restrict__ param, float* __restrict__ grad, float* _
   }
 }
 
+// ---- voxel-granular touched list (data-parallel exchange of g_k0) -------------------------------------------------
+// Only ~23 % of the voxels of a touched 4^3 brick carry a gradient, so the collective ships voxels (48 bytes each),
+// not bricks.  One byte per voxel, set by the backward scatter; the list is ASCENDING (identical on every rank that
+// holds the same flags) and built by two launches over all SMs: per-CTA counts, then every CTA sums the counts in
+// front of it, re-scans its own flags and writes its ids (flags cleared on the way).  list[0] = count.
+constexpr int kVoxPerThread = 64, kVoxThreads = 256, kVoxPerCta = kVoxPerThread * kVoxThreads;
+
+__device__ __forceinline__ int vox_load_masks(const unsigned char* __restrict__ flags, long long beg, long long n,
+                                              bool vec, uint32_t (&m)[16]) {
+  if (vec && beg + kVoxPerThread <= n) {
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(flags + beg);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = src[q];
+      m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long b = beg + 4 * i + j;
+        if (b < n) x |= (uint32_t)flags[b] << (8 * j);
+      }
+      m[i] = x;
+    }
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    m[i] = ((((m[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m[i]) & 0x80808080u);   // bit 8 j + 7 <=> flag 4 i + j nonzero
+    cnt += __popc(m[i]);
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(kVoxThreads)
+voxel_count_kernel(const unsigned char* __restrict__ flags, long long n, int* __restrict__ cta_counts) {
+  __shared__ int s_warp[kVoxThreads / 32];
+  uint32_t m[16];
+  const long long beg = (long long)blockIdx.x * kVoxPerCta + (long long)threadIdx.x * kVoxPerThread;
+  int cnt = beg < n ? vox_load_masks(flags, beg, n, (((uintptr_t)flags) & 15) == 0, m) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane_id() == 0) s_warp[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kVoxThreads / 32; ++w) t += s_warp[w];
+    cta_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kVoxThreads)
+voxel_write_kernel(unsigned char* __restrict__ flags, long long n, const int* __restrict__ cta_counts,
+                   int* __restrict__ list) {
+  __shared__ int s_warp[kVoxThreads / 32];
+  __shared__ int s_base;
+  // ids in front of this CTA (a few hundred counts: one warp sums them)
+  if (threadIdx.x < 32) {
+    int t = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 32) t += cta_counts[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) s_base = t;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) list[0] = t + cta_counts[blockIdx.x];
+  }
+  uint32_t m[16];
+  const bool vec = (((uintptr_t)flags) & 15) == 0;
+  const long long beg = (long long)blockIdx.x * kVoxPerCta + (long long)threadIdx.x * kVoxPerThread;
+  const int cnt = beg < n ? vox_load_masks(flags, beg, n, vec, m) : 0;
+  const int incl = warp_incl_scan(cnt);
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_warp[w] = incl;
+  __syncthreads();
+  int before = 0;
+  for (int i = 0; i < w; ++i) before += s_warp[i];
+  if (cnt) {
+    int o = 1 + s_base + before + incl - cnt;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t x = m[i];
+      while (x) {
+        const int bit = __ffs(x) - 1;
+        x &= x - 1;
+        list[o++] = (int)(beg + 4 * i + (bit >> 3));
+      }
+    }
+    if (vec && beg + kVoxPerThread <= n) {
+      uint4* __restrict__ dst = reinterpret_cast<uint4*>(flags + beg);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = z;
+    } else {
+      for (long long b = beg; b < min(beg + (long long)kVoxPerThread, n); ++b) flags[b] = 0;
+    }
+  }
+}
+
+// gather / scatter of the listed voxels' 12 gradient channels (3 float4 per voxel) to / from a compact buffer
+template <bool PACK>
+__global__ void __launch_bounds__(kBlock)
+voxel_copy_kernel(float* __restrict__ grid, float* __restrict__ compact, const int* __restrict__ list, int max_voxels) {
+  const int count = min(list[0], max_voxels);
+  const long long total = 3LL * count;
+  for (long long q = blockIdx.x * (long long)kBlock + threadIdx.x; q < total; q += (long long)gridDim.x * kBlock) {
+    const int e = (int)(q / 3), j = (int)(q - 3LL * e);
+    const size_t off = (size_t)list[1 + e] * 12 + 4 * j;
+    if (PACK) st4(compact + 4 * q, ld4(grid + off));
+    else st4(grid + off, ld4(compact + 4 * q));
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -413,6 +527,37 @@ int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_lis
 }
 
 // compact[e][768] <- grad bricks list[1+e] (pack != 0), or grad bricks <- compact (pack == 0); e < max_bricks
+int64_t fgs_voxel_list_ints(int64_t n_voxels) {
+  return 1 + n_voxels + (n_voxels + kVoxPerCta - 1) / kVoxPerCta;      // count, ids, per-CTA counts (scratch at the end)
+}
+
+int fgs_voxel_list(uint8_t* voxel_flags, int64_t n_voxels, int32_t* voxel_list, fgs_stream_t stream) {
+  FGS_REQUIRE(n_voxels > 0 && n_voxels < (1LL << 31), "bad voxel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ctas = (int)((n_voxels + kVoxPerCta - 1) / kVoxPerCta);
+  int* counts = voxel_list + 1 + n_voxels;
+  FGS_PREFER_MAX_SHARED(voxel_count_kernel);
+  FGS_PREFER_MAX_SHARED(voxel_write_kernel);
+  voxel_count_kernel<<<ctas, kVoxThreads, 0, st>>>(voxel_flags, n_voxels, counts);
+  int rc = fgs::check_launch("voxel_count", st);
+  if (rc) return rc;
+  voxel_write_kernel<<<ctas, kVoxThreads, 0, st>>>(voxel_flags, n_voxels, counts, voxel_list);
+  return fgs::check_launch("voxel_list", st);
+}
+
+int fgs_voxel_copy(float* grid, float* compact, const int32_t* voxel_list, int max_voxels, int channels, int pack,
+                   fgs_stream_t stream) {
+  FGS_REQUIRE(channels == 12, "voxel copy is specialised for the 12-channel channels-last k0 grid");
+  if (max_voxels <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid_dim = fgs::stream_grid(3LL * max_voxels, kBlock, 8);
+  FGS_PREFER_MAX_SHARED(voxel_copy_kernel<true>);
+  FGS_PREFER_MAX_SHARED(voxel_copy_kernel<false>);
+  if (pack) voxel_copy_kernel<true><<<grid_dim, kBlock, 0, st>>>(grid, compact, voxel_list, max_voxels);
+  else voxel_copy_kernel<false><<<grid_dim, kBlock, 0, st>>>(grid, compact, voxel_list, max_voxels);
+  return fgs::check_launch(pack ? "voxel_pack" : "voxel_unpack", st);
+}
+
 int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int max_bricks, int X, int Y, int Z,
                    int channels, int pack, fgs_stream_t stream) {
   FGS_REQUIRE(channels == 12 && X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick copy: 12-channel grid, Z % 4 == 0");

@@ -227,7 +227,9 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
             if (brick != last_brick) P.k0_brick_flags[brick] = 1;
             last_brick = brick;
           }
-          float* v = P.g_k0 + (((size_t)z * g.Y + y) * g.Z + x) * FGS_K0_DIM;
+          const size_t vox = ((size_t)z * g.Y + y) * g.Z + x;
+          if (P.k0_vox_flags) P.k0_vox_flags[vox] = 1;
+          float* v = P.g_k0 + vox * FGS_K0_DIM;
           const float w = t.w[c];
           red_add_v4(v, w * d0.x, w * d0.y, w * d0.z, w * d0.w);
           red_add_v4(v + 4, w * d1.x, w * d1.y, w * d1.z, w * d1.w);

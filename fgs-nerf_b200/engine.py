@@ -59,7 +59,7 @@ class FgsFineParams(C.Structure):
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
         ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
-        ("dZ", _fp),
+        ("dZ", _fp), ("k0_vox_flags", _fp),
     ]
 
 
@@ -191,7 +191,7 @@ class FineStepEngine:
     """State + workspace of the fine-stage model for batches of `n_rays` rays on one GPU."""
 
     def __init__(self, scene, n_rays, device="cuda", train_cfg=None, cap_m1_per_ray=128, cap_m2_per_ray=16,
-                 world_size=1, rank=0):
+                 world_size=1, rank=0, voxel_exchange=False):
         from .scene import FINE_TRAIN
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -292,6 +292,14 @@ class FineStepEngine:
         ws["k0_brick_flags"] = torch.zeros(nb, dtype=torch.uint8, device=dev)
         ws["k0_brick_list"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)), dtype=i32, device=dev)
         self.sparse_k0 = (Z % 4 == 0)      # brick-driven masked Adam (else the dense reference-style scan)
+        # data parallel, optional: the k0 gradient travels at VOXEL granularity (one flag byte per voxel, ascending
+        # voxel list: a third of the bytes of the brick exchange).  Off by default: the union of the voxel flags is a
+        # 4 MB MAX all-reduce that, squeezed in beside the weight-gradient kernel, takes longer than the 19 MB it saves
+        # (2 GPUs: 1.28 vs 1.17 ms per step); it needs bit-packed flags before it pays.
+        self.voxel_exchange = bool(voxel_exchange) and self.sparse_k0 and self.world_size > 1
+        if self.voxel_exchange:
+            ws["k0_vox_flags"] = torch.zeros(X * Y * Z, dtype=torch.uint8, device=dev)
+            ws["k0_vox_list"] = torch.zeros(int(lib.fgs_voxel_list_ints(X * Y * Z)), dtype=i32, device=dev)
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         self._brick_list_ready = False
         self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -337,6 +345,7 @@ class FineStepEngine:
                   "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
                   "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ"):
             setattr(P, k, ptr(ws[k]))
+        P.k0_vox_flags = ptr(ws["k0_vox_flags"]) if self.voxel_exchange else None
 
     def s_val(self, global_step):
         """model/nerf.py:514 (python floats)."""
@@ -475,6 +484,8 @@ class FineStepEngine:
             check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
             check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
             check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
+            if self.voxel_exchange:
+                check(lib.fgs_memset_zero(ptr(self.ws["k0_vox_flags"]), self.ws["k0_vox_flags"].numel(), st))
         self._grads_clean = True
 
     def loss_backward(self, target, n_rays_global=None, has_last_ray=True, phase=0):
@@ -614,10 +625,17 @@ class FineStepEngine:
         dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
         if not self.sparse_k0:
             return
+        if self.voxel_exchange:
+            dist.all_reduce(ws["k0_vox_flags"], op=dist.ReduceOp.MAX)          # union of the touched voxels
         with torch.cuda.device(self.device):
             st = stream()
+            # the brick list drives the masked Adam; the voxel list (when enabled) the pack / unpack of the exchange
             check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
-            self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
+            if self.voxel_exchange:
+                check(lib.fgs_voxel_list(ptr(ws["k0_vox_flags"]), self.X * self.Y * self.Z, ptr(ws["k0_vox_list"]), st))
+                self._count_host.copy_(ws["k0_vox_list"][:1], non_blocking=True)
+            else:
+                self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
             self._count_evt.record()
 
     def _exchange_pack(self):
@@ -627,15 +645,15 @@ class FineStepEngine:
             return
         with torch.cuda.device(self.device):
             self._count_evt.synchronize()
-            n = int(self._count_host[0])
+            n = int(self._count_host[0])                            # voxels (12 floats each) or bricks (768 floats)
             self.exchange_bricks = n
+            per = K0_DIM if self.voxel_exchange else 768
             self._xbuf_overflow = None
-            if n > self._xcap_bricks:                               # rare: more bricks than the shared buffer holds
-                self._xbuf_overflow = torch.empty(n * 768, dtype=torch.float32, device=self.device)
+            if n * per > self._compact.numel():                     # rare: more than the shared buffer holds
+                self._xbuf_overflow = torch.empty(n * per, dtype=torch.float32, device=self.device)
             if n > 0:
                 buf = self._xbuf_overflow if self._xbuf_overflow is not None else self._compact
-                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
-                                         self.Z, K0_DIM, 1, stream()))
+                self._copy_touched(buf, n, 1)
         self._brick_list_ready = True
 
     def _exchange_reduce(self):
@@ -648,18 +666,26 @@ class FineStepEngine:
             lib.fgs_prof_mark(1, stream())
             return
         n = self.exchange_bricks
+        per = K0_DIM if self.voxel_exchange else 768
         with torch.cuda.device(self.device):
             if self._xbuf_overflow is not None:
                 dist.all_reduce(self._xbuf[:self._xdense])
                 dist.all_reduce(self._xbuf_overflow)
                 buf = self._xbuf_overflow
             else:
-                dist.all_reduce(self._xbuf[:self._xdense + n * 768])
+                dist.all_reduce(self._xbuf[:self._xdense + n * per])
                 buf = self._compact
             lib.fgs_prof_mark(1, stream())
             if n > 0:
-                check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
-                                         self.Z, K0_DIM, 0, stream()))
+                self._copy_touched(buf, n, 0)
+
+    def _copy_touched(self, buf, n, pack):
+        """Gather (pack=1) / scatter the touched part of g_k0 to / from `buf`: listed voxels or listed bricks."""
+        if self.voxel_exchange:
+            check(lib.fgs_voxel_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_vox_list"]), n, K0_DIM, pack, stream()))
+        else:
+            check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
+                                     self.Z, K0_DIM, pack, stream()))
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True):

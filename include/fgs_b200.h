@@ -159,6 +159,15 @@ int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp
                            int step, float beta1, float beta2, float lr, float eps,
                            fgs_stream_t stream);
 int64_t fgs_brick_list_ints(int X, int Y, int Z);
+/* Voxel-granular versions for the data-parallel exchange (only ~23 % of the voxels of a touched brick carry a
+ * gradient): voxel_flags has one byte per voxel of the [X][Y][Z][12] grid (FgsFineParams::k0_vox_flags, set by the
+ * backward scatter); fgs_voxel_list writes count + ascending voxel ids into voxel_list (fgs_voxel_list_ints(V) ints,
+ * the tail is scratch) with two launches over all SMs and clears the flags; fgs_voxel_copy gathers (pack != 0) /
+ * scatters the 12 channels of the first min(count, max_voxels) listed voxels to / from compact [count][12]. */
+int64_t fgs_voxel_list_ints(int64_t n_voxels);
+int fgs_voxel_list(uint8_t* voxel_flags, int64_t n_voxels, int32_t* voxel_list, fgs_stream_t stream);
+int fgs_voxel_copy(float* grid, float* compact, const int32_t* voxel_list, int max_voxels, int channels, int pack,
+                   fgs_stream_t stream);
 int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_list, fgs_stream_t stream);
 int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int max_bricks, int X, int Y,
                    int Z, int channels, int pack, fgs_stream_t stream);

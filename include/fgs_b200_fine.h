@@ -130,6 +130,8 @@ typedef struct FgsFineParams {
   float *dZ;         /* optional [6][cap_m2][256]: one buffer per hidden layer's pre-activation gradient, so the
                         backward-data chain runs as ONE launch and the 8 weight-gradient GEMMs follow it
                         (NULL: per-layer launches through the dA / dB ping-pong) */
+  uint8_t *k0_vox_flags; /* optional [X*Y*Z]: set to 1 by the backward scatter for every k0 voxel that received a
+                        gradient (data-parallel exchange at voxel granularity, fgs_voxel_list); NULL = not recorded */
 } FgsFineParams;
 
 /* size of FgsFineParams::w_split in floats */

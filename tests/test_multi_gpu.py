@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, voxel_exchange=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -27,15 +27,18 @@ def _worker(rank, world, port, q):
         sc = scene.make_scene(G=48, mask_G=40)
         rays = [t.to(dev) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
         a, b = ray_shard(N, world, rank)
-        eng = engine.FineStepEngine(sc, b - a, dev, world_size=world, rank=rank)
+        eng = engine.FineStepEngine(sc, b - a, dev, world_size=world, rank=rank, voxel_exchange=voxel_exchange)
         eng.set_nonempty_mask()
-        eng.train_step(*[t[a:b].contiguous() for t in rays], step, n_rays_global=N, has_last_ray=(rank == world - 1))
+        shard = [t[a:b].contiguous() for t in rays]
+        for k in range(2):             # two steps: the second one also checks that the exchange left flags / lists clean
+            eng.train_step(*shard, step + k, n_rays_global=N, has_last_ray=(rank == world - 1))
         torch.cuda.synchronize()
         out = None
         if rank == 0:
             ref = engine.FineStepEngine(sc, N, dev)
             ref.set_nonempty_mask()
-            ref.train_step(*rays, step)
+            for k in range(2):
+                ref.train_step(*rays, step + k)
             torch.cuda.synchronize()
             errs = {}
             t = eng.train_cfg
@@ -55,13 +58,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_step_equals_single_gpu_step():
+@pytest.mark.parametrize("voxel_exchange", [False, True])
+def test_two_gpu_step_equals_single_gpu_step(voxel_exchange):
+    """voxel_exchange: the touched part of g_k0 travels as packed 4^3 bricks (default) or as packed voxels."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 2000) + (1 if voxel_exchange else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, voxel_exchange)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in procs)

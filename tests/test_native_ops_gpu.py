@@ -292,3 +292,34 @@ def test_error_behaviour(cuda):
         ru.sample_pts_on_rays(ro.t().contiguous().t(), rd, mn, mx, 0.2, 1e9, 0.01)
     with pytest.raises(RuntimeError):
         ad.adam_upd(ro.double(), ro, ro, ro, 1, 0.9, 0.99, 1e-3, 1e-8)
+
+
+def test_voxel_list_and_copy():
+    """fgs_voxel_list (ascending ids of the flagged voxels, flags cleared, two launches over all SMs) and
+    fgs_voxel_copy (gather / scatter of 12 channels per listed voxel) against torch."""
+    import torch
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    dev = torch.device("cuda:0")
+    for n, p in ((48 ** 3, 0.02), (16384 * 3 + 777, 0.3), (1000, 0.0), (160 ** 3, 0.03)):
+        g = torch.Generator(device="cpu").manual_seed(n)
+        flags = (torch.rand(n, generator=g) < p).to(torch.uint8).to(dev)
+        want = flags.nonzero()[:, 0].to(torch.int32)
+        lst = torch.zeros(int(lib.fgs_voxel_list_ints(n)), dtype=torch.int32, device=dev)
+        check(lib.fgs_voxel_list(ptr(flags), n, ptr(lst), stream()))
+        torch.cuda.synchronize()
+        cnt = int(lst[0])
+        assert cnt == want.numel()
+        assert torch.equal(lst[1:1 + cnt], want)
+        assert int(flags.sum()) == 0, "flags must be cleared"
+        if cnt:
+            grid = torch.randn(n, 12, generator=g).to(dev)
+            compact = torch.zeros(cnt, 12, device=dev)
+            check(lib.fgs_voxel_copy(ptr(grid), ptr(compact), ptr(lst), cnt, 12, 1, stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(compact, grid[want.long()])
+            grid2 = torch.zeros_like(grid)
+            check(lib.fgs_voxel_copy(ptr(grid2), ptr(compact), ptr(lst), cnt, 12, 0, stream()))
+            torch.cuda.synchronize()
+            ref = torch.zeros_like(grid)
+            ref[want.long()] = grid[want.long()]
+            assert torch.equal(grid2, ref)
