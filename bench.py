@@ -179,7 +179,8 @@ def run_ours(args):
 
     N = args.rays
     sc = scene.make_scene(G=args.grid)
-    eng = engine.FineStepEngine(sc, N, dev, world_size=world, rank=rank, cap_m2_per_ray=args.cap_m2_per_ray)
+    eng = engine.FineStepEngine(sc, N, dev, world_size=world, rank=rank, cap_m2_per_ray=args.cap_m2_per_ray,
+                                voxel_exchange=(args.exchange == "voxels"))
     eng.set_nonempty_mask()
     nb = 4
     host = []
@@ -356,6 +357,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference arm / baseline")
     ap.add_argument("--cap-m2-per-ray", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="bricks", choices=["bricks", "voxels"],
+                    help="granularity of the data-parallel k0 gradient exchange (N > 1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

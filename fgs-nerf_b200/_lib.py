@@ -54,6 +54,8 @@ _SIGS = {
     "fgs_brick_list_ints": (_l, [_i, _i, _i]),
     "fgs_voxel_list_ints": (_l, [_l]),
     "fgs_voxel_list": (_i, [_p, _l, _p, _p]),
+    "fgs_voxel_bits_pack": (_i, [_p, _p, _l, _p]),
+    "fgs_voxel_bits_union_list": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "fgs_voxel_copy": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "fgs_brick_list": (_i, [_p, _i, _i, _i, _p, _p]),
     "fgs_brick_copy": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

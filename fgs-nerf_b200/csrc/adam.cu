@@ -481,6 +481,116 @@ voxel_write_kernel(unsigned char* __restrict__ flags, long long n, const int* __
   }
 }
 
+// ---- bit-packed variant: the union of the ranks' touched voxels travels as an all-gather of bit masks --------------
+// (a MAX all-reduce of the byte flags moves 8x the bytes through a reduction kernel).  Per rank: byte flags -> one
+// word per 32 voxels (flags cleared); after the all-gather every rank ORs the `world` masks, derives the touched-brick
+// byte flags from the union (they drive the brick Adam) and builds the ascending voxel list from the union words.
+__global__ void __launch_bounds__(kBlock)
+voxel_bits_pack_kernel(unsigned char* __restrict__ flags, uint32_t* __restrict__ bits, long long n_words) {
+  for (long long w = blockIdx.x * (long long)kBlock + threadIdx.x; w < n_words; w += (long long)gridDim.x * kBlock) {
+    uint4* __restrict__ src = reinterpret_cast<uint4*>(flags + 32 * w);
+    const uint4 a = src[0], b = src[1];
+    const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t m = (((x[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x[i]) & 0x80808080u;   // bit 8 j + 7 <=> byte j != 0
+      word |= (((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u)) << (4 * i);
+    }
+    bits[w] = word;
+    if (word) {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      src[0] = z;
+      src[1] = z;
+    }
+  }
+}
+
+constexpr int kBitsPerCtaWords = 2048;     // words (of 32 voxels) per CTA of the union / list kernels: 8 per thread
+
+// pass 1: union word = OR over the ranks (stored into slice 0), brick flags, per-CTA voxel counts
+__global__ void __launch_bounds__(kBlock)
+voxel_bits_union_kernel(uint32_t* __restrict__ bits_all, int world, long long n_words, int Y, int Z,
+                        unsigned char* __restrict__ brick_flags, int* __restrict__ cta_counts) {
+  __shared__ int s_warp[kBlock / 32];
+  const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
+  int cnt = 0;
+  for (int i = 0; i < kBitsPerCtaWords / kBlock; ++i) {
+    const long long w = (long long)blockIdx.x * kBitsPerCtaWords + i * kBlock + threadIdx.x;
+    if (w >= n_words) break;
+    uint32_t u = 0;
+    for (int r = 0; r < world; ++r) u |= bits_all[(long long)r * n_words + w];
+    bits_all[w] = u;
+    cnt += __popc(u);
+    if (u && brick_flags) {
+      // a nibble = 4 consecutive z voxels starting at a multiple of 4 (Z % 4 == 0): one brick
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if ((u >> (4 * q)) & 0xfu) {
+          const long long v = 32 * w + 4 * q;
+          const int z = (int)(v % Z);
+          const long long xy = v / Z;
+          const int y = (int)(xy % Y), x = (int)(xy / Y);
+          brick_flags[((x >> 2) * nbY + (y >> 2)) * nbZ + (z >> 2)] = 1;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane_id() == 0) s_warp[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kBlock / 32; ++w) t += s_warp[w];
+    cta_counts[blockIdx.x] = t;
+  }
+}
+
+// pass 2: ascending voxel ids from the union words (slice 0)
+__global__ void __launch_bounds__(kBlock)
+voxel_bits_list_kernel(const uint32_t* __restrict__ bits, long long n_words, const int* __restrict__ cta_counts,
+                       int* __restrict__ list) {
+  __shared__ int s_warp[kBlock / 32];
+  __shared__ int s_base;
+  if (threadIdx.x < 32) {
+    int t = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 32) t += cta_counts[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) s_base = t;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) list[0] = t + cta_counts[blockIdx.x];
+  }
+  // thread t owns the CONSECUTIVE words [8 t, 8 t + 8) of the CTA's range (ids stay ascending)
+  constexpr int kPer = kBitsPerCtaWords / kBlock;
+  uint32_t u[kPer];
+  int cnt = 0;
+  const long long w0 = (long long)blockIdx.x * kBitsPerCtaWords + (long long)threadIdx.x * kPer;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    u[i] = (w0 + i < n_words) ? bits[w0 + i] : 0u;
+    cnt += __popc(u[i]);
+  }
+  const int incl = warp_incl_scan(cnt);
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_warp[w] = incl;
+  __syncthreads();
+  int before = 0;
+  for (int i = 0; i < w; ++i) before += s_warp[i];
+  if (cnt) {
+    int o = 1 + s_base + before + incl - cnt;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      uint32_t x = u[i];
+      while (x) {
+        const int bit = __ffs(x) - 1;
+        x &= x - 1;
+        list[o++] = (int)(32 * (w0 + i) + bit);
+      }
+    }
+  }
+}
+
 // gather / scatter of the listed voxels' 12 gradient channels (3 float4 per voxel) to / from a compact buffer
 template <bool PACK>
 __global__ void __launch_bounds__(kBlock)
@@ -542,6 +652,33 @@ int fgs_voxel_list(uint8_t* voxel_flags, int64_t n_voxels, int32_t* voxel_list, 
   int rc = fgs::check_launch("voxel_count", st);
   if (rc) return rc;
   voxel_write_kernel<<<ctas, kVoxThreads, 0, st>>>(voxel_flags, n_voxels, counts, voxel_list);
+  return fgs::check_launch("voxel_list", st);
+}
+
+int fgs_voxel_bits_pack(uint8_t* voxel_flags, uint32_t* bits, int64_t n_voxels, fgs_stream_t stream) {
+  FGS_REQUIRE(n_voxels > 0 && (n_voxels % 32) == 0, "voxel bit masks need a voxel count that is a multiple of 32");
+  FGS_REQUIRE((((uintptr_t)voxel_flags) & 15) == 0, "voxel_flags must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  FGS_PREFER_MAX_SHARED(voxel_bits_pack_kernel);
+  voxel_bits_pack_kernel<<<fgs::stream_grid(n_voxels / 32, kBlock, 8), kBlock, 0, st>>>(voxel_flags, bits, n_voxels / 32);
+  return fgs::check_launch("voxel_bits_pack", st);
+}
+
+int fgs_voxel_bits_union_list(uint32_t* bits_all, int world, int X, int Y, int Z, uint8_t* brick_flags,
+                              int32_t* voxel_list, fgs_stream_t stream) {
+  const int64_t n_voxels = (int64_t)X * Y * Z;
+  FGS_REQUIRE(world >= 1 && X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0 && (n_voxels % 32) == 0,
+              "voxel bit masks need Z % 4 == 0 and a voxel count that is a multiple of 32");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n_words = n_voxels / 32;
+  const int ctas = (int)((n_words + kBitsPerCtaWords - 1) / kBitsPerCtaWords);
+  int* counts = voxel_list + 1 + n_voxels;                     // scratch tail of fgs_voxel_list_ints()
+  FGS_PREFER_MAX_SHARED(voxel_bits_union_kernel);
+  FGS_PREFER_MAX_SHARED(voxel_bits_list_kernel);
+  voxel_bits_union_kernel<<<ctas, kBlock, 0, st>>>(bits_all, world, n_words, Y, Z, brick_flags, counts);
+  int rc = fgs::check_launch("voxel_bits_union", st);
+  if (rc) return rc;
+  voxel_bits_list_kernel<<<ctas, kBlock, 0, st>>>(bits_all, n_words, counts, voxel_list);
   return fgs::check_launch("voxel_list", st);
 }
 

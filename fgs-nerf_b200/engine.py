@@ -300,6 +300,10 @@ class FineStepEngine:
         if self.voxel_exchange:
             ws["k0_vox_flags"] = torch.zeros(X * Y * Z, dtype=torch.uint8, device=dev)
             ws["k0_vox_list"] = torch.zeros(int(lib.fgs_voxel_list_ints(X * Y * Z)), dtype=i32, device=dev)
+            # bit masks of the touched voxels of every rank (all-gather target), when the grid allows it
+            self.voxel_bits = (X * Y * Z) % 32 == 0
+            if self.voxel_bits:
+                ws["k0_vox_bits"] = torch.zeros(self.world_size, X * Y * Z // 32, dtype=i32, device=dev)
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         self._brick_list_ready = False
         self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -622,6 +626,23 @@ class FineStepEngine:
         the way to the host."""
         import torch.distributed as dist
         ws = self.ws
+        if self.voxel_exchange and self.voxel_bits:
+            # union of the touched voxels as an all-gather of bit masks (512 KB per rank at 160^3); the union's
+            # touched bricks (for the brick Adam) are derived from it: no other collective before the big one
+            V = self.X * self.Y * self.Z
+            bits = ws["k0_vox_bits"]
+            with torch.cuda.device(self.device):
+                check(lib.fgs_voxel_bits_pack(ptr(ws["k0_vox_flags"]), ptr(bits[self.rank]), V, stream()))
+            dist.all_gather_into_tensor(bits.view(-1), bits[self.rank])
+            with torch.cuda.device(self.device):
+                st = stream()
+                check(lib.fgs_memset_zero(ptr(ws["k0_brick_flags"]), ws["k0_brick_flags"].numel(), st))
+                check(lib.fgs_voxel_bits_union_list(ptr(bits), self.world_size, self.X, self.Y, self.Z,
+                                                    ptr(ws["k0_brick_flags"]), ptr(ws["k0_vox_list"]), st))
+                check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
+                self._count_host.copy_(ws["k0_vox_list"][:1], non_blocking=True)
+                self._count_evt.record()
+            return
         dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
         if not self.sparse_k0:
             return

@@ -165,6 +165,14 @@ int64_t fgs_brick_list_ints(int X, int Y, int Z);
  * the tail is scratch) with two launches over all SMs and clears the flags; fgs_voxel_copy gathers (pack != 0) /
  * scatters the 12 channels of the first min(count, max_voxels) listed voxels to / from compact [count][12]. */
 int64_t fgs_voxel_list_ints(int64_t n_voxels);
+/* Bit-packed variant for the multi-rank union: fgs_voxel_bits_pack turns the byte flags into one word per 32 voxels
+ * (and clears them); after an all-gather of the ranks' masks into bits_all [world][n_voxels / 32],
+ * fgs_voxel_bits_union_list ORs them (union left in slice 0), sets the touched-brick byte flags of the union (may be
+ * NULL) and writes count + ascending voxel ids into voxel_list (fgs_voxel_list_ints ints).  Needs Z % 4 == 0 and
+ * X*Y*Z % 32 == 0. */
+int fgs_voxel_bits_pack(uint8_t* voxel_flags, uint32_t* bits, int64_t n_voxels, fgs_stream_t stream);
+int fgs_voxel_bits_union_list(uint32_t* bits_all, int world, int X, int Y, int Z, uint8_t* brick_flags,
+                              int32_t* voxel_list, fgs_stream_t stream);
 int fgs_voxel_list(uint8_t* voxel_flags, int64_t n_voxels, int32_t* voxel_list, fgs_stream_t stream);
 int fgs_voxel_copy(float* grid, float* compact, const int32_t* voxel_list, int max_voxels, int channels, int pack,
                    fgs_stream_t stream);

@@ -323,3 +323,33 @@ def test_voxel_list_and_copy():
             ref = torch.zeros_like(grid)
             ref[want.long()] = grid[want.long()]
             assert torch.equal(grid2, ref)
+
+
+def test_voxel_bit_masks_union_list():
+    """fgs_voxel_bits_pack + fgs_voxel_bits_union_list: byte flags -> bit masks, OR over `world` masks, touched-brick
+    flags of the union, ascending voxel list -- against torch."""
+    import torch
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    dev = torch.device("cuda:0")
+    for (X, Y, Z), world in (((48, 48, 48), 2), ((16, 20, 32), 3), ((160, 160, 160), 8)):
+        V = X * Y * Z
+        g = torch.Generator(device="cpu").manual_seed(V + world)
+        masks = [(torch.rand(V, generator=g) < 0.01) for _ in range(world)]
+        bits = torch.zeros(world, V // 32, dtype=torch.int32, device=dev)
+        for r, m in enumerate(masks):
+            flags = m.to(torch.uint8).to(dev)
+            check(lib.fgs_voxel_bits_pack(ptr(flags), ptr(bits[r]), V, stream()))
+            torch.cuda.synchronize()
+            assert int(flags.sum()) == 0, "byte flags must be cleared"
+        union = torch.stack(masks).any(0).to(dev)
+        want = union.nonzero()[:, 0].to(torch.int32)
+        nb = ((X + 3) // 4, (Y + 3) // 4, (Z + 3) // 4)
+        brick_flags = torch.zeros(nb[0] * nb[1] * nb[2], dtype=torch.uint8, device=dev)
+        lst = torch.zeros(int(lib.fgs_voxel_list_ints(V)), dtype=torch.int32, device=dev)
+        check(lib.fgs_voxel_bits_union_list(ptr(bits), world, X, Y, Z, ptr(brick_flags), ptr(lst), stream()))
+        torch.cuda.synchronize()
+        cnt = int(lst[0])
+        assert cnt == want.numel() and torch.equal(lst[1:1 + cnt], want)
+        u3 = union.reshape(X, Y, Z)
+        want_bricks = torch.nn.functional.max_pool3d(u3[None, None].float(), 4, 4, ceil_mode=True)[0, 0].reshape(-1) > 0
+        assert torch.equal(brick_flags.bool(), want_bricks)
