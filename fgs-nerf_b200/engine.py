@@ -100,6 +100,9 @@ _lib.declare("fgs_set_mlp_fusion", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_chain_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_set_mlp_dw_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
+_i = C.c_int
+_lib.declare("fgs_grid_resize_trilinear", C.c_int, [_fp, _i, _i, _i, _i, _fp, _i, _i, _i, _i, _fp])
+_lib.declare("fgs_gather_rays", C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _i, _fp, _fp, _fp, _fp, _fp, _fp])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
@@ -166,6 +169,40 @@ def grid_sample_backward(grid_shape, channels_last, xyz, xyz_min, xyz_max, grad_
     return grad_grid
 
 
+def grid_resize(grid, new_world_size):
+    """DenseGrid.scale_volume_grid (model/grid.py:101-106): F.interpolate(grid [1,C,X,Y,Z], size, 'trilinear',
+    align_corners=True) as one streaming kernel.  A channels_last_3d grid (the engine's k0) stays channels_last_3d."""
+    _lib.check_input(grid if grid.is_contiguous() else grid.permute(0, 2, 3, 4, 1), "grid", torch.float32)
+    if grid.dim() != 5 or grid.shape[0] != 1:
+        raise RuntimeError(f"grid must be [1,C,X,Y,Z], got {tuple(grid.shape)}")
+    Cn, X, Y, Z = (int(v) for v in grid.shape[1:])
+    X2, Y2, Z2 = (int(v) for v in new_world_size)
+    cl = int(not grid.is_contiguous())
+    out = torch.empty((1, Cn, X2, Y2, Z2), dtype=torch.float32, device=grid.device,
+                      memory_format=torch.channels_last_3d if cl else torch.contiguous_format)
+    with torch.cuda.device(grid.device):
+        check(lib.fgs_grid_resize_trilinear(ptr(grid), Cn, X, Y, Z, ptr(out), X2, Y2, Z2, cl, stream()))
+    return out
+
+
+def gather_rays(rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, sel, out=None, bad=None):
+    """The four `x_tr[sel_i]` selections of the training loop (model/nerf_training.py:253-258) in one launch.
+    sel: int64 [n] on the device.  Returns rays_o, rays_d, viewdirs, target [n,3]."""
+    n_total = rays_o_tr.shape[0]
+    for t, name in ((rays_o_tr, "rays_o_tr"), (rays_d_tr, "rays_d_tr"), (viewdirs_tr, "viewdirs_tr"), (rgb_tr, "rgb_tr")):
+        _lib.check_input(t, name, torch.float32)
+        if tuple(t.shape) != (n_total, 3):
+            raise RuntimeError(f"{name} must be [{n_total},3], got {tuple(t.shape)}")
+    _lib.check_input(sel, "sel", torch.int64)
+    n = sel.numel()
+    if out is None:
+        out = tuple(torch.empty((n, 3), dtype=torch.float32, device=sel.device) for _ in range(4))
+    with torch.cuda.device(sel.device):
+        check(lib.fgs_gather_rays(ptr(rays_o_tr), ptr(rays_d_tr), ptr(viewdirs_tr), ptr(rgb_tr), n_total, ptr(sel), n,
+                                  ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(bad), stream()))
+    return out
+
+
 def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None, tc=False,
          bits_in=None, bits_out=None):
     """fgs_gemm / fgs_gemm_tc on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
@@ -201,6 +238,12 @@ class FineStepEngine:
         self.train_cfg = dict(train_cfg if train_cfg is not None else FINE_TRAIN)
         self.n_rays = int(n_rays)
         self.world_size, self.rank = int(world_size), int(rank)
+        self._ctor = dict(n_rays=int(n_rays), device=device, train_cfg=self.train_cfg, cap_m1_per_ray=cap_m1_per_ray,
+                          cap_m2_per_ray=cap_m2_per_ray, world_size=int(world_size), rank=int(rank),
+                          voxel_exchange=voxel_exchange)
+        # learning rates of the four param groups (python floats that the training loop multiplies step by step,
+        # model/nerf_training.py:389-414; create_optimizer_or_freeze_model, :9-37)
+        self.lr = {k: float(self.train_cfg["lrate_" + k]) for k in ("sdf", "k0", "rgbnet", "refnet")}
         f32 = torch.float32
         # ---- parameters ----
         self.xyz_min = scene.xyz_min.clone().float()
@@ -230,6 +273,7 @@ class FineStepEngine:
         self.Bt = [b.to(dev, f32).contiguous().clone() for _, b in layers]
         X, Y, Z = self.sdf.shape[2:]
         self.X, self.Y, self.Z = X, Y, Z
+        self.num_voxels = X * Y * Z          # model.num_voxels (scale_volume_grid multiplies it by scale_ratio)
         # ---- gradients + Adam state ----
         self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
         # all 16 MLP gradient tensors are views of one flat buffer (one clear, one all-reduce bucket)
@@ -544,6 +588,44 @@ class FineStepEngine:
             check(lib.fgs_total_variation_add_grad(ptr(self.sdf), ptr(self.g_sdf), None, w, w, w, 1, self.X, self.Y,
                                                    self.Z, int(dense), 0, stream()))
 
+    def reset_optimizer(self, global_step=0):
+        """create_optimizer_or_freeze_model (model/nerf_training.py:9-37): fresh MaskedAdam state, learning rates
+        back to lrate_* x 0.1^(global_step / (lrate_decay * 1000))."""
+        t = self.train_cfg
+        decay = 0.1 ** (global_step / (t.get("lrate_decay", 20) * 1000))
+        self.lr = {k: float(t["lrate_" + k]) * decay for k in ("sdf", "k0", "rgbnet", "refnet")}
+        self.adam = {}
+        self.adam_step = 0
+
+    @torch.no_grad()
+    def scale_volume_grid(self, num_voxels):
+        """nerf.scale_volume_grid (model/nerf.py:369-381) with _set_grid_resolution (:298-303): new voxel size and
+        world size from `num_voxels`, SDF and k0 resampled trilinearly (fgs_grid_resize_trilinear), non-empty mask
+        recomputed.  Every grid-sized buffer changes shape, so this returns a NEW engine that shares the MLPs'
+        values; the optimiser starts fresh like the reference's (nerf_training.py:254)."""
+        from .scene import Scene
+        ext = (self.xyz_max - self.xyz_min).float()
+        voxel_size = (ext.prod() / num_voxels).pow(1 / 3)                 # fp32 tensor arithmetic, as the reference
+        world_size = (ext / voxel_size).long().tolist()
+        sdf = grid_resize(self.sdf, world_size)
+        k0 = grid_resize(self.k0, world_size)
+        sc = Scene(G=int(world_size[0]), xyz_min=self.xyz_min, xyz_max=self.xyz_max, voxel_size=float(voxel_size),
+                   sdf=sdf, k0=k0, mask_grid=self.mask_grid, mask_xyz_min=self.mask_xyz_min,
+                   mask_xyz_max=self.mask_xyz_max, mask_thres=float(self.mask_thres),
+                   rgbnet=[(w, b) for w, b in zip(self.weights[:4], self.Bt[:4])],
+                   refnet=[(w, b) for w, b in zip(self.weights[4:], self.Bt[4:])], cfg=dict(self.cfg))
+        had_mask = self.nonempty_mask is not None
+        ctor = dict(self._ctor)
+        # drop this engine's grid-sized buffers before the new ones are allocated (256^3: 0.8 GB per k0-sized tensor)
+        self.sdf = self.k0 = self.g_k0 = self._xbuf = self.g_sdf = self._compact = None
+        self.adam, self.tv_scratch, self.nonempty_mask = {}, None, None
+        new = FineStepEngine(sc, **ctor)
+        new.num_voxels = num_voxels
+        if had_mask:
+            new.set_nonempty_mask()
+        new.reset_optimizer(0)
+        return new
+
     def _ensure_adam(self):
         """Adam state (allocated and zeroed on the calling stream, before any side-stream use)."""
         if self.adam:
@@ -579,7 +661,7 @@ class FineStepEngine:
             m, v = self.adam["sdf"]
             # sdf: dense Adam (not in skip_zero_grad_fields), gradient cleared by the same kernel
             check(lib.fgs_adam_upd_zero_grad(ptr(self.sdf), ptr(self.g_sdf), ptr(m), ptr(v), self.sdf.numel(), step,
-                                             b1, b2, t["lrate_sdf"] * lr_scale, eps, st))
+                                             b1, b2, self.lr["sdf"] * lr_scale, eps, st))
             m, v = self.adam["k0"]
             if self.sparse_k0:
                 # k0: masked Adam over the touched bricks only; clears the gradients / flags it consumed
@@ -588,11 +670,11 @@ class FineStepEngine:
                                              ptr(self.ws["k0_brick_list"]), st))
                 self._brick_list_ready = False
                 check(lib.fgs_adam_upd_bricks(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), ptr(self.ws["k0_brick_list"]),
-                                              self.X, self.Y, self.Z, K0_DIM, step, b1, b2, t["lrate_k0"] * lr_scale,
+                                              self.X, self.Y, self.Z, K0_DIM, step, b1, b2, self.lr["k0"] * lr_scale,
                                               eps, st))
             else:
                 check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
-                                       b1, b2, t["lrate_k0"] * lr_scale, eps, 1, st))
+                                       b1, b2, self.lr["k0"] * lr_scale, eps, 1, st))
                 check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
                 check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
             self._grads_clean = True
@@ -602,7 +684,7 @@ class FineStepEngine:
     def _adam_mlp(self, step, lr_scale, b1, b2, eps, st):
         t = self.train_cfg
         n = 2 * MLP_LAYERS
-        lrs = [t["lrate_rgbnet"]] * 4 + [t["lrate_refnet"]] * 4
+        lrs = [self.lr["rgbnet"]] * 4 + [self.lr["refnet"]] * 4
         lrs = (C.c_float * n)(*[x * lr_scale for x in lrs + lrs])
         steps = (C.c_int * n)(*([step] * n))
         mt = self._mt

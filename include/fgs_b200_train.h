@@ -1,0 +1,46 @@
+/*
+ * fgs_b200_train.h -- C-ABI of the pieces AROUND the per-ray step that SURVEY.md 8(f) ranks next:
+ * the training loop's batch gather (f2) and the progressive grid scaling between stages (f3).
+ * Same conventions as fgs_b200.h: device pointers, dense fp32, enqueue-only, 0 on success.
+ */
+#ifndef FGS_B200_TRAIN_H
+#define FGS_B200_TRAIN_H
+
+#include "fgs_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Progressive scaling  (reference: DenseGrid.scale_volume_grid, model/grid.py:101-106, called by
+ * nerf.scale_volume_grid, model/nerf.py:369-381, at the pg_scale iterations, nerf_training.py:244-254)
+ *
+ *   dst[1,C,X2,Y2,Z2] = F.interpolate(src[1,C,X,Y,Z], size=(X2,Y2,Z2), mode='trilinear', align_corners=True)
+ *
+ * ATen's upsample_trilinear3d arithmetic (float scale = (in-1)/(out-1), 0 when out == 1; source index
+ * = scale * dst index; truncation; lambda1 = frac, lambda0 = 1 - lambda1; nested w -> h -> d
+ * blend).  channels_last = 0: both tensors contiguous NCDHW (the reference layout, the SDF grid);
+ * channels_last = 1: both in torch.channels_last_3d storage, C innermost (the engine's k0 layout;
+ * needs C % 4 == 0).  One streaming pass: every output element is written once with 128-bit stores,
+ * the (smaller) source is read through L1 / L2.
+ * ------------------------------------------------------------------------------------ */
+int fgs_grid_resize_trilinear(const float* src, int C, int X, int Y, int Z, float* dst, int X2, int Y2,
+                              int Z2, int channels_last, fgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Batch gather  (reference: the `flatten` / `in_maskcache` ray sampler of the training loop,
+ * model/nerf_training.py:253-258:  target = rgb_tr[sel_i]; rays_o = rays_o_tr[sel_i]; ... )
+ *
+ * sel [n] int64 indices into the flattened training rays [n_total,3]; the four selections are one
+ * launch.  Indices outside [0, n_total) are an error in the reference (device assert); here they set
+ * *bad (device int32, may be NULL) to 1 and the row is zero-filled.
+ * ------------------------------------------------------------------------------------ */
+int fgs_gather_rays(const float* rays_o_tr, const float* rays_d_tr, const float* viewdirs_tr,
+                    const float* rgb_tr, int64_t n_total, const int64_t* sel, int n, float* rays_o,
+                    float* rays_d, float* viewdirs, float* target, int32_t* bad, fgs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGS_B200_TRAIN_H */
