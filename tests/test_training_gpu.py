@@ -1,0 +1,250 @@
+"""GPU tests of the between-step operators and the training-loop host side,
+through the C-ABI of include/fgs_b200_train.h:
+  * fgs_grid_resize_trilinear against torch's CUDA F.interpolate (the reference's call, model/grid.py:106)
+    and against the numpy oracle (oracle/stage_ref.py);
+  * fgs_gather_rays against torch indexing (bit-exact: it moves bytes);
+  * FineTrainer against the same iterations issued by hand with the ORACLE's batches and learning rates,
+    and its second iteration against the oracle's own step (oracle/nerf_ref.py + the reference's kernels);
+  * a pg_scale iteration: grids resampled as the reference does, optimiser re-created."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import nerf_ref as R  # noqa: E402
+from oracle import ref_ext, stage_ref  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("C,cl,src,dst", [
+    (1, False, (48, 48, 48), (77, 77, 77)),        # odd Z2: scalar stores
+    (1, False, (40, 40, 40), (64, 64, 64)),        # 128-bit stores
+    (12, True, (20, 20, 20), (52, 52, 52)),        # the engine's k0 layout
+    (12, False, (16, 12, 20), (24, 30, 28)),       # reference layout, non-cubic
+    (3, False, (9, 9, 9), (1, 5, 9)),              # an axis of output size 1 (scale 0), an identity axis
+    (4, True, (10, 10, 10), (7, 6, 5)),            # shrinking
+])
+def test_grid_resize_matches_aten_and_oracle(cuda, C, cl, src, dst):
+    from fgs_nerf_b200 import engine
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, C, *src, generator=g)
+    xd = x.to(cuda)
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last_3d)
+    got = engine.grid_resize(xd, dst)
+    assert tuple(got.shape) == (1, C, *dst)
+    assert got.is_contiguous() != cl or C == 1
+    want = F.interpolate(x.to(cuda), size=dst, mode="trilinear", align_corners=True)
+    scale = max(1.0, float(want.abs().max()))
+    err = float((got - want).abs().max())
+    assert err <= 2e-6 * scale, f"vs torch CUDA F.interpolate: {err:.3e}"
+    orc = torch.from_numpy(stage_ref.grid_resize_trilinear(x[0].numpy(), dst))[None]
+    err = float((got.cpu() - orc).abs().max())
+    assert err <= 2e-6 * scale, f"vs the numpy oracle: {err:.3e}"
+    print("bit-identical to torch CUDA:", float((got == want).float().mean()))
+
+
+def test_grid_resize_full_size_properties(cuda):
+    """160^3 -> 256^3 (the pg_scale step of config/shiny_blender.py:203-204) on the 12-channel k0 layout:
+    the first corner is copied exactly, a linear ramp stays a linear ramp, the range does not widen."""
+    from fgs_nerf_b200 import engine
+    G, G2 = 160, 256
+    lin = torch.linspace(-1, 1, G, device=cuda)
+    ramp = (0.25 * lin[:, None, None] - 0.5 * lin[None, :, None] + lin[None, None, :])
+    x = torch.randn(1, 12, G, G, G, device=cuda, generator=torch.Generator(device=cuda).manual_seed(3))
+    x[0, 0] = ramp
+    xc = x.contiguous(memory_format=torch.channels_last_3d)
+    y = engine.grid_resize(xc, (G2, G2, G2))
+    assert torch.equal(y[0, :, 0, 0, 0], x[0, :, 0, 0, 0])      # index 0: weights exactly (1, 0) on every axis
+    assert float((y[0, :, -1, -1, -1] - x[0, :, -1, -1, -1]).abs().max()) < 1e-4   # fl(159/255)*255 need not be 159
+    lin2 = torch.linspace(-1, 1, G2, device=cuda)
+    ramp2 = (0.25 * lin2[:, None, None] - 0.5 * lin2[None, :, None] + lin2[None, None, :])
+    assert float((y[0, 0] - ramp2).abs().max()) < 2e-6
+    assert float(y.max()) <= float(x.max()) + 1e-5 and float(y.min()) >= float(x.min()) - 1e-5
+    want = F.interpolate(x[:, 1:3], size=(G2, G2, G2), mode="trilinear", align_corners=True)
+    assert float((y[:, 1:3] - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+def test_grid_resize_rejects_bad_arguments(cuda):
+    from fgs_nerf_b200 import engine
+    with pytest.raises(RuntimeError):
+        engine.grid_resize(torch.zeros(1, 1, 4, 4, 4), (8, 8, 8))                     # not a CUDA tensor
+    with pytest.raises(RuntimeError):
+        engine.grid_resize(torch.zeros(2, 1, 4, 4, 4, device=cuda), (8, 8, 8))       # batch must be 1
+    with pytest.raises(RuntimeError):
+        engine.grid_resize(torch.zeros(1, 1, 4, 4, 4, device=cuda), (8, 0, 8))       # empty output
+
+
+def test_gather_rays_matches_indexing(cuda):
+    from fgs_nerf_b200 import engine
+    g = torch.Generator().manual_seed(21)
+    n_total, n = 5000, 777
+    arrs = [torch.randn(n_total, 3, generator=g).to(cuda) for _ in range(4)]
+    sel = torch.randint(0, n_total, (n,), generator=g).to(cuda)
+    bad = torch.zeros(1, dtype=torch.int32, device=cuda)
+    out = engine.gather_rays(*arrs, sel, bad=bad)
+    for o, a in zip(out, arrs):
+        assert torch.equal(o, a[sel])
+    assert int(bad.item()) == 0
+    want = stage_ref.gather_rays(*[a.cpu().numpy() for a in arrs], sel.cpu().numpy())
+    for o, w in zip(out, want):
+        assert np.array_equal(o.cpu().numpy(), w)
+    sel2 = sel.clone()
+    sel2[5] = n_total                                   # one past the end: flagged, row zero-filled, rest intact
+    out2 = engine.gather_rays(*arrs, sel2, bad=bad)
+    assert int(bad.item()) == 1
+    assert float(out2[0][5].abs().sum()) == 0.0 and torch.equal(out2[0][6:], arrs[0][sel[6:]])
+    empty = engine.gather_rays(*arrs, sel[:0])
+    assert empty[0].shape == (0, 3)
+
+
+def _training_rays(cuda, n_total):
+    from fgs_nerf_b200 import scene
+    return [t.to(cuda) for t in scene.make_rays(N=n_total, H=100, W=100, n_views=8)]
+
+
+def _frac_differing(a, b, before, lr):
+    """Share of parameters whose accumulated update differs by more than Adam's noise floor (an entry whose gradient
+    is at rounding-noise level moves by ~lr in a direction rounding decides; see test_fine_gpu)."""
+    d_a, d_b = (a.detach() - before).float(), (b.detach() - before).float()
+    return float(((d_a - d_b).abs() > 1e-3 * lr + 1e-4 * d_b.abs()).float().mean())
+
+
+def test_trainer_equals_hand_issued_iterations(cuda):
+    """FineTrainer.run(3) against three engine.train_step calls fed by the ORACLE: batches from torch indexing with the
+    reference generator's indices, learning rates from oracle RefSchedule (pinned to the reference's block on the CPU)."""
+    from fgs_nerf_b200 import engine, scene, training
+    N, n_total, K = 192, 1500, 3
+    cfg = dict(scene.FINE_TRAIN, tv_every=2, N_rand=N, lrate_decay=20, N_iters=20000, cosine_lr=True,
+               cosine_lr_cfg=dict(warm_up_iters=0, const_warm_up=True, warm_up_min_ratio=1.0),
+               decay_step_module={4999: dict(sdf=0.1)}, pg_scale=[])     # keyed on global_step - 1: after iteration 5000
+    rays = _training_rays(cuda, n_total)
+    sc = scene.make_scene(G=48, mask_G=40)
+    start = 4999
+
+    eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
+    eng.set_nonempty_mask()
+    tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=start, rng=np.random.RandomState(7))
+    assert tr.run(K) == start + K
+    st = tr.stats()
+    assert st["steps"] == [start + 1, start + 2, start + 3] and np.isfinite(st["psnr"]) and st["terms"].shape == (K, 5)
+
+    ref_t = dict(cfg, tv_terms=dict(sdf_tv=cfg["sdf_tv"], smooth_grad_tv=cfg["smooth_grad_tv"]))
+    sch = stage_ref.RefSchedule(ref_t)
+    sch._fresh_optimizer(start)                        # create_optimizer_or_freeze_model(global_step=start)
+    eng2 = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(cfg))
+    eng2.set_nonempty_mask()
+    gen = training.batch_indices_generator(n_total, N, rng=np.random.RandomState(7))
+    losses = []
+    for i in range(K):
+        gs = start + 1 + i
+        sel = torch.from_numpy(next(gen)).to(cuda)
+        ro, rd, vd, tgt = [r[sel].contiguous() for r in rays]
+        eng2.lr = dict(sch.lr)
+        eng2.train_step(ro, rd, vd, tgt, gs)
+        torch.cuda.synchronize()
+        losses.append(eng2.ws["loss"].cpu().numpy().copy())
+        sch.iteration(gs)
+    assert tr.engine.lr == pytest.approx(sch.lr, rel=1e-13)
+    assert sch.lr["sdf"] < 0.11 * sch.lr["k0"] * cfg["lrate_sdf"] / cfg["lrate_k0"]      # decay_step_module applied
+    # the scatter-adds are float atomics, so two runs agree to rounding (amplified by Adam where a gradient is
+    # itself rounding noise), not bit for bit: first iteration tight, later ones to 1e-3
+    assert np.allclose(st["terms"][0], losses[0], rtol=1e-6, atol=1e-12)
+    assert np.allclose(st["terms"], np.stack(losses), rtol=1e-3, atol=1e-7)
+    for name, a, b, lr in (("sdf", tr.engine.sdf, eng2.sdf, cfg["lrate_sdf"]), ("k0", tr.engine.k0, eng2.k0, cfg["lrate_k0"]),
+                           ("W0", tr.engine.weights[0], eng2.weights[0], 1e-3), ("W7", tr.engine.weights[7], eng2.weights[7], 1e-3)):
+        before = {"sdf": sc.sdf, "k0": sc.k0, "W0": sc.rgbnet[0][0], "W7": sc.refnet[3][0]}[name].to(cuda)
+        frac = _frac_differing(a, b, before, lr)
+        assert frac < 1e-2, f"{name}: {frac:.5f} of the parameters differ after {K} iterations"
+
+
+def test_trainer_second_iteration_against_oracle_step(cuda):
+    """Two iterations of the trainer against two of the oracle's steps (oracle/nerf_ref.py with the reference's
+    compiled kernels), the second one with a learning rate the schedule has changed (sdf x0.1)."""
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    from fgs_nerf_b200 import engine, scene, training
+    N, n_total = 192, 1500
+    cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, decay_step_module={5000: dict(sdf=0.1)}, pg_scale=[])
+    rays = _training_rays(cuda, n_total)
+    sc = scene.make_scene(G=48, mask_G=40)
+    start = 5000
+    eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
+    eng.set_nonempty_mask()
+    tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=start, rng=np.random.RandomState(9))
+    tr.run(2)
+    torch.cuda.synchronize()
+
+    native = R.RefCudaNative()
+    m = R.FineModel(sc, device=cuda)
+    m.set_nonempty_mask()
+    opt = R.RefOptimizer(m, cfg, native)
+    sch = stage_ref.RefSchedule(dict(cfg, tv_terms=dict(sdf_tv=cfg["sdf_tv"], smooth_grad_tv=cfg["smooth_grad_tv"])))
+    sch._fresh_optimizer(start)
+    gen = training.batch_indices_generator(n_total, N, rng=np.random.RandomState(9))
+    before = {k: v.detach().clone() for k, v in m.params()}
+    for gs in (start + 1, start + 2):
+        sel = torch.from_numpy(next(gen)).to(cuda)
+        ro, rd, vd, tgt = [r[sel].contiguous() for r in rays]
+        for g in opt.groups:
+            g["lr"] = sch.lr[g["name"].split(".")[0]]
+        R.train_step(m, native, opt, ro, rd, vd, tgt, gs, cfg, near=2.0, stepsize=0.5, bg=1.0)
+        sch.iteration(gs)
+    ref = dict(m.params())
+    assert sch.lr["sdf"] == pytest.approx(tr.engine.lr["sdf"], rel=1e-13)
+    for name, mine, lr in (("sdf", tr.engine.sdf, cfg["lrate_sdf"]), ("k0", tr.engine.k0, cfg["lrate_k0"]),
+                           ("rgbnet.0.weight", tr.engine.weights[0], 1e-3), ("refnet.3.weight", tr.engine.weights[7], 1e-3)):
+        frac = _frac_differing(mine, ref[name], before[name], lr)
+        assert frac < 2e-2, f"{name}: {frac:.5f} of the two-iteration updates differ from the oracle's"
+    # the sdf step of iteration 2 used a tenth of the rate: |update| <= lr1 + 1.001 lr2 (Adam's bias-corrected ratio
+    # is at most 1.001 at step 2), where two full-rate steps would reach 2 lr1
+    lr1 = cfg["lrate_sdf"] * 0.1 ** (start / 20000)
+    d = (tr.engine.sdf - before["sdf"]).abs().max()
+    assert float(d) <= lr1 * (1.0 + 0.1 * 1.001) * 1.02
+    assert float(d) >= lr1 * 0.99
+
+
+def test_pg_scale_iteration_rescales_grids_and_restarts_optimizer(cuda):
+    from fgs_nerf_b200 import engine, scene, training
+    N, n_total = 192, 1500
+    ratio = (64 / 48) ** 3
+    cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, pg_scale=[5002], scale_ratio=ratio)
+    rays = _training_rays(cuda, n_total)
+    sc = scene.make_scene(G=48, mask_G=40)
+    eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
+    eng.set_nonempty_mask()
+    tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=5000, rng=np.random.RandomState(1))
+    tr.step()
+    torch.cuda.synchronize()
+    sdf_before, k0_before = tr.engine.sdf.clone(), tr.engine.k0.clone()
+    assert tr.engine.adam_step == 1
+    # what the reference computes (model/nerf.py:298-303, 369-381; model/grid.py:101-106)
+    ext = (sc.xyz_max - sc.xyz_min).float()
+    vs = (ext.prod() / (48 ** 3 * ratio)).pow(1 / 3)
+    ws = (ext / vs).long().tolist()
+    want_sdf = F.interpolate(sdf_before, size=tuple(ws), mode="trilinear", align_corners=True)
+    want_k0 = F.interpolate(k0_before.contiguous(), size=tuple(ws), mode="trilinear", align_corners=True)
+    new = tr.engine.scale_volume_grid(tr.engine.num_voxels * ratio)       # the call step() makes at a pg_scale iteration
+    assert [new.X, new.Y, new.Z] == ws and abs(float(new.voxel_size) - float(vs)) < 1e-9
+    assert float((new.sdf - want_sdf).abs().max()) <= 2e-6 * float(want_sdf.abs().max())
+    assert float((new.k0 - want_k0).abs().max()) <= 2e-6 * float(want_k0.abs().max())
+    assert new.nonempty_mask is not None and tuple(new.nonempty_mask.shape) == tuple(ws)
+    assert new.adam_step == 0 and not new.adam and new.lr == {k: cfg["lrate_" + k] for k in new.lr}
+    for a, b in zip(new.weights, tr.engine.weights):
+        assert torch.equal(a, b)
+    # ... and through the loop: iteration 5002 rescales, trains on, with a fresh optimiser
+    tr2 = training.FineTrainer(engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN)), *rays, cfg_train=cfg,
+                               start=5000, rng=np.random.RandomState(1))
+    tr2.engine.set_nonempty_mask()
+    tr2.run(3)
+    st = tr2.stats()
+    assert [tr2.engine.X, tr2.engine.Y, tr2.engine.Z] == ws
+    assert tr2.engine.adam_step == 2 and np.isfinite(st["terms"]).all() and st["terms"][:, 0].min() > 0
+    f = 0.1 ** (1 / 20000)
+    assert tr2.engine.lr["k0"] == pytest.approx(cfg["lrate_k0"] * f * f, rel=1e-12)
+    assert tr2.engine.counters()["M2"] > 0

@@ -1,0 +1,86 @@
+"""Dry run of the Python host paths (engine.scale_volume_grid, FineTrainer) WITHOUT a GPU: torch.cuda's
+stream / event objects are replaced by dummies, the engine's device check is lifted and every C-ABI return code is
+ignored (the launches fail with 'no CUDA device' and do nothing).  It only proves that the Python control flow,
+attribute names, shapes and schedules hold together -- numerics are the GPU tests' job
+(tests/test_training_gpu.py).  Development aid for a container without a GPU; not part of the product or the tests.
+
+    python tools/mock_trainer_dryrun.py
+"""
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class _Event:
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_event(self, e):
+        pass
+
+
+torch.cuda.Event = _Event
+torch.cuda.Stream = lambda **k: _Stream()
+torch.cuda.current_stream = lambda *a: _Stream()
+torch.cuda.device = lambda d: contextlib.nullcontext()
+torch.cuda.stream = lambda s: contextlib.nullcontext()
+torch.cuda.current_device = lambda: 0
+torch.Tensor.pin_memory = lambda self: self
+
+import fgs_nerf_b200  # noqa: E402,F401
+from fgs_nerf_b200 import _lib  # noqa: E402
+
+_lib.check_input = lambda *a, **k: None
+_lib.stream = lambda: 0
+_lib.check = lambda rc: None
+src = open(os.path.join(ROOT, "fgs-nerf_b200", "engine.py")).read().replace('if self.device.type != "cuda":', "if False:").replace("assert grid.is_cuda and", "assert")
+mod = types.ModuleType("fgs_nerf_b200.engine")
+mod.__package__ = "fgs_nerf_b200"
+mod.__file__ = os.path.join(ROOT, "fgs-nerf_b200", "engine.py")
+sys.modules["fgs_nerf_b200.engine"] = mod
+exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+fgs_nerf_b200.engine = mod
+
+from fgs_nerf_b200 import scene, training  # noqa: E402
+
+engine = mod
+dev = "cpu"
+N, n_total = 64, 500
+sc = scene.make_scene(G=24, mask_G=20)
+rays = scene.make_rays(N=n_total, H=50, W=50, n_views=4)
+
+out = engine.grid_resize(sc.sdf, (30, 30, 30))
+assert tuple(out.shape) == (1, 1, 30, 30, 30)
+k0cl = sc.k0.contiguous(memory_format=torch.channels_last_3d)
+out = engine.grid_resize(k0cl, (30, 31, 32))
+assert tuple(out.shape) == (1, 12, 30, 31, 32) and not out.is_contiguous()
+o = engine.gather_rays(*rays, torch.arange(10))
+assert o[0].shape == (10, 3)
+
+ratio = (32 / 24) ** 3
+cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, pg_scale=[5002], scale_ratio=ratio,
+           decay_step_module={5000: dict(sdf=0.1)}, tv_updates={5001: dict(sdf_tv=0.3)}, s_updates={5001: dict(s_ratio=40)})
+eng = engine.FineStepEngine(sc, N, dev, train_cfg=dict(scene.FINE_TRAIN))
+eng.set_nonempty_mask()
+tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=5000, rng=np.random.RandomState(1))
+tr.run(4, i_print=2, log=lambda s: print("  log:", s))
+st = tr.stats()
+print("steps", st["steps"], "lr", st["lr"])
+print("engine grid", tr.engine.X, tr.engine.Y, tr.engine.Z, "adam_step", tr.engine.adam_step, "num_voxels", tr.engine.num_voxels)
+assert tr.engine.train_cfg["sdf_tv"] == 0.3 and tr.engine.cfg["s_ratio"] == 40
+assert tr.engine.adam_step == 3
+print("dry run ok")
