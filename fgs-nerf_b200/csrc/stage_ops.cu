@@ -1,6 +1,7 @@
 // Between-step operators of the training loop: progressive grid scaling and the batch gather.
 // Both are single-pass streaming kernels: HBM-bound, 128-bit stores, grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "fine_common.cuh"
 #include "../../include/fgs_b200_train.h"
 
 namespace {
@@ -125,7 +126,44 @@ __global__ void __launch_bounds__(kBlock) gather_rays_kernel(const float* __rest
   out[3 * (long long)i + 2] = e;
 }
 
+// SDF field on a regular lattice (extract_fields): one thread per lattice point, z fastest (coalesced stores);
+// the coordinates come from the three 1-D arrays the caller built with torch.linspace, the sample is ATen's
+// grid_sampler_3d arithmetic (ray_math.cuh), so the values equal the reference's query_func bit for bit.
+__global__ void __launch_bounds__(kBlock) lattice_sample_kernel(const float* __restrict__ grid, fine::GridGeo g,
+                                                                const float* __restrict__ xs, int nx,
+                                                                const float* __restrict__ ys, int ny,
+                                                                const float* __restrict__ zs, int nz, float sign,
+                                                                float* __restrict__ out, long long n) {
+  for (long long p = blockIdx.x * (long long)kBlock + threadIdx.x; p < n; p += (long long)gridDim.x * kBlock) {
+    const int k = (int)(p % nz);
+    const long long r = p / nz;
+    const int j = (int)(r % ny), i = (int)(r / ny);
+    float iw, ih, id;
+    fine::cont_index(g, __ldg(xs + i), __ldg(ys + j), __ldg(zs + k), iw, ih, id);
+    const Tri t = tri_setup(iw, ih, id);
+    out[p] = __fmul_rn(sign, tri_sample1(grid, t, g.X, g.Y, g.Z));
+  }
+}
+
 }  // namespace
+
+extern "C" int fgs_grid_sample_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min,
+                                       const float* xyz_max, const float* xs, int nx, const float* ys, int ny,
+                                       const float* zs, int nz, float sign, float* out, fgs_stream_t stream) {
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0 && nx >= 0 && ny >= 0 && nz >= 0, "grid_sample_lattice: bad size");
+  const long long n = (long long)nx * ny * nz;
+  if (n == 0) return 0;
+  FGS_REQUIRE(grid && xs && ys && zs && out && xyz_min && xyz_max, "grid_sample_lattice: null pointer");
+  fine::GridGeo g;
+  for (int c = 0; c < 3; ++c) {
+    g.mn[c] = xyz_min[c];
+    g.ext[c] = xyz_max[c] - xyz_min[c];  // fp32 subtraction, as torch evaluates (xyz_max - xyz_min)
+  }
+  g.X = X; g.Y = Y; g.Z = Z;
+  cudaStream_t st = (cudaStream_t)stream;
+  lattice_sample_kernel<<<fgs::stream_grid(n, kBlock, 8), kBlock, 0, st>>>(grid, g, xs, nx, ys, ny, zs, nz, sign, out, n);
+  return fgs::check_launch("grid_sample_lattice", st);
+}
 
 extern "C" int fgs_grid_resize_trilinear(const float* src, int C, int X, int Y, int Z, float* dst, int X2, int Y2,
                                          int Z2, int channels_last, fgs_stream_t stream) {

@@ -102,6 +102,8 @@ _lib.declare("fgs_set_mlp_dw_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
 _i = C.c_int
 _lib.declare("fgs_grid_resize_trilinear", C.c_int, [_fp, _i, _i, _i, _i, _fp, _i, _i, _i, _i, _fp])
+_lib.declare("fgs_grid_sample_lattice", C.c_int,
+             [_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _i, _fp, _i, C.c_float, _fp, _fp])
 _lib.declare("fgs_gather_rays", C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _i, _fp, _fp, _fp, _fp, _fp, _fp])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
@@ -506,6 +508,12 @@ class FineStepEngine:
             res["depth"] = res["depth"][:, 0]
             res["disp"] = 1 / res["depth"]
         return res
+
+    def extract_fields(self, bound_min, bound_max, resolution=128):
+        """The SDF field nerf.extract_geometry queries (model/nerf.py:1157-1170 -> extract_geometry.py:5-19):
+        -trilinear(sdf) on a resolution^3 lattice, one launch, device tensor [res,res,res]."""
+        from .extract_geometry import extract_sdf_field
+        return extract_sdf_field(self.sdf, self.xyz_min, self.xyz_max, bound_min, bound_max, resolution)
 
     def set_nonempty_mask(self):
         """nerf._set_nonempty_mask (model/nerf.py:339-353): MaskCache at the voxel centres."""

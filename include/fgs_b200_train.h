@@ -40,6 +40,22 @@ int fgs_gather_rays(const float* rays_o_tr, const float* rays_d_tr, const float*
                     const float* rgb_tr, int64_t n_total, const int64_t* sel, int n, float* rays_o,
                     float* rays_d, float* viewdirs, float* target, int32_t* bad, fgs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * SDF field query for mesh extraction  (reference: extract_fields, model/extract_geometry.py:5-19, with the
+ * query_func of nerf.extract_geometry, model/nerf.py:1157-1170: grid_sampler(pts, -sdf_grid))
+ *
+ *   out[i][j][k] = sign * trilinear(grid [X][Y][Z], (xs[i], ys[j], zs[k]))      (zero padding outside the bbox)
+ *
+ * xs / ys / zs are the three coordinate arrays (device; the reference builds them with torch.linspace), so the
+ * lattice points never exist as a [M,3] tensor: 4 bytes written per point instead of 12 written + 12 read + 4
+ * written, and no host round trip per 64^3 block.  xyz_min / xyz_max are HOST pointers to 3 floats (the grid's
+ * bbox).  sign = -1 gives the reference's field (it samples the negated grid).  Same arithmetic as
+ * fgs_grid_sample_fwd (ATen grid_sampler_3d), so values are bit-identical to the reference's on CUDA.
+ * ------------------------------------------------------------------------------------ */
+int fgs_grid_sample_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min, const float* xyz_max,
+                            const float* xs, int nx, const float* ys, int ny, const float* zs, int nz, float sign,
+                            float* out, fgs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
