@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import render_utils_cuda, total_variation_cuda
-from .engine import grid_sample, grid_sample_backward
+from .engine import grid_resize, grid_sample, grid_sample_backward
 
 
 def create_grid(type, **kwargs):
@@ -59,14 +59,12 @@ class DenseGrid(nn.Module):
         return out
 
     def scale_volume_grid(self, new_world_size):
-        """model/grid.py:101-106 (trilinear F.interpolate: resolution change between stages, off the
-        per-step path -- kept on the library op like the reference)."""
+        """model/grid.py:101-106: F.interpolate(grid, size, 'trilinear', align_corners=True) as one streaming
+        kernel (fgs_grid_resize_trilinear)."""
         if self.channels == 0:
             self.grid = nn.Parameter(torch.zeros([1, self.channels, *new_world_size]))
         else:
-            self.grid = nn.Parameter(
-                F.interpolate(self.grid.data, size=tuple(int(w) for w in new_world_size), mode='trilinear',
-                              align_corners=True))
+            self.grid = nn.Parameter(grid_resize(self.grid.data, [int(w) for w in new_world_size]))
         self.world_size = new_world_size
 
     def total_variation_add_grad(self, wx, wy, wz, dense_mode, mask=None):

@@ -43,8 +43,10 @@ def test_dense_grid_forward_backward_and_tv(cuda):
             dg.total_variation_add_grad(0.3, 0.3, 0.3, True)
             assert torch.equal(dg.grid.grad, gref)
         assert tuple(dg.state_dict()['grid'].shape) == (1, C, 20, 18, 22)
+    want = F.interpolate(dg.grid.data, size=(30, 30, 30), mode='trilinear', align_corners=True)   # model/grid.py:106
     dg.scale_volume_grid(torch.tensor([30, 30, 30]))
-    assert tuple(dg.grid.shape) == (1, 12, 30, 30, 30)
+    assert tuple(dg.grid.shape) == (1, 12, 30, 30, 30) and isinstance(dg.grid, torch.nn.Parameter)
+    assert float((dg.grid.data - want).abs().max()) <= 2e-6 * float(want.abs().max())
 
 
 def test_mask_grid_and_mask_cache(cuda):
