@@ -145,7 +145,82 @@ __global__ void __launch_bounds__(kBlock) lattice_sample_kernel(const float* __r
   }
 }
 
+// Dense k^3 convolution of a single-channel volume with replicate padding (nn.Conv3d(1, 1, k, padding=k//2,
+// padding_mode='replicate'), the reference's Gaussian smoother).  A CTA computes a 4 x 8 x 32 block of outputs from a
+// shared-memory tile with its halo (each input voxel is read from HBM ~1.5-2x instead of k^3 times); the k^3 weights
+// travel as a kernel parameter (constant bank, uniform index).  pre_div / post_div fold the reference's
+// `m(sdf0 / reduce) / reduce` into the same pass the way torch's CUDA kernel divides a tensor by a python scalar:
+// one fp32 reciprocal on the host, a multiplication per element (skipped when the divisor is 1).
+constexpr int kConvMaxK = 7;
+constexpr int CTX = 4, CTY = 8, CTZ = 32;
+struct ConvWeights { float w[kConvMaxK * kConvMaxK * kConvMaxK]; };
+
+template <int K>
+__global__ void __launch_bounds__(kBlock) conv3d_replicate_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 int X, int Y, int Z, ConvWeights cw, float pre_inv,
+                                                                 float post_inv, int tiles_y, int tiles_z) {
+  constexpr int H = K / 2;
+  constexpr int SX = CTX + 2 * H, SY = CTY + 2 * H, SZ = CTZ + 2 * H;
+  __shared__ float tile[SX * SY * SZ];
+  const int tz = blockIdx.x % tiles_z, ty = (blockIdx.x / tiles_z) % tiles_y, tx = blockIdx.x / (tiles_z * tiles_y);
+  const int x0 = tx * CTX, y0 = ty * CTY, z0 = tz * CTZ;
+  for (int i = threadIdx.x; i < SX * SY * SZ; i += kBlock) {
+    const int lz = i % SZ, ly = (i / SZ) % SY, lx = i / (SZ * SY);
+    const int gx = min(max(x0 + lx - H, 0), X - 1), gy = min(max(y0 + ly - H, 0), Y - 1), gz = min(max(z0 + lz - H, 0), Z - 1);
+    float v = __ldg(src + ((long long)gx * Y + gy) * Z + gz);
+    if (pre_inv != 1.f) v = __fmul_rn(v, pre_inv);
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int lz = threadIdx.x % CTZ, ly = threadIdx.x / CTZ;       // 32 x 8 threads, each walks the CTX planes
+#pragma unroll 1
+  for (int lx = 0; lx < CTX; ++lx) {
+    float acc = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+      for (int b = 0; b < K; ++b)
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          acc = __fmaf_rn(cw.w[(a * K + b) * K + c], tile[((lx + a) * SY + (ly + b)) * SZ + lz + c], acc);
+    const int gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
+    if (gx < X && gy < Y && gz < Z) {
+      if (post_inv != 1.f) acc = __fmul_rn(acc, post_inv);
+      dst[((long long)gx * Y + gy) * Z + gz] = acc;
+    }
+  }
+}
+
+template <int K>
+int launch_conv(const float* src, float* dst, int X, int Y, int Z, const float* w, float pre_div, float post_div,
+                cudaStream_t st) {
+  ConvWeights cw;
+  for (int i = 0; i < K * K * K; ++i) cw.w[i] = w[i];
+  const int tx = fgs::cdiv(X, CTX), ty = fgs::cdiv(Y, CTY), tz = fgs::cdiv(Z, CTZ);
+  const long long blocks = (long long)tx * ty * tz;
+  if (blocks > 0x7fffffffLL) return fgs::fail_arg("conv3d_replicate: volume too large");
+  // ATen's div_true_kernel_cuda with a CPU-scalar divisor: inv_b = 1.0f / b, then a * inv_b
+  const float pre_inv = pre_div == 1.f ? 1.f : 1.0f / pre_div, post_inv = post_div == 1.f ? 1.f : 1.0f / post_div;
+  conv3d_replicate_kernel<K><<<(unsigned)blocks, kBlock, 0, st>>>(src, dst, X, Y, Z, cw, pre_inv, post_inv, ty, tz);
+  return fgs::check_launch("conv3d_replicate", st);
+}
+
 }  // namespace
+
+extern "C" int fgs_conv3d_replicate(const float* src, float* dst, int X, int Y, int Z, const float* weights, int ksize,
+                                    float pre_div, float post_div, fgs_stream_t stream) {
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "conv3d_replicate: sizes must be positive");
+  FGS_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "conv3d_replicate: ksize must be 1, 3, 5 or 7");
+  FGS_REQUIRE(src && dst && src != dst && weights, "conv3d_replicate: src / dst must be distinct non-null buffers");
+  FGS_REQUIRE(pre_div != 0.f && post_div != 0.f, "conv3d_replicate: zero divisor");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ksize) {
+    case 1: return launch_conv<1>(src, dst, X, Y, Z, weights, pre_div, post_div, st);
+    case 3: return launch_conv<3>(src, dst, X, Y, Z, weights, pre_div, post_div, st);
+    case 5: return launch_conv<5>(src, dst, X, Y, Z, weights, pre_div, post_div, st);
+    default: return launch_conv<7>(src, dst, X, Y, Z, weights, pre_div, post_div, st);
+  }
+}
 
 extern "C" int fgs_grid_sample_lattice(const float* grid, int X, int Y, int Z, const float* xyz_min,
                                        const float* xyz_max, const float* xs, int nx, const float* ys, int ny,

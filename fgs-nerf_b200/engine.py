@@ -104,6 +104,7 @@ _i = C.c_int
 _lib.declare("fgs_grid_resize_trilinear", C.c_int, [_fp, _i, _i, _i, _i, _fp, _i, _i, _i, _i, _fp])
 _lib.declare("fgs_grid_sample_lattice", C.c_int,
              [_fp, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _i, _fp, _i, C.c_float, _fp, _fp])
+_lib.declare("fgs_conv3d_replicate", C.c_int, [_fp, _fp, _i, _i, _i, _fp, _i, C.c_float, C.c_float, _fp])
 _lib.declare("fgs_gather_rays", C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _i, _fp, _fp, _fp, _fp, _fp, _fp])
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
@@ -184,6 +185,34 @@ def grid_resize(grid, new_world_size):
                       memory_format=torch.channels_last_3d if cl else torch.contiguous_format)
     with torch.cuda.device(grid.device):
         check(lib.fgs_grid_resize_trilinear(ptr(grid), Cn, X, Y, Z, ptr(out), X2, Y2, Z2, cl, stream()))
+    return out
+
+
+def gaussian_3dconv_weights(ksize=3, sigma=1, device="cpu"):
+    """The kernel of nerf._gaussian_3dconv (model/nerf.py:260-268), built step for step as the reference builds it:
+    float64 exp on an integer lattice, cast to fp32 on the grid's device, divided by its fp32 sum there.
+    Returns a CPU fp32 tensor [k,k,k]."""
+    r = np.arange(-(ksize // 2), ksize // 2 + 1, 1)
+    xx, yy, zz = np.meshgrid(r, r, r)
+    kernel = np.exp(-(xx ** 2 + yy ** 2 + zz ** 2) / (2 * sigma ** 2))
+    kernel = torch.from_numpy(kernel).to(device=device, dtype=torch.float32)
+    return (kernel / kernel.sum()).cpu().contiguous()
+
+
+def smooth_conv(grid, ksize=3, sigma=1, pre_div=1.0, post_div=1.0, weights=None):
+    """nerf._gaussian_3dconv(ksize, sigma)(grid) for a [1,1,X,Y,Z] volume (Conv3d, replicate padding) as one
+    shared-memory tiled launch; pre_div / post_div give m(grid / pre_div) / post_div in the same pass."""
+    _lib.check_input(grid, "grid", torch.float32)
+    if grid.dim() != 5 or grid.shape[0] != 1 or grid.shape[1] != 1:
+        raise RuntimeError(f"grid must be [1,1,X,Y,Z], got {tuple(grid.shape)}")
+    w = gaussian_3dconv_weights(ksize, sigma, grid.device) if weights is None else weights.float().cpu().contiguous()
+    if tuple(w.shape) != (ksize,) * 3:
+        raise RuntimeError(f"weights must be [{ksize},{ksize},{ksize}]")
+    X, Y, Z = (int(v) for v in grid.shape[2:])
+    out = torch.empty_like(grid)
+    with torch.cuda.device(grid.device):
+        check(lib.fgs_conv3d_replicate(ptr(grid), ptr(out), X, Y, Z, w.data_ptr(), int(ksize), float(pre_div),
+                                       float(post_div), stream()))
     return out
 
 
@@ -633,6 +662,25 @@ class FineStepEngine:
             new.set_nonempty_mask()
         new.reset_optimizer(0)
         return new
+
+    @torch.no_grad()
+    def init_sdf_from_sdf(self, sdf0, smooth=False, reduce=1., ksize=3, sigma=1., smooth_scale=True):
+        """nerf.init_sdf_from_sdf (model/nerf.py:280-296), the stage hand-off of nerf_training.py:122-129: the earlier
+        stage's SDF grid resampled to this resolution, divided by `reduce` (the reference divides twice when `smooth`),
+        optionally smoothed, then -- `smooth_scale`, the reference's default -- smoothed with the 5^3, sigma 1 Gaussian.
+        Writes into the existing self.sdf storage (the C structs keep their pointers)."""
+        sdf0 = sdf0.to(self.device, torch.float32).contiguous()
+        if tuple(sdf0.shape) != tuple(self.sdf.shape):
+            sdf0 = grid_resize(sdf0, (self.X, self.Y, self.Z))
+        if smooth:
+            data = smooth_conv(sdf0, ksize, sigma, pre_div=reduce, post_div=reduce)
+        else:
+            data = smooth_conv(sdf0, 1, 1, pre_div=reduce, weights=torch.ones(1, 1, 1))     # sdf0 / reduce
+        if self.nonempty_mask is not None:
+            self.set_nonempty_mask()
+        if smooth_scale:
+            data = smooth_conv(data, 5, 1)
+        self.sdf.copy_(data)
 
     def _ensure_adam(self):
         """Adam state (allocated and zeroed on the calling stream, before any side-stream use)."""

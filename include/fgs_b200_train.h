@@ -41,6 +41,23 @@ int fgs_gather_rays(const float* rays_o_tr, const float* rays_d_tr, const float*
                     float* rays_d, float* viewdirs, float* target, int32_t* bad, fgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Gaussian smoothing of the SDF volume  (reference: nerf._gaussian_3dconv, model/nerf.py:260-272 =
+ * nn.Conv3d(1, 1, ksize, stride=1, padding=ksize//2, padding_mode='replicate'), zero bias; used at the stage
+ * hand-off by nerf.init_sdf_from_sdf, model/nerf.py:280-296, called from model/nerf_training.py:128)
+ *
+ *   dst[x][y][z] = ( sum_{a,b,c} w[a][b][c] * (src[clamp(x+a-h)][clamp(y+b-h)][clamp(z+c-h)] / pre_div) ) / post_div
+ *
+ * weights: HOST pointer to ksize^3 floats in [a][b][c] order (the caller builds them exactly as the reference
+ * does: float64 exp, cast to fp32, divided by their fp32 sum); ksize in {1,3,5,7}; pre_div / post_div fold
+ * init_sdf_from_sdf's `m(sdf0 / reduce) / reduce` into the pass (pass 1 to skip), evaluated as torch's CUDA
+ * tensor / python-scalar division is: x * (1.0f / divisor).  One shared-memory tiled pass:
+ * 8 bytes per voxel of compulsory traffic.  The accumulation order (a, b, c ascending, FMA) is this kernel's own --
+ * cuDNN's is unspecified -- so parity with the reference is to fp32 rounding (tests: 2e-6 of max|dst|).
+ * ------------------------------------------------------------------------------------ */
+int fgs_conv3d_replicate(const float* src, float* dst, int X, int Y, int Z, const float* weights, int ksize,
+                         float pre_div, float post_div, fgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * SDF field query for mesh extraction  (reference: extract_fields, model/extract_geometry.py:5-19, with the
  * query_func of nerf.extract_geometry, model/nerf.py:1157-1170: grid_sampler(pts, -sdf_grid))
  *

@@ -8,6 +8,8 @@
                           value = d0*(h0*(w0*v000 + w1*v001) + h1*(...)) + d1*(...).
                           Pinned against torch's own F.interpolate (the reference's call) in
                           tests/test_training_host.py.
+  gaussian_3dconv         nerf._gaussian_3dconv (model/nerf.py:260-272), pinned against the reference's own method
+                          executed from its source (tests/golden/make_stage_golden.py); init_sdf_from_sdf (:280-296).
   gather_rays             the four `x_tr[sel_i]` selections of model/nerf_training.py:253-258.
   RefSchedule             python restatement of the loop's schedule block (nerf_training.py:244-254, 386-433),
                           pinned against tests/golden/schedule_golden.npz (the reference's block executed
@@ -47,6 +49,51 @@ def grid_resize_trilinear(src, size):
     lo = (b0 * (c0 * v(x0, y0, z0) + c1 * v(x0, y0, z1)).astype(f) + b1 * (c0 * v(x0, y1, z0) + c1 * v(x0, y1, z1)).astype(f)).astype(f)
     hi = (b0 * (c0 * v(x1, y0, z0) + c1 * v(x1, y0, z1)).astype(f) + b1 * (c0 * v(x1, y1, z0) + c1 * v(x1, y1, z1)).astype(f)).astype(f)
     return (a0 * lo + a1 * hi).astype(f)
+
+
+def gaussian_3dconv_weights(ksize=3, sigma=1):
+    """model/nerf.py:261-268: float64 exp -> fp32 -> divided by the fp32 sum."""
+    r = np.arange(-(ksize // 2), ksize // 2 + 1, 1)
+    xx, yy, zz = np.meshgrid(r, r, r)
+    k = np.exp(-(xx ** 2 + yy ** 2 + zz ** 2) / (2 * sigma ** 2)).astype(np.float32)
+    return (k / k.sum(dtype=np.float32)).astype(np.float32)
+
+
+def gaussian_3dconv(vol, ksize=3, sigma=1, pre_div=1.0, post_div=1.0):
+    """nerf._gaussian_3dconv(ksize, sigma) applied to vol [X,Y,Z] (model/nerf.py:260-272): Conv3d(1, 1, k,
+    padding=k//2, padding_mode='replicate'), zero bias; cross-correlation like torch's conv.  fp32 accumulation in
+    (a, b, c) order.  Pinned against the reference's own method executed from its source
+    (tests/golden/make_stage_golden.py)."""
+    f = np.float32
+    w = gaussian_3dconv_weights(ksize, sigma)
+    h = ksize // 2
+    v = np.asarray(vol, dtype=f)
+    if pre_div != 1.0:
+        v = (v * (f(1) / f(pre_div))).astype(f)       # torch CUDA: tensor / python scalar = x * (1.0f / s)
+    p = np.pad(v, h, mode="edge")
+    X, Y, Z = v.shape
+    acc = np.zeros_like(v)
+    for a in range(ksize):
+        for b in range(ksize):
+            for c in range(ksize):
+                acc = (acc + w[a, b, c] * p[a:a + X, b:b + Y, c:c + Z]).astype(f)
+    if post_div != 1.0:
+        acc = (acc * (f(1) / f(post_div))).astype(f)
+    return acc
+
+
+def init_sdf_from_sdf(sdf0, world_size, smooth=False, reduce=1.0, ksize=3, sigma=1.0, smooth_scale=True):
+    """model/nerf.py:280-296 on a [X0,Y0,Z0] volume -> [X,Y,Z]."""
+    v = np.asarray(sdf0, dtype=np.float32)
+    if tuple(v.shape) != tuple(world_size):
+        v = grid_resize_trilinear(v[None], world_size)[0]
+    if smooth:
+        v = gaussian_3dconv(v, ksize, sigma, pre_div=reduce, post_div=reduce)
+    else:
+        v = (v * (np.float32(1) / np.float32(reduce))).astype(np.float32)
+    if smooth_scale:
+        v = gaussian_3dconv(v, 5, 1)
+    return v
 
 
 def gather_rays(rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, sel):

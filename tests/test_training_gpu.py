@@ -269,3 +269,59 @@ def test_sdf_field_query_matches_reference_blockwise_query(cuda, res, bound):
     assert np.array_equal(got, want), f"max abs diff {np.abs(got - want).max():.3e}"
     eng = engine.FineStepEngine(sc, 64, cuda)
     assert np.array_equal(eng.extract_fields(bmin, bmax, res).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("k,s,shape", [(3, 1, (12, 10, 14)), (5, 1, (33, 20, 70)), (5, 0.8, (8, 8, 32)), (7, 2, (16, 9, 40)),
+                                       (1, 1, (5, 6, 7))])
+def test_gaussian_conv_matches_torch_conv3d_and_oracle(cuda, k, s, shape):
+    """fgs_conv3d_replicate against nn.Conv3d(1, 1, k, padding=k//2, padding_mode='replicate') with the reference's
+    kernel (model/nerf.py:260-272) on CUDA, and against the numpy oracle; ragged tiles and every supported ksize."""
+    from fgs_nerf_b200 import engine
+    g = torch.Generator().manual_seed(41)
+    vol = torch.randn(1, 1, *shape, generator=g)
+    w = engine.gaussian_3dconv_weights(k, s, cuda)
+    assert np.abs(w.numpy() - stage_ref.gaussian_3dconv_weights(k, s)).max() <= 1.2e-7 * float(w.max())
+    m = torch.nn.Conv3d(1, 1, k, stride=1, padding=k // 2, padding_mode='replicate').to(cuda)
+    m.weight.data = w[None, None].to(cuda)
+    m.bias.data = torch.zeros(1, device=cuda)
+    with torch.no_grad():
+        want = m(vol.to(cuda))
+    got = engine.smooth_conv(vol.to(cuda), k, s)
+    tol = 2e-6 * float(want.abs().max())
+    assert float((got - want).abs().max()) <= tol
+    orc = stage_ref.gaussian_3dconv(vol[0, 0].numpy(), k, s)
+    assert np.abs(got[0, 0].cpu().numpy() - orc).max() <= tol
+    # folded divisions: m(x / r) / r, as init_sdf_from_sdf(smooth=True) computes it
+    got = engine.smooth_conv(vol.to(cuda), k, s, pre_div=0.3, post_div=0.3)
+    with torch.no_grad():
+        want = m(vol.to(cuda) / 0.3) / 0.3
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+def test_stage_handoff_init_sdf_from_sdf(cuda):
+    """engine.init_sdf_from_sdf against the reference's steps made with torch's CUDA ops (model/nerf.py:280-296,
+    called with smooth=False, reduce=sdf_reduce at nerf_training.py:128; smooth_scale defaults to True) and against
+    the numpy oracle; the grid's storage must stay where it is (the C structs hold its pointer)."""
+    from fgs_nerf_b200 import engine, scene
+    sc = scene.make_scene(G=48, mask_G=40)
+    eng = engine.FineStepEngine(sc, 64, cuda)
+    eng.set_nonempty_mask()
+    g = torch.Generator().manual_seed(43)
+    sdf0 = torch.randn(1, 1, 30, 30, 30, generator=g)
+    p0 = eng.sdf.data_ptr()
+    eng.init_sdf_from_sdf(sdf0, smooth=False, reduce=0.3)
+    assert eng.sdf.data_ptr() == p0 and tuple(eng.sdf.shape) == (1, 1, 48, 48, 48)
+    x = F.interpolate(sdf0.to(cuda), size=(48, 48, 48), mode="trilinear", align_corners=True) / 0.3
+    w = engine.gaussian_3dconv_weights(5, 1, cuda)[None, None].to(cuda)
+    want = F.conv3d(F.pad(x, (2,) * 6, mode="replicate"), w)
+    tol = 3e-6 * float(want.abs().max())
+    assert float((eng.sdf - want).abs().max()) <= tol
+    orc = stage_ref.init_sdf_from_sdf(sdf0[0, 0].numpy(), (48, 48, 48), smooth=False, reduce=0.3)
+    assert np.abs(eng.sdf[0, 0].cpu().numpy() - orc).max() <= tol
+    # the engine still steps on the new grid
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=64, H=100, W=100, n_views=8)]
+    eng.sdf.copy_(sc.sdf.to(cuda))
+    eng.init_sdf_from_sdf(sc.sdf, smooth=True, reduce=1.0, ksize=3, sigma=1.0, smooth_scale=False)
+    eng.train_step(ro, rd, vd, tgt, 5000)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(eng.ws["rgb_marched"]).all()) and eng.counters()["M1"] > 0

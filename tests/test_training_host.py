@@ -127,3 +127,32 @@ def test_cosine_factor_known_values():
         prod *= training.lr_decay_factor(t, gs)
     assert abs(prod - 0.5) < 1e-9                                   # half-way down the cosine after 10001 iterations
     assert training.lr_decay_factor(dict(lrate_decay=20), 7) == 0.1 ** (1 / 20000)
+
+
+STAGE = np.load(os.path.join(HERE, "golden", "stage_golden.npz"))
+
+
+@pytest.mark.parametrize("k,s", [(3, 1), (5, 1), (5, 0.8), (7, 2)])
+def test_oracle_gaussian_conv_matches_reference_method(k, s):
+    """oracle gaussian_3dconv against the output of the reference's own nerf._gaussian_3dconv (executed from its
+    source by tests/golden/make_stage_golden.py): weights bit-exact or 1 ulp, volume to fp32 rounding."""
+    from oracle import stage_ref
+    w = stage_ref.gaussian_3dconv_weights(k, s)
+    assert np.abs(w - STAGE[f"weight_k{k}_s{s}"]).max() <= 1.2e-7 * w.max()
+    got = stage_ref.gaussian_3dconv(STAGE["vol"], k, s)
+    want = STAGE[f"conv_k{k}_s{s}"]
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_oracle_resize_matches_golden_and_handoff_composes():
+    from oracle import stage_ref
+    got = stage_ref.grid_resize_trilinear(STAGE["vol"][None], (20, 17, 23))[0]
+    assert np.abs(got - STAGE["resize_20_17_23"]).max() <= 2e-6 * np.abs(STAGE["resize_20_17_23"]).max()
+    # init_sdf_from_sdf (model/nerf.py:280-296) = resize, / reduce, 5^3 sigma-1 smoothing -- against the same steps
+    # made with torch's ops
+    vol = torch.from_numpy(STAGE["vol"])[None, None]
+    x = F.interpolate(vol, size=(20, 17, 23), mode="trilinear", align_corners=True) / 0.3
+    w = torch.from_numpy(STAGE["weight_k5_s1"])[None, None]
+    want = F.conv3d(F.pad(x, (2,) * 6, mode="replicate"), w)[0, 0].numpy()
+    got = stage_ref.init_sdf_from_sdf(STAGE["vol"], (20, 17, 23), smooth=False, reduce=0.3)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
