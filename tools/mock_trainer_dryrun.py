@@ -71,6 +71,21 @@ assert tuple(out.shape) == (1, 12, 30, 31, 32) and not out.is_contiguous()
 o = engine.gather_rays(*rays, torch.arange(10))
 assert o[0].shape == (10, 3)
 
+w = engine.gaussian_3dconv_weights(5, 1)
+assert tuple(w.shape) == (5, 5, 5) and abs(float(w.sum()) - 1) < 1e-6
+assert engine.smooth_conv(sc.sdf, 5, 1).shape == sc.sdf.shape
+e0 = engine.FineStepEngine(sc, N, dev)
+e0.set_nonempty_mask()
+p0 = e0.sdf.data_ptr()
+e0.init_sdf_from_sdf(torch.randn(1, 1, 10, 10, 10), smooth=False, reduce=0.3)
+e0.init_sdf_from_sdf(sc.sdf, smooth=True, reduce=0.5, ksize=3, sigma=1.0, smooth_scale=False)
+assert e0.sdf.data_ptr() == p0
+u = e0.extract_fields(torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3), 20)
+assert tuple(u.shape) == (20, 20, 20)
+from fgs_nerf_b200 import extract_geometry  # noqa: E402
+v = extract_geometry.extract_fields(torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3), 20, lambda p: p[:, 0], N=8)
+assert v.shape == (20, 20, 20) and abs(v[-1, 0, 0] - 1.0) < 1e-6
+
 ratio = (32 / 24) ** 3
 cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, pg_scale=[5002], scale_ratio=ratio,
            decay_step_module={5000: dict(sdf=0.1)}, tv_updates={5001: dict(sdf_tv=0.3)}, s_updates={5001: dict(s_ratio=40)})
