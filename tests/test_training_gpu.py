@@ -325,3 +325,54 @@ def test_stage_handoff_init_sdf_from_sdf(cuda):
     eng.train_step(ro, rd, vd, tgt, 5000)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(eng.ws["rgb_marched"]).all()) and eng.counters()["M1"] > 0
+
+
+def test_checkpoint_layout_and_round_trip(cuda, tmp_path):
+    """The checkpoint dict (model/nerf_training.py:522-531) has the reference's keys, order, shapes and dtypes --
+    tests/golden/ckpt_layout.json was dumped from the reference's own model / optimizer objects -- and restores an
+    engine that continues exactly where the saved one was."""
+    import json
+    from fgs_nerf_b200 import checkpoint, engine, scene
+    layout = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ckpt_layout.json")))
+    N = 64
+    sc = scene.make_scene(G=24, mask_G=20)                  # the sizes the layout was dumped at
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
+    eng = engine.FineStepEngine(sc, N, cuda)
+    eng.set_nonempty_mask()
+    for gs in (5001, 5002):
+        eng.train_step(ro, rd, vd, tgt, gs)
+    eng.lr["sdf"] *= 0.1
+    torch.cuda.synchronize()
+    ck = checkpoint.checkpoint_dict(eng, 5002)
+    const = ("grad_conv.", "tv_smooth_conv.")               # frozen stencils the reference's constructor re-creates
+    want = [(k, s, d) for k, s, d in layout["model_state_dict"] if not k.startswith(const)]
+    got = [(k, list(v.shape), str(v.dtype)) for k, v in ck["model_state_dict"].items() if k != "sdf_mask.grid"]
+    assert got == want
+    assert tuple(ck["model_state_dict"]["sdf_mask.grid"].shape) == (1, 1, 24, 24, 24)          # nerf.set_sdf_mask
+    assert list(ck["model_kwargs"].keys()) == list(layout["model_kwargs"].keys())
+    assert list(ck["MaskCache_kwargs"].keys()) == list(layout["MaskCache_kwargs"].keys())
+    osd = ck["optimizer_state_dict"]
+    assert len(osd["state"]) == layout["optimizer_state_count"]
+    for g, w in zip(osd["param_groups"], layout["optimizer_param_groups"]):
+        assert (g["name"], g["skip_zero_grad"], list(g["betas"]), g["eps"], len(g["params"])) == \
+            (w["name"], w["skip_zero_grad"], list(w["betas"]), w["eps"], w["params"])
+    assert set(osd["state"][0].keys()) == set(layout["optimizer_state_entry"].keys())
+    assert list(osd["state"][0]["exp_avg"].shape) == layout["optimizer_state_entry"]["exp_avg"] and osd["state"][0]["step"] == 2
+    assert tuple(osd["state"][2]["exp_avg"].shape) == (256, 106) and tuple(osd["state"][10]["exp_avg"].shape) == (256, 307)
+    # round trip through torch.save
+    path = str(tmp_path / "fine_last.tar")
+    checkpoint.save_checkpoint(eng, 5002, path)
+    eng2, start = checkpoint.engine_from_checkpoint(path, N, cuda)
+    assert start == 5002 and eng2.adam_step == 2 and eng2.lr == eng.lr
+    assert torch.equal(eng2.sdf, eng.sdf) and torch.equal(eng2.k0, eng.k0) and torch.equal(eng2.nonempty_mask, eng.nonempty_mask)
+    for i in range(8):
+        assert torch.equal(eng2.weights[i], eng.weights[i]) and torch.equal(eng2.Bt[i], eng.Bt[i])
+        assert torch.equal(eng2.adam["W"][i][0], eng.adam["W"][i][0]) and torch.equal(eng2.adam["B"][i][1], eng.adam["B"][i][1])
+    assert torch.equal(eng2.adam["k0"][1], eng.adam["k0"][1]) and torch.equal(eng2.adam["sdf"][0], eng.adam["sdf"][0])
+    before = {"sdf": eng.sdf.clone(), "k0": eng.k0.clone(), "W4": eng.weights[4].clone()}
+    eng.train_step(ro, rd, vd, tgt, 5003)
+    eng2.train_step(ro, rd, vd, tgt, 5003)
+    torch.cuda.synchronize()
+    assert np.allclose(eng.ws["loss"].cpu().numpy(), eng2.ws["loss"].cpu().numpy(), rtol=1e-6, atol=1e-12)
+    for name, a, b, lr in (("sdf", eng.sdf, eng2.sdf, 0.005), ("k0", eng.k0, eng2.k0, 0.1), ("W4", eng.weights[4], eng2.weights[4], 1e-3)):
+        assert _frac_differing(a, b, before[name], lr) < 1e-3, name

@@ -98,4 +98,16 @@ print("steps", st["steps"], "lr", st["lr"])
 print("engine grid", tr.engine.X, tr.engine.Y, tr.engine.Z, "adam_step", tr.engine.adam_step, "num_voxels", tr.engine.num_voxels)
 assert tr.engine.train_cfg["sdf_tv"] == 0.3 and tr.engine.cfg["s_ratio"] == 40
 assert tr.engine.adam_step == 3
+import tempfile  # noqa: E402
+
+from fgs_nerf_b200 import checkpoint  # noqa: E402
+
+ck = checkpoint.checkpoint_dict(tr.engine, tr.global_step)
+assert len(ck["optimizer_state_dict"]["state"]) == 18 and len(ck["model_kwargs"]) == 22
+with tempfile.TemporaryDirectory() as td:
+    checkpoint.save_checkpoint(tr.engine, tr.global_step, os.path.join(td, "fine_last.tar"))
+    e2, start = checkpoint.engine_from_checkpoint(os.path.join(td, "fine_last.tar"), N, dev, train_cfg=dict(tr.engine.train_cfg))
+assert start == tr.global_step and e2.adam_step == tr.engine.adam_step and e2.lr == tr.engine.lr
+assert torch.equal(e2.k0, tr.engine.k0) and torch.equal(e2.weights[4], tr.engine.weights[4])
+assert torch.equal(e2.nonempty_mask, tr.engine.nonempty_mask)
 print("dry run ok")
