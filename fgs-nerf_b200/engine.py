@@ -73,8 +73,25 @@ class FgsFineLoss(C.Structure):
     ]
 
 
+class FgsFineStep(C.Structure):
+    """include/fgs_b200_fine.h: FgsFineStep (same field order and types)."""
+    _fields_ = [
+        ("tv_smooth", C.c_int), ("smooth_weight", C.c_float), ("smooth_n_sel", C.c_double),
+        ("nonempty", _fp), ("tv_scratch", _fp),
+        ("tv_sdf", C.c_int), ("sdf_tv_weight", C.c_float), ("sdf_tv_dense", C.c_int),
+        ("adam_step", C.c_int), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("lr_sdf", C.c_float), ("lr_k0", C.c_float),
+        ("sdf_m", _fp), ("sdf_v", _fp), ("k0_m", _fp), ("k0_v", _fp),
+        ("sparse_k0", C.c_int), ("brick_list", _fp),
+        ("n_mlp", C.c_int), ("mlp_p", _fp), ("mlp_g", _fp), ("mlp_m", _fp), ("mlp_v", _fp), ("mlp_n", _fp),
+        ("mlp_steps", _fp), ("mlp_lrs", _fp),
+        ("side_stream", _fp),
+    ]
+
+
 _PP = C.POINTER(FgsFineParams)
 _LP = C.POINTER(FgsFineLoss)
+_lib.declare("fgs_fine_train_step", C.c_int, [_PP, _LP, C.POINTER(FgsFineStep), _fp])
 _lib.declare("fgs_fine_forward", C.c_int, [_PP, _fp])
 _lib.declare("fgs_fine_loss", C.c_int, [_PP, _LP, _fp])
 _lib.declare("fgs_fine_backward", C.c_int, [_PP, _LP, _fp])
@@ -385,6 +402,8 @@ class FineStepEngine:
         self._count_evt = torch.cuda.Event()
         self.exchange_bricks = 0
         self._side = None                  # side stream of the overlapped gradient exchange (data parallel)
+        self.native_step = True            # single GPU: the iteration is one library call (fgs_fine_train_step)
+        self._S = None
         self.dw_sm_reserve = 16            # SMs the weight-gradient kernel leaves to the collectives
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
         ws["loss"] = torch.zeros(5, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv
@@ -577,6 +596,15 @@ class FineStepEngine:
         """Loss block + backward (model/nerf_training.py:307-347); grads of the MLPs are overwritten,
         g_sdf / g_k0 accumulated into (call zero_grad() first).  phase=1 stops after the grid gradients are
         complete (the weight gradients follow with backward_weights())."""
+        L = self._fill_loss(target, n_rays_global, has_last_ray)
+        self.ws["loss"].zero_()
+        self._grads_clean = False
+        with torch.cuda.device(self.device):
+            st = stream()
+            check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
+            check(lib.fgs_fine_backward_phase(C.byref(self.P), C.byref(L), int(phase), st))
+
+    def _fill_loss(self, target, n_rays_global, has_last_ray):
         t = self.train_cfg
         L = self.L
         _lib.check_input(target, "target", torch.float32)
@@ -588,12 +616,7 @@ class FineStepEngine:
         L.has_last_ray = int(bool(has_last_ray))
         L.g_alphainv_last = ptr(self.ws["g_alphainv_last"])
         L.loss_out = ptr(self.ws["loss"])
-        self.ws["loss"].zero_()
-        self._grads_clean = False
-        with torch.cuda.device(self.device):
-            st = stream()
-            check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
-            check(lib.fgs_fine_backward_phase(C.byref(self.P), C.byref(L), int(phase), st))
+        return L
 
     def backward_weights(self):
         """Second phase of loss_backward(phase=1): the MLP weight / bias gradients."""
@@ -633,6 +656,7 @@ class FineStepEngine:
         self.lr = {k: float(t["lrate_" + k]) * decay for k in ("sdf", "k0", "rgbnet", "refnet")}
         self.adam = {}
         self.adam_step = 0
+        self._S = None                      # cached pointers of the Adam state
 
     @torch.no_grad()
     def scale_volume_grid(self, num_voxels):
@@ -691,6 +715,7 @@ class FineStepEngine:
                      "W": [(torch.zeros_like(w), torch.zeros_like(w)) for w in self.Wt],
                      "B": [(torch.zeros_like(b), torch.zeros_like(b)) for b in self.Bt]}
         n = 2 * MLP_LAYERS
+        self._S = None
         self._mt = dict(
             p=(_fp * n)(*[ptr(x) for x in self.Wt + self.Bt]),
             g=(_fp * n)(*[ptr(x) for x in self.gW + self.gB]),
@@ -838,6 +863,54 @@ class FineStepEngine:
             if n > 0:
                 self._copy_touched(buf, n, 0)
 
+    def _native_train_step(self, rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv):
+        """The single-GPU iteration as ONE library call (fgs_fine_train_step): same launches, order and streams as the
+        host-sequenced branch of train_step below, without ~20 Python -> C round trips per iteration."""
+        t = self.train_cfg
+        self._bind_inputs(rays_o, rays_d, viewdirs, global_step, near, bg, False, False)
+        L = self._fill_loss(target, n_rays_global, has_last_ray)
+        S = self._S
+        if S is None:
+            S = self._S = FgsFineStep()
+            n = 2 * MLP_LAYERS
+            self._S_steps, self._S_lrs = (C.c_int * n)(), (C.c_float * n)()
+            mt = self._mt
+            S.beta1, S.beta2, S.eps = 0.9, 0.99, 1e-8
+            S.sdf_m, S.sdf_v = ptr(self.adam["sdf"][0]), ptr(self.adam["sdf"][1])
+            S.k0_m, S.k0_v = ptr(self.adam["k0"][0]), ptr(self.adam["k0"][1])
+            S.sparse_k0 = int(self.sparse_k0)
+            S.brick_list = ptr(self.ws["k0_brick_list"])
+            S.n_mlp = n
+            S.mlp_p, S.mlp_g = C.cast(mt["p"], _fp), C.cast(mt["g"], _fp)
+            S.mlp_m, S.mlp_v = C.cast(mt["m"], _fp), C.cast(mt["v"], _fp)
+            S.mlp_n = C.cast(mt["n"], _fp)
+            S.mlp_steps, S.mlp_lrs = C.cast(self._S_steps, _fp), C.cast(self._S_lrs, _fp)
+            S.side_stream = self._side.cuda_stream
+        S.tv_smooth = int(tv and t["smooth_grad_tv"] > 0)
+        if S.tv_smooth:
+            S.smooth_weight = t["weight_tv_density"] * t["smooth_grad_tv"]
+            if self.nonempty_mask is not None:
+                S.smooth_n_sel, S.nonempty = 3.0 * self.n_nonempty, ptr(self.nonempty_mask)
+            else:
+                S.smooth_n_sel, S.nonempty = 3.0 * self.X * self.Y * self.Z, None
+            S.tv_scratch = ptr(self.tv_scratch)
+        S.tv_sdf = int(tv and t["sdf_tv"] > 0)
+        if S.tv_sdf:
+            w = t["weight_tv_density"] * t["sdf_tv"] / (n_rays_global or self.n_rays)
+            S.sdf_tv_weight = float(w * max(self.X, self.Y, self.Z) / 128)
+            S.sdf_tv_dense = int(global_step < t["tv_dense_before"])
+        self.adam_step += 1
+        S.adam_step = self.adam_step
+        S.lr_sdf, S.lr_k0 = self.lr["sdf"], self.lr["k0"]
+        for i in range(MLP_LAYERS):
+            lr = self.lr["rgbnet"] if i < 4 else self.lr["refnet"]
+            self._S_lrs[i] = self._S_lrs[MLP_LAYERS + i] = lr
+            self._S_steps[i] = self._S_steps[MLP_LAYERS + i] = self.adam_step
+        with torch.cuda.device(self.device):
+            check(lib.fgs_fine_train_step(C.byref(self.P), C.byref(L), C.byref(S), stream()))
+        self._grads_clean = True
+        self._brick_list_ready = False
+
     def _copy_touched(self, buf, n, pack):
         """Gather (pack=1) / scatter the touched part of g_k0 to / from `buf`: listed voxels or listed bricks."""
         if self.voxel_exchange:
@@ -853,7 +926,9 @@ class FineStepEngine:
         the touched k0 bricks, its count (the one host sync) and the pack run on a side stream while the
         weight-gradient kernel (which leaves a few SMs free for them) runs on the main one; then ONE all-reduce over
         [g_sdf | MLP bucket | packed bricks]."""
-        self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
+        native = self.world_size == 1 and self.native_step
+        if not native:
+            self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
         t = self.train_cfg
         tv = self.is_tv_step(global_step) and t["weight_tv_density"] > 0
@@ -865,6 +940,9 @@ class FineStepEngine:
             self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
             check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve if self.world_size > 1 else 0))
         main = torch.cuda.current_stream(self.device)
+        if self.world_size == 1 and self.native_step:
+            self._native_train_step(rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv)
+            return
         if self.world_size == 1:
             # the grid gradients are final after phase 1: their regularisers and optimiser kernels (HBM-bound, small
             # CTAs) run on the side stream next to the tensor-core-bound weight-gradient kernel

@@ -179,6 +179,47 @@ int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const uint8_t* n
                                 float weight, double n_sel, double* loss_out,
                                 fgs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * One whole single-GPU training iteration (model/nerf_training.py:300-373) sequenced by the library: the host makes
+ * ONE call per iteration instead of ~20 (the Python driver's per-launch overhead was as long as the step itself).
+ * Same launches, same order, same streams as the host-sequenced step:
+ *   main : loss buffer clear, fgs_fine_forward (composite skipped), fgs_fine_loss, backward phase 1,
+ *          smooth-gradient TV and SDF TV add-grad on their schedule, [fork] backward phase 2 (weight gradients),
+ *          multi-tensor Adam of the 16 MLP tensors, [join]
+ *   side : (after the fork) dense SDF Adam + gradient clear, touched-brick list, brick Adam of k0
+ * `side_stream` must differ from `stream`; the two events the fork / join need live in the library (one pair per
+ * process).  Everything is enqueued; nothing synchronises.
+ * ------------------------------------------------------------------------------------ */
+typedef struct FgsFineStep {
+  /* regularisers of this iteration (host decides from its schedule) */
+  int tv_smooth;            /* != 0: fgs_smooth_grad_tv_add_grad */
+  float smooth_weight;      /* weight_tv_density * smooth_grad_tv */
+  double smooth_n_sel;      /* 3 * selected voxels */
+  const uint8_t* nonempty;  /* [X*Y*Z] or NULL */
+  float* tv_scratch;        /* 6 * X*Y*Z floats (only read when tv_smooth) */
+  int tv_sdf;               /* != 0: fgs_total_variation_add_grad on the SDF grid */
+  float sdf_tv_weight;      /* already scaled by max(world_size)/128 and 1/n_rays_global */
+  int sdf_tv_dense;
+  /* optimiser */
+  int adam_step;
+  float beta1, beta2, eps;
+  float lr_sdf, lr_k0;
+  float *sdf_m, *sdf_v, *k0_m, *k0_v;
+  int sparse_k0;            /* != 0: brick list + brick Adam; 0: dense masked Adam + clears */
+  int32_t* brick_list;
+  int n_mlp;                /* tensors of the multi-tensor Adam (HOST arrays below, n_mlp entries each) */
+  float* const* mlp_p;
+  const float* const* mlp_g;
+  float* const* mlp_m;
+  float* const* mlp_v;
+  const int64_t* mlp_n;
+  const int* mlp_steps;
+  const float* mlp_lrs;
+  fgs_stream_t side_stream;
+} FgsFineStep;
+
+int fgs_fine_train_step(const FgsFineParams* p, const FgsFineLoss* l, const FgsFineStep* s, fgs_stream_t stream);
+
 /* DenseGrid.forward / backward (model/grid.py:49-59) and MaskCache.forward (model/nerf.py:
  * 1202-1209) as stand-alone ops: ATen grid_sample arithmetic, any channel count.
  * channels_last: 0 = [C][X][Y][Z], 1 = [X][Y][Z][C].  out: [M][C].

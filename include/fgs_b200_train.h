@@ -51,7 +51,7 @@ int fgs_gather_rays(const float* rays_o_tr, const float* rays_d_tr, const float*
  * does: float64 exp, cast to fp32, divided by their fp32 sum); ksize in {1,3,5,7}; pre_div / post_div fold
  * init_sdf_from_sdf's `m(sdf0 / reduce) / reduce` into the pass (pass 1 to skip), evaluated as torch's CUDA
  * tensor / python-scalar division is: x * (1.0f / divisor).  One shared-memory tiled pass:
- * 8 bytes per voxel of compulsory traffic.  The accumulation order (a, b, c ascending, FMA) is this kernel's own --
+ * 8 bytes per voxel of compulsory traffic.  The accumulation order ((b, c) outer, a inner, FMA) is this kernel's own --
  * cuDNN's is unspecified -- so parity with the reference is to fp32 rounding (tests: 2e-6 of max|dst|).
  * ------------------------------------------------------------------------------------ */
 int fgs_conv3d_replicate(const float* src, float* dst, int X, int Y, int Z, const float* weights, int ksize,

@@ -376,3 +376,39 @@ def test_checkpoint_layout_and_round_trip(cuda, tmp_path):
     assert np.allclose(eng.ws["loss"].cpu().numpy(), eng2.ws["loss"].cpu().numpy(), rtol=1e-6, atol=1e-12)
     for name, a, b, lr in (("sdf", eng.sdf, eng2.sdf, 0.005), ("k0", eng.k0, eng2.k0, 0.1), ("W4", eng.weights[4], eng2.weights[4], 1e-3)):
         assert _frac_differing(a, b, before[name], lr) < 1e-3, name
+
+
+def test_library_sequenced_step_equals_host_sequenced_step(cuda):
+    """fgs_fine_train_step (one call per iteration) against the same iteration sequenced launch by launch from
+    Python: three iterations with both TV terms on, then the parameters, the Adam state and the loss terms agree to
+    the rounding of the float atomics."""
+    from fgs_nerf_b200 import engine, scene
+    N = 192
+    sc = scene.make_scene(G=48, mask_G=40)
+    cfg = dict(scene.FINE_TRAIN, tv_every=1)
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
+    engs = []
+    for native in (True, False):
+        e = engine.FineStepEngine(sc, N, cuda, train_cfg=cfg)
+        e.set_nonempty_mask()
+        e.native_step = native
+        losses = []
+        for gs in (5000, 5001, 5002):
+            e.lr["sdf"] *= 0.9                                   # the per-group rates reach both drivers
+            e.train_step(ro, rd, vd, tgt, gs)
+            torch.cuda.synchronize()
+            losses.append(e.ws["loss"].cpu().numpy().copy())
+        engs.append((e, np.stack(losses)))
+    (a, la), (b, lb) = engs
+    assert a.adam_step == b.adam_step == 3 and la[:, 4].min() > 0           # the smooth-TV term was computed
+    assert np.allclose(la[0], lb[0], rtol=1e-6, atol=1e-12) and np.allclose(la, lb, rtol=1e-3, atol=1e-7)
+    for name, x, y, before, lr in (("sdf", a.sdf, b.sdf, sc.sdf, 0.005), ("k0", a.k0, b.k0, sc.k0, 0.1),
+                                   ("W0", a.weights[0], b.weights[0], sc.rgbnet[0][0], 1e-3),
+                                   ("B7", a.Bt[7], b.Bt[7], sc.refnet[3][1], 1e-3)):
+        assert _frac_differing(x, y, before.to(cuda), lr) < 1e-2, name
+    assert float((a.adam["sdf"][1] - b.adam["sdf"][1]).abs().max()) <= 1e-3 * float(b.adam["sdf"][1].abs().max())
+    assert int(a.ws["k0_brick_flags"].sum()) == 0 and float(a.g_sdf.abs().max()) == 0.0   # cleared by the optimiser
+    # argument errors come back as RuntimeError, like every other entry point
+    a._S.side_stream = torch.cuda.current_stream().cuda_stream
+    with pytest.raises(RuntimeError):
+        a.train_step(ro, rd, vd, tgt, 5003)
