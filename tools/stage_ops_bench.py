@@ -121,17 +121,28 @@ def main():
     loop_ms = a.elapsed_time(b) / args.steps
     st = tr.stats()
     batch = [t[:N].contiguous() for t in (ro, rd, vd, tgt)]
-    for i in range(5):
-        eng.train_step(*batch, 5100 + i)
-    torch.cuda.synchronize()
-    a.record()
-    for i in range(args.steps):
-        eng.train_step(*batch, 5200 + i)
-    b.record()
-    b.synchronize()
-    bare_ms = a.elapsed_time(b) / args.steps
-    rows.append(dict(op="FineTrainer iteration vs bare train_step (160^3, 8192 rays)", loop_ms_per_step=round(loop_ms, 4),
-                     bare_ms_per_step=round(bare_ms, 4), loop_rays_per_s=round(N / loop_ms * 1e3),
+    import time as _time
+
+    def bare(native, first):
+        eng.native_step = native
+        for i in range(5):
+            eng.train_step(*batch, first + i)
+        torch.cuda.synchronize()
+        a.record()
+        t0 = _time.perf_counter()
+        for i in range(args.steps):
+            eng.train_step(*batch, first + 100 + i)
+        cpu_ms = (_time.perf_counter() - t0) * 1e3 / args.steps      # host time to ENQUEUE an iteration
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / args.steps, cpu_ms
+
+    host_ms, host_cpu = bare(False, 5100)
+    lib_ms, lib_cpu = bare(True, 5400)
+    rows.append(dict(op="training iteration, 160^3, 8192 rays: FineTrainer loop / bare step sequenced by the library / by Python",
+                     trainer_loop_ms_per_step=round(loop_ms, 4), trainer_loop_rays_per_s=round(N / loop_ms * 1e3),
+                     library_sequenced_ms_per_step=round(lib_ms, 4), library_sequenced_host_enqueue_ms=round(lib_cpu, 4),
+                     python_sequenced_ms_per_step=round(host_ms, 4), python_sequenced_host_enqueue_ms=round(host_cpu, 4),
                      psnr=round(st["psnr"], 3), steps=args.steps))
     print(json.dumps(rows[-1]), flush=True)
     if args.out:
