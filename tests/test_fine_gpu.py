@@ -493,7 +493,7 @@ def test_gemm_weight_gradient_kernel(cuda, M, N, K, pairs):
     try:
         _dw_case(cuda, M, N, K)
     finally:
-        check(lib.fgs_set_mlp_dw_pairs(0))
+        check(lib.fgs_set_mlp_dw_pairs(1))      # the library default
 
 
 def _dw_case(cuda, M, N, K):
@@ -624,7 +624,7 @@ def test_mlp_chain_on_cta_pairs(cuda):
         a = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(False), N=512)
         b = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(True), N=512)
     finally:
-        engine.set_mlp_chain_pairs(False)
+        engine.set_mlp_chain_pairs(True)        # the library default
     assert a["cnt"] == b["cnt"] and a["cnt"]["M2"] > 256
     assert torch.equal(a["rgb"], b["rgb"])
     for k in ("g_sdf", "g_k0", "g_mlp"):
