@@ -156,3 +156,19 @@ def test_oracle_resize_matches_golden_and_handoff_composes():
     want = F.conv3d(F.pad(x, (2,) * 6, mode="replicate"), w)[0, 0].numpy()
     got = stage_ref.init_sdf_from_sdf(STAGE["vol"], (20, 17, 23), smooth=False, reduce=0.3)
     assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+def test_ranks_draw_the_same_global_batch_and_shard_it():
+    """Data parallel: every rank runs the same index stream (same seed) and keeps its contiguous slice of the global
+    batch (dist.ray_shard), so the union over ranks is exactly the reference's single-process batch."""
+    from fgs_nerf_b200 import training
+    from fgs_nerf_b200.dist import ray_shard
+    want = GOLD["batches_N1000_BS96_seed123"]
+    world = 4
+    samplers = [training.DeviceBatchSampler(1000, 96, "cpu", rng=np.random.RandomState(123)) for _ in range(world)]
+    for b in range(len(want)):
+        parts = []
+        for r, smp in enumerate(samplers):
+            lo, hi = ray_shard(96, world, r)
+            parts.append(next(smp)[lo:hi].numpy().copy())
+        assert np.array_equal(np.concatenate(parts), want[b])
