@@ -10,6 +10,7 @@
       it is called when importable, like the reference does.
 """
 import ctypes as C
+import itertools
 
 import numpy as np
 import torch
@@ -21,22 +22,21 @@ from . import engine  # noqa: F401  (registers the ctypes signatures of include/
 
 
 def extract_fields(bound_min, bound_max, resolution, query_func, N=64):
+    """Any scalar field on the resolution^3 lattice between the two corners, queried in N^3 blocks in the reference's
+    block order; the result is assembled on the device and copied to the host once."""
     dev = bound_min.device if torch.is_tensor(bound_min) else None
-    X = torch.linspace(float(bound_min[0]), float(bound_max[0]), resolution, device=dev).split(N)
-    Y = torch.linspace(float(bound_min[1]), float(bound_max[1]), resolution, device=dev).split(N)
-    Z = torch.linspace(float(bound_min[2]), float(bound_max[2]), resolution, device=dev).split(N)
-    u = None
+    axes = [torch.linspace(float(bound_min[c]), float(bound_max[c]), resolution, device=dev) for c in range(3)]
+    starts = list(range(0, resolution, N))
+    field = None
     with torch.no_grad():
-        for xi, xs in enumerate(X):
-            for yi, ys in enumerate(Y):
-                for zi, zs in enumerate(Z):
-                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
-                    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                    val = query_func(pts).reshape(len(xs), len(ys), len(zs)).detach()
-                    if u is None:
-                        u = torch.zeros([resolution] * 3, dtype=torch.float32, device=val.device)
-                    u[xi * N: xi * N + len(xs), yi * N: yi * N + len(ys), zi * N: zi * N + len(zs)] = val
-    return u.cpu().numpy()
+        for x0, y0, z0 in itertools.product(starts, starts, starts):
+            sub = [ax[o:o + N] for ax, o in zip(axes, (x0, y0, z0))]
+            pts = torch.stack(torch.meshgrid(*sub, indexing='ij'), dim=-1).reshape(-1, 3)
+            val = query_func(pts).detach().reshape([len(t) for t in sub])
+            if field is None:
+                field = torch.zeros((resolution,) * 3, dtype=torch.float32, device=val.device)
+            field[x0:x0 + val.shape[0], y0:y0 + val.shape[1], z0:z0 + val.shape[2]] = val
+    return field.cpu().numpy()
 
 
 @torch.no_grad()
