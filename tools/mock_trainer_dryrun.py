@@ -110,4 +110,28 @@ with tempfile.TemporaryDirectory() as td:
 assert start == tr.global_step and e2.adam_step == tr.engine.adam_step and e2.lr == tr.engine.lr
 assert torch.equal(e2.k0, tr.engine.k0) and torch.equal(e2.weights[4], tr.engine.weights[4])
 assert torch.equal(e2.nonempty_mask, tr.engine.nonempty_mask)
+from fgs_nerf_b200 import nerf as nerf_mod  # noqa: E402
+
+mc = nerf_mod.MaskCache(mask_cache_thres=1e-3, sdf_mask=sc.mask_grid, xyz_min=sc.mask_xyz_min, xyz_max=sc.mask_xyz_max)
+kw = dict(xyz_min=[-1, -1, -1], xyz_max=[1, 1, 1], num_voxels=24 ** 3, num_voxels_base=24 ** 3, mask_cache=mc,
+          fast_color_thres=1e-4, ref=True, grad_feat=(0.5, 1.0, 1.5, 2.0), sdf_feat=(0.5, 1.0, 1.5, 2.0), s_ratio=50,
+          s_start=0.05, stage="fine", n_rays=N, device=dev)
+model = nerf_mod.nerf(**kw)
+assert tuple(model.sdf.grid.shape) == (1, 1, 24, 24, 24) and tuple(model.k0.grid.shape) == (1, 12, 24, 24, 24)
+rk = dict(near=2.0, far=6.0, stepsize=0.5, bg=1.0, render_depth=True, render_grad=True)
+full = model(rays[0][:N], rays[1][:N], rays[2][:N], **rk)
+part = model(rays[0][:10], rays[1][:10], rays[2][:10], **rk)
+ref_keys = ["alphainv_cum", "weights", "ray_id", "viewdirs", "rgb_marched", "sigmoid_rgb", "normal_marched", "normal",
+            "raw_alpha", "raw_rgb", "depth", "disp", "mask", "mask_outbbox", "gradient", "s_val"]
+print("missing keys:", [k for k in ref_keys if k not in full], [k for k in ref_keys if k not in part])
+assert part["rgb_marched"].shape == (10, 3) and part["alphainv_cum"].shape == (10,)
+sd = model.state_dict()
+model.load_state_dict(sd)
+model.scale_volume_grid(model.num_voxels * (32 / 24) ** 3)
+assert model.world_size.tolist() == [32, 32, 32]
+try:
+    nerf_mod.nerf(**dict(kw, stage="coarse"))
+    raise SystemExit("coarse stage must be refused")
+except NotImplementedError:
+    pass
 print("dry run ok")
