@@ -2,9 +2,7 @@
 "Python-class API to keep"): constructor keywords, `model(rays_o, rays_d, viewdirs, global_step=..., **render_kwargs)`
 with the reference's result keys, `load_state_dict` / `state_dict` in the reference's key layout -- against the oracle's
 forward_fine (oracle/nerf_ref.py + the reference's compiled kernels).
-
-NOTE: written at the very end of round 1, after the round's GPU budget was spent: the Python control flow was
-dry-run on the CPU (tools/mock_trainer_dryrun.py) but this file has not yet run on a GPU.  It sorts last on purpose."""
+"""
 import json
 import os
 import sys
