@@ -153,6 +153,9 @@ class FineTrainer:
     *_tr          flattened training rays [n_total,3] on the engine's device (what get_training_rays_* return)
     cfg_train     reference-style dict (tv_terms nested or flat)
     start         the loop runs global_step = start + 1 ... (checkpoint resume: nerf_training.py:120-133)
+    rng           numpy RandomState of the batch index stream (None: numpy's global state, which the reference seeds
+                  in run.py).  Data parallel: every rank must run the SAME stream (same seed) -- each keeps its
+                  contiguous slice of the global batch (dist.ray_shard), the last rank owns the batch's last ray.
     """
 
     def __init__(self, engine, rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, cfg_train=None, start=0, near=2.0, bg=1.0,
