@@ -24,11 +24,14 @@ from split_numerics_probe import SCHEMES, mm_split  # noqa: E402
 
 
 class SplitLinear(torch.autograd.Function):
+    """Linear whose three GEMMs (forward, backward-data, weight gradient) use emulated operand splits; `bwd` may name
+    a different split for the two backward products."""
+
     @staticmethod
-    def forward(ctx, x, w, b, rnd, terms):
+    def forward(ctx, x, w, b, fwd, bwd):
         ctx.save_for_backward(x, w)
-        ctx.s = (rnd, terms)
-        return mm_split(x, w.T.contiguous(), rnd, terms) + b
+        ctx.s = bwd
+        return mm_split(x, w.T.contiguous(), fwd[0], fwd[1]) + b
 
     @staticmethod
     def backward(ctx, g):
@@ -70,15 +73,17 @@ def run(G, N):
         a, b = a.detach().double(), b.detach().double()
         return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300)), float((a - b).norm() / b.norm().clamp_min(1e-300))
 
-    for name, sch in SCHEMES.items():
-        if sch is None:
-            continue
+    t32 = SCHEMES["3xTF32  (hh+hl+lh)          [today]"]
+    bf3 = SCHEMES["3xBF16  (hh+hm+mh)"]
+    cases = [(name, sch, sch) for name, sch in SCHEMES.items() if sch is not None]
+    cases.append(("forward 3xTF32, backward-data + weight gradients 3xBF16", t32, bf3))
+    for name, sch, sch_bwd in cases:
         it = iter(masks)
         flips = [0]
 
-        def split_mlp(x, layers, sch=sch):
+        def split_mlp(x, layers, sch=sch, sch_bwd=sch_bwd):
             for i, (w, b) in enumerate(layers):
-                x = SplitLinear.apply(x, w, b, sch[0], sch[1])
+                x = SplitLinear.apply(x, w, b, sch, sch_bwd)
                 if i + 1 < len(layers):
                     mk = next(it)
                     flips[0] += int(((x > 0) != mk).sum())
