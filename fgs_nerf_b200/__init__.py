@@ -1,8 +1,10 @@
-"""Import shim: the package directory is `fgs-nerf_b200/` (not a valid Python identifier);
-`import fgs_nerf_b200` resolves to it."""
-import os as _os
+"""fgs_b200: B200-native (sm_100a) implementation of FGS-NeRF's per-ray training/rendering hot
+path, behind the reference's own operator API.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "fgs-nerf_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Submodules (imported lazily -- importing any of them loads libfgs_b200.so and fails loudly if
+it has not been built):
+  render_utils_cuda, adam_upd_cuda, total_variation_cuda   module-level ops (reference names)
+  grid (DenseGrid, MaskGrid, create_grid), adam (MaskedAdam), nerf (nerf, Alphas2Weights, MaskCache)
+  engine (FineStepEngine: fused fwd+bwd+TV+Adam step), scene (synthetic scenes of SURVEY 8d)
+"""
+__version__ = "0.1.0"

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libfgs_b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it first (python __graft_entry__.py build, or "
-        f"python fgs-nerf_b200/build.py). fgs_b200 has no CPU / eager fallback.")
+        f"python fgs_nerf_b200/build.py). fgs_b200 has no CPU / eager fallback.")
 
 lib = C.CDLL(LIB_PATH)
 

@@ -21,7 +21,7 @@ def _declared():
 def test_library_exports_header_symbols():
     import __graft_entry__ as ge
     ge.build()
-    path = os.path.join(ROOT, "fgs-nerf_b200", "libfgs_b200.so")
+    path = os.path.join(ROOT, "fgs_nerf_b200", "libfgs_b200.so")
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     names = _declared()
@@ -41,7 +41,7 @@ def test_ctypes_signatures_cover_header():
 
 def test_product_does_not_import_oracle():
     """The product package must never route through oracle/ (test infrastructure only)."""
-    pkg = os.path.join(ROOT, "fgs-nerf_b200")
+    pkg = os.path.join(ROOT, "fgs_nerf_b200")
     bad = []
     for dirpath, _, files in os.walk(pkg):
         for fn in files:

@@ -47,10 +47,10 @@ from fgs_nerf_b200 import _lib  # noqa: E402
 _lib.check_input = lambda *a, **k: None
 _lib.stream = lambda: 0
 _lib.check = lambda rc: None
-src = open(os.path.join(ROOT, "fgs-nerf_b200", "engine.py")).read().replace('if self.device.type != "cuda":', "if False:").replace("assert grid.is_cuda and", "assert")
+src = open(os.path.join(ROOT, "fgs_nerf_b200", "engine.py")).read().replace('if self.device.type != "cuda":', "if False:").replace("assert grid.is_cuda and", "assert")
 mod = types.ModuleType("fgs_nerf_b200.engine")
 mod.__package__ = "fgs_nerf_b200"
-mod.__file__ = os.path.join(ROOT, "fgs-nerf_b200", "engine.py")
+mod.__file__ = os.path.join(ROOT, "fgs_nerf_b200", "engine.py")
 sys.modules["fgs_nerf_b200.engine"] = mod
 exec(compile(src, mod.__file__, "exec"), mod.__dict__)
 fgs_nerf_b200.engine = mod
