@@ -88,15 +88,18 @@ def checkpoint_dict(eng, global_step):
                                 c["rgbnet_width"])
     kwargs = {   # nerf.get_kwargs (model/nerf.py:309-329)
         "xyz_min": eng.xyz_min.cpu().numpy(), "xyz_max": eng.xyz_max.cpu().numpy(),
-        "num_voxels": eng.num_voxels, "num_voxels_base": eng.num_voxels, "voxel_size": torch.tensor(float(eng.voxel_size)),
+        "num_voxels": eng.num_voxels, "num_voxels_base": eng.num_voxels_base, "voxel_size": torch.tensor(float(eng.voxel_size)),
         "nearest": False, "k0_dim": c["k0_dim"], "grad_feat": tuple(c["grad_feat"]), "sdf_feat": tuple(c["sdf_feat"]),
         "center_sdf": True, "fast_color_thres": float(c["fast_color_thres"]), "stage": "fine", "ref": True,
         "use_viewdir": True, "s_ratio": c["s_ratio"], "s_start": c["s_start"],
         "rgbnet_dim": rgb_dim, "rgbnet_width": c["rgbnet_width"], "rgbnet_depth": c["rgbnet_depth"],
         "refnet_dim": ref_dim, "refnet_width": c["refnet_width"], "refnet_depth": c["refnet_depth"],
     }
+    # voxel_size_ratio = voxel_size / voxel_size_base, voxel_size_base from num_voxels_base (model/nerf.py:68, 303)
+    ext = (eng.xyz_max - eng.xyz_min).float()
+    voxel_size_base = (ext.prod() / eng.num_voxels_base).pow(1 / 3)
     mc = {"xyz_min": eng.xyz_min.cpu().numpy(), "xyz_max": eng.xyz_max.cpu().numpy(),      # get_MaskCache_kwargs (:331-337)
-          "voxel_size_ratio": torch.tensor(1.0), "nearest": False}
+          "voxel_size_ratio": torch.tensor(float(eng.voxel_size)) / voxel_size_base, "nearest": False}
     return {"global_step": int(global_step), "model_kwargs": kwargs, "MaskCache_kwargs": mc,
             "model_state_dict": model_state_dict(eng, global_step), "optimizer_state_dict": optimizer_state_dict(eng)}
 
@@ -135,6 +138,7 @@ def engine_from_checkpoint(ckpt, n_rays, device="cuda", model_cfg=None, train_cf
     eng = FineStepEngine(sc, n_rays, device, train_cfg=train_cfg, **kw)
     if "num_voxels" in mk:
         eng.num_voxels = mk["num_voxels"]
+    eng.num_voxels_base = mk.get("num_voxels_base", eng.num_voxels)
     if "nonempty_mask" in sd:
         eng.nonempty_mask = sd["nonempty_mask"].to(eng.device).reshape(eng.X, eng.Y, eng.Z).contiguous()
         eng.n_nonempty = int(eng.nonempty_mask.sum().item())

@@ -209,7 +209,7 @@ adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, floa
   const long long nth = (long long)gridDim.x * kBlock;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = tid; i < n4; i += nth) {
-    const float4 g = ld_stream4(grad + 4 * i);
+    const float4 g = ld4(grad + 4 * i);       // plain load: this kernel also WRITES grad (ld.global.nc would be UB)
     float4 p = ld4(param + 4 * i), m = ld4(exp_avg + 4 * i), v = ld4(exp_avg_sq + 4 * i);
     adam_elem(p.x, g.x, m.x, v.x, c, c.step_size);
     adam_elem(p.y, g.y, m.y, v.y, c, c.step_size);

@@ -12,10 +12,6 @@ int launch_feat(const FgsFineParams& P, cudaStream_t st);
 int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st);
 int launch_composite(const FgsFineParams& P, const FgsFineLoss* L, cudaStream_t st);
 int launch_level1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t st);
-int gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-         int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-         const int32_t* rows_dev, cudaStream_t st);
-int colsum(const float* X, int ld, int rows, int N, const int32_t* rows_dev, float* out, cudaStream_t st);
 }  // namespace fine
 
 namespace {
@@ -34,33 +30,7 @@ int check_params(const FgsFineParams* p) {
 
 float* hidden(const FgsFineParams& P, int i) { return P.H + (size_t)i * P.cap_m2 * W; }
 
-// 1 = tcgen05 3xTF32 tensor-core GEMMs (default), 0 = fp32 SIMT GEMMs (gemm.cu)
-int g_backend = 1;
-
 uint32_t* hbits(const FgsFineParams& P, int i) { return P.hbits + (size_t)i * P.cap_m2 * 8; }
-
-// One MLP GEMM of the fused step.  layer: which weight matrix (modes 0/1); hid: hidden buffer whose
-// ReLU mask is produced (mode 0 with relu) or applied (mode 1), -1 for none.
-int mm(const FgsFineParams& P, int mode, int layer, int hid, int M, int N, int K, const float* A, int lda,
-       const float* B, int ldb, float* C, int ldc, const float* bias, int relu, const int32_t* rows_dev,
-       cudaStream_t st, float* gbias = nullptr) {
-  if (!g_backend) {
-    const float* mask = (mode == 1 && hid >= 0) ? hidden(P, hid) : nullptr;
-    int rc = gemm(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, W, rows_dev, st);
-    if (!rc && mode == 2 && gbias) rc = colsum(A, lda, K, M, rows_dev, gbias, st);   // bias gradient
-    return rc;
-  }
-  if (mode == 2) return gemm_tn(M, N, K, A, lda, B, ldb, C, ldc, gbias, rows_dev, st);
-  const WSplitLayout L = wsplit_layout();
-  if (mode == 0)
-    return gemm_w(M, N, K, A, lda, P.w_split + L.hi[layer], P.w_split + L.lo[layer], L.in_ld[layer], C, ldc, bias,
-                  relu, nullptr, (relu && hid >= 0) ? hbits(P, hid) : nullptr, rows_dev, st);
-  return gemm_w(M, N, K, A, lda, P.w_split + L.thi[layer], P.w_split + L.tlo[layer], L.ldt[layer], C, ldc, nullptr,
-                0, hid >= 0 ? hbits(P, hid) : nullptr, nullptr, rows_dev, st);
-}
-
-int g_fusion = 1;
-bool use_chain() { return g_backend && g_fusion && tmem_accumulate_enabled(); }
 
 // forward step `layer`: C = act(A W_layer^T + b_layer) (straight planes)
 ChainStepHost fwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer, const float* A, int lda, int K,
@@ -87,7 +57,6 @@ ChainStepHost bwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer,
 
 // hi / lo TF32 planes of the 8 weight matrices, straight and transposed, in one launch
 int prep_weights(const FgsFineParams& P, cudaStream_t st) {
-  if (!g_backend) return 0;
   FGS_REQUIRE(P.w_split != nullptr && P.hbits != nullptr, "w_split / hbits workspace is NULL");
   const WSplitLayout L = wsplit_layout();
   SplitJobHost jobs[2 * FGS_MLP_LAYERS];
@@ -110,16 +79,6 @@ int fgs_set_dw_sm_reserve(int n_sms) {
   return 0;
 }
 
-int fgs_set_mlp_fusion(int on) {
-  g_fusion = on ? 1 : 0;
-  return 0;
-}
-
-int fgs_set_gemm_backend(int tensor_core) {
-  g_backend = tensor_core ? 1 : 0;
-  return 0;
-}
-
 int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
   int rc = check_params(p);
   if (rc) return rc;
@@ -130,32 +89,18 @@ int fgs_fine_forward(const FgsFineParams* p, fgs_stream_t stream) {
   const int* m2 = P.counters + FGS_CNT_M2;
   const int cap = P.cap_m2;
   if ((rc = prep_weights(P, st))) return rc;
-  if (use_chain()) {
-    // rgbnet (model/nerf.py:125-134, 877) and refnet (:136-151, 883-884) as one persistent launch
-    const WSplitLayout L = wsplit_layout();
-    const ChainStepHost steps[8] = {
-        fwd_step(P, L, 0, P.X0, FGS_X0_LD, FGS_X0_LD, hidden(P, 0), W, W, 1, 0),
-        fwd_step(P, L, 1, hidden(P, 0), W, W, hidden(P, 1), W, W, 1, 1),
-        fwd_step(P, L, 2, hidden(P, 1), W, W, hidden(P, 2), W, W, 1, 2),
-        fwd_step(P, L, 3, hidden(P, 2), W, W, P.XR, FGS_XR_LD, W, 0, -1),
-        fwd_step(P, L, 4, P.XR, FGS_XR_LD, FGS_XR_LD, hidden(P, 3), W, W, 1, 3),
-        fwd_step(P, L, 5, hidden(P, 3), W, W, hidden(P, 4), W, W, 1, 4),
-        fwd_step(P, L, 6, hidden(P, 4), W, W, hidden(P, 5), W, W, 1, 5),
-        fwd_step(P, L, 7, hidden(P, 5), W, W, P.logit, 4, 3, 0, -1)};
-    if ((rc = mlp_chain(steps, 8, cap, m2, st))) return rc;
-    if (P.skip_composite) return 0;
-    return launch_composite(P, nullptr, st);
-  }
-  // rgbnet (model/nerf.py:125-134, 877)
-  if ((rc = mm(P, 0, 0, 0, cap, W, FGS_X0_LD, P.X0, FGS_X0_LD, P.W[0], FGS_X0_LD, hidden(P, 0), W, P.B[0], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 1, 1, cap, W, W, hidden(P, 0), W, P.W[1], W, hidden(P, 1), W, P.B[1], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 2, 2, cap, W, W, hidden(P, 1), W, P.W[2], W, hidden(P, 2), W, P.B[2], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 3, -1, cap, W, W, hidden(P, 2), W, P.W[3], W, P.XR, FGS_XR_LD, P.B[3], 0, m2, st))) return rc;
-  // refnet (model/nerf.py:136-151, 883-884)
-  if ((rc = mm(P, 0, 4, 3, cap, W, FGS_XR_LD, P.XR, FGS_XR_LD, P.W[4], FGS_XR_LD, hidden(P, 3), W, P.B[4], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 5, 4, cap, W, W, hidden(P, 3), W, P.W[5], W, hidden(P, 4), W, P.B[5], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 6, 5, cap, W, W, hidden(P, 4), W, P.W[6], W, hidden(P, 5), W, P.B[6], 1, m2, st))) return rc;
-  if ((rc = mm(P, 0, 7, -1, cap, 3, W, hidden(P, 5), W, P.W[7], W, P.logit, 4, P.B[7], 0, m2, st))) return rc;
+  // rgbnet (model/nerf.py:125-134, 877) and refnet (:136-151, 883-884) as one persistent launch
+  const WSplitLayout L = wsplit_layout();
+  const ChainStepHost steps[8] = {
+      fwd_step(P, L, 0, P.X0, FGS_X0_LD, FGS_X0_LD, hidden(P, 0), W, W, 1, 0),
+      fwd_step(P, L, 1, hidden(P, 0), W, W, hidden(P, 1), W, W, 1, 1),
+      fwd_step(P, L, 2, hidden(P, 1), W, W, hidden(P, 2), W, W, 1, 2),
+      fwd_step(P, L, 3, hidden(P, 2), W, W, P.XR, FGS_XR_LD, W, 0, -1),
+      fwd_step(P, L, 4, P.XR, FGS_XR_LD, FGS_XR_LD, hidden(P, 3), W, W, 1, 3),
+      fwd_step(P, L, 5, hidden(P, 3), W, W, hidden(P, 4), W, W, 1, 4),
+      fwd_step(P, L, 6, hidden(P, 4), W, W, hidden(P, 5), W, W, 1, 5),
+      fwd_step(P, L, 7, hidden(P, 5), W, W, P.logit, 4, 3, 0, -1)};
+  if ((rc = mlp_chain(steps, 8, cap, m2, st))) return rc;
   if (P.skip_composite) return 0;   // training: fgs_fine_loss runs the compositing with the loss fused
   return launch_composite(P, nullptr, st);
 }
@@ -177,15 +122,14 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
   if (rc) return rc;
   FGS_REQUIRE(l && l->g_alphainv_last, "loss descriptor incomplete");
   FGS_REQUIRE(phase >= 0 && phase <= 2, "phase must be 0 (all), 1 (data path) or 2 (weight gradients)");
-  const bool chain = use_chain() && p->dZ;
-  if (phase == 2 && !chain) return 0;      // per-layer path: everything ran in phase 1
+  FGS_REQUIRE(p->dZ != nullptr, "dZ workspace is NULL");
   const FgsFineParams& P = *p;
   cudaStream_t st = (cudaStream_t)stream;
   const int* m2 = P.counters + FGS_CNT_M2;
   const int cap = P.cap_m2;
   const int in_dim[8] = {FGS_X0_LD, W, W, W, FGS_XR_LD, W, W, W};
   const int out_dim[8] = {W, W, W, W, W, W, W, 3};
-  if (chain) {
+  {
     const WSplitLayout L = wsplit_layout();
     auto dz = [&](int i) { return P.dZ + (size_t)i * P.cap_m2 * W; };   // dZ6, dZ5, dZ4, dZ2, dZ1, dZ0
     if (phase != 2) {
@@ -228,43 +172,6 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
     }
     return 0;
   }
-  if (P.g_mlp_flat && P.g_mlp_floats > 0) {
-    if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
-  } else {
-    for (int i = 0; i < 8; ++i) {
-      if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
-      if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
-    }
-  }
-  fgs::prof_mark("memset", st);
-  // ---- refnet, last layer first.  dZ = gradient at a layer's pre-activation ----
-  // layer 7: logit = H5 W7^T + b7
-  if ((rc = mm(P, 2, -1, -1, 3, W, cap, P.dlogit, 4, hidden(P, 5), W, P.gW[7], W, nullptr, 0, m2, st, P.gB[7]))) return rc;
-  if ((rc = mm(P, 1, 7, 5, cap, W, 3, P.dlogit, 4, P.W[7], W, P.dA, W, nullptr, 0, m2, st))) return rc;
-  // layer 6: H5 = relu(H4 W6^T + b6); dA = dZ6
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 4), W, P.gW[6], W, nullptr, 0, m2, st, P.gB[6]))) return rc;
-  if ((rc = mm(P, 1, 6, 4, cap, W, W, P.dA, W, P.W[6], W, P.dB, W, nullptr, 0, m2, st))) return rc;
-  // layer 5: dB = dZ5
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 3), W, P.gW[5], W, nullptr, 0, m2, st, P.gB[5]))) return rc;
-  if ((rc = mm(P, 1, 5, 3, cap, W, W, P.dB, W, P.W[5], W, P.dA, W, nullptr, 0, m2, st))) return rc;
-  // layer 4: H3 = relu(XR W4^T + b4); dA = dZ4; dXR = dZ4 W4 (no mask: XR is not a ReLU output)
-  if ((rc = mm(P, 2, -1, -1, W, FGS_XR_LD, cap, P.dA, W, P.XR, FGS_XR_LD, P.gW[4], FGS_XR_LD, nullptr, 0, m2, st, P.gB[4]))) return rc;
-  if ((rc = mm(P, 1, 4, -1, cap, FGS_XR_LD, W, P.dA, W, P.W[4], FGS_XR_LD, P.dXR, FGS_XR_LD, nullptr, 0, m2, st))) return rc;
-  // ---- rgbnet: dZ3 = dXR[:, 0:256] (last rgbnet layer is linear) ----
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dXR, FGS_XR_LD, hidden(P, 2), W, P.gW[3], W, nullptr, 0, m2, st, P.gB[3]))) return rc;
-  if ((rc = mm(P, 1, 3, 2, cap, W, W, P.dXR, FGS_XR_LD, P.W[3], W, P.dB, W, nullptr, 0, m2, st))) return rc;
-  // layer 2
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dB, W, hidden(P, 1), W, P.gW[2], W, nullptr, 0, m2, st, P.gB[2]))) return rc;
-  if ((rc = mm(P, 1, 2, 1, cap, W, W, P.dB, W, P.W[2], W, P.dA, W, nullptr, 0, m2, st))) return rc;
-  // layer 1
-  if ((rc = mm(P, 2, -1, -1, W, W, cap, P.dA, W, hidden(P, 0), W, P.gW[1], W, nullptr, 0, m2, st, P.gB[1]))) return rc;
-  if ((rc = mm(P, 1, 1, 0, cap, W, W, P.dA, W, P.W[1], W, P.dB, W, nullptr, 0, m2, st))) return rc;
-  // layer 0
-  if ((rc = mm(P, 2, -1, -1, W, FGS_X0_LD, cap, P.dB, W, P.X0, FGS_X0_LD, P.gW[0], FGS_X0_LD, nullptr, 0, m2, st, P.gB[0]))) return rc;
-  if ((rc = mm(P, 1, 0, -1, cap, FGS_X0_LD, W, P.dB, W, P.W[0], FGS_X0_LD, P.dX0, FGS_X0_LD, nullptr, 0, m2, st))) return rc;
-  // ---- features -> level-1 quantities -> grids ----
-  if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
-  return launch_level1_bwd(P, l->g_alphainv_last, st);
 }
 
 }  // extern "C"

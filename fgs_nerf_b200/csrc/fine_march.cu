@@ -23,6 +23,13 @@ using namespace fine;
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 
+// workspace overflow: the per-forward bit AND the sticky word that only the host clears (an asynchronous training
+// loop reads the counters every i_print iterations; the per-forward word only ever shows the last one)
+__device__ __forceinline__ void flag_overflow(int* counters, int bit) {
+  atomicOr(counters + FGS_CNT_OVERFLOW, bit);
+  atomicOr(counters + FGS_CNT_STICKY, bit);
+}
+
 __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ FgsFineParams P) {
   const int lane = lane_id();
   const GridGeo mg = make_geo(P.mask_xyz_min, P.mask_xyz_max, P.mX, P.mY, P.mZ);
@@ -41,7 +48,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
       P.t_min[ray] = is.t_min;
       P.t_max[ray] = is.t_max;
       P.n_steps[ray] = (int)(n64 < 0x7fffffffLL ? n64 : 0x7fffffffLL);
-      if (n64 > cap) atomicOr(P.counters + FGS_CNT_OVERFLOW, 1);
+      if (n64 > cap) flag_overflow(P.counters, 1);
       tot_steps += n64;
     }
     const Ray r = make_ray(o, d, is.t_min);
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
     if (lane_id() == 31) {
       off[n] = sc;
       counters[slot] = sc;
-      if (sc > cap) atomicOr(counters + FGS_CNT_OVERFLOW, overflow_bit);
+      if (sc > cap) flag_overflow(counters, overflow_bit);
     }
   }
   __syncthreads();
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant_
 namespace fine {
 
 int launch_march(const FgsFineParams& P, cudaStream_t st) {
-  int rc = fgs::check_cuda(cudaMemsetAsync(P.counters, 0, sizeof(int32_t) * FGS_NUM_COUNTERS, st),
+  int rc = fgs::check_cuda(cudaMemsetAsync(P.counters, 0, sizeof(int32_t) * FGS_CNT_STICKY, st),
                            "fine counters memset");
   if (rc) return rc;
   fgs::prof_mark("memset", st);

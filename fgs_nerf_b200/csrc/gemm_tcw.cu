@@ -351,192 +351,6 @@ __device__ __forceinline__ uint32_t epilogue_block(float* v, uint32_t bias_addr,
   return out_bits;
 }
 
-// Warp-specialised: issuer, producers and consumers only meet at mbarriers
-//   a_full[st]   producers -> MMA     (128 arrivals: the A hi/lo slab is stored and proxy-fenced)
-//   b_full[st]   TMA       -> MMA     (expect_tx: B hi/lo bytes landed)
-//   free[st]     MMA       -> producers, TMA (tcgen05.commit: the MMAs reading the stage are done)
-//   r_full[r]    MMA       -> consumers (tcgen05.commit at the end of a 32-k chunk)
-//   r_empty[r]   consumers -> MMA     (256 arrivals: the chunk has been added into registers)
-// The producers run up to kStages slabs ahead of the tensor core (across tile boundaries), the tensor
-// core up to kRegions chunks ahead of the consumers, so the epilogue of tile t overlaps the MMAs of
-// tile t + 1 and nobody waits for a block-wide barrier.
-__global__ void __launch_bounds__(kThreadsWS, 1)
-gemm_w_kernel(const WArgs a, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-              const __grid_constant__ CUtensorMap tm_c) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t smem = smem_u32(smem_raw);
-  const Bars B = make_bars(smem);
-
-  int M = a.M;
-  if (a.rows_dev) M = min(M, *a.rows_dev);
-  const int n0 = blockIdx.x * TN;
-  const int n_tiles = (M + BM - 1) / BM;
-  if ((int)blockIdx.y >= n_tiles) return;
-  const int K = a.K;
-  const int BN = min(TN, (a.N - n0 + 15) & ~15);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid < TN) reinterpret_cast<float*>(smem_raw + kBiasOff)[tid] = (a.bias && n0 + tid < a.N) ? a.bias[n0 + tid] : 0.f;
-  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducers);
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                         ((uint32_t)(BM >> 4) << 24);
-
-  const uint32_t n_slabs = (uint32_t)((K + BK - 1) / BK);
-  const int my_tiles = (n_tiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1;
-  const uint32_t total_slabs = (uint32_t)my_tiles * n_slabs;
-  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-
-  if (warp >= kIssuerWarp) {
-    // ================= MMA + TMA issuer (one thread of warp 12) =================
-    if (warp == kIssuerWarp && lane == 0) {
-      constexpr uint32_t kPfB = kStages - 1;
-      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
-      if (dbg_cta) t_all = clock64();
-      auto issue_b = [&](uint32_t gs) {
-        const uint32_t st = gs % kStages;
-        const uint32_t b_hi = smem + st * kStage + 2 * kATile, b_lo = b_hi + kBTile;
-        const uint32_t bar = B.bfull0 + 8 * st;
-        const int k0 = (int)(gs % n_slabs) * BK;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBTile) : "memory");
-        tma_load_2d(b_hi, &tm_hi, bar, k0, n0);
-        tma_load_2d(b_lo, &tm_lo, bar, k0, n0);
-      };
-      for (uint32_t gs = 0; gs < kPfB && gs < total_slabs; ++gs) issue_b(gs);
-      for (uint32_t g = 0; g < total_slabs; ++g) {      // global slab index = global chunk index
-        const uint32_t st = g % kStages;
-        const uint32_t par = (g / kStages) & 1;
-        if (dbg_cta) t0 = clock64();
-        mbar_wait(B.afull0 + 8 * st, par);
-        if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
-        mbar_wait(B.bfull0 + 8 * st, par);
-        if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
-        if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
-        if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma_slab(tmem_d + (g % kRegions) * TN, smem + st * kStage, idesc);
-        mma_commit(B.free0 + 8 * st);
-        mma_commit(B.rfull0 + 8 * (g % kRegions));
-        const uint32_t gs = g + kPfB;   // B two slabs ahead; its stage was read by slab gs - kStages
-        if (gs < total_slabs) {
-          if (dbg_cta) t0 = clock64();
-          if (gs >= (uint32_t)kStages) mbar_wait(B.free0 + 8 * (gs % kStages), ((gs / kStages) - 1) & 1);
-          if (dbg_cta) t_f += clock64() - t0;
-          issue_b(gs);
-        }
-      }
-      if (dbg_cta) {
-        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
-      }
-    }
-  } else if (warp >= kConsumers / 32) {
-    // ================= producers: activation slabs -> hi / lo TF32 tiles =================
-    // warp pw owns tile rows [32 pw, 32 pw + 32); load i (0..7) covers rows 4 i + lane / 8 with lane % 8 =
-    // 16-byte k-chunk: 8 lanes read one full 128-byte row (coalesced), and since chunk c of row r lives at
-    // chunk position c ^ (r % 8) the quarter-warp's stores fill one permuted 128-byte row (conflict-free)
-    const int pw = warp - kConsumers / 32;
-    const int prow = pw * 32 + (lane >> 3), pc = lane & 7;
-    const bool dbg_on = dbg_cta && tid == kConsumers;
-    long long t_wait = 0, t_work = 0, t0 = 0;
-    auto load_a = [&](float4 (&v)[8], uint32_t gs) {
-      if (gs >= total_slabs) return;
-      const int tile = (int)blockIdx.y + (int)(gs / n_slabs) * (int)gridDim.y;
-      const int k = (int)(gs % n_slabs) * BK + 4 * pc;
-      const float* __restrict__ src = a.A + (size_t)(tile * BM + prow) * a.lda + k;
-      const int mleft = M - (tile * BM + prow);          // rows 4 i with 4 i < mleft are valid
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * a.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    auto produce = [&](float4 (&v)[8], uint32_t g) {
-      const uint32_t st = g % kStages;
-      const uint32_t stage_base = smem + st * kStage;
-      if (dbg_on) t0 = clock64();
-      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
-      if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = prow + 4 * i;
-        const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
-        split_store(stage_base + off, stage_base + kATile + off, v[i]);
-      }
-      load_a(v, g + 2);                                  // two slabs stay in flight
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
-      if (dbg_on) t_work += clock64() - t0;
-    };
-    float4 v0[8], v1[8];
-    load_a(v0, 0);
-    load_a(v1, 1);
-    for (uint32_t g = 0; g < total_slabs; g += 2) {
-      produce(v0, g);
-      if (g + 1 < total_slabs) produce(v1, g + 1);
-    }
-    if (dbg_on) { a.dbg[3] = t_wait; a.dbg[4] = t_work; }
-  } else {
-    // ================= consumers: TMEM drain, epilogue =================
-    const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
-    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
-    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
-    const uint32_t bias_s = smem + kBiasOff;
-    uint32_t gc = 0;
-    long long t_main = 0, t_epi = 0, t0 = 0;
-    const bool dbg_on = dbg_cta && tid == 0;
-
-    for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-      const int m0 = tile * BM;
-      if (dbg_on) t0 = clock64();
-      float acc[kAcc];
-#pragma unroll
-      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-      for (uint32_t c = 0; c < n_slabs; ++c) drain_chunk<true>(acc, tmem_row, col_half, gc + c, BN, B.rfull0, B.rempty0);
-      gc += n_slabs;
-      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
-
-      // ---- epilogue: (bias, ReLU, mask) in registers -> swizzled 32 x 128-byte block -> one TMA store ----
-      const int mr0 = m0 + quarter * 32;
-      const int m = mr0 + lane;                                  // the row this thread accumulated
-#pragma unroll
-      for (int q = 0; q < kAcc / 32; ++q) {
-        const int c0 = col_half + 32 * q;
-        if (c0 < BN) {
-          const int word = (n0 + c0) >> 5;
-          uint32_t in_bits = 0xffffffffu, out_bits = 0;
-          if (a.bits_in && m < M) in_bits = a.bits_in[(size_t)m * 8 + word];
-          float* v = acc + 32 * q;
-          const uint32_t baddr = bias_s + 4 * c0;
-          const bool hb = a.bias != nullptr;
-          if (a.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
-          else if (a.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
-          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
-          if (a.bits_out && m < M) a.bits_out[(size_t)m * 8 + word] = out_bits;
-          if (a.c_tma && mr0 + 32 <= M) {
-            if (lane == 0) tma_store_wait_read();                // the previous block has left the staging tile
-            __syncwarp();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
-                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tma_store_2d(&tm_c, stg, n0 + c0, mr0);   // columns >= N are clipped by the map
-          } else if (m < M) {
-            // the 32-row block straddles the device-side row count (or C is not TMA-addressable): row stores
-            float* __restrict__ cp = a.C + (size_t)m * a.ldc + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < a.N) cp[j] = v[j];
-          }
-        }
-      }
-      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
-    }
-    if (lane == 0) tma_store_wait_all();
-    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; a.dbg[2] = 0; }
-  }
-  cta_teardown(tmem_d, warp);
-}
-
 // ---- fast variant: whole-K accumulation in TMEM, 256-column tiles --------------------------------------
 // gemm_w_kernel keeps the tensor core's accumulation chains short (12 MMAs, then a round-to-nearest add on
 // the CUDA cores) because the TMEM accumulator truncates at every MMA; that costs 128-column tiles (the
@@ -780,235 +594,6 @@ struct ChainArgs {
 struct ChainMaps {
   CUtensorMap hi[kChainMaxSteps], lo[kChainMaxSteps], c[kChainMaxSteps];
 };
-
-__global__ void __launch_bounds__(kThreadsF, 1)
-mlp_chain_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t smem = smem_u32(smem_raw);
-  const Bars B = make_bars(smem);
-  const uint32_t cdone0 = smem + kCDoneOff;
-
-  int M = a.M;
-  if (a.rows_dev) M = min(M, *a.rows_dev);
-  const int n_tiles = (M + BM - 1) / BM;
-  if ((int)blockIdx.x >= n_tiles) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0)
-    for (int i = 0; i < kChainMaxTiles; ++i) mbar_init(cdone0 + 8 * i, 8);   // lane 0 of the 8 consumer warps
-  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersF);
-
-  const int my_tiles = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
-  const int n_items = a.n_steps * my_tiles;                  // item w: step w / my_tiles, local tile w % my_tiles
-  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
-
-  if (warp >= kIssuerWarpF) {
-    // ================= MMA + TMA issuer =================
-    if (warp == kIssuerWarpF && lane == 0) {
-      long long t_a = 0, t_b = 0, t_r = 0, t_f = 0, t_all = 0, t0 = 0;
-      if (dbg_cta) t_all = clock64();
-      auto issue_b = [&](int step, int kt, uint32_t gs) {
-        const ChainStep& S = a.s[step];
-        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
-        const int n_boxes = BN > 128 ? 2 : 1;
-        const uint32_t st = gs % kStagesF;
-        const uint32_t b_hi = smem + st * kStageF + 2 * kATile, b_lo = b_hi + kBTileF;
-        const uint32_t bar = B.bfull0 + 8 * st;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_boxes * 2 * kBTile) : "memory");
-        for (int bx = 0; bx < n_boxes; ++bx) {
-          tma_load_2d(b_hi + bx * kBTile, &maps.hi[step], bar, kt * BK, S.n0 + 128 * bx);
-          tma_load_2d(b_lo + bx * kBTile, &maps.lo[step], bar, kt * BK, S.n0 + 128 * bx);
-        }
-      };
-      issue_b(0, 0, 0);
-      uint32_t g = 0;
-      for (int w = 0; w < n_items; ++w) {
-        const int step = w / my_tiles;
-        const ChainStep& S = a.s[step];
-        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
-        const int n_slabs = (S.K + BK - 1) / BK;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(BM >> 4) << 24);
-        const uint32_t rg = (uint32_t)w & 1;
-        for (int kt = 0; kt < n_slabs; ++kt, ++g) {
-          const uint32_t st = g % kStagesF;
-          const uint32_t par = (g / kStagesF) & 1;
-          if (dbg_cta) t0 = clock64();
-          mbar_wait(B.afull0 + 8 * st, par);
-          if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
-          mbar_wait(B.bfull0 + 8 * st, par);
-          if (dbg_cta) { const long long t1 = clock64(); t_b += t1 - t0; t0 = t1; }
-          if (kt == 0 && w >= 2) mbar_wait(B.rempty0 + 8 * rg, (((uint32_t)w >> 1) - 1) & 1);
-          if (dbg_cta) { const long long t1 = clock64(); t_r += t1 - t0; }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          {
-            const uint32_t stage_base = smem + st * kStageF, d = tmem_d + rg * TNF;
-            const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
-            const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTileF;
-#pragma unroll
-            for (int j = 0; j < BK / 8; ++j) {
-              const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
-              const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-              mma_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);
-              mma_tf32(d, dah, dbl, idesc, 1);
-              mma_tf32(d, dah, dbh, idesc, 1);
-            }
-          }
-          mma_commit(B.free0 + 8 * st);
-          if (kt == n_slabs - 1) mma_commit(B.rfull0 + 8 * rg);
-          // weights of the next slab (possibly the first slab of the next item: weights have no dependency)
-          int nstep = step, nkt = kt + 1;
-          if (nkt == n_slabs) { nkt = 0; nstep = (w + 1) / my_tiles; }
-          if (nkt != 0 || w + 1 < n_items) {
-            const uint32_t gs = g + 1;
-            if (dbg_cta) t0 = clock64();
-            if (gs >= (uint32_t)kStagesF) mbar_wait(B.free0 + 8 * (gs % kStagesF), ((gs / kStagesF) - 1) & 1);
-            if (dbg_cta) t_f += clock64() - t0;
-            issue_b(nstep, nkt, gs);
-          }
-        }
-      }
-      if (dbg_cta) {
-        a.dbg[5] = t_a; a.dbg[6] = t_b; a.dbg[7] = t_r; a.dbg[8] = t_f; a.dbg[9] = clock64() - t_all;
-      }
-    }
-  } else if (warp >= kConsumers / 32) {
-    // ================= producers: activation slabs -> hi / lo TF32 tiles =================
-    const int pw = warp - kConsumers / 32;
-    const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
-    const bool dbg_on = dbg_cta && tid == kConsumers;
-    long long t_wait = 0, t_work = 0, t_dep = 0, t0 = 0;
-    uint32_t g = 0;
-    for (int w = 0; w < n_items; ++w) {
-      const int step = w / my_tiles, lt = w - step * my_tiles;
-      const ChainStep& S = a.s[step];
-      const int K = S.K, lda = S.lda;
-      const int n_slabs = (K + BK - 1) / BK;
-      const int row = ((int)blockIdx.x + lt * (int)gridDim.x) * BM + prow;
-      const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
-      const int mleft = M - row;
-      if (step > 0) {
-        // the tile's rows of this step's input were stored by the consumers of (tile, step - 1)
-        if (dbg_on) t0 = clock64();
-        mbar_wait_relaxed(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        if (dbg_on) t_dep += clock64() - t0;
-      }
-      auto load_a = [&](float4 (&v)[4], int kt) {
-        if (kt >= n_slabs) return;
-        const int k = kt * BK + 4 * pc;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      auto produce = [&](float4 (&v)[4], int kt) {
-        const uint32_t st = g % kStagesF;
-        const uint32_t stage_base = smem + st * kStageF;
-        if (dbg_on) t0 = clock64();
-        if (g >= (uint32_t)kStagesF) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesF) - 1) & 1);
-        if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = prow + 4 * i;
-          const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
-          split_store(stage_base + off, stage_base + kATile + off, v[i]);
-        }
-        load_a(v, kt + 2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
-        ++g;
-        if (dbg_on) t_work += clock64() - t0;
-      };
-      float4 v0[4], v1[4];
-      load_a(v0, 0);
-      load_a(v1, 1);
-      for (int kt = 0; kt < n_slabs; kt += 2) {
-        produce(v0, kt);
-        if (kt + 1 < n_slabs) produce(v1, kt + 1);
-      }
-    }
-    if (dbg_on) { a.dbg[2] = t_dep; a.dbg[3] = t_wait; a.dbg[4] = t_work; }
-  } else {
-    // ================= consumers: epilogue of item w while item w + 1 multiplies =================
-    const int quarter = warp & 3, col_half = (warp >> 2) * (TNF / 2);
-    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
-    const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
-    long long t_main = 0, t_epi = 0, t0 = 0;
-    const bool dbg_on = dbg_cta && tid == 0;
-    for (int w = 0; w < n_items; ++w) {
-      const int step = w / my_tiles, lt = w - step * my_tiles;
-      const ChainStep& S = a.s[step];
-      const int n0 = S.n0, N = S.N;
-      const int BN = min(TNF, (N - n0 + 15) & ~15);
-      const uint32_t rg = (uint32_t)w & 1;
-      const uint32_t bias_s = smem + kBiasOff + rg * (TNF * 4);
-      // bias slice of this item (the other buffer may still be read by a slower warp of item w - 1)
-      reinterpret_cast<float*>(smem_raw + kBiasOff)[rg * TNF + tid] = (S.bias && n0 + tid < N) ? S.bias[n0 + tid] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (dbg_on) t0 = clock64();
-      mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
-      const int m0 = ((int)blockIdx.x + lt * (int)gridDim.x) * BM;
-      const int mr0 = m0 + quarter * 32;
-      const int m = mr0 + lane;
-#pragma unroll 1
-      for (int q = 0; q < TNF / 2 / 32; ++q) {
-        const int c0 = col_half + 32 * q;
-        if (c0 < BN) {
-          float v[32];
-          {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
-            tmem_ld16(tmem_row + rg * TNF + 32 * q + 16, r1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
-          }
-          const int word = (n0 + c0) >> 5;
-          uint32_t in_bits = 0xffffffffu, out_bits = 0;
-          if (S.bits_in && m < M) in_bits = S.bits_in[(size_t)m * 8 + word];
-          const uint32_t baddr = bias_s + 4 * c0;
-          const bool hb = S.bias != nullptr;
-          if (S.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
-          else if (S.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
-          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
-          if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + word] = out_bits;
-          if (S.c_tma && mr0 + 32 <= M) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
-                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tma_store_2d(&maps.c[step], stg, n0 + c0, mr0);
-          } else if (m < M) {
-            float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < N) cp[j] = v[j];
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(B.rempty0 + 8 * rg);                 // item w + 2 may overwrite the region
-      // the tile's rows of this step are complete in global memory -> (tile, step + 1) may load them
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_wait_all();
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __threadfence();
-        mbar_arrive(cdone0 + 8 * lt);
-      }
-      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
-    }
-    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
-  }
-  cta_teardown(tmem_d, warp);
-}
 
 // ---- the same chain on CTA PAIRS (tcgen05 cta_group::2): M = 256 per MMA, each SM holds half of the weights -----
 // In the single-CTA chain every SM streams the whole 64 KB weight slab per 32 k and its tensor core reads 12 KB
@@ -1396,177 +981,6 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t addr) {
          (1ull << 61);
 }
 
-__global__ void __launch_bounds__(kThreadsTn, 1) mlp_dw_kernel(const __grid_constant__ DwArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t smem = smem_u32(smem_raw);
-  const Bars B = make_bars(smem);
-
-  int K = a.K;
-  if (a.rows_dev) K = min(K, *a.rows_dev);
-  const int n_slabs = (K + BK - 1) / BK;
-  const long long units = (long long)a.n_tiles * n_slabs;
-  const int u_beg = (int)(units * blockIdx.x / gridDim.x), u_end = (int)(units * (blockIdx.x + 1) / gridDim.x);
-  if (u_beg >= u_end) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t tmem_d = cta_setup(smem_raw, B, warp, tid, kProducersTn);
-  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
-
-  if (warp >= kIssuerWarpTn) {
-    if (warp == kIssuerWarpTn && lane == 0) {
-      uint32_t g = 0;
-      long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
-      if (dbg_cta) t_all = clock64();
-      for (int u = u_beg; u < u_end;) {
-        const int tile = u / n_slabs, s0 = u - tile * n_slabs;
-        const int len = min(n_slabs - s0, u_end - u);
-        const DwProblem& P = a.p[a.tile_prob[tile]];
-        const int BN = min(TN, (P.N - a.tile_n[tile] * TN + 15) & ~15);
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // A and B MN-major
-        for (int i = 0; i < len; ++i, ++g) {
-          const uint32_t st = g % kStages;
-          if (dbg_cta) t0 = clock64();
-          mbar_wait(B.afull0 + 8 * st, (g / kStages) & 1);
-          if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
-          if (g >= (uint32_t)kRegions) mbar_wait(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
-          if (dbg_cta) t_r += clock64() - t0;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t stage_base = smem + st * kStage, d = tmem_d + (g % kRegions) * TN;
-          const uint32_t a_hi = stage_base, a_lo = stage_base + kATile;
-          const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBTile;
-#pragma unroll
-          for (int j = 0; j < BK / 8; ++j) {            // k-step j = sample rows [8 j, 8 j + 8) of every block
-            const uint64_t dah = make_desc_mn(a_hi + j * 1024), dal = make_desc_mn(a_lo + j * 1024);
-            const uint64_t dbh = make_desc_mn(b_hi + j * 1024), dbl = make_desc_mn(b_lo + j * 1024);
-            mma_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
-            mma_tf32(d, dah, dbl, idesc, 1);
-            mma_tf32(d, dah, dbh, idesc, 1);
-          }
-          mma_commit(B.free0 + 8 * st);
-          mma_commit(B.rfull0 + 8 * (g % kRegions));
-        }
-        u += len;
-      }
-      if (dbg_cta) { a.dbg[5] = t_a; a.dbg[6] = 0; a.dbg[7] = t_r; a.dbg[8] = g; a.dbg[9] = clock64() - t_all; }
-    }
-  } else if (warp >= kConsumers / 32) {
-    // ================= producers: split both operands, no transposition =================
-    // warp pw owns sample rows 4 pw .. 4 pw + 3 of every slab; lane l owns features 4 l .. 4 l + 3 of the tile
-    const int pw = warp - kConsumers / 32;
-    // smem offset of (features 4 l.., sample row r): block l / 8, row r, 32-byte chunk ((l % 8) / 2) ^ (r % 4)
-    const uint32_t lane_blk = (uint32_t)(lane >> 3) * 4096u + (uint32_t)(lane & 1) * 16u;
-    const uint32_t lane_c32 = (uint32_t)((lane & 7) >> 1);
-    uint32_t g = 0;
-    // flattened walk over the CTA's (tile, slab) units with two slabs in flight
-    struct Cur { int u, tile, s; };
-    auto advance = [&](Cur& c) {                       // next unit
-      ++c.u; ++c.s;
-      if (c.s == n_slabs) { c.s = 0; ++c.tile; }
-    };
-    auto load_ab = [&](float4 (&va)[4], float4 (&vb)[4], const Cur& c) {
-      if (c.u >= u_end) return;
-      const DwProblem& P = a.p[a.tile_prob[c.tile]];
-      const int fa = a.tile_m[c.tile] * BM + 4 * lane, fb = a.tile_n[c.tile] * TN + 4 * lane;
-      const int k0 = c.s * BK + 4 * pw;
-      const bool in_a = fa < P.M, in_b = fb < P.N;     // (rows are padded to 4 floats: lda, ldb % 4 == 0)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool kin = k0 + i < K;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-        // (features M .. round_up(M, 4) - 1 of a row are read too: they only reach output rows / columns >= M / N,
-        // which are never stored)
-        if (kin && in_a) x = ldcg4(P.A + (size_t)(k0 + i) * P.lda + fa);
-        if (kin && in_b) y = ldcg4(P.B + (size_t)(k0 + i) * P.ldb + fb);
-        va[i] = x; vb[i] = y;
-      }
-    };
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);     // bias-gradient partial sums of this lane's 4 features
-    auto flush_colsum = [&](int tile) {
-      const DwProblem& P = a.p[a.tile_prob[tile]];
-      if (P.colsum && a.tile_n[tile] == 0) {
-        const int f = a.tile_m[tile] * BM + 4 * lane;
-        if (f < P.M && cs.x != 0.f) atomicAdd(P.colsum + f, cs.x);
-        if (f + 1 < P.M && cs.y != 0.f) atomicAdd(P.colsum + f + 1, cs.y);
-        if (f + 2 < P.M && cs.z != 0.f) atomicAdd(P.colsum + f + 2, cs.z);
-        if (f + 3 < P.M && cs.w != 0.f) atomicAdd(P.colsum + f + 3, cs.w);
-      }
-      cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    auto produce = [&](float4 (&va)[4], float4 (&vb)[4], const Cur& c, Cur& pf) {
-      const uint32_t st = g % kStages;
-      const uint32_t stage_base = smem + st * kStage;
-      if (g >= (uint32_t)kStages) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages) - 1) & 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
-        const uint32_t r = (uint32_t)(4 * pw + i);
-        const uint32_t off = lane_blk + r * 128u + ((lane_c32 ^ (r & 3u)) * 32u);
-        split_store(stage_base + off, stage_base + kATile + off, va[i]);
-        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBTile + off, vb[i]);
-      }
-      if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);   // last slab of this tile in the range
-      load_ab(va, vb, pf);                               // two slabs stay in flight
-      advance(pf);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // one arrival per producer warp
-      ++g;
-    };
-    Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs}, pf = c;
-    float4 va0[4], vb0[4], va1[4], vb1[4];
-    load_ab(va0, vb0, pf); advance(pf);
-    load_ab(va1, vb1, pf); advance(pf);
-    while (c.u < u_end) {
-      produce(va0, vb0, c, pf); advance(c);
-      if (c.u < u_end) { produce(va1, vb1, c, pf); advance(c); }
-    }
-  } else {
-    // ================= consumers: TMEM drain, red.global.add epilogue per tile segment =================
-    const int quarter = warp & 3, col_half = (warp >> 2) * kAcc;
-    const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
-    float* stg = reinterpret_cast<float*>(smem_raw + kStagingOff + warp * kStagingWarp);
-    uint32_t g = 0;
-    const bool dbg_c = dbg_cta && tid == 0;
-    long long t_main = 0, t_epi = 0, t0c = 0;
-    for (int u = u_beg; u < u_end;) {
-      const int tile = u / n_slabs, s0 = u - tile * n_slabs;
-      const int len = min(n_slabs - s0, u_end - u);
-      const DwProblem& P = a.p[a.tile_prob[tile]];
-      const int m0 = a.tile_m[tile] * BM, n0 = a.tile_n[tile] * TN;
-      const int BN = min(TN, (P.N - n0 + 15) & ~15);
-      float acc[kAcc];
-#pragma unroll
-      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-      if (dbg_c) t0c = clock64();
-      for (int i = 0; i < len; ++i, ++g) drain_chunk<false>(acc, tmem_row, col_half, g, BN, B.rfull0, B.rempty0);
-      if (dbg_c) { const long long t1 = clock64(); t_main += t1 - t0c; t0c = t1; }
-      // ---- registers -> 32x32 smem transpose (XOR-swizzled columns) -> 128-byte red.global.add rows ----
-#pragma unroll
-      for (int q = 0; q < kAcc / 32; ++q) {
-        const int c0 = col_half + 32 * q;
-        if (c0 < BN) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = acc[32 * q + j];
-          __syncwarp();
-          const int col = n0 + c0 + lane;
-          if (col < P.N) {
-            const int mr0 = m0 + quarter * 32;
-            float* __restrict__ cp = P.C + (size_t)mr0 * P.ldc + col;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-              if (mr0 + r < P.M) atomicAdd(cp + (size_t)r * P.ldc, stg[r * 32 + (lane ^ r)]);
-          }
-          __syncwarp();
-        }
-      }
-      u += len;
-      if (dbg_c) t_epi += clock64() - t0c;
-    }
-    if (dbg_c) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
-  }
-  cta_teardown(tmem_d, warp);
-}
-
 // ---- the same on CTA pairs (cta_group::2): a pair owns a 256 (all out-features) x 128 output tile ----------------
 // Each CTA produces the MN-major tile of ITS 128 out-features of dZ (A) and of ITS half of the tile's input features
 // of X (B): per slab 48 KB of st.shared per SM instead of 64 KB, for twice the output, and one M256 N128 K8 MMA
@@ -1820,10 +1234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
 
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
-int g_chain_pairs = 1;     // 1: mlp_chain2_kernel (CTA pairs, tcgen05 cta_group::2)
-int g_dw_pairs = 1;        // 1: mlp_dw2_kernel (CTA pairs)
 int g_dw_sm_reserve = 0;
-int g_tmem_accumulate = 1;   // 1: gemm_wf_kernel (whole-K TMEM accumulation), 0: gemm_w_kernel (32-k chunks)
 
 template <typename Kern>
 int configure_once(Kern kern, bool& configured, const char* what, uint32_t smem_bytes) {
@@ -1899,10 +1310,8 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
     return fgs::fail_arg("gemm_w needs 16-byte aligned operands with leading dimensions % 4 == 0");
   if (K > ldb) return fgs::fail_arg("gemm_w: K exceeds the weight plane's row length");
   const int n_tiles = fgs::cdiv(M, BM);
-  const bool fast = g_tmem_accumulate != 0;
-  static bool configured = false, configured_f = false;
-  int rc = fast ? configure_once(gemm_wf_kernel, configured_f, "gemm_wf smem attribute", kSmemBytesF)
-                : configure_once(gemm_w_kernel, configured, "gemm_w smem attribute", kSmemBytes);
+  static bool configured_f = false;
+  int rc = configure_once(gemm_wf_kernel, configured_f, "gemm_wf smem attribute", kSmemBytesF);
   if (rc) return rc;
   CUtensorMap tm_hi, tm_lo;
   const int rows_alloc = (N + 7) & ~7;
@@ -1914,14 +1323,11 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
   if (c_tma && (rc = get_map(C, N, M, ldc, 32, &tm_c))) return rc;
   WArgs a{A, C, bias, bits_in, bits_out, rows_dev, M, N, K, lda, ldc, relu, c_tma, g_dbg};
   // persistent CTAs: one per SM, nx column blocks x ny row-tile walkers
-  const int nx = fgs::cdiv(N, fast ? TNF : TN);
+  const int nx = fgs::cdiv(N, TNF);
   int ny = FGS_NUM_SMS / nx;
   if (ny > n_tiles) ny = n_tiles;
   if (ny < 1) ny = 1;
-  if (fast)
-    gemm_wf_kernel<<<dim3(nx, ny, 1), kThreadsF, kSmemBytesF, st>>>(a, tm_hi, tm_lo, tm_c);
-  else
-    gemm_w_kernel<<<dim3(nx, ny, 1), kThreadsWS, kSmemBytes, st>>>(a, tm_hi, tm_lo, tm_c);
+  gemm_wf_kernel<<<dim3(nx, ny, 1), kThreadsF, kSmemBytesF, st>>>(a, tm_hi, tm_lo, tm_c);
   return fgs::check_launch("gemm_w", st);
 }
 
@@ -1930,14 +1336,8 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
 int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st) {
   if (M <= 0 || n_steps <= 0) return 0;
   if (n_steps > kChainMaxSteps) return fgs::fail_arg("mlp_chain: too many steps");
-  const int n_tiles = fgs::cdiv(M, BM);
-  int grid = FGS_NUM_SMS;
-  if (grid > n_tiles) grid = n_tiles;
-  if (fgs::cdiv(n_tiles, grid) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
-  static bool configured = false, configured2 = false;
-  const bool pairs = g_chain_pairs != 0;
-  int rc = pairs ? configure_once(mlp_chain2_kernel, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2)
-                 : configure_once(mlp_chain_kernel, configured, "mlp_chain smem attribute", kSmemBytesChain);
+  static bool configured2 = false;
+  int rc = configure_once(mlp_chain2_kernel, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
   if (rc) return rc;
   ChainArgs a;
   ChainMaps maps;
@@ -1959,16 +1359,12 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   }
   for (int i = n_steps; i < kChainMaxSteps; ++i) { maps.hi[i] = maps.hi[0]; maps.lo[i] = maps.lo[0]; maps.c[i] = maps.c[0]; }
   a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = M;
-  if (pairs) {
-    // CTA pairs (static cluster size 2): the grid is a whole number of pairs
-    const int n_pair_tiles = fgs::cdiv(M, 2 * BM);
-    int pairs_n = FGS_NUM_SMS / 2;
-    if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
-    if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
-    mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
-  } else {
-    mlp_chain_kernel<<<grid, kThreadsF, kSmemBytesChain, st>>>(a, maps);
-  }
+  // CTA pairs (static cluster size 2): the grid is a whole number of pairs
+  const int n_pair_tiles = fgs::cdiv(M, 2 * BM);
+  int pairs_n = FGS_NUM_SMS / 2;
+  if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
+  if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
+  mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
   return fgs::check_launch("mlp_chain", st);
 }
 
@@ -1978,64 +1374,37 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
 int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st) {
   if (n <= 0 || K <= 0) return 0;
   if (n > kDwMaxProblems) return fgs::fail_arg("mlp_dw: too many problems");
-  DwArgs a;
-  memset(&a, 0, sizeof(a));
-  int nt = 0;
+  // CTA pairs: a pair owns all (<= 256) out-features x one 128-wide block of input features
+  Dw2Args b;
+  memset(&b, 0, sizeof(b));
+  int nt2 = 0;
   for (int i = 0; i < n; ++i) {
     const DwProblemHost& h = probs[i];
     if (h.M <= 0 || h.N <= 0) continue;
     if ((h.lda & 3) || (h.ldb & 3) || (((uintptr_t)h.A | (uintptr_t)h.B) & 15))
       return fgs::fail_arg("mlp_dw needs 16-byte aligned operands with leading dimensions % 4 == 0");
     if (((h.M + 3) & ~3) > h.lda || ((h.N + 3) & ~3) > h.ldb) return fgs::fail_arg("mlp_dw: operand rows must be padded to 4 floats");
-    DwProblem& p = a.p[i];
+    if (h.M > 2 * BM) return fgs::fail_arg("mlp_dw: more than 256 out-features");
+    DwProblem& p = b.p[i];
     p.A = h.A; p.B = h.B; p.C = h.C; p.colsum = h.colsum;
     p.M = h.M; p.N = h.N; p.lda = h.lda; p.ldb = h.ldb; p.ldc = h.ldc;
-    for (int m = 0; m < fgs::cdiv(h.M, BM); ++m)
-      for (int c = 0; c < fgs::cdiv(h.N, TN); ++c) {
-        if (nt >= kDwMaxTiles) return fgs::fail_arg("mlp_dw: more than 32 output tiles");
-        a.tile_prob[nt] = (unsigned char)i; a.tile_m[nt] = (unsigned char)m; a.tile_n[nt] = (unsigned char)c;
-        ++nt;
-      }
-  }
-  if (nt == 0) return 0;
-  if (g_dw_pairs) {
-    // CTA pairs: a pair owns all (<= 256) out-features x one 128-wide block of input features
-    bool fits = true;
-    for (int i = 0; i < n; ++i) fits = fits && probs[i].M <= 2 * BM;
-    if (fits) {
-      Dw2Args b;
-      memset(&b, 0, sizeof(b));
-      int nt2 = 0;
-      for (int i = 0; i < n; ++i) {
-        b.p[i] = a.p[i];
-        if (probs[i].M <= 0 || probs[i].N <= 0) continue;
-        for (int c = 0; c < fgs::cdiv(probs[i].N, TN); ++c) {
-          b.tile_prob[nt2] = (unsigned char)i; b.tile_n[nt2] = (unsigned char)c;
-          ++nt2;
-        }
-      }
-      b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
-      static bool configured2 = false;
-      int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
-      if (rc2) return rc2;
-      const long long units2 = (long long)nt2 * fgs::cdiv(K, BK);
-      int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
-      if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
-      if (pairs_n < 1) pairs_n = 1;
-      mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
-      return fgs::check_launch("mlp_dw", st);
+    for (int c = 0; c < fgs::cdiv(h.N, TN); ++c) {
+      if (nt2 >= kDwMaxTiles) return fgs::fail_arg("mlp_dw: more than 32 output tiles");
+      b.tile_prob[nt2] = (unsigned char)i; b.tile_n[nt2] = (unsigned char)c;
+      ++nt2;
     }
   }
-  a.n_tiles = nt; a.K = K; a.rows_dev = rows_dev; a.dbg = g_dbg_dw;
-  static bool configured = false;
-  int rc = configure_once(mlp_dw_kernel, configured, "mlp_dw smem attribute", kSmemBytes);
-  if (rc) return rc;
-  // every CTA should own at least ~8 slabs, else the epilogues dominate
-  const long long units = (long long)nt * fgs::cdiv(K, BK);
-  int grid = FGS_NUM_SMS - g_dw_sm_reserve;
-  if (units < 8LL * grid) grid = (int)((units + 7) / 8);
-  if (grid < 1) grid = 1;
-  mlp_dw_kernel<<<grid, kThreadsTn, kSmemBytes, st>>>(a);
+  if (nt2 == 0) return 0;
+  b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
+  static bool configured2 = false;
+  int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
+  if (rc2) return rc2;
+  // every pair should own at least ~8 slabs, else the epilogues dominate
+  const long long units2 = (long long)nt2 * fgs::cdiv(K, BK);
+  int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
+  if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
+  if (pairs_n < 1) pairs_n = 1;
+  mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
   return fgs::check_launch("mlp_dw", st);
 }
 
@@ -2047,7 +1416,6 @@ int gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ld
   return mlp_dw(&p, 1, K, rows_dev, st);
 }
 
-bool tmem_accumulate_enabled() { return g_tmem_accumulate != 0; }
 void set_dw_sm_reserve(int n_sms) { g_dw_sm_reserve = n_sms; }
 
 // ---- weight splitting ------------------------------------------------------------------------
@@ -2104,25 +1472,6 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 extern "C" int fgs_debug_gemm_phases(void* buf) {
   g_dbg = (long long*)buf;
   g_dbg_dw = buf ? (long long*)buf + 10 : nullptr;    // slots 10..19: the weight-gradient kernel
-  return 0;
-}
-
-// MLP chain on CTA pairs (cta_group::2) instead of single CTAs.
-extern "C" int fgs_set_mlp_chain_pairs(int on) {
-  g_chain_pairs = on ? 1 : 0;
-  return 0;
-}
-
-// Weight-gradient kernel on CTA pairs (default) or single CTAs.
-extern "C" int fgs_set_mlp_dw_pairs(int on) {
-  g_dw_pairs = on ? 1 : 0;
-  return 0;
-}
-
-// Accumulation mode of the pre-split GEMMs: 1 = whole K in one TMEM accumulator (fast, ~3e-6 of max|out|),
-// 0 = 32-k chunks added into fp32 registers with round-to-nearest (~3e-7).
-extern "C" int fgs_set_gemm_tmem_accumulate(int on) {
-  g_tmem_accumulate = on ? 1 : 0;
   return 0;
 }
 

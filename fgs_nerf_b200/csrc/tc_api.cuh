@@ -1,4 +1,4 @@
-// Internal interface of the tensor-core GEMM translation units (gemm_tc.cu, gemm_tcw.cu).
+// Internal interface of the tensor-core GEMM translation unit (gemm_tcw.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +33,6 @@ struct ChainStepHost {
   const uint32_t* bits_in; uint32_t* bits_out;
 };
 int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
-bool tmem_accumulate_enabled();
 
 // One weight-gradient problem of mlp_dw (gemm_tcw.cu: mlp_dw_kernel): C[M,N] += A[K,M]^T B[K,N], colsum[m] += sum_k A[k][m]
 struct DwProblemHost {
@@ -43,11 +42,6 @@ struct DwProblemHost {
 int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st);
 // leave n SMs free while mlp_dw runs (a data-parallel step overlaps the gradient exchange with it)
 void set_dw_sm_reserve(int n_sms);
-
-// generic 3xTF32 kernel on raw fp32 operands, modes 0 / 1 / 2 as fgs_gemm   (gemm_tc.cu)
-int gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-            int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-            const int32_t* rows_dev, cudaStream_t st, float* colsum = nullptr);
 
 // Layout of FgsFineParams::w_split: per layer the straight planes [out][in_ld] (forward) and the
 // transposed planes [in_ld][ldt] (backward-data), hi then lo.

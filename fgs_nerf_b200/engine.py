@@ -24,7 +24,7 @@ X0_DIM, X0_LD = 106, 112
 XR_DIM, XR_LD = 307, 320
 K0_DIM = 12
 NUM_COUNTERS = 8
-CNT = dict(M1=0, M2=1, OVERFLOW=2, MA=3, TOTAL_LO=4, TOTAL_HI=5, M0=6)
+CNT = dict(M1=0, M2=1, OVERFLOW=2, MA=3, TOTAL_LO=4, TOTAL_HI=5, M0=6, STICKY=7)
 F_ALPHA, F_VISIT, F_L2 = 1, 2, 4
 
 _fp = C.c_void_p
@@ -104,18 +104,9 @@ _lib.declare("fgs_grid_sample_fwd", C.c_int,
              [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
 _lib.declare("fgs_grid_sample_bwd", C.c_int,
              [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
-_GEMM_SIG = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
-             _fp, C.c_int, _fp, _fp]
-_lib.declare("fgs_gemm", C.c_int, _GEMM_SIG)
-_lib.declare("fgs_gemm_tc", C.c_int, _GEMM_SIG)
-_lib.declare("fgs_set_gemm_backend", C.c_int, [C.c_int])
 _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
-_lib.declare("fgs_set_gemm_tmem_accumulate", C.c_int, [C.c_int])
-_lib.declare("fgs_set_mlp_fusion", C.c_int, [C.c_int])
-_lib.declare("fgs_set_mlp_chain_pairs", C.c_int, [C.c_int])
-_lib.declare("fgs_set_mlp_dw_pairs", C.c_int, [C.c_int])
 _lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
 _i = C.c_int
 _lib.declare("fgs_grid_resize_trilinear", C.c_int, [_fp, _i, _i, _i, _i, _fp, _i, _i, _i, _i, _fp])
@@ -126,27 +117,6 @@ _lib.declare("fgs_gather_rays", C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _i
 _lib.declare("fgs_gemm_tcw", C.c_int,
              [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int,
               _fp, _fp, _fp, _fp])
-
-
-def set_gemm_backend(tensor_core=True):
-    """MLP GEMMs of the fused step: tcgen05 3xTF32 tensor cores (default) or the fp32 SIMT kernel."""
-    check(lib.fgs_set_gemm_backend(int(bool(tensor_core))))
-
-
-def set_gemm_tmem_accumulate(on=True):
-    """Pre-split tensor-core GEMMs: whole-K TMEM accumulation (fast, default) or 32-k chunks + fp32 register
-    accumulators (the most accurate mode)."""
-    check(lib.fgs_set_gemm_tmem_accumulate(int(bool(on))))
-
-
-def set_mlp_chain_pairs(on=True):
-    """MLP chains on CTA pairs (tcgen05 cta_group::2) or on single CTAs."""
-    check(lib.fgs_set_mlp_chain_pairs(int(bool(on))))
-
-
-def set_mlp_fusion(on=True):
-    """Fused step: run each direction of the MLPs as one persistent launch (default) or one launch per layer."""
-    check(lib.fgs_set_mlp_fusion(int(bool(on))))
 
 
 def _c3(t):
@@ -251,31 +221,24 @@ def gather_rays(rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, sel, out=None, bad=No
     return out
 
 
-def gemm(mode, A, B, out, bias=None, relu=False, relu_mask=None, rows_dev=None, M=None, N=None, K=None, tc=False,
-         bits_in=None, bits_out=None):
-    """fgs_gemm / fgs_gemm_tc on 2-D row-major fp32 CUDA tensors (see include/fgs_b200_fine.h)."""
+def gemm(mode, A, B, out, bias=None, relu=False, rows_dev=None, M=None, N=None, K=None, bits_in=None, bits_out=None):
+    """fgs_gemm_tcw on 2-D row-major fp32 CUDA tensors (include/fgs_b200_fine.h): mode 0 = A B^T, 1 = A B."""
     if mode == 0:
         m, k = A.shape; n = B.shape[0]
     elif mode == 1:
         m, k = A.shape; n = B.shape[1]
     else:
-        k, m = A.shape; n = B.shape[1]
+        raise ValueError("mode must be 0 or 1 (the weight-gradient product is fgs_gemm_tn)")
     M, N, K = M or m, N or n, K or k
-    if tc == "w":
-        assert relu_mask is None
-        check(lib.fgs_gemm_tcw(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
-                               ptr(bias), int(relu), ptr(bits_in), ptr(bits_out), ptr(rows_dev), stream()))
-        return out
-    check((lib.fgs_gemm_tc if tc else lib.fgs_gemm)(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
-                       ptr(bias), int(relu), ptr(relu_mask), relu_mask.stride(0) if relu_mask is not None else 0,
-                       ptr(rows_dev), stream()))
+    check(lib.fgs_gemm_tcw(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
+                           ptr(bias), int(relu), ptr(bits_in), ptr(bits_out), ptr(rows_dev), stream()))
     return out
 
 
 class FineStepEngine:
     """State + workspace of the fine-stage model for batches of `n_rays` rays on one GPU."""
 
-    def __init__(self, scene, n_rays, device="cuda", train_cfg=None, cap_m1_per_ray=128, cap_m2_per_ray=16,
+    def __init__(self, scene, n_rays, device="cuda", train_cfg=None, cap_m1_per_ray=192, cap_m2_per_ray=32,
                  world_size=1, rank=0, voxel_exchange=False):
         from .scene import FINE_TRAIN
         self.device = torch.device(device)
@@ -322,6 +285,7 @@ class FineStepEngine:
         X, Y, Z = self.sdf.shape[2:]
         self.X, self.Y, self.Z = X, Y, Z
         self.num_voxels = X * Y * Z          # model.num_voxels (scale_volume_grid multiplies it by scale_ratio)
+        self.num_voxels_base = self.num_voxels   # config value, unchanged by scale_volume_grid (model/nerf.py:67-68)
         # ---- gradients + Adam state ----
         self.g_k0 = torch.zeros_like(self.k0)       # keeps channels_last_3d
         # all 16 MLP gradient tensors are views of one flat buffer (one clear, one all-reduce bucket)
@@ -476,12 +440,26 @@ class FineStepEngine:
     def counters(self):
         """Host copy of the device counters (synchronises)."""
         c = self.ws["counters"].cpu().numpy().astype(np.int64)
-        out = {k: int(c[i]) for k, i in CNT.items() if not k.startswith("TOTAL")}
+        out = {k: int(c[i]) for k, i in CNT.items() if not k.startswith("TOTAL") and k != "STICKY"}
         out["total_len"] = int((c[CNT["TOTAL_HI"]] << 32) | (c[CNT["TOTAL_LO"]] & 0xffffffff))
         if out["OVERFLOW"]:
             raise RuntimeError(f"fgs_b200 fine step: workspace overflow (bits {out['OVERFLOW']:#x}: "
                                f"1=steps/ray, 2=cap_m1 {self.cap_m1}, 4=cap_m2 {self.cap_m2}); counts {out}")
         return out
+
+    def check_overflow(self, clear=True):
+        """Synchronises.  Raises if ANY forward since the last check ran out of workspace: the per-forward overflow word
+        is cleared by every forward, so an asynchronous loop that only looks every i_print iterations would miss the
+        others; counters[STICKY] is only cleared here.  (An overflowing ray's samples are dropped by the kernels, i.e.
+        the gradients of that iteration were wrong.)"""
+        word = self.ws["counters"][CNT["STICKY"]:CNT["STICKY"] + 1]
+        bits = int(word.item())
+        if clear and bits:
+            word.zero_()
+        if bits:
+            raise RuntimeError(f"fgs_b200 fine step: workspace overflow in an earlier iteration (bits {bits:#x}: "
+                               f"1=steps/ray > {self.cap_words * 32}, 2=cap_m1 {self.cap_m1}, 4=cap_m2 {self.cap_m2}); "
+                               f"raise cap_m1_per_ray / cap_m2_per_ray")
 
     def outputs(self):
         """The reference's render_result dict (model/nerf.py:922-939) from the workspace;
@@ -514,41 +492,54 @@ class FineStepEngine:
     def render(self, rays_o, rays_d, viewdirs, global_step=20000, near=2.0, bg=1.0, render_depth=True,
                render_grad=True, world_size=1, rank=0):
         """Full-image rendering (model/utils.py:249-441, render_viewpoints): the rays [R,3] are cut into
-        chunks of self.n_rays (the reference uses 8192, utils.py:296-299), each chunk runs the fused
-        forward, per-ray results are gathered on the device.  With world_size > 1 the chunks are dealt
-        round-robin to the ranks and the results all-gathered (rendering needs no other exchange).
+        chunks of self.n_rays (the reference uses 8192, utils.py:296-299) and each chunk runs the fused
+        forward.  The per-ray outputs of a chunk are written by the kernels STRAIGHT into the image-sized
+        result buffers (the output pointers of the parameter block are re-aimed per chunk: no copies).
+        With world_size > 1 the chunks are dealt round-robin to the ranks and every result is
+        all-gathered once per image -- each rank sends only the pixels it rendered (rendering needs no
+        other exchange).
         Returns rgb_marched, sigmoid_rgb, depth, disp, normal_marched, alphainv_cum, cum_weights."""
         R = rays_o.shape[0]
         N = self.n_rays
         n_chunks = (R + N - 1) // N
+        n_local = (n_chunks + world_size - 1) // world_size        # chunks per rank (the last ranks may idle once)
         dev = self.device
         keys = [("rgb_marched", 3), ("sigmoid_rgb", 3), ("alphainv_last", 1), ("cum_weights", 1)]
         if render_depth:
             keys.append(("depth", 1))
         if render_grad:
             keys.append(("normal_marched", 3))
-        out = {k: torch.zeros((n_chunks * N, c), dtype=torch.float32, device=dev) for k, c in keys}
+        pad = n_chunks * N - R
+        if pad:                                                     # last chunk: repeat the last ray
+            rays_o, rays_d, viewdirs = (torch.cat([t, t[-1:].expand(pad, 3)]) for t in (rays_o, rays_d, viewdirs))
+        rays_o, rays_d, viewdirs = (t.contiguous() for t in (rays_o, rays_d, viewdirs))
+        out = {k: torch.zeros((n_local * N, c), dtype=torch.float32, device=dev) for k, c in keys}
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-        for ci in range(rank, n_chunks, world_size):
-            a, b = ci * N, min(R, (ci + 1) * N)
-            chunk = []
-            for t in (rays_o, rays_d, viewdirs):
-                c = t[a:b].contiguous()
-                if b - a < N:                                   # last chunk: pad by repeating its last ray
-                    c = torch.cat([c, c[-1:].expand(N - (b - a), 3)]).contiguous()
-                chunk.append(c)
-            self.forward(*chunk, global_step=global_step, near=near, bg=bg, render_depth=render_depth,
-                         render_grad=render_grad)
-            for k, c in keys:
-                out[k][a:a + N] = self.ws[k].reshape(N, c)
-            ovf |= self.ws["counters"][CNT["OVERFLOW"]]
+        P = self.P
+        saved = {k: getattr(P, k) for k, _ in keys}
+        try:
+            for li, ci in enumerate(range(rank, n_chunks, world_size)):
+                a = ci * N
+                for k, c in keys:
+                    setattr(P, k, out[k].data_ptr() + li * N * c * 4)
+                self.forward(rays_o[a:a + N], rays_d[a:a + N], viewdirs[a:a + N], global_step=global_step, near=near,
+                             bg=bg, render_depth=render_depth, render_grad=render_grad)
+            ovf |= self.ws["counters"][CNT["STICKY"]]
+        finally:
+            for k, v in saved.items():
+                setattr(P, k, v)
         if world_size > 1:
             import torch.distributed as dist
-            for k in out:
-                dist.all_reduce(out[k])                         # chunks are disjoint across ranks: sum = gather
+            for k, c in keys:
+                full = torch.empty((world_size, n_local * N, c), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(full, out[k])
+                # chunk ci was rendered by rank ci % world as its local chunk ci // world
+                out[k] = full.view(world_size, n_local, N, c).permute(1, 0, 2, 3).reshape(n_local * world_size * N, c)
             dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
-        if int(ovf.item()):
-            raise RuntimeError(f"fgs_b200 render: workspace overflow (bits {int(ovf.item()):#x}); raise cap_m1/cap_m2")
+        bits = int(ovf.item())
+        if bits:
+            self.ws["counters"][CNT["STICKY"]] = 0
+            raise RuntimeError(f"fgs_b200 render: workspace overflow (bits {bits:#x}); raise cap_m1_per_ray / cap_m2_per_ray")
         res = {k: v[:R] for k, v in out.items()}
         res["alphainv_cum"] = res.pop("alphainv_last")[:, 0]
         res["cum_weights"] = res["cum_weights"][:, 0]
@@ -682,6 +673,7 @@ class FineStepEngine:
         self.adam, self.tv_scratch, self.nonempty_mask = {}, None, None
         new = FineStepEngine(sc, **ctor)
         new.num_voxels = num_voxels
+        new.num_voxels_base = self.num_voxels_base
         if had_mask:
             new.set_nonempty_mask()
         new.reset_optimizer(0)

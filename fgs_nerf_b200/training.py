@@ -122,7 +122,14 @@ def end_of_iteration_updates(t, lr, global_step, engine_train_cfg=None, model_cf
         t[term] = value
         if engine_train_cfg is not None:
             engine_train_cfg[term] = value
-    for term, value in t.get("s_updates", {}).get(gs_, {}).items():
+    # s_updates / smooth_updates live in the MODEL config in the reference (getattr(cfg_model, ...), :446-456); the
+    # train cfg is accepted too
+    s_updates = dict(t.get("s_updates", {}))
+    if model_cfg is not None:
+        s_updates.update(model_cfg.get("s_updates", {}))
+        if model_cfg.get("smooth_updates"):
+            raise NotImplementedError("smooth_updates (init_smooth_conv, coarse stages) is not on the fine-stage path")
+    for term, value in s_updates.get(gs_, {}).items():
         if model_cfg is not None:
             model_cfg[term] = value
 
@@ -141,6 +148,8 @@ def flatten_train_cfg(cfg_train):
         raise NotImplementedError("ori_tv / weight_tv_k0 / grad_norm / grad_tv are 0 in every fine-stage config")
     if t.get("voxel_inc", False) or t.get("pervoxel_lr", False) or t.get("reset_iter"):
         raise NotImplementedError("voxel_inc / pervoxel_lr / reset_iter belong to the coarse stages")
+    if t.get("smooth_updates"):
+        raise NotImplementedError("smooth_updates (init_smooth_conv, coarse stages) is not on the fine-stage path")
     if t.get("ray_sampler", "in_maskcache") not in ("flatten", "in_maskcache"):
         raise NotImplementedError(f"ray_sampler {t['ray_sampler']!r}")
     return t
@@ -153,13 +162,18 @@ class FineTrainer:
     *_tr          flattened training rays [n_total,3] on the engine's device (what get_training_rays_* return)
     cfg_train     reference-style dict (tv_terms nested or flat)
     start         the loop runs global_step = start + 1 ... (checkpoint resume: nerf_training.py:120-133)
+    reset_optimizer  None (default): a fresh MaskedAdam at the base learning rates -- create_optimizer_or_freeze_model(...,
+                  global_step=0), nerf_training.py:117 -- UNLESS the engine already carries optimiser state (loaded by
+                  checkpoint.engine_from_checkpoint = utils.load_checkpoint's optimizer.load_state_dict, utils.py:49-56),
+                  which is then kept: moments, step count and the per-group learning rates.  True forces the fresh
+                  optimiser (the reference's --no_reload_optimizer), False never touches the engine's.
     rng           numpy RandomState of the batch index stream (None: numpy's global state, which the reference seeds
                   in run.py).  Data parallel: every rank must run the SAME stream (same seed) -- each keeps its
                   contiguous slice of the global batch (dist.ray_shard), the last rank owns the batch's last ray.
     """
 
     def __init__(self, engine, rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, cfg_train=None, start=0, near=2.0, bg=1.0,
-                 rng=None, ring=256):
+                 rng=None, ring=256, reset_optimizer=None):
         self.engine = engine
         self.cfg_train = flatten_train_cfg(cfg_train if cfg_train is not None else engine.train_cfg)
         engine.train_cfg.update({k: v for k, v in self.cfg_train.items() if k in engine.train_cfg or k in
@@ -179,7 +193,10 @@ class FineTrainer:
         self.global_step = int(start)
         self._ring = torch.zeros((int(ring), 5), dtype=torch.float64, device=dev)
         self._since = 0                      # iterations since the last stats()
-        engine.reset_optimizer(self.global_step)
+        if reset_optimizer is None:
+            reset_optimizer = not (engine.adam and engine.adam_step > 0)
+        if reset_optimizer:
+            engine.reset_optimizer(0)            # the reference always builds the optimiser with global_step=0
 
     # ---------------------------------------------------------------------------------
     def step(self):
@@ -208,6 +225,8 @@ class FineTrainer:
                 s = self.stats()
                 log(f"scene_rep_reconstruction (fine): iter {gs:6d} / Loss: {s['loss']:.9f} / PSNR: {s['psnr']:5.2f} / "
                     f"s_val: {self.engine.s_val(gs):5.2g}")
+        if not i_print:
+            self.engine.check_overflow()               # nobody called stats(): still never return silently corrupted
         return self.global_step
 
     def stats(self, reduce=True):
@@ -226,7 +245,7 @@ class FineTrainer:
         ring = ring.cpu().numpy()
         if int(bad.item()):
             raise RuntimeError("batch index outside the training rays")
-        self.engine.counters()                         # raises on workspace overflow
+        self.engine.check_overflow()                   # sticky over ALL iterations since the last check; raises
         steps = list(range(self.global_step - n + 1, self.global_step + 1))
         if n == 0:
             return dict(steps=steps, loss=float("nan"), psnr=float("nan"), terms=ring[:0], lr=dict(self.engine.lr))

@@ -65,6 +65,8 @@ extern "C" {
 #define FGS_CNT_TOTAL_LO 4  /* total_len = sum of N_steps, low / high 32 bits           */
 #define FGS_CNT_TOTAL_HI 5
 #define FGS_CNT_M0 6        /* samples inside the bbox (before the MaskCache)           */
+#define FGS_CNT_STICKY 7    /* OR of every overflow bit since the HOST last cleared it: fgs_fine_forward clears
+                               counters[0..6] only, so an overflow in any iteration stays visible until read */
 #define FGS_NUM_COUNTERS 8
 
 /* flag1[] bits */
@@ -233,27 +235,15 @@ int fgs_grid_sample_bwd(float* g_grid, int C, int X, int Y, int Z, int channels_
                         const float* xyz, int64_t M, const float* xyz_min, const float* xyz_max,
                         const float* g_out, fgs_stream_t stream);
 
-/* Row-major fp32 GEMM used by the MLPs, exposed for tests:
+/* Row-major fp32 GEMMs of the MLPs on the tcgen05 tensor cores (3xTF32 split, fp32-grade accuracy), exposed
+ * stand-alone for tests and for callers with other layer shapes:
  *   mode 0 (NT): C[M,N] = A[M,K] * B[N,K]^T     mode 1 (NN): C = A[M,K] * B[K,N]
- *   mode 2 (TN): C[M,N] += A[K,M]^T * B[K,N]  (split over K, atomically accumulated)
- * bias (may be NULL) is added per output column; relu!=0 applies max(0,.);
- * relu_mask (may be NULL, [M][ld_mask]) multiplies the result by (relu_mask > 0).
- * The row count of the sample dimension (M for modes 0/1, K for mode 2) is read on the
- * device from *rows_dev when rows_dev != NULL (clamped to the host value). */
-int fgs_gemm(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-             float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-             const int32_t* rows_dev, fgs_stream_t stream);
-
-/* Same contract on the tcgen05 tensor cores (3xTF32 split, fp32-grade accuracy).  Operands must be
- * 16-byte aligned with leading dimensions % 4 == 0, and readable up to the next multiple of 4
- * along their contiguous dimension. */
-int fgs_gemm_tc(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                float* C, int ldc, const float* bias, int relu, const float* relu_mask, int ld_mask,
-                const int32_t* rows_dev, fgs_stream_t stream);
-
-/* modes 0 / 1 with the weight operand B split once into TF32 hi / lo planes (internal scratch) and
- * streamed by TMA -- the kernel the fused step uses for X*W^T and dZ*W.  bits_out (mode 0,
- * relu) receives the ReLU mask as [M][8] words; bits_in (may be NULL) masks the result. */
+ * bias (may be NULL) is added per output column; relu != 0 applies max(0, .).
+ * The row count of the sample dimension is read on the device from *rows_dev when rows_dev != NULL (clamped to
+ * the host value).  Operands must be 16-byte aligned with leading dimensions % 4 == 0. */
+/* The weight operand B is split once into TF32 hi / lo planes (internal scratch) and streamed by TMA; whole-K
+ * accumulation in TMEM (error ~3e-6 of max|out|).  bits_out (mode 0, relu) receives the ReLU mask as [M][8]
+ * words; bits_in (may be NULL) masks the result. */
 int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                  float* C, int ldc, const float* bias, int relu, const uint32_t* bits_in,
                  uint32_t* bits_out, const int32_t* rows_dev, fgs_stream_t stream);
@@ -268,29 +258,9 @@ int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, in
  * a_full / b_full / r_empty / free, issuer total; tools/gemm_phase_probe.py).  NULL = off. */
 int fgs_debug_gemm_phases(void* buf);
 
-/* Accumulation mode of the pre-split tensor-core GEMMs (fgs_gemm_tcw and the fused step):
- * 1 (default) = the whole K dimension accumulates in one TMEM accumulator (128 x 256 tiles; the accumulator
- * truncates at every MMA: error ~3e-6 of max|out|); 0 = 32-k chunks are added into fp32 registers with
- * round-to-nearest (128 x 128 tiles, ~3e-7, about 2x slower).  Both are far inside the 1e-4 parity bar. */
-int fgs_set_gemm_tmem_accumulate(int on);
-
-/* 1 (default): the 8 forward GEMMs and the 8 backward-data GEMMs of the fused step each run as one
- * persistent launch (mlp_chain_kernel; needs the tcgen05 backend with TMEM accumulation); 0: one launch per
- * layer. */
-int fgs_set_mlp_fusion(int on);
-
-/* 1: the MLP chains run on CTA pairs (tcgen05 cta_group::2: 256-row tiles, each SM of a pair holds half of the
- * weight rows); 0: one CTA per 128-row tile. */
-int fgs_set_mlp_chain_pairs(int on);
-/* The same for the weight-gradient kernel (default 1). */
-int fgs_set_mlp_dw_pairs(int on);
-
 /* Timing aid: run only row part `task` (0 k0, 1 encodings, 2 reflection chain, 3..6 displacement levels) of the
  * level-2 feature kernels; -1 = all (default).  Results are incomplete while it is set. */
 int fgs_debug_feat_task(int task);
-
-/* GEMM backend of fgs_fine_forward / fgs_fine_backward: 1 = tcgen05 3xTF32 (default), 0 = fp32 SIMT. */
-int fgs_set_gemm_backend(int tensor_core);
 
 #ifdef __cplusplus
 }

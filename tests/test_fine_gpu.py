@@ -265,38 +265,6 @@ def test_golden_fixture_from_reference_python(cuda):
         assert frac > 0.9, f"{k}: only {frac:.3f} of the rays agree with the CPU fixture"
 
 
-@pytest.mark.parametrize("mode,M,N,K", [(0, 300, 256, 106), (0, 129, 3, 256), (1, 257, 307, 256), (1, 100, 256, 3),
-                                        (2, 256, 307, 1000), (2, 3, 256, 777)])
-def test_gemm_modes(cuda, mode, M, N, K):
-    from fgs_nerf_b200 import engine
-    g = torch.Generator(device="cpu").manual_seed(mode * 1000 + M)
-    r = lambda *s: torch.randn(*s, generator=g).to(cuda)
-    if mode == 0:
-        A, B = r(M, K), r(N, K)
-        want = A.double() @ B.double().T
-    elif mode == 1:
-        A, B = r(M, K), r(K, N)
-        want = A.double() @ B.double()
-    else:
-        A, B = r(K, M), r(K, N)
-        want = A.double().T @ B.double()
-    out = torch.zeros(M, N, device=cuda)
-    rows = torch.tensor([K if mode == 2 else M], dtype=torch.int32, device=cuda)
-    engine.gemm(mode, A, B, out, rows_dev=rows)
-    assert _rel(out, want) < 1e-5
-    if mode != 2:
-        bias = r(N)
-        mask = r(M, N)
-        engine.gemm(mode, A, B, out, bias=bias, relu=True, relu_mask=mask, rows_dev=rows)
-        want2 = torch.relu(want + bias.double()) * (mask > 0)
-        assert _rel(out, want2) < 1e-5
-        # device-side row count smaller than the launch extent: rows beyond it stay untouched
-        out.fill_(7.0)
-        rows.fill_(M // 2)
-        engine.gemm(mode, A, B, out, rows_dev=rows)
-        assert bool((out[M // 2:] == 7.0).all()) and _rel(out[:M // 2], want[:M // 2]) < 1e-5
-
-
 @pytest.mark.parametrize("C,cl", [(1, False), (12, True), (3, False)])
 def test_grid_sample_matches_aten(cuda, C, cl):
     """DenseGrid.forward arithmetic = F.grid_sample(align_corners=True) on CUDA: bit-exact forward."""
@@ -343,70 +311,13 @@ def _tc_case(cuda, mode, M, N, K, seed):
 
 
 @pytest.mark.parametrize("mode,M,N,K", [
-    (0, 300, 256, 112), (0, 129, 3, 256), (0, 1000, 256, 320), (0, 128, 256, 16), (0, 5, 16, 4),
-    (1, 257, 320, 256), (1, 100, 256, 3), (1, 640, 112, 256),
-    (2, 256, 320, 1000), (2, 3, 256, 777), (2, 256, 112, 40000), (2, 256, 256, 130)])
-def test_gemm_tensor_core_3xtf32(cuda, mode, M, N, K):
-    """tcgen05 kind::tf32 with the 3xTF32 split must be fp32-grade (the reference's MLPs are true
-    fp32 SGEMMs): max error relative to the largest output < 2e-6, far inside the 1e-4 bar."""
-    from fgs_nerf_b200 import engine
-    A, B, want = _tc_case(cuda, mode, M, N, K, mode * 7919 + M + N + K)
-    out = torch.full((M, (N + 3) // 4 * 4), 0.0, device=cuda)
-    rows = torch.tensor([K if mode == 2 else M], dtype=torch.int32, device=cuda)
-    engine.gemm(mode, A, B, out, rows_dev=rows, M=M, N=N, K=K, tc=True)
-    torch.cuda.synchronize()
-    err = _rel(out[:, :N], want)
-    print(f"tc gemm mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
-    assert err < 2e-6, err
-    if mode != 2:
-        g = torch.Generator(device="cpu").manual_seed(1)
-        bias = torch.randn(N, generator=g).to(cuda)
-        mask = torch.randn(M, (N + 3) // 4 * 4, generator=g).to(cuda)
-        out.fill_(7.0)
-        rows.fill_(M // 2)
-        engine.gemm(mode, A, B, out, bias=bias, relu=True, relu_mask=mask, rows_dev=rows, M=M, N=N, K=K, tc=True)
-        want2 = torch.relu(want + bias.double()) * (mask[:, :N] > 0)
-        assert bool((out[M // 2:, :N] == 7.0).all()), "rows beyond the device-side row count were written"
-        if M // 2 > 0:
-            assert _rel(out[:M // 2, :N], want2[:M // 2]) < 1e-5
-
-
-def test_simt_backend_agrees_with_tensor_core_backend(cuda):
-    """The fp32 SIMT GEMM path stays selectable; both backends must give the same step."""
-    from fgs_nerf_b200 import engine, scene
-    sc = scene.make_scene(G=48, mask_G=40)
-    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=192, H=100, W=100, n_views=8)]
-    res = []
-    try:
-        for tc in (True, False):
-            engine.set_gemm_backend(tc)
-            eng = engine.FineStepEngine(sc, 192, cuda)
-            eng.forward(ro, rd, vd, 5000)
-            eng.zero_grad()
-            eng.loss_backward(tgt)
-            torch.cuda.synchronize()
-            res.append((eng.ws["rgb_marched"].clone(), eng.g_sdf.clone(), eng.g_k0.clone(), eng.gW[0].clone(), eng.gW[4].clone()))
-    finally:
-        engine.set_gemm_backend(True)
-    for a, b, n in zip(res[0], res[1], ("rgb_marched", "g_sdf", "g_k0", "gW0", "gW4")):
-        assert _rel(a, b) < 2e-5, (n, _rel(a, b))
-
-
-@pytest.mark.parametrize("mode,M,N,K", [
     (0, 300, 256, 112), (0, 129, 3, 256), (0, 40000, 256, 320), (0, 128, 256, 16), (0, 5, 16, 4),
     (1, 257, 320, 256), (1, 100, 256, 3), (1, 30000, 112, 256), (0, 19000, 256, 256)])
-@pytest.mark.parametrize("tmem_acc", [1, 0])
-def test_gemm_presplit_weights_kernel(cuda, mode, M, N, K, tmem_acc):
-    """fgs_gemm_tcw = the kernels the fused step runs for X*W^T and dZ*W: weights pre-split into TF32
-    hi/lo planes and streamed by TMA, persistent CTAs over the sample tiles, ReLU masks as bits.
-    tmem_acc=1: whole-K accumulation in TMEM (default; the accumulator truncates per MMA: < 1e-5 of
-    max|out|); tmem_acc=0: 32-k chunks + fp32 register accumulators (< 2e-6).  Bar: 1e-4."""
-    from fgs_nerf_b200 import engine
-    engine.set_gemm_tmem_accumulate(tmem_acc)
-    try:
-        _presplit_case(cuda, mode, M, N, K, 1e-5 if tmem_acc else 2e-6)
-    finally:
-        engine.set_gemm_tmem_accumulate(1)
+def test_gemm_presplit_weights_kernel(cuda, mode, M, N, K):
+    """fgs_gemm_tcw = the per-layer form of the kernels the fused step runs for X*W^T and dZ*W: weights pre-split
+    into TF32 hi/lo planes and streamed by TMA, persistent CTAs over the sample tiles, ReLU masks as bits,
+    whole-K accumulation in TMEM (the accumulator truncates per MMA: < 1e-5 of max|out|).  Bar: 1e-4."""
+    _presplit_case(cuda, mode, M, N, K, 1e-5)
 
 
 def _presplit_case(cuda, mode, M, N, K, tol):
@@ -415,7 +326,7 @@ def _presplit_case(cuda, mode, M, N, K, tol):
     ldc = (N + 3) // 4 * 4
     out = torch.zeros(M, ldc, device=cuda)
     rows = torch.tensor([M], dtype=torch.int32, device=cuda)
-    engine.gemm(mode, A, B, out, rows_dev=rows, M=M, N=N, K=K, tc="w")
+    engine.gemm(mode, A, B, out, rows_dev=rows, M=M, N=N, K=K)
     torch.cuda.synchronize()
     err = _rel(out[:, :N], want)
     print(f"tcw gemm mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
@@ -428,7 +339,7 @@ def _presplit_case(cuda, mode, M, N, K, tol):
     out.fill_(7.0)
     if N == 256:
         bits = torch.zeros(M, 8, dtype=torch.int32, device=cuda)
-        engine.gemm(mode, A, B, out, bias=bias, relu=True, rows_dev=rows, M=M, N=N, K=K, tc="w", bits_out=bits)
+        engine.gemm(mode, A, B, out, bias=bias, relu=True, rows_dev=rows, M=M, N=N, K=K, bits_out=bits)
         torch.cuda.synchronize()
         pre = want + bias.double()
         assert bool((out[half:, :N] == 7.0).all()), "rows beyond the device-side row count were written"
@@ -438,11 +349,11 @@ def _presplit_case(cuda, mode, M, N, K, tol):
         assert torch.equal(unpacked, out[:half, :N] > 0)
         # and applied as an input mask
         out2 = torch.zeros(M, ldc, device=cuda)
-        engine.gemm(mode, A, B, out2, rows_dev=rows, M=M, N=N, K=K, tc="w", bits_in=bits)
+        engine.gemm(mode, A, B, out2, rows_dev=rows, M=M, N=N, K=K, bits_in=bits)
         torch.cuda.synchronize()
         assert _rel(out2[:half, :N], want[:half] * unpacked) < tol
     else:
-        engine.gemm(mode, A, B, out, bias=bias, rows_dev=rows, M=M, N=N, K=K, tc="w")
+        engine.gemm(mode, A, B, out, bias=bias, rows_dev=rows, M=M, N=N, K=K)
         torch.cuda.synchronize()
         assert bool((out[half:, :N] == 7.0).all())
         if half:
@@ -483,17 +394,10 @@ def test_brick_adam_equals_dense_masked_adam(cuda):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 320, 1000), (3, 256, 777), (256, 112, 40000), (256, 256, 130), (256, 256, 27000)])
-@pytest.mark.parametrize("pairs", [0, 1])
-def test_gemm_weight_gradient_kernel(cuda, M, N, K, pairs):
-    """fgs_gemm_tn = the stream-K kernel of the weight / bias gradients (dW = dZ^T X, MN-major operand tiles);
-    pairs=1: the CTA-pair (cta_group::2) variant."""
-    from fgs_nerf_b200 import engine
-    from fgs_nerf_b200._lib import lib, check, ptr, stream
-    check(lib.fgs_set_mlp_dw_pairs(pairs))
-    try:
-        _dw_case(cuda, M, N, K)
-    finally:
-        check(lib.fgs_set_mlp_dw_pairs(1))      # the library default
+def test_gemm_weight_gradient_kernel(cuda, M, N, K):
+    """fgs_gemm_tn = the stream-K kernel of the weight / bias gradients (dW = dZ^T X, MN-major operand tiles on CTA
+    pairs, tcgen05 cta_group::2)."""
+    _dw_case(cuda, M, N, K)
 
 
 def _dw_case(cuda, M, N, K):
@@ -562,22 +466,6 @@ def _one_step(cuda, setup=None, phase_split=False, rays=None, N=192, G=48):
     return out
 
 
-def test_fused_mlp_chain_equals_per_layer_launches(cuda):
-    """mlp_chain_kernel (8 forward layers / 9 backward-data steps per launch) + the batched weight-gradient
-    kernel against one launch per layer: same kernels' arithmetic, so the step must agree to rounding of the
-    atomics' order (bar 1e-4; observed ~1e-6)."""
-    from fgs_nerf_b200 import engine
-    try:
-        a = _one_step(cuda, lambda e: e.set_mlp_fusion(True))
-        b = _one_step(cuda, lambda e: e.set_mlp_fusion(False))
-    finally:
-        engine.set_mlp_fusion(True)
-    assert a["cnt"] == b["cnt"]
-    assert torch.equal(a["rgb"], b["rgb"]), "the fused forward chain runs the same MMAs in the same order"
-    for k in ("g_sdf", "g_k0", "g_mlp"):
-        assert _rel(a[k], b[k]) < 2e-5, (k, _rel(a[k], b[k]))
-
-
 def test_backward_in_two_phases_equals_one_call(cuda):
     """fgs_fine_backward_phase: 1 (grid gradients final) then 2 (weight gradients) == phase 0; phase 2 must
     not touch g_sdf / g_k0 (the data-parallel step exchanges them while it runs)."""
@@ -613,19 +501,3 @@ def test_batch_that_misses_the_volume(cuda):
     assert bool((out["rgb"] == 1.0).all())
     assert int(out["g_sdf"].count_nonzero()) == 0 and int(out["g_k0"].count_nonzero()) == 0
     assert int(out["g_mlp"].count_nonzero()) == 0
-
-
-def test_mlp_chain_on_cta_pairs(cuda):
-    """mlp_chain2_kernel (tcgen05 cta_group::2: 256-row tiles across two SMs, each holding half of the weight rows)
-    against the single-CTA chain: the same products accumulate in the same order per output element, so the
-    forward must be identical and the gradients agree to the order of the atomics."""
-    from fgs_nerf_b200 import engine
-    try:
-        a = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(False), N=512)
-        b = _one_step(cuda, lambda e: e.set_mlp_chain_pairs(True), N=512)
-    finally:
-        engine.set_mlp_chain_pairs(True)        # the library default
-    assert a["cnt"] == b["cnt"] and a["cnt"]["M2"] > 256
-    assert torch.equal(a["rgb"], b["rgb"])
-    for k in ("g_sdf", "g_k0", "g_mlp"):
-        assert _rel(a[k], b[k]) < 2e-5, (k, _rel(a[k], b[k]))

@@ -136,7 +136,7 @@ def test_trainer_equals_hand_issued_iterations(cuda):
 
     ref_t = dict(cfg, tv_terms=dict(sdf_tv=cfg["sdf_tv"], smooth_grad_tv=cfg["smooth_grad_tv"]))
     sch = stage_ref.RefSchedule(ref_t)
-    sch._fresh_optimizer(start)                        # create_optimizer_or_freeze_model(global_step=start)
+    sch._fresh_optimizer(0)                            # create_optimizer_or_freeze_model(global_step=0), nerf_training.py:117
     eng2 = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(cfg))
     eng2.set_nonempty_mask()
     gen = training.batch_indices_generator(n_total, N, rng=np.random.RandomState(7))
@@ -185,7 +185,7 @@ def test_trainer_second_iteration_against_oracle_step(cuda):
     m.set_nonempty_mask()
     opt = R.RefOptimizer(m, cfg, native)
     sch = stage_ref.RefSchedule(dict(cfg, tv_terms=dict(sdf_tv=cfg["sdf_tv"], smooth_grad_tv=cfg["smooth_grad_tv"])))
-    sch._fresh_optimizer(start)
+    sch._fresh_optimizer(0)
     gen = training.batch_indices_generator(n_total, N, rng=np.random.RandomState(9))
     before = {k: v.detach().clone() for k, v in m.params()}
     for gs in (start + 1, start + 2):
@@ -203,7 +203,7 @@ def test_trainer_second_iteration_against_oracle_step(cuda):
         assert frac < 2e-2, f"{name}: {frac:.5f} of the two-iteration updates differ from the oracle's"
     # the sdf step of iteration 2 used a tenth of the rate: |update| <= lr1 + 1.001 lr2 (Adam's bias-corrected ratio
     # is at most 1.001 at step 2), where two full-rate steps would reach 2 lr1
-    lr1 = cfg["lrate_sdf"] * 0.1 ** (start / 20000)
+    lr1 = cfg["lrate_sdf"]                       # a fresh optimiser starts at the base rate (global_step=0)
     d = (tr.engine.sdf - before["sdf"]).abs().max()
     assert float(d) <= lr1 * (1.0 + 0.1 * 1.001) * 1.02
     assert float(d) >= lr1 * 0.99
@@ -248,6 +248,75 @@ def test_pg_scale_iteration_rescales_grids_and_restarts_optimizer(cuda):
     f = 0.1 ** (1 / 20000)
     assert tr2.engine.lr["k0"] == pytest.approx(cfg["lrate_k0"] * f * f, rel=1e-12)
     assert tr2.engine.counters()["M2"] > 0
+
+
+def test_resume_keeps_optimizer_state_and_rates(cuda):
+    """utils.load_checkpoint -> optimizer.load_state_dict (model/utils.py:49-56): a trainer built on a reloaded engine
+    continues with the saved moments, step count and per-group learning rates -- the 4th iteration after a resume at 3
+    equals the 4th iteration of the uninterrupted run (up to the float atomics of the scatters)."""
+    from fgs_nerf_b200 import checkpoint, engine, scene, training
+    N, n_total = 192, 1500
+    cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, pg_scale=[])
+    rays = _training_rays(cuda, n_total)
+    sc = scene.make_scene(G=48, mask_G=40)
+    eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
+    eng.set_nonempty_mask()
+    tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=0, rng=np.random.RandomState(3))
+    tr.run(3)
+    torch.cuda.synchronize()
+    ck = checkpoint.checkpoint_dict(tr.engine, 3)
+    before = {"sdf": tr.engine.sdf.clone(), "k0": tr.engine.k0.clone(), "W0": tr.engine.weights[0].clone()}
+    lr_at_3 = dict(tr.engine.lr)
+    tr.run(1)
+    torch.cuda.synchronize()
+
+    eng2, start = checkpoint.engine_from_checkpoint(ck, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
+    assert start == 3 and eng2.adam_step == 3
+    tr2 = training.FineTrainer(eng2, *rays, cfg_train=cfg, start=start, rng=np.random.RandomState(3))
+    assert eng2.adam_step == 3 and eng2.adam, "the loaded optimiser state was thrown away"
+    assert eng2.lr == pytest.approx(lr_at_3, rel=1e-12)
+    for _ in range(3):
+        next(tr2.sampler)                                  # the index stream continues where the first run stood
+    tr2.run(1)
+    torch.cuda.synchronize()
+    assert tr2.engine.adam_step == 4 and tr2.engine.lr == pytest.approx(tr.engine.lr, rel=1e-12)
+    for name, a, b, lr in (("sdf", tr2.engine.sdf, tr.engine.sdf, cfg["lrate_sdf"]),
+                           ("k0", tr2.engine.k0, tr.engine.k0, cfg["lrate_k0"]),
+                           ("W0", tr2.engine.weights[0], tr.engine.weights[0], 1e-3)):
+        frac = _frac_differing(a, b, before[name], lr)
+        assert frac < 1e-2, f"{name}: {frac:.5f} of the 4th-iteration updates differ after the resume"
+        # a restarted Adam (zero moments, step 1) would move every touched entry by the full lr: measurably different
+        moved = (b - before[name]).abs()
+        assert float((a - b).abs().max()) < 0.5 * float(moved.max())
+    # --no_reload_optimizer: fresh state, base rates
+    eng3, _ = checkpoint.engine_from_checkpoint(ck, N, cuda, train_cfg=dict(scene.FINE_TRAIN), no_reload_optimizer=True)
+    tr3 = training.FineTrainer(eng3, *rays, cfg_train=cfg, start=3, rng=np.random.RandomState(3))
+    assert tr3.engine.adam_step == 0 and tr3.engine.lr == {k: cfg["lrate_" + k] for k in tr3.engine.lr}
+
+
+def test_workspace_overflow_is_sticky_across_iterations(cuda):
+    """An iteration that runs out of level-2 workspace must not be forgotten when a later one fits: run() with
+    i_print=0 never reads the per-forward counters, the sticky word still raises."""
+    from fgs_nerf_b200 import engine, scene, training
+    N, n_total = 192, 1500
+    cfg = dict(scene.FINE_TRAIN, tv_every=1, N_rand=N, lrate_decay=20, pg_scale=[])
+    rays = _training_rays(cuda, n_total)
+    sc = scene.make_scene(G=48, mask_G=40)
+    eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN), cap_m2_per_ray=1)
+    eng.set_nonempty_mask()
+    tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=5000, rng=np.random.RandomState(1))
+    with pytest.raises(RuntimeError, match="overflow"):
+        tr.run(2)
+    eng.check_overflow()                                   # cleared by the check that raised
+    # a forward that fits leaves the per-forward word clean while the sticky one still remembers the earlier overflow
+    ro, rd, vd, tgt = [r[:N].contiguous() for r in rays]
+    eng.train_step(ro, rd, vd, tgt, 5001)                  # overflows (cap_m2 = 1 per ray)
+    far = ro + 100.0                                       # rays that miss the box: no samples, no overflow
+    eng.forward(far, rd, vd, 5001)
+    torch.cuda.synchronize()
+    assert eng.counters()["OVERFLOW"] == 0
+    with pytest.raises(RuntimeError, match="earlier iteration"):
+        eng.check_overflow()
 
 
 @pytest.mark.parametrize("res,bound", [(33, 1.0), (40, 1.1), (64, 0.7)])
