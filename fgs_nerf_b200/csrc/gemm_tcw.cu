@@ -1365,7 +1365,7 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
   if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
   mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
-  return fgs::check_launch("mlp_chain", st);
+  return fgs::check_launch(steps[0].bias ? "mlp_chain_fwd" : "mlp_chain_bwd", st);   // (only the forward adds biases)
 }
 
 // All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first

@@ -16,27 +16,25 @@ def ray_shard(n_global, world_size, rank):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def all_reduce_sum_(tensors, group=None, bucket_numel=1 << 22):
-    """In-place sum over ranks of a list of gradient tensors.  Tensors of at least `bucket_numel`
-    elements (the grids) are reduced in place; the small ones (16 MLP tensors) travel in one
-    packed bucket, so a step issues 3 collectives instead of 18."""
+def chunks_of_rank(n_chunks, world_size, rank):
+    """Rendering (model/utils.py:296-299 cuts an image into 8192-ray chunks): chunk ci is rendered by rank
+    ci % world_size as its local chunk ci // world_size."""
+    return range(rank, n_chunks, world_size)
+
+
+def local_chunk_count(n_chunks, world_size):
+    return (n_chunks + world_size - 1) // world_size
+
+
+def gather_dealt_chunks(local, chunk_rows, world_size, group=None):
+    """local: [n_local * chunk_rows, c], this rank's chunks in its local order (the same n_local on every rank; a rank
+    with one chunk fewer leaves its last slot as it is).  Returns [n_local * world_size * chunk_rows, c] in GLOBAL
+    chunk order: one all_gather -- every rank sends only what it rendered -- and a strided view."""
     import torch.distributed as dist
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
-    small = []
-    for t in tensors:
-        if t.numel() >= bucket_numel and t.is_contiguous():
-            dist.all_reduce(t, group=group)
-        elif t.numel() >= bucket_numel:
-            # channels_last_3d etc.: reduce the underlying storage order, not a contiguous copy
-            flat = torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
-            dist.all_reduce(flat, group=group)
-        else:
-            small.append(t)
-    if small:
-        flat = torch.cat([t.reshape(-1) for t in small])
-        dist.all_reduce(flat, group=group)
-        o = 0
-        for t in small:
-            t.copy_(flat[o:o + t.numel()].view_as(t))
-            o += t.numel()
+    if world_size == 1:
+        return local
+    n_local = local.shape[0] // chunk_rows
+    c = local.shape[1]
+    full = torch.empty((world_size * local.shape[0], c), dtype=local.dtype, device=local.device)   # rank-major
+    dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+    return full.view(world_size, n_local, chunk_rows, c).permute(1, 0, 2, 3).reshape(n_local * world_size * chunk_rows, c)

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import dist as fdist
 from ._lib import check, lib, ptr, stream
 
 MLP_LAYERS = 8
@@ -502,7 +503,7 @@ class FineStepEngine:
         R = rays_o.shape[0]
         N = self.n_rays
         n_chunks = (R + N - 1) // N
-        n_local = (n_chunks + world_size - 1) // world_size        # chunks per rank (the last ranks may idle once)
+        n_local = fdist.local_chunk_count(n_chunks, world_size)    # chunks per rank (the last ranks may idle once)
         dev = self.device
         keys = [("rgb_marched", 3), ("sigmoid_rgb", 3), ("alphainv_last", 1), ("cum_weights", 1)]
         if render_depth:
@@ -518,7 +519,7 @@ class FineStepEngine:
         P = self.P
         saved = {k: getattr(P, k) for k, _ in keys}
         try:
-            for li, ci in enumerate(range(rank, n_chunks, world_size)):
+            for li, ci in enumerate(fdist.chunks_of_rank(n_chunks, world_size, rank)):
                 a = ci * N
                 for k, c in keys:
                     setattr(P, k, out[k].data_ptr() + li * N * c * 4)
@@ -531,10 +532,7 @@ class FineStepEngine:
         if world_size > 1:
             import torch.distributed as dist
             for k, c in keys:
-                full = torch.empty((world_size, n_local * N, c), dtype=torch.float32, device=dev)
-                dist.all_gather_into_tensor(full, out[k])
-                # chunk ci was rendered by rank ci % world as its local chunk ci // world
-                out[k] = full.view(world_size, n_local, N, c).permute(1, 0, 2, 3).reshape(n_local * world_size * N, c)
+                out[k] = fdist.gather_dealt_chunks(out[k], N, world_size)
             dist.all_reduce(ovf, op=dist.ReduceOp.MAX)
         bits = int(ovf.item())
         if bits:
@@ -913,13 +911,13 @@ class FineStepEngine:
                                      self.Z, K0_DIM, pack, stream()))
 
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
-                   has_last_ray=True):
+                   has_last_ray=True, _stop_before_optimizer=False):
         """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous.
         Data-parallel (world_size > 1): the backward runs in two phases -- the grid gradients first; the union of
         the touched k0 bricks, its count (the one host sync) and the pack run on a side stream while the
         weight-gradient kernel (which leaves a few SMs free for them) runs on the main one; then ONE all-reduce over
         [g_sdf | MLP bucket | packed bricks]."""
-        native = self.world_size == 1 and self.native_step
+        native = self.world_size == 1 and self.native_step and not _stop_before_optimizer
         if not native:
             self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)   # fgs_fine_loss composites
         self.zero_grad()                                                   # optimizer.zero_grad(set_to_none)
@@ -933,7 +931,7 @@ class FineStepEngine:
             self._ev_grids, self._ev_exch = torch.cuda.Event(), torch.cuda.Event()
             check(lib.fgs_set_dw_sm_reserve(self.dw_sm_reserve if self.world_size > 1 else 0))
         main = torch.cuda.current_stream(self.device)
-        if self.world_size == 1 and self.native_step:
+        if native:
             self._native_train_step(rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv)
             return
         if self.world_size == 1:
@@ -946,6 +944,9 @@ class FineStepEngine:
                 self.smooth_grad_tv_add_grad()
             if tv and t["sdf_tv"] > 0:
                 self.sdf_tv_add_grad(global_step, n_rays_global)
+            if _stop_before_optimizer:                  # tests: the gradients an optimiser step would consume
+                self.backward_weights()
+                return
             self._ev_grids.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_grids)
@@ -975,6 +976,8 @@ class FineStepEngine:
             self._exchange_reduce()                                        # ONE all-reduce of everything, unpack
         if tv and t["sdf_tv"] > 0:
             self.sdf_tv_add_grad(global_step, n_rays_global)
+        if _stop_before_optimizer:
+            return
         self.optimizer_step()
 
 

@@ -1,5 +1,6 @@
-"""CPU tests (gloo, world_size 2) of the host-side multi-GPU logic: ray sharding and the gradient
-exchange of fgs_nerf_b200.dist.  The kernels themselves need a GPU (tests/test_multi_gpu.py)."""
+"""CPU tests (gloo, world_size 2) of the host-side multi-GPU logic: ray sharding (training) and the chunk dealing /
+gathering of multi-rank rendering.  The gradient exchange itself is kernels + NCCL (brick flags -> list -> pack ->
+all-reduce -> unpack) and is tested on two GPUs in tests/test_multi_gpu.py."""
 import os
 import sys
 
@@ -30,30 +31,27 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from fgs_nerf_b200.dist import all_reduce_sum_
-        g = torch.Generator().manual_seed(100 + rank)
-        big = torch.randn(1, 3, 8, 8, 8, generator=g)                                   # "grid", reduced in place
-        cl = torch.randn(1, 12, 6, 6, 6, generator=g).contiguous(memory_format=torch.channels_last_3d)
-        small = [torch.randn(5, 7, generator=g), torch.randn(7, generator=g), torch.randn(3, 4, generator=g)]
-        mine = [t.clone() for t in [big, cl] + small]
-        all_reduce_sum_([big, cl] + small, bucket_numel=500)
-        # expected: sum over both ranks' tensors, regenerated locally
-        want = None
-        for r in range(world):
-            gg = torch.Generator().manual_seed(100 + r)
-            ts = [torch.randn(1, 3, 8, 8, 8, generator=gg),
-                  torch.randn(1, 12, 6, 6, 6, generator=gg).contiguous(memory_format=torch.channels_last_3d),
-                  torch.randn(5, 7, generator=gg), torch.randn(7, generator=gg), torch.randn(3, 4, generator=gg)]
-            want = ts if want is None else [a + b for a, b in zip(want, ts)]
-        ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip([big, cl] + small, want))
-        ok = ok and cl.is_contiguous(memory_format=torch.channels_last_3d)                # layout untouched
-        ok = ok and not torch.equal(mine[0], big)
+        from fgs_nerf_b200.dist import chunks_of_rank, gather_dealt_chunks, local_chunk_count
+        ok = True
+        for n_chunks in (1, 2, 5, 8):
+            rows, c = 6, 3
+            n_local = local_chunk_count(n_chunks, world)
+            local = torch.full((n_local * rows, c), -1.0)
+            for li, ci in enumerate(chunks_of_rank(n_chunks, world, rank)):
+                local[li * rows:(li + 1) * rows] = float(ci) + torch.arange(rows * c).reshape(rows, c) / 100.0
+            full = gather_dealt_chunks(local, rows, world)
+            ok = ok and tuple(full.shape) == (n_local * world * rows, c)
+            for ci in range(n_chunks):                     # global chunk order, every chunk from the rank that owns it
+                want = float(ci) + torch.arange(rows * c).reshape(rows, c) / 100.0
+                ok = ok and torch.equal(full[ci * rows:(ci + 1) * rows], want)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-def test_gradient_exchange_gloo_world2():
+def test_render_chunk_gather_gloo_world2():
+    """The host side of multi-rank rendering (engine.render): chunks dealt round-robin, one all_gather per output,
+    global chunk order restored -- including chunk counts that do not divide by the world size."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)

@@ -6,7 +6,7 @@ from fgs_nerf_b200 import engine, scene
 from fgs_nerf_b200._lib import lib, check
 dev = torch.device("cuda:0")
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 160
-engine.set_mlp_chain_pairs(bool(int(sys.argv[2])) if len(sys.argv) > 2 else False)
+# (the chain always runs on CTA pairs)
 N = 8192
 sc = scene.make_scene(G=G)
 ro, rd, vd, tgt = [t.to(dev) for t in scene.make_rays(N=N)]
