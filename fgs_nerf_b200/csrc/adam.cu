@@ -341,6 +341,39 @@ brick_copy_kernel(float* __restrict__ grid, float* __restrict__ compact, const i
 // all gradient loads issued before any dependent work.
 constexpr int kBrickBlock = 128;
 // (128 threads x ~98 registers: small enough to be resident next to a tensor-core CTA on a side stream)
+__device__ __forceinline__ void adam_one_brick(float* __restrict__ param, float* __restrict__ grad,
+                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int br,
+                                               int X, int Y, int Z, int nbY, int nbZ, int lane, const AdamConst& c) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int bz = br % nbZ, by = (br / nbZ) % nbY, bx = br / (nbZ * nbY);
+  size_t off[6];
+  float4 g[6];
+  bool ok[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int q = lane + 32 * i;
+    const int row = q / 12, f4 = q - row * 12;
+    const int x = 4 * bx + (row >> 2), y = 4 * by + (row & 3), z = 4 * bz + f4 / 3;
+    ok[i] = x < X && y < Y && z < Z;
+    off[i] = (((size_t)x * Y + y) * Z + 4 * bz) * 12 + 4 * f4;
+    g[i] = ok[i] ? ld4(grad + off[i]) : z4;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (ok[i] && (g[i].x != 0.f || g[i].y != 0.f || g[i].z != 0.f || g[i].w != 0.f)) {
+      float4 p = ld4(param + off[i]), m = ld4(exp_avg + off[i]), v = ld4(exp_avg_sq + off[i]);
+      if (g[i].x != 0.f) adam_elem(p.x, g[i].x, m.x, v.x, c, c.step_size);
+      if (g[i].y != 0.f) adam_elem(p.y, g[i].y, m.y, v.y, c, c.step_size);
+      if (g[i].z != 0.f) adam_elem(p.z, g[i].z, m.z, v.z, c, c.step_size);
+      if (g[i].w != 0.f) adam_elem(p.w, g[i].w, m.w, v.w, c, c.step_size);
+      st4(param + off[i], p);
+      st4(exp_avg + off[i], m);
+      st4(exp_avg_sq + off[i], v);
+      st4(grad + off[i], z4);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBrickBlock)
 adam_bricks_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ exp_avg,
                    float* __restrict__ exp_avg_sq, const int* __restrict__ list, int X, int Y, int Z, AdamConst c) {
@@ -348,35 +381,30 @@ adam_bricks_kernel(float* __restrict__ param, float* __restrict__ grad, float* _
   const int lane = lane_id();
   const int wpb = kBrickBlock / 32;
   const int count = list[0];
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < count; e += gridDim.x * wpb) {
-    const int br = list[1 + e];
-    const int bz = br % nbZ, by = (br / nbZ) % nbY, bx = br / (nbZ * nbY);
-    size_t off[6];
-    float4 g[6];
-    bool ok[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int q = lane + 32 * i;
-      const int row = q / 12, f4 = q - row * 12;
-      const int x = 4 * bx + (row >> 2), y = 4 * by + (row & 3), z = 4 * bz + f4 / 3;
-      ok[i] = x < X && y < Y && z < Z;
-      off[i] = (((size_t)x * Y + y) * Z + 4 * bz) * 12 + 4 * f4;
-      g[i] = ok[i] ? ld4(grad + off[i]) : z4;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      if (ok[i] && (g[i].x != 0.f || g[i].y != 0.f || g[i].z != 0.f || g[i].w != 0.f)) {
-        float4 p = ld4(param + off[i]), m = ld4(exp_avg + off[i]), v = ld4(exp_avg_sq + off[i]);
-        if (g[i].x != 0.f) adam_elem(p.x, g[i].x, m.x, v.x, c, c.step_size);
-        if (g[i].y != 0.f) adam_elem(p.y, g[i].y, m.y, v.y, c, c.step_size);
-        if (g[i].z != 0.f) adam_elem(p.z, g[i].z, m.z, v.z, c, c.step_size);
-        if (g[i].w != 0.f) adam_elem(p.w, g[i].w, m.w, v.w, c, c.step_size);
-        st4(param + off[i], p);
-        st4(exp_avg + off[i], m);
-        st4(exp_avg_sq + off[i], v);
-        st4(grad + off[i], z4);
-      }
+  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < count; e += gridDim.x * wpb)
+    adam_one_brick(param, grad, exp_avg, exp_avg_sq, list[1 + e], X, Y, Z, nbY, nbZ, lane, c);
+}
+
+// The same driven by the FLAGS themselves (single GPU: nobody needs the ordered list, whose single-CTA scan was the
+// longest kernel of the optimiser's side stream): a warp takes 32 consecutive flags with one coalesced load, walks the
+// set ones and clears them.  64 K flags at 160^3 = 2 K warp tasks over all SMs.
+__global__ void __launch_bounds__(kBrickBlock)
+adam_bricks_flags_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ exp_avg,
+                         float* __restrict__ exp_avg_sq, unsigned char* __restrict__ flags, int n_bricks, int X, int Y,
+                         int Z, AdamConst c) {
+  const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
+  const int lane = lane_id();
+  const int wpb = kBrickBlock / 32;
+  const int groups = (n_bricks + 31) >> 5;
+  for (int gidx = blockIdx.x * wpb + (threadIdx.x >> 5); gidx < groups; gidx += gridDim.x * wpb) {
+    const int b = gidx * 32 + lane;
+    const bool set = b < n_bricks && flags[b] != 0;
+    unsigned m = __ballot_sync(0xffffffffu, set);
+    if (set) flags[b] = 0;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      adam_one_brick(param, grad, exp_avg, exp_avg_sq, gidx * 32 + j, X, Y, Z, nbY, nbZ, lane, c);
     }
   }
 }
@@ -717,6 +745,20 @@ int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_av
   FGS_PREFER_MAX_SHARED(adam_bricks_kernel);
   adam_bricks_kernel<<<FGS_NUM_SMS * 16, kBrickBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
                                                                           brick_list, X, Y, Z, c);
+  return fgs::check_launch("adam_bricks", (cudaStream_t)stream);
+}
+
+int fgs_adam_upd_brick_flags(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* brick_flags,
+                             int X, int Y, int Z, int channels, int step, float beta1, float beta2, float lr,
+                             float eps, fgs_stream_t stream) {
+  FGS_REQUIRE(channels == 12, "brick Adam is specialised for the 12-channel channels-last k0 grid");
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick Adam needs Z % 4 == 0");
+  AdamConst c{host_step_size(lr, beta1, beta2, step), beta1, beta2, 1 - beta1, 1 - beta2, eps};
+  const int n_bricks = ((X + 3) / 4) * ((Y + 3) / 4) * ((Z + 3) / 4);
+  FGS_PREFER_MAX_SHARED(adam_bricks_flags_kernel);
+  const int grid = fgs::stream_grid((n_bricks + 31) / 32, kBrickBlock / 32, 16);
+  adam_bricks_flags_kernel<<<grid, kBrickBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, brick_flags,
+                                                                          n_bricks, X, Y, Z, c);
   return fgs::check_launch("adam_bricks", (cudaStream_t)stream);
 }
 

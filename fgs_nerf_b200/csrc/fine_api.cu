@@ -55,14 +55,14 @@ ChainStepHost bwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer,
   return s;
 }
 
-// hi / lo TF32 planes of the 8 weight matrices, straight and transposed, in one launch
+// operand planes of the 8 weight matrices in one launch: straight TF32 hi / lo (forward), transposed bf16 hi / mid (backward)
 int prep_weights(const FgsFineParams& P, cudaStream_t st) {
   FGS_REQUIRE(P.w_split != nullptr && P.hbits != nullptr, "w_split / hbits workspace is NULL");
   const WSplitLayout L = wsplit_layout();
   SplitJobHost jobs[2 * FGS_MLP_LAYERS];
   for (int l = 0; l < FGS_MLP_LAYERS; ++l) {
-    jobs[2 * l] = {P.W[l], P.w_split + L.hi[l], P.w_split + L.lo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.in_ld[l], 0};
-    jobs[2 * l + 1] = {P.W[l], P.w_split + L.thi[l], P.w_split + L.tlo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.ldt[l], 1};
+    jobs[2 * l] = {P.W[l], P.w_split + L.hi[l], P.w_split + L.lo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.in_ld[l], 0, 0};
+    jobs[2 * l + 1] = {P.W[l], P.w_split + L.thi[l], P.w_split + L.tlo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.ldt[l], 1, 1};
   }
   return weight_split_jobs(jobs, 2 * FGS_MLP_LAYERS, st);
 }
@@ -146,7 +146,7 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
           bwd_step(P, L, 2, dz(3), W, W, dz(4), W, W, 0, 1),
           bwd_step(P, L, 1, dz(4), W, W, dz(5), W, W, 0, 0),
           bwd_step(P, L, 0, dz(5), W, W, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1)};
-      if ((rc = mlp_chain(steps, 9, cap, m2, st))) return rc;
+      if ((rc = mlp_chain(steps, 9, cap, m2, st, true))) return rc;     // 3xBF16 (masks are the forward's)
       if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
       if ((rc = launch_level1_bwd(P, l->g_alphainv_last, st))) return rc;
     }
@@ -168,7 +168,7 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
       DwProblemHost dw[8];
       for (int i = 0; i < 8; ++i)
         dw[i] = DwProblemHost{dzl[i], xin[i], P.gW[i], P.gB[i], out_dim[i], in_dim[i], dz_ld[i], in_dim[i], in_dim[i]};
-      if ((rc = mlp_dw(dw, 8, cap, m2, st))) return rc;
+      if ((rc = mlp_dw(dw, 8, cap, m2, st, true))) return rc;          // 3xBF16
     }
     return 0;
   }

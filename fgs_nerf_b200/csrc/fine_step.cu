@@ -55,9 +55,8 @@ extern "C" int fgs_fine_train_step(const FgsFineParams* p, const FgsFineLoss* l,
                                    s->lr_sdf, s->eps, s->side_stream)))
     return rc;
   if (s->sparse_k0) {
-    if ((rc = fgs_brick_list(P.k0_brick_flags, X, Y, Z, s->brick_list, s->side_stream))) return rc;
-    if ((rc = fgs_adam_upd_bricks((float*)P.k0, P.g_k0, s->k0_m, s->k0_v, s->brick_list, X, Y, Z, FGS_K0_DIM,
-                                  s->adam_step, s->beta1, s->beta2, s->lr_k0, s->eps, s->side_stream)))
+    if ((rc = fgs_adam_upd_brick_flags((float*)P.k0, P.g_k0, s->k0_m, s->k0_v, P.k0_brick_flags, X, Y, Z, FGS_K0_DIM,
+                                       s->adam_step, s->beta1, s->beta2, s->lr_k0, s->eps, s->side_stream)))
       return rc;
   } else {
     if ((rc = fgs_adam_upd((float*)P.k0, P.g_k0, s->k0_m, s->k0_v, nullptr, V * FGS_K0_DIM, s->adam_step, s->beta1,

@@ -156,6 +156,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 struct SplitJob {
   const float* W; float* hi; float* lo;
   int rows, cols, ld, ld_out, transpose;  // transpose: out[c][r] (ld_out >= rows) else out[r][c] (ld_out >= cols)
+  int bf16;                               // planes are bf16 hi / mid (ld_out in elements) instead of TF32 hi / lo
 };
 struct SplitJobs {
   SplitJob j[16];
@@ -168,10 +169,17 @@ __global__ void __launch_bounds__(256) weight_split_kernel(const __grid_constant
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
     const int r = i / J.cols, c = i - r * J.cols;
     const float x = J.W[(size_t)r * J.ld + c];
-    const float h = rn_tf32(x), l = rn_tf32(x - h);
     const size_t o = J.transpose ? (size_t)c * J.ld_out + r : (size_t)r * J.ld_out + c;
-    J.hi[o] = h;
-    J.lo[o] = l;
+    if (J.bf16) {
+      const uint32_t h = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+      const uint32_t m = __float_as_uint(x - __uint_as_float(h)) + 0x8000u;
+      reinterpret_cast<uint16_t*>(J.hi)[o] = (uint16_t)(h >> 16);
+      reinterpret_cast<uint16_t*>(J.lo)[o] = (uint16_t)(m >> 16);
+    } else {
+      const float h = rn_tf32(x), l = rn_tf32(x - h);
+      J.hi[o] = h;
+      J.lo[o] = l;
+    }
   }
 }
 
@@ -262,6 +270,44 @@ __device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, 
   lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
   st_shared_v4(hi_addr, hi);
   st_shared_v4(lo_addr, lo);
+}
+
+// ---- 3xBF16 operands (backward kernels) ----
+// x = hi + mid + O(2^-17 |x|) with hi = bf16(x), mid = bf16(x - hi); the products hi*hi + hi*mid + mid*hi leave
+// a relative error of ~2^-16 per product (the mid*mid term), measured end to end at <= 1.2e-5 on every gradient
+//  -- inside the 1e-4 bar -- at HALF the tensor-core instructions of 3xTF32: a kind::f16 MMA covers
+// K = 16 in the 32 bytes per row a kind::tf32 MMA needs for K = 8.  Rounding on the integer pipe (add half an ulp,
+// keep the upper 16 bits), two values packed per word with one PRMT.
+__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+  const uint32_t h0 = (__float_as_uint(x0) + 0x8000u) & 0xFFFF0000u, h1 = (__float_as_uint(x1) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t m0 = __float_as_uint(x0 - __uint_as_float(h0)) + 0x8000u;
+  const uint32_t m1 = __float_as_uint(x1 - __uint_as_float(h1)) + 0x8000u;
+  hi = __byte_perm(h0, h1, 0x7632);      // element 0 in the low half
+  mid = __byte_perm(m0, m1, 0x7632);
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2u(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// 8 consecutive k of one row -> one 16-byte chunk of the hi tile and of the mid tile
+__device__ __forceinline__ void split_store_bf8(uint32_t hi_addr, uint32_t mid_addr, const float4& a, const float4& b) {
+  uint32_t h[4], m[4];
+  bf16_split2(a.x, a.y, h[0], m[0]);
+  bf16_split2(a.z, a.w, h[1], m[1]);
+  bf16_split2(b.x, b.y, h[2], m[2]);
+  bf16_split2(b.z, b.w, h[3], m[3]);
+  st_shared_v4u(hi_addr, h[0], h[1], h[2], h[3]);
+  st_shared_v4u(mid_addr, m[0], m[1], m[2], m[3]);
+}
+// 4 consecutive MN elements of one k row (MN-major tiles of the weight-gradient kernel) -> 8 bytes per tile
+__device__ __forceinline__ void split_store_bf4(uint32_t hi_addr, uint32_t mid_addr, const float4& a) {
+  uint32_t h[2], m[2];
+  bf16_split2(a.x, a.y, h[0], m[0]);
+  bf16_split2(a.z, a.w, h[1], m[1]);
+  st_shared_v2u(hi_addr, h[0], h[1]);
+  st_shared_v2u(mid_addr, m[0], m[1]);
 }
 
 struct Bars {
@@ -658,18 +704,41 @@ __device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma2_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void mma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (BF) mma2_bf16(tmem_d, da, db, idesc, accumulate);
+  else mma2_tf32(tmem_d, da, db, idesc, accumulate);
+}
+// instruction descriptor: fp32 accumulator, A / B format TF32 (2) or BF16 (1), N, M
+__device__ __forceinline__ uint32_t make_idesc(bool bf, int N, int M, bool mn_major) {
+  const uint32_t fmt = bf ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void mma2_commit(uint32_t bar) {    // arrives on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((unsigned short)3)
                : "memory");
 }
 
+// BF = false: TF32 hi / lo planes, kind::tf32, 32-k slabs (the forward).  BF = true: bf16 hi / mid planes, kind::f16,
+// 64-k slabs in the same bytes (the backward-data chain): same 12 MMAs per slab, half as many slabs.
+template <bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
 mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
   const Bars B = make_bars(smem);
   const uint32_t cdone0 = smem + kCDoneOff;
+  constexpr int SK = BF ? 2 * BK : BK;                         // k per slab (one 128-byte swizzle row per operand row)
 
   int M = a.M;
   if (a.rows_dev) M = min(M, *a.rows_dev);
@@ -726,7 +795,7 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
         if (++c.kt == c.n_slabs) {
           c.kt = 0;
           ++c.w;
-          if (c.w < n_items) { c.step = c.w / my_tiles; c.n_slabs = (a.s[c.step].K + BK - 1) / BK; }
+          if (c.w < n_items) { c.step = c.w / my_tiles; c.n_slabs = (a.s[c.step].K + SK - 1) / SK; }
         }
       };
       auto issue_b = [&](const Cursor& c, uint32_t gs) {
@@ -740,10 +809,10 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(B.bfull0 + 8 * st), "r"(4 * kBHalf2) : "memory");
         const uint32_t bar = l_bfull0 + 8 * st;
         const int row0 = S.n0 + (int)rank * (BN >> 1);          // B is split along N between the two CTAs
-        tma2_load_2d(b_hi, &maps.hi[c.step], bar, c.kt * BK, row0);
-        tma2_load_2d(b_lo, &maps.lo[c.step], bar, c.kt * BK, row0);
+        tma2_load_2d(b_hi, &maps.hi[c.step], bar, c.kt * SK, row0);
+        tma2_load_2d(b_lo, &maps.lo[c.step], bar, c.kt * SK, row0);
       };
-      Cursor lc{0, 0, 0, (a.s[0].K + BK - 1) / BK};
+      Cursor lc{0, 0, 0, (a.s[0].K + SK - 1) / SK};
       uint32_t lg = 0;
       constexpr uint32_t kPf = kStages2 - 1;                   // weight slabs in flight ahead of the MMAs
       for (; lg < kPf && lc.w < n_items; ++lg) { issue_b(lc, lg); cur_next(lc); }
@@ -752,9 +821,8 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
         const int step = w / my_tiles;
         const ChainStep& S = a.s[step];
         const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
-        const int n_slabs = (S.K + BK - 1) / BK;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)((2 * BM) >> 4) << 24);          // M = 256 across the pair
+        const int n_slabs = (S.K + SK - 1) / SK;
+        const uint32_t idesc = make_idesc(BF, BN, 2 * BM, false);          // M = 256 across the pair
         const uint32_t rg = (uint32_t)w & 1;
         for (int kt = 0; kt < n_slabs; ++kt, ++g) {
           const uint32_t st = g % kStages2;
@@ -775,9 +843,9 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
             for (int j = 0; j < BK / 8; ++j) {
               const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
               const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-              mma2_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);
-              mma2_tf32(d, dah, dbl, idesc, 1);
-              mma2_tf32(d, dah, dbh, idesc, 1);
+              mma2<BF>(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);   // (32 bytes per row per k-step either way)
+              mma2<BF>(d, dah, dbl, idesc, 1);
+              mma2<BF>(d, dah, dbh, idesc, 1);
             }
             mma2_commit(B.free0 + 8 * st);
             if (kt == n_slabs - 1) mma2_commit(B.rfull0 + 8 * rg);
@@ -801,9 +869,8 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
       }
     }
   } else if (warp >= kConsumers / 32) {
-    // ================= producers: this CTA's 128 activation rows -> hi / lo TF32 tiles =================
+    // ================= producers: this CTA's 128 activation rows -> hi / lo operand tiles =================
     const int pw = warp - kConsumers / 32;
-    const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
     const bool dbg_on = dbg_cta && tid == kConsumers;
     long long t_wait = 0, t_work = 0, t_dep = 0, t0 = 0;
     uint32_t g = 0;
@@ -811,48 +878,103 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
       const int step = w / my_tiles, lt = w - step * my_tiles;
       const ChainStep& S = a.s[step];
       const int K = S.K, lda = S.lda;
-      const int n_slabs = (K + BK - 1) / BK;
-      const int row = tile_row0(lt) + prow;
-      const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
-      const int mleft = M - row;
+      const int n_slabs = (K + SK - 1) / SK;
       if (step > 0) {
         if (dbg_on) t0 = clock64();
         mbar_wait_relaxed(cdone0 + 8 * lt, (uint32_t)(step - 1) & 1);
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (dbg_on) t_dep += clock64() - t0;
       }
-      auto load_a = [&](float4 (&v)[4], int kt) {
-        if (kt >= n_slabs) return;
-        const int k = kt * BK + 4 * pc;
+      if constexpr (!BF) {
+        // warp pw owns tile rows [16 pw, 16 pw + 16); load i (0..3) covers rows 4 i + lane / 8, lane % 8 = 16-byte k-chunk
+        const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
+        const int row = tile_row0(lt) + prow;
+        const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
+        const int mleft = M - row;
+        auto load_a = [&](float4 (&v)[4], int kt) {
+          if (kt >= n_slabs) return;
+          const int k = kt * BK + 4 * pc;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      auto produce = [&](float4 (&v)[4], int kt) {
-        const uint32_t st = g % kStages2;
-        const uint32_t stage_base = smem + st * kStage2;
-        if (dbg_on) t0 = clock64();
-        if (g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
-        if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          for (int i = 0; i < 4; ++i)
+            v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto produce = [&](float4 (&v)[4], int kt) {
+          const uint32_t st = g % kStages2;
+          const uint32_t stage_base = smem + st * kStage2;
+          if (dbg_on) t0 = clock64();
+          if (g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
+          if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = prow + 4 * i;
-          const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
-          split_store(stage_base + off, stage_base + kATile + off, v[i]);
+          for (int i = 0; i < 4; ++i) {
+            const int r = prow + 4 * i;
+            const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+            split_store(stage_base + off, stage_base + kATile + off, v[i]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(B.afull0 + 8 * st);            // own CTA's barrier (the follower's is relayed)
+          load_a(v, kt + 2);
+          ++g;
+          if (dbg_on) t_work += clock64() - t0;
+        };
+        float4 v0[4], v1[4];
+        load_a(v0, 0);
+        load_a(v1, 1);
+        for (int kt = 0; kt < n_slabs; kt += 2) {
+          produce(v0, kt);
+          if (kt + 1 < n_slabs) produce(v1, kt + 1);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(B.afull0 + 8 * st);            // own CTA's barrier (the follower's is relayed)
-        load_a(v, kt + 2);
-        ++g;
-        if (dbg_on) t_work += clock64() - t0;
-      };
-      float4 v0[4], v1[4];
-      load_a(v0, 0);
-      load_a(v1, 1);
-      for (int kt = 0; kt < n_slabs; kt += 2) {
-        produce(v0, kt);
-        if (kt + 1 < n_slabs) produce(v1, kt + 1);
+      } else {
+        // bf16 planes: a 64-k slab is produced as two 32-k halves (the register budget holds two halves in flight, as it
+        // holds two 32-k slabs above).  Per half a warp covers its 16 rows in two groups of 8: lane / 4 = row in the
+        // group, lane % 4 = which 8 floats (32 bytes, two 128-bit loads) -> ONE 16-byte chunk of each plane.  A store
+        // instruction then covers 8 rows x 4 chunks whose swizzled positions (chunk ^ row % 8) tile all 32 banks:
+        // 512 bytes in 4 wavefronts.
+        const int prow8 = pw * 16 + (lane >> 2), q = lane & 3;
+        const int row = tile_row0(lt) + prow8;
+        const float* __restrict__ src = S.A + (size_t)row * lda + 8 * q;
+        const int mleft = M - row;
+        const int n_halves = 2 * n_slabs;
+        auto load_h = [&](float4 (&v)[4], int hs) {
+          if (hs >= n_halves) return;
+          const int k = hs * BK + 8 * q;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool ok = 8 * i < mleft;
+            const float* __restrict__ p = src + (size_t)(8 * i) * lda + hs * BK;
+            v[2 * i] = (ok && k < K) ? ldcg4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[2 * i + 1] = (ok && k + 4 < K) ? ldcg4(p + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        auto produce_h = [&](float4 (&v)[4], int hs) {
+          const uint32_t st = g % kStages2;
+          const uint32_t stage_base = smem + st * kStage2;
+          const int h = hs & 1;
+          if (dbg_on) t0 = clock64();
+          if (h == 0 && g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
+          if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = prow8 + 8 * i;
+            const uint32_t off = (uint32_t)(r * 128 + (((4 * h + q) ^ (r & 7)) * 16));
+            split_store_bf8(stage_base + off, stage_base + kATile + off, v[2 * i], v[2 * i + 1]);
+          }
+          if (h == 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(B.afull0 + 8 * st);          // own CTA's barrier (the follower's is relayed)
+            ++g;
+          }
+          load_h(v, hs + 2);
+          if (dbg_on) t_work += clock64() - t0;
+        };
+        float4 v0[4], v1[4];
+        load_h(v0, 0);
+        load_h(v1, 1);
+        for (int hs = 0; hs < n_halves; hs += 2) {
+          produce_h(v0, hs);
+          produce_h(v1, hs + 1);
+        }
       }
     }
     if (dbg_on) { a.dbg[2] = t_dep; a.dbg[3] = t_wait; a.dbg[4] = t_work; }
@@ -1005,6 +1127,17 @@ struct Dw2Args {
   int n_tiles, K;
 };
 
+// MN-major SWIZZLE_128B descriptor for 16-bit elements (the canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in units of
+// 16 bytes): 64 MN elements = one 128-byte row per k, 8 k-rows = one 1024-byte swizzle atom (chunk ^ k % 8), SBO 1024
+// between 8-k groups, LBO 8192 between 64-wide MN blocks (64 k-rows of a slab each); layout_type 2.
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// BF = false: TF32 hi / lo tiles, 32-sample slabs (kept for the stand-alone fp32-grade entry fgs_gemm_tn).
+// BF = true: bf16 hi / mid tiles, 64-sample slabs in the same bytes, kind::f16: the weight gradients of the fused step.
+template <bool BF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_dw2_kernel(const __grid_constant__ Dw2Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
@@ -1017,7 +1150,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
 
   int K = a.K;
   if (a.rows_dev) K = min(K, *a.rows_dev);
-  const int n_slabs = (K + BK - 1) / BK;
+  constexpr int SK = BF ? 2 * BK : BK;                          // samples per slab
+  const int n_slabs = (K + SK - 1) / SK;
   const long long units = (long long)a.n_tiles * n_slabs;
   const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
   const int u_beg = (int)(units * pair / n_pairs), u_end = (int)(units * (pair + 1) / n_pairs);
@@ -1070,8 +1204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
         const int len = min(n_slabs - s0, u_end - u);
         const DwProblem& P = a.p[a.tile_prob[tile]];
         const int BN = min(TN, (P.N - a.tile_n[tile] * TN + 15) & ~15);
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256, MN-major
+        const uint32_t idesc = make_idesc(BF, BN, 2 * BM, true);                            // M = 256, MN-major
         for (int i = 0; i < len; ++i, ++g) {
           const uint32_t st = g % kStagesD2;
           if (dbg_cta) t0 = clock64();
@@ -1085,11 +1218,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
           const uint32_t b_hi = stage_base + 2 * kATile, b_lo = b_hi + kBHalfD2;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dah = make_desc_mn(a_hi + j * 1024), dal = make_desc_mn(a_lo + j * 1024);
-            const uint64_t dbh = make_desc_mn(b_hi + j * 1024), dbl = make_desc_mn(b_lo + j * 1024);
-            mma2_tf32(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
-            mma2_tf32(d, dah, dbl, idesc, 1);
-            mma2_tf32(d, dah, dbh, idesc, 1);
+            // k-step j: TF32 = sample rows [8 j, 8 j + 8) of every block (1024 bytes on); bf16 = rows [16 j, 16 j + 16)
+            // = two 8-row groups (2048 bytes on)
+            const uint32_t ko = BF ? j * 2048 : j * 1024;
+            const uint64_t dah = BF ? make_desc_mn16(a_hi + ko) : make_desc_mn(a_hi + ko);
+            const uint64_t dal = BF ? make_desc_mn16(a_lo + ko) : make_desc_mn(a_lo + ko);
+            const uint64_t dbh = BF ? make_desc_mn16(b_hi + ko) : make_desc_mn(b_hi + ko);
+            const uint64_t dbl = BF ? make_desc_mn16(b_lo + ko) : make_desc_mn(b_lo + ko);
+            mma2<BF>(d, dal, dbh, idesc, j != 0 ? 1u : 0u);
+            mma2<BF>(d, dah, dbl, idesc, 1);
+            mma2<BF>(d, dah, dbh, idesc, 1);
           }
           mma2_commit(B.free0 + 8 * st);
           mma2_commit(B.rfull0 + 8 * (g % kRegions));
@@ -1102,15 +1240,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
     // ================= producers =================
     // A: warp pw owns sample rows 4 pw .. 4 pw + 3; lane l owns out-features 128 rank + 4 l .. + 3
     // B: this CTA's half (h = BN / 2 <= 64 input features): 16 lanes per sample row, two rows per load
+    // bf16: the same loads per 32 samples; a 64-sample slab is produced as two halves (rows 32 h + ...), 8-byte stores:
+    // lane l's 4 features sit in block l / 16 at chunk (l % 16) / 2 (^ row % 8), byte (l % 2) * 8 of the 128-byte row
     const int pw = warp - kConsumers / 32;
-    const uint32_t a_blk = (uint32_t)(lane >> 3) * 4096u + (uint32_t)(lane & 1) * 16u;
-    const uint32_t a_c32 = (uint32_t)((lane & 7) >> 1);
+    const uint32_t a_blk = BF ? (uint32_t)(lane >> 4) * 8192u + (uint32_t)(lane & 1) * 8u
+                              : (uint32_t)(lane >> 3) * 4096u + (uint32_t)(lane & 1) * 16u;
+    const uint32_t a_c32 = BF ? (uint32_t)((lane & 15) >> 1) : (uint32_t)((lane & 7) >> 1);
     const int bq = lane & 15, bsub = lane >> 4;                 // feature quad and row-in-pair of the B loads
-    const uint32_t b_blk = (uint32_t)(bq >> 3) * 4096u + (uint32_t)(bq & 1) * 16u;
-    const uint32_t b_c32 = (uint32_t)((bq & 7) >> 1);
+    const uint32_t b_blk = BF ? (uint32_t)(bq & 1) * 8u : (uint32_t)(bq >> 3) * 4096u + (uint32_t)(bq & 1) * 16u;
+    const uint32_t b_c32 = BF ? (uint32_t)(bq >> 1) : (uint32_t)((bq & 7) >> 1);
     uint32_t g = 0;
-    struct Cur { int u, tile, s; };
+    // cursor over the CTA's units; bf16 walks HALF slabs (h = 0, 1 inside slab s of `tile`)
+    struct Cur { int u, tile, s, h; };
     auto advance = [&](Cur& c) {
+      if (BF && c.h == 0) { c.h = 1; return; }
+      c.h = 0;
       ++c.u; ++c.s;
       if (c.s == n_slabs) { c.s = 0; ++c.tile; }
     };
@@ -1120,7 +1264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
       const int n0 = a.tile_n[c.tile] * TN;
       const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;        // input features per CTA
       const int fa = (int)rank * BM + 4 * lane, fb = n0 + (int)rank * h + 4 * bq;
-      const int k0 = c.s * BK + 4 * pw;
+      const int k0 = (BF ? (2 * c.s + c.h) : c.s) * BK + 4 * pw;
       const bool in_a = fa < P.M, in_b = 4 * bq < h && fb < P.N;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1151,29 +1295,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
     auto produce = [&](float4 (&va)[4], float4 (&vb)[2], const Cur& c, Cur& pf) {
       const uint32_t st = g % kStagesD2;
       const uint32_t stage_base = smem + st * kStageD2;
-      if (g >= (uint32_t)kStagesD2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesD2) - 1) & 1);
+      const bool first = !BF || c.h == 0, last = !BF || c.h == 1;      // of this slab's units
+      if (first && g >= (uint32_t)kStagesD2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesD2) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
-        const uint32_t r = (uint32_t)(4 * pw + i);
-        const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 3u)) * 32u);
-        split_store(stage_base + off, stage_base + kATile + off, va[i]);
+        if (BF) {
+          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + i);
+          const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 7u)) * 16u);
+          split_store_bf4(stage_base + off, stage_base + kATile + off, va[i]);
+        } else {
+          const uint32_t r = (uint32_t)(4 * pw + i);
+          const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 3u)) * 32u);
+          split_store(stage_base + off, stage_base + kATile + off, va[i]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t r = (uint32_t)(4 * pw + 2 * i + bsub);
-        const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 3u)) * 32u);
-        split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
+        if (BF) {
+          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + 2 * i + bsub);
+          const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 7u)) * 16u);
+          split_store_bf4(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
+        } else {
+          const uint32_t r = (uint32_t)(4 * pw + 2 * i + bsub);
+          const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 3u)) * 32u);
+          split_store(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
+        }
       }
-      if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(B.afull0 + 8 * st);     // own CTA's barrier (the follower's is relayed)
+      if (last) {
+        if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.afull0 + 8 * st);   // own CTA's barrier (the follower's is relayed)
+        ++g;
+      }
       load_ab(va, vb, pf);
       advance(pf);
-      ++g;
     };
-    Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs}, pf = c;
+    Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs, 0}, pf = c;
     float4 va0[4], vb0[2], va1[4], vb1[2];
     load_ab(va0, vb0, pf); advance(pf);
     load_ab(va1, vb1, pf); advance(pf);
@@ -1254,12 +1413,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> g_maps;
 
 // 2-D map of a row-major fp32 matrix: `cols` valid columns (dim 0), `rows` rows of pitch ld floats; box =
 // (32 floats, box_rows rows), SWIZZLE_128B.  Out-of-range box elements read as zero / are not written.
-int get_map(const float* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out) {
-  auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows);
+// bf16: the plane holds 2-byte elements (cols / ld in elements), box = (64 elements, box_rows rows): the same 128 bytes.
+int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out, bool bf16 = false) {
+  auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows, (int)bf16);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -1274,11 +1434,11 @@ int get_map(const float* plane, int cols, int rows, int ld, int box_rows, CUtens
     g_encode = (EncodeTiledFn)fn;
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};                           // bytes, dim 1
-  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};              // bytes, dim 1
+  const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BK : BK), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
-  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
+  CUresult r = g_encode(&tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1333,23 +1493,24 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
 
 // The MLP chain in one launch (see mlp_chain_kernel).  steps[i]: C_i = act(A_i W_i^T + b_i) on the column
 // block [n0, n0 + 256) with pre-split weight planes Bh / Bl ([round_up(N,8)][ldb], K-major).
-int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st) {
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st, bool bf16) {
   if (M <= 0 || n_steps <= 0) return 0;
   if (n_steps > kChainMaxSteps) return fgs::fail_arg("mlp_chain: too many steps");
-  static bool configured2 = false;
-  int rc = configure_once(mlp_chain2_kernel, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
+  static bool configured2 = false, configured2b = false;
+  int rc = bf16 ? configure_once(mlp_chain2_kernel<true>, configured2b, "mlp_chain2 (bf16) smem attribute", kSmemBytesChain2)
+                : configure_once(mlp_chain2_kernel<false>, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
   if (rc) return rc;
   ChainArgs a;
   ChainMaps maps;
   memset(&a, 0, sizeof(a));
   for (int i = 0; i < n_steps; ++i) {
     const ChainStepHost& h = steps[i];
-    if ((h.lda & 3) || (h.ldb & 3) || (((uintptr_t)h.A | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
-      return fgs::fail_arg("mlp_chain needs 16-byte aligned operands with leading dimensions % 4 == 0");
+    if ((h.lda & 3) || (h.ldb & (bf16 ? 7 : 3)) || (((uintptr_t)h.A | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
+      return fgs::fail_arg("mlp_chain needs 16-byte aligned operands and rows");
     if (h.K > h.ldb) return fgs::fail_arg("mlp_chain: K exceeds the weight plane's row length");
     const int rows_alloc = (h.N + 7) & ~7;
-    if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.hi[i]))) return rc;
-    if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.lo[i]))) return rc;
+    if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.hi[i], bf16))) return rc;
+    if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.lo[i], bf16))) return rc;
     const int c_tma = ((h.ldc & 3) == 0 && ((uintptr_t)h.C & 15) == 0) ? 1 : 0;
     maps.c[i] = maps.hi[i];
     if (c_tma && (rc = get_map(h.C, h.N, M, h.ldc, 32, &maps.c[i]))) return rc;
@@ -1364,14 +1525,15 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   int pairs_n = FGS_NUM_SMS / 2;
   if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
   if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
-  mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+  if (bf16) mlp_chain2_kernel<true><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+  else mlp_chain2_kernel<false><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
   return fgs::check_launch(steps[0].bias ? "mlp_chain_fwd" : "mlp_chain_bwd", st);   // (only the forward adds biases)
 }
 
 // All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first
 // min(K, *rows_dev) rows, colsum_i[m] += sum_k A_i[k][m] (may be NULL).  Rows of A / B must be readable in whole
 // float4s (lda, ldb % 4 == 0, 16-byte aligned bases).
-int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st) {
+int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st, bool bf16) {
   if (n <= 0 || K <= 0) return 0;
   if (n > kDwMaxProblems) return fgs::fail_arg("mlp_dw: too many problems");
   // CTA pairs: a pair owns all (<= 256) out-features x one 128-wide block of input features
@@ -1396,15 +1558,17 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   }
   if (nt2 == 0) return 0;
   b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
-  static bool configured2 = false;
-  int rc2 = configure_once(mlp_dw2_kernel, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
+  static bool configured2 = false, configured2b = false;
+  int rc2 = bf16 ? configure_once(mlp_dw2_kernel<true>, configured2b, "mlp_dw2 (bf16) smem attribute", kSmemBytesDw2)
+                 : configure_once(mlp_dw2_kernel<false>, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
   if (rc2) return rc2;
   // every pair should own at least ~8 slabs, else the epilogues dominate
-  const long long units2 = (long long)nt2 * fgs::cdiv(K, BK);
+  const long long units2 = (long long)nt2 * fgs::cdiv(K, bf16 ? 2 * BK : BK);
   int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
   if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
   if (pairs_n < 1) pairs_n = 1;
-  mlp_dw2_kernel<<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
+  if (bf16) mlp_dw2_kernel<true><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
+  else mlp_dw2_kernel<false><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
   return fgs::check_launch("mlp_dw", st);
 }
 
@@ -1427,7 +1591,7 @@ int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     J.j[i].W = jobs[i].W; J.j[i].hi = jobs[i].hi; J.j[i].lo = jobs[i].lo;
     J.j[i].rows = jobs[i].rows; J.j[i].cols = jobs[i].cols; J.j[i].ld = jobs[i].ld;
-    J.j[i].ld_out = jobs[i].ld_out; J.j[i].transpose = jobs[i].transpose;
+    J.j[i].ld_out = jobs[i].ld_out; J.j[i].transpose = jobs[i].transpose; J.j[i].bf16 = jobs[i].bf16;
   }
   weight_split_kernel<<<dim3(32, n), 256, 0, st>>>(J);
   return fgs::check_launch("weight_split", st);
@@ -1460,11 +1624,55 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
   if (rc) return rc;
   fine::SplitJobHost job;
   job.W = B; job.hi = g_scratch; job.lo = g_scratch + (size_t)np * kp;
-  job.ld = ldb; job.ld_out = kp;
+  job.ld = ldb; job.ld_out = kp; job.bf16 = 0;
   if (mode == 0) { job.rows = N; job.cols = K; job.transpose = 0; }
   else { job.rows = K; job.cols = N; job.transpose = 1; }
   if ((rc = fine::weight_split_jobs(&job, 1, st))) return rc;
   return fine::gemm_w(M, N, K, A, lda, job.hi, job.lo, kp, C, ldc, bias, relu, bits_in, bits_out, rows_dev, st);
+}
+
+// Stand-alone entries of the 3xBF16 kernels the fused step's BACKWARD runs (tests): one step of the chain kernel
+// (C = A B^T for mode 0 / A B for mode 1, optional mask bits) and the weight-gradient product.
+extern "C" int fgs_gemm_tcw_bf16(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                 float* C, int ldc, const uint32_t* bits_in, const int32_t* rows_dev,
+                                 fgs_stream_t stream) {
+  FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+  FGS_REQUIRE(mode == 0 || mode == 1, "fgs_gemm_tcw_bf16: mode must be 0 (B [N][K]) or 1 (B [K][N])");
+  FGS_REQUIRE(N <= 256, "fgs_gemm_tcw_bf16: one 256-column block");
+  if (M == 0 || N == 0 || K == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kp = (K + 7) & ~7, np = (N + 7) & ~7;
+  const size_t need = (size_t)np * kp;                       // 2 bf16 planes = np * kp floats
+  if (need > g_scratch_floats) {
+    if (g_scratch) {
+      cudaStreamSynchronize(st);
+      cudaFree(g_scratch);
+      g_maps.clear();
+    }
+    int rc = fgs::check_cuda(cudaMalloc(&g_scratch, need * sizeof(float)), "gemm_tcw scratch");
+    if (rc) return rc;
+    g_scratch_floats = need;
+  }
+  int rc = fgs::check_cuda(cudaMemsetAsync(g_scratch, 0, need * sizeof(float), st), "gemm_tcw scratch memset");
+  if (rc) return rc;
+  fine::SplitJobHost job;
+  job.W = B; job.hi = g_scratch; job.lo = g_scratch + (size_t)np * kp / 2;
+  job.ld = ldb; job.ld_out = kp; job.bf16 = 1;
+  if (mode == 0) { job.rows = N; job.cols = K; job.transpose = 0; }
+  else { job.rows = K; job.cols = N; job.transpose = 1; }
+  if ((rc = fine::weight_split_jobs(&job, 1, st))) return rc;
+  fine::ChainStepHost s{};
+  s.A = A; s.lda = lda; s.K = K; s.Bh = job.hi; s.Bl = job.lo; s.ldb = kp;
+  s.C = C; s.ldc = ldc; s.N = N; s.n0 = 0; s.bias = nullptr; s.relu = 0; s.bits_in = bits_in; s.bits_out = nullptr;
+  return fine::mlp_chain(&s, 1, M, rows_dev, st, true);
+}
+
+extern "C" int fgs_gemm_tn_bf16(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                                int ldc, float* colsum, const int32_t* rows_dev, fgs_stream_t stream) {
+  FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  fine::DwProblemHost p{A, B, C, colsum, M, N, lda, ldb, ldc};
+  return fine::mlp_dw(&p, 1, K, rows_dev, (cudaStream_t)stream, true);
 }
 
 // Debug: device buffer of 2 int64 that the next gemm_w launches fill with the clock cycles consumer 0 of

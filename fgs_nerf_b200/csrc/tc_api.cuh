@@ -10,6 +10,7 @@ namespace fine {
 struct SplitJobHost {
   const float* W; float* hi; float* lo;
   int rows, cols, ld, ld_out, transpose;  // transpose: out[c][r] (ld_out >= rows) else out[r][c]
+  int bf16;                               // 1: bf16 hi / mid planes (ld_out in 2-byte elements), 0: TF32 hi / lo
 };
 // hi / lo TF32 planes of up to 16 weight matrices in one launch (gemm_tcw.cu)
 int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st);
@@ -32,19 +33,21 @@ struct ChainStepHost {
   const float* bias; int relu;
   const uint32_t* bits_in; uint32_t* bits_out;
 };
-int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
+// bf16: Bh / Bl are bf16 hi / mid planes (ldb in elements, % 8 == 0) and the chain runs kind::f16 (3xBF16)
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st, bool bf16 = false);
 
 // One weight-gradient problem of mlp_dw (gemm_tcw.cu: mlp_dw_kernel): C[M,N] += A[K,M]^T B[K,N], colsum[m] += sum_k A[k][m]
 struct DwProblemHost {
   const float* A; const float* B; float* C; float* colsum;
   int M, N, lda, ldb, ldc;
 };
-int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st);
+// bf16: 3xBF16 operands (kind::f16, 64-sample slabs) instead of 3xTF32
+int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st, bool bf16 = false);
 // leave n SMs free while mlp_dw runs (a data-parallel step overlaps the gradient exchange with it)
 void set_dw_sm_reserve(int n_sms);
 
-// Layout of FgsFineParams::w_split: per layer the straight planes [out][in_ld] (forward) and the
-// transposed planes [in_ld][ldt] (backward-data), hi then lo.
+// Layout of FgsFineParams::w_split (in floats): per layer the straight TF32 hi / lo planes [out][in_ld] (forward, 3xTF32)
+// and the transposed bf16 hi / mid planes [in_ld][ldt] (backward-data, 3xBF16; ldt in 2-byte elements).
 struct WSplitLayout {
   size_t hi[FGS_MLP_LAYERS], lo[FGS_MLP_LAYERS], thi[FGS_MLP_LAYERS], tlo[FGS_MLP_LAYERS];
   int in_ld[FGS_MLP_LAYERS], out[FGS_MLP_LAYERS], ldt[FGS_MLP_LAYERS];
@@ -57,9 +60,9 @@ inline WSplitLayout wsplit_layout() {
   for (int l = 0; l < FGS_MLP_LAYERS; ++l) {
     L.in_ld[l] = in_ld[l];
     L.out[l] = (l == FGS_MLP_LAYERS - 1) ? 3 : FGS_MLP_WIDTH;
-    L.ldt[l] = (l == FGS_MLP_LAYERS - 1) ? 4 : FGS_MLP_WIDTH;
+    L.ldt[l] = (l == FGS_MLP_LAYERS - 1) ? 8 : FGS_MLP_WIDTH;     // bf16 rows are 16-byte multiples
     // straight planes are allocated with the row count rounded up to 8 (TMA row groups)
-    const size_t s = (size_t)((L.out[l] + 7) & ~7) * in_ld[l], t = (size_t)in_ld[l] * L.ldt[l];
+    const size_t s = (size_t)((L.out[l] + 7) & ~7) * in_ld[l], t = (size_t)in_ld[l] * L.ldt[l] / 2;
     L.hi[l] = o; o += s;
     L.lo[l] = o; o += s;
     L.thi[l] = o; o += t;

@@ -107,6 +107,9 @@ _lib.declare("fgs_grid_sample_bwd", C.c_int,
              [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _f3, _f3, _fp, _fp])
 _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
+_lib.declare("fgs_gemm_tn_bf16", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
+_lib.declare("fgs_gemm_tcw_bf16", C.c_int,
+             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
 _lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
 _i = C.c_int
@@ -736,13 +739,15 @@ class FineStepEngine:
             m, v = self.adam["k0"]
             if self.sparse_k0:
                 # k0: masked Adam over the touched bricks only; clears the gradients / flags it consumed
-                if not self._brick_list_ready:      # (the multi-GPU exchange has already built it)
-                    check(lib.fgs_brick_list(ptr(self.ws["k0_brick_flags"]), self.X, self.Y, self.Z,
-                                             ptr(self.ws["k0_brick_list"]), st))
+                if self._brick_list_ready:          # the multi-GPU exchange has built the (ordered) list of the union
+                    check(lib.fgs_adam_upd_bricks(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), ptr(self.ws["k0_brick_list"]),
+                                                  self.X, self.Y, self.Z, K0_DIM, step, b1, b2, self.lr["k0"] * lr_scale,
+                                                  eps, st))
+                else:                               # single GPU: straight from the flags, no list
+                    check(lib.fgs_adam_upd_brick_flags(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v),
+                                                       ptr(self.ws["k0_brick_flags"]), self.X, self.Y, self.Z, K0_DIM, step,
+                                                       b1, b2, self.lr["k0"] * lr_scale, eps, st))
                 self._brick_list_ready = False
-                check(lib.fgs_adam_upd_bricks(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), ptr(self.ws["k0_brick_list"]),
-                                              self.X, self.Y, self.Z, K0_DIM, step, b1, b2, self.lr["k0"] * lr_scale,
-                                              eps, st))
             else:
                 check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
                                        b1, b2, self.lr["k0"] * lr_scale, eps, 1, st))

@@ -182,6 +182,11 @@ int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int m
 int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                         const int32_t* brick_list, int X, int Y, int Z, int channels, int step,
                         float beta1, float beta2, float lr, float eps, fgs_stream_t stream);
+/* The same masked Adam driven by the touched-brick FLAGS directly (no list; the flags it consumes are cleared): what a
+ * single-GPU step uses -- the ordered list is only needed to pack / unpack the multi-GPU exchange. */
+int fgs_adam_upd_brick_flags(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* brick_flags,
+                             int X, int Y, int Z, int channels, int step, float beta1, float beta2, float lr,
+                             float eps, fgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Total variation  (reference: model/cuda/total_variation.cpp:16-32, _kernel.cu:13-133)

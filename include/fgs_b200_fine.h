@@ -253,6 +253,16 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
 int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
 
+/* The kernels of the fused step's BACKWARD, stand-alone: operands split into bf16 hi / mid planes, products
+ * hi*hi + hi*mid + mid*hi on tcgen05 kind::f16 (3xBF16: ~1e-5 relative, half the tensor-core time of 3xTF32; the
+ * forward keeps 3xTF32 so that the ReLU branch assignment stays the fp32 one).  fgs_gemm_tcw_bf16: one step of the
+ * chain kernel, C[M,N<=256] = A B^T (mode 0) / A B (mode 1), masked by bits_in when given.  fgs_gemm_tn_bf16: the
+ * weight-gradient product C[M<=256,N] += A[K,M]^T B[K,N], colsum as fgs_gemm_tn. */
+int fgs_gemm_tcw_bf16(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                      float* C, int ldc, const uint32_t* bits_in, const int32_t* rows_dev, fgs_stream_t stream);
+int fgs_gemm_tn_bf16(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
+
 /* Debug aid: 20 x int64 device buffer (slots 10..19: the same phases of the weight-gradient kernel) that subsequent pre-split GEMM launches fill with the clock cycles
  * the roles of CTA (0,0) spent per phase (consumer drain / epilogue, producer wait / work, issuer waits on
  * a_full / b_full / r_empty / free, issuer total; tools/gemm_phase_probe.py).  NULL = off. */

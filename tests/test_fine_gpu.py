@@ -466,6 +466,62 @@ def _dw_case(cuda, M, N, K):
     assert _rel(out[:, :N], A[:K // 2, :M].double().T @ B[:K // 2, :N].double()) < 2e-6
 
 
+@pytest.mark.parametrize("mode,M,N,K", [(1, 257, 256, 256), (1, 100, 256, 3), (1, 30000, 112, 256), (1, 19000, 64, 256),
+                                        (1, 515, 256, 320), (0, 300, 256, 128), (0, 1000, 192, 72)])
+def test_chain_step_3xbf16(cuda, mode, M, N, K):
+    """fgs_gemm_tcw_bf16 = one step of the chain kernel in the form the BACKWARD-data chain runs it: operands as bf16
+    hi / mid planes, hi*hi + hi*mid + mid*hi on tcgen05 kind::f16.  Error model: 2^-16 per product (the dropped
+    mid*mid term) -> <= 3e-5 of max|out| (observed ~5e-6); the bar is 1e-4."""
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    A, B, want = _tc_case(cuda, mode, M, N, K, mode * 611 + M + N + K)
+    ldc = (N + 3) // 4 * 4
+    out = torch.full((M, ldc), 7.0, device=cuda)
+    rows = torch.tensor([M], dtype=torch.int32, device=cuda)
+    check(lib.fgs_gemm_tcw_bf16(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), None,
+                                ptr(rows), stream()))
+    torch.cuda.synchronize()
+    err = _rel(out[:, :N], want)
+    print(f"3xBF16 chain step mode {mode} {M}x{N}x{K}: rel err {err:.3e}")
+    assert err < 3e-5, err
+    if N == 256:
+        g = torch.Generator(device="cpu").manual_seed(3)
+        bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (M, 8), generator=g, dtype=torch.int64).to(torch.int32).to(cuda)
+        half = M // 2
+        rows.fill_(half)
+        out.fill_(7.0)
+        check(lib.fgs_gemm_tcw_bf16(mode, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0),
+                                    ptr(bits), ptr(rows), stream()))
+        torch.cuda.synchronize()
+        unpacked = ((bits[:half].long().unsqueeze(-1) >> torch.arange(32, device=cuda)) & 1).reshape(half, 256).bool()
+        assert bool((out[half:, :N] == 7.0).all()), "rows beyond the device-side row count were written"
+        if half:
+            assert _rel(out[:half, :N], want[:half] * unpacked) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 320, 1000), (3, 256, 777), (256, 112, 40000), (256, 256, 130), (256, 256, 27000),
+                                   (192, 104, 5000), (256, 64, 63)])
+def test_weight_gradient_kernel_3xbf16(cuda, M, N, K):
+    """fgs_gemm_tn_bf16 = the weight / bias gradient kernel of the fused step (MN-major bf16 hi / mid tiles, 64-sample
+    slabs, kind::f16 on CTA pairs): <= 3e-5 of max|out|; the bias gradient (column sums) is accumulated in fp32."""
+    from fgs_nerf_b200._lib import lib, check, ptr, stream
+    A, B, want = _tc_case(cuda, 2, M, N, K, 17 * M + N + K)
+    out = torch.zeros(M, (N + 3) // 4 * 4, device=cuda)
+    csum = torch.zeros(M, device=cuda)
+    rows = torch.tensor([K], dtype=torch.int32, device=cuda)
+    check(lib.fgs_gemm_tn_bf16(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), ptr(csum),
+                               ptr(rows), stream()))
+    torch.cuda.synchronize()
+    err = _rel(out[:, :N], want)
+    cerr = _rel(csum, A[:, :M].double().sum(0))
+    print(f"3xBF16 tn gemm {M}x{N}x{K}: rel err {err:.3e}, colsum rel err {cerr:.3e}")
+    assert err < 3e-5 and cerr < 2e-6
+    out.zero_(); csum.zero_(); rows.fill_(K // 2)
+    check(lib.fgs_gemm_tn_bf16(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(out), out.stride(0), ptr(csum),
+                               ptr(rows), stream()))
+    torch.cuda.synchronize()
+    assert _rel(out[:, :N], A[:K // 2, :M].double().T @ B[:K // 2, :N].double()) < 3e-5
+
+
 def test_chunked_render_matches_oracle_forward(cuda):
     """engine.render (the render_viewpoints chunk loop, model/utils.py:296-299) over a ragged ray set
     (2 full chunks + a short one) equals the oracle's forward_fine on the same rays."""
