@@ -60,7 +60,7 @@ _SIGS = {
     "fgs_brick_list": (_i, [_p, _i, _i, _i, _p, _p]),
     "fgs_brick_copy": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fgs_adam_upd_bricks": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _p]),
-    "fgs_adam_upd_brick_flags": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _p]),
+    "fgs_adam_upd_brick_flags": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _p]),
     "fgs_total_variation_add_grad": (_i, [_p, _p, _p, _f, _f, _f, _i, _i, _i, _i, _i, _i, _p]),
 }
 

@@ -294,15 +294,19 @@ __global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant_
     if (c2 == 0) continue;
     const int base1 = P.off1[ray], c1 = P.cnt1[ray];
     int dst = P.off2[ray];
-    if (dst + c2 > P.cap_m2) continue;  // flagged by the scan
+    // a ray that does not fit (flagged by the scan: the step's results are void) still fills the slots that exist, so
+    // that every row below min(M2, cap_m2) names a real sample and nothing downstream indexes with stale memory
+    if (dst >= P.cap_m2) continue;
     for (int b = 0; b < c1; b += 32) {
       const int i = b + lane;
       const bool l2 = (i < c1) && (P.flag1[base1 + i] & FGS_F_L2);
       const unsigned m = __ballot_sync(0xffffffffu, l2);
       if (l2) {
         const int s = dst + __popc(m & lanemask_lt());
-        P.idx1_of2[s] = base1 + i;
-        P.ray_id2[s] = ray;
+        if (s < P.cap_m2) {
+          P.idx1_of2[s] = base1 + i;
+          P.ray_id2[s] = ray;
+        }
       }
       dst += __popc(m);
     }

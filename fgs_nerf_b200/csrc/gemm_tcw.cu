@@ -983,29 +983,38 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
     const int quarter = warp & 3, col_half = (warp >> 2) * (TNF / 2);
     const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_half;
     const uint32_t stg = smem + kStagingOff + (uint32_t)warp * kStagingWarp;
-    long long t_main = 0, t_epi = 0, t0 = 0;
+    long long t_main = 0, t_epi = 0, t0 = 0, t_bias = 0, t_tm = 0, t_ma = 0, t_st = 0, t_fe = 0, tq = 0;
     const bool dbg_on = dbg_cta && tid == 0;
     for (int w = 0; w < n_items; ++w) {
       const int step = w / my_tiles, lt = w - step * my_tiles;
       const ChainStep& S = a.s[step];
       const int n0 = S.n0, N = S.N;
+      if (dbg_on) tq = clock64();
       const int BN = min(TNF, (N - n0 + 15) & ~15);
       const uint32_t rg = (uint32_t)w & 1;
       const uint32_t bias_s = smem + kBiasOff + rg * (TNF * 4);
       reinterpret_cast<float*>(smem_raw + kBiasOff)[rg * TNF + tid] = (S.bias && n0 + tid < N) ? S.bias[n0 + tid] : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (dbg_on) t0 = clock64();
-      mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+      if (dbg_on) { t0 = clock64(); t_bias += t0 - tq; }
       const int m0 = tile_row0(lt);
       const int mr0 = m0 + quarter * 32;
       const int m = mr0 + lane;
+      // the ReLU-mask words of this thread's row (backward-data steps): in flight while the accumulator is still being
+      // computed (loaded inside the block loop they cost one L2 round trip per block: 44 of the epilogue's 190 us)
+      uint32_t mask_w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (S.bits_in && m < M) {
+        const uint4 mw = *reinterpret_cast<const uint4*>(S.bits_in + (size_t)m * 8 + ((n0 + col_half) >> 5));
+        mask_w[0] = mw.x; mask_w[1] = mw.y; mask_w[2] = mw.z; mask_w[3] = mw.w;
+      }
+      mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
 #pragma unroll 1
       for (int q = 0; q < TNF / 2 / 32; ++q) {
         const int c0 = col_half + 32 * q;
         if (c0 < BN) {
           float v[32];
+          if (dbg_on) tq = clock64();
           {
             uint32_t r0[16], r1[16];
             tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
@@ -1014,16 +1023,21 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
           }
+          if (dbg_on) { const long long t1 = clock64(); t_tm += t1 - tq; tq = t1; }
           const int word = (n0 + c0) >> 5;
-          uint32_t in_bits = 0xffffffffu, out_bits = 0;
-          if (S.bits_in && m < M) in_bits = S.bits_in[(size_t)m * 8 + word];
+          uint32_t in_bits = q == 0 ? mask_w[0] : q == 1 ? mask_w[1] : q == 2 ? mask_w[2] : mask_w[3], out_bits = 0;
           const uint32_t baddr = bias_s + 4 * c0;
           const bool hb = S.bias != nullptr;
           if (S.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
           else if (S.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
           else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
           if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + word] = out_bits;
+          if (dbg_on) { const long long t1 = clock64(); t_ma += t1 - tq; tq = t1; }
           if (S.c_tma && mr0 + 32 <= M) {
+            // (TMA store: the copy engine moves the block.  A version that read the staging tile back and stored it with
+            // 128-bit st.global was SLOWER, 0.230 -> 0.266 ms for the backward chain: with 17 warps sharing four
+            // schedulers the kernel is bound by CUDA-core issue slots -- operand split + epilogue arithmetic -- as much
+            // as by the tensor core, and those stores are instructions the TMA version does not issue.)
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
 #pragma unroll
@@ -1041,12 +1055,14 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
           }
         }
       }
+      if (dbg_on) { const long long t1 = clock64(); t_st += t1 - t0 - 0; tq = t1; }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {                                          // the leader may overwrite the region in BOTH CTAs
         if (rank == 0) mbar_arrive(B.rempty0 + 8 * rg);
         else mbar_arrive_cluster(l_rempty0 + 8 * rg);
       }
+      // the tile's rows of this step are complete in global memory -> (tile, step + 1) may load them
       __syncwarp();
       if (lane == 0) {
         tma_store_wait_all();
@@ -1054,10 +1070,14 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
         __threadfence();
         mbar_arrive(cdone0 + 8 * lt);
       }
-      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; }
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - t0; t_fe += t1 - tq; }
     }
-    if (lane == 0) tma_store_wait_all();
-    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; }
+    if (dbg_on) {
+      a.dbg[0] = t_main; a.dbg[1] = t_epi;
+      // finer split of the epilogue (slots 20..24): bias fill + consumer barrier, TMEM loads, bits + arithmetic,
+      // whole q loop incl. stores (from r_full), fence + arrivals
+      a.dbg[20] = t_bias; a.dbg[21] = t_tm; a.dbg[22] = t_ma; a.dbg[23] = t_st; a.dbg[24] = t_fe;
+    }
   }
   // ---- teardown: nobody may leave (or free TMEM) while the partner can still signal it or multiply into it ----
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1119,12 +1139,19 @@ static_assert(kStagesD2 * kStageD2 == kStagingOff, "staging / barrier offsets ar
 constexpr uint32_t kBarD2Off = kCDoneOff;                        // its own barrier block (4 stages do not fit Bars)
 constexpr uint32_t kSmemBytesDw2 = kBarD2Off + 8 * (2 * kStagesD2 + 2 * kRegions);
 
+constexpr int kDwMaxPairs = FGS_NUM_SMS / 2;
 struct Dw2Args {
   DwProblem p[kDwMaxProblems];
   unsigned char tile_prob[kDwMaxTiles], tile_n[kDwMaxTiles];
+  // aligned != 0: pair i works on ONE tile, pair_tile[i], and owns the pair_rank[i]-th of pair_q[i] equal slab ranges of
+  // it.  All tiles of a problem get the same q, so the pairs that read the same rows of dZ_l (one per 128-wide block
+  // of input features) walk them at the same time and the second reader finds them in L2: with the tile-major
+  // stream-K cut (aligned == 0, kept for launches with fewer pairs than tiles) every pair sat in a different layer
+  // and dZ_l came from DRAM once per block (1.05 GB per launch against 0.64 GB of operands, L2 hit rate 16 %).
+  unsigned char pair_tile[kDwMaxPairs], pair_rank[kDwMaxPairs], pair_q[kDwMaxPairs];
   const int* rows_dev;
   long long* dbg;
-  int n_tiles, K;
+  int n_tiles, K, aligned;
 };
 
 // MN-major SWIZZLE_128B descriptor for 16-bit elements (the canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in units of
@@ -1154,7 +1181,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
   const int n_slabs = (K + SK - 1) / SK;
   const long long units = (long long)a.n_tiles * n_slabs;
   const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
-  const int u_beg = (int)(units * pair / n_pairs), u_end = (int)(units * (pair + 1) / n_pairs);
+  int u_beg, u_end;
+  if (a.aligned) {
+    const int t = a.pair_tile[pair], r = a.pair_rank[pair], q = a.pair_q[pair];
+    u_beg = t * n_slabs + (int)((long long)n_slabs * r / q);
+    u_end = t * n_slabs + (int)((long long)n_slabs * (r + 1) / q);
+  } else {
+    u_beg = (int)(units * pair / n_pairs);
+    u_end = (int)(units * (pair + 1) / n_pairs);
+  }
   if (u_beg >= u_end) return;                                  // both CTAs of the pair
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1567,6 +1602,28 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
   if (units2 < 8LL * pairs_n) pairs_n = (int)((units2 + 7) / 8);
   if (pairs_n < 1) pairs_n = 1;
+  if (pairs_n >= 2 * nt2) {
+    // sibling-aligned cut: q pairs per tile, the same q for all tiles of a problem; the pairs left over go, one per
+    // tile, to the problems with the fewest pairs per tile that still fit
+    int q[kDwMaxProblems] = {0}, tiles_of[kDwMaxProblems] = {0};
+    for (int t = 0; t < nt2; ++t) ++tiles_of[b.tile_prob[t]];
+    const int base = pairs_n / nt2;
+    int left = pairs_n - base * nt2;
+    for (int i = 0; i < n; ++i) q[i] = tiles_of[i] ? base : 0;
+    for (bool again = true; again && left > 0;) {
+      again = false;
+      for (int i = 0; i < n && left > 0; ++i)
+        if (tiles_of[i] && q[i] == base && tiles_of[i] <= left) { ++q[i]; left -= tiles_of[i]; again = true; }
+    }
+    int np = 0;
+    for (int t = 0; t < nt2; ++t)
+      for (int r = 0; r < q[b.tile_prob[t]]; ++r) {
+        b.pair_tile[np] = (unsigned char)t; b.pair_rank[np] = (unsigned char)r; b.pair_q[np] = (unsigned char)q[b.tile_prob[t]];
+        ++np;
+      }
+    pairs_n = np;
+    b.aligned = 1;
+  }
   if (bf16) mlp_dw2_kernel<true><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
   else mlp_dw2_kernel<false><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
   return fgs::check_launch("mlp_dw", st);

@@ -351,6 +351,7 @@ class FineStepEngine:
         nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
         ws["k0_brick_flags"] = torch.zeros(nb, dtype=torch.uint8, device=dev)
         ws["k0_brick_list"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)), dtype=i32, device=dev)
+        ws["k0_brick_ulist"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)) + 1, dtype=i32, device=dev)
         self.sparse_k0 = (Z % 4 == 0)      # brick-driven masked Adam (else the dense reference-style scan)
         # data parallel, optional: the k0 gradient travels at VOXEL granularity (one flag byte per voxel, ascending
         # voxel list: a third of the bytes of the brick exchange).  Off by default: the union of the voxel flags is a
@@ -648,6 +649,7 @@ class FineStepEngine:
         self.lr = {k: float(t["lrate_" + k]) * decay for k in ("sdf", "k0", "rgbnet", "refnet")}
         self.adam = {}
         self.adam_step = 0
+        self.ws["k0_brick_ulist"][:2].zero_()   # its two counters alternate with the parity of adam_step
         self._S = None                      # cached pointers of the Adam state
 
     @torch.no_grad()
@@ -745,8 +747,9 @@ class FineStepEngine:
                                                   eps, st))
                 else:                               # single GPU: straight from the flags, no list
                     check(lib.fgs_adam_upd_brick_flags(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v),
-                                                       ptr(self.ws["k0_brick_flags"]), self.X, self.Y, self.Z, K0_DIM, step,
-                                                       b1, b2, self.lr["k0"] * lr_scale, eps, st))
+                                                       ptr(self.ws["k0_brick_flags"]), ptr(self.ws["k0_brick_ulist"]),
+                                                       self.X, self.Y, self.Z, K0_DIM, step, b1, b2,
+                                                       self.lr["k0"] * lr_scale, eps, st))
                 self._brick_list_ready = False
             else:
                 check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step,
@@ -875,7 +878,7 @@ class FineStepEngine:
             S.sdf_m, S.sdf_v = ptr(self.adam["sdf"][0]), ptr(self.adam["sdf"][1])
             S.k0_m, S.k0_v = ptr(self.adam["k0"][0]), ptr(self.adam["k0"][1])
             S.sparse_k0 = int(self.sparse_k0)
-            S.brick_list = ptr(self.ws["k0_brick_list"])
+            S.brick_list = ptr(self.ws["k0_brick_ulist"])     # single GPU: the unordered list (two counters + ids)
             S.n_mlp = n
             S.mlp_p, S.mlp_g = C.cast(mt["p"], _fp), C.cast(mt["g"], _fp)
             S.mlp_m, S.mlp_v = C.cast(mt["m"], _fp), C.cast(mt["v"], _fp)
@@ -940,11 +943,7 @@ class FineStepEngine:
             self._native_train_step(rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv)
             return
         if self.world_size == 1:
-            # the grid gradients are final after phase 1: their regularisers and optimiser kernels (HBM-bound, small
-            # CTAs) run on the side stream next to the tensor-core-bound weight-gradient kernel
-            self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
-            # the TV regularisers stay on the main stream: full-grid stencils run 4x slower squeezed in beside the
-            # weight-gradient CTAs than alone (75 us), and the join would wait for them
+            self.loss_backward(target, n_rays_global, has_last_ray, phase=1)     # the grid gradients are final after phase 1
             if tv and t["smooth_grad_tv"] > 0:
                 self.smooth_grad_tv_add_grad()
             if tv and t["sdf_tv"] > 0:
@@ -952,16 +951,11 @@ class FineStepEngine:
             if _stop_before_optimizer:                  # tests: the gradients an optimiser step would consume
                 self.backward_weights()
                 return
-            self._ev_grids.record(main)
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(self._ev_grids)
-                lib.fgs_prof_mark(4, stream())
-                self.optimizer_step(parts="grids")
-                self._ev_exch.record(self._side)
+            # one stream: the optimiser kernels of the grids first (their gradients are final and still in L2), then the
+            # weight gradients (a side stream cannot run beside the persistent weight-gradient CTAs, see fine_step.cu)
+            self.optimizer_step(parts="grids")
             self.backward_weights()
             self.optimizer_step(parts="mlp")
-            main.wait_event(self._ev_exch)
-            lib.fgs_prof_mark(5, stream())
             return
         else:
             self.loss_backward(target, n_rays_global, has_last_ray, phase=1)

@@ -182,11 +182,13 @@ int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int m
 int fgs_adam_upd_bricks(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                         const int32_t* brick_list, int X, int Y, int Z, int channels, int step,
                         float beta1, float beta2, float lr, float eps, fgs_stream_t stream);
-/* The same masked Adam driven by the touched-brick FLAGS directly (no list; the flags it consumes are cleared): what a
- * single-GPU step uses -- the ordered list is only needed to pack / unpack the multi-GPU exchange. */
+/* The same masked Adam for ONE GPU, where nobody needs the ordered list (it exists to pack / unpack the multi-GPU
+ * exchange): the flags are compacted over all SMs in arrival order into brick_ulist (fgs_brick_list_ints() + 1 ints,
+ * zero-initialised once: two alternating counters keyed on `step & 1`, then ids) and cleared, then one warp per listed
+ * brick.  `step` must advance by one per call. */
 int fgs_adam_upd_brick_flags(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* brick_flags,
-                             int X, int Y, int Z, int channels, int step, float beta1, float beta2, float lr,
-                             float eps, fgs_stream_t stream);
+                             int32_t* brick_ulist, int X, int Y, int Z, int channels, int step, float beta1,
+                             float beta2, float lr, float eps, fgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Total variation  (reference: model/cuda/total_variation.cpp:16-32, _kernel.cu:13-133)

@@ -81,18 +81,9 @@ class Case:
         self.backward_done = False
         torch.cuda.synchronize()
 
-    def backward_at_oracle_branches(self):
-        """Our backward, evaluated at the ORACLE's ReLU branch assignment.  The derivative of a ReLU
-        network is only defined up to the branch taken at the kinks: a hidden unit whose pre-activation
-        is within fp32 rounding noise of 0 lands on either side in two fp32 GEMM implementations (4 of
-        69.7 M units at config 2), and a different branch changes that sample's gradient by O(1).  So
-        the gradient comparison injects the oracle's masks (recomputed from its own activations) into
-        our mask bits; the number of units where our forward chose differently is returned."""
-        if self.backward_done:
-            return self.flips
+    def oracle_masks(self):
+        """ReLU masks of the six hidden layers recomputed from the ORACLE's own activations."""
         import torch.nn.functional as F
-        M2 = self.mine["counts"]["M2"]
-        eng = self.eng
         h = self.stages["rgb_feat_in"]
         masks = []
         for w, b in self.sc.rgbnet[:3]:
@@ -103,19 +94,36 @@ class Case:
         for w, b in self.sc.refnet[:3]:
             h = F.relu(F.linear(h, w.to(h.device), b.to(h.device)))
             masks.append(h > 0)
+        return masks
+
+    def inject_oracle_branches(self, eng):
+        """Overwrite the mask bits `eng`'s forward left behind with the oracle's; returns how many units differed."""
+        M2 = eng.counters()["M2"]
         flips = 0
-        pw = (1 << torch.arange(32, device=h.device, dtype=torch.int64))
-        for k, mk in enumerate(masks):
+        pw = (1 << torch.arange(32, device=eng.device, dtype=torch.int64))
+        for k, mk in enumerate(self.oracle_masks()):
             flips += int((mk != (eng.ws["H"][k][:M2] > 0)).sum())
             words = (mk.reshape(M2, 8, 32).long() * pw).sum(-1)                  # bit j of word w = unit 32 w + j
             words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
             eng.ws["hbits"][k][:M2] = words
-        self.flips, self.units = flips, 6 * M2 * 256
+        return flips
+
+    def backward_at_oracle_branches(self):
+        """Our backward, evaluated at the ORACLE's ReLU branch assignment.  The derivative of a ReLU
+        network is only defined up to the branch taken at the kinks: a hidden unit whose pre-activation
+        is within fp32 rounding noise of 0 lands on either side in two fp32 GEMM implementations (a few of
+        69.7 M units at config 2), and a different branch changes that sample's gradient by O(1).  So
+        the gradient comparison injects the oracle's masks (recomputed from its own activations) into
+        our mask bits; the number of units where our forward chose differently is returned."""
+        if self.backward_done:
+            return self.flips
+        eng = self.eng
+        self.flips, self.units = self.inject_oracle_branches(eng), 6 * self.mine["counts"]["M2"] * 256
         eng.zero_grad()
         eng.loss_backward(self.tgt)
         torch.cuda.synchronize()
         self.backward_done = True
-        return flips
+        return self.flips
 
 
 @pytest.fixture(scope="module")
@@ -216,22 +224,30 @@ def test_loss_and_gradients(case, request):
 
 @pytest.mark.parametrize("case", ["small", "config2"])
 def test_full_train_step_elementwise_against_reference_optimizer(case, request, cuda):
-    """forward + loss + backward + both TV terms + MaskedAdam as ONE library call (fgs_fine_train_step) against the
-    oracle's step, element by element, at the headline size too (160^3, 8192 rays).  Bound: the interval the first
-    Adam update of an element can lie in when its gradient is within 1e-4 (max norm) of the oracle's
-    (parity_util.adam_first_step_violations).  A hidden unit that takes the other ReLU branch than the oracle changes
-    one sample's gradient by O(1) (see Case.backward_at_oracle_branches): each such unit may put the parameters that
-    sample touches (8 x 12 k0 values, 31 x 8 sdf voxels) outside; nothing else may be."""
+    """forward + loss + backward + both TV terms + MaskedAdam against the oracle's step, ELEMENT BY ELEMENT, at the
+    headline size too (160^3, 8192 rays).  Bound: the interval the first Adam update of an element can lie in when its
+    gradient is within 1e-4 (max norm) of the oracle's (parity_util.adam_first_step_violations); no element of any
+    tensor may be outside.  Like the gradient test, the step is evaluated at the oracle's ReLU branch assignment (one
+    unit on the other branch moves one sample's contribution to EVERY weight gradient by ~1 / sqrt(M2) of the entry,
+    see Case.backward_at_oracle_branches), so it is issued launch by launch -- forward, mask injection, then the same
+    kernels fgs_fine_train_step runs; test_library_sequenced_step_equals_host_sequenced_step ties the two drivers."""
     import parity_util as U
     from fgs_nerf_b200 import engine
     c = request.getfixturevalue(case)
     N = c.rays[0].shape[0]
     eng = engine.FineStepEngine(c.sc, N, cuda, train_cfg=c.train_cfg)
     eng.set_nonempty_mask()
-    eng.train_step(*c.rays, c.step)
+    ro, rd, vd, tgt = c.rays
+    eng.forward(ro, rd, vd, c.step, _skip_composite=True)
+    torch.cuda.synchronize()
+    flips = c.inject_oracle_branches(eng)
+    eng.zero_grad()
+    eng.loss_backward(tgt)
+    eng.smooth_grad_tv_add_grad()
+    eng.sdf_tv_add_grad(c.step)
+    eng.optimizer_step()
     torch.cuda.synchronize()
     eng.check_overflow()
-    flips = c.backward_at_oracle_branches()
     ref = dict(c.m.params())
     t = c.train_cfg
     names = [f"rgbnet.{i}" for i in range(4)] + [f"refnet.{i}" for i in range(4)]
@@ -240,19 +256,12 @@ def test_full_train_step_elementwise_against_reference_optimizer(case, request, 
         items += [(n + ".weight", eng.weights[i], 1e-3, False), (n + ".bias", eng.Bt[i], 1e-3, False)]
     report = {}
     for name, mine, lr, masked in items:
-        bad = U.adam_first_step_violations(mine, c.p_before[name], ref[name].grad, lr, masked=masked)
-        report[name] = bad
-        assert bad <= 400 * flips, f"{case} {name}: {bad} of {mine.numel()} updates outside the element-wise bound ({flips} ReLU flips)"
-    print(f"{case}: elements outside the bound per tensor {report}; {flips} units on the other ReLU branch")
+        report[name] = U.adam_first_step_violations(mine, c.p_before[name], ref[name].grad, lr, masked=masked)
+    print(f"{case}: elements outside the bound per tensor {report}; {flips} units were on the other ReLU branch before the injection")
+    assert all(v == 0 for v in report.values()), report
     # masked Adam: untouched k0 voxels must be bit-identical to before
     untouched = ref["k0"].grad == 0
     assert torch.equal(eng.k0[untouched], c.p_before["k0"][untouched])
-    # and the updated parameters themselves: |p_mine - p_ref| <= 1e-4 of the largest update, except where a gradient is
-    # rounding noise (counted above)
-    for name, mine, lr, masked in items:
-        d = (mine.detach() - ref[name].detach()).abs()
-        frac = float((d > 1e-3 * lr).float().mean())
-        assert frac < 1e-3, f"{case} {name}: {frac:.2e} of the parameters differ from the oracle's by more than 1e-3 lr"
 
 
 def test_config5_forward_parity_384(cuda):

@@ -478,6 +478,6 @@ def test_library_sequenced_step_equals_host_sequenced_step(cuda):
     assert float((a.adam["sdf"][1] - b.adam["sdf"][1]).abs().max()) <= 1e-3 * float(b.adam["sdf"][1].abs().max())
     assert int(a.ws["k0_brick_flags"].sum()) == 0 and float(a.g_sdf.abs().max()) == 0.0   # cleared by the optimiser
     # argument errors come back as RuntimeError, like every other entry point
-    a._S.side_stream = torch.cuda.current_stream().cuda_stream
+    a._S.sdf_m = None
     with pytest.raises(RuntimeError):
         a.train_step(ro, rd, vd, tgt, 5003)

@@ -18,12 +18,17 @@ torch.cuda.synchronize()
 names = ["consumer: wait r_full", "consumer: epilogue (+store wait)", "producer: wait c_done (dependency)",
          "producer: wait stage free", "producer: split/store/load issue", "issuer: wait a_full", "issuer: wait b_full",
          "issuer: wait r_empty", "issuer: wait free (B prefetch)", "issuer: total"]
-dbg = torch.zeros(20, dtype=torch.int64, device=dev)
+dbg = torch.zeros(32, dtype=torch.int64, device=dev)
 def show(tag, ms, off=0):
     d = dbg.cpu().tolist()[off:off + 10]; tot = max(d[9], 1)
     print(f"{tag}: {ms*1e3:.1f} us, M2 = {eng.counters()['M2']}")
     for n, v in zip(names, d):
         print(f"  {n:36s} {v:9d} cyc  {100*v/tot:5.1f}%   {v/1965:.2f} us")
+    if off == 0:
+        e = dbg.cpu().tolist()[20:25]
+        for n, v in zip(["epilogue: bias fill + barrier", "epilogue: TMEM loads", "epilogue: bits + arithmetic",
+                         "epilogue: q loop total (from r_full)", "epilogue: fence + arrivals"], e):
+            print(f"    {n:36s} {v:9d} cyc  {v/1965:.2f} us")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 check(lib.fgs_debug_gemm_phases(dbg.data_ptr()))
 e0.record(); eng.forward(ro, rd, vd, 5003, _skip_composite=True); e1.record(); torch.cuda.synchronize()
