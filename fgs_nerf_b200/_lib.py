@@ -50,6 +50,7 @@ _SIGS = {
     "fgs_alpha2weight_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _p]),
     "fgs_adam_upd": (_i, [_p, _p, _p, _p, _p, _l, _i, _f, _f, _f, _f, _i, _p]),
     "fgs_adam_upd_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p]),
+    "fgs_adam_upd_multi_zero_grad": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p]),
     "fgs_adam_upd_zero_grad": (_i, [_p, _p, _p, _p, _l, _i, _f, _f, _f, _f, _p]),
     "fgs_brick_list_ints": (_l, [_i, _i, _i]),
     "fgs_voxel_list_ints": (_l, [_l]),

@@ -95,6 +95,7 @@ struct MultiArgs {
   float step_size[FGS_MAX_MT];
   int blk_start[FGS_MAX_MT + 1];  // first CTA of each tensor
   int count;
+  int zero_grad;                  // clear every gradient element once it has been consumed
   float beta1, beta2, omb1, omb2, eps;
 };
 
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) adam_multi_kernel(const __grid_constan
   const long long base = (long long)(blockIdx.x - a.blk_start[t]) * kMtChunk;
   AdamConst c{a.step_size[t], a.beta1, a.beta2, a.omb1, a.omb2, a.eps};
   float* __restrict__ P = a.p[t];
-  const float* __restrict__ G = a.g[t];
+  float* __restrict__ G = const_cast<float*>(a.g[t]);
   float* __restrict__ M = a.m[t];
   float* __restrict__ V = a.v[t];
   const long long n = a.n[t];
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kBlock) adam_multi_kernel(const __grid_constan
       float p = P[i], m = M[i], v = V[i];
       adam_elem(p, G[i], m, v, c, c.step_size);
       P[i] = p; M[i] = m; V[i] = v;
+      if (a.zero_grad) G[i] = 0.f;
     }
   }
 }
@@ -163,14 +165,34 @@ int fgs_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg
   }
 }
 
+static int adam_upd_multi_impl(int n_tensors, float* const* params, const float* const* grads,
+                               float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
+                               const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                               int zero_grad, fgs_stream_t stream);
+
 int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* grads,
                        float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
                        const int* steps, const float* lrs, float beta1, float beta2, float eps,
                        fgs_stream_t stream) {
+  return adam_upd_multi_impl(n_tensors, params, grads, exp_avgs, exp_avg_sqs, numels, steps, lrs, beta1, beta2, eps, 0, stream);
+}
+
+int fgs_adam_upd_multi_zero_grad(int n_tensors, float* const* params, float* const* grads,
+                                 float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
+                                 const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                                 fgs_stream_t stream) {
+  return adam_upd_multi_impl(n_tensors, params, grads, exp_avgs, exp_avg_sqs, numels, steps, lrs, beta1, beta2, eps, 1, stream);
+}
+
+static int adam_upd_multi_impl(int n_tensors, float* const* params, const float* const* grads,
+                               float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
+                               const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                               int zero_grad, fgs_stream_t stream) {
   FGS_REQUIRE(n_tensors >= 0 && n_tensors <= FGS_MAX_MT, "n_tensors out of range");
   if (n_tensors == 0) return 0;
   MultiArgs a;
   a.count = n_tensors;
+  a.zero_grad = zero_grad;
   a.beta1 = beta1; a.beta2 = beta2; a.omb1 = 1 - beta1; a.omb2 = 1 - beta2; a.eps = eps;
   int blk = 0;
   for (int t = 0; t < n_tensors; ++t) {

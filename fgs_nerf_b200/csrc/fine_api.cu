@@ -152,7 +152,9 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
     }
     if (phase != 1) {
       // ---- weight / bias gradients: dW_l = dZ_l^T X_l, all layers in one launch ----
-      if (P.g_mlp_flat && P.g_mlp_floats > 0) {
+      if (P.mlp_grads_zeroed) {
+        // cleared by the previous step's fgs_adam_upd_multi_zero_grad
+      } else if (P.g_mlp_flat && P.g_mlp_floats > 0) {
         // all 16 MLP gradient tensors are views of one buffer: one clear instead of 16
         if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
       } else {

@@ -140,6 +140,52 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
   }
 }
 
+
+// Exclusive scan of the per-ray counts FUSED into the kernels that consume the offsets (expand1, compact2): a CTA owns
+// a contiguous range of rays, sums the counts of all rays in front of it (<= 8192 ints: 32 coalesced loads per thread),
+// scans its own (<= kRaysPerCta) counts with one warp and publishes off[ray]; the last CTA also publishes the total, the
+// device-side count and the overflow bit.  This replaces a single-CTA scan launch (12 us each, twice per forward).
+constexpr int kRaysPerCta = 64;
+__device__ __forceinline__ void cta_scan_counts(const int* __restrict__ cnt, int* __restrict__ off, int n, int r0, int r1,
+                                                int* __restrict__ counters, int slot, int cap, int overflow_bit,
+                                                int* s_off /* [kRaysPerCta + 1] */, int* s_red /* [kWarps] */,
+                                                bool prescanned) {
+  const int tid = threadIdx.x, lane = lane_id(), w = tid >> 5;
+  if (prescanned) {                                    // very large batches: scan_kernel has already written off[0..n]
+    if (tid <= kRaysPerCta && r0 + tid <= n) s_off[tid] = off[r0 + tid];
+    __syncthreads();
+    return;
+  }
+  int part = 0;
+  for (int i = tid; i < r0; i += kBlock) part += cnt[i];
+  part = warp_sum(part);
+  if (lane == 0) s_red[w] = part;
+  __syncthreads();
+  if (w == 0) {
+    int base = lane < kWarps ? s_red[lane] : 0;
+    base = warp_sum(base);
+    // the CTA's own rays: two per lane
+    const int i0 = r0 + 2 * lane, i1 = i0 + 1;
+    const int c0 = i0 < r1 ? cnt[i0] : 0, c1 = i1 < r1 ? cnt[i1] : 0;
+    const int incl = warp_incl_scan(c0 + c1);
+    const int ex = base + incl - (c0 + c1);
+    s_off[2 * lane] = ex;
+    s_off[2 * lane + 1] = ex + c0;
+    if (i0 < r1) off[i0] = ex;
+    if (i1 < r1) off[i1] = ex + c0;
+    if (lane == 31) {
+      s_off[kRaysPerCta] = base + incl;
+      if (r1 == n) {                                   // last CTA: the total
+        const int total = base + incl;
+        off[n] = total;
+        counters[slot] = total;
+        if (total > cap) flag_overflow(counters, overflow_bit);
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // trilinear SDF value + 6-tap finite-difference gradient (nerf.grid_sampler, model/nerf.py:
 // 639-672 with sample_sdfs(displace=[1.0]) :597-637); gradient returned in x,y,z order (:664).
 __device__ __forceinline__ void sdf_and_grad(const FgsFineParams& P, const GridGeo& g, float px, float py,
@@ -184,10 +230,13 @@ __device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float
 //   weights1_kernel  warp per ray: transmittance recurrence over the ray's alphas (early stop T < 1e-3,
 //                    alpha / weight thresholds), flags, level-2 count
 // The arithmetic per sample and the order of the recurrence are unchanged.
-__global__ void __launch_bounds__(kBlock) expand1_kernel(const __grid_constant__ FgsFineParams P) {
+__global__ void __launch_bounds__(kBlock) expand1_kernel(const __grid_constant__ FgsFineParams P, bool prescanned) {
+  __shared__ int s_off[kRaysPerCta + 1], s_red[kWarps];
   const int lane = lane_id();
-  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
-    const int base = P.off1[ray];
+  const int r0 = blockIdx.x * kRaysPerCta, r1 = min(r0 + kRaysPerCta, P.n_rays);
+  cta_scan_counts(P.cnt1, P.off1, P.n_rays, r0, r1, P.counters, FGS_CNT_M1, P.cap_m1, 2, s_off, s_red, prescanned);
+  for (int ray = r0 + (threadIdx.x >> 5); ray < r1; ray += kWarps) {
+    const int base = s_off[ray - r0];
     const int c1 = P.cnt1[ray];
     if (c1 == 0) continue;
     if (base + c1 > P.cap_m1) {           // over capacity (flagged by the scan): mark the slots that exist
@@ -287,13 +336,16 @@ __global__ void __launch_bounds__(kBlock) weights1_kernel(const __grid_constant_
   if (lane == 0 && tot_a) atomicAdd(P.counters + FGS_CNT_MA, tot_a);
 }
 
-__global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant__ FgsFineParams P) {
+__global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant__ FgsFineParams P, bool prescanned) {
+  __shared__ int s_off[kRaysPerCta + 1], s_red[kWarps];
   const int lane = lane_id();
-  for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
+  const int r0 = blockIdx.x * kRaysPerCta, r1 = min(r0 + kRaysPerCta, P.n_rays);
+  cta_scan_counts(P.cnt2, P.off2, P.n_rays, r0, r1, P.counters, FGS_CNT_M2, P.cap_m2, 4, s_off, s_red, prescanned);
+  for (int ray = r0 + (threadIdx.x >> 5); ray < r1; ray += kWarps) {
     const int c2 = P.cnt2[ray];
     if (c2 == 0) continue;
     const int base1 = P.off1[ray], c1 = P.cnt1[ray];
-    int dst = P.off2[ray];
+    int dst = s_off[ray - r0];
     // a ray that does not fit (flagged by the scan: the step's results are void) still fills the slots that exist, so
     // that every row below min(M2, cap_m2) names a real sample and nothing downstream indexes with stale memory
     if (dst >= P.cap_m2) continue;
@@ -325,9 +377,15 @@ int launch_march(const FgsFineParams& P, cudaStream_t st) {
   const int grid = fgs::stream_grid(P.n_rays, kWarps, 8);
   march_kernel<<<grid, kBlock, 0, st>>>(P);
   if ((rc = fgs::check_launch("fine march", st))) return rc;
-  scan_kernel<<<1, 1024, 0, st>>>(P.cnt1, P.off1, P.n_rays, P.counters, FGS_CNT_M1, P.cap_m1, 2);
-  if ((rc = fgs::check_launch("fine scan1", st))) return rc;
-  expand1_kernel<<<grid, kBlock, 0, st>>>(P);
+  const int grid_r = fgs::cdiv(P.n_rays, kRaysPerCta);          // scan fused: a CTA owns kRaysPerCta consecutive rays
+  // (every CTA re-reads the counts in front of it: O(n^2 / 64) loads, fine up to the usual 8192-ray batches; beyond
+  // 32 K rays the single-CTA scan runs first)
+  const bool prescan = P.n_rays > 32768;
+  if (prescan) {
+    scan_kernel<<<1, 1024, 0, st>>>(P.cnt1, P.off1, P.n_rays, P.counters, FGS_CNT_M1, P.cap_m1, 2);
+    if ((rc = fgs::check_launch("fine scan1", st))) return rc;
+  }
+  expand1_kernel<<<grid_r, kBlock, 0, st>>>(P, prescan);
   if ((rc = fgs::check_launch("fine expand1", st))) return rc;
   // the sample count lives on the device: size the grid for the capacity, capped at a few waves (grid-stride loop)
   const int grid_s = fgs::stream_grid(P.cap_m1, kBlock, 8);
@@ -335,9 +393,11 @@ int launch_march(const FgsFineParams& P, cudaStream_t st) {
   if ((rc = fgs::check_launch("fine level1", st))) return rc;
   weights1_kernel<<<grid, kBlock, 0, st>>>(P);
   if ((rc = fgs::check_launch("fine weights1", st))) return rc;
-  scan_kernel<<<1, 1024, 0, st>>>(P.cnt2, P.off2, P.n_rays, P.counters, FGS_CNT_M2, P.cap_m2, 4);
-  if ((rc = fgs::check_launch("fine scan2", st))) return rc;
-  compact2_kernel<<<grid, kBlock, 0, st>>>(P);
+  if (prescan) {
+    scan_kernel<<<1, 1024, 0, st>>>(P.cnt2, P.off2, P.n_rays, P.counters, FGS_CNT_M2, P.cap_m2, 4);
+    if ((rc = fgs::check_launch("fine scan2", st))) return rc;
+  }
+  compact2_kernel<<<grid_r, kBlock, 0, st>>>(P, prescan);
   return fgs::check_launch("fine compact2", st);
 }
 

@@ -55,7 +55,7 @@ extern "C" int fgs_fine_train_step(const FgsFineParams* p, const FgsFineLoss* l,
     }
   }
   if ((rc = fgs_fine_backward_phase(&P, l, 2, stream))) return rc;
-  if (s->n_mlp > 0 && (rc = fgs_adam_upd_multi(s->n_mlp, s->mlp_p, s->mlp_g, s->mlp_m, s->mlp_v, s->mlp_n, s->mlp_steps,
+  if (s->n_mlp > 0 && (rc = fgs_adam_upd_multi_zero_grad(s->n_mlp, s->mlp_p, s->mlp_g, s->mlp_m, s->mlp_v, s->mlp_n, s->mlp_steps,
                                                s->mlp_lrs, s->beta1, s->beta2, s->eps, stream)))
     return rc;
   return 0;

@@ -195,6 +195,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Consumer side of the accumulation: chunk c (one 32-k slab = 12 MMAs) has been committed into TMEM region
@@ -375,11 +383,11 @@ __device__ __forceinline__ void mma_slab(uint32_t d, uint32_t stage_base, uint32
 }
 
 // Epilogue arithmetic on one 32-column block of a consumer thread's row, in place.
-template <bool RELU, bool MASK>
+template <bool RELU, bool MASK, int NV = 32>
 __device__ __forceinline__ uint32_t epilogue_block(float* v, uint32_t bias_addr, bool has_bias, uint32_t in_bits) {
   uint32_t out_bits = 0;
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
+  for (int j4 = 0; j4 < NV / 4; ++j4) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_bias) b = lds4(bias_addr + 16 * j4);           // same address in every lane: a broadcast
     float x[4] = {v[4 * j4] + b.x, v[4 * j4 + 1] + b.y, v[4 * j4 + 2] + b.z, v[4 * j4 + 3] + b.w};
@@ -636,6 +644,7 @@ struct ChainArgs {
   const int* rows_dev;
   long long* dbg;
   int n_steps, M;
+  int row_off;     // this launch covers rows [row_off, row_off + M) of the problem (device-side count: *rows_dev - row_off)
 };
 struct ChainMaps {
   CUtensorMap hi[kChainMaxSteps], lo[kChainMaxSteps], c[kChainMaxSteps];
@@ -741,7 +750,8 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
   constexpr int SK = BF ? 2 * BK : BK;                         // k per slab (one 128-byte swizzle row per operand row)
 
   int M = a.M;
-  if (a.rows_dev) M = min(M, *a.rows_dev);
+  if (a.rows_dev) M = min(M, *a.rows_dev - a.row_off);
+  if (M <= 0) return;
   const int n_pair_tiles = (M + 2 * BM - 1) / (2 * BM);        // 256-row tiles
   const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
   if (pair >= n_pair_tiles) return;                            // both CTAs of the pair leave together
@@ -1009,59 +1019,86 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
       mbar_wait_relaxed(B.rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbg_on) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
-#pragma unroll 1
-      for (int q = 0; q < TNF / 2 / 32; ++q) {
-        const int c0 = col_half + 32 * q;
-        if (c0 < BN) {
-          float v[32];
-          if (dbg_on) tq = clock64();
-          {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(tmem_row + rg * TNF + 32 * q, r0);
-            tmem_ld16(tmem_row + rg * TNF + 32 * q + 16, r1);
-            tmem_ld_wait();
+      // The 4 column blocks of this warp, in halves of 16 columns: the TMEM load of half h + 1 is in flight while
+      // half h goes through the arithmetic and into the staging tile (tcgen05.ld needs several hundred cycles while the
+      // tensor core accumulates into the other region; issued and awaited block by block that latency was exposed four
+      // times per item), and the region goes back to the issuer as soon as the LAST load has landed, not after the
+      // last store.  (Two whole 32-column blocks in flight do not fit the 96-register budget: 2 KB of spills.)
+      const int nblk = max(0, min(4, (BN - col_half + 31) >> 5));
+      const bool hb = S.bias != nullptr;
+      const int relu = S.relu;
+      const bool has_mask = S.bits_in != nullptr;
+      const bool tma_out = S.c_tma && mr0 + 32 <= M;
+      auto release_region = [&]() {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {                                        // the leader may overwrite the region in BOTH CTAs
+          if (rank == 0) mbar_arrive(B.rempty0 + 8 * rg);
+          else mbar_arrive_cluster(l_rempty0 + 8 * rg);
+        }
+      };
+      // half hf (0..7) = columns col_half + 16 hf .. + 16 of the item; returns its 16 mask bits (ReLU forward)
+      auto process_half = [&](uint32_t (&r)[16], int hf, uint32_t in_bits16) -> uint32_t {
+        const int c0 = col_half + 16 * hf;
+        float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
-          }
-          if (dbg_on) { const long long t1 = clock64(); t_tm += t1 - tq; tq = t1; }
-          const int word = (n0 + c0) >> 5;
-          uint32_t in_bits = q == 0 ? mask_w[0] : q == 1 ? mask_w[1] : q == 2 ? mask_w[2] : mask_w[3], out_bits = 0;
-          const uint32_t baddr = bias_s + 4 * c0;
-          const bool hb = S.bias != nullptr;
-          if (S.relu) out_bits = epilogue_block<true, false>(v, baddr, hb, in_bits);
-          else if (S.bits_in) out_bits = epilogue_block<false, true>(v, baddr, hb, in_bits);
-          else out_bits = epilogue_block<false, false>(v, baddr, hb, in_bits);
-          if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + word] = out_bits;
-          if (dbg_on) { const long long t1 = clock64(); t_ma += t1 - tq; tq = t1; }
-          if (S.c_tma && mr0 + 32 <= M) {
-            // (TMA store: the copy engine moves the block.  A version that read the staging tile back and stored it with
-            // 128-bit st.global was SLOWER, 0.230 -> 0.266 ms for the backward chain: with 17 warps sharing four
-            // schedulers the kernel is bound by CUDA-core issue slots -- operand split + epilogue arithmetic -- as much
-            // as by the tensor core, and those stores are instructions the TMA version does not issue.)
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        uint32_t out_bits = 0;
+        const uint32_t baddr = bias_s + 4 * c0;
+        if (relu) out_bits = epilogue_block<true, false, 16>(v, baddr, hb, in_bits16);
+        else if (has_mask) out_bits = epilogue_block<false, true, 16>(v, baddr, hb, in_bits16);
+        else out_bits = epilogue_block<false, false, 16>(v, baddr, hb, in_bits16);
+        if (tma_out) {
+          if ((hf & 1) == 0) {                                  // first half of a 32-column block: the tile must be free
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
+          }
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              st_shared_v4(stg + (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) * 16)),
-                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          for (int j4 = 0; j4 < 4; ++j4)
+            st_shared_v4(stg + (uint32_t)(lane * 128 + (((4 * (hf & 1) + j4) ^ (lane & 7)) * 16)),
+                         make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+          if (hf & 1) {
+            // (TMA store: the copy engine moves the 32 x 32 block.  A version that read the staging tile back and stored
+            // it with 128-bit st.global was slower, 0.230 -> 0.266 ms for the backward chain.)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) tma_store_2d(&maps.c[step], stg, n0 + c0, mr0);
-          } else if (m < M) {
-            float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
+            if (lane == 0) tma_store_2d(&maps.c[step], stg, n0 + c0 - 16, mr0);
+          }
+        } else if (m < M) {
+          float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < N) cp[j] = v[j];
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < N) cp[j] = v[j];
+        }
+        return out_bits;
+      };
+      {
+        uint32_t ra[16], rb[16];
+        const int nhalf = 2 * nblk;
+        if (nhalf > 0) tmem_ld16(tmem_row + rg * TNF, ra);
+        else release_region();
+        uint32_t bits_lo = 0;
+#pragma unroll
+        for (int hf = 0; hf < 8; ++hf) {
+          if (hf < nhalf) {
+            tmem_ld_wait();                                     // half hf is in registers
+            if (hf + 1 < nhalf) {
+              if (hf & 1) tmem_ld16(tmem_row + rg * TNF + 16 * (hf + 1), ra);
+              else tmem_ld16(tmem_row + rg * TNF + 16 * (hf + 1), rb);
+            } else {
+              release_region();
+            }
+            const uint32_t mw = mask_w[hf >> 1] >> (16 * (hf & 1));
+            const uint32_t ob = (hf & 1) ? process_half(rb, hf, mw) : process_half(ra, hf, mw);
+            if (hf & 1) {
+              if (S.bits_out && m < M) S.bits_out[(size_t)m * 8 + ((n0 + col_half) >> 5) + (hf >> 1)] = bits_lo | (ob << 16);
+            } else {
+              bits_lo = ob;
+            }
           }
         }
       }
       if (dbg_on) { const long long t1 = clock64(); t_st += t1 - t0 - 0; tq = t1; }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {                                          // the leader may overwrite the region in BOTH CTAs
-        if (rank == 0) mbar_arrive(B.rempty0 + 8 * rg);
-        else mbar_arrive_cluster(l_rempty0 + 8 * rg);
-      }
       // the tile's rows of this step are complete in global memory -> (tile, step + 1) may load them
       __syncwarp();
       if (lane == 0) {
@@ -1535,34 +1572,45 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   int rc = bf16 ? configure_once(mlp_chain2_kernel<true>, configured2b, "mlp_chain2 (bf16) smem attribute", kSmemBytesChain2)
                 : configure_once(mlp_chain2_kernel<false>, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
   if (rc) return rc;
-  ChainArgs a;
-  ChainMaps maps;
-  memset(&a, 0, sizeof(a));
-  for (int i = 0; i < n_steps; ++i) {
-    const ChainStepHost& h = steps[i];
-    if ((h.lda & 3) || (h.ldb & (bf16 ? 7 : 3)) || (((uintptr_t)h.A | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
-      return fgs::fail_arg("mlp_chain needs 16-byte aligned operands and rows");
-    if (h.K > h.ldb) return fgs::fail_arg("mlp_chain: K exceeds the weight plane's row length");
-    const int rows_alloc = (h.N + 7) & ~7;
-    if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.hi[i], bf16))) return rc;
-    if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.lo[i], bf16))) return rc;
-    const int c_tma = ((h.ldc & 3) == 0 && ((uintptr_t)h.C & 15) == 0) ? 1 : 0;
-    maps.c[i] = maps.hi[i];
-    if (c_tma && (rc = get_map(h.C, h.N, M, h.ldc, 32, &maps.c[i]))) return rc;
-    ChainStep& s = a.s[i];
-    s.A = h.A; s.C = h.C; s.bias = h.bias; s.bits_in = h.bits_in; s.bits_out = h.bits_out;
-    s.lda = h.lda; s.ldc = h.ldc; s.K = h.K; s.N = h.N; s.n0 = h.n0; s.relu = h.relu; s.c_tma = c_tma;
+  // a CTA pair walks at most kChainMaxTiles 256-row tiles (one completion barrier each): larger workspaces (the host
+  // only knows the CAPACITY; the sample count lives on the device) are covered by several launches over row ranges,
+  // of which all but the first exit at once when the device-side count is small
+  const int pairs_all = FGS_NUM_SMS / 2;
+  const int max_rows = kChainMaxTiles * pairs_all * 2 * BM;
+  for (int row_off = 0; row_off < M; row_off += max_rows) {
+    const int Mc = M - row_off < max_rows ? M - row_off : max_rows;
+    ChainArgs a;
+    ChainMaps maps;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_steps; ++i) {
+      const ChainStepHost& h = steps[i];
+      if ((h.lda & 3) || (h.ldb & (bf16 ? 7 : 3)) || (((uintptr_t)h.A | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
+        return fgs::fail_arg("mlp_chain needs 16-byte aligned operands and rows");
+      if (h.K > h.ldb) return fgs::fail_arg("mlp_chain: K exceeds the weight plane's row length");
+      const int rows_alloc = (h.N + 7) & ~7;
+      if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.hi[i], bf16))) return rc;
+      if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.lo[i], bf16))) return rc;
+      float* Cc = h.C + (size_t)row_off * h.ldc;
+      const int c_tma = ((h.ldc & 3) == 0 && ((uintptr_t)Cc & 15) == 0) ? 1 : 0;
+      maps.c[i] = maps.hi[i];
+      if (c_tma && (rc = get_map(Cc, h.N, Mc, h.ldc, 32, &maps.c[i]))) return rc;
+      ChainStep& s = a.s[i];
+      s.A = h.A + (size_t)row_off * h.lda; s.C = Cc; s.bias = h.bias;
+      s.bits_in = h.bits_in ? h.bits_in + (size_t)row_off * 8 : nullptr;
+      s.bits_out = h.bits_out ? h.bits_out + (size_t)row_off * 8 : nullptr;
+      s.lda = h.lda; s.ldc = h.ldc; s.K = h.K; s.N = h.N; s.n0 = h.n0; s.relu = h.relu; s.c_tma = c_tma;
+    }
+    for (int i = n_steps; i < kChainMaxSteps; ++i) { maps.hi[i] = maps.hi[0]; maps.lo[i] = maps.lo[0]; maps.c[i] = maps.c[0]; }
+    a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = Mc; a.row_off = row_off;
+    // CTA pairs (static cluster size 2): the grid is a whole number of pairs
+    const int n_pair_tiles = fgs::cdiv(Mc, 2 * BM);
+    int pairs_n = pairs_all;
+    if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
+    if (bf16) mlp_chain2_kernel<true><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+    else mlp_chain2_kernel<false><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+    if ((rc = fgs::check_launch(steps[0].bias ? "mlp_chain_fwd" : "mlp_chain_bwd", st))) return rc;   // (only the forward adds biases)
   }
-  for (int i = n_steps; i < kChainMaxSteps; ++i) { maps.hi[i] = maps.hi[0]; maps.lo[i] = maps.lo[0]; maps.c[i] = maps.c[0]; }
-  a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = M;
-  // CTA pairs (static cluster size 2): the grid is a whole number of pairs
-  const int n_pair_tiles = fgs::cdiv(M, 2 * BM);
-  int pairs_n = FGS_NUM_SMS / 2;
-  if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
-  if (fgs::cdiv(n_pair_tiles, pairs_n) > kChainMaxTiles) return fgs::fail_arg("mlp_chain: more than 16 row tiles per CTA");
-  if (bf16) mlp_chain2_kernel<true><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
-  else mlp_chain2_kernel<false><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
-  return fgs::check_launch(steps[0].bias ? "mlp_chain_fwd" : "mlp_chain_bwd", st);   // (only the forward adds biases)
+  return 0;
 }
 
 // All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first

@@ -38,7 +38,7 @@ class FgsFineParams(C.Structure):
         ("mX", C.c_int32), ("mY", C.c_int32), ("mZ", C.c_int32),
         ("cap_words", C.c_int32), ("cap_m1", C.c_int32), ("cap_m2", C.c_int32),
         ("render_depth", C.c_int32), ("render_normal", C.c_int32),
-        ("skip_composite", C.c_int32), ("pad1_", C.c_int32),
+        ("skip_composite", C.c_int32), ("mlp_grads_zeroed", C.c_int32),
         ("xyz_min", C.c_float * 3), ("xyz_max", C.c_float * 3),
         ("mask_xyz_min", C.c_float * 3), ("mask_xyz_max", C.c_float * 3),
         ("near_", C.c_float), ("far_", C.c_float), ("stepdist", C.c_float), ("dist", C.c_float),
@@ -366,6 +366,7 @@ class FineStepEngine:
             if self.voxel_bits:
                 ws["k0_vox_bits"] = torch.zeros(self.world_size, X * Y * Z // 32, dtype=i32, device=dev)
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
+        self._mlp_grads_clean = True       # the MLP gradient bucket is all-zero (fresh, or cleared by the native step's Adam)
         self._brick_list_ready = False
         self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._count_evt = torch.cuda.Event()
@@ -592,6 +593,8 @@ class FineStepEngine:
         L = self._fill_loss(target, n_rays_global, has_last_ray)
         self.ws["loss"].zero_()
         self._grads_clean = False
+        self._mlp_grads_clean = False
+        self.P.mlp_grads_zeroed = 0
         with torch.cuda.device(self.device):
             st = stream()
             check(lib.fgs_fine_loss(C.byref(self.P), C.byref(L), st))
@@ -613,6 +616,8 @@ class FineStepEngine:
 
     def backward_weights(self):
         """Second phase of loss_backward(phase=1): the MLP weight / bias gradients."""
+        self._mlp_grads_clean = False
+        self.P.mlp_grads_zeroed = 0
         with torch.cuda.device(self.device):
             check(lib.fgs_fine_backward_phase(C.byref(self.P), C.byref(self.L), 2, stream()))
 
@@ -905,8 +910,10 @@ class FineStepEngine:
             lr = self.lr["rgbnet"] if i < 4 else self.lr["refnet"]
             self._S_lrs[i] = self._S_lrs[MLP_LAYERS + i] = lr
             self._S_steps[i] = self._S_steps[MLP_LAYERS + i] = self.adam_step
+        self.P.mlp_grads_zeroed = int(self._mlp_grads_clean)     # its Adam clears the MLP gradients it consumes
         with torch.cuda.device(self.device):
             check(lib.fgs_fine_train_step(C.byref(self.P), C.byref(L), C.byref(S), stream()))
+        self._mlp_grads_clean = True
         self._grads_clean = True
         self._brick_list_ready = False
 

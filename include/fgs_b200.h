@@ -144,6 +144,12 @@ int fgs_adam_upd_multi(int n_tensors, float* const* params, const float* const* 
                        float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
                        const int* steps, const float* lrs, float beta1, float beta2, float eps,
                        fgs_stream_t stream);
+/* The same, clearing every gradient element it consumes (the fused step's MLP gradients are accumulated with atomics:
+ * this replaces the memset before the next step's weight-gradient kernel). */
+int fgs_adam_upd_multi_zero_grad(int n_tensors, float* const* params, float* const* grads,
+                                 float* const* exp_avgs, float* const* exp_avg_sqs, const int64_t* numels,
+                                 const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                                 fgs_stream_t stream);
 
 /* Fused-step variants (same arithmetic, less traffic):
  *  fgs_adam_upd_zero_grad : dense adam_upd that also clears the consumed gradient (no memset pass);

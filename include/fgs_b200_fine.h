@@ -83,7 +83,8 @@ typedef struct FgsFineParams {
   int32_t cap_m1, cap_m2;       /* sample capacities; cap_m2 % 128 == 0   */
   int32_t render_depth, render_normal;
   int32_t skip_composite;       /* fgs_fine_forward stops after the MLPs (fgs_fine_loss composites) */
-  int32_t pad1_;
+  int32_t mlp_grads_zeroed;     /* the MLP gradient bucket is already all-zero (cleared by fgs_adam_upd_multi_zero_grad):
+                                   fgs_fine_backward skips its memset */
   /* ---- scalars ---- */
   float xyz_min[3], xyz_max[3], mask_xyz_min[3], mask_xyz_max[3];
   float near_, far_, stepdist, dist, voxel_size, mask_thres, fast_color_thres, inv_s, bg;
@@ -213,7 +214,7 @@ typedef struct FgsFineStep {
   int32_t* brick_list;
   int n_mlp;                /* tensors of the multi-tensor Adam (HOST arrays below, n_mlp entries each) */
   float* const* mlp_p;
-  const float* const* mlp_g;
+  float* const* mlp_g;            /* cleared by the step's Adam once consumed */
   float* const* mlp_m;
   float* const* mlp_v;
   const int64_t* mlp_n;

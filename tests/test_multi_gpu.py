@@ -26,6 +26,15 @@ CASES = {
 
 
 def _worker(rank, world, port, q, case, voxel_exchange):
+    """Never leave the parent waiting: whatever happens, one entry goes on the queue."""
+    try:
+        _worker_body(rank, world, port, q, case, voxel_exchange)
+    except BaseException as e:                      # noqa: BLE001 -- reported to the parent, which fails the test
+        import traceback
+        q.put((rank, {"error": f"{type(e).__name__}: {e}\n{traceback.format_exc()[-1500:]}"}))
+
+
+def _worker_body(rank, world, port, q, case, voxel_exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -130,9 +139,26 @@ def test_two_gpu_step_equals_single_gpu_step(case, voxel_exchange):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, case, voxel_exchange)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=900) for _ in procs)
+    res = {}
+    import queue as _queue
+    import time as _time
+    deadline = _time.time() + 600
+    while len(res) < len(procs) and _time.time() < deadline:
+        try:
+            r, o = q.get(timeout=5)
+            res[r] = o
+            if isinstance(o, dict) and "error" in o:
+                break
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):      # a worker died without reporting
+                break
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=20)
+        if p.is_alive():
+            p.terminate()
+    errs = {r: o["error"] for r, o in res.items() if isinstance(o, dict) and "error" in o}
+    assert not errs, errs
+    assert len(res) == len(procs), f"workers did not report: got {sorted(res)}; exit codes {[p.exitcode for p in procs]}"
     out = res[0]
     print(f"[{case}, voxel_exchange={voxel_exchange}] M2 (rank 0 shard, full batch): {out['M2']}")
     print("  gradient errors after the exchange (relative L2, max norm):")
