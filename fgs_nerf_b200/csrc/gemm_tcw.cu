@@ -1201,13 +1201,33 @@ __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t addr) {
 
 // BF = false: TF32 hi / lo tiles, 32-sample slabs (kept for the stand-alone fp32-grade entry fgs_gemm_tn).
 // BF = true: bf16 hi / mid tiles, 64-sample slabs in the same bytes, kind::f16: the weight gradients of the fused step.
+// bf16 variant: the fp32 operands reach the SM through a per-warp TMA ring.  With register double-buffering the loads
+// in flight were bounded by the producers' registers (48 KB per SM): at ~3400 cycles of loaded memory latency that is
+// 14 B / cycle / SM = 4 TB/s, and the issuer waited for operands 60 % of the time.  Each producer warp now owns a ring
+// of kRawSlots units (4 sample rows x [128 dZ features | 64 X features] fp32 = 3 KB) filled by two bulk-tensor loads
+// that its lane 0 issues four units ahead, completion on the warp's own mbarriers: 96 KB in flight per SM, no
+// registers, no cross-warp synchronisation.  The operand tiles keep two stages (conversion is fast against memory).
+struct DwMaps {
+  CUtensorMap a[kDwMaxProblems], b[kDwMaxProblems];     // [rows = samples][features] fp32, boxes (128, 4) and (64, 4)
+};
+constexpr int kRawSlots = 4;
+constexpr uint32_t kRawA = 4 * 128 * 4, kRawB = 4 * 64 * 4, kRawUnit = kRawA + kRawB;          // 2 KB + 1 KB
+constexpr int kStagesD2B = 2;
+constexpr uint32_t kRawOff = kStagesD2B * kStageD2;                                             // 96 KB
+static_assert(kRawOff + 8 * kRawSlots * kRawUnit <= kStagingOff, "raw ring overlaps the epilogue staging");
+constexpr uint32_t kRawBarOff = kBarD2Off + 8 * (2 * kStagesD2 + 2 * kRegions);                 // 8 warps x kRawSlots barriers
+constexpr uint32_t kSmemBytesDw2B = kRawBarOff + 8 * 8 * kRawSlots;
+static_assert(kSmemBytesDw2B <= 232448, "shared memory budget");
+
 template <bool BF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_dw2_kernel(const __grid_constant__ Dw2Args a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1)
+mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps maps) {
+  constexpr int NST = BF ? kStagesD2B : kStagesD2;              // operand-tile stages
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
   Bars B;                                                       // free[4], afull[4], rfull[4], rempty[4]
   B.free0 = smem + kBarD2Off;
-  B.afull0 = B.free0 + 8 * kStagesD2;
+  B.afull0 = B.free0 + 8 * kStagesD2;          // (barrier block laid out for the larger stage count)
   B.rfull0 = B.afull0 + 8 * kStagesD2;
   B.rempty0 = B.rfull0 + 8 * kRegions;
   B.bfull0 = 0;
@@ -1233,10 +1253,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kTmemSlotOff);
   if (tid == 0) {
-    for (int i = 0; i < kStagesD2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(B.free0 + 8 * i, 1);
       mbar_init(B.afull0 + 8 * i, kProducersTn / 32 + (rank == 0 ? 1 : 0));   // own producer warps (+ the follower's relay)
     }
+    if (BF)
+      for (int i = 0; i < 8 * kRawSlots; ++i) mbar_init(smem + kRawBarOff + 8 * i, 1);   // one expect_tx arrival each
     for (int i = 0; i < kRegions; ++i) {
       mbar_init(B.rfull0 + 8 * i, 1);
       mbar_init(B.rempty0 + 8 * i, 2 * (kConsumers / 32));     // consumer warps of both CTAs
@@ -1262,8 +1284,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
       // follower: forward "my operand tiles of slab g are in place" to the leader (see mlp_chain2_kernel)
       const uint32_t total = (uint32_t)(u_end - u_beg);
       for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t st = g % kStagesD2;
-        mbar_wait(B.afull0 + 8 * st, (g / kStagesD2) & 1);
+        const uint32_t st = g % NST;
+        mbar_wait(B.afull0 + 8 * st, (g / NST) & 1);
         mbar_arrive_cluster(l_afull0 + 8 * st);
       }
     }
@@ -1278,9 +1300,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
         const int BN = min(TN, (P.N - a.tile_n[tile] * TN + 15) & ~15);
         const uint32_t idesc = make_idesc(BF, BN, 2 * BM, true);                            // M = 256, MN-major
         for (int i = 0; i < len; ++i, ++g) {
-          const uint32_t st = g % kStagesD2;
+          const uint32_t st = g % NST;
           if (dbg_cta) t0 = clock64();
-          mbar_wait_cluster(B.afull0 + 8 * st, (g / kStagesD2) & 1);
+          mbar_wait_cluster(B.afull0 + 8 * st, (g / NST) & 1);
           if (dbg_cta) { const long long t1 = clock64(); t_a += t1 - t0; t0 = t1; }
           if (g >= (uint32_t)kRegions) mbar_wait_cluster(B.rempty0 + 8 * (g % kRegions), ((g / kRegions) - 1) & 1);
           if (dbg_cta) t_r += clock64() - t0;
@@ -1322,6 +1344,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
     const uint32_t b_blk = BF ? (uint32_t)(bq & 1) * 8u : (uint32_t)(bq >> 3) * 4096u + (uint32_t)(bq & 1) * 16u;
     const uint32_t b_c32 = BF ? (uint32_t)(bq >> 1) : (uint32_t)((bq & 7) >> 1);
     uint32_t g = 0;
+    if constexpr (BF) {
+      // ---- per-warp TMA ring of raw fp32 rows -> bf16 hi / mid operand tiles ----
+      struct Cur { int u, tile, s, h; };                       // unit = half slab h of slab s of `tile`
+      auto advance = [&](Cur& c) {
+        if (c.h == 0) { c.h = 1; return; }
+        c.h = 0;
+        ++c.u; ++c.s;
+        if (c.s == n_slabs) { c.s = 0; ++c.tile; }
+      };
+      const uint32_t raw0 = smem + kRawOff + (uint32_t)pw * (kRawSlots * kRawUnit);
+      const uint32_t rbar0 = smem + kRawBarOff + (uint32_t)pw * (8 * kRawSlots);
+      auto issue = [&](const Cur& c, uint32_t n) {              // lane 0: two bulk-tensor loads of unit n into slot n % 4
+        if (c.u >= u_end) return;
+        const int prob = a.tile_prob[c.tile];
+        const DwProblem& P = a.p[prob];
+        const int n0 = a.tile_n[c.tile] * TN;
+        const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
+        const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
+        const uint32_t slot = n % kRawSlots, dst = raw0 + slot * kRawUnit, bar = rbar0 + 8 * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kRawUnit) : "memory");
+        tma_load_2d(dst, &maps.a[prob], bar, (int)rank * BM, k0);
+        tma_load_2d(dst + kRawA, &maps.b[prob], bar, n0 + (int)rank * h, k0);
+      };
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto flush_colsum = [&](int tile) {
+        const DwProblem& P = a.p[a.tile_prob[tile]];
+        if (P.colsum && a.tile_n[tile] == 0) {
+          const int f = (int)rank * BM + 4 * lane;
+          if (f < P.M && cs.x != 0.f) atomicAdd(P.colsum + f, cs.x);
+          if (f + 1 < P.M && cs.y != 0.f) atomicAdd(P.colsum + f + 1, cs.y);
+          if (f + 2 < P.M && cs.z != 0.f) atomicAdd(P.colsum + f + 2, cs.z);
+          if (f + 3 < P.M && cs.w != 0.f) atomicAdd(P.colsum + f + 3, cs.w);
+        }
+        cs = make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs, 0}, pf = c;
+      uint32_t n_iss = 0;
+      if (lane == 0)
+        for (; n_iss < (uint32_t)kRawSlots; ++n_iss) { issue(pf, n_iss); advance(pf); }
+      for (uint32_t n = 0; c.u < u_end; ++n) {
+        const DwProblem& P = a.p[a.tile_prob[c.tile]];
+        const int n0 = a.tile_n[c.tile] * TN;
+        const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
+        const bool in_a = (int)rank * BM + 4 * lane < P.M, in_b = 4 * bq < h && n0 + (int)rank * h + 4 * bq < P.N;
+        const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
+        const uint32_t slot = n % kRawSlots, src = raw0 + slot * kRawUnit;
+        mbar_wait_relaxed(rbar0 + 8 * slot, (n / kRawSlots) & 1);
+        float4 va[4], vb[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = lds4(src + (uint32_t)(i * 512 + lane * 16));
+          va[i] = (k0 + i < K && in_a) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = 2 * i + bsub;
+          const float4 y = lds4(src + kRawA + (uint32_t)(r * 256 + bq * 16));
+          vb[i] = (k0 + r < K && in_b) ? y : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();                                           // every lane has read the slot: it may be refilled
+        if (lane == 0) { issue(pf, n + kRawSlots); advance(pf); }
+        const uint32_t st = g % NST;
+        const uint32_t stage_base = smem + st * kStageD2;
+        if (c.h == 0 && g >= (uint32_t)NST) mbar_wait_relaxed(B.free0 + 8 * st, ((g / NST) - 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
+          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + i);
+          const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 7u)) * 16u);
+          split_store_bf4(stage_base + off, stage_base + kATile + off, va[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + 2 * i + bsub);
+          const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 7u)) * 16u);
+          split_store_bf4(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
+        }
+        if (c.h == 1) {
+          if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(B.afull0 + 8 * st);       // own CTA's barrier (the follower's is relayed)
+          ++g;
+        }
+        advance(c);
+      }
+    } else {
     // cursor over the CTA's units; bf16 walks HALF slabs (h = 0, 1 inside slab s of `tile`)
     struct Cur { int u, tile, s, h; };
     auto advance = [&](Cur& c) {
@@ -1365,10 +1474,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
       cs = make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto produce = [&](float4 (&va)[4], float4 (&vb)[2], const Cur& c, Cur& pf) {
-      const uint32_t st = g % kStagesD2;
+      const uint32_t st = g % NST;
       const uint32_t stage_base = smem + st * kStageD2;
       const bool first = !BF || c.h == 0, last = !BF || c.h == 1;      // of this slab's units
-      if (first && g >= (uint32_t)kStagesD2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStagesD2) - 1) & 1);
+      if (first && g >= (uint32_t)NST) mbar_wait_relaxed(B.free0 + 8 * st, ((g / NST) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
@@ -1411,6 +1520,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTn, 1) mlp_d
     while (c.u < u_end) {
       produce(va0, vb0, c, pf); advance(c);
       if (c.u < u_end) { produce(va1, vb1, c, pf); advance(c); }
+    }
     }
   } else {
     // ================= consumers: this CTA's 128 out-features x BN =================
@@ -1490,8 +1600,10 @@ std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> g_maps;
 // 2-D map of a row-major fp32 matrix: `cols` valid columns (dim 0), `rows` rows of pitch ld floats; box =
 // (32 floats, box_rows rows), SWIZZLE_128B.  Out-of-range box elements read as zero / are not written.
 // bf16: the plane holds 2-byte elements (cols / ld in elements), box = (64 elements, box_rows rows): the same 128 bytes.
-int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out, bool bf16 = false) {
-  auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows, (int)bf16);
+// raw_box_cols > 0: a plain (unswizzled) fp32 box of raw_box_cols x box_rows (the raw operand ring of the weight-gradient kernel).
+int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out, bool bf16 = false,
+            int raw_box_cols = 0) {
+  auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows, (int)bf16 + 2 * raw_box_cols);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -1507,18 +1619,18 @@ int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtenso
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};              // bytes, dim 1
-  const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BK : BK), (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)(raw_box_cols > 0 ? raw_box_cols : (bf16 ? 2 * BK : BK)), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
   CUresult r = g_encode(&tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, raw_box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) cols %d rows %d ld %d",
              (int)r, cols, rows, ld);
     return FGS_E_BADARG;
   }
-  if (g_maps.size() > 4096) g_maps.clear();   // the fused step uses ~50 distinct maps; tests may churn through more
+  if (g_maps.size() > 4096) g_maps.clear();   // the fused step uses ~70 distinct maps; tests may churn through more
   g_maps[key] = tm;
   *out = tm;
   return 0;
@@ -1642,9 +1754,25 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   if (nt2 == 0) return 0;
   b.n_tiles = nt2; b.K = K; b.rows_dev = rows_dev; b.dbg = g_dbg_dw;
   static bool configured2 = false, configured2b = false;
-  int rc2 = bf16 ? configure_once(mlp_dw2_kernel<true>, configured2b, "mlp_dw2 (bf16) smem attribute", kSmemBytesDw2)
+  int rc2 = bf16 ? configure_once(mlp_dw2_kernel<true>, configured2b, "mlp_dw2 (bf16) smem attribute", kSmemBytesDw2B)
                  : configure_once(mlp_dw2_kernel<false>, configured2, "mlp_dw2 smem attribute", kSmemBytesDw2);
   if (rc2) return rc2;
+  DwMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (bf16) {
+    // raw operand boxes of the per-warp TMA rings: 4 sample rows x 128 out-features of dZ / x 64 input features of X;
+    // columns beyond the matrix and rows beyond the allocation read as zero
+    int first = -1;
+    for (int i = 0; i < n; ++i) {
+      const DwProblemHost& h = probs[i];
+      if (h.M <= 0 || h.N <= 0) continue;
+      if ((rc2 = get_map(h.A, h.lda, K, h.lda, 4, &maps.a[i], false, 128))) return rc2;
+      if ((rc2 = get_map(h.B, h.ldb, K, h.ldb, 4, &maps.b[i], false, 64))) return rc2;
+      if (first < 0) first = i;
+    }
+    for (int i = 0; i < kDwMaxProblems; ++i)
+      if (i >= n || probs[i].M <= 0 || probs[i].N <= 0) { maps.a[i] = maps.a[first]; maps.b[i] = maps.b[first]; }
+  }
   // every pair should own at least ~8 slabs, else the epilogues dominate
   const long long units2 = (long long)nt2 * fgs::cdiv(K, bf16 ? 2 * BK : BK);
   int pairs_n = (FGS_NUM_SMS - g_dw_sm_reserve) / 2;
@@ -1672,8 +1800,8 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
     pairs_n = np;
     b.aligned = 1;
   }
-  if (bf16) mlp_dw2_kernel<true><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
-  else mlp_dw2_kernel<false><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b);
+  if (bf16) mlp_dw2_kernel<true><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2B, st>>>(b, maps);
+  else mlp_dw2_kernel<false><<<2 * pairs_n, kThreadsTn, kSmemBytesDw2, st>>>(b, maps);
   return fgs::check_launch("mlp_dw", st);
 }
 
