@@ -110,6 +110,24 @@ int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t str
   if (rc) return rc;
   FGS_REQUIRE(l && l->target && l->g_alphainv_last && l->loss_out, "loss descriptor incomplete");
   FGS_REQUIRE(l->n_rays_global >= p->n_rays, "n_rays_global < n_rays");
+  // The MLP gradient bucket is accumulated into from here on (bias gradients: by the compositing kernel for the last
+  // layer, by the backward chain's epilogues for the others; weights: by the stream-K weight-gradient kernel), so it
+  // is cleared HERE unless the caller says the previous step's Adam already did (mlp_grads_zeroed).
+  if (!p->mlp_grads_zeroed) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->g_mlp_flat && p->g_mlp_floats > 0) {
+      rc = fgs::check_cuda(cudaMemsetAsync(p->g_mlp_flat, 0, sizeof(float) * (size_t)p->g_mlp_floats, st), "g_mlp memset");
+      if (rc) return rc;
+    } else {
+      const int in_dim[8] = {FGS_X0_LD, W, W, W, FGS_XR_LD, W, W, W};
+      const int out_dim[8] = {W, W, W, W, W, W, W, 3};
+      for (int i = 0; i < 8; ++i) {
+        if ((rc = fgs::check_cuda(cudaMemsetAsync(p->gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
+        if ((rc = fgs::check_cuda(cudaMemsetAsync(p->gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
+      }
+    }
+    fgs::prof_mark("memset", st);
+  }
   return launch_composite(*p, l, (cudaStream_t)stream);
 }
 
@@ -131,46 +149,54 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
   const int out_dim[8] = {W, W, W, W, W, W, W, 3};
   {
     const WSplitLayout L = wsplit_layout();
-    auto dz = [&](int i) { return P.dZ + (size_t)i * P.cap_m2 * W; };   // dZ6, dZ5, dZ4, dZ2, dZ1, dZ0
+    FGS_REQUIRE(P.dXRp && P.dlogit_p, "dXRp / dlogit_p workspaces are NULL");
+    // gradient planes: layer slot i of dZ = [hi plane | mid plane], each [cap_m2][256] bf16 (dZ6, dZ5, dZ4, dZ2, dZ1, dZ0)
+    const size_t plane = (size_t)P.cap_m2 * W;                    // elements per plane
+    auto zhi = [&](int i) { return reinterpret_cast<uint16_t*>(P.dZ + (size_t)i * P.cap_m2 * W); };
+    auto zmid = [&](int i) { return zhi(i) + plane; };
+    uint16_t* xr_hi = P.dXRp; uint16_t* xr_mid = P.dXRp + plane;
+    uint16_t* lg_hi = P.dlogit_p; uint16_t* lg_mid = P.dlogit_p + (size_t)P.cap_m2 * 8;
     if (phase != 2) {
-      // ---- data path: backward-data chain in one launch, dZ_l = (dZ_{l+1} W_{l+1}) masked by relu'(H_l),
-      // then the scatters into the grids.  The weight gradients (phase 2) only read what this phase wrote, so a
-      // data-parallel caller can exchange the grid gradients while they run. ----
-      const ChainStepHost steps[9] = {
-          bwd_step(P, L, 7, P.dlogit, 4, 3, dz(0), W, W, 0, 5),
-          bwd_step(P, L, 6, dz(0), W, W, dz(1), W, W, 0, 4),
-          bwd_step(P, L, 5, dz(1), W, W, dz(2), W, W, 0, 3),
-          bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 0, -1),      // dXR[:, 0:256] = dZ3 (linear layer)
-          bwd_step(P, L, 4, dz(2), W, W, P.dXR, FGS_XR_LD, FGS_XR_LD, 256, -1),    // dXR[:, 256:320] -> feat_bwd
-          bwd_step(P, L, 3, P.dXR, FGS_XR_LD, W, dz(3), W, W, 0, 2),
-          bwd_step(P, L, 2, dz(3), W, W, dz(4), W, W, 0, 1),
-          bwd_step(P, L, 1, dz(4), W, W, dz(5), W, W, 0, 0),
-          bwd_step(P, L, 0, dz(5), W, W, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1)};
-      if ((rc = mlp_chain(steps, 9, cap, m2, st, true))) return rc;     // 3xBF16 (masks are the forward's)
+      // ---- data path: backward-data chain in one launch on bf16 planes, dZ_l = (dZ_{l+1} W_{l+1}) masked by relu'(H_l);
+      // the epilogue of the step that produces dZ_l also sums its columns (= the bias gradient of layer l).  Then the
+      // scatters into the grids.  The weight gradients (phase 2) only read what this phase wrote, so a data-parallel
+      // caller can exchange the grid gradients while they run. ----
+      auto step = [&](int layer, const uint16_t* ahi, const uint16_t* amid, int lda, int K, uint16_t* chi, uint16_t* cmid,
+                      float* c32, int ldc, int N, int n0, int hid, float* colsum) {
+        BwStepHost s{};
+        s.Ahi = ahi; s.Amid = amid; s.lda = lda; s.K = K;
+        s.Bh = P.w_split + L.thi[layer]; s.Bl = P.w_split + L.tlo[layer]; s.ldb = L.ldt[layer];
+        s.C = c32; s.ldc = ldc; s.Chi = chi; s.Cmid = cmid; s.out_planes = chi != nullptr;
+        s.N = N; s.n0 = n0; s.bits_in = hid >= 0 ? hbits(P, hid) : nullptr; s.colsum = colsum;
+        return s;
+      };
+      const BwStepHost steps[9] = {
+          step(7, lg_hi, lg_mid, 8, 3, zhi(0), zmid(0), nullptr, 0, W, 0, 5, P.gB[6]),
+          step(6, zhi(0), zmid(0), W, W, zhi(1), zmid(1), nullptr, 0, W, 0, 4, P.gB[5]),
+          step(5, zhi(1), zmid(1), W, W, zhi(2), zmid(2), nullptr, 0, W, 0, 3, P.gB[4]),
+          step(4, zhi(2), zmid(2), W, W, xr_hi, xr_mid, nullptr, 0, W, 0, -1, P.gB[3]),          // dXR[:, 0:256] = dZ3 (linear layer)
+          step(4, zhi(2), zmid(2), W, W, nullptr, nullptr, P.dXR, FGS_XR_LD, FGS_XR_LD, 256, -1, nullptr),   // dXR[:, 256:320] -> feat_bwd
+          step(3, xr_hi, xr_mid, W, W, zhi(3), zmid(3), nullptr, 0, W, 0, 2, P.gB[2]),
+          step(2, zhi(3), zmid(3), W, W, zhi(4), zmid(4), nullptr, 0, W, 0, 1, P.gB[1]),
+          step(1, zhi(4), zmid(4), W, W, zhi(5), zmid(5), nullptr, 0, W, 0, 0, P.gB[0]),
+          step(0, zhi(5), zmid(5), W, W, nullptr, nullptr, P.dX0, FGS_X0_LD, FGS_X0_LD, 0, -1, nullptr)};
+      if ((rc = mlp_bwd_planes(steps, 9, cap, m2, st))) return rc;
       if ((rc = launch_feat_bwd(P, l->weight_orientation, st))) return rc;
       if ((rc = launch_level1_bwd(P, l->g_alphainv_last, st))) return rc;
     }
     if (phase != 1) {
-      // ---- weight / bias gradients: dW_l = dZ_l^T X_l, all layers in one launch ----
-      if (P.mlp_grads_zeroed) {
-        // cleared by the previous step's fgs_adam_upd_multi_zero_grad
-      } else if (P.g_mlp_flat && P.g_mlp_floats > 0) {
-        // all 16 MLP gradient tensors are views of one buffer: one clear instead of 16
-        if ((rc = fgs::check_cuda(cudaMemsetAsync(P.g_mlp_flat, 0, sizeof(float) * (size_t)P.g_mlp_floats, st), "g_mlp memset"))) return rc;
-      } else {
-        for (int i = 0; i < 8; ++i) {
-          if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gW[i], 0, sizeof(float) * (size_t)in_dim[i] * out_dim[i], st), "gW memset"))) return rc;
-          if ((rc = fgs::check_cuda(cudaMemsetAsync(P.gB[i], 0, sizeof(float) * (size_t)out_dim[i], st), "gB memset"))) return rc;
-        }
-      }
-      fgs::prof_mark("memset", st);
-      const float* dzl[8] = {dz(5), dz(4), dz(3), P.dXR, dz(2), dz(1), dz(0), P.dlogit};
-      const int dz_ld[8] = {W, W, W, FGS_XR_LD, W, W, W, 4};
+      // ---- weight gradients: dW_l = dZ_l^T X_l, all layers in one launch (3xBF16; dZ_l read as planes).  The bias
+      // gradients were accumulated by fgs_fine_loss (layer 7) and by the chain above; the bucket was cleared before. ----
+      const uint16_t* ahi[8] = {zhi(5), zhi(4), zhi(3), xr_hi, zhi(2), zhi(1), zhi(0), lg_hi};
+      const uint16_t* amid[8] = {zmid(5), zmid(4), zmid(3), xr_mid, zmid(2), zmid(1), zmid(0), lg_mid};
+      const int ldp[8] = {W, W, W, W, W, W, W, 8};
       const float* xin[8] = {P.X0, hidden(P, 0), hidden(P, 1), hidden(P, 2), P.XR, hidden(P, 3), hidden(P, 4), hidden(P, 5)};
       DwProblemHost dw[8];
-      for (int i = 0; i < 8; ++i)
-        dw[i] = DwProblemHost{dzl[i], xin[i], P.gW[i], P.gB[i], out_dim[i], in_dim[i], dz_ld[i], in_dim[i], in_dim[i]};
-      if ((rc = mlp_dw(dw, 8, cap, m2, st, true))) return rc;          // 3xBF16
+      for (int i = 0; i < 8; ++i) {
+        dw[i] = DwProblemHost{nullptr, xin[i], P.gW[i], nullptr, out_dim[i], in_dim[i], 0, in_dim[i], in_dim[i]};
+        dw[i].Ahi = ahi[i]; dw[i].Amid = amid[i]; dw[i].ldp = ldp[i];
+      }
+      if ((rc = mlp_dw(dw, 8, cap, m2, st, true))) return rc;
     }
     return 0;
   }

@@ -109,6 +109,16 @@ __device__ __forceinline__ float tap_grad(float flo, float fhi, float diff, floa
   return __fdiv_rn(__fdiv_rn(__fsub_rn(fhi, flo), diff), voxel_size);
 }
 
+// x = hi + mid + O(2^-17 |x|), hi = bf16(x), mid = bf16(x - hi): the operand split of the 3xBF16 GEMMs (gemm_tcw.cu),
+// two values packed per word, element 0 in the low half.
+__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+  const uint32_t h0 = (__float_as_uint(x0) + 0x8000u) & 0xFFFF0000u, h1 = (__float_as_uint(x1) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t m0 = __float_as_uint(x0 - __uint_as_float(h0)) + 0x8000u;
+  const uint32_t m1 = __float_as_uint(x1 - __uint_as_float(h1)) + 0x8000u;
+  hi = __byte_perm(h0, h1, 0x7632);
+  mid = __byte_perm(m0, m1, 0x7632);
+}
+
 __device__ __forceinline__ int lanemask_lt() {
   int m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

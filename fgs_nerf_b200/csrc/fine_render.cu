@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kBlock)
 composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant__ FgsFineLoss L) {
   const int lane = lane_id();
   double l_mse = 0., l_srgb = 0., l_ori = 0., l_ent = 0.;
+  float gb7[3] = {0.f, 0.f, 0.f};          // bias gradient of the last MLP layer = column sums of dlogit
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
     const int b = P.off2[ray];
     int c = P.cnt2[ray];
@@ -105,6 +106,15 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
         dw += r[k] * g_r[k] + sr * g_s[k];
       }
       st4(P.dlogit + 4 * (size_t)s, make_float4(dz[0], dz[1], dz[2], 0.f));
+      if (P.dlogit_p) {
+        // the same row as bf16 hi / mid planes [cap_m2][8]: the operand format of the backward GEMMs (3xBF16)
+        uint32_t h01, m01, h2, m2;
+        bf16_split2(dz[0], dz[1], h01, m01);
+        bf16_split2(dz[2], 0.f, h2, m2);
+        reinterpret_cast<uint4*>(P.dlogit_p)[s] = make_uint4(h01, h2, 0u, 0u);
+        reinterpret_cast<uint4*>(P.dlogit_p + (size_t)P.cap_m2 * 8)[s] = make_uint4(m01, m2, 0u, 0u);
+      }
+      gb7[0] += dz[0]; gb7[1] += dz[1]; gb7[2] += dz[2];
       P.d_w1[idx1] = dw;
     }
     if (lane == 0) {
@@ -117,6 +127,13 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
         if (a >= 1e-6f && a <= 1.f - 1e-6f) g_last = L.weight_entropy_last * (logf(1.f - p) - logf(p));
       }
       L.g_alphainv_last[ray] = g_last;
+    }
+  }
+  if (LOSS && P.gB[FGS_MLP_LAYERS - 1]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float t = warp_sum(gb7[k]);
+      if (lane == 0 && t != 0.f) atomicAdd(P.gB[FGS_MLP_LAYERS - 1] + k, t);
     }
   }
   if (LOSS && lane == 0) {

@@ -1201,19 +1201,24 @@ __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t addr) {
 
 // BF = false: TF32 hi / lo tiles, 32-sample slabs (kept for the stand-alone fp32-grade entry fgs_gemm_tn).
 // BF = true: bf16 hi / mid tiles, 64-sample slabs in the same bytes, kind::f16: the weight gradients of the fused step.
-// bf16 variant: the fp32 operands reach the SM through a per-warp TMA ring.  With register double-buffering the loads
-// in flight were bounded by the producers' registers (48 KB per SM): at ~3400 cycles of loaded memory latency that is
-// 14 B / cycle / SM = 4 TB/s, and the issuer waited for operands 60 % of the time.  Each producer warp now owns a ring
-// of kRawSlots units (4 sample rows x [128 dZ features | 64 X features] fp32 = 3 KB) filled by two bulk-tensor loads
-// that its lane 0 issues four units ahead, completion on the warp's own mbarriers: 96 KB in flight per SM, no
-// registers, no cross-warp synchronisation.  The operand tiles keep two stages (conversion is fast against memory).
+// bf16 variant (the fused step): NO conversion of the dZ operand and no register staging.
+//   A (dZ_l, 2/3 of the operand elements) is read as the bf16 hi / mid planes that the backward chain's epilogue wrote:
+//     per slab and CTA four bulk-tensor loads (2 planes x 2 blocks of 64 out-features x 64 samples) land directly in
+//     the MN-major SWIZZLE_128B operand tile -- a row of the plane IS a row of the tile;
+//   B (X_l, fp32 activations of the forward) still has to be split, by the 8 producer warps, but reaches them through
+//     a per-warp TMA ring (4 sample rows x 64 features = 1 KB per unit, kRawSlots units in flight, the warp's own
+//     mbarriers, no registers, no cross-warp synchronisation).
+// History: with both operands converted from registers the issuer waited for operands 60 % of the time; a ring for both
+// (96 KB in flight instead of 48 KB) changed nothing -- the conversion (5 integer ops per element, 12 K elements per
+// slab), not the loads, was the bound (ncu: issue slots 53 % busy with 17 warps, tensor pipe 22 %).
 struct DwMaps {
-  CUtensorMap a[kDwMaxProblems], b[kDwMaxProblems];     // [rows = samples][features] fp32, boxes (128, 4) and (64, 4)
+  CUtensorMap a_hi[kDwMaxProblems], a_mid[kDwMaxProblems];   // bf16 planes [samples][features]: box (64 features, 64 samples), SWIZZLE_128B
+  CUtensorMap b[kDwMaxProblems];                             // fp32 [samples][features]: box (64 features, 4 samples), no swizzle
 };
-constexpr int kRawSlots = 4;
-constexpr uint32_t kRawA = 4 * 128 * 4, kRawB = 4 * 64 * 4, kRawUnit = kRawA + kRawB;          // 2 KB + 1 KB
-constexpr int kStagesD2B = 2;
-constexpr uint32_t kRawOff = kStagesD2B * kStageD2;                                             // 96 KB
+constexpr int kRawSlots = 6;
+constexpr uint32_t kRawUnit = 4 * 64 * 4;                                                      // 1 KB
+constexpr int kStagesD2B = 3;
+constexpr uint32_t kRawOff = kStagesD2B * kStageD2;                                             // 144 KB
 static_assert(kRawOff + 8 * kRawSlots * kRawUnit <= kStagingOff, "raw ring overlaps the epilogue staging");
 constexpr uint32_t kRawBarOff = kBarD2Off + 8 * (2 * kStagesD2 + 2 * kRegions);                 // 8 warps x kRawSlots barriers
 constexpr uint32_t kSmemBytesDw2B = kRawBarOff + 8 * 8 * kRawSlots;
@@ -1255,7 +1260,7 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       mbar_init(B.free0 + 8 * i, 1);
-      mbar_init(B.afull0 + 8 * i, kProducersTn / 32 + (rank == 0 ? 1 : 0));   // own producer warps (+ the follower's relay)
+      mbar_init(B.afull0 + 8 * i, kProducersTn / 32 + (rank == 0 ? (BF ? 2 : 1) : 0));   // own producer warps (+ the follower's relay, + the leader's expect_tx of the A planes)
     }
     if (BF)
       for (int i = 0; i < 8 * kRawSlots; ++i) mbar_init(smem + kRawBarOff + 8 * i, 1);   // one expect_tx arrival each
@@ -1280,19 +1285,41 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
   const uint32_t l_afull0 = map_to_cta(B.afull0, 0), l_rempty0 = map_to_cta(B.rempty0, 0);
 
   if (warp >= kIssuerWarpTn) {
+    // A planes (bf16 variant): both CTAs load their own 128 out-features of slab g into stage g % NST, completing on the
+    // LEADER's a_full (armed by the leader for both CTAs' 2 x 32 KB)
+    long long t_ia = 0;
+    auto issue_a = [&](uint32_t g, int u) {
+      const long long ti0 = dbg_cta ? clock64() : 0;
+      const int tile = u / n_slabs, s = u - tile * n_slabs;
+      const int prob = a.tile_prob[tile];
+      const uint32_t st = g % NST, base = smem + st * kStageD2;
+      if (g >= (uint32_t)NST) mbar_wait(B.free0 + 8 * st, ((g / NST) - 1) & 1);
+      if (rank == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(B.afull0 + 8 * st), "r"(4 * kATile) : "memory");
+      const uint32_t bar = l_afull0 + 8 * st;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        tma2_load_2d(base + blk * 8192, &maps.a_hi[prob], bar, (int)rank * BM + 64 * blk, s * 64);
+        tma2_load_2d(base + kATile + blk * 8192, &maps.a_mid[prob], bar, (int)rank * BM + 64 * blk, s * 64);
+      }
+      if (dbg_cta) t_ia += clock64() - ti0;
+    };
     if (rank != 0 && warp == kIssuerWarpTn && lane == 0) {
       // follower: forward "my operand tiles of slab g are in place" to the leader (see mlp_chain2_kernel)
       const uint32_t total = (uint32_t)(u_end - u_beg);
+      if (BF) issue_a(0, u_beg);
       for (uint32_t g = 0; g < total; ++g) {
         const uint32_t st = g % NST;
         mbar_wait(B.afull0 + 8 * st, (g / NST) & 1);
         mbar_arrive_cluster(l_afull0 + 8 * st);
+        if (BF && g + 1 < total) issue_a(g + 1, u_beg + (int)g + 1);
       }
     }
     if (rank == 0 && warp == kIssuerWarpTn && lane == 0) {
       uint32_t g = 0;
       long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
       if (dbg_cta) t_all = clock64();
+      if (BF) issue_a(0, u_beg);
       for (int u = u_beg; u < u_end;) {
         const int tile = u / n_slabs, s0 = u - tile * n_slabs;
         const int len = min(n_slabs - s0, u_end - u);
@@ -1325,10 +1352,11 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
           }
           mma2_commit(B.free0 + 8 * st);
           mma2_commit(B.rfull0 + 8 * (g % kRegions));
+          if (BF && u + i + 1 < u_end) issue_a(g + 1, u + i + 1);      // the A planes of the next slab
         }
         u += len;
       }
-      if (dbg_cta) { a.dbg[5] = t_a; a.dbg[6] = 0; a.dbg[7] = t_r; a.dbg[8] = g; a.dbg[9] = clock64() - t_all; }
+      if (dbg_cta) { a.dbg[5] = t_a; a.dbg[6] = t_ia; a.dbg[7] = t_r; a.dbg[8] = g; a.dbg[9] = clock64() - t_all; }
     }
   } else if (warp >= kConsumers / 32) {
     // ================= producers =================
@@ -1345,7 +1373,7 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
     const uint32_t b_c32 = BF ? (uint32_t)(bq >> 1) : (uint32_t)((bq & 7) >> 1);
     uint32_t g = 0;
     if constexpr (BF) {
-      // ---- per-warp TMA ring of raw fp32 rows -> bf16 hi / mid operand tiles ----
+      // ---- B only: per-warp TMA ring of raw fp32 rows of X -> bf16 hi / mid operand tile ----
       struct Cur { int u, tile, s, h; };                       // unit = half slab h of slab s of `tile`
       auto advance = [&](Cur& c) {
         if (c.h == 0) { c.h = 1; return; }
@@ -1355,66 +1383,46 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
       };
       const uint32_t raw0 = smem + kRawOff + (uint32_t)pw * (kRawSlots * kRawUnit);
       const uint32_t rbar0 = smem + kRawBarOff + (uint32_t)pw * (8 * kRawSlots);
-      auto issue = [&](const Cur& c, uint32_t n) {              // lane 0: two bulk-tensor loads of unit n into slot n % 4
+      auto issue = [&](const Cur& c, uint32_t n) {              // lane 0: one bulk-tensor load of unit n into slot n % kRawSlots
         if (c.u >= u_end) return;
         const int prob = a.tile_prob[c.tile];
         const DwProblem& P = a.p[prob];
         const int n0 = a.tile_n[c.tile] * TN;
         const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
         const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
-        const uint32_t slot = n % kRawSlots, dst = raw0 + slot * kRawUnit, bar = rbar0 + 8 * slot;
+        const uint32_t slot = n % kRawSlots, bar = rbar0 + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kRawUnit) : "memory");
-        tma_load_2d(dst, &maps.a[prob], bar, (int)rank * BM, k0);
-        tma_load_2d(dst + kRawA, &maps.b[prob], bar, n0 + (int)rank * h, k0);
-      };
-      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto flush_colsum = [&](int tile) {
-        const DwProblem& P = a.p[a.tile_prob[tile]];
-        if (P.colsum && a.tile_n[tile] == 0) {
-          const int f = (int)rank * BM + 4 * lane;
-          if (f < P.M && cs.x != 0.f) atomicAdd(P.colsum + f, cs.x);
-          if (f + 1 < P.M && cs.y != 0.f) atomicAdd(P.colsum + f + 1, cs.y);
-          if (f + 2 < P.M && cs.z != 0.f) atomicAdd(P.colsum + f + 2, cs.z);
-          if (f + 3 < P.M && cs.w != 0.f) atomicAdd(P.colsum + f + 3, cs.w);
-        }
-        cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        tma_load_2d(raw0 + slot * kRawUnit, &maps.b[prob], bar, n0 + (int)rank * h, k0);
       };
       Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs, 0}, pf = c;
-      uint32_t n_iss = 0;
       if (lane == 0)
-        for (; n_iss < (uint32_t)kRawSlots; ++n_iss) { issue(pf, n_iss); advance(pf); }
+        for (uint32_t n_iss = 0; n_iss < (uint32_t)kRawSlots; ++n_iss) { issue(pf, n_iss); advance(pf); }
+      const bool dbg_p = dbg_cta && tid == kConsumers;
+      long long tp_raw = 0, tp_free = 0, tp_work = 0, tp0 = 0;
       for (uint32_t n = 0; c.u < u_end; ++n) {
+        if (dbg_p) tp0 = clock64();
         const DwProblem& P = a.p[a.tile_prob[c.tile]];
         const int n0 = a.tile_n[c.tile] * TN;
         const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
-        const bool in_a = (int)rank * BM + 4 * lane < P.M, in_b = 4 * bq < h && n0 + (int)rank * h + 4 * bq < P.N;
+        const bool in_b = 4 * bq < h && n0 + (int)rank * h + 4 * bq < P.N;
         const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
         const uint32_t slot = n % kRawSlots, src = raw0 + slot * kRawUnit;
         mbar_wait_relaxed(rbar0 + 8 * slot, (n / kRawSlots) & 1);
-        float4 va[4], vb[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x = lds4(src + (uint32_t)(i * 512 + lane * 16));
-          va[i] = (k0 + i < K && in_a) ? x : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (dbg_p) { const long long t1 = clock64(); tp_raw += t1 - tp0; tp0 = t1; }
+        float4 vb[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = 2 * i + bsub;
-          const float4 y = lds4(src + kRawA + (uint32_t)(r * 256 + bq * 16));
-          vb[i] = (k0 + r < K && in_b) ? y : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 y = lds4(src + (uint32_t)(r * 256 + bq * 16));
+          vb[i] = (k0 + r < K && in_b) ? y : make_float4(0.f, 0.f, 0.f, 0.f);   // samples beyond the count multiply as 0
         }
         __syncwarp();                                           // every lane has read the slot: it may be refilled
         if (lane == 0) { issue(pf, n + kRawSlots); advance(pf); }
         const uint32_t st = g % NST;
         const uint32_t stage_base = smem + st * kStageD2;
+        if (dbg_p) { const long long t1 = clock64(); tp_work += t1 - tp0; tp0 = t1; }
         if (c.h == 0 && g >= (uint32_t)NST) mbar_wait_relaxed(B.free0 + 8 * st, ((g / NST) - 1) & 1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          cs.x += va[i].x; cs.y += va[i].y; cs.z += va[i].z; cs.w += va[i].w;
-          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + i);
-          const uint32_t off = a_blk + r * 128u + ((a_c32 ^ (r & 7u)) * 16u);
-          split_store_bf4(stage_base + off, stage_base + kATile + off, va[i]);
-        }
+        if (dbg_p) { const long long t1 = clock64(); tp_free += t1 - tp0; tp0 = t1; }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + 2 * i + bsub);
@@ -1422,14 +1430,15 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
           split_store_bf4(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
         }
         if (c.h == 1) {
-          if (c.s == n_slabs - 1 || c.u == u_end - 1) flush_colsum(c.tile);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(B.afull0 + 8 * st);       // own CTA's barrier (the follower's is relayed)
           ++g;
         }
         advance(c);
+        if (dbg_p) tp_work += clock64() - tp0;
       }
+      if (dbg_p) { a.dbg[2] = tp_raw; a.dbg[3] = tp_free; a.dbg[4] = tp_work; }
     } else {
     // cursor over the CTA's units; bf16 walks HALF slabs (h = 0, 1 inside slab s of `tile`)
     struct Cur { int u, tile, s, h; };
@@ -1573,6 +1582,401 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
   }
 }
 
+// ---- backward-data chain on bf16 PLANES: no operand producers at all ---------------------------------------------
+// Measured on the 3xBF16 chain above (tools/chain_phase_probe.py, ncu): once the tensor core needs half the time, the
+// kernel is bound by the CUDA cores -- the producers split every activation into hi / mid again (5 integer ops per
+// element) right after the epilogue of the previous step wrote it as fp32, the weight-gradient kernel splits the same
+// dZ a second time, and 8 epilogue warps cannot keep up with 12 MMAs per 64 k (issuer waiting for a free accumulator
+// 30-40 % of the time).  Here every gradient tensor that feeds another GEMM lives in HBM / L2 as two bf16 planes
+// ([rows][256] hi, then mid: the same 4 bytes per element as fp32), written ONCE by the epilogue that computes it and
+// read by TMA straight into the operand tiles of the next step and of the weight-gradient kernel:
+//   * no producer warps: one thread per CTA issues four bulk-tensor loads per 64-k slab (its 128 rows of A hi / mid
+//     and its half of the weight rows hi / mid), all completing on the leader's barrier;
+//   * 16 epilogue warps (4 per TMEM lane quarter, 64 columns each) instead of 8: TMEM -> mask -> column sums (the
+//     bias gradient, which the weight-gradient kernel can no longer take from fp32 operands) -> hi / mid split ->
+//     swizzled staging tile -> one TMA store per plane and 32-column block;
+//   * the steps whose output leaves the GEMMs (dX0, the reflection part of dXR -> feat_bwd_kernel) store fp32.
+constexpr int kBwConsumers = 512;
+constexpr int kBwIssuerWarp = kBwConsumers / 32;
+constexpr int kBwThreads = kBwConsumers + 32;
+constexpr int kBwStages = 2;
+constexpr uint32_t kBwPlane = 128 * 128;                          // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t kBwStage = 4 * kBwPlane;                       // A_hi, A_mid, B_hi, B_mid (this CTA's half) = 64 KB
+constexpr uint32_t kBwStagingOff = kBwStages * kBwStage;          // 128 KB
+constexpr uint32_t kBwStagingWarp = 4096;                         // [hi 32 x 64 B | mid 32 x 64 B] or fp32 32 x 128 B
+constexpr uint32_t kBwBarOff = kBwStagingOff + 16 * kBwStagingWarp;   // 192 KB: free[2] full[2] rfull[2] rempty[2]
+constexpr uint32_t kBwCDoneOff = kBwBarOff + 8 * 8;
+constexpr uint32_t kBwTmemSlotOff = kBwCDoneOff + 8 * kChainMaxTiles;
+constexpr uint32_t kBwColsumOff = kBwTmemSlotOff + 16;
+constexpr uint32_t kSmemBytesBw = kBwColsumOff + 256 * 4;
+
+struct BwStep {
+  const uint32_t* bits_in;      // ReLU mask of the layer this gradient flows into ([rows][8] words), NULL: none
+  float* C;                     // fp32 output [rows][ldc] (out_planes == 0)
+  uint16_t* Chi; uint16_t* Cmid;   // bf16 planes [rows][256] (out_planes != 0)
+  float* colsum;                // += column sums of the masked output = the bias gradient of that layer, NULL: none
+  int ldc, K, N, n0, out_planes, pad_;
+};
+struct BwArgs {
+  BwStep s[kChainMaxSteps];
+  const int* rows_dev;
+  long long* dbg;
+  int n_steps, M, row_off;
+};
+struct BwMaps {
+  CUtensorMap a_hi[kChainMaxSteps], a_mid[kChainMaxSteps], b_hi[kChainMaxSteps], b_mid[kChainMaxSteps],
+      c_hi[kChainMaxSteps], c_mid[kChainMaxSteps], c32[kChainMaxSteps];
+};
+
+// sum over the 32 lanes of a warp of 16 per-lane values: butterfly that halves the values per round (8 + 4 + 2 + 1 + 1
+// shuffles); afterwards the lane pair (2 c, 2 c + 1) holds the total of column c_of_lane
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, int& col) {
+  float a8[8], a4[4], a2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8];
+    a8[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? a8[i] : a8[i + 4];
+    a4[i] = (b3 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? a4[i] : a4[i + 2];
+    a2[i] = (b2 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? a2[0] : a2[1];
+  float r = (b1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  col = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwThreads, 1)
+mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ BwMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem = smem_u32(smem_raw);
+  const uint32_t free0 = smem + kBwBarOff, full0 = free0 + 16, rfull0 = full0 + 16, rempty0 = rfull0 + 16;
+  const uint32_t cdone0 = smem + kBwCDoneOff;
+  float* s_colsum = reinterpret_cast<float*>(smem_raw + kBwColsumOff);
+
+  int M = a.M;
+  if (a.rows_dev) M = min(M, *a.rows_dev - a.row_off);
+  if (M <= 0) return;
+  const int n_pair_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+  if (pair >= n_pair_tiles) return;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + kBwTmemSlotOff);
+  if (tid == 0) {
+    for (int i = 0; i < kChainMaxTiles; ++i) mbar_init(cdone0 + 8 * i, kBwConsumers / 32);
+    for (int i = 0; i < kBwStages; ++i) {
+      mbar_init(free0 + 8 * i, 1);                               // one multicast commit
+      mbar_init(full0 + 8 * i, 1);                               // the leader's expect_tx arrive; bytes from both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(rfull0 + 8 * i, 1);
+      mbar_init(rempty0 + 8 * i, 2 * (kBwConsumers / 32));       // consumer warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 256) s_colsum[tid] = 0.f;
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int my_tiles = (n_pair_tiles - 1 - pair) / n_pairs + 1;
+  const int n_items = a.n_steps * my_tiles;                    // item w: step w / my_tiles, local tile w % my_tiles
+  const uint32_t l_full0 = map_to_cta(full0, 0), l_rempty0 = map_to_cta(rempty0, 0);
+  const bool dbg_cta = a.dbg != nullptr && blockIdx.x == 0;
+  auto tile_row0 = [&](int lt) { return ((pair + lt * n_pairs) * 2 + (int)rank) * BM; };   // this CTA's 128 rows
+
+  if (warp == kBwIssuerWarp) {
+    if (lane == 0) {
+      // both CTAs: TMA of THIS CTA's rows of A and its half of the weight rows; leader: also every MMA
+      struct Cursor { int w, step, lt, kt, n_slabs; };
+      auto cur_init = [&](Cursor& c) {
+        c.w = 0; c.step = 0; c.lt = 0; c.kt = 0; c.n_slabs = (a.s[0].K + 63) / 64;
+      };
+      auto cur_next = [&](Cursor& c) {
+        if (++c.kt == c.n_slabs) {
+          c.kt = 0;
+          ++c.w;
+          if (c.w < n_items) { c.step = c.w / my_tiles; c.lt = c.w - c.step * my_tiles; c.n_slabs = (a.s[c.step].K + 63) / 64; }
+        }
+      };
+      long long t_iss = 0, t_full = 0, t_rem = 0, t_all = dbg_cta ? clock64() : 0, t0 = 0;
+      auto issue = [&](const Cursor& c, uint32_t g) {
+        const long long ti0 = dbg_cta ? clock64() : 0;
+        const BwStep& S = a.s[c.step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const uint32_t st = g % kBwStages, base = smem + st * kBwStage;
+        if (g >= (uint32_t)kBwStages) mbar_wait(free0 + 8 * st, ((g / kBwStages) - 1) & 1);
+        if (c.kt == 0 && c.step > 0) {
+          // this tile's rows of the step's input were stored by the epilogue of (tile, step - 1)
+          mbar_wait(cdone0 + 8 * c.lt, (uint32_t)(c.step - 1) & 1);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        if (rank == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * st), "r"(8 * kBwPlane) : "memory");
+        const uint32_t bar = l_full0 + 8 * st;
+        const int row0 = tile_row0(c.lt), brow0 = S.n0 + (int)rank * (BN >> 1);
+        tma2_load_2d(base, &maps.a_hi[c.step], bar, c.kt * 64, row0);
+        tma2_load_2d(base + kBwPlane, &maps.a_mid[c.step], bar, c.kt * 64, row0);
+        tma2_load_2d(base + 2 * kBwPlane, &maps.b_hi[c.step], bar, c.kt * 64, brow0);
+        tma2_load_2d(base + 3 * kBwPlane, &maps.b_mid[c.step], bar, c.kt * 64, brow0);
+        if (dbg_cta) t_iss += clock64() - ti0;
+      };
+      Cursor lc;
+      cur_init(lc);
+      issue(lc, 0);
+      cur_next(lc);
+      uint32_t g = 0;
+      for (int w = 0; w < n_items; ++w) {
+        const int step = w / my_tiles;
+        const BwStep& S = a.s[step];
+        const int BN = min(TNF, (S.N - S.n0 + 15) & ~15);
+        const int n_slabs = (S.K + 63) / 64;
+        const uint32_t idesc = make_idesc(true, BN, 2 * BM, false);
+        const uint32_t rg = (uint32_t)w & 1;
+        for (int kt = 0; kt < n_slabs; ++kt, ++g) {
+          const uint32_t st = g % kBwStages;
+          if (rank == 0) {
+            if (dbg_cta) t0 = clock64();
+            mbar_wait_cluster(full0 + 8 * st, (g / kBwStages) & 1);
+            if (dbg_cta) { const long long t1 = clock64(); t_full += t1 - t0; t0 = t1; }
+            if (kt == 0 && w >= 2) mbar_wait_cluster(rempty0 + 8 * rg, (((uint32_t)w >> 1) - 1) & 1);
+            if (dbg_cta) t_rem += clock64() - t0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem + st * kBwStage, d = tmem_d + rg * TNF;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t dah = make_desc(base + j * 32), dam = make_desc(base + kBwPlane + j * 32);
+              const uint64_t dbh = make_desc(base + 2 * kBwPlane + j * 32), dbm = make_desc(base + 3 * kBwPlane + j * 32);
+              mma2_bf16(d, dam, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);
+              mma2_bf16(d, dah, dbm, idesc, 1);
+              mma2_bf16(d, dah, dbh, idesc, 1);
+            }
+            mma2_commit(free0 + 8 * st);
+            if (kt == n_slabs - 1) mma2_commit(rfull0 + 8 * rg);
+          }
+          // operands of the next slab (its stage was read by slab g - 1, whose MMAs are queued in front of slab g's)
+          if (lc.w < n_items) {
+            issue(lc, g + 1);
+            cur_next(lc);
+          }
+        }
+      }
+      // (slots as mlp_chain2_kernel: 5 = operands not there yet, 7 = no free accumulator, 8 = inside issue(): stage /
+      // dependency waits + 4 TMA, 9 = total)
+      if (dbg_cta) { a.dbg[5] = t_full; a.dbg[6] = 0; a.dbg[7] = t_rem; a.dbg[8] = t_iss; a.dbg[9] = clock64() - t_all; }
+    }
+  } else {
+    // ================= 16 epilogue warps =================
+    const int quarter = warp & 3, cg = warp >> 2;                // TMEM lanes 32 quarter.., columns 64 cg..
+    const uint32_t stg = smem + kBwStagingOff + (uint32_t)warp * kBwStagingWarp;
+    const uint32_t swz64 = (uint32_t)((lane >> 1) & 3);        // SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+    const bool dbg_on = dbg_cta && tid == 0;
+    long long t_main = 0, t_epi = 0, t_fe = 0, tc0 = 0;
+    for (int w = 0; w < n_items; ++w) {
+      const int step = w / my_tiles, lt = w - step * my_tiles;
+      const BwStep& S = a.s[step];
+      const int n0 = S.n0, N = S.N;
+      const int BN = min(TNF, (N - n0 + 15) & ~15);
+      const uint32_t rg = (uint32_t)w & 1;
+      const int m0 = tile_row0(lt), mr0 = m0 + quarter * 32, m = mr0 + lane;
+      const uint32_t tmem_row = tmem_d + ((uint32_t)(quarter * 32) << 16) + rg * TNF + 64 * cg;
+      const int nhalf = max(0, min(4, (BN - 64 * cg + 15) >> 4));
+      const bool has_mask = S.bits_in != nullptr, planes = S.out_planes != 0, do_colsum = S.colsum != nullptr;
+      const bool tma_out = mr0 + 32 <= M;
+      uint32_t mw0 = 0xffffffffu, mw1 = 0xffffffffu;
+      if (has_mask && m < M) {
+        const uint2 t = *reinterpret_cast<const uint2*>(S.bits_in + (size_t)m * 8 + 2 * cg);
+        mw0 = t.x; mw1 = t.y;
+      }
+      if (dbg_on) tc0 = clock64();
+      mbar_wait_relaxed(rfull0 + 8 * rg, ((uint32_t)w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg_on) { const long long t1 = clock64(); t_main += t1 - tc0; tc0 = t1; }
+      auto release_region = [&]() {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(rempty0 + 8 * rg);
+          else mbar_arrive_cluster(l_rempty0 + 8 * rg);
+        }
+      };
+      // half hf (0..3) = columns 64 cg + 16 hf .. + 16 of the item
+      auto process_half = [&](uint32_t (&r)[16], int hf, uint32_t bits16) {
+        const int c0 = 64 * cg + 16 * hf;                      // column within the item's 256-wide block
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          // mask bit j of bits16 -> all-ones / all-zeros by sign extension of a 1-bit field
+          const int keep = has_mask ? ((int)(bits16 << (31 - j)) >> 31) : -1;
+          v[j] = __uint_as_float(r[j] & (uint32_t)keep);
+        }
+        if (m >= M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;             // rows beyond the sample count: keep them out of the sums
+        }
+        if (do_colsum) {
+          int col;
+          const float tot = warp_colsum16(v, lane, col);
+          if ((lane & 1) == 0 && tot != 0.f) atomicAdd(s_colsum + c0 + col, tot);
+        }
+        if (planes) {
+          uint32_t h[8], md[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bf16_split2(v[2 * j], v[2 * j + 1], h[j], md[j]);
+          if (tma_out) {
+            if ((hf & 1) == 0) {                               // first half of a 32-column block: the tile must be free
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+            const uint32_t row = stg + (uint32_t)lane * 64;
+            const uint32_t ch0 = (uint32_t)(2 * (hf & 1));
+            st_shared_v4u(row + (((ch0) ^ swz64) * 16), h[0], h[1], h[2], h[3]);
+            st_shared_v4u(row + (((ch0 + 1) ^ swz64) * 16), h[4], h[5], h[6], h[7]);
+            st_shared_v4u(row + 2048 + (((ch0) ^ swz64) * 16), md[0], md[1], md[2], md[3]);
+            st_shared_v4u(row + 2048 + (((ch0 + 1) ^ swz64) * 16), md[4], md[5], md[6], md[7]);
+            if (hf & 1) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&maps.c_hi[step], stg, n0 + c0 - 16, mr0);
+                tma_store_2d(&maps.c_mid[step], stg + 2048, n0 + c0 - 16, mr0);
+              }
+            }
+          } else if (m < M) {
+            uint4* ph = reinterpret_cast<uint4*>(S.Chi + (size_t)m * 256 + n0 + c0);
+            uint4* pm = reinterpret_cast<uint4*>(S.Cmid + (size_t)m * 256 + n0 + c0);
+            ph[0] = make_uint4(h[0], h[1], h[2], h[3]); ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            pm[0] = make_uint4(md[0], md[1], md[2], md[3]); pm[1] = make_uint4(md[4], md[5], md[6], md[7]);
+          }
+        } else {
+          if (tma_out) {
+            if ((hf & 1) == 0) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              st_shared_v4(stg + (uint32_t)(lane * 128 + (((4 * (hf & 1) + j4) ^ (lane & 7)) * 16)),
+                           make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+            if (hf & 1) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&maps.c32[step], stg, n0 + c0 - 16, mr0);
+            }
+          } else if (m < M) {
+            float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < N) cp[j] = v[j];
+          }
+        }
+      };
+      {
+        uint32_t ra[16], rb[16];
+        if (nhalf > 0) tmem_ld16(tmem_row, ra);
+        else release_region();
+#pragma unroll
+        for (int hf = 0; hf < 4; ++hf) {
+          if (hf < nhalf) {
+            tmem_ld_wait();
+            if (hf + 1 < nhalf) {
+              if (hf & 1) tmem_ld16(tmem_row + 16 * (hf + 1), ra);
+              else tmem_ld16(tmem_row + 16 * (hf + 1), rb);
+            } else {
+              release_region();
+            }
+            const uint32_t bits16 = (hf < 2 ? mw0 : mw1) >> (16 * (hf & 1));
+            if (hf & 1) process_half(rb, hf, bits16); else process_half(ra, hf, bits16);
+          }
+        }
+        // an odd number of halves (N % 32 == 16) leaves a half-filled staging tile: send it
+        if ((nhalf & 1) && tma_out) {
+          const int c0 = 64 * cg + 16 * (nhalf - 1);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (planes) {
+              tma_store_2d(&maps.c_hi[step], stg, n0 + c0, mr0);
+              tma_store_2d(&maps.c_mid[step], stg + 2048, n0 + c0, mr0);
+            } else {
+              tma_store_2d(&maps.c32[step], stg, n0 + c0, mr0);
+            }
+          }
+        }
+      }
+      // the tile's rows of this step are complete in global memory -> the issuer may load them for (tile, step + 1)
+      __syncwarp();
+      if (dbg_on) { const long long t1 = clock64(); t_epi += t1 - tc0; tc0 = t1; }
+      if (lane == 0) {
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        mbar_arrive(cdone0 + 8 * lt);
+      }
+      // bias gradient of this step: the CTA's partial column sums leave once its last tile of the step is done
+      if (do_colsum && lt == my_tiles - 1) {
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < 256) {
+          const float t = s_colsum[tid];
+          if (t != 0.f && n0 + tid < N) atomicAdd(S.colsum + n0 + tid, t);
+          s_colsum[tid] = 0.f;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
+      if (dbg_on) t_fe += clock64() - tc0;
+    }
+    if (dbg_on) { a.dbg[0] = t_main; a.dbg[1] = t_epi; a.dbg[24] = t_fe; }
+  }
+  // ---- teardown: nobody may leave (or free TMEM) while the partner can still signal it or multiply into it ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
+// fp32 rows -> bf16 hi / mid planes (tests and stand-alone entries; inside the fused step the planes are written by the
+// kernels that compute the values).  One thread per 2 elements; column sums by atomics (small matrices only).
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ X, int ld, int rows, int cols, uint16_t* __restrict__ hi,
+                    uint16_t* __restrict__ mid, int ldp, float* __restrict__ colsum, const int* __restrict__ rows_dev) {
+  int valid = rows;
+  if (rows_dev) valid = min(valid, *rows_dev);
+  const int half = ldp >> 1;
+  const long long total = (long long)rows * half;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / half), c = 2 * (int)(i - (long long)r * half);
+    const float x0 = (c < cols) ? X[(size_t)r * ld + c] : 0.f, x1 = (c + 1 < cols) ? X[(size_t)r * ld + c + 1] : 0.f;
+    uint32_t h, m;
+    bf16_split2(x0, x1, h, m);
+    reinterpret_cast<uint32_t*>(hi + (size_t)r * ldp)[c >> 1] = h;
+    reinterpret_cast<uint32_t*>(mid + (size_t)r * ldp)[c >> 1] = m;
+    if (colsum && r < valid) {
+      if (c < cols && x0 != 0.f) atomicAdd(colsum + c, x0);
+      if (c + 1 < cols && x1 != 0.f) atomicAdd(colsum + c + 1, x1);
+    }
+  }
+}
+
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
 int g_dw_sm_reserve = 0;
@@ -1600,7 +2004,8 @@ std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> g_maps;
 // 2-D map of a row-major fp32 matrix: `cols` valid columns (dim 0), `rows` rows of pitch ld floats; box =
 // (32 floats, box_rows rows), SWIZZLE_128B.  Out-of-range box elements read as zero / are not written.
 // bf16: the plane holds 2-byte elements (cols / ld in elements), box = (64 elements, box_rows rows): the same 128 bytes.
-// raw_box_cols > 0: a plain (unswizzled) fp32 box of raw_box_cols x box_rows (the raw operand ring of the weight-gradient kernel).
+// raw_box_cols > 0: a plain (unswizzled) box of raw_box_cols x box_rows (the raw operand ring of the weight-gradient kernel);
+// raw_box_cols < 0: a box of -raw_box_cols columns with SWIZZLE_64B (the 64-byte rows of the plane epilogue's staging tile).
 int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out, bool bf16 = false,
             int raw_box_cols = 0) {
   auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows, (int)bf16 + 2 * raw_box_cols);
@@ -1619,11 +2024,13 @@ int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtenso
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};              // bytes, dim 1
-  const cuuint32_t box[2] = {(cuuint32_t)(raw_box_cols > 0 ? raw_box_cols : (bf16 ? 2 * BK : BK)), (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)(raw_box_cols > 0 ? raw_box_cols : raw_box_cols < 0 ? -raw_box_cols : (bf16 ? 2 * BK : BK)),
+                             (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
   CUresult r = g_encode(&tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, raw_box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        raw_box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : raw_box_cols < 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) cols %d rows %d ld %d",
@@ -1725,6 +2132,73 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
   return 0;
 }
 
+// The backward-data chain on bf16 planes (mlp_bwd_planes_kernel), large workspaces in row ranges like mlp_chain.
+int mlp_bwd_planes(const BwStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st) {
+  if (M <= 0 || n_steps <= 0) return 0;
+  if (n_steps > kChainMaxSteps) return fgs::fail_arg("mlp_bwd_planes: too many steps");
+  static bool configured = false;
+  int rc = configure_once(mlp_bwd_planes_kernel, configured, "mlp_bwd_planes smem attribute", kSmemBytesBw);
+  if (rc) return rc;
+  const int pairs_all = FGS_NUM_SMS / 2;
+  const int max_rows = kChainMaxTiles * pairs_all * 2 * BM;
+  for (int row_off = 0; row_off < M; row_off += max_rows) {
+    const int Mc = M - row_off < max_rows ? M - row_off : max_rows;
+    BwArgs a;
+    BwMaps maps;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_steps; ++i) {
+      const BwStepHost& h = steps[i];
+      if ((h.lda & 7) || (h.ldb & 7) || (((uintptr_t)h.Ahi | (uintptr_t)h.Amid | (uintptr_t)h.Bh | (uintptr_t)h.Bl) & 15))
+        return fgs::fail_arg("mlp_bwd_planes needs 16-byte aligned planes with rows of whole 16 bytes");
+      if (h.K > h.ldb || h.K > h.lda) return fgs::fail_arg("mlp_bwd_planes: K exceeds a plane's row length");
+      const uint16_t* ah = h.Ahi + (size_t)row_off * h.lda;
+      const uint16_t* am = h.Amid + (size_t)row_off * h.lda;
+      if ((rc = get_map(ah, h.lda, Mc, h.lda, 128, &maps.a_hi[i], true))) return rc;
+      if ((rc = get_map(am, h.lda, Mc, h.lda, 128, &maps.a_mid[i], true))) return rc;
+      const int rows_alloc = (h.N + 7) & ~7;
+      if ((rc = get_map(h.Bh, h.ldb, rows_alloc, h.ldb, TN, &maps.b_hi[i], true))) return rc;
+      if ((rc = get_map(h.Bl, h.ldb, rows_alloc, h.ldb, TN, &maps.b_mid[i], true))) return rc;
+      BwStep& s = a.s[i];
+      s.bits_in = h.bits_in ? h.bits_in + (size_t)row_off * 8 : nullptr;
+      s.colsum = h.colsum;
+      s.K = h.K; s.N = h.N; s.n0 = h.n0; s.out_planes = h.out_planes; s.ldc = h.ldc;
+      maps.c_hi[i] = maps.a_hi[i]; maps.c_mid[i] = maps.a_hi[i]; maps.c32[i] = maps.a_hi[i];
+      if (h.out_planes) {
+        if (h.N > 256 || h.n0 != 0) return fgs::fail_arg("mlp_bwd_planes: plane outputs are [rows][256]");
+        s.Chi = h.Chi + (size_t)row_off * 256; s.Cmid = h.Cmid + (size_t)row_off * 256;
+        if ((((uintptr_t)s.Chi | (uintptr_t)s.Cmid) & 15)) return fgs::fail_arg("mlp_bwd_planes: unaligned output planes");
+        // box 32 columns x 32 rows of 2-byte elements = 64-byte rows, SWIZZLE_64B (the staging tile's layout)
+        if ((rc = get_map(s.Chi, 256, Mc, 256, 32, &maps.c_hi[i], true, -32))) return rc;
+        if ((rc = get_map(s.Cmid, 256, Mc, 256, 32, &maps.c_mid[i], true, -32))) return rc;
+      } else {
+        s.C = h.C + (size_t)row_off * h.ldc;
+        if ((h.ldc & 3) || (((uintptr_t)s.C) & 15)) return fgs::fail_arg("mlp_bwd_planes: fp32 output rows must be 16-byte aligned");
+        if ((rc = get_map(s.C, h.N, Mc, h.ldc, 32, &maps.c32[i]))) return rc;
+      }
+    }
+    for (int i = n_steps; i < kChainMaxSteps; ++i) {
+      maps.a_hi[i] = maps.a_hi[0]; maps.a_mid[i] = maps.a_hi[0]; maps.b_hi[i] = maps.a_hi[0]; maps.b_mid[i] = maps.a_hi[0];
+      maps.c_hi[i] = maps.a_hi[0]; maps.c_mid[i] = maps.a_hi[0]; maps.c32[i] = maps.a_hi[0];
+    }
+    a.rows_dev = rows_dev; a.dbg = g_dbg; a.n_steps = n_steps; a.M = Mc; a.row_off = row_off;
+    const int n_pair_tiles = fgs::cdiv(Mc, 2 * BM);
+    int pairs_n = pairs_all;
+    if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
+    mlp_bwd_planes_kernel<<<2 * pairs_n, kBwThreads, kSmemBytesBw, st>>>(a, maps);
+    if ((rc = fgs::check_launch("mlp_chain_bwd", st))) return rc;
+  }
+  return 0;
+}
+
+int split_planes(const float* X, int ld, int rows, int cols, uint16_t* hi, uint16_t* mid, int ldp, float* colsum,
+                 const int32_t* rows_dev, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if ((ldp & 1) || cols > ldp) return fgs::fail_arg("split_planes: ldp must be even and >= cols");
+  const int grid = fgs::stream_grid((long long)rows * (ldp >> 1), 256, 8);
+  split_planes_kernel<<<grid, 256, 0, st>>>(X, ld, rows, cols, hi, mid, ldp, colsum, rows_dev);
+  return fgs::check_launch("split_planes", st);
+}
+
 // All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first
 // min(K, *rows_dev) rows, colsum_i[m] += sum_k A_i[k][m] (may be NULL).  Rows of A / B must be readable in whole
 // float4s (lda, ldb % 4 == 0, 16-byte aligned bases).
@@ -1738,9 +2212,10 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   for (int i = 0; i < n; ++i) {
     const DwProblemHost& h = probs[i];
     if (h.M <= 0 || h.N <= 0) continue;
-    if ((h.lda & 3) || (h.ldb & 3) || (((uintptr_t)h.A | (uintptr_t)h.B) & 15))
+    if (!bf16 && ((h.lda & 3) || (((uintptr_t)h.A) & 15) || ((h.M + 3) & ~3) > h.lda))
       return fgs::fail_arg("mlp_dw needs 16-byte aligned operands with leading dimensions % 4 == 0");
-    if (((h.M + 3) & ~3) > h.lda || ((h.N + 3) & ~3) > h.ldb) return fgs::fail_arg("mlp_dw: operand rows must be padded to 4 floats");
+    if ((h.ldb & 3) || (((uintptr_t)h.B) & 15) || ((h.N + 3) & ~3) > h.ldb)
+      return fgs::fail_arg("mlp_dw: operand rows must be padded to 4 floats");
     if (h.M > 2 * BM) return fgs::fail_arg("mlp_dw: more than 256 out-features");
     DwProblem& p = b.p[i];
     p.A = h.A; p.B = h.B; p.C = h.C; p.colsum = h.colsum;
@@ -1760,18 +2235,22 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
   DwMaps maps;
   memset(&maps, 0, sizeof(maps));
   if (bf16) {
-    // raw operand boxes of the per-warp TMA rings: 4 sample rows x 128 out-features of dZ / x 64 input features of X;
-    // columns beyond the matrix and rows beyond the allocation read as zero
+    // A: bf16 planes of dZ, boxes of 64 out-features x 64 samples straight into the MN-major operand tile;
+    // B: raw fp32 rows of X for the per-warp rings (4 samples x 64 features).  Columns beyond the matrix and rows beyond
+    // the allocation read as zero.
     int first = -1;
     for (int i = 0; i < n; ++i) {
       const DwProblemHost& h = probs[i];
       if (h.M <= 0 || h.N <= 0) continue;
-      if ((rc2 = get_map(h.A, h.lda, K, h.lda, 4, &maps.a[i], false, 128))) return rc2;
+      if (!h.Ahi || !h.Amid || (h.ldp & 7) || h.colsum)
+        return fgs::fail_arg("mlp_dw (bf16): A must be given as bf16 planes (ldp % 8 == 0) and colsum must be NULL");
+      if ((rc2 = get_map(h.Ahi, h.ldp, K, h.ldp, 64, &maps.a_hi[i], true))) return rc2;
+      if ((rc2 = get_map(h.Amid, h.ldp, K, h.ldp, 64, &maps.a_mid[i], true))) return rc2;
       if ((rc2 = get_map(h.B, h.ldb, K, h.ldb, 4, &maps.b[i], false, 64))) return rc2;
       if (first < 0) first = i;
     }
     for (int i = 0; i < kDwMaxProblems; ++i)
-      if (i >= n || probs[i].M <= 0 || probs[i].N <= 0) { maps.a[i] = maps.a[first]; maps.b[i] = maps.b[first]; }
+      if (i >= n || probs[i].M <= 0 || probs[i].N <= 0) { maps.a_hi[i] = maps.a_hi[first]; maps.a_mid[i] = maps.a_mid[first]; maps.b[i] = maps.b[first]; }
   }
   // every pair should own at least ~8 slabs, else the epilogues dominate
   const long long units2 = (long long)nt2 * fgs::cdiv(K, bf16 ? 2 * BK : BK);
@@ -1866,46 +2345,91 @@ extern "C" int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int l
 
 // Stand-alone entries of the 3xBF16 kernels the fused step's BACKWARD runs (tests): one step of the chain kernel
 // (C = A B^T for mode 0 / A B for mode 1, optional mask bits) and the weight-gradient product.
+namespace {
+// scratch for the stand-alone bf16 entries: weight planes + operand planes + output planes
+void* g_scratch2 = nullptr;
+size_t g_scratch2_bytes = 0;
+int ensure_scratch2(size_t bytes, cudaStream_t st) {
+  if (bytes <= g_scratch2_bytes) return 0;
+  if (g_scratch2) {
+    cudaStreamSynchronize(st);
+    cudaFree(g_scratch2);
+    g_maps.clear();
+  }
+  int rc = fgs::check_cuda(cudaMalloc(&g_scratch2, bytes), "bf16 scratch");
+  if (rc) return rc;
+  g_scratch2_bytes = bytes;
+  return 0;
+}
+__global__ void __launch_bounds__(256)
+planes_to_fp32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ mid, int ldp, int rows, int cols,
+                      float* __restrict__ C, int ldc, const int* __restrict__ rows_dev) {
+  int valid = rows;
+  if (rows_dev) valid = min(valid, *rows_dev);
+  const long long total = (long long)valid * cols;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    C[(size_t)r * ldc + c] = __uint_as_float((uint32_t)hi[(size_t)r * ldp + c] << 16) + __uint_as_float((uint32_t)mid[(size_t)r * ldp + c] << 16);
+  }
+}
+}  // namespace
+
+// Stand-alone entries of the 3xBF16 kernels the fused step's BACKWARD runs (tests): one step of the planes chain
+// (C = A B^T for mode 0 / A B for mode 1, optional mask bits, fp32 or plane output) and the weight-gradient product.
+// A is split into bf16 planes by a pre-pass (inside the fused step the producing kernels write the planes).
 extern "C" int fgs_gemm_tcw_bf16(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                                 float* C, int ldc, const uint32_t* bits_in, const int32_t* rows_dev,
-                                 fgs_stream_t stream) {
+                                 float* C, int ldc, const uint32_t* bits_in, float* colsum, int via_planes,
+                                 const int32_t* rows_dev, fgs_stream_t stream) {
   FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
   FGS_REQUIRE(mode == 0 || mode == 1, "fgs_gemm_tcw_bf16: mode must be 0 (B [N][K]) or 1 (B [K][N])");
   FGS_REQUIRE(N <= 256, "fgs_gemm_tcw_bf16: one 256-column block");
+  FGS_REQUIRE(!via_planes || (ldc >= N), "bad ldc");
   if (M == 0 || N == 0 || K == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int kp = (K + 7) & ~7, np = (N + 7) & ~7;
-  const size_t need = (size_t)np * kp;                       // 2 bf16 planes = np * kp floats
-  if (need > g_scratch_floats) {
-    if (g_scratch) {
-      cudaStreamSynchronize(st);
-      cudaFree(g_scratch);
-      g_maps.clear();
-    }
-    int rc = fgs::check_cuda(cudaMalloc(&g_scratch, need * sizeof(float)), "gemm_tcw scratch");
-    if (rc) return rc;
-    g_scratch_floats = need;
-  }
-  int rc = fgs::check_cuda(cudaMemsetAsync(g_scratch, 0, need * sizeof(float), st), "gemm_tcw scratch memset");
+  const size_t wbytes = (size_t)np * kp * 4, abytes = (size_t)M * kp * 4, cbytes = (size_t)M * 256 * 4;
+  int rc = ensure_scratch2(wbytes + abytes + cbytes + 1024, st);
   if (rc) return rc;
+  if ((rc = fgs::check_cuda(cudaMemsetAsync(g_scratch2, 0, wbytes + abytes + cbytes, st), "bf16 scratch memset"))) return rc;
+  char* base = (char*)g_scratch2;
   fine::SplitJobHost job;
-  job.W = B; job.hi = g_scratch; job.lo = g_scratch + (size_t)np * kp / 2;
+  job.W = B; job.hi = (float*)base; job.lo = (float*)(base + wbytes / 2);
   job.ld = ldb; job.ld_out = kp; job.bf16 = 1;
   if (mode == 0) { job.rows = N; job.cols = K; job.transpose = 0; }
   else { job.rows = K; job.cols = N; job.transpose = 1; }
   if ((rc = fine::weight_split_jobs(&job, 1, st))) return rc;
-  fine::ChainStepHost s{};
-  s.A = A; s.lda = lda; s.K = K; s.Bh = job.hi; s.Bl = job.lo; s.ldb = kp;
-  s.C = C; s.ldc = ldc; s.N = N; s.n0 = 0; s.bias = nullptr; s.relu = 0; s.bits_in = bits_in; s.bits_out = nullptr;
-  return fine::mlp_chain(&s, 1, M, rows_dev, st, true);
+  uint16_t* ahi = (uint16_t*)(base + wbytes);
+  uint16_t* amid = (uint16_t*)(base + wbytes + abytes / 2);
+  if ((rc = fine::split_planes(A, lda, M, K, ahi, amid, kp, nullptr, nullptr, st))) return rc;
+  uint16_t* chi = (uint16_t*)(base + wbytes + abytes);
+  uint16_t* cmid = (uint16_t*)(base + wbytes + abytes + cbytes / 2);
+  fine::BwStepHost s{};
+  s.Ahi = ahi; s.Amid = amid; s.lda = kp; s.K = K; s.Bh = job.hi; s.Bl = job.lo; s.ldb = kp;
+  s.C = C; s.ldc = ldc; s.Chi = chi; s.Cmid = cmid; s.out_planes = via_planes ? 1 : 0;
+  s.N = N; s.n0 = 0; s.bits_in = bits_in; s.colsum = colsum;
+  if ((rc = fine::mlp_bwd_planes(&s, 1, M, rows_dev, st))) return rc;
+  if (via_planes) {
+    planes_to_fp32_kernel<<<fgs::stream_grid((long long)M * N, 256, 8), 256, 0, st>>>(chi, cmid, 256, M, N, C, ldc, rows_dev);
+    return fgs::check_launch("planes_to_fp32", st);
+  }
+  return 0;
 }
 
 extern "C" int fgs_gemm_tn_bf16(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                                 int ldc, float* colsum, const int32_t* rows_dev, fgs_stream_t stream) {
   FGS_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  fine::DwProblemHost p{A, B, C, colsum, M, N, lda, ldb, ldc};
-  return fine::mlp_dw(&p, 1, K, rows_dev, (cudaStream_t)stream, true);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mp = (M + 7) & ~7;
+  const size_t abytes = (size_t)K * mp * 4;
+  int rc = ensure_scratch2(abytes + 1024, st);
+  if (rc) return rc;
+  uint16_t* ahi = (uint16_t*)g_scratch2;
+  uint16_t* amid = (uint16_t*)((char*)g_scratch2 + abytes / 2);
+  if ((rc = fine::split_planes(A, lda, K, M, ahi, amid, mp, colsum, rows_dev, st))) return rc;
+  fine::DwProblemHost p{A, B, C, nullptr, M, N, lda, ldb, ldc};
+  p.Ahi = ahi; p.Amid = amid; p.ldp = mp;
+  return fine::mlp_dw(&p, 1, K, rows_dev, st, true);
 }
 
 // Debug: device buffer of 2 int64 that the next gemm_w launches fill with the clock cycles consumer 0 of

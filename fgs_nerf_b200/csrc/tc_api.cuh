@@ -40,11 +40,29 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
 struct DwProblemHost {
   const float* A; const float* B; float* C; float* colsum;
   int M, N, lda, ldb, ldc;
+  // bf16 variant: A is given as bf16 hi / mid planes [K][ldp] (ldp elements, % 8 == 0) instead of fp32, and colsum
+  // must be NULL (the bias gradient is a by-product of whoever wrote the planes)
+  const uint16_t* Ahi = nullptr; const uint16_t* Amid = nullptr; int ldp = 0;
 };
 // bf16: 3xBF16 operands (kind::f16, 64-sample slabs) instead of 3xTF32
 int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st, bool bf16 = false);
 // leave n SMs free while mlp_dw runs (a data-parallel step overlaps the gradient exchange with it)
 void set_dw_sm_reserve(int n_sms);
+
+// One step of the backward-data chain on bf16 planes (gemm_tcw.cu: mlp_bwd_planes_kernel):
+//   out[:, n0 : n0 + 256) = (A W^T-planes) masked by bits_in, A = Ahi + Amid [rows][lda] bf16 planes (lda elements),
+//   written as bf16 planes Chi / Cmid [rows][256] (out_planes) or as fp32 C [rows][ldc]; colsum += column sums.
+struct BwStepHost {
+  const uint16_t* Ahi; const uint16_t* Amid; int lda; int K;
+  const float* Bh; const float* Bl; int ldb;           // bf16 hi / mid weight planes [N][ldb] (as mlp_chain, bf16 = true)
+  float* C; int ldc; uint16_t* Chi; uint16_t* Cmid; int out_planes;
+  int N; int n0;
+  const uint32_t* bits_in; float* colsum;
+};
+int mlp_bwd_planes(const BwStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
+// fp32 [rows][ld] -> bf16 hi / mid planes [rows][ldp] (+ optional column sums over the first min(rows, *rows_dev) rows)
+int split_planes(const float* X, int ld, int rows, int cols, uint16_t* hi, uint16_t* mid, int ldp, float* colsum,
+                 const int32_t* rows_dev, cudaStream_t st);
 
 // Layout of FgsFineParams::w_split (in floats): per layer the straight TF32 hi / lo planes [out][in_ld] (forward, 3xTF32)
 // and the transposed bf16 hi / mid planes [in_ld][ldt] (backward-data, 3xBF16; ldt in 2-byte elements).

@@ -58,7 +58,7 @@ class FgsFineParams(C.Structure):
         ("rgb_marched", _fp), ("sigmoid_rgb", _fp), ("cum_weights", _fp), ("depth", _fp),
         ("normal_marched", _fp), ("counters", _fp),
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
-        ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp),
+        ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp), ("dlogit_p", _fp), ("dXRp", _fp),
         ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
         ("dZ", _fp), ("k0_vox_flags", _fp),
     ]
@@ -109,7 +109,7 @@ _lib.declare("fgs_fine_wsplit_floats", C.c_int64, [])
 _lib.declare("fgs_gemm_tn", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_gemm_tn_bf16", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
 _lib.declare("fgs_gemm_tcw_bf16", C.c_int,
-             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp])
+             [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp])
 _lib.declare("fgs_debug_gemm_phases", C.c_int, [_fp])
 _lib.declare("fgs_debug_feat_task", C.c_int, [C.c_int])
 _i = C.c_int
@@ -342,7 +342,12 @@ class FineStepEngine:
         ws["XR"] = e(self.cap_m2, XR_LD)
         ws["logit"], ws["normal2"], ws["dlogit"] = e(self.cap_m2, 4), e(self.cap_m2, 4), e(self.cap_m2, 4)
         ws["dA"], ws["dB"] = e(self.cap_m2, WIDTH), e(self.cap_m2, WIDTH)
-        ws["dZ"] = e(6, self.cap_m2, WIDTH)      # per-layer pre-activation gradients (one-launch backward chain)
+        # pre-activation gradients of the six hidden layers, each as two bf16 planes (hi, mid: the 3xBF16 operand format
+        # of the backward GEMMs) in the bytes of one fp32 [cap_m2][256]; the same for the gradient at rgbnet's output
+        # (dXR[:, :256]) and for dlogit.  ZERO-initialised: rows beyond the sample count are multiplied by zeros.
+        ws["dZ"] = torch.zeros(6, self.cap_m2, WIDTH, dtype=f32, device=dev)
+        ws["dXRp"] = torch.zeros(self.cap_m2, WIDTH, dtype=f32, device=dev)
+        ws["dlogit_p"] = torch.zeros(2, self.cap_m2, 8, dtype=torch.int16, device=dev)
         ws["dXR"], ws["dX0"] = e(self.cap_m2, XR_LD), e(self.cap_m2, X0_LD)
         for k in ("rgb_marched", "sigmoid_rgb", "normal_marched"):
             ws[k] = e(N, 3)
@@ -411,7 +416,7 @@ class FineStepEngine:
                   "ray_id1", "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1",
                   "d_w1", "idx1_of2", "ray_id2", "X0", "H", "XR", "logit", "normal2", "rgb_marched",
                   "sigmoid_rgb", "cum_weights", "depth", "normal_marched", "counters", "dA", "dB", "dXR",
-                  "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ"):
+                  "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ", "dXRp", "dlogit_p"):
             setattr(P, k, ptr(ws[k]))
         P.k0_vox_flags = ptr(ws["k0_vox_flags"]) if self.voxel_exchange else None
 

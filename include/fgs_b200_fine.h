@@ -122,6 +122,8 @@ typedef struct FgsFineParams {
   float *dXR;      /* [cap_m2][FGS_XR_LD]      */
   float *dX0;      /* [cap_m2][FGS_X0_LD]      */
   float *dlogit;   /* [cap_m2][4]              */
+  uint16_t *dlogit_p;  /* [2][cap_m2][8] bf16 hi / mid planes of dlogit (written with it by fgs_fine_loss) */
+  uint16_t *dXRp;      /* [2][cap_m2][256] bf16 hi / mid planes of dXR[:, 0:256] = the gradient at rgbnet's output */
   /* ---- tensor-core MLP workspace ---- */
   float *w_split;    /* fgs_fine_wsplit_floats() floats: hi / lo TF32 planes of the 8 weight matrices,
                         straight and transposed; rewritten by every fgs_fine_forward; zero-initialised */
@@ -130,9 +132,10 @@ typedef struct FgsFineParams {
   int64_t g_mlp_floats;
   uint8_t *k0_brick_flags; /* [ceil(X/4)*ceil(Y/4)*ceil(Z/4)] set to 1 by the backward scatter for every
                         4x4x4 brick of k0 that received a gradient (may be NULL); see fgs_adam_upd_bricks */
-  float *dZ;         /* optional [6][cap_m2][256]: one buffer per hidden layer's pre-activation gradient, so the
-                        backward-data chain runs as ONE launch and the 8 weight-gradient GEMMs follow it
-                        (NULL: per-layer launches through the dA / dB ping-pong) */
+  float *dZ;         /* [6][cap_m2][256] x 4 bytes: the pre-activation gradient of every hidden layer, each as TWO bf16
+                        planes (hi [cap_m2][256], then mid [cap_m2][256]: the 3xBF16 operand format), written once by
+                        the backward chain's epilogue and read by TMA by its next step and by the weight-gradient
+                        kernel.  Zero-initialise it once: rows beyond the sample count are multiplied by zeros */
   uint8_t *k0_vox_flags; /* optional [X*Y*Z]: set to 1 by the backward scatter for every k0 voxel that received a
                         gradient (data-parallel exchange at voxel granularity, fgs_voxel_list); NULL = not recorded */
 } FgsFineParams;
@@ -254,13 +257,17 @@ int fgs_gemm_tcw(int mode, int M, int N, int K, const float* A, int lda, const f
 int fgs_gemm_tn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
 
-/* The kernels of the fused step's BACKWARD, stand-alone: operands split into bf16 hi / mid planes, products
+/* The kernels of the fused step's BACKWARD, stand-alone: operands as bf16 hi / mid planes, products
  * hi*hi + hi*mid + mid*hi on tcgen05 kind::f16 (3xBF16: ~1e-5 relative, half the tensor-core time of 3xTF32; the
- * forward keeps 3xTF32 so that the ReLU branch assignment stays the fp32 one).  fgs_gemm_tcw_bf16: one step of the
- * chain kernel, C[M,N<=256] = A B^T (mode 0) / A B (mode 1), masked by bits_in when given.  fgs_gemm_tn_bf16: the
- * weight-gradient product C[M<=256,N] += A[K,M]^T B[K,N], colsum as fgs_gemm_tn. */
+ * forward keeps 3xTF32 so that the ReLU branch assignment stays the fp32 one).  Inside the fused step the planes are
+ * written by the kernels that compute the values; these entries split their fp32 arguments in a pre-pass.
+ * fgs_gemm_tcw_bf16: one step of the planes chain, C[M,N<=256] = A B^T (mode 0) / A B (mode 1), masked by bits_in
+ *   when given, colsum[n] += column sums of the (masked) result when given; via_planes != 0 routes the result through
+ *   the bf16-plane output path of the epilogue (C = hi + mid: the value the next step would read).
+ * fgs_gemm_tn_bf16: the weight-gradient product C[M<=256,N] += A[K,M]^T B[K,N], colsum as fgs_gemm_tn. */
 int fgs_gemm_tcw_bf16(int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                      float* C, int ldc, const uint32_t* bits_in, const int32_t* rows_dev, fgs_stream_t stream);
+                      float* C, int ldc, const uint32_t* bits_in, float* colsum, int via_planes,
+                      const int32_t* rows_dev, fgs_stream_t stream);
 int fgs_gemm_tn_bf16(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                      float* colsum, const int32_t* rows_dev, fgs_stream_t stream);
 

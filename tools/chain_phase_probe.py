@@ -38,3 +38,7 @@ e0.record(); eng.loss_backward(tgt); e1.record(); torch.cuda.synchronize()
 check(lib.fgs_debug_gemm_phases(None))
 show("loss + backward (chain + dW + scatter)", e0.elapsed_time(e1))
 show("  dW kernel (slot 8 = slabs of CTA 0)", e0.elapsed_time(e1), 10)
+d = dbg.cpu().tolist()
+print("  dW extra: producer wait raw ring %.1f us, wait stage free %.1f us, convert+store %.1f us; issuer inside issue_a %.1f us" %
+      (d[12] / 1965, d[13] / 1965, d[14] / 1965, d[16] / 1965))
+print("  bwd planes extra: issuer inside issue() %.1f us; consumer fence+colsum flush %.1f us" % (d[8] / 1965, d[24] / 1965))
