@@ -43,18 +43,6 @@ ChainStepHost fwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer,
   s.bits_in = nullptr; s.bits_out = (relu && hid >= 0) ? hbits(P, hid) : nullptr;
   return s;
 }
-// backward-data step through `layer`: C = (A W_layer) masked by the ReLU bits of hidden buffer `hid`
-ChainStepHost bwd_step(const FgsFineParams& P, const WSplitLayout& L, int layer, const float* A, int lda, int K,
-                       float* C, int ldc, int N, int n0, int hid) {
-  ChainStepHost s{};
-  s.A = A; s.lda = lda; s.K = K;
-  s.Bh = P.w_split + L.thi[layer]; s.Bl = P.w_split + L.tlo[layer]; s.ldb = L.ldt[layer];
-  s.C = C; s.ldc = ldc; s.N = N; s.n0 = n0;
-  s.bias = nullptr; s.relu = 0;
-  s.bits_in = hid >= 0 ? hbits(P, hid) : nullptr; s.bits_out = nullptr;
-  return s;
-}
-
 // operand planes of the 8 weight matrices in one launch: straight TF32 hi / lo (forward), transposed bf16 hi / mid (backward)
 int prep_weights(const FgsFineParams& P, cudaStream_t st) {
   FGS_REQUIRE(P.w_split != nullptr && P.hbits != nullptr, "w_split / hbits workspace is NULL");
@@ -196,7 +184,9 @@ int fgs_fine_backward_phase(const FgsFineParams* p, const FgsFineLoss* l, int ph
         dw[i] = DwProblemHost{nullptr, xin[i], P.gW[i], nullptr, out_dim[i], in_dim[i], 0, in_dim[i], in_dim[i]};
         dw[i].Ahi = ahi[i]; dw[i].Amid = amid[i]; dw[i].ldp = ldp[i];
       }
-      if ((rc = mlp_dw(dw, 8, cap, m2, st, true))) return rc;
+      // the last layer has 3 out-features: a 256-row MMA tile would spend 12 % of the kernel on it; fp32 SIMT instead
+      if ((rc = mlp_dw(dw, 7, cap, m2, st, true))) return rc;
+      if ((rc = dw_small(out_dim[7], in_dim[7], cap, P.dlogit, 4, xin[7], in_dim[7], P.gW[7], in_dim[7], m2, st))) return rc;
     }
     return 0;
   }

@@ -299,16 +299,6 @@ __device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_
 __device__ __forceinline__ void st_shared_v2u(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-// 8 consecutive k of one row -> one 16-byte chunk of the hi tile and of the mid tile
-__device__ __forceinline__ void split_store_bf8(uint32_t hi_addr, uint32_t mid_addr, const float4& a, const float4& b) {
-  uint32_t h[4], m[4];
-  bf16_split2(a.x, a.y, h[0], m[0]);
-  bf16_split2(a.z, a.w, h[1], m[1]);
-  bf16_split2(b.x, b.y, h[2], m[2]);
-  bf16_split2(b.z, b.w, h[3], m[3]);
-  st_shared_v4u(hi_addr, h[0], h[1], h[2], h[3]);
-  st_shared_v4u(mid_addr, m[0], m[1], m[2], m[3]);
-}
 // 4 consecutive MN elements of one k row (MN-major tiles of the weight-gradient kernel) -> 8 bytes per tile
 __device__ __forceinline__ void split_store_bf4(uint32_t hi_addr, uint32_t mid_addr, const float4& a) {
   uint32_t h[2], m[2];
@@ -738,16 +728,15 @@ __device__ __forceinline__ void mma2_commit(uint32_t bar) {    // arrives on `ba
                : "memory");
 }
 
-// BF = false: TF32 hi / lo planes, kind::tf32, 32-k slabs (the forward).  BF = true: bf16 hi / mid planes, kind::f16,
-// 64-k slabs in the same bytes (the backward-data chain): same 12 MMAs per slab, half as many slabs.
-template <bool BF>
+// (The forward chain: TF32 hi / lo planes, kind::tf32, 32-k slabs.  The backward-data chain is mlp_bwd_planes_kernel.)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
 mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ ChainMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
   const Bars B = make_bars(smem);
   const uint32_t cdone0 = smem + kCDoneOff;
-  constexpr int SK = BF ? 2 * BK : BK;                         // k per slab (one 128-byte swizzle row per operand row)
+  constexpr int SK = BK;                                       // k per slab (one 128-byte swizzle row per operand row)
+  constexpr bool BF = false;
 
   int M = a.M;
   if (a.rows_dev) M = min(M, *a.rows_dev - a.row_off);
@@ -853,9 +842,9 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
             for (int j = 0; j < BK / 8; ++j) {
               const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
               const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-              mma2<BF>(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);   // (32 bytes per row per k-step either way)
-              mma2<BF>(d, dah, dbl, idesc, 1);
-              mma2<BF>(d, dah, dbh, idesc, 1);
+              mma2_tf32(d, dal, dbh, idesc, (kt != 0 || j != 0) ? 1u : 0u);   // (32 bytes per row per k-step either way)
+              mma2_tf32(d, dah, dbl, idesc, 1);
+              mma2_tf32(d, dah, dbh, idesc, 1);
             }
             mma2_commit(B.free0 + 8 * st);
             if (kt == n_slabs - 1) mma2_commit(B.rfull0 + 8 * rg);
@@ -895,96 +884,43 @@ mlp_chain2_kernel(const __grid_constant__ ChainArgs a, const __grid_constant__ C
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (dbg_on) t_dep += clock64() - t0;
       }
-      if constexpr (!BF) {
-        // warp pw owns tile rows [16 pw, 16 pw + 16); load i (0..3) covers rows 4 i + lane / 8, lane % 8 = 16-byte k-chunk
-        const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
-        const int row = tile_row0(lt) + prow;
-        const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
-        const int mleft = M - row;
-        auto load_a = [&](float4 (&v)[4], int kt) {
-          if (kt >= n_slabs) return;
-          const int k = kt * BK + 4 * pc;
+      // warp pw owns tile rows [16 pw, 16 pw + 16); load i (0..3) covers rows 4 i + lane / 8, lane % 8 = 16-byte k-chunk
+      const int prow = pw * 16 + (lane >> 3), pc = lane & 7;
+      const int row = tile_row0(lt) + prow;
+      const float* __restrict__ src = S.A + (size_t)row * lda + 4 * pc;
+      const int mleft = M - row;
+      auto load_a = [&](float4 (&v)[4], int kt) {
+        if (kt >= n_slabs) return;
+        const int k = kt * BK + 4 * pc;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        auto produce = [&](float4 (&v)[4], int kt) {
-          const uint32_t st = g % kStages2;
-          const uint32_t stage_base = smem + st * kStage2;
-          if (dbg_on) t0 = clock64();
-          if (g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
-          if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+        for (int i = 0; i < 4; ++i)
+          v[i] = (4 * i < mleft && k < K) ? ldcg4(src + (size_t)(4 * i) * lda + kt * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto produce = [&](float4 (&v)[4], int kt) {
+        const uint32_t st = g % kStages2;
+        const uint32_t stage_base = smem + st * kStage2;
+        if (dbg_on) t0 = clock64();
+        if (g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
+        if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = prow + 4 * i;
-            const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
-            split_store(stage_base + off, stage_base + kATile + off, v[i]);
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(B.afull0 + 8 * st);            // own CTA's barrier (the follower's is relayed)
-          load_a(v, kt + 2);
-          ++g;
-          if (dbg_on) t_work += clock64() - t0;
-        };
-        float4 v0[4], v1[4];
-        load_a(v0, 0);
-        load_a(v1, 1);
-        for (int kt = 0; kt < n_slabs; kt += 2) {
-          produce(v0, kt);
-          if (kt + 1 < n_slabs) produce(v1, kt + 1);
+        for (int i = 0; i < 4; ++i) {
+          const int r = prow + 4 * i;
+          const uint32_t off = (uint32_t)(r * 128 + ((pc ^ (r & 7)) * 16));
+          split_store(stage_base + off, stage_base + kATile + off, v[i]);
         }
-      } else {
-        // bf16 planes: a 64-k slab is produced as two 32-k halves (the register budget holds two halves in flight, as it
-        // holds two 32-k slabs above).  Per half a warp covers its 16 rows in two groups of 8: lane / 4 = row in the
-        // group, lane % 4 = which 8 floats (32 bytes, two 128-bit loads) -> ONE 16-byte chunk of each plane.  A store
-        // instruction then covers 8 rows x 4 chunks whose swizzled positions (chunk ^ row % 8) tile all 32 banks:
-        // 512 bytes in 4 wavefronts.
-        const int prow8 = pw * 16 + (lane >> 2), q = lane & 3;
-        const int row = tile_row0(lt) + prow8;
-        const float* __restrict__ src = S.A + (size_t)row * lda + 8 * q;
-        const int mleft = M - row;
-        const int n_halves = 2 * n_slabs;
-        auto load_h = [&](float4 (&v)[4], int hs) {
-          if (hs >= n_halves) return;
-          const int k = hs * BK + 8 * q;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const bool ok = 8 * i < mleft;
-            const float* __restrict__ p = src + (size_t)(8 * i) * lda + hs * BK;
-            v[2 * i] = (ok && k < K) ? ldcg4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[2 * i + 1] = (ok && k + 4 < K) ? ldcg4(p + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        };
-        auto produce_h = [&](float4 (&v)[4], int hs) {
-          const uint32_t st = g % kStages2;
-          const uint32_t stage_base = smem + st * kStage2;
-          const int h = hs & 1;
-          if (dbg_on) t0 = clock64();
-          if (h == 0 && g >= (uint32_t)kStages2) mbar_wait_relaxed(B.free0 + 8 * st, ((g / kStages2) - 1) & 1);
-          if (dbg_on) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int r = prow8 + 8 * i;
-            const uint32_t off = (uint32_t)(r * 128 + (((4 * h + q) ^ (r & 7)) * 16));
-            split_store_bf8(stage_base + off, stage_base + kATile + off, v[2 * i], v[2 * i + 1]);
-          }
-          if (h == 1) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(B.afull0 + 8 * st);          // own CTA's barrier (the follower's is relayed)
-            ++g;
-          }
-          load_h(v, hs + 2);
-          if (dbg_on) t_work += clock64() - t0;
-        };
-        float4 v0[4], v1[4];
-        load_h(v0, 0);
-        load_h(v1, 1);
-        for (int hs = 0; hs < n_halves; hs += 2) {
-          produce_h(v0, hs);
-          produce_h(v1, hs + 1);
-        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.afull0 + 8 * st);            // own CTA's barrier (the follower's is relayed)
+        load_a(v, kt + 2);
+        ++g;
+        if (dbg_on) t_work += clock64() - t0;
+      };
+      float4 v0[4], v1[4];
+      load_a(v0, 0);
+      load_a(v1, 1);
+      for (int kt = 0; kt < n_slabs; kt += 2) {
+        produce(v0, kt);
+        if (kt + 1 < n_slabs) produce(v1, kt + 1);
       }
     }
     if (dbg_on) { a.dbg[2] = t_dep; a.dbg[3] = t_wait; a.dbg[4] = t_work; }
@@ -1213,10 +1149,10 @@ __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t addr) {
 // slab), not the loads, was the bound (ncu: issue slots 53 % busy with 17 warps, tensor pipe 22 %).
 struct DwMaps {
   CUtensorMap a_hi[kDwMaxProblems], a_mid[kDwMaxProblems];   // bf16 planes [samples][features]: box (64 features, 64 samples), SWIZZLE_128B
-  CUtensorMap b[kDwMaxProblems];                             // fp32 [samples][features]: box (64 features, 4 samples), no swizzle
+  CUtensorMap b[kDwMaxProblems];                             // fp32 [samples][features]: box (64 features, 8 samples), no swizzle
 };
-constexpr int kRawSlots = 6;
-constexpr uint32_t kRawUnit = 4 * 64 * 4;                                                      // 1 KB
+constexpr int kRawSlots = 3;
+constexpr uint32_t kRawUnit = 8 * 64 * 4;                                                      // 2 KB: 8 samples x 64 features
 constexpr int kStagesD2B = 3;
 constexpr uint32_t kRawOff = kStagesD2B * kStageD2;                                             // 144 KB
 static_assert(kRawOff + 8 * kRawSlots * kRawUnit <= kStagingOff, "raw ring overlaps the epilogue staging");
@@ -1307,19 +1243,27 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
     if (rank != 0 && warp == kIssuerWarpTn && lane == 0) {
       // follower: forward "my operand tiles of slab g are in place" to the leader (see mlp_chain2_kernel)
       const uint32_t total = (uint32_t)(u_end - u_beg);
-      if (BF) issue_a(0, u_beg);
+      if (BF) {
+        issue_a(0, u_beg);
+        if (total > 1) issue_a(1, u_beg + 1);
+      }
       for (uint32_t g = 0; g < total; ++g) {
         const uint32_t st = g % NST;
         mbar_wait(B.afull0 + 8 * st, (g / NST) & 1);
         mbar_arrive_cluster(l_afull0 + 8 * st);
-        if (BF && g + 1 < total) issue_a(g + 1, u_beg + (int)g + 1);
+        if (BF && g + 2 < total) issue_a(g + 2, u_beg + (int)g + 2);     // two slabs ahead (NST = 3 stages)
       }
     }
     if (rank == 0 && warp == kIssuerWarpTn && lane == 0) {
       uint32_t g = 0;
       long long t_a = 0, t_r = 0, t_all = 0, t0 = 0;
       if (dbg_cta) t_all = clock64();
-      if (BF) issue_a(0, u_beg);
+      if (BF) {
+        // the A planes run TWO slabs ahead of the MMAs (three stages): issued one slab ahead, right before waiting for
+        // them, the whole load latency (~1 us) was exposed every slab -- 1.7 us per slab for 0.73 us of MMAs
+        issue_a(0, u_beg);
+        if (u_beg + 1 < u_end) issue_a(1, u_beg + 1);
+      }
       for (int u = u_beg; u < u_end;) {
         const int tile = u / n_slabs, s0 = u - tile * n_slabs;
         const int len = min(n_slabs - s0, u_end - u);
@@ -1352,7 +1296,7 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
           }
           mma2_commit(B.free0 + 8 * st);
           mma2_commit(B.rfull0 + 8 * (g % kRegions));
-          if (BF && u + i + 1 < u_end) issue_a(g + 1, u + i + 1);      // the A planes of the next slab
+          if (BF && u + i + 2 < u_end) issue_a(g + 2, u + i + 2);      // the A planes two slabs on (waits for MMA g - 1)
         }
         u += len;
       }
@@ -1374,68 +1318,62 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
     uint32_t g = 0;
     if constexpr (BF) {
       // ---- B only: per-warp TMA ring of raw fp32 rows of X -> bf16 hi / mid operand tile ----
-      struct Cur { int u, tile, s, h; };                       // unit = half slab h of slab s of `tile`
-      auto advance = [&](Cur& c) {
-        if (c.h == 0) { c.h = 1; return; }
-        c.h = 0;
-        ++c.u; ++c.s;
-        if (c.s == n_slabs) { c.s = 0; ++c.tile; }
-      };
+      // unit = this warp's 8 sample rows of one 64-sample slab (2 KB): one barrier wait, one TMA issue, one proxy fence
+      // and one arrival per SLAB (with 4-row half-slab units those fixed latencies, ~670 cycles per unit, made the
+      // conversion of a slab as long as its 12 MMAs although only a third of the operand elements is converted here)
       const uint32_t raw0 = smem + kRawOff + (uint32_t)pw * (kRawSlots * kRawUnit);
       const uint32_t rbar0 = smem + kRawBarOff + (uint32_t)pw * (8 * kRawSlots);
-      auto issue = [&](const Cur& c, uint32_t n) {              // lane 0: one bulk-tensor load of unit n into slot n % kRawSlots
-        if (c.u >= u_end) return;
-        const int prob = a.tile_prob[c.tile];
+      auto issue = [&](int u, uint32_t n) {                     // lane 0: one bulk-tensor load of unit n into slot n % kRawSlots
+        if (u >= u_end) return;
+        const int tile = u / n_slabs, sl = u - tile * n_slabs;
+        const int prob = a.tile_prob[tile];
         const DwProblem& P = a.p[prob];
-        const int n0 = a.tile_n[c.tile] * TN;
+        const int n0 = a.tile_n[tile] * TN;
         const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
-        const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
         const uint32_t slot = n % kRawSlots, bar = rbar0 + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kRawUnit) : "memory");
-        tma_load_2d(raw0 + slot * kRawUnit, &maps.b[prob], bar, n0 + (int)rank * h, k0);
+        tma_load_2d(raw0 + slot * kRawUnit, &maps.b[prob], bar, n0 + (int)rank * h, sl * 64 + 8 * pw);
       };
-      Cur c{u_beg, u_beg / n_slabs, u_beg % n_slabs, 0}, pf = c;
       if (lane == 0)
-        for (uint32_t n_iss = 0; n_iss < (uint32_t)kRawSlots; ++n_iss) { issue(pf, n_iss); advance(pf); }
+        for (uint32_t n_iss = 0; n_iss < (uint32_t)kRawSlots; ++n_iss) issue(u_beg + (int)n_iss, n_iss);
       const bool dbg_p = dbg_cta && tid == kConsumers;
       long long tp_raw = 0, tp_free = 0, tp_work = 0, tp0 = 0;
-      for (uint32_t n = 0; c.u < u_end; ++n) {
+      uint32_t n = 0;
+      for (int u = u_beg; u < u_end; ++u, ++n) {
         if (dbg_p) tp0 = clock64();
-        const DwProblem& P = a.p[a.tile_prob[c.tile]];
-        const int n0 = a.tile_n[c.tile] * TN;
+        const int tile = u / n_slabs, sl = u - tile * n_slabs;
+        const DwProblem& P = a.p[a.tile_prob[tile]];
+        const int n0 = a.tile_n[tile] * TN;
         const int h = min(TN, (P.N - n0 + 15) & ~15) >> 1;
         const bool in_b = 4 * bq < h && n0 + (int)rank * h + 4 * bq < P.N;
-        const int k0 = (2 * c.s + c.h) * BK + 4 * pw;
+        const int k0 = sl * 64 + 8 * pw;
         const uint32_t slot = n % kRawSlots, src = raw0 + slot * kRawUnit;
         mbar_wait_relaxed(rbar0 + 8 * slot, (n / kRawSlots) & 1);
         if (dbg_p) { const long long t1 = clock64(); tp_raw += t1 - tp0; tp0 = t1; }
-        float4 vb[2];
+        float4 vb[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int r = 2 * i + bsub;
           const float4 y = lds4(src + (uint32_t)(r * 256 + bq * 16));
           vb[i] = (k0 + r < K && in_b) ? y : make_float4(0.f, 0.f, 0.f, 0.f);   // samples beyond the count multiply as 0
         }
         __syncwarp();                                           // every lane has read the slot: it may be refilled
-        if (lane == 0) { issue(pf, n + kRawSlots); advance(pf); }
+        if (lane == 0) issue(u + kRawSlots, n + kRawSlots);
         const uint32_t st = g % NST;
         const uint32_t stage_base = smem + st * kStageD2;
         if (dbg_p) { const long long t1 = clock64(); tp_work += t1 - tp0; tp0 = t1; }
-        if (c.h == 0 && g >= (uint32_t)NST) mbar_wait_relaxed(B.free0 + 8 * st, ((g / NST) - 1) & 1);
+        if (g >= (uint32_t)NST) mbar_wait_relaxed(B.free0 + 8 * st, ((g / NST) - 1) & 1);
         if (dbg_p) { const long long t1 = clock64(); tp_free += t1 - tp0; tp0 = t1; }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const uint32_t r = (uint32_t)(32 * c.h + 4 * pw + 2 * i + bsub);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t r = (uint32_t)(8 * pw + 2 * i + bsub);
           const uint32_t off = b_blk + r * 128u + ((b_c32 ^ (r & 7u)) * 16u);
           split_store_bf4(stage_base + 2 * kATile + off, stage_base + 2 * kATile + kBHalfD2 + off, vb[i]);
         }
-        if (c.h == 1) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(B.afull0 + 8 * st);       // own CTA's barrier (the follower's is relayed)
-          ++g;
-        }
-        advance(c);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.afull0 + 8 * st);         // own CTA's barrier (the follower's is relayed)
+        ++g;
         if (dbg_p) tp_work += clock64() - tp0;
       }
       if (dbg_p) { a.dbg[2] = tp_raw; a.dbg[3] = tp_free; a.dbg[4] = tp_work; }
@@ -1599,13 +1537,14 @@ mlp_dw2_kernel(const __grid_constant__ Dw2Args a, const __grid_constant__ DwMaps
 constexpr int kBwConsumers = 512;
 constexpr int kBwIssuerWarp = kBwConsumers / 32;
 constexpr int kBwThreads = kBwConsumers + 32;
-constexpr int kBwStages = 2;
+constexpr int kBwStages = 3;
 constexpr uint32_t kBwPlane = 128 * 128;                          // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kBwStage = 4 * kBwPlane;                       // A_hi, A_mid, B_hi, B_mid (this CTA's half) = 64 KB
-constexpr uint32_t kBwStagingOff = kBwStages * kBwStage;          // 128 KB
-constexpr uint32_t kBwStagingWarp = 4096;                         // [hi 32 x 64 B | mid 32 x 64 B] or fp32 32 x 128 B
-constexpr uint32_t kBwBarOff = kBwStagingOff + 16 * kBwStagingWarp;   // 192 KB: free[2] full[2] rfull[2] rempty[2]
-constexpr uint32_t kBwCDoneOff = kBwBarOff + 8 * 8;
+constexpr uint32_t kBwStagingOff = kBwStages * kBwStage;          // 192 KB
+constexpr uint32_t kBwStagingWarp = 2048;                         // 16 columns: [hi 32 x 32 B | mid 32 x 32 B] or fp32 32 x 64 B
+constexpr uint32_t kBwBarOff = kBwStagingOff + 16 * kBwStagingWarp;   // 224 KB: free[3] full[3] rfull[2] rempty[2]
+constexpr uint32_t kBwCDoneOff = kBwBarOff + 8 * 10;
+static_assert(kBwCDoneOff + 8 * kChainMaxTiles + 16 + 256 * 4 <= 232448, "shared memory budget");
 constexpr uint32_t kBwTmemSlotOff = kBwCDoneOff + 8 * kChainMaxTiles;
 constexpr uint32_t kBwColsumOff = kBwTmemSlotOff + 16;
 constexpr uint32_t kSmemBytesBw = kBwColsumOff + 256 * 4;
@@ -1659,7 +1598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwThreads, 1)
 mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ BwMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem = smem_u32(smem_raw);
-  const uint32_t free0 = smem + kBwBarOff, full0 = free0 + 16, rfull0 = full0 + 16, rempty0 = rfull0 + 16;
+  const uint32_t free0 = smem + kBwBarOff, full0 = free0 + 8 * kBwStages, rfull0 = full0 + 8 * kBwStages, rempty0 = rfull0 + 16;
   const uint32_t cdone0 = smem + kBwCDoneOff;
   float* s_colsum = reinterpret_cast<float*>(smem_raw + kBwColsumOff);
 
@@ -1740,10 +1679,14 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
         tma2_load_2d(base + 3 * kBwPlane, &maps.b_mid[c.step], bar, c.kt * 64, brow0);
         if (dbg_cta) t_iss += clock64() - ti0;
       };
+      // operand loads run kPf slabs ahead of the MMAs.  Two (three stages) where the dependency allows it: the loads of
+      // an item's first slab wait for the epilogue of (tile, step - 1), i.e. of the item my_tiles places earlier, whose
+      // MMAs must have been ISSUED before this thread may block on it -- true two slabs ahead iff my_tiles >= 2.
+      const uint32_t kPf = my_tiles >= 2 ? 2u : 1u;
       Cursor lc;
       cur_init(lc);
-      issue(lc, 0);
-      cur_next(lc);
+      uint32_t lg = 0;
+      for (; lg < kPf && lc.w < n_items; ++lg) { issue(lc, lg); cur_next(lc); }
       uint32_t g = 0;
       for (int w = 0; w < n_items; ++w) {
         const int step = w / my_tiles;
@@ -1773,10 +1716,11 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
             mma2_commit(free0 + 8 * st);
             if (kt == n_slabs - 1) mma2_commit(rfull0 + 8 * rg);
           }
-          // operands of the next slab (its stage was read by slab g - 1, whose MMAs are queued in front of slab g's)
+          // operands kPf slabs on (their stage was read by slab g + kPf - 3, whose MMAs are queued in front of slab g's)
           if (lc.w < n_items) {
-            issue(lc, g + 1);
+            issue(lc, lg);
             cur_next(lc);
+            ++lg;
           }
         }
       }
@@ -1789,6 +1733,7 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
     const int quarter = warp & 3, cg = warp >> 2;                // TMEM lanes 32 quarter.., columns 64 cg..
     const uint32_t stg = smem + kBwStagingOff + (uint32_t)warp * kBwStagingWarp;
     const uint32_t swz64 = (uint32_t)((lane >> 1) & 3);        // SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+    const uint32_t swz32 = (uint32_t)((lane >> 2) & 1);        // SWIZZLE_32B: 16-byte chunk ^= (row / 4) % 2
     const bool dbg_on = dbg_cta && tid == 0;
     long long t_main = 0, t_epi = 0, t_fe = 0, tc0 = 0;
     for (int w = 0; w < n_items; ++w) {
@@ -1843,23 +1788,19 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) bf16_split2(v[2 * j], v[2 * j + 1], h[j], md[j]);
           if (tma_out) {
-            if ((hf & 1) == 0) {                               // first half of a 32-column block: the tile must be free
-              if (lane == 0) tma_store_wait_read();
-              __syncwarp();
-            }
-            const uint32_t row = stg + (uint32_t)lane * 64;
-            const uint32_t ch0 = (uint32_t)(2 * (hf & 1));
-            st_shared_v4u(row + (((ch0) ^ swz64) * 16), h[0], h[1], h[2], h[3]);
-            st_shared_v4u(row + (((ch0 + 1) ^ swz64) * 16), h[4], h[5], h[6], h[7]);
-            st_shared_v4u(row + 2048 + (((ch0) ^ swz64) * 16), md[0], md[1], md[2], md[3]);
-            st_shared_v4u(row + 2048 + (((ch0 + 1) ^ swz64) * 16), md[4], md[5], md[6], md[7]);
-            if (hf & 1) {
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&maps.c_hi[step], stg, n0 + c0 - 16, mr0);
-                tma_store_2d(&maps.c_mid[step], stg + 2048, n0 + c0 - 16, mr0);
-              }
+            // staging tile of this warp: [hi 32 rows x 32 B | mid 32 rows x 32 B], one TMA store per plane and half
+            if (lane == 0) tma_store_wait_read();              // (the previous half's stores have read the tile; the
+            __syncwarp();                                      //  arithmetic above ran while they did)
+            const uint32_t row = stg + (uint32_t)lane * 32;
+            st_shared_v4u(row + ((0u ^ swz32) * 16), h[0], h[1], h[2], h[3]);
+            st_shared_v4u(row + ((1u ^ swz32) * 16), h[4], h[5], h[6], h[7]);
+            st_shared_v4u(row + 1024 + ((0u ^ swz32) * 16), md[0], md[1], md[2], md[3]);
+            st_shared_v4u(row + 1024 + ((1u ^ swz32) * 16), md[4], md[5], md[6], md[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&maps.c_hi[step], stg, n0 + c0, mr0);
+              tma_store_2d(&maps.c_mid[step], stg + 1024, n0 + c0, mr0);
             }
           } else if (m < M) {
             uint4* ph = reinterpret_cast<uint4*>(S.Chi + (size_t)m * 256 + n0 + c0);
@@ -1869,19 +1810,15 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
           }
         } else {
           if (tma_out) {
-            if ((hf & 1) == 0) {
-              if (lane == 0) tma_store_wait_read();
-              __syncwarp();
-            }
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4)
-              st_shared_v4(stg + (uint32_t)(lane * 128 + (((4 * (hf & 1) + j4) ^ (lane & 7)) * 16)),
+              st_shared_v4(stg + (uint32_t)(lane * 64 + (((uint32_t)j4 ^ swz64) * 16)),
                            make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-            if (hf & 1) {
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) tma_store_2d(&maps.c32[step], stg, n0 + c0 - 16, mr0);
-            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&maps.c32[step], stg, n0 + c0, mr0);
           } else if (m < M) {
             float* __restrict__ cp = S.C + (size_t)m * S.ldc + n0 + c0;
 #pragma unroll
@@ -1906,20 +1843,6 @@ mlp_bwd_planes_kernel(const __grid_constant__ BwArgs a, const __grid_constant__ 
             }
             const uint32_t bits16 = (hf < 2 ? mw0 : mw1) >> (16 * (hf & 1));
             if (hf & 1) process_half(rb, hf, bits16); else process_half(ra, hf, bits16);
-          }
-        }
-        // an odd number of halves (N % 32 == 16) leaves a half-filled staging tile: send it
-        if ((nhalf & 1) && tma_out) {
-          const int c0 = 64 * cg + 16 * (nhalf - 1);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (planes) {
-              tma_store_2d(&maps.c_hi[step], stg, n0 + c0, mr0);
-              tma_store_2d(&maps.c_mid[step], stg + 2048, n0 + c0, mr0);
-            } else {
-              tma_store_2d(&maps.c32[step], stg, n0 + c0, mr0);
-            }
           }
         }
       }
@@ -1977,6 +1900,47 @@ split_planes_kernel(const float* __restrict__ X, int ld, int rows, int cols, uin
   }
 }
 
+// Weight gradient of a layer with a handful of out-features (the last refnet layer: 3): C[m][n] += sum_k A[k][m] B[k][n],
+// A fp32 [K][lda] (lda >= 4, m < 4), B fp32 [K][ldb].  On the tensor-core kernel these problems cost as much as a
+// 256-out-feature layer (the MMA is 256 rows tall: 2 of 16 tiles, 12 % of the kernel, for 0.3 % of the FLOPs); here one
+// thread per input feature streams B once (coalesced rows) with the A row broadcast from shared memory.
+constexpr int kDwSmallRows = 64;
+__global__ void __launch_bounds__(256)
+dw_small_kernel(const float* __restrict__ A, int lda, int M, const float* __restrict__ B, int ldb, int N,
+                float* __restrict__ C, int ldc, int K, const int* __restrict__ rows_dev) {
+  __shared__ float4 s_a[kDwSmallRows];
+  if (rows_dev) K = min(K, *rows_dev);
+  const int n = blockIdx.y * 256 + threadIdx.x;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = blockIdx.x * kDwSmallRows; k0 < K; k0 += gridDim.x * kDwSmallRows) {
+    __syncthreads();
+    if (threadIdx.x < kDwSmallRows) {
+      const int k = k0 + threadIdx.x;
+      s_a[threadIdx.x] = k < K ? *reinterpret_cast<const float4*>(A + (size_t)k * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (n < N) {
+      // 16 independent row loads in flight per thread, then the FMAs (a loop with a run-time trip count left every
+      // load's latency exposed: 0.5 us per row)
+#pragma unroll 1
+      for (int r0 = 0; r0 < kDwSmallRows && k0 + r0 < K; r0 += 16) {
+        float b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = (k0 + r0 + j < K) ? __ldg(B + (size_t)(k0 + r0 + j) * ldb + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 a4 = s_a[r0 + j];
+          acc[0] = fmaf(a4.x, b[j], acc[0]); acc[1] = fmaf(a4.y, b[j], acc[1]);
+          acc[2] = fmaf(a4.z, b[j], acc[2]); acc[3] = fmaf(a4.w, b[j], acc[3]);
+        }
+      }
+    }
+  }
+  if (n < N)
+    for (int m = 0; m < M && m < 4; ++m)
+      if (acc[m] != 0.f) atomicAdd(C + (size_t)m * ldc + n, acc[m]);
+}
+
 long long* g_dbg = nullptr;
 long long* g_dbg_dw = nullptr;
 int g_dw_sm_reserve = 0;
@@ -2005,7 +1969,8 @@ std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> g_maps;
 // (32 floats, box_rows rows), SWIZZLE_128B.  Out-of-range box elements read as zero / are not written.
 // bf16: the plane holds 2-byte elements (cols / ld in elements), box = (64 elements, box_rows rows): the same 128 bytes.
 // raw_box_cols > 0: a plain (unswizzled) box of raw_box_cols x box_rows (the raw operand ring of the weight-gradient kernel);
-// raw_box_cols < 0: a box of -raw_box_cols columns with SWIZZLE_64B (the 64-byte rows of the plane epilogue's staging tile).
+// raw_box_cols < 0: a box of -raw_box_cols columns with SWIZZLE_32B / SWIZZLE_64B (32- / 64-byte rows: the staging tiles of
+// the plane epilogue).
 int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtensorMap* out, bool bf16 = false,
             int raw_box_cols = 0) {
   auto key = std::make_tuple((const void*)plane, cols, rows, ld, box_rows, (int)bf16 + 2 * raw_box_cols);
@@ -2030,7 +1995,9 @@ int get_map(const void* plane, int cols, int rows, int ld, int box_rows, CUtenso
   CUtensorMap tm;
   CUresult r = g_encode(&tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)plane, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        raw_box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : raw_box_cols < 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        raw_box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                        : raw_box_cols < 0 ? ((-raw_box_cols) * (bf16 ? 2 : 4) == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B)
+                                           : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(fgs::g_err, sizeof(fgs::g_err), "fgs_b200: cuTensorMapEncodeTiled failed (%d) cols %d rows %d ld %d",
@@ -2084,12 +2051,12 @@ int gemm_w(int M, int N, int K, const float* A, int lda, const float* Bh, const 
 
 // The MLP chain in one launch (see mlp_chain_kernel).  steps[i]: C_i = act(A_i W_i^T + b_i) on the column
 // block [n0, n0 + 256) with pre-split weight planes Bh / Bl ([round_up(N,8)][ldb], K-major).
-int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st, bool bf16) {
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st) {
+  constexpr bool bf16 = false;
   if (M <= 0 || n_steps <= 0) return 0;
   if (n_steps > kChainMaxSteps) return fgs::fail_arg("mlp_chain: too many steps");
-  static bool configured2 = false, configured2b = false;
-  int rc = bf16 ? configure_once(mlp_chain2_kernel<true>, configured2b, "mlp_chain2 (bf16) smem attribute", kSmemBytesChain2)
-                : configure_once(mlp_chain2_kernel<false>, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
+  static bool configured2 = false;
+  int rc = configure_once(mlp_chain2_kernel, configured2, "mlp_chain2 smem attribute", kSmemBytesChain2);
   if (rc) return rc;
   // a CTA pair walks at most kChainMaxTiles 256-row tiles (one completion barrier each): larger workspaces (the host
   // only knows the CAPACITY; the sample count lives on the device) are covered by several launches over row ranges,
@@ -2125,8 +2092,7 @@ int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* row
     const int n_pair_tiles = fgs::cdiv(Mc, 2 * BM);
     int pairs_n = pairs_all;
     if (pairs_n > n_pair_tiles) pairs_n = n_pair_tiles;
-    if (bf16) mlp_chain2_kernel<true><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
-    else mlp_chain2_kernel<false><<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
+    mlp_chain2_kernel<<<2 * pairs_n, kThreadsF, kSmemBytesChain2, st>>>(a, maps);
     if ((rc = fgs::check_launch(steps[0].bias ? "mlp_chain_fwd" : "mlp_chain_bwd", st))) return rc;   // (only the forward adds biases)
   }
   return 0;
@@ -2167,13 +2133,13 @@ int mlp_bwd_planes(const BwStepHost* steps, int n_steps, int M, const int32_t* r
         if (h.N > 256 || h.n0 != 0) return fgs::fail_arg("mlp_bwd_planes: plane outputs are [rows][256]");
         s.Chi = h.Chi + (size_t)row_off * 256; s.Cmid = h.Cmid + (size_t)row_off * 256;
         if ((((uintptr_t)s.Chi | (uintptr_t)s.Cmid) & 15)) return fgs::fail_arg("mlp_bwd_planes: unaligned output planes");
-        // box 32 columns x 32 rows of 2-byte elements = 64-byte rows, SWIZZLE_64B (the staging tile's layout)
-        if ((rc = get_map(s.Chi, 256, Mc, 256, 32, &maps.c_hi[i], true, -32))) return rc;
-        if ((rc = get_map(s.Cmid, 256, Mc, 256, 32, &maps.c_mid[i], true, -32))) return rc;
+        // box 16 columns x 32 rows of 2-byte elements = 32-byte rows, SWIZZLE_32B (the staging tile's layout)
+        if ((rc = get_map(s.Chi, 256, Mc, 256, 32, &maps.c_hi[i], true, -16))) return rc;
+        if ((rc = get_map(s.Cmid, 256, Mc, 256, 32, &maps.c_mid[i], true, -16))) return rc;
       } else {
         s.C = h.C + (size_t)row_off * h.ldc;
         if ((h.ldc & 3) || (((uintptr_t)s.C) & 15)) return fgs::fail_arg("mlp_bwd_planes: fp32 output rows must be 16-byte aligned");
-        if ((rc = get_map(s.C, h.N, Mc, h.ldc, 32, &maps.c32[i]))) return rc;
+        if ((rc = get_map(s.C, h.N, Mc, h.ldc, 32, &maps.c32[i], false, -16))) return rc;   // 16 fp32 columns = 64-byte rows
       }
     }
     for (int i = n_steps; i < kChainMaxSteps; ++i) {
@@ -2197,6 +2163,16 @@ int split_planes(const float* X, int ld, int rows, int cols, uint16_t* hi, uint1
   const int grid = fgs::stream_grid((long long)rows * (ldp >> 1), 256, 8);
   split_planes_kernel<<<grid, 256, 0, st>>>(X, ld, rows, cols, hi, mid, ldp, colsum, rows_dev);
   return fgs::check_launch("split_planes", st);
+}
+
+// C[M <= 4][N] += A[K][M]^T B[K][N] in fp32 on the CUDA cores (A rows read as float4: lda % 4 == 0)
+int dw_small(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const int32_t* rows_dev, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M > 4 || (lda & 3) || (((uintptr_t)A) & 15)) return fgs::fail_arg("dw_small: M <= 4 and 16-byte aligned A rows");
+  const int gx = fgs::stream_grid(fgs::cdiv(K, kDwSmallRows), 1, 4);
+  dw_small_kernel<<<dim3(gx, fgs::cdiv(N, 256)), 256, 0, st>>>(A, lda, M, B, ldb, N, C, ldc, K, rows_dev);
+  return fgs::check_launch("mlp_dw_small", st);
 }
 
 // All weight / bias gradients of the step in one launch: C_i[M_i,N_i] += A_i[K,M_i]^T B_i[K,N_i] over the first
@@ -2246,7 +2222,7 @@ int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cu
         return fgs::fail_arg("mlp_dw (bf16): A must be given as bf16 planes (ldp % 8 == 0) and colsum must be NULL");
       if ((rc2 = get_map(h.Ahi, h.ldp, K, h.ldp, 64, &maps.a_hi[i], true))) return rc2;
       if ((rc2 = get_map(h.Amid, h.ldp, K, h.ldp, 64, &maps.a_mid[i], true))) return rc2;
-      if ((rc2 = get_map(h.B, h.ldb, K, h.ldb, 4, &maps.b[i], false, 64))) return rc2;
+      if ((rc2 = get_map(h.B, h.ldb, K, h.ldb, 8, &maps.b[i], false, 64))) return rc2;
       if (first < 0) first = i;
     }
     for (int i = 0; i < kDwMaxProblems; ++i)

@@ -33,8 +33,7 @@ struct ChainStepHost {
   const float* bias; int relu;
   const uint32_t* bits_in; uint32_t* bits_out;
 };
-// bf16: Bh / Bl are bf16 hi / mid planes (ldb in elements, % 8 == 0) and the chain runs kind::f16 (3xBF16)
-int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st, bool bf16 = false);
+int mlp_chain(const ChainStepHost* steps, int n_steps, int M, const int32_t* rows_dev, cudaStream_t st);
 
 // One weight-gradient problem of mlp_dw (gemm_tcw.cu: mlp_dw_kernel): C[M,N] += A[K,M]^T B[K,N], colsum[m] += sum_k A[k][m]
 struct DwProblemHost {
@@ -46,6 +45,9 @@ struct DwProblemHost {
 };
 // bf16: 3xBF16 operands (kind::f16, 64-sample slabs) instead of 3xTF32
 int mlp_dw(const DwProblemHost* probs, int n, int K, const int32_t* rows_dev, cudaStream_t st, bool bf16 = false);
+// C[M <= 4][N] += A[K][M]^T B[K][N], fp32 SIMT: layers with a handful of out-features (the last refnet layer)
+int dw_small(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const int32_t* rows_dev, cudaStream_t st);
 // leave n SMs free while mlp_dw runs (a data-parallel step overlaps the gradient exchange with it)
 void set_dw_sm_reserve(int n_sms);
 
