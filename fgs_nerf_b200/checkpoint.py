@@ -18,12 +18,15 @@ from .scene import Scene, mlp_dims
 
 # nn.Sequential indices of the Linear layers (model/nerf.py:125-142: Linear+ReLU, [Sequential(Linear, ReLU)] x2, Linear)
 _LIN = ("0", "2.0", "3.0", "4")
+_LIN3 = ("0", "2.0", "3")                            # the coarse stage's 3-layer refnet
 _GROUPS = ("k0", "sdf", "rgbnet", "refnet")          # order of create_optimizer_or_freeze_model's param groups
 
 
 def _mlp_items(eng):
     """(key, weight view [out,in], bias, engine layer index) in the reference's state_dict order: refnet, then rgbnet."""
     out = []
+    if hasattr(eng, "biases"):                       # coarse.CoarseStepEngine: refnet only
+        return [(f"refnet.{idx}", j) for j, idx in enumerate(_LIN3)]
     for name, base in (("refnet", 4), ("rgbnet", 0)):
         for j, idx in enumerate(_LIN):
             out.append((f"{name}.{idx}", base + j))
@@ -46,7 +49,7 @@ def model_state_dict(eng, global_step=None):
     sd["k0.grid"] = eng.k0.detach().contiguous().clone()                            # NCDHW, as the reference stores it
     for key, i in _mlp_items(eng):
         sd[key + ".weight"] = eng.weights[i].detach().clone().contiguous()
-        sd[key + ".bias"] = eng.Bt[i].detach().clone()
+        sd[key + ".bias"] = (eng.biases[i] if hasattr(eng, "biases") else eng.Bt[i]).detach().clone()
     sd["mask_cache.xyz_min"] = eng.mask_xyz_min.to(dev)
     sd["mask_cache.xyz_max"] = eng.mask_xyz_max.to(dev)
     sd["mask_cache.sdf_mask"] = eng.mask_grid.clone()

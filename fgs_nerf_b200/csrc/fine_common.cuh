@@ -119,6 +119,40 @@ __device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t& hi, ui
   mid = __byte_perm(m0, m1, 0x7632);
 }
 
+// nerf.neus_alpha_from_sdf_scatter, model/nerf.py:510-544 (cos_anneal_ratio = 1)
+__device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float gz, float vx, float vy,
+                                            float vz, float dist, float inv_s) {
+  const float tc = sum3_inner(__fmul_rn(vx, gx), __fmul_rn(vy, gy), __fmul_rn(vz, gz));
+  // -(relu(-tc*0.5+0.5)*0 + relu(-tc)*1)
+  const float r1 = __fmul_rn(fmaxf(__fadd_rn(__fmul_rn(-tc, 0.5f), 0.5f), 0.f), 0.f);
+  const float r2 = __fmul_rn(fmaxf(-tc, 0.f), 1.f);
+  const float ic = -__fadd_rn(r1, r2);
+  const float h = __fmul_rn(__fmul_rn(ic, dist), 0.5f);
+  const float nx = __fadd_rn(sdf, h), pv = __fsub_rn(sdf, h);
+  const float pc = torch_sigmoid(__fmul_rn(pv, inv_s));
+  const float nc = torch_sigmoid(__fmul_rn(nx, inv_s));
+  const float p = __fsub_rn(pc, nc);
+  const float a = __fdiv_rn(__fadd_rn(p, 1e-5f), __fadd_rn(pc, 1e-5f));
+  return fminf(fmaxf(a, 0.f), 1.f);
+}
+
+
+// normal = l2_normalize(g / (||g|| + 1e-7))   (model/nerf.py:835, :480-483)
+struct NormalCtx {
+  float gn, den, ux, uy, uz, ss, L, nx, ny, nz;
+};
+__device__ __forceinline__ NormalCtx make_normal(float gx, float gy, float gz) {
+  NormalCtx c;
+  c.gn = __fsqrt_rn(sum3_inner(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+  c.den = __fadd_rn(c.gn, 1e-7f);
+  c.ux = __fdiv_rn(gx, c.den); c.uy = __fdiv_rn(gy, c.den); c.uz = __fdiv_rn(gz, c.den);
+  c.ss = sum3_inner(__fmul_rn(c.ux, c.ux), __fmul_rn(c.uy, c.uy), __fmul_rn(c.uz, c.uz));
+  c.L = __fsqrt_rn(fmaxf(c.ss, 1.1920928955078125e-07f));
+  c.nx = __fdiv_rn(c.ux, c.L); c.ny = __fdiv_rn(c.uy, c.L); c.nz = __fdiv_rn(c.uz, c.L);
+  return c;
+}
+
+
 __device__ __forceinline__ int lanemask_lt() {
   int m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

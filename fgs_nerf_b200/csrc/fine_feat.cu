@@ -45,21 +45,6 @@ __device__ __forceinline__ Sample load_sample(const FgsFineParams& P, int s) {
   return q;
 }
 
-// normal = l2_normalize(g / (||g|| + 1e-7))   (model/nerf.py:835, :480-483)
-struct NormalCtx {
-  float gn, den, ux, uy, uz, ss, L, nx, ny, nz;
-};
-__device__ __forceinline__ NormalCtx make_normal(float gx, float gy, float gz) {
-  NormalCtx c;
-  c.gn = __fsqrt_rn(sum3_inner(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz)));
-  c.den = __fadd_rn(c.gn, 1e-7f);
-  c.ux = __fdiv_rn(gx, c.den); c.uy = __fdiv_rn(gy, c.den); c.uz = __fdiv_rn(gz, c.den);
-  c.ss = sum3_inner(__fmul_rn(c.ux, c.ux), __fmul_rn(c.uy, c.uy), __fmul_rn(c.uz, c.uz));
-  c.L = __fsqrt_rn(fmaxf(c.ss, 1.1920928955078125e-07f));
-  c.nx = __fdiv_rn(c.ux, c.L); c.ny = __fdiv_rn(c.uy, c.L); c.nz = __fdiv_rn(c.uz, c.L);
-  return c;
-}
-
 // displace_list = sorted(set(grad_feat + (1.0,))) = 0.5, 1.0, 1.5, 2.0 (model/nerf.py:843-850)
 __device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); }
 

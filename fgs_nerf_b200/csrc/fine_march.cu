@@ -205,23 +205,6 @@ __device__ __forceinline__ void sdf_and_grad(const FgsFineParams& P, const GridG
   gx = gr[2]; gy = gr[1]; gz = gr[0];
 }
 
-// nerf.neus_alpha_from_sdf_scatter, model/nerf.py:510-544 (cos_anneal_ratio = 1)
-__device__ __forceinline__ float neus_alpha(float sdf, float gx, float gy, float gz, float vx, float vy,
-                                            float vz, float dist, float inv_s) {
-  const float tc = sum3_inner(__fmul_rn(vx, gx), __fmul_rn(vy, gy), __fmul_rn(vz, gz));
-  // -(relu(-tc*0.5+0.5)*0 + relu(-tc)*1)
-  const float r1 = __fmul_rn(fmaxf(__fadd_rn(__fmul_rn(-tc, 0.5f), 0.5f), 0.f), 0.f);
-  const float r2 = __fmul_rn(fmaxf(-tc, 0.f), 1.f);
-  const float ic = -__fadd_rn(r1, r2);
-  const float h = __fmul_rn(__fmul_rn(ic, dist), 0.5f);
-  const float nx = __fadd_rn(sdf, h), pv = __fsub_rn(sdf, h);
-  const float pc = torch_sigmoid(__fmul_rn(pv, inv_s));
-  const float nc = torch_sigmoid(__fmul_rn(nx, inv_s));
-  const float p = __fsub_rn(pc, nc);
-  const float a = __fdiv_rn(__fadd_rn(p, 1e-5f), __fadd_rn(pc, 1e-5f));
-  return fminf(fmaxf(a, 0.f), 1.f);
-}
-
 // Level 1 runs as three kernels so that the expensive part is balanced over SAMPLES, not rays (rays keep
 // between 0 and ~200 samples after the MaskCache; with a warp walking one ray's step bitmap the longest rays
 // set the kernel time while 90 % of the warp slots sat empty: 85 us, sm__warps_active 11 %):
@@ -368,6 +351,38 @@ __global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant_
 }  // namespace
 
 namespace fine {
+
+// sampling + MaskCache + level-1 id arrays only (shared with the coarse stage, whose per-sample kernels differ)
+int launch_march_expand(const FgsFineParams& P, cudaStream_t st) {
+  int rc = fgs::check_cuda(cudaMemsetAsync(P.counters, 0, sizeof(int32_t) * FGS_CNT_STICKY, st),
+                           "fine counters memset");
+  if (rc) return rc;
+  fgs::prof_mark("memset", st);
+  const int grid = fgs::stream_grid(P.n_rays, kWarps, 8);
+  march_kernel<<<grid, kBlock, 0, st>>>(P);
+  if ((rc = fgs::check_launch("fine march", st))) return rc;
+  const int grid_r = fgs::cdiv(P.n_rays, kRaysPerCta);
+  const bool prescan = P.n_rays > 32768;
+  if (prescan) {
+    scan_kernel<<<1, 1024, 0, st>>>(P.cnt1, P.off1, P.n_rays, P.counters, FGS_CNT_M1, P.cap_m1, 2);
+    if ((rc = fgs::check_launch("fine scan1", st))) return rc;
+  }
+  expand1_kernel<<<grid_r, kBlock, 0, st>>>(P, prescan);
+  return fgs::check_launch("fine expand1", st);
+}
+
+// level-2 index list from the flags the weights kernel left (shared with the coarse stage)
+int launch_compact2(const FgsFineParams& P, cudaStream_t st) {
+  int rc = 0;
+  const int grid_r = fgs::cdiv(P.n_rays, kRaysPerCta);
+  const bool prescan = P.n_rays > 32768;
+  if (prescan) {
+    scan_kernel<<<1, 1024, 0, st>>>(P.cnt2, P.off2, P.n_rays, P.counters, FGS_CNT_M2, P.cap_m2, 4);
+    if ((rc = fgs::check_launch("fine scan2", st))) return rc;
+  }
+  compact2_kernel<<<grid_r, kBlock, 0, st>>>(P, prescan);
+  return fgs::check_launch("fine compact2", st);
+}
 
 int launch_march(const FgsFineParams& P, cudaStream_t st) {
   int rc = fgs::check_cuda(cudaMemsetAsync(P.counters, 0, sizeof(int32_t) * FGS_CNT_STICKY, st),

@@ -23,7 +23,7 @@ template <bool LOSS>
 __global__ void __launch_bounds__(kBlock)
 composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant__ FgsFineLoss L) {
   const int lane = lane_id();
-  double l_mse = 0., l_srgb = 0., l_ori = 0., l_ent = 0.;
+  double l_mse = 0., l_srgb = 0., l_ori = 0., l_ent = 0., l_rgbper = 0.;
   float gb7[3] = {0.f, 0.f, 0.f};          // bias gradient of the last MLP layer = column sums of dlogit
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
     const int b = P.off2[ray];
@@ -102,7 +102,14 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
       for (int k = 0; k < 3; ++k) {
         const float sr = sigm(r[k]);
         const float d_rgb = w * g_r[k] + w * g_s[k] * sr * (1.f - sr);
-        dz[k] = d_rgb * r[k] * (1.f - r[k]);
+        float d_rgb_k = d_rgb;
+        if (L.weight_rgbper > 0.f) {
+          // weight_rgbper * sum_s w.detach() * sum_c (rgb - target[ray])^2 / N   (model/nerf_training.py:311-314)
+          const float e = r[k] - L.target[3 * (size_t)ray + k];
+          d_rgb_k += L.weight_rgbper * w * 2.f * e / (float)L.n_rays_global;
+          l_rgbper += (double)w * (double)e * (double)e;
+        }
+        dz[k] = d_rgb_k * r[k] * (1.f - r[k]);
         dw += r[k] * g_r[k] + sr * g_s[k];
       }
       st4(P.dlogit + 4 * (size_t)s, make_float4(dz[0], dz[1], dz[2], 0.f));
@@ -142,6 +149,10 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
     if (l_ent != 0.) atomicAdd(L.loss_out + 1, (double)L.weight_entropy_last * l_ent);
     if (l_ori != 0.) atomicAdd(L.loss_out + 2, (double)L.weight_orientation * l_ori);
     if (l_srgb != 0.) atomicAdd(L.loss_out + 3, (double)L.sigmoid_rgb_loss * l_srgb * inv_cnt);
+  }
+  if (LOSS && L.weight_rgbper > 0.f) {            // (accumulated by every lane: reduce over the warp first)
+    const double t = warp_sum(l_rgbper);
+    if (lane == 0 && t != 0.) atomicAdd(L.loss_out + 0, (double)L.weight_rgbper * t / (double)L.n_rays_global);
   }
 }
 
@@ -254,6 +265,13 @@ int launch_composite(const FgsFineParams& P, const FgsFineLoss* L, cudaStream_t 
     composite_kernel<false><<<grid, kBlock, 0, st>>>(P, z);
   }
   return fgs::check_launch("fine composite", st);
+}
+
+// alpha2weight backward alone (shared with the coarse stage)
+int launch_weights1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t st) {
+  const int grid = fgs::stream_grid(P.n_rays, kWarps, 8);
+  weights1_bwd_kernel<<<grid, kBlock, 0, st>>>(P, g_last);
+  return fgs::check_launch("fine weights1_bwd", st);
 }
 
 int launch_level1_bwd(const FgsFineParams& P, const float* g_last, cudaStream_t st) {

@@ -262,6 +262,58 @@ tv_scatter_v4_kernel(const float* __restrict__ E, float* __restrict__ g_sdf, int
   }
 }
 
+// nerf.density_total_variation(sdf_tv) of the coarse stage (ori_tv: through autograd in the reference; here its
+// closed form): per voxel the signs of the up-to-6 masked differences it takes part in.  total_variation,
+// model/nerf.py:1212-1221: |v.diff(axis)| over pairs with both voxels in the mask.
+__global__ void __launch_bounds__(kBlock)
+l1_tv_kernel(const float* __restrict__ sdf, const unsigned char* __restrict__ mask, float* __restrict__ g_sdf, int X, int Y,
+             int Z, float scale, double* __restrict__ loss_out, double loss_scale) {
+  const long long V = (long long)X * Y * Z;
+  const long long sj = Z, si = (long long)Z * Y;
+  double lsum = 0.;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < V; idx += (long long)gridDim.x * kBlock) {
+    if (!mask[idx]) continue;
+    long long r = idx;
+    const int k = (int)(r % Z); r /= Z;
+    const int j = (int)(r % Y); r /= Y;
+    const int i = (int)r;
+    const float c = sdf[idx];
+    float acc = 0.f;
+    auto fwd = [&](long long o) {          // pair (idx, idx + o): d = sdf[idx + o] - c, this voxel gets -sign(d)
+      if (mask[idx + o]) {
+        const float d = sdf[idx + o] - c;
+        lsum += (double)fabsf(d);
+        acc -= (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+      }
+    };
+    auto bwd = [&](long long o) {          // pair (idx - o, idx): d = c - sdf[idx - o], this voxel gets +sign(d)
+      if (mask[idx - o]) {
+        const float d = c - sdf[idx - o];
+        acc += (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+      }
+    };
+    if (i + 1 < X) fwd(si);
+    if (i > 0) bwd(si);
+    if (j + 1 < Y) fwd(sj);
+    if (j > 0) bwd(sj);
+    if (k + 1 < Z) fwd(1);
+    if (k > 0) bwd(1);
+    if (acc != 0.f) g_sdf[idx] += scale * acc;
+  }
+  if (loss_out) {
+    __shared__ double s[kBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.;
+      for (int w = 0; w < kBlock / 32; ++w) t += s[w];
+      if (t != 0.) atomicAdd(loss_out, t * loss_scale);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const uint8_t* nonempty,
@@ -300,4 +352,38 @@ extern "C" int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const
   if ((rc = fgs::check_launch("smooth_tv err", st))) return rc;
   tv_scatter_kernel<<<grid, kBlock, 0, st>>>(E, g_sdf, X, Y, Z, voxel_size);
   return fgs::check_launch("smooth_tv scatter", st);
+}
+
+extern "C" int fgs_sdf_gradient_grid(const float* sdf, float* G, int X, int Y, int Z, float voxel_size, fgs_stream_t stream) {
+  FGS_REQUIRE(sdf && G && X >= 3 && Y >= 3 && Z >= 3, "sdf_gradient_grid: grid must be at least 3^3");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long V = (long long)X * Y * Z;
+  if ((Z & 3) == 0 && ((((uintptr_t)sdf | (uintptr_t)G) & 15) == 0) && (V & 3) == 0)
+    tv_grad_grid_v4_kernel<<<fgs::stream_grid(V >> 2, kBlock, 8), kBlock, 0, st>>>(sdf, G, X, Y, Z, voxel_size);
+  else
+    tv_grad_grid_kernel<<<fgs::stream_grid(V, kBlock, 8), kBlock, 0, st>>>(sdf, G, X, Y, Z, voxel_size);
+  return fgs::check_launch("sdf_gradient_grid", st);
+}
+
+extern "C" int fgs_sdf_gradient_grid_bwd(const float* g_G, float* g_sdf, int X, int Y, int Z, float voxel_size,
+                                         fgs_stream_t stream) {
+  FGS_REQUIRE(g_G && g_sdf && X >= 3 && Y >= 3 && Z >= 3, "sdf_gradient_grid_bwd: grid must be at least 3^3");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long V = (long long)X * Y * Z;
+  if ((Z & 3) == 0 && ((((uintptr_t)g_sdf | (uintptr_t)g_G) & 15) == 0) && (V & 3) == 0)
+    tv_scatter_v4_kernel<<<fgs::stream_grid(V >> 2, kBlock, 8), kBlock, 0, st>>>(g_G, g_sdf, X, Y, Z, voxel_size);
+  else
+    tv_scatter_kernel<<<fgs::stream_grid(V, kBlock, 8), kBlock, 0, st>>>(g_G, g_sdf, X, Y, Z, voxel_size);
+  return fgs::check_launch("sdf_gradient_grid_bwd", st);
+}
+
+extern "C" int fgs_l1_tv_add_grad(const float* sdf, const uint8_t* mask, float* g_sdf, int X, int Y, int Z, double weight,
+                                  double mask_count, double* loss_out, fgs_stream_t stream) {
+  FGS_REQUIRE(sdf && g_sdf && X >= 2 && Y >= 2 && Z >= 2, "l1_tv_add_grad: bad grid");
+  FGS_REQUIRE(mask != nullptr && mask_count > 0, "l1_tv_add_grad: the non-empty mask (and its count) is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long V = (long long)X * Y * Z;
+  const double s = weight / 3.0 / mask_count;
+  l1_tv_kernel<<<fgs::stream_grid(V, kBlock, 8), kBlock, 0, st>>>(sdf, mask, g_sdf, X, Y, Z, (float)s, loss_out, s);
+  return fgs::check_launch("l1_tv_add_grad", st);
 }

@@ -249,6 +249,67 @@ int launch_conv(const float* src, float* dst, int X, int Y, int Z, const float* 
   return fgs::check_launch("conv3d_replicate", st);
 }
 
+// Transpose of the convolution above (its backward with respect to the input volume).  Replicate padding = the same
+// correlation over a padded copy P[p] = src[clamp(p)], p in [-H, n + H): so g_P[p] = sum_a w[a] g_out[p - a + H] (g_out read
+// as ZERO outside the volume) = the forward kernel's loop with flipped weights over the extended domain, and
+// g_src[clamp(p)] += g_P[p].  Interior voxels receive exactly one add; only the faces fold several p onto one voxel.
+template <int K>
+__global__ void __launch_bounds__(kBlock) conv3d_replicate_bwd_kernel(const float* __restrict__ g_out, float* __restrict__ g_in,
+                                                                     int X, int Y, int Z, ConvWeights cw, int tiles_y,
+                                                                     int tiles_z) {
+  constexpr int H = K / 2;
+  constexpr int SX = CTX + 2 * H, SY = CTY + 2 * H, SZ = CTZ + 2 * H;
+  __shared__ float tile[SX * SY * SZ];
+  const int tz = blockIdx.x % tiles_z, ty = (blockIdx.x / tiles_z) % tiles_y, tx = blockIdx.x / (tiles_z * tiles_y);
+  const int x0 = tx * CTX - H, y0 = ty * CTY - H, z0 = tz * CTZ - H;          // padded coordinates of this block
+  for (int i = threadIdx.x; i < SX * SY * SZ; i += kBlock) {
+    const int lz = i % SZ, ly = (i / SZ) % SY, lx = i / (SZ * SY);
+    const int gx = x0 + lx - H, gy = y0 + ly - H, gz = z0 + lz - H;
+    const bool in = gx >= 0 && gx < X && gy >= 0 && gy < Y && gz >= 0 && gz < Z;
+    tile[i] = in ? __ldg(g_out + ((long long)gx * Y + gy) * Z + gz) : 0.f;
+  }
+  __syncthreads();
+  const int lz = threadIdx.x % CTZ, ly = threadIdx.x / CTZ;
+  float acc[CTX];
+#pragma unroll
+  for (int lx = 0; lx < CTX; ++lx) acc[lx] = 0.f;
+#pragma unroll 1
+  for (int b = 0; b < K; ++b) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      float col[CTX + K - 1];
+#pragma unroll
+      for (int i = 0; i < CTX + K - 1; ++i) col[i] = tile[(i * SY + (ly + b)) * SZ + lz + c];
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        const float w = cw.w[((K - 1 - a) * K + (K - 1 - b)) * K + (K - 1 - c)];
+#pragma unroll
+        for (int lx = 0; lx < CTX; ++lx) acc[lx] = __fmaf_rn(w, col[lx + a], acc[lx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int lx = 0; lx < CTX; ++lx) {
+    const int px = x0 + lx, py = y0 + ly, pz = z0 + lz;
+    if (px < X + H && py < Y + H && pz < Z + H && acc[lx] != 0.f) {
+      const int gx = min(max(px, 0), X - 1), gy = min(max(py, 0), Y - 1), gz = min(max(pz, 0), Z - 1);
+      atomicAdd(g_in + ((long long)gx * Y + gy) * Z + gz, acc[lx]);
+    }
+  }
+}
+
+template <int K>
+int launch_conv_bwd(const float* g_out, float* g_in, int X, int Y, int Z, const float* w, cudaStream_t st) {
+  ConvWeights cw;
+  for (int i = 0; i < K * K * K; ++i) cw.w[i] = w[i];
+  constexpr int H = K / 2;
+  const int tx = fgs::cdiv(X + 2 * H, CTX), ty = fgs::cdiv(Y + 2 * H, CTY), tz = fgs::cdiv(Z + 2 * H, CTZ);
+  const long long blocks = (long long)tx * ty * tz;
+  if (blocks > 0x7fffffffLL) return fgs::fail_arg("conv3d_replicate_bwd: volume too large");
+  conv3d_replicate_bwd_kernel<K><<<(unsigned)blocks, kBlock, 0, st>>>(g_out, g_in, X, Y, Z, cw, ty, tz);
+  return fgs::check_launch("conv3d_replicate_bwd", st);
+}
+
 }  // namespace
 
 extern "C" int fgs_conv3d_replicate(const float* src, float* dst, int X, int Y, int Z, const float* weights, int ksize,
@@ -327,4 +388,18 @@ extern "C" int fgs_gather_rays(const float* rays_o_tr, const float* rays_d_tr, c
   gather_rays_kernel<<<fgs::cdiv(4ll * n, kBlock), kBlock, 0, st>>>(rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, n_total,
                                                                     sel, n, rays_o, rays_d, viewdirs, target, bad);
   return fgs::check_launch("gather_rays", st);
+}
+
+extern "C" int fgs_conv3d_replicate_bwd(const float* g_out, float* g_in, int X, int Y, int Z, const float* weights, int ksize,
+                                        fgs_stream_t stream) {
+  FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "conv3d_replicate_bwd: sizes must be positive");
+  FGS_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "conv3d_replicate_bwd: ksize must be 1, 3, 5 or 7");
+  FGS_REQUIRE(g_out && g_in && g_out != g_in && weights, "conv3d_replicate_bwd: g_out / g_in must be distinct non-null buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ksize) {
+    case 1: return launch_conv_bwd<1>(g_out, g_in, X, Y, Z, weights, st);
+    case 3: return launch_conv_bwd<3>(g_out, g_in, X, Y, Z, weights, st);
+    case 5: return launch_conv_bwd<5>(g_out, g_in, X, Y, Z, weights, st);
+    default: return launch_conv_bwd<7>(g_out, g_in, X, Y, Z, weights, st);
+  }
 }

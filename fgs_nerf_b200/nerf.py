@@ -65,7 +65,9 @@ class _GridView:
 
 
 class nerf(nn.Module):
-    """The reference's scene model class for the FINE stage (model/nerf.py:20-941) on top of FineStepEngine: same
+    """The reference's scene model class (model/nerf.py:20-1075) on top of FineStepEngine (stage='fine') or
+    coarse.CoarseStepEngine (stage='coarse': forward_coarse, :943-1075; k0_dim 12, refnet in -> width -> width -> 3 with
+    width <= 256, any PE counts, Gaussian SDF smoothing): same
     constructor keywords, `forward(rays_o, rays_d, viewdirs, global_step=..., **render_kwargs) -> dict` with the
     reference's keys (:922-939), `sdf.grid` / `k0.grid`, `state_dict()` in the reference's layout, `scale_volume_grid`,
     `extract_geometry`'s field.  What differs, stated loudly:
@@ -73,18 +75,24 @@ class nerf(nn.Module):
         (the reference's loss.backward() has no counterpart to hook into -- the backward is fused with the loss);
       * only the fine-stage architecture the kernels are specialised for is accepted (k0_dim 12, 4 x 256 rgbnet and
         refnet, PE 5 / 3 / 8, grad_feat = sdf_feat = (0.5, 1, 1.5, 2), ref, use_viewdir, no SDF smoothing); anything
-        else raises NotImplementedError (coarse stages: SURVEY 8f row 1, not built);
+        else raises NotImplementedError (the 'geometry_searching' stage -- k0_dim 6, no MaskCache, voxel_inc -- is not built);
       * a batch may have at most `n_rays` rays (the workspace is allocated once); shorter batches are padded."""
 
     def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, nearest=False, mask_cache_path=None,
                  mask_cache_thres=1e-5, fast_color_thres=0, k0_dim=12, rgbnet_depth=4, rgbnet_width=256, ref=False,
                  refnet_width=256, refnet_depth=4, posbase_pe=5, viewbase_pe=3, refbase_pe=8, grad_feat=(), sdf_feat=(),
-                 s_ratio=2000, s_start=0.05, step_start=0, smooth_ksize=0, stage='', use_viewdir=True, stepsize=0.5,
+                 s_ratio=2000, s_start=0.05, step_start=0, smooth_ksize=0, smooth_sigma=1, stage='', use_viewdir=True, stepsize=0.5,
                  n_rays=8192, device="cuda", mask_cache=None, train_cfg=None, **kwargs):
         super().__init__()
         import numpy as np
         from .engine import FineStepEngine
         from .scene import Scene
+        if stage == "coarse":
+            self._init_coarse(xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
+                              fast_color_thres, k0_dim, ref, refnet_width, refnet_depth, posbase_pe, viewbase_pe, refbase_pe,
+                              s_ratio, s_start, step_start, smooth_ksize, smooth_sigma, use_viewdir, stepsize, n_rays, device,
+                              mask_cache, train_cfg)
+            return
         want = dict(stage="fine", ref=True, use_viewdir=True, nearest=False, k0_dim=12, rgbnet_depth=4, rgbnet_width=256,
                     refnet_depth=4, refnet_width=256, posbase_pe=5, viewbase_pe=3, refbase_pe=8,
                     grad_feat=(0.5, 1.0, 1.5, 2.0), sdf_feat=(0.5, 1.0, 1.5, 2.0), smooth_ksize=0)
@@ -136,6 +144,53 @@ class nerf(nn.Module):
         self.sdf = _GridView(lambda: self.engine.sdf)
         self.k0 = _GridView(lambda: self.engine.k0)
 
+    def _init_coarse(self, xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
+                     fast_color_thres, k0_dim, ref, refnet_width, refnet_depth, posbase_pe, viewbase_pe, refbase_pe, s_ratio,
+                     s_start, step_start, smooth_ksize, smooth_sigma, use_viewdir, stepsize, n_rays, device, mask_cache,
+                     train_cfg):
+        """stage='coarse' (model/nerf.py:47-48, 113-133, 171-172): no rgbnet, refnet on [k0 | xyz_emb | reflect_emb | normal |
+        viewdirs_emb], SDF sampled from the Gaussian-smoothed grid, sdf = 1 outside the non-empty mask."""
+        import numpy as np
+        from .coarse import CoarseStepEngine
+        from .scene import Scene
+        bad = {}
+        if not (ref and use_viewdir) or nearest:
+            bad.update(ref=ref, use_viewdir=use_viewdir, nearest=nearest)
+        if k0_dim != 12 or refnet_depth != 3 or refnet_width > 256:
+            bad.update(k0_dim=k0_dim, refnet_depth=refnet_depth, refnet_width=refnet_width)
+        if bad:
+            raise NotImplementedError(f"fgs_b200.nerf(stage='coarse'): unsupported {bad}")
+        self.stage, self.ref, self.use_viewdir = "coarse", ref, use_viewdir
+        xyz_min = torch.as_tensor(np.asarray(xyz_min), dtype=torch.float32)
+        xyz_max = torch.as_tensor(np.asarray(xyz_max), dtype=torch.float32)
+        voxel_size = ((xyz_max - xyz_min).prod() / num_voxels).pow(1 / 3)
+        world_size = ((xyz_max - xyz_min) / voxel_size).long().tolist()
+        x, y, z = np.mgrid[-1.0:1.0:world_size[0] * 1j, -1.0:1.0:world_size[1] * 1j, -1.0:1.0:world_size[2] * 1j]
+        sdf = torch.from_numpy((x ** 2 + y ** 2 + z ** 2) ** 0.5 - 1).float()[None, None, ...]       # ball init (:77-82)
+        k0 = torch.zeros([1, k0_dim, *world_size])
+        dim = (3 + 3 * refbase_pe * 2) + k0_dim + (3 + 3 * posbase_pe * 2) + 3 + (3 + 3 * viewbase_pe * 2)   # :116-122
+        ls = [nn.Linear(dim, refnet_width), nn.Linear(refnet_width, refnet_width), nn.Linear(refnet_width, 3)]
+        refnet = [(l.weight.data.clone(), l.bias.data.clone()) for l in ls]
+        if mask_cache is None:
+            if mask_cache_path is None:
+                raise ValueError("the coarse stage needs the MaskCache of the earlier stage (mask_cache_path or mask_cache)")
+            mask_cache = MaskCache(path=mask_cache_path, mask_cache_thres=mask_cache_thres)
+        self.mask_cache = mask_cache
+        cfg = dict(k0_dim=k0_dim, refnet_width=refnet_width, refnet_depth=refnet_depth, posbase_pe=posbase_pe,
+                   viewbase_pe=viewbase_pe, refbase_pe=refbase_pe, smooth_ksize=smooth_ksize, smooth_sigma=smooth_sigma,
+                   s_ratio=s_ratio, s_start=s_start, step_start=step_start, stepsize=stepsize,
+                   fast_color_thres=fast_color_thres, mask_cache_thres=mask_cache.mask_cache_thres)
+        sc = Scene(G=int(world_size[0]), xyz_min=xyz_min, xyz_max=xyz_max, voxel_size=float(voxel_size), sdf=sdf, k0=k0,
+                   mask_grid=mask_cache.sdf_mask, mask_xyz_min=mask_cache.xyz_min.cpu(), mask_xyz_max=mask_cache.xyz_max.cpu(),
+                   mask_thres=mask_cache.mask_cache_thres, cfg=cfg)
+        self.engine = CoarseStepEngine(sc, refnet, n_rays, device, cfg=cfg, train_cfg=train_cfg)
+        self.engine.num_voxels = num_voxels
+        self.engine.num_voxels_base = num_voxels_base or num_voxels
+        self.num_voxels, self.num_voxels_base = num_voxels, num_voxels_base or num_voxels
+        self.engine.set_nonempty_mask()                       # (:170-172: also sdf = 1 outside the mask)
+        self.sdf = _GridView(lambda: self.engine.sdf)
+        self.k0 = _GridView(lambda: self.engine.k0)
+
     # ---- attributes the reference's callers read ----
     @property
     def world_size(self):
@@ -159,7 +214,8 @@ class nerf(nn.Module):
 
     @torch.no_grad()
     def forward(self, rays_o, rays_d, viewdirs, global_step=20000, **render_kwargs):
-        """nerf.forward_fine (model/nerf.py:776-941).  Keys and per-key shapes of the reference's ret_dict."""
+        """nerf.forward_fine (model/nerf.py:776-941) or, for stage='coarse', nerf.forward_coarse (:943-1075).  Keys and
+        per-key shapes of the reference's ret_dict."""
         eng = self.engine
         if "stepsize" in render_kwargs and float(render_kwargs["stepsize"]) != float(eng.cfg["stepsize"]):
             raise RuntimeError(f"stepsize {render_kwargs['stepsize']} differs from the one the model was built with "
@@ -222,6 +278,13 @@ class nerf(nn.Module):
                     raise RuntimeError(f"{key}: checkpoint {tuple(sd[key].shape)} vs model {tuple(dst.shape)} "
                                        f"(scale_volume_grid first, as utils.load_checkpoint does)")
                 dst.copy_(sd[key].to(dst.device))
+        if self.stage == "coarse":
+            from .checkpoint import _LIN3
+            for j, idx in enumerate(_LIN3):
+                if f"refnet.{idx}.weight" in sd:
+                    eng.weights[j].copy_(sd[f"refnet.{idx}.weight"].to(eng.device))
+                    eng.biases[j].copy_(sd[f"refnet.{idx}.bias"].to(eng.device))
+            return
         for name, base in (("rgbnet", 0), ("refnet", 4)):
             for j, idx in enumerate(_LIN):
                 if f"{name}.{idx}.weight" in sd:

@@ -158,7 +158,10 @@ typedef struct FgsFineLoss {
   int32_t n_rays_global;        /* N of the whole (multi-GPU) batch: mse means divide by 3*this */
   int32_t has_last_ray;         /* this rank owns the global last ray (entropy quirk)          */
   float* g_alphainv_last;       /* [N] written                                                 */
-  double* loss_out;             /* [4] device                                                  */
+  double* loss_out;             /* [5] device: mse (+ rgbper), entropy, orientation, sigmoid_rgb, smooth TV */
+  float weight_rgbper;          /* coarse stage (model/nerf_training.py:311-314): per-point colour loss, added to
+                                   loss_out[0]; 0 in the fine stage */
+  float pad_;
 } FgsFineLoss;
 int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream);
 
@@ -279,6 +282,48 @@ int fgs_debug_gemm_phases(void* buf);
 /* Timing aid: run only row part `task` (0 k0, 1 encodings, 2 reflection chain, 3..6 displacement levels) of the
  * level-2 feature kernels; -1 = all (default).  Results are incomplete while it is set. */
 int fgs_debug_feat_task(int task);
+
+/* ---- coarse stage (nerf.forward_coarse, model/nerf.py:943-1075) -------------------------------
+ * Same sampling, MaskCache, NeuS alpha, compositing, loss and tensor-core MLP kernels as the fine stage; what differs:
+ *   * the SDF value is sampled from the Gaussian-smoothed grid of THIS forward (fgs_conv3d_replicate, nerf.py:969),
+ *     the gradient trilinearly from the central-difference grid of the RAW sdf (fgs_sdf_gradient_grid, :972-973);
+ *   * alpha2weight runs twice: over all level-1 samples, ONE prune `weights > fast_color_thres`, and again over the
+ *     pruned samples (:978-990) -- one in-order warp sweep per ray carries both recurrences;
+ *   * features [k0 | xyz_emb | reflect_emb | normal | viewdirs_emb] -> refnet in -> width -> width -> 3 (:992-1006);
+ *   * the loss adds weight_rgbper (FgsFineLoss; fgs_fine_loss is the loss entry of both stages); the SDF gradient
+ *     flows back through the two grids: fgs_conv3d_replicate_bwd and fgs_sdf_gradient_grid_bwd add into g_sdf.
+ * FgsFineParams supplies the shared workspaces, with these conventions: X0 holds the refnet input with row length
+ * FgsCoarse.in_ld, H the two hidden layers, dZ / hbits two slots; the refnet's three layers live in slots 0, 1 and 7
+ * of W / B / gW / gB, stored ZERO-PADDED to the kernels' 256-wide tiles: W[0] [256][in_ld], W[1] [256][256],
+ * W[7] [3][256], B[0], B[1] [256] (rows / columns beyond refnet_width stay exactly 0 under Adam: their pre-activations
+ * are 0, relu'(0) = 0, so every gradient that touches them is 0); w_split has fgs_coarse_wsplit_floats(in_ld) floats.
+ * flag1: FGS_F_ALPHA on every level-1 sample (no alpha prune in this stage), FGS_F_L2 = pruned set (reaches the
+ * refnet), FGS_F_VISIT = visited by the second recurrence before its T < 1e-3 stop; w1 / T1 are the SECOND pass's. */
+typedef struct FgsCoarse {
+  const float* sdf_smooth;   /* [X][Y][Z]    smooth_conv(sdf) of this forward                                   */
+  const float* grad_grid;    /* [3][X][Y][Z] neus_sdf_gradient('interpolate'): d/dx, d/dy, d/dz                  */
+  float* g_smooth;           /* [X][Y][Z]    gradient wrt sdf_smooth, accumulated into (caller zeroes)          */
+  float* g_grad_grid;        /* [3][X][Y][Z] gradient wrt grad_grid, accumulated into (caller zeroes)           */
+  int32_t in_dim, in_ld;     /* refnet input width (90 / 102) and row length of X0 (% 32 == 0, 32..256)          */
+  int32_t pos_pe, view_pe, ref_pe;   /* frequencies of the three encodings (5, 1, 5), each <= 10                 */
+  int32_t pad_;
+} FgsCoarse;
+int64_t fgs_coarse_wsplit_floats(int in_ld);
+int fgs_coarse_forward(const FgsFineParams* p, const FgsCoarse* c, fgs_stream_t stream);
+int fgs_coarse_backward(const FgsFineParams* p, const FgsFineLoss* l, const FgsCoarse* c, fgs_stream_t stream);
+/* G[3][X][Y][Z] = nerf.neus_sdf_gradient('interpolate') (model/nerf.py:485-494): central differences / 2 / voxel_size
+ * on interior planes, 0 on the faces; and its transpose: g_sdf += dG/dsdf^T g_G. */
+int fgs_sdf_gradient_grid(const float* sdf, float* G, int X, int Y, int Z, float voxel_size, fgs_stream_t stream);
+int fgs_sdf_gradient_grid_bwd(const float* g_G, float* g_sdf, int X, int Y, int Z, float voxel_size, fgs_stream_t stream);
+/* transpose of fgs_conv3d_replicate (k^3 weights, replicate padding): g_in += conv^T g_out.  weights: HOST [k][k][k]. */
+int fgs_conv3d_replicate_bwd(const float* g_out, float* g_in, int X, int Y, int Z, const float* weights, int ksize,
+                             fgs_stream_t stream);
+/* nerf.density_total_variation(sdf_tv) through autograd (ori_tv, model/nerf.py:430-447, total_variation :1212-1221):
+ * loss = weight * (sum over the three axes of |sdf[v+e] - sdf[v]| with both voxels in `mask`) / 3 / mask_count;
+ * g_sdf += d loss / d sdf; *loss_out += loss.  `mask` (the non-empty mask, [X][Y][Z] bytes) is required: the
+ * reference's unmasked branch divides by sdf.sum(), which no config reaches (_set_nonempty_mask always runs). */
+int fgs_l1_tv_add_grad(const float* sdf, const uint8_t* mask, float* g_sdf, int X, int Y, int Z, double weight,
+                       double mask_count, double* loss_out, fgs_stream_t stream);
 
 #ifdef __cplusplus
 }

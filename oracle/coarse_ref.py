@@ -2,7 +2,7 @@
  -- `nerf.forward_coarse` (model/nerf.py:943-1075) with the helpers it calls, and the loss lines of
 model/nerf_training.py:307-345 for a `coarse_train`-style config (weight_rgbper, ori_tv).  Same library ops as the
 reference (F.grid_sample, nn.Conv3d semantics via F.conv3d + replicate pad, F.linear, index_add_ for
-torch_scatter.segment_coo).  Only tests/ may import it; no product code path does, and no kernel exists for this row yet.
+torch_scatter.segment_coo).  Only tests/ may import it; no product code path does (the kernels it checks: fgs_nerf_b200/csrc/coarse.cu).
 
 PINNED against tests/golden/coarse_golden.npz, produced by importing the reference's real `nerf` (stage='coarse') in
 this container on the CPU (tests/golden/make_coarse_golden.py): tests/test_oracle_coarse.py.
@@ -122,6 +122,8 @@ def forward_coarse(m, native, rays_o, rays_d, viewdirs, global_step, near, steps
     viewdirs_emb = torch.cat([viewdirs, viewdirs_emb.sin(), viewdirs_emb.cos()], -1)
     viewdirs_emb = viewdirs_emb.flatten(0, -2)[ray_id]
     ref_feat = torch.cat([k0, xyz_emb, reflect_emb, normal, viewdirs_emb], dim=-1)            # :1005
+    if stages is not None:
+        stages["ref_feat"] = ref_feat.detach()
     rgb = torch.sigmoid(R.mlp(ref_feat, m.refnet))
     sigmoid_rgb = torch.sigmoid(rgb)
     rgb_marched = R.segment_sum(weights.unsqueeze(-1) * rgb, ray_id, N)

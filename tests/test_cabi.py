@@ -35,6 +35,7 @@ def test_library_exports_header_symbols():
 def test_ctypes_signatures_cover_header():
     from fgs_nerf_b200 import _lib
     import fgs_nerf_b200.engine  # noqa: F401  (registers the fused-step entry points)
+    import fgs_nerf_b200.coarse  # noqa: F401  (the coarse-stage entry points)
     undeclared = [n for n in _declared() if n not in _lib._SIGS]
     assert not undeclared, f"no ctypes signature for: {undeclared}"
 
