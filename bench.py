@@ -374,6 +374,8 @@ def run_ours(args):
     eng = engine.FineStepEngine(sc, N, dev, world_size=world, rank=rank, cap_m2_per_ray=args.cap_m2_per_ray,
                                 voxel_exchange=(args.exchange == "voxels"))
     eng.set_nonempty_mask()
+    if args.dw_sm_reserve >= 0:
+        eng.dw_sm_reserve = args.dw_sm_reserve
     if args.freeze:
         eng.lr = {k: 0.0 for k in eng.lr}
     cam = camera(args)
@@ -381,9 +383,9 @@ def run_ours(args):
     host = []
     for b in range(nb):
         rays = scene.make_rays(N=N, offset=(rank * nb + b) * N, **cam)
-        host.append([t.pin_memory() for t in rays])
-    resident = [[t.to(dev) for t in h] for h in host]
-    staging = [torch.empty_like(t, device=dev) for t in host[0]]
+        host.append(torch.stack(rays).pin_memory())       # one pinned [4, N, 3] block per batch: rays_o, rays_d, viewdirs, target
+    resident = [[t.contiguous() for t in h.to(dev)] for h in host]
+    staging = torch.empty_like(host[0], device=dev)
     loss_host = torch.empty(5, dtype=torch.float64).pin_memory()
     cnt_host = torch.empty(8, dtype=torch.int32).pin_memory()
     n_glob = N * world
@@ -393,9 +395,9 @@ def run_ours(args):
         eng.train_step(ro, rd, vd, tgt, args.global_step + i, n_rays_global=n_glob, has_last_ray=(rank == world - 1))
 
     def step_e2e(i):
-        for s, h in zip(staging, host[i % nb]):
-            s.copy_(h, non_blocking=True)
-        eng.train_step(*staging, args.global_step + i, n_rays_global=n_glob, has_last_ray=(rank == world - 1))
+        staging.copy_(host[i % nb], non_blocking=True)     # ONE host -> device copy per step (pinned source)
+        eng.train_step(staging[0], staging[1], staging[2], staging[3], args.global_step + i, n_rays_global=n_glob,
+                       has_last_ray=(rank == world - 1))
         loss_host.copy_(eng.ws["loss"], non_blocking=True)
         cnt_host.copy_(eng.ws["counters"], non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the step's loss
@@ -519,7 +521,7 @@ def run_ours(args):
                            k0_voxels_touched=touched, k0_bricks_touched=bricks, unique_voxels=uv),
             "clocks": clocks,
             "e2e": {"value": n_glob * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in host[0])),
+                    "h2d_bytes_per_step": int(host[0].numel() * 4),
                     "d2h_bytes_per_step": int(loss_host.numel() * 8 + cnt_host.numel() * 4)},
             "gpu_launches": launches, "roofline": roof, "kernels": kern,
             "kernel_sum_ms_per_step": round(step_ms_prof, 5),
@@ -628,6 +630,8 @@ def main():
     ap.add_argument("--cap-m1-per-ray", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-oracle", action="store_true")
+    ap.add_argument("--dw-sm-reserve", type=int, default=-1,
+                    help="N > 1: SMs the weight-gradient kernel leaves to the overlapped exchange (-1: the engine's default)")
     ap.add_argument("--exchange", default="bricks", choices=["bricks", "voxels"],
                     help="granularity of the data-parallel k0 gradient exchange (N > 1)")
     args = ap.parse_args()

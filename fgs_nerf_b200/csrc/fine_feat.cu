@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(kBlock)
 feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientation, int only_task) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
-  const int task = blockIdx.y;     // k0 scatter | (unused) | reflection chain | 4 displacement levels
-  if (task == kTaskPE) return;     // the encodings of xyz / viewdirs have no trainable inputs
+  __shared__ float s_acc[32 * kBlock];
+  const int task = blockIdx.y;     // k0 scatter | (unused) | reflection chain | the three tap axes | (unused)
+  if (task == kTaskPE || task == kTaskTap0 + 3) return;     // (the encodings of xyz / viewdirs have no trainable inputs)
   if (only_task >= 0 && task != only_task) return;
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
@@ -222,30 +223,67 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
         }
       }
     }
-    // ---- 24 hierarchical taps: direct (all_feat) + through the normalised gradients ----
-    if (task >= kTaskTap0 && task < kTaskTap0 + 4) {
-      const int d = task - kTaskTap0;
-      TapPair tp[3];
-      float gr[3], dG[3];
+    // ---- 24 hierarchical taps: direct (all_feat) + through the normalised gradients.  One task per AXIS: the eight
+    // taps of an axis (4 displacements x lo / hi) lie on one line -- they share the 2 x 2 footprint on the other two axes
+    // and cover at most 8 cells along the axis -- so their 64 corner contributions are summed per voxel in shared memory
+    // first (32 accumulators per thread) and leave as <= 24-32 reductions instead of 64 (shared-memory pre-aggregation of
+    // the scatter; 192 -> ~72 atomics per sample over the three axes). ----
+    if (task >= kTaskTap0 && task < kTaskTap0 + 3) {
+      const int a = task - kTaskTap0;                       // 0 = W / grid z, 1 = H / grid y, 2 = D / grid x
+      float* acc = s_acc + threadIdx.x;                     // acc[q * kBlock], q = slot * 4 + corner on the other axes
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        tp[a] = make_taps(g, iw, ih, id, a, disp_of(d));
-        gr[a] = tap_grad(row[FGS_X0_FEAT + (2 * a) * 4 + d], row[FGS_X0_FEAT + (2 * a + 1) * 4 + d],
-                         tp[a].diff, P.voxel_size);
-        dG[a] = drow[FGS_X0_AGRAD + a * 4 + d];
-      }
-      const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
-      const float inv = 1.f / (nrm + 1e-5f);
-      const float dotg = dG[0] * gr[0] + dG[1] * gr[1] + dG[2] * gr[2];
-      const float k = (nrm > 0.f) ? dotg * inv * inv / nrm : 0.f;
+      for (int q = 0; q < 32; ++q) acc[q * kBlock] = 0.f;
+      const float ia[3] = {iw, ih, id};
+      const int S[3] = {g.Z, g.Y, g.X};
+      const int b0 = (int)floorf(ia[a]) - 3;               // cells b0 .. b0 + 7 hold every corner of the eight taps
+      int o0 = 0, o1 = 0;                                   // floor corner on the two other axes (the same for all taps)
+#pragma unroll 1
+      for (int d = 0; d < 4; ++d) {
+        const float disp = disp_of(d);
+        float gr[3], dG[3], diff[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
+        for (int a2 = 0; a2 < 3; ++a2) {
+          diff[a2] = __fsub_rn(tap_clamp(ia[a2], disp, S[a2]), tap_clamp(ia[a2], -disp, S[a2]));
+          gr[a2] = tap_grad(row[FGS_X0_FEAT + (2 * a2) * 4 + d], row[FGS_X0_FEAT + (2 * a2 + 1) * 4 + d], diff[a2], P.voxel_size);
+          dG[a2] = drow[FGS_X0_AGRAD + a2 * 4 + d];
+        }
+        const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+        const float inv = 1.f / (nrm + 1e-5f);
+        const float dotg = dG[0] * gr[0] + dG[1] * gr[1] + dG[2] * gr[2];
+        const float k = (nrm > 0.f) ? dotg * inv * inv / nrm : 0.f;
         const float dgr = dG[a] * inv - k * gr[a];
-        const float df = dgr / tp[a].diff / P.voxel_size;
-        const float dlo = drow[FGS_X0_FEAT + (2 * a) * 4 + d] - df;
-        const float dhi = drow[FGS_X0_FEAT + (2 * a + 1) * 4 + d] + df;
-        tri_scatter1(P.g_sdf, tp[a].lo, g.X, g.Y, g.Z, dlo);
-        tri_scatter1(P.g_sdf, tp[a].hi, g.X, g.Y, g.Z, dhi);
+        const float df = dgr / diff[a] / P.voxel_size;
+        const float go[2] = {drow[FGS_X0_FEAT + (2 * a) * 4 + d] - df, drow[FGS_X0_FEAT + (2 * a + 1) * 4 + d] + df};
+        const TapPair tp = make_taps(g, iw, ih, id, a, disp);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const Tri& t = side ? tp.hi : tp.lo;
+          const int ai = (a == 0 ? t.x0 : a == 1 ? t.y0 : t.z0) - b0;
+          o0 = (a == 0) ? t.y0 : t.x0;
+          o1 = (a == 2) ? t.y0 : t.z0;
+          if (go[side] == 0.f) continue;
+          if (ai < 0 || ai > 6) {                           // cannot happen for points inside the bbox; stay correct anyway
+            tri_scatter1(P.g_sdf, t, g.X, g.Y, g.Z, go[side]);
+            continue;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int bit = (c >> a) & 1;
+            const int oc = (a == 0) ? (c >> 1) : (a == 1) ? ((c & 1) | ((c >> 2) << 1)) : (c & 3);
+            acc[((ai + bit) * 4 + oc) * kBlock] += __fmul_rn(t.w[c], go[side]);
+          }
+        }
+      }
+#pragma unroll 4
+      for (int q = 0; q < 32; ++q) {
+        const float v = acc[q * kBlock];
+        if (v == 0.f) continue;
+        const int line = b0 + (q >> 2), c0 = o0 + (q & 1), c1 = o1 + ((q >> 1) & 1);
+        const int x = (a == 0) ? line : c0;                 // W / grid z
+        const int y = (a == 1) ? line : (a == 0 ? c0 : c1); // H / grid y
+        const int z = (a == 2) ? line : c1;                 // D / grid x
+        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X)
+          atomicAdd(P.g_sdf + ((size_t)z * g.Y + y) * g.Z + x, v);
       }
     }
     if (task != kTaskRefl) continue;
