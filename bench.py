@@ -5,6 +5,7 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   (reference's CPU path)
     python bench.py --grid 256 --camera dtu ...               (BASELINE configs 3 / 4)
     python bench.py --mode render --grid 384 ...              (BASELINE config 5: full-image inference)
+    python bench.py --stage coarse --grid 116 --global-step 3000   (the coarse-stage iteration)
 
 Workload (BASELINE.json configs[1], the default): shiny-blender fine stage, 160^3 SDF + 12-channel feature grid,
 8192 rays per GPU per step, <= 256 post-mask samples per ray, synthetic scene of SURVEY.md 8d (random-init grids +
@@ -367,6 +368,10 @@ def run_ours(args):
             os.close(saved_stdout)
     if args.mode == "render":
         return run_render(args, world, rank, dev)
+    if args.stage == "coarse":
+        if world > 1:
+            raise SystemExit("bench.py --stage coarse: the coarse stage runs on one GPU")
+        return run_coarse(args, dev)
     from fgs_nerf_b200 import _lib, engine, scene
 
     N = args.rays
@@ -540,6 +545,90 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def run_coarse(args, dev):
+    """one coarse-stage training iteration (forward_coarse + loss incl. weight_rgbper + backward + both
+    TV terms + masked Adam) on one GPU: config/shiny_blender.py `coarse_model` / `coarse_train`, ~1.5 M voxels."""
+    import torch
+    from fgs_nerf_b200 import _lib, coarse, scene
+    N = args.rays
+    sc = scene.make_scene(G=args.grid, with_mlps=False)
+    eng = coarse.CoarseStepEngine(sc, coarse.make_refnet(), N, dev)
+    eng.set_nonempty_mask()
+    if args.freeze:
+        eng.lr = {k: 0.0 for k in eng.lr}
+    cam = camera(args)
+    nb = 4
+    host = [torch.stack(scene.make_rays(N=N, offset=b * N, **cam)).pin_memory() for b in range(nb)]
+    resident = [[t.contiguous() for t in h.to(dev)] for h in host]
+    staging = torch.empty_like(host[0], device=dev)
+    loss_host = torch.empty(6, dtype=torch.float64).pin_memory()
+    cnt_host = torch.empty(8, dtype=torch.int32).pin_memory()
+
+    def step_resident(i):
+        eng.train_step(*resident[i % nb], args.global_step + i)
+
+    def step_e2e(i):
+        staging.copy_(host[i % nb], non_blocking=True)
+        eng.train_step(staging[0], staging[1], staging[2], staging[3], args.global_step + i)
+        loss_host.copy_(eng.ws["loss"], non_blocking=True)
+        cnt_host.copy_(eng.ws["counters"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, k, i0):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i0 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    it = 0
+    for _ in range(args.warmup):
+        step_resident(it); it += 1
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    _lib.lib.fgs_reset_launch_count()
+    K = args.steps
+    ms = timed(step_resident, K, it); it += K
+    launches = int(_lib.lib.fgs_launch_count())
+    clocks = sampler.stop()
+    cnt = eng.counters()
+    for _ in range(2):
+        step_e2e(it); it += 1
+    ms_e2e = timed(step_e2e, K, it); it += K
+    torch.cuda.synchronize()
+    _lib.prof_begin()
+    for i in range(K):
+        step_resident(it + i)
+    prof = {}
+    for name, t in _lib.prof_end():
+        a = prof.setdefault(name, [0.0, 0])
+        a[0] += t; a[1] += 1
+    eng.check_overflow()
+    tot = sum(v[0] for v in prof.values()) / K
+    kern = [{"name": n, "ms_per_step": round(t / K, 5), "launches_per_step": round(c / K, 2), "share": round(t / K / tot, 4)}
+            for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])]
+    V = args.grid ** 3
+    line = {"metric": METRIC, "value": N * K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic",
+            "config": {"workload": f"shiny-blender COARSE-stage training step (forward_coarse + loss incl. weight_rgbper + bwd + "
+                                   f"smooth-grad TV + autograd SDF TV every step + masked Adam), {args.grid}^3 SDF + 12-ch k0 "
+                                   f"grid, 5^3 Gaussian SDF smoothing per forward, refnet 90-192-192-3, {N} rays/step, "
+                                   f"global_step {args.global_step}+",
+                       "stage": "coarse", "grid": args.grid, "rays_per_gpu": N, "frozen_trajectory": bool(args.freeze),
+                       "l2_policy": f"k0 + grad + Adam state = 4 x {48 * V / 1e6:.0f} MB, larger than the 126 MB L2",
+                       "samples_per_ray": {"total_len": cnt["total_len"] / N, "M1": cnt["M1"] / N, "M2": cnt["M2"] / N}},
+            "clocks": clocks,
+            "e2e": {"value": N * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 6 * 8 + 8 * 4},
+            "gpu_launches": launches, "kernels": kern, "kernel_sum_ms_per_step": round(tot, 5),
+            "loss_last": [round(float(x), 6) for x in loss_host.tolist()]}
+    print(json.dumps(line), flush=True)
+
+
 def run_render(args, world, rank, dev):
     """BASELINE config 5: full-image inference, chunks dealt round-robin to the ranks (model/utils.py:296-299)."""
     import torch
@@ -618,6 +707,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "render"])
+    ap.add_argument("--stage", default="fine", choices=["fine", "coarse"],
+                    help="coarse: one coarse-stage iteration (SURVEY 8f row 1; use --grid 116 --global-step 3000)")
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (train) / chunk size (render)")
     ap.add_argument("--camera", default="blender", choices=["blender", "dtu"])

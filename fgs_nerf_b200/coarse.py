@@ -98,6 +98,22 @@ def l1_tv_add_grad(sdf, mask, g_sdf, weight, loss_out=None):
         check(lib.fgs_l1_tv_add_grad(ptr(sdf), ptr(mask), ptr(g_sdf), X, Y, Z, float(weight), cnt, ptr(loss_out), stream()))
 
 
+def make_refnet(cfg=None, seed=790):
+    """A coarse-stage refnet with nn.Linear's default initialisation under a fixed seed (synthetic scenes / benchmarks):
+    [(W [w,in], b [w]), (W [w,w], b [w]), (W [3,w], b [3])]."""
+    c = dict(COARSE_MODEL)
+    c.update(cfg or {})
+    dim = (3 + 6 * c["refbase_pe"]) + c["k0_dim"] + (3 + 6 * c["posbase_pe"]) + 3 + (3 + 6 * c["viewbase_pe"])
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(i, o):
+        b = 1.0 / math.sqrt(i)
+        return ((torch.rand(o, i, generator=g) * 2 - 1) * b).float(), ((torch.rand(o, generator=g) * 2 - 1) * b).float()
+
+    w = c["refnet_width"]
+    return [lin(dim, w), lin(w, w), lin(w, 3)]
+
+
 class CoarseStepEngine(FineStepEngine):
     """State + workspace of the coarse-stage model (`nerf(stage='coarse')`) for batches of `n_rays` rays on one GPU.
     `refnet`: [(W [w,in], b [w]), (W [w,w], b [w]), (W [3,w], b [3])], in = 12 + PE dims + 3 (90 for the shipped
@@ -105,7 +121,7 @@ class CoarseStepEngine(FineStepEngine):
     and columns provably stay 0 under Adam: see include/fgs_b200_fine.h)."""
 
     def __init__(self, scene, refnet, n_rays, device="cuda", cfg=None, train_cfg=None, cap_m1_per_ray=192,
-                 cap_m2_per_ray=96):
+                 cap_m2_per_ray=36):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CoarseStepEngine needs a CUDA device: fgs_b200 has no CPU path")
@@ -252,6 +268,7 @@ class CoarseStepEngine(FineStepEngine):
                   "ray_id2", "X0", "H", "logit", "normal2", "rgb_marched", "sigmoid_rgb", "cum_weights", "depth",
                   "normal_marched", "counters", "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ", "dlogit_p"):
             setattr(P, k, ptr(ws[k]))
+        self._build_mask_occupancy()
         Cc = self.Cc
         # without a smoother (smooth_ksize 0) the SDF is sampled from the raw grid and its gradient lands in g_sdf directly
         Cc.sdf_smooth = ptr(self.sdf_smooth if self.smooth_ksize > 0 else self.sdf)
@@ -378,8 +395,11 @@ class CoarseStepEngine(FineStepEngine):
             mt = self._mt
             check(lib.fgs_adam_upd_multi(n, mt["p"], mt["g"], mt["m"], mt["v"], mt["n"], steps, lrs, b1, b2, eps, st))
 
-    def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, _stop_before_optimizer=False):
+    def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
+                   has_last_ray=True, _stop_before_optimizer=False):
         """One iteration of model/nerf_training.py:300-373 with a coarse_train-style config.  Asynchronous."""
+        if (n_rays_global or self.n_rays) != self.n_rays or not has_last_ray:
+            raise NotImplementedError("the coarse stage runs on one GPU (no ray sharding)")
         t = self.train_cfg
         self.forward(rays_o, rays_d, viewdirs, global_step, near, bg, _skip_composite=True)
         self.zero_grad()

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
   const int lane = lane_id();
   const GridGeo mg = make_geo(P.mask_xyz_min, P.mask_xyz_max, P.mX, P.mY, P.mZ);
   const float thres = P.mask_thres;
+  const uint32_t* __restrict__ occ = (thres > 0.f) ? P.mask_occ : nullptr;
   long long tot_steps = 0;
   int tot_m0 = 0;
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
@@ -67,8 +68,20 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
         // MaskCache.forward, model/nerf.py:1202-1209
         float iw, ih, id;
         cont_index(mg, px, py, pz, iw, ih, id);
-        const Tri t = tri_setup(iw, ih, id);
-        keep = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
+        bool gather = true;
+        if (occ) {
+          // cell of the sample; all 8 corners zero -> the trilinear value is exactly 0 < thres (thres > 0 checked by the
+          // host): no gathers.  Cells outside the grid (a model bbox larger than the mask's) take the full path.
+          const int cx = (int)floorf(iw), cy = (int)floorf(ih), cz = (int)floorf(id);
+          if (cx >= 0 && cx < mg.Z - 1 && cy >= 0 && cy < mg.Y - 1 && cz >= 0 && cz < mg.X - 1) {
+            const unsigned cell = ((unsigned)cz * (unsigned)(mg.Y - 1) + (unsigned)cy) * (unsigned)(mg.Z - 1) + (unsigned)cx;
+            gather = (__ldg(occ + (cell >> 5)) >> (cell & 31)) & 1u;
+          }
+        }
+        if (gather) {
+          const Tri t = tri_setup(iw, ih, id);
+          keep = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
+        }
       }
       const unsigned m0 = __ballot_sync(0xffffffffu, in);
       const unsigned word = __ballot_sync(0xffffffffu, keep);
@@ -348,7 +361,40 @@ __global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant_
   }
 }
 
+// one bit per cell (z0, y0, x0 = the floor corner in D, H, W order) of the MaskCache grid: any of its 8 corners non-zero
+__global__ void __launch_bounds__(kBlock)
+mask_occupancy_kernel(const float* __restrict__ grid, int D, int H, int W, uint32_t* __restrict__ occ) {
+  const long long cells = (long long)(D - 1) * (H - 1) * (W - 1);
+  for (long long c = blockIdx.x * (long long)kBlock + threadIdx.x; c < cells; c += (long long)gridDim.x * kBlock) {
+    long long r = c;
+    const int x = (int)(r % (W - 1)); r /= (W - 1);
+    const int y = (int)(r % (H - 1)); r /= (H - 1);
+    const int z = (int)r;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      any |= grid[((size_t)(z + (k >> 2)) * H + (y + ((k >> 1) & 1))) * W + (x + (k & 1))] != 0.f;
+    if (any) atomicOr(occ + (c >> 5), 1u << (c & 31));
+  }
+}
+
 }  // namespace
+
+extern "C" int64_t fgs_mask_occupancy_words(int mX, int mY, int mZ) {
+  if (mX < 2 || mY < 2 || mZ < 2) return 1;
+  return ((int64_t)(mX - 1) * (mY - 1) * (mZ - 1) + 31) / 32;
+}
+
+extern "C" int fgs_mask_occupancy(const float* mask_grid, int mX, int mY, int mZ, uint32_t* occ, fgs_stream_t stream) {
+  FGS_REQUIRE(mask_grid && occ && mX >= 2 && mY >= 2 && mZ >= 2, "mask_occupancy: grid must be at least 2^3");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t words = fgs_mask_occupancy_words(mX, mY, mZ);
+  int rc = fgs::check_cuda(cudaMemsetAsync(occ, 0, sizeof(uint32_t) * (size_t)words, st), "mask_occupancy memset");
+  if (rc) return rc;
+  const long long cells = (long long)(mX - 1) * (mY - 1) * (mZ - 1);
+  mask_occupancy_kernel<<<fgs::stream_grid(cells, kBlock, 8), kBlock, 0, st>>>(mask_grid, mX, mY, mZ, occ);
+  return fgs::check_launch("mask_occupancy", st);
+}
 
 namespace fine {
 

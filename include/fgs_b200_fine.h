@@ -138,7 +138,16 @@ typedef struct FgsFineParams {
                         kernel.  Zero-initialise it once: rows beyond the sample count are multiplied by zeros */
   uint8_t *k0_vox_flags; /* optional [X*Y*Z]: set to 1 by the backward scatter for every k0 voxel that received a
                         gradient (data-parallel exchange at voxel granularity, fgs_voxel_list); NULL = not recorded */
+  const uint32_t *mask_occ; /* optional: fgs_mask_occupancy() of mask_grid -- one bit per CELL of the MaskCache grid, set
+                        iff any of the cell's 8 corners is non-zero.  A sample in a cell whose corners are all 0
+                        interpolates to exactly 0 < mask_thres (requires mask_thres > 0), so the march kernel skips its
+                        8 gathers: the result is the same bit for bit.  NULL = always gather */
 } FgsFineParams;
+
+/* words of FgsFineParams::mask_occ for an [mX][mY][mZ] mask grid, and the kernel that fills it (re-run whenever the
+ * mask grid changes; model/nerf.py:1192-1209 builds the grid once per stage) */
+int64_t fgs_mask_occupancy_words(int mX, int mY, int mZ);
+int fgs_mask_occupancy(const float* mask_grid, int mX, int mY, int mZ, uint32_t* occ, fgs_stream_t stream);
 
 /* size of FgsFineParams::w_split in floats */
 int64_t fgs_fine_wsplit_floats(void);
@@ -193,13 +202,15 @@ int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const uint8_t* n
  * ONE call per iteration instead of ~20.  Measured on a B200 (profiles/r01_stage_ops_v2.json): the host needs 0.10 ms
  * to enqueue an iteration instead of 0.18 ms from Python; the device time of the iteration is unchanged (the step is
  * GPU-bound either way) -- this buys host headroom, not throughput.
- * Same launches, same order, same streams as the host-sequenced step:
- *   main : loss buffer clear, fgs_fine_forward (composite skipped), fgs_fine_loss, backward phase 1,
- *          smooth-gradient TV and SDF TV add-grad on their schedule, [fork] backward phase 2 (weight gradients),
- *          multi-tensor Adam of the 16 MLP tensors, [join]
- *   side : (after the fork) dense SDF Adam + gradient clear, touched-brick list, brick Adam of k0
- * `side_stream` must differ from `stream`; the two events the fork / join need live in the library (one pair per
- * process).  Everything is enqueued; nothing synchronises.
+ * Same launches and order as the host-sequenced step, all on `stream`:
+ *   loss buffer clear, fgs_fine_forward (composite skipped), fgs_fine_loss, backward phase 1 (data path + grid
+ *   scatters), smooth-gradient TV and SDF TV add-grad on their schedule, dense SDF Adam + gradient clear, unordered
+ *   touched-brick list + brick Adam of k0, backward phase 2 (weight gradients), multi-tensor Adam of the 16 MLP tensors
+ *   (which clears the gradients it consumes).
+ * (Round 1 ran the grid optimiser kernels on `side_stream` beside the weight-gradient kernel; its persistent CTAs
+ * hold every SM's shared memory, so the side stream only started when they retired and the join waited for it:
+ * 0.13 ms exposed per step.  `side_stream` is kept in the descriptor for ABI stability and is unused.)
+ * Everything is enqueued; nothing synchronises.
  * ------------------------------------------------------------------------------------ */
 typedef struct FgsFineStep {
   /* regularisers of this iteration (host decides from its schedule) */

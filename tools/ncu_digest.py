@@ -16,11 +16,15 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__inst_executed.sum", "sm__cycles_active.avg", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "launch__grid_size", "launch__block_size"]
 # launch name in the library's own per-launch timing (fgs_prof_*) for each kernel function
-LABEL = [("mlp_chain2_kernel<(bool)0>", "mlp_chain_fwd"), ("mlp_chain2_kernel<(bool)1>", "mlp_chain_bwd"), ("mlp_dw2_kernel", "mlp_dw"),
-         ("sample1_kernel", "fine level1"), ("sample1_bwd_kernel", "fine level1_bwd"), ("feat_kernel", "fine feat"),
-         ("feat_bwd_kernel", "fine feat_bwd"), ("march_kernel", "fine march"), ("composite_kernel", "fine composite"),
-         ("adam_bricks_kernel", "adam_bricks"), ("adam_dense_zero_kernel", "adam_dense_zero"), ("weights1_kernel", "fine weights1"),
-         ("weights1_bwd_kernel", "fine weights1_bwd")]
+LABEL = [("mlp_chain2_kernel", "mlp_chain_fwd"), ("mlp_bwd_planes_kernel", "mlp_chain_bwd"), ("mlp_dw2_kernel", "mlp_dw"),
+         ("dw_small_kernel", "mlp_dw_small"), ("weight_split_kernel", "weight_split"),
+         ("sample1_bwd_kernel", "fine level1_bwd"), ("sample1_kernel", "fine level1"), ("feat_bwd_kernel", "fine feat_bwd"),
+         ("feat_kernel", "fine feat"), ("march_kernel", "fine march"), ("expand1_kernel", "fine expand1"),
+         ("compact2_kernel", "fine compact2"), ("composite_kernel", "fine composite"),
+         ("adam_bricks_kernel", "adam_bricks"), ("adam_dense_zero_kernel", "adam_dense_zero"), ("adam_multi", "adam_upd_multi"),
+         ("brick_ulist_kernel", "brick_ulist"), ("weights1_bwd_kernel", "fine weights1_bwd"), ("weights1_kernel", "fine weights1"),
+         ("tv_grad_grid", "smooth_tv grad grid"), ("tv_err", "smooth_tv err"), ("tv_scatter", "smooth_tv scatter"),
+         ("tv_kernel", "total_variation_add_grad_v4")]
 
 
 def unit_scale(unit):
