@@ -144,7 +144,15 @@ __global__ void __launch_bounds__(kBlock) coarse_weights1_kernel(const __grid_co
       P.alphainv_last[ray] = T2c;
     }
   }
-  if (lane == 0 && tot_a) atomicAdd(P.counters + FGS_CNT_MA, tot_a);
+  __shared__ int s_a[kWarps];
+  if (lane == 0) s_a[threadIdx.x >> 5] = tot_a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) t += s_a[i];
+    if (t) atomicAdd(P.counters + FGS_CNT_MA, t);
+  }
 }
 
 struct Sample {

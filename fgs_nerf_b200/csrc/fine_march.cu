@@ -93,11 +93,18 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
     }
     if (lane == 0) P.cnt1[ray] = c1;
   }
-  if (lane == 0) {
-    if (tot_m0) atomicAdd(P.counters + FGS_CNT_M0, tot_m0);
-    if (tot_steps) {
-      atomicAdd((unsigned long long*)(P.counters + FGS_CNT_TOTAL_LO), (unsigned long long)tot_steps);
-    }
+  // one atomic per CTA and counter (per-warp atomics into the same two addresses serialise in L2)
+  __shared__ long long s_steps[kWarps];
+  __shared__ int s_m0[kWarps];
+  if (lane == 0) { s_steps[threadIdx.x >> 5] = tot_steps; s_m0[threadIdx.x >> 5] = tot_m0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long ts = 0;
+    int tm = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) { ts += s_steps[i]; tm += s_m0[i]; }
+    if (tm) atomicAdd(P.counters + FGS_CNT_M0, tm);
+    if (ts) atomicAdd((unsigned long long*)(P.counters + FGS_CNT_TOTAL_LO), (unsigned long long)ts);
   }
 }
 
@@ -158,7 +165,9 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
 // a contiguous range of rays, sums the counts of all rays in front of it (<= 8192 ints: 32 coalesced loads per thread),
 // scans its own (<= kRaysPerCta) counts with one warp and publishes off[ray]; the last CTA also publishes the total, the
 // device-side count and the overflow bit.  This replaces a single-CTA scan launch (12 us each, twice per forward).
-constexpr int kRaysPerCta = 64;
+constexpr int kRaysPerCta = 16;        // 512 CTAs at 8192 rays, two rays per warp (64 rays per CTA left 128 CTAs of 8 warps
+                                       // walking 8 rays each, one after the other: expand1 18 us, compact2 16 us)
+constexpr int kScanPerLane = (kRaysPerCta + 31) / 32;
 __device__ __forceinline__ void cta_scan_counts(const int* __restrict__ cnt, int* __restrict__ off, int n, int r0, int r1,
                                                 int* __restrict__ counters, int slot, int cap, int overflow_bit,
                                                 int* s_off /* [kRaysPerCta + 1] */, int* s_red /* [kWarps] */,
@@ -177,15 +186,23 @@ __device__ __forceinline__ void cta_scan_counts(const int* __restrict__ cnt, int
   if (w == 0) {
     int base = lane < kWarps ? s_red[lane] : 0;
     base = warp_sum(base);
-    // the CTA's own rays: two per lane
-    const int i0 = r0 + 2 * lane, i1 = i0 + 1;
-    const int c0 = i0 < r1 ? cnt[i0] : 0, c1 = i1 < r1 ? cnt[i1] : 0;
-    const int incl = warp_incl_scan(c0 + c1);
-    const int ex = base + incl - (c0 + c1);
-    s_off[2 * lane] = ex;
-    s_off[2 * lane + 1] = ex + c0;
-    if (i0 < r1) off[i0] = ex;
-    if (i1 < r1) off[i1] = ex + c0;
+    // the CTA's own rays: kScanPerLane consecutive rays per lane
+    int c[kScanPerLane], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerLane; ++j) {
+      const int local = lane * kScanPerLane + j, i = r0 + local;
+      c[j] = (local < kRaysPerCta && i < r1) ? cnt[i] : 0;
+      sum += c[j];
+    }
+    const int incl = warp_incl_scan(sum);
+    int run = base + incl - sum;
+#pragma unroll
+    for (int j = 0; j < kScanPerLane; ++j) {
+      const int local = lane * kScanPerLane + j, i = r0 + local;
+      if (local < kRaysPerCta) s_off[local] = run;
+      if (local < kRaysPerCta && i < r1) off[i] = run;
+      run += c[j];
+    }
     if (lane == 31) {
       s_off[kRaysPerCta] = base + incl;
       if (r1 == n) {                                   // last CTA: the total
@@ -329,7 +346,15 @@ __global__ void __launch_bounds__(kBlock) weights1_kernel(const __grid_constant_
       P.alphainv_last[ray] = Tc;
     }
   }
-  if (lane == 0 && tot_a) atomicAdd(P.counters + FGS_CNT_MA, tot_a);
+  __shared__ int s_a[kWarps];
+  if (lane == 0) s_a[threadIdx.x >> 5] = tot_a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) t += s_a[i];
+    if (t) atomicAdd(P.counters + FGS_CNT_MA, t);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) compact2_kernel(const __grid_constant__ FgsFineParams P, bool prescanned) {

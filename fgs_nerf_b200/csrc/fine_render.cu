@@ -136,23 +136,41 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
       L.g_alphainv_last[ray] = g_last;
     }
   }
-  if (LOSS && P.gB[FGS_MLP_LAYERS - 1]) {
+  // loss terms and the last layer's bias gradient: one atomic per CTA and term (8192 warps adding into the same
+  // handful of addresses serialise in L2: ~50 K same-address atomics per launch were most of this kernel's time)
+  if (LOSS) {
+    __shared__ double s_l[kWarps][5];
+    __shared__ float s_g[kWarps][3];
+    const int w = threadIdx.x >> 5;
+    const double t_per = (L.weight_rgbper > 0.f) ? warp_sum(l_rgbper) : 0.;     // accumulated by every lane
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float t = warp_sum(gb7[k]);
-      if (lane == 0 && t != 0.f) atomicAdd(P.gB[FGS_MLP_LAYERS - 1] + k, t);
+    for (int k = 0; k < 3; ++k) gb7[k] = warp_sum(gb7[k]);
+    if (lane == 0) {
+      s_l[w][0] = l_mse; s_l[w][1] = l_ent; s_l[w][2] = l_ori; s_l[w][3] = l_srgb; s_l[w][4] = t_per;
+      s_g[w][0] = gb7[0]; s_g[w][1] = gb7[1]; s_g[w][2] = gb7[2];
     }
-  }
-  if (LOSS && lane == 0) {
-    const double inv_cnt = 1. / (3. * (double)L.n_rays_global);
-    if (l_mse != 0.) atomicAdd(L.loss_out + 0, (double)L.weight_main * l_mse * inv_cnt);
-    if (l_ent != 0.) atomicAdd(L.loss_out + 1, (double)L.weight_entropy_last * l_ent);
-    if (l_ori != 0.) atomicAdd(L.loss_out + 2, (double)L.weight_orientation * l_ori);
-    if (l_srgb != 0.) atomicAdd(L.loss_out + 3, (double)L.sigmoid_rgb_loss * l_srgb * inv_cnt);
-  }
-  if (LOSS && L.weight_rgbper > 0.f) {            // (accumulated by every lane: reduce over the warp first)
-    const double t = warp_sum(l_rgbper);
-    if (lane == 0 && t != 0.) atomicAdd(L.loss_out + 0, (double)L.weight_rgbper * t / (double)L.n_rays_global);
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int k = threadIdx.x;
+      if (k < 5) {
+        double t = 0.;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) t += s_l[i][k];
+        const double inv_cnt = 1. / (3. * (double)L.n_rays_global);
+        if (t != 0.) {
+          if (k == 0) atomicAdd(L.loss_out + 0, (double)L.weight_main * t * inv_cnt);
+          else if (k == 1) atomicAdd(L.loss_out + 1, (double)L.weight_entropy_last * t);
+          else if (k == 2) atomicAdd(L.loss_out + 2, (double)L.weight_orientation * t);
+          else if (k == 3) atomicAdd(L.loss_out + 3, (double)L.sigmoid_rgb_loss * t * inv_cnt);
+          else atomicAdd(L.loss_out + 0, (double)L.weight_rgbper * t / (double)L.n_rays_global);
+        }
+      } else if (P.gB[FGS_MLP_LAYERS - 1]) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) t += s_g[i][k - 5];
+        if (t != 0.f) atomicAdd(P.gB[FGS_MLP_LAYERS - 1] + (k - 5), t);
+      }
+    }
   }
 }
 

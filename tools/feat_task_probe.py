@@ -12,7 +12,7 @@ eng.set_nonempty_mask()
 for i in range(3):
     eng.train_step(ro, rd, vd, tgt, 5000 + i)
 torch.cuda.synchronize()
-names = ["k0", "encodings", "reflection", "taps d=0.5", "taps d=1.0", "taps d=1.5", "taps d=2.0", "all"]
+names = ["k0", "encodings", "reflection", "taps d=0.5 | bwd axis z", "taps d=1.0 | bwd axis y", "taps d=1.5 | bwd axis x", "taps d=2.0 | bwd -", "all"]
 for task in list(range(7)) + [-1]:
     lib.fgs_debug_feat_task(task)
     acc = {}
@@ -26,5 +26,5 @@ for task in list(range(7)) + [-1]:
                 acc.setdefault(n, []).append(ms)
         eng._grads_clean = False
         eng.zero_grad()
-    print(f"{names[task]:12s} feat {1e3*min(acc['fine feat']):6.1f} us   feat_bwd {1e3*min(acc['fine feat_bwd']):6.1f} us   (M2 = {eng.counters()['M2']})")
+    print(f"{names[task]:26s} feat {1e3*min(acc['fine feat']):6.1f} us   feat_bwd {1e3*min(acc['fine feat_bwd']):6.1f} us   (M2 = {eng.counters()['M2']})")
 lib.fgs_debug_feat_task(-1)
