@@ -49,7 +49,9 @@ __device__ __forceinline__ Sample load_sample(const FgsFineParams& P, int s) {
 __device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); }
 
 // independent parts of a level-2 row (blockIdx.y of feat_kernel / feat_bwd_kernel)
-constexpr int kTaskK0 = 0, kTaskPE = 1, kTaskRefl = 2, kTaskTap0 = 3, kNumTasks = 7;
+// forward: k0 | xyz / view encodings | reflection chain | 4 displacement levels
+// backward: k0 scatter | - | reflection chain | (tap axis, displacement pair) x 6
+constexpr int kTaskK0 = 0, kTaskPE = 1, kTaskRefl = 2, kTaskTap0 = 3, kNumTasks = 7, kNumTasksBwd = 9;
 
 __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P, int only_task) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ Fg
 #pragma unroll
     for (int c = FGS_X0_DIM; c < FGS_X0_LD; ++c) row[c] = 0.f;
     // ---- normal, reflection direction and its encoding (model/nerf.py:835, 879-882) ----
+    // (one task: splitting the 24 sincosf over three per-component tasks made the kernel slower, 47 -> 56 us -- every
+    // extra task repeats the sample's address chain, and the kernel is bound by that, not by the longest task)
     const NormalCtx nc = make_normal(gx, gy, gz);
     const float dot = sum3_inner(__fmul_rn(v[0], nc.nx), __fmul_rn(v[1], nc.ny), __fmul_rn(v[2], nc.nz));
     const float n3[3] = {nc.nx, nc.ny, nc.nz};
@@ -190,7 +194,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
   __shared__ float s_acc[32 * kBlock];
   const int task = blockIdx.y;     // k0 scatter | (unused) | reflection chain | the three tap axes | (unused)
-  if (task == kTaskPE || task == kTaskTap0 + 3) return;     // (the encodings of xyz / viewdirs have no trainable inputs)
+  if (task == kTaskPE) return;     // (the encodings of xyz / viewdirs have no trainable inputs)
   if (only_task >= 0 && task != only_task) return;
   for (int s = blockIdx.x * kBlock + threadIdx.x; s < M2; s += gridDim.x * kBlock) {
     const Sample q = load_sample(P, s);
@@ -226,10 +230,12 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
     // ---- 24 hierarchical taps: direct (all_feat) + through the normalised gradients.  One task per AXIS: the eight
     // taps of an axis (4 displacements x lo / hi) lie on one line -- they share the 2 x 2 footprint on the other two axes
     // and cover at most 8 cells along the axis -- so their 64 corner contributions are summed per voxel in shared memory
-    // first (32 accumulators per thread) and leave as <= 24-32 reductions instead of 64 (shared-memory pre-aggregation of
-    // the scatter; 192 -> ~72 atomics per sample over the three axes). ----
-    if (task >= kTaskTap0 && task < kTaskTap0 + 3) {
-      const int a = task - kTaskTap0;                       // 0 = W / grid z, 1 = H / grid y, 2 = D / grid x
+    // first (32 accumulators per thread) before the reductions (shared-memory pre-aggregation of the scatter).  Two tasks
+    // per axis (displacements {0.5, 1.0} and {1.5, 2.0}: 32 corner contributions each): three axis-wide tasks left the
+    // kernel with 4 K long-running warps, 22-26 us per task; 192 -> ~100 atomics per sample over the six tasks. ----
+    if (task >= kTaskTap0 && task < kTaskTap0 + 6) {
+      const int a = (task - kTaskTap0) >> 1;                // 0 = W / grid z, 1 = H / grid y, 2 = D / grid x
+      const int d_begin = ((task - kTaskTap0) & 1) * 2;     // displacements {0.5, 1.0} or {1.5, 2.0}
       float* acc = s_acc + threadIdx.x;                     // acc[q * kBlock], q = slot * 4 + corner on the other axes
 #pragma unroll
       for (int q = 0; q < 32; ++q) acc[q * kBlock] = 0.f;
@@ -238,7 +244,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
       const int b0 = (int)floorf(ia[a]) - 3;               // cells b0 .. b0 + 7 hold every corner of the eight taps
       int o0 = 0, o1 = 0;                                   // floor corner on the two other axes (the same for all taps)
 #pragma unroll 1
-      for (int d = 0; d < 4; ++d) {
+      for (int d = d_begin; d < d_begin + 2; ++d) {
         const float disp = disp_of(d);
         float gr[3], dG[3], diff[3];
 #pragma unroll
@@ -375,7 +381,7 @@ int launch_feat(const FgsFineParams& P, cudaStream_t st) {
 
 int launch_feat_bwd(const FgsFineParams& P, float weight_orientation, cudaStream_t st) {
   const int grid = fgs::stream_grid(P.cap_m2, kBlock, 4);
-  feat_bwd_kernel<<<dim3(grid, kNumTasks), kBlock, 0, st>>>(P, weight_orientation, g_only_task);
+  feat_bwd_kernel<<<dim3(grid, kNumTasksBwd), kBlock, 0, st>>>(P, weight_orientation, g_only_task);
   return fgs::check_launch("fine feat_bwd", st);
 }
 

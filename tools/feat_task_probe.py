@@ -12,8 +12,8 @@ eng.set_nonempty_mask()
 for i in range(3):
     eng.train_step(ro, rd, vd, tgt, 5000 + i)
 torch.cuda.synchronize()
-names = ["k0", "encodings", "reflection", "taps d=0.5 | bwd axis z", "taps d=1.0 | bwd axis y", "taps d=1.5 | bwd axis x", "taps d=2.0 | bwd -", "all"]
-for task in list(range(7)) + [-1]:
+names = ["k0 | bwd k0", "encodings | bwd -", "reflection | bwd reflection", "taps d=0.5 | bwd z {0.5,1}", "taps d=1.0 | bwd z {1.5,2}", "taps d=1.5 | bwd y {0.5,1}", "taps d=2.0 | bwd y {1.5,2}", "- | bwd x {0.5,1}", "- | bwd x {1.5,2}", "all"]
+for task in list(range(9)) + [-1]:
     lib.fgs_debug_feat_task(task)
     acc = {}
     for rep in range(5):
