@@ -249,85 +249,112 @@ adam_dense_zero_kernel(float* __restrict__ param, float* __restrict__ grad, floa
   }
 }
 
-// touched-brick list in ASCENDING brick order (deterministic, identical on every rank that holds the
-// same flags): single CTA, each thread counts a contiguous run of flags, block scan, ordered write;
-// the flags are cleared on the way.  list[0] = count, list[1..] = brick ids.
+// touched-brick list in ASCENDING brick order (deterministic, identical on every rank that holds the same flags); the
+// flags are cleared on the way.  list[0] = count, list[1..] = brick ids, list[1 + n_bricks ..] = per-CTA counts (scratch).
+// Two launches over chunks of 4096 flags (a thread owns 16 consecutive flags = one 16-byte load): brick_count_kernel
+// counts per chunk, brick_fill_kernel sums the counts of the chunks in front of its own (<= a few hundred values) and
+// writes its ids in order.  (The first version was ONE CTA walking all flags in passes of 16 K: 50 us at 160^3 and
+// 110 us at 256^3 -- twice per data-parallel step since the SDF gradient also travels as bricks.)
 constexpr int kListThreads = 256;
-// (256 threads, <= 40 registers: the CTA fits next to a resident tensor-core CTA when the optimiser runs on a side stream)
+constexpr int kListRun = 16;
+constexpr int kListChunk = kListThreads * kListRun;
+
+// the thread's 16 flags as 4 words with bit 8 j + 7 of word i set <=> flag 4 i + j nonzero; returns the count
+__device__ __forceinline__ int list_load_run(const unsigned char* __restrict__ flags, int beg, int n_bricks, bool vec,
+                                             uint32_t (&m)[4]) {
+  if (vec && beg + kListRun <= n_bricks) {
+    const uint4 v = *reinterpret_cast<const uint4*>(flags + beg);
+    m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = beg + 4 * i + j;
+        if (b < n_bricks) x |= (uint32_t)flags[b] << (8 * j);
+      }
+      m[i] = x;
+    }
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = ((((m[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m[i]) & 0x80808080u);
+    cnt += __popc(m[i]);
+  }
+  return cnt;
+}
+
 __global__ void __launch_bounds__(kListThreads)
-brick_list_kernel(unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ list) {
+brick_count_kernel(const unsigned char* __restrict__ flags, int n_bricks, int* __restrict__ counts) {
+  __shared__ int s_warp[kListThreads / 32];
+  const bool vec = (((uintptr_t)flags) & 15) == 0;
+  uint32_t m[4];
+  int cnt = list_load_run(flags, blockIdx.x * kListChunk + threadIdx.x * kListRun, n_bricks, vec, m);
+  cnt = warp_sum(cnt);
+  if (lane_id() == 0) s_warp[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kListThreads / 32; ++i) t += s_warp[i];
+    counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kListThreads)
+brick_fill_kernel(unsigned char* __restrict__ flags, int n_bricks, const int* __restrict__ counts, int* __restrict__ list) {
   __shared__ int s_warp[kListThreads / 32];
   __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5;
+  const int w = threadIdx.x >> 5, lane = lane_id();
   const bool vec = (((uintptr_t)flags) & 15) == 0;
-  // passes of 256 threads x 64 flags; a thread's run is read as four 16-byte words, all loads in flight
-  // (the byte-by-byte dependent loop took 23 us for 64 K flags)
-  for (int base = 0; base < n_bricks; base += kListThreads * 64) {
-    const int beg = base + threadIdx.x * 64;
-    uint32_t m[16];                                   // bit 8 j + 7 of word i set <=> flag 4 i + j nonzero
-    const bool full = vec && beg + 64 <= n_bricks;
-    if (full) {
-      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(flags + beg);
+  const int beg = blockIdx.x * kListChunk + threadIdx.x * kListRun;
+  uint32_t m[4];
+  const int cnt = list_load_run(flags, beg, n_bricks, vec, m);
+  // ids in front of this chunk
+  int part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += kListThreads) part += counts[i];
+  part = warp_sum(part);
+  const int incl = warp_incl_scan(cnt);
+  __syncthreads();
+  if (lane == 0) s_warp[w] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 v = src[q];
-        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int b = beg + 4 * i + j;
-          if (b < n_bricks) x |= (uint32_t)flags[b] << (8 * j);
-        }
-        m[i] = x;
-      }
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      m[i] = ((((m[i] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m[i]) & 0x80808080u);
-      cnt += __popc(m[i]);
-    }
-    const int incl = warp_incl_scan(cnt);
-    const int carry = s_carry;                        // total of the previous passes (rewritten below by warp 0)
-    if (lane_id() == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      const int v = lane_id() < kListThreads / 32 ? s_warp[lane_id()] : 0;
-      const int sc = warp_incl_scan(v);
-      if (lane_id() < kListThreads / 32) s_warp[lane_id()] = sc - v;
-      __syncwarp();
-      if (lane_id() == 31) s_carry = carry + sc;
-    }
-    __syncthreads();
-    if (cnt) {
-      int o = 1 + carry + incl - cnt + s_warp[w];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        uint32_t x = m[i];
-        while (x) {
-          const int bit = __ffs(x) - 1;               // 7, 15, 23 or 31
-          x &= x - 1;
-          list[o++] = beg + 4 * i + (bit >> 3);
-        }
-      }
-      if (full) {
-        uint4* __restrict__ dst = reinterpret_cast<uint4*>(flags + beg);
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = z;
-      } else {
-        for (int b = beg; b < min(beg + 64, n_bricks); ++b) flags[b] = 0;
-      }
-    }
-    __syncthreads();                                  // s_warp / s_carry are reused by the next pass
+    for (int i = 0; i < kListThreads / 32; ++i) t += s_warp[i];
+    s_carry = t;
   }
-  if (threadIdx.x == 0) list[0] = s_carry;
+  __syncthreads();
+  const int carry = s_carry;
+  __syncthreads();
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const int v = lane < kListThreads / 32 ? s_warp[lane] : 0;
+    const int sc = warp_incl_scan(v);
+    if (lane < kListThreads / 32) s_warp[lane] = sc - v;
+    if (lane == 31 && blockIdx.x == gridDim.x - 1) list[0] = carry + sc;      // last chunk: the total
+  }
+  __syncthreads();
+  if (cnt) {
+    int o = 1 + carry + incl - cnt + s_warp[w];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t x = m[i];
+      while (x) {
+        const int bit = __ffs(x) - 1;               // 7, 15, 23 or 31
+        x &= x - 1;
+        list[o++] = beg + 4 * i + (bit >> 3);
+      }
+    }
+    if (vec && beg + kListRun <= n_bricks) {
+      *reinterpret_cast<uint4*>(flags + beg) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int b = beg; b < min(beg + kListRun, n_bricks); ++b) flags[b] = 0;
+    }
+  }
 }
 
 // gather / scatter of listed k0 gradient bricks (768 floats each, channels-last [X][Y][Z][12]) to and
@@ -355,6 +382,31 @@ brick_copy_kernel(float* __restrict__ grid, float* __restrict__ compact, const i
       if (PACK) st4(c + 4 * q, ok ? ld4(grid + off) : z4);
       else if (ok) st4(grid + off, ld4(c + 4 * q));
     }
+  }
+}
+
+// the same for a single-channel grid [X][Y][Z] (the SDF gradient): 64 floats per brick, 16 rows of one float4; two bricks
+// per warp
+template <bool PACK>
+__global__ void __launch_bounds__(kBlock)
+brick_copy1_kernel(float* __restrict__ grid, float* __restrict__ compact, const int* __restrict__ list, int max_bricks,
+                   int X, int Y, int Z) {
+  const int nbY = (Y + 3) >> 2, nbZ = (Z + 3) >> 2;
+  const int lane = lane_id(), half = lane >> 4, row = lane & 15;
+  const int wpb = kBlock / 32;
+  const int count = min(list[0], max_bricks);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e0 = 2 * (blockIdx.x * wpb + (threadIdx.x >> 5)); e0 < count; e0 += 2 * gridDim.x * wpb) {
+    const int e = e0 + half;
+    if (e >= count) continue;
+    const int br = list[1 + e];
+    const int bz = br % nbZ, by = (br / nbZ) % nbY, bx = br / (nbZ * nbY);
+    const int x = 4 * bx + (row >> 2), y = 4 * by + (row & 3);
+    const bool ok = x < X && y < Y;
+    const size_t off = ((size_t)x * Y + y) * Z + 4 * bz;
+    float* __restrict__ c = compact + (size_t)e * 64 + 4 * row;
+    if (PACK) st4(c, ok ? ld4(grid + off) : z4);
+    else if (ok) st4(grid + off, ld4(c));
   }
 }
 
@@ -675,7 +727,8 @@ int fgs_adam_upd_zero_grad(float* param, float* grad, float* exp_avg, float* exp
 }
 
 int64_t fgs_brick_list_ints(int X, int Y, int Z) {
-  return 1 + (int64_t)((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
+  const int64_t nb = (int64_t)((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
+  return 1 + nb + (nb + kListChunk - 1) / kListChunk;       // count, ids, per-chunk counts (scratch)
 }
 
 // brick_flags -> brick_list (count + ids), flags cleared
@@ -683,8 +736,14 @@ int fgs_brick_list(uint8_t* brick_flags, int X, int Y, int Z, int32_t* brick_lis
   FGS_REQUIRE(X > 0 && Y > 0 && Z > 0, "bad grid size");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_bricks = ((X + 3) >> 2) * ((Y + 3) >> 2) * ((Z + 3) >> 2);
-  FGS_PREFER_MAX_SHARED(brick_list_kernel);
-  brick_list_kernel<<<1, kListThreads, 0, st>>>(brick_flags, n_bricks, brick_list);
+  FGS_PREFER_MAX_SHARED(brick_count_kernel);
+  FGS_PREFER_MAX_SHARED(brick_fill_kernel);
+  const int chunks = fgs::cdiv(n_bricks, kListChunk);
+  int* counts = brick_list + 1 + n_bricks;
+  brick_count_kernel<<<chunks, kListThreads, 0, st>>>(brick_flags, n_bricks, counts);
+  int rc = fgs::check_launch("brick_list", st);
+  if (rc) return rc;
+  brick_fill_kernel<<<chunks, kListThreads, 0, st>>>(brick_flags, n_bricks, counts, brick_list);
   return fgs::check_launch("brick_list", st);
 }
 
@@ -749,9 +808,18 @@ int fgs_voxel_copy(float* grid, float* compact, const int32_t* voxel_list, int m
 
 int fgs_brick_copy(float* grid, float* compact, const int32_t* brick_list, int max_bricks, int X, int Y, int Z,
                    int channels, int pack, fgs_stream_t stream) {
-  FGS_REQUIRE(channels == 12 && X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0, "brick copy: 12-channel grid, Z % 4 == 0");
+  FGS_REQUIRE((channels == 12 || channels == 1) && X > 0 && Y > 0 && Z > 0 && (Z % 4) == 0,
+              "brick copy: 12-channel (channels-last) or single-channel grid, Z % 4 == 0");
   if (max_bricks <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (channels == 1) {
+    const int grid1 = fgs::stream_grid((max_bricks + 1) / 2, kBlock / 32, 8);
+    FGS_PREFER_MAX_SHARED(brick_copy1_kernel<true>);
+    FGS_PREFER_MAX_SHARED(brick_copy1_kernel<false>);
+    if (pack) brick_copy1_kernel<true><<<grid1, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
+    else brick_copy1_kernel<false><<<grid1, kBlock, 0, st>>>(grid, compact, brick_list, max_bricks, X, Y, Z);
+    return fgs::check_launch(pack ? "brick_pack" : "brick_unpack", st);
+  }
   const int grid_dim = fgs::stream_grid(max_bricks, kBlock / 32, 8);
   FGS_PREFER_MAX_SHARED(brick_copy_kernel<true>);
   FGS_PREFER_MAX_SHARED(brick_copy_kernel<false>);

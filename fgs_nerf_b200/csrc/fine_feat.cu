@@ -269,7 +269,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
           o1 = (a == 2) ? t.y0 : t.z0;
           if (go[side] == 0.f) continue;
           if (ai < 0 || ai > 6) {                           // cannot happen for points inside the bbox; stay correct anyway
-            tri_scatter1(P.g_sdf, t, g.X, g.Y, g.Z, go[side]);
+            tri_scatter1_flag(P.g_sdf, P.sdf_brick_flags, t, g.X, g.Y, g.Z, go[side]);
             continue;
           }
 #pragma unroll
@@ -280,6 +280,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
           }
         }
       }
+      int last_brick = -1;
 #pragma unroll 4
       for (int q = 0; q < 32; ++q) {
         const float v = acc[q * kBlock];
@@ -288,8 +289,14 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
         const int x = (a == 0) ? line : c0;                 // W / grid z
         const int y = (a == 1) ? line : (a == 0 ? c0 : c1); // H / grid y
         const int z = (a == 2) ? line : c1;                 // D / grid x
-        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X)
+        if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
           atomicAdd(P.g_sdf + ((size_t)z * g.Y + y) * g.Z + x, v);
+          if (P.sdf_brick_flags) {
+            const int b = ((z >> 2) * ((g.Y + 3) >> 2) + (y >> 2)) * ((g.Z + 3) >> 2) + (x >> 2);
+            if (b != last_brick) P.sdf_brick_flags[b] = 1;
+            last_brick = b;
+          }
+        }
       }
     }
     if (task != kTaskRefl) continue;

@@ -257,15 +257,15 @@ __global__ void __launch_bounds__(kBlock) sample1_bwd_kernel(const __grid_consta
     float px, py, pz, iw, ih, id;
     ray_point(r, P.stepdist, P.step_id1[idx], px, py, pz);
     cont_index(g, px, py, pz, iw, ih, id);
-    if (d_sdf != 0.f) tri_scatter1(P.g_sdf, tri_setup(iw, ih, id), g.X, g.Y, g.Z, d_sdf);
+    if (d_sdf != 0.f) tri_scatter1_flag(P.g_sdf, P.sdf_brick_flags, tri_setup(iw, ih, id), g.X, g.Y, g.Z, d_sdf);
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
       const float dgr = d_g[2 - ax];  // axis 0 = z, 1 = y, 2 = x
       if (dgr == 0.f) continue;
       const TapPair tp = make_taps(g, iw, ih, id, ax, 1.0f);
       const float df = dgr / tp.diff / P.voxel_size;
-      tri_scatter1(P.g_sdf, tp.lo, g.X, g.Y, g.Z, -df);
-      tri_scatter1(P.g_sdf, tp.hi, g.X, g.Y, g.Z, df);
+      tri_scatter1_flag(P.g_sdf, P.sdf_brick_flags, tp.lo, g.X, g.Y, g.Z, -df);
+      tri_scatter1_flag(P.g_sdf, P.sdf_brick_flags, tp.hi, g.X, g.Y, g.Z, df);
     }
   }
 }

@@ -110,6 +110,25 @@ __device__ __forceinline__ void tri_scatter1(float* __restrict__ g, const Tri& t
   }
 }
 
+// the same scatter, also marking the 4^3 bricks it touches (flags may be NULL; plain byte stores of 1)
+__device__ __forceinline__ void tri_scatter1_flag(float* __restrict__ g, unsigned char* __restrict__ flags, const Tri& t, int D,
+                                                  int H, int W, float go) {
+  const int nbY = (H + 3) >> 2, nbZ = (W + 3) >> 2;
+  int last = -1;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int x = t.x0 + TRI_DX(c), y = t.y0 + TRI_DY(c), z = t.z0 + TRI_DZ(c);
+    if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
+      atomicAdd(g + ((size_t)z * H + y) * W + x, __fmul_rn(t.w[c], go));
+      if (flags) {
+        const int b = ((z >> 2) * nbY + (y >> 2)) * nbZ + (x >> 2);
+        if (b != last) flags[b] = 1;
+        last = b;
+      }
+    }
+  }
+}
+
 // 3-element sums in the association torch's CUDA reduction kernels use (probed bit-for-bit on
 // a B200 with tools/probe_torch_arith.py, 2^20 random triples each):
 //   reduce over a contiguous innermost dim of 3 ((a*b).sum(-1), x.norm(dim=-1),

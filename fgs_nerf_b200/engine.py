@@ -60,7 +60,7 @@ class FgsFineParams(C.Structure):
         ("g_sdf", _fp), ("g_k0", _fp), ("gW", _fp * MLP_LAYERS), ("gB", _fp * MLP_LAYERS),
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp), ("dlogit_p", _fp), ("dXRp", _fp),
         ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
-        ("dZ", _fp), ("k0_vox_flags", _fp), ("mask_occ", _fp),
+        ("dZ", _fp), ("k0_vox_flags", _fp), ("mask_occ", _fp), ("sdf_brick_flags", _fp),
     ]
 
 
@@ -306,7 +306,11 @@ class FineStepEngine:
         Vp = (V + 3) // 4 * 4
         nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
         self._xcap_bricks = min(nb, 32768) if self.world_size > 1 else 0
-        self._xbuf = torch.zeros(Vp + offs[-1] + self._xcap_bricks * 768, dtype=f32, device=dev)
+        # data parallel: g_sdf travels as packed 4^3 bricks too (64 floats each) behind the k0 bricks -- the dense grid
+        # is 16 MB of a 44 MB all-reduce at 160^3 / 8 GPUs and 67 MB at 256^3
+        self.sparse_sdf = self.world_size > 1 and (Z % 4 == 0) and not voxel_exchange
+        self._xbuf = torch.zeros(Vp + offs[-1] + self._xcap_bricks * 768 + (nb * 64 if self.sparse_sdf else 0),
+                                 dtype=f32, device=dev)
         self.g_sdf = self._xbuf[:V].view_as(self.sdf)
         self.g_mlp_flat = self._xbuf[Vp:Vp + offs[-1]]
         self._compact = self._xbuf[Vp + offs[-1]:]
@@ -357,8 +361,11 @@ class FineStepEngine:
         ws["w_split"] = torch.zeros(int(lib.fgs_fine_wsplit_floats()), dtype=f32, device=dev)
         ws["hbits"] = e(6, self.cap_m2, 8, dt=i32)
         nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
-        ws["k0_brick_flags"] = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        # [k0 flags | sdf flags] in one allocation: the union over the ranks is ONE MAX all-reduce
+        self._brick_flags2 = torch.zeros(2 * nb, dtype=torch.uint8, device=dev)
+        ws["k0_brick_flags"], ws["sdf_brick_flags"] = self._brick_flags2[:nb], self._brick_flags2[nb:]
         ws["k0_brick_list"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)), dtype=i32, device=dev)
+        ws["sdf_brick_list"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)) if self.sparse_sdf else 1, dtype=i32, device=dev)
         ws["k0_brick_ulist"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)) + 1, dtype=i32, device=dev)
         self.sparse_k0 = (Z % 4 == 0)      # brick-driven masked Adam (else the dense reference-style scan)
         # data parallel, optional: the k0 gradient travels at VOXEL granularity (one flag byte per voxel, ascending
@@ -376,9 +383,10 @@ class FineStepEngine:
         self._grads_clean = True           # g_sdf / g_k0 are all-zero (fresh, or cleared by the optimiser)
         self._mlp_grads_clean = True       # the MLP gradient bucket is all-zero (fresh, or cleared by the native step's Adam)
         self._brick_list_ready = False
-        self._count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._count_host = torch.zeros(2, dtype=torch.int32).pin_memory()      # touched k0 bricks (or voxels), touched sdf bricks
         self._count_evt = torch.cuda.Event()
         self.exchange_bricks = 0
+        self.exchange_sdf_bricks = 0
         self._side = None                  # side stream of the overlapped gradient exchange (data parallel)
         self.native_step = True            # single GPU: the iteration is one library call (fgs_fine_train_step)
         self._S = None
@@ -422,6 +430,7 @@ class FineStepEngine:
                   "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ", "dXRp", "dlogit_p"):
             setattr(P, k, ptr(ws[k]))
         P.k0_vox_flags = ptr(ws["k0_vox_flags"]) if self.voxel_exchange else None
+        P.sdf_brick_flags = ptr(ws["sdf_brick_flags"]) if self.sparse_sdf else None
         self._build_mask_occupancy()
 
     def _build_mask_occupancy(self):
@@ -603,7 +612,7 @@ class FineStepEngine:
             st = stream()
             check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
             check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
-            check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
+            check(lib.fgs_memset_zero(ptr(self._brick_flags2), self._brick_flags2.numel(), st))
             if self.voxel_exchange:
                 check(lib.fgs_memset_zero(ptr(self.ws["k0_vox_flags"]), self.ws["k0_vox_flags"].numel(), st))
         self._grads_clean = True
@@ -828,10 +837,11 @@ class FineStepEngine:
                 check(lib.fgs_voxel_bits_union_list(ptr(bits), self.world_size, self.X, self.Y, self.Z,
                                                     ptr(ws["k0_brick_flags"]), ptr(ws["k0_vox_list"]), st))
                 check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
-                self._count_host.copy_(ws["k0_vox_list"][:1], non_blocking=True)
+                self._count_host[:1].copy_(ws["k0_vox_list"][:1], non_blocking=True)
                 self._count_evt.record()
             return
-        dist.all_reduce(ws["k0_brick_flags"], op=dist.ReduceOp.MAX)            # union of the touched bricks
+        # union of the touched bricks (k0 and, when g_sdf travels sparsely, the SDF grid) over the ranks
+        dist.all_reduce(self._brick_flags2 if self.sparse_sdf else ws["k0_brick_flags"], op=dist.ReduceOp.MAX)
         if not self.sparse_k0:
             return
         if self.voxel_exchange:
@@ -842,9 +852,12 @@ class FineStepEngine:
             check(lib.fgs_brick_list(ptr(ws["k0_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["k0_brick_list"]), st))
             if self.voxel_exchange:
                 check(lib.fgs_voxel_list(ptr(ws["k0_vox_flags"]), self.X * self.Y * self.Z, ptr(ws["k0_vox_list"]), st))
-                self._count_host.copy_(ws["k0_vox_list"][:1], non_blocking=True)
+                self._count_host[:1].copy_(ws["k0_vox_list"][:1], non_blocking=True)
             else:
-                self._count_host.copy_(ws["k0_brick_list"][:1], non_blocking=True)
+                self._count_host[:1].copy_(ws["k0_brick_list"][:1], non_blocking=True)
+            if self.sparse_sdf:
+                check(lib.fgs_brick_list(ptr(ws["sdf_brick_flags"]), self.X, self.Y, self.Z, ptr(ws["sdf_brick_list"]), st))
+                self._count_host[1:].copy_(ws["sdf_brick_list"][:1], non_blocking=True)
             self._count_evt.record()
 
     def _exchange_pack(self):
@@ -855,14 +868,17 @@ class FineStepEngine:
         with torch.cuda.device(self.device):
             self._count_evt.synchronize()
             n = int(self._count_host[0])                            # voxels (12 floats each) or bricks (768 floats)
-            self.exchange_bricks = n
+            ns = int(self._count_host[1]) if self.sparse_sdf else 0 # touched SDF bricks (64 floats each)
+            self.exchange_bricks, self.exchange_sdf_bricks = n, ns
             per = K0_DIM if self.voxel_exchange else 768
             self._xbuf_overflow = None
-            if n * per > self._compact.numel():                     # rare: more than the shared buffer holds
-                self._xbuf_overflow = torch.empty(n * per, dtype=torch.float32, device=self.device)
+            if n * per + ns * 64 > self._compact.numel():           # rare: more than the shared buffer holds
+                self._xbuf_overflow = torch.empty(n * per + ns * 64, dtype=torch.float32, device=self.device)
+            buf = self._xbuf_overflow if self._xbuf_overflow is not None else self._compact
             if n > 0:
-                buf = self._xbuf_overflow if self._xbuf_overflow is not None else self._compact
                 self._copy_touched(buf, n, 1)
+            if ns > 0:
+                self._copy_sdf_bricks(buf[n * per:], ns, 1)
         self._brick_list_ready = True
 
     def _exchange_reduce(self):
@@ -874,19 +890,23 @@ class FineStepEngine:
             dist.all_reduce(torch.as_strided(g, (g.numel(),), (1,), g.storage_offset()))
             lib.fgs_prof_mark(1, stream())
             return
-        n = self.exchange_bricks
+        n, ns = self.exchange_bricks, self.exchange_sdf_bricks
         per = K0_DIM if self.voxel_exchange else 768
+        # with g_sdf among the packed bricks the collective starts at the MLP bucket, not at the dense grid
+        lo = self._xdense - self.g_mlp_flat.numel() if self.sparse_sdf else 0
         with torch.cuda.device(self.device):
             if self._xbuf_overflow is not None:
-                dist.all_reduce(self._xbuf[:self._xdense])
+                dist.all_reduce(self._xbuf[lo:self._xdense])
                 dist.all_reduce(self._xbuf_overflow)
                 buf = self._xbuf_overflow
             else:
-                dist.all_reduce(self._xbuf[:self._xdense + n * per])
+                dist.all_reduce(self._xbuf[lo:self._xdense + n * per + ns * 64])
                 buf = self._compact
             lib.fgs_prof_mark(1, stream())
             if n > 0:
                 self._copy_touched(buf, n, 0)
+            if ns > 0:
+                self._copy_sdf_bricks(buf[n * per:], ns, 0)
 
     def _native_train_step(self, rays_o, rays_d, viewdirs, target, global_step, near, bg, n_rays_global, has_last_ray, tv):
         """The single-GPU iteration as ONE library call (fgs_fine_train_step): same launches, order and streams as the
@@ -947,6 +967,11 @@ class FineStepEngine:
             check(lib.fgs_brick_copy(ptr(self.g_k0), ptr(buf), ptr(self.ws["k0_brick_list"]), n, self.X, self.Y,
                                      self.Z, K0_DIM, pack, stream()))
 
+    def _copy_sdf_bricks(self, buf, n, pack):
+        """Gather (pack=1) / scatter the touched 4^3 bricks of g_sdf (64 floats each) to / from `buf`."""
+        check(lib.fgs_brick_copy(ptr(self.g_sdf), ptr(buf), ptr(self.ws["sdf_brick_list"]), n, self.X, self.Y, self.Z,
+                                 1, pack, stream()))
+
     def train_step(self, rays_o, rays_d, viewdirs, target, global_step, near=2.0, bg=1.0, n_rays_global=None,
                    has_last_ray=True, _stop_before_optimizer=False):
         """One iteration of model/nerf_training.py:300-373 (fine stage).  Asynchronous.
@@ -988,7 +1013,7 @@ class FineStepEngine:
             return
         else:
             self.loss_backward(target, n_rays_global, has_last_ray, phase=1)
-            if tv and t["smooth_grad_tv"] > 0 and self.rank == 0:
+            if tv and t["smooth_grad_tv"] > 0 and self.rank == 0 and not self.sparse_sdf:
                 self.smooth_grad_tv_add_grad()                             # a pure function of the params:
             self._ev_grids.record(main)                                    # added once, not per rank
             with torch.cuda.stream(self._side):
@@ -1002,6 +1027,10 @@ class FineStepEngine:
             main.wait_event(self._ev_exch)
             lib.fgs_prof_mark(5, stream())
             self._exchange_reduce()                                        # ONE all-reduce of everything, unpack
+            if tv and t["smooth_grad_tv"] > 0 and self.sparse_sdf:
+                # g_sdf travelled as touched bricks: the (dense) smooth-TV gradient, a pure function of the replicated
+                # parameters, is added by every rank AFTER the reduce (every rank waited for rank 0's copy before anyway)
+                self.smooth_grad_tv_add_grad()
         if tv and t["sdf_tv"] > 0:
             self.sdf_tv_add_grad(global_step, n_rays_global)
         if _stop_before_optimizer:

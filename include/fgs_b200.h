@@ -156,8 +156,9 @@ int fgs_adam_upd_multi_zero_grad(int n_tensors, float* const* params, float* con
  *  fgs_brick_list         : compacts the touched-brick flags that fgs_fine_backward leaves behind (one
  *      byte per 4x4x4-voxel brick of k0, [ceil(X/4)*ceil(Y/4)*ceil(Z/4)]) into brick_list
  *      (fgs_brick_list_ints() ints: count, then brick ids in ascending order) and clears the flags;
- *  fgs_brick_copy         : gathers (pack != 0) / scatters the listed gradient bricks (768 floats each)
- *      to / from a compact [count][768] buffer -- the payload of the sparse multi-GPU exchange;
+ *  fgs_brick_copy         : gathers (pack != 0) / scatters the listed gradient bricks to / from a compact
+ *      [count][64 * channels] buffer -- the payload of the sparse multi-GPU exchange; channels 12 (k0, channels-last,
+ *      768 floats per brick) or 1 (the SDF gradient, 64 floats per brick);
  *  fgs_adam_upd_bricks    : masked_adam_upd of a channels-last [X][Y][Z][12] grid restricted to the
  *      listed bricks, one warp per brick; clears the gradients it consumed.  Identical p, m, v to
  *      masked_adam_upd provided every voxel with grad != 0 lies in a listed brick. */

@@ -142,6 +142,9 @@ typedef struct FgsFineParams {
                         iff any of the cell's 8 corners is non-zero.  A sample in a cell whose corners are all 0
                         interpolates to exactly 0 < mask_thres (requires mask_thres > 0), so the march kernel skips its
                         8 gathers: the result is the same bit for bit.  NULL = always gather */
+  uint8_t *sdf_brick_flags; /* optional [ceil(X/4)*ceil(Y/4)*ceil(Z/4)]: set to 1 by the backward scatters for every 4^3
+                        brick of the SDF grid that received a gradient (data-parallel exchange: g_sdf then travels as
+                        packed bricks like g_k0 instead of as the dense grid); NULL = not recorded */
 } FgsFineParams;
 
 /* words of FgsFineParams::mask_occ for an [mX][mY][mZ] mask grid, and the kernel that fills it (re-run whenever the

@@ -622,3 +622,23 @@ def test_batch_that_misses_the_volume(cuda):
     assert bool((out["rgb"] == 1.0).all())
     assert int(out["g_sdf"].count_nonzero()) == 0 and int(out["g_k0"].count_nonzero()) == 0
     assert int(out["g_mlp"].count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("dims", [(160, 160, 160), (36, 20, 52), (256, 256, 256), (8, 8, 4)])
+def test_ordered_brick_list(cuda, dims):
+    """fgs_brick_list (the data-parallel exchange's ordered list, two multi-CTA launches): ascending ids of the set flags,
+    their count, flags cleared -- at sizes with partial chunks and partial 16-flag runs."""
+    from fgs_nerf_b200._lib import check, lib, ptr, stream
+    X, Y, Z = dims
+    nb = ((X + 3) // 4) * ((Y + 3) // 4) * ((Z + 3) // 4)
+    g = torch.Generator().manual_seed(nb)
+    for density in (0.0, 0.03, 0.6, 1.0):
+        flags = (torch.rand(nb, generator=g) < density).to(torch.uint8).to(cuda)
+        want = torch.nonzero(flags).reshape(-1).to(torch.int32)
+        lst = torch.full((int(lib.fgs_brick_list_ints(X, Y, Z)),), -7, dtype=torch.int32, device=cuda)
+        check(lib.fgs_brick_list(ptr(flags), X, Y, Z, ptr(lst), stream()))
+        torch.cuda.synchronize()
+        n = int(lst[0])
+        assert n == want.numel(), (dims, density, n, want.numel())
+        assert torch.equal(lst[1:1 + n], want)
+        assert int(flags.sum()) == 0
