@@ -263,7 +263,7 @@ coarse_feat_bwd_kernel(const __grid_constant__ FgsFineParams P, const __grid_con
         if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
           if (P.k0_brick_flags) {
             const int brick = ((z >> 2) * nbY + (y >> 2)) * nbZ + (x >> 2);
-            if (brick != last_brick) P.k0_brick_flags[brick] = 1;
+            if (brick != last_brick && P.k0_brick_flags[brick] == 0) P.k0_brick_flags[brick] = 1;
             last_brick = brick;
           }
           const size_t vox = ((size_t)z * g.Y + y) * g.Z + x;

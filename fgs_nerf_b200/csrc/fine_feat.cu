@@ -214,7 +214,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
         if (x >= 0 && x < g.Z && y >= 0 && y < g.Y && z >= 0 && z < g.X) {
           if (P.k0_brick_flags) {   // touched-brick flag for the sparse masked Adam / gradient exchange
             const int brick = ((z >> 2) * nbY + (y >> 2)) * nbZ + (x >> 2);
-            if (brick != last_brick) P.k0_brick_flags[brick] = 1;
+            if (brick != last_brick && P.k0_brick_flags[brick] == 0) P.k0_brick_flags[brick] = 1;
             last_brick = brick;
           }
           const size_t vox = ((size_t)z * g.Y + y) * g.Z + x;
@@ -293,7 +293,7 @@ feat_bwd_kernel(const __grid_constant__ FgsFineParams P, float weight_orientatio
           atomicAdd(P.g_sdf + ((size_t)z * g.Y + y) * g.Z + x, v);
           if (P.sdf_brick_flags) {
             const int b = ((z >> 2) * ((g.Y + 3) >> 2) + (y >> 2)) * ((g.Z + 3) >> 2) + (x >> 2);
-            if (b != last_brick) P.sdf_brick_flags[b] = 1;
+            if (b != last_brick && P.sdf_brick_flags[b] == 0) P.sdf_brick_flags[b] = 1;
             last_brick = b;
           }
         }

@@ -122,7 +122,7 @@ __device__ __forceinline__ void tri_scatter1_flag(float* __restrict__ g, unsigne
       atomicAdd(g + ((size_t)z * H + y) * W + x, __fmul_rn(t.w[c], go));
       if (flags) {
         const int b = ((z >> 2) * nbY + (y >> 2)) * nbZ + (x >> 2);
-        if (b != last) flags[b] = 1;
+        if (b != last && flags[b] == 0) flags[b] = 1;      // (the L1-cached test spares most of the stores)
         last = b;
       }
     }
