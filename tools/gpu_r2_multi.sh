@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N"
 timeout 300 $RUN --steps 30 --warmup 5 > gpurun_out/r2_final_bench_cfg2_n$N.json 2> gpurun_out/r2_final_bench_cfg2_n$N.err; echo "cfg2 n$N rc=$?"
 timeout 400 $RUN --steps 30 --warmup 5 --grid 256 > gpurun_out/r2_final_bench_cfg4_n$N.json 2> gpurun_out/r2_final_bench_cfg4_n$N.err; echo "cfg4 n$N rc=$?"
-timeout 400 $RUN --mode render --grid 384 --steps 3 --warmup 1 > gpurun_out/r2_final_bench_cfg5_n$N.json 2> gpurun_out/r2_final_bench_cfg5_n$N.err; echo "cfg5 n$N rc=$?"
+timeout 400 $RUN --mode render --grid 384 --steps 5 --warmup 2 > gpurun_out/r2_final_bench_cfg5_n$N.json 2> gpurun_out/r2_final_bench_cfg5_n$N.err; echo "cfg5 n$N rc=$?"
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_final_bench_*_n$N.json")):
