@@ -561,7 +561,7 @@ def run_coarse(args, dev):
     host = [torch.stack(scene.make_rays(N=N, offset=b * N, **cam)).pin_memory() for b in range(nb)]
     resident = [[t.contiguous() for t in h.to(dev)] for h in host]
     staging = torch.empty_like(host[0], device=dev)
-    loss_host = torch.empty(6, dtype=torch.float64).pin_memory()
+    loss_host = torch.empty(7, dtype=torch.float64).pin_memory()
     cnt_host = torch.empty(8, dtype=torch.int32).pin_memory()
 
     def step_resident(i):
@@ -623,7 +623,7 @@ def run_coarse(args, dev):
                        "samples_per_ray": {"total_len": cnt["total_len"] / N, "M1": cnt["M1"] / N, "M2": cnt["M2"] / N}},
             "clocks": clocks,
             "e2e": {"value": N * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 6 * 8 + 8 * 4},
+                    "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 7 * 8 + 8 * 4},
             "gpu_launches": launches, "kernels": kern, "kernel_sum_ms_per_step": round(tot, 5),
             "loss_last": [round(float(x), 6) for x in loss_host.tolist()]}
     print(json.dumps(line), flush=True)

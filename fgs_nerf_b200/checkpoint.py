@@ -63,30 +63,57 @@ def optimizer_state_dict(eng):
     group order k0, sdf, rgbnet (weight, bias per layer), refnet."""
     eng._ensure_adam()
     params, groups, k = [], [], 0
+    coarse = hasattr(eng, "biases")
     per_group = {"k0": [("k0", None)], "sdf": [("sdf", None)],
                  "rgbnet": [(kind, i) for i in range(0, 4) for kind in ("W", "B")],
-                 "refnet": [(kind, i) for i in range(4, 8) for kind in ("W", "B")]}
-    for name in _GROUPS:
+                 "refnet": [(kind, i) for i in (range(3) if coarse else range(4, 8)) for kind in ("W", "B")]}
+    skip = tuple(eng.train_cfg.get("skip_zero_grad_fields", ("k0",))) if coarse else ("k0",)
+    for name in (("k0", "sdf", "refnet") if coarse else _GROUPS):
         ids = []
         for kind, i in per_group[name]:
             if i is None:
                 m, v = eng.adam[kind]
                 m, v = m.contiguous().clone(), v.contiguous().clone()
-            elif kind == "W":
-                m, v = (t[:, :eng.weights[i].shape[1]].contiguous().clone() for t in eng.adam["W"][i])
+            elif kind == "W":       # (the engines store the layers zero-padded: cut back to nn.Linear's shape)
+                o, n_in = eng.weights[i].shape
+                m, v = (t[:o, :n_in].contiguous().clone() for t in eng.adam["W"][i])
             else:
-                m, v = (t.clone() for t in eng.adam["B"][i])
+                o = eng.weights[i].shape[0]
+                m, v = (t[:o].clone() for t in eng.adam["B"][i])
             params.append({"step": int(eng.adam_step), "exp_avg": m, "exp_avg_sq": v})
             ids.append(k)
             k += 1
-        groups.append({"lr": eng.lr[name], "name": name, "skip_zero_grad": name == "k0", "betas": (0.9, 0.99), "eps": 1e-8,
+        groups.append({"lr": eng.lr[name], "name": name, "skip_zero_grad": name in skip, "betas": (0.9, 0.99), "eps": 1e-8,
                        "params": ids})
     state = {i: p for i, p in enumerate(params)} if eng.adam_step > 0 else {}
     return {"state": state, "param_groups": groups}
 
 
+def _coarse_model_kwargs(eng):
+    """nerf.get_kwargs (model/nerf.py:309-329) of a stage='coarse' model: no grad / sdf features, rgbnet_dim is still
+    computed by the constructor (:108-112) although no rgbnet is built."""
+    c = eng.cfg
+    rgb_dim = (3 + 3 * c["posbase_pe"] * 2) + c["k0_dim"] + 3 + 1 + (3 + 3 * c["viewbase_pe"] * 2)
+    return {
+        "xyz_min": eng.xyz_min.cpu().numpy(), "xyz_max": eng.xyz_max.cpu().numpy(),
+        "num_voxels": eng.num_voxels, "num_voxels_base": eng.num_voxels_base, "voxel_size": torch.tensor(float(eng.voxel_size)),
+        "nearest": False, "k0_dim": c["k0_dim"], "grad_feat": (), "sdf_feat": (), "center_sdf": True,
+        "fast_color_thres": float(c["fast_color_thres"]), "stage": "coarse", "ref": True, "use_viewdir": True,
+        "s_ratio": c["s_ratio"], "s_start": c["s_start"],
+        "rgbnet_dim": rgb_dim, "rgbnet_width": c.get("rgbnet_width", 192), "rgbnet_depth": c.get("rgbnet_depth", 3),
+        "refnet_dim": eng.in_dim, "refnet_width": c["refnet_width"], "refnet_depth": c["refnet_depth"],
+    }
+
+
 def checkpoint_dict(eng, global_step):
     c = eng.cfg
+    if hasattr(eng, "biases"):                      # coarse.CoarseStepEngine
+        ext = (eng.xyz_max - eng.xyz_min).float()
+        voxel_size_base = (ext.prod() / eng.num_voxels_base).pow(1 / 3)
+        mc = {"xyz_min": eng.xyz_min.cpu().numpy(), "xyz_max": eng.xyz_max.cpu().numpy(),
+              "voxel_size_ratio": torch.tensor(float(eng.voxel_size)) / voxel_size_base, "nearest": False}
+        return {"global_step": int(global_step), "model_kwargs": _coarse_model_kwargs(eng), "MaskCache_kwargs": mc,
+                "model_state_dict": model_state_dict(eng, global_step), "optimizer_state_dict": optimizer_state_dict(eng)}
     rgb_dim, ref_dim = mlp_dims(c["k0_dim"], c["posbase_pe"], c["viewbase_pe"], c["refbase_pe"], len(c["grad_feat"]),
                                 c["rgbnet_width"])
     kwargs = {   # nerf.get_kwargs (model/nerf.py:309-329)
@@ -181,3 +208,61 @@ def load_optimizer_state_dict(eng, osd):
             put(eng.adam["B"][base + j][0], b["exp_avg"])
             put(eng.adam["B"][base + j][1], b["exp_avg_sq"])
 
+
+
+def coarse_engine_from_checkpoint(ckpt, n_rays, device="cuda", model_cfg=None, train_cfg=None, no_reload_optimizer=False, **kw):
+    """utils.load_checkpoint (model/utils.py:42-56) for a stage='coarse' checkpoint (also one the reference wrote):
+    a coarse.CoarseStepEngine holding its parameters and, unless no_reload_optimizer, its MaskedAdam state.
+    Returns (engine, start)."""
+    from .coarse import COARSE_MODEL, CoarseStepEngine
+    if not isinstance(ckpt, dict):
+        ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
+    sd, mk = ckpt["model_state_dict"], ckpt.get("model_kwargs", {})
+    cfg = dict(model_cfg if model_cfg is not None else COARSE_MODEL)
+    for k in ("k0_dim", "s_ratio", "s_start", "fast_color_thres", "refnet_width", "refnet_depth"):
+        if k in mk:
+            cfg[k] = mk[k]
+    for key, name in (("posfreq", "posbase_pe"), ("viewfreq", "viewbase_pe"), ("reffreq", "refbase_pe")):
+        if key in sd:
+            cfg[name] = int(sd[key].numel())
+    sdf, k0 = sd["sdf.grid"].float(), sd["k0.grid"].float()
+    xyz_min, xyz_max = sd["xyz_min"].float().cpu(), sd["xyz_max"].float().cpu()
+    voxel_size = float(mk["voxel_size"]) if "voxel_size" in mk else float(((xyz_max - xyz_min).prod() / sdf[0, 0].numel()).pow(1 / 3))
+    refnet = [(sd[f"refnet.{i}.weight"].float(), sd[f"refnet.{i}.bias"].float()) for i in _LIN3]
+    sc = Scene(G=int(sdf.shape[2]), xyz_min=xyz_min, xyz_max=xyz_max, voxel_size=voxel_size, sdf=sdf, k0=k0,
+               mask_grid=sd["mask_cache.sdf_mask"].float(), mask_xyz_min=sd["mask_cache.xyz_min"].float().cpu(),
+               mask_xyz_max=sd["mask_cache.xyz_max"].float().cpu(), mask_thres=cfg["mask_cache_thres"], cfg=cfg)
+    eng = CoarseStepEngine(sc, refnet, n_rays, device, cfg=cfg, train_cfg=train_cfg, **kw)
+    if "num_voxels" in mk:
+        eng.num_voxels = mk["num_voxels"]
+    eng.num_voxels_base = mk.get("num_voxels_base", eng.num_voxels)
+    if "nonempty_mask" in sd:
+        eng.nonempty_mask = sd["nonempty_mask"].to(eng.device).reshape(eng.X, eng.Y, eng.Z).contiguous()
+        eng.n_nonempty = int(eng.nonempty_mask.sum().item())
+    osd = ckpt.get("optimizer_state_dict")
+    if not no_reload_optimizer and osd and osd.get("state"):
+        eng._ensure_adam()
+        st = osd["state"]
+        ids = {g["name"]: list(g["params"]) for g in osd["param_groups"]}
+        for g in osd["param_groups"]:
+            if g["name"] in eng.lr:
+                eng.lr[g["name"]] = float(g["lr"])
+        steps = {int(st[i]["step"]) for i in st}
+        if len(steps) != 1:
+            raise RuntimeError(f"per-parameter Adam steps differ ({sorted(steps)}): the fused optimiser keeps one step count")
+        eng.adam_step = steps.pop()
+
+        def put(dst, src):
+            dst.zero_()
+            view = dst[tuple(slice(0, n) for n in src.shape)]
+            view.copy_(src.to(dst.device))
+
+        for name in ("k0", "sdf"):
+            e = st[ids[name][0]]
+            put(eng.adam[name][0], e["exp_avg"])
+            put(eng.adam[name][1], e["exp_avg_sq"])
+        for j in range(3):
+            w, b = st[ids["refnet"][2 * j]], st[ids["refnet"][2 * j + 1]]
+            put(eng.adam["W"][j][0], w["exp_avg"]); put(eng.adam["W"][j][1], w["exp_avg_sq"])
+            put(eng.adam["B"][j][0], b["exp_avg"]); put(eng.adam["B"][j][1], b["exp_avg_sq"])
+    return eng, int(ckpt.get("global_step", 0))

@@ -231,7 +231,7 @@ class CoarseStepEngine(FineStepEngine):
         ws["k0_brick_ulist"] = torch.zeros(int(lib.fgs_brick_list_ints(X, Y, Z)) + 1, dtype=i32, device=dev)
         self.sparse_k0 = (Z % 4 == 0)
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
-        ws["loss"] = torch.zeros(6, dtype=torch.float64, device=dev)   # mse + rgbper, entropy, orientation, sigmoid_rgb, smooth_tv, sdf_tv
+        ws["loss"] = torch.zeros(7, dtype=torch.float64, device=dev)   # mse, entropy, orientation, sigmoid_rgb, smooth_tv, sdf_tv, rgbper
         self._grads_clean = True
         self._mlp_grads_clean = True
         self._brick_list_ready = False
@@ -277,6 +277,17 @@ class CoarseStepEngine(FineStepEngine):
         Cc.in_dim, Cc.in_ld = self.in_dim, self.in_ld
         Cc.pos_pe, Cc.view_pe, Cc.ref_pe = c["posbase_pe"], c["viewbase_pe"], c["refbase_pe"]
 
+    def init_smooth_conv(self, ksize=3, sigma=1):
+        """nerf.init_smooth_conv (model/nerf.py:274-278; the `smooth_updates` schedule): a new Gaussian for the SDF
+        smoothing of every forward.  ksize 0 switches it off."""
+        had = self.smooth_ksize > 0
+        self.smooth_ksize = int(ksize)
+        self.cfg["smooth_ksize"], self.cfg["smooth_sigma"] = int(ksize), sigma
+        self.smooth_weights = gaussian_3dconv_weights(self.smooth_ksize, sigma, self.device) if ksize > 0 else None
+        if had != (ksize > 0):
+            self.Cc.sdf_smooth = ptr(self.sdf_smooth if ksize > 0 else self.sdf)
+            self.Cc.g_smooth = ptr(self.g_smooth if ksize > 0 else self.g_sdf)
+
     def set_nonempty_mask(self):
         """nerf._set_nonempty_mask (model/nerf.py:339-353): in the coarse stage the SDF outside the mask becomes 1."""
         m = super().set_nonempty_mask()
@@ -311,6 +322,7 @@ class CoarseStepEngine(FineStepEngine):
     def _fill_loss(self, target, n_rays_global=None, has_last_ray=True):
         L = super()._fill_loss(target, n_rays_global, has_last_ray)
         L.weight_rgbper = float(self.train_cfg.get("weight_rgbper", 0.0))
+        L.rgbper_slot = 6
         return L
 
     def loss_backward(self, target):

@@ -162,7 +162,7 @@ composite_kernel(const __grid_constant__ FgsFineParams P, const __grid_constant_
           else if (k == 1) atomicAdd(L.loss_out + 1, (double)L.weight_entropy_last * t);
           else if (k == 2) atomicAdd(L.loss_out + 2, (double)L.weight_orientation * t);
           else if (k == 3) atomicAdd(L.loss_out + 3, (double)L.sigmoid_rgb_loss * t * inv_cnt);
-          else atomicAdd(L.loss_out + 0, (double)L.weight_rgbper * t / (double)L.n_rays_global);
+          else atomicAdd(L.loss_out + max(L.rgbper_slot, 0), (double)L.weight_rgbper * t / (double)L.n_rays_global);
         }
       } else if (P.gB[FGS_MLP_LAYERS - 1]) {
         float t = 0.f;

@@ -71,7 +71,7 @@ class FgsFineLoss(C.Structure):
         ("weight_orientation", C.c_float), ("sigmoid_rgb_loss", C.c_float),
         ("n_rays_global", C.c_int32), ("has_last_ray", C.c_int32),
         ("g_alphainv_last", _fp), ("loss_out", _fp),
-        ("weight_rgbper", C.c_float), ("pad_", C.c_float),
+        ("weight_rgbper", C.c_float), ("rgbper_slot", C.c_int32),
     ]
 
 

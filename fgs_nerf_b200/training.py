@@ -126,9 +126,7 @@ def end_of_iteration_updates(t, lr, global_step, engine_train_cfg=None, model_cf
     # train cfg is accepted too
     s_updates = dict(t.get("s_updates", {}))
     if model_cfg is not None:
-        s_updates.update(model_cfg.get("s_updates", {}))
-        if model_cfg.get("smooth_updates"):
-            raise NotImplementedError("smooth_updates (init_smooth_conv, coarse stages) is not on the fine-stage path")
+        s_updates.update(model_cfg.get("s_updates", {}))      # (smooth_updates: CoarseTrainer.step, after this block)
     for term, value in s_updates.get(gs_, {}).items():
         if model_cfg is not None:
             model_cfg[term] = value
@@ -155,6 +153,23 @@ def flatten_train_cfg(cfg_train):
     return t
 
 
+def flatten_coarse_train_cfg(cfg_train):
+    """Reference-style coarse_train dict (config/shiny_blender.py:103-146) -> the flat dict CoarseStepEngine reads:
+    weight_rgbper and ori_tv belong to this stage; what the coarse kernels do not cover fails loudly."""
+    t = dict(cfg_train)
+    for k, v in dict(t.pop("tv_terms", {})).items():
+        t[k] = v
+    t.setdefault("sdf_tv", 0.0)
+    t.setdefault("smooth_grad_tv", 0.0)
+    if t.get("weight_tv_k0", 0) > 0 or t.get("grad_norm", 0) > 0 or t.get("grad_tv", 0) > 0:
+        raise NotImplementedError("weight_tv_k0 / grad_norm / grad_tv are 0 in every shipped coarse config")
+    if t.get("voxel_inc", False) or t.get("pervoxel_lr", False) or t.get("reset_iter"):
+        raise NotImplementedError("voxel_inc / pervoxel_lr / reset_iter belong to the geometry_searching stage")
+    if t.get("ray_sampler", "in_maskcache") not in ("flatten", "in_maskcache"):
+        raise NotImplementedError(f"ray_sampler {t['ray_sampler']!r}")
+    return t
+
+
 class FineTrainer:
     """scene_rep_reconstruction's iteration loop for stage 'fine' (model/nerf_training.py:237-460).
 
@@ -172,10 +187,13 @@ class FineTrainer:
                   contiguous slice of the global batch (dist.ray_shard), the last rank owns the batch's last ray.
     """
 
+    _flatten = staticmethod(flatten_train_cfg)
+    _stage = "fine"
+
     def __init__(self, engine, rays_o_tr, rays_d_tr, viewdirs_tr, rgb_tr, cfg_train=None, start=0, near=2.0, bg=1.0,
                  rng=None, ring=256, reset_optimizer=None):
         self.engine = engine
-        self.cfg_train = flatten_train_cfg(cfg_train if cfg_train is not None else engine.train_cfg)
+        self.cfg_train = self._flatten(cfg_train if cfg_train is not None else engine.train_cfg)
         engine.train_cfg.update({k: v for k, v in self.cfg_train.items() if k in engine.train_cfg or k in
                                  ("sdf_tv", "smooth_grad_tv", "lrate_decay")})
         self.world_size, self.rank = engine.world_size, engine.rank
@@ -191,7 +209,7 @@ class FineTrainer:
         self._bad = torch.zeros(1, dtype=torch.int32, device=dev)
         self.near, self.bg = float(near), float(bg)
         self.global_step = int(start)
-        self._ring = torch.zeros((int(ring), 5), dtype=torch.float64, device=dev)
+        self._ring = torch.zeros((int(ring), engine.ws["loss"].numel()), dtype=torch.float64, device=dev)
         self._since = 0                      # iterations since the last stats()
         if reset_optimizer is None:
             reset_optimizer = not (engine.adam and engine.adam_step > 0)
@@ -216,14 +234,19 @@ class FineTrainer:
         self._ring[self._since % self._ring.shape[0]].copy_(eng.ws["loss"])
         self._since += 1
         end_of_iteration_updates(t, eng.lr, gs, eng.train_cfg, eng.cfg)
+        self._after_updates(gs)
         return gs
+
+    def _after_updates(self, gs):
+        if self.engine.cfg.get("smooth_updates"):
+            raise NotImplementedError("smooth_updates (init_smooth_conv) belongs to the coarse stages: use CoarseTrainer")
 
     def run(self, n_steps, i_print=0, log=print):
         for _ in range(int(n_steps)):
             gs = self.step()
             if i_print and gs % i_print == 0:
                 s = self.stats()
-                log(f"scene_rep_reconstruction (fine): iter {gs:6d} / Loss: {s['loss']:.9f} / PSNR: {s['psnr']:5.2f} / "
+                log(f"scene_rep_reconstruction ({self._stage}): iter {gs:6d} / Loss: {s['loss']:.9f} / PSNR: {s['psnr']:5.2f} / "
                     f"s_val: {self.engine.s_val(gs):5.2g}")
         if not i_print:
             self.engine.check_overflow()               # nobody called stats(): still never return silently corrupted
@@ -253,3 +276,17 @@ class FineTrainer:
         mse = np.maximum(rows[:, 0], 1e-30)
         psnr = float(np.mean(-10.0 * np.log10(mse)))  # utils.mse2psnr on weight_main * mse (nerf_training.py:308-309)
         return dict(steps=steps, loss=float(rows[-1].sum()), psnr=psnr, terms=rows, lr=dict(self.engine.lr))
+
+
+class CoarseTrainer(FineTrainer):
+    """scene_rep_reconstruction's iteration loop for stage 'coarse' (model/nerf_training.py:237-460 with `coarse_train` /
+    `coarse_model`): the same loop on a coarse.CoarseStepEngine -- batch sampler, one-launch gather, lr decay,
+    decay_step_module, tv_updates, s_updates, pg_scale (scale_volume_grid + a fresh optimiser) -- plus the coarse
+    model's `smooth_updates` (init_smooth_conv).  Single GPU."""
+    _flatten = staticmethod(flatten_coarse_train_cfg)
+    _stage = "coarse"
+
+    def _after_updates(self, gs):
+        upd = self.engine.cfg.get("smooth_updates", {}).get(gs - 1)
+        if upd:
+            self.engine.init_smooth_conv(**upd)                        # model/nerf_training.py:452-456

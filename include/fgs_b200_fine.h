@@ -171,9 +171,9 @@ typedef struct FgsFineLoss {
   int32_t has_last_ray;         /* this rank owns the global last ray (entropy quirk)          */
   float* g_alphainv_last;       /* [N] written                                                 */
   double* loss_out;             /* [5] device: mse (+ rgbper), entropy, orientation, sigmoid_rgb, smooth TV */
-  float weight_rgbper;          /* coarse stage (model/nerf_training.py:311-314): per-point colour loss, added to
-                                   loss_out[0]; 0 in the fine stage */
-  float pad_;
+  float weight_rgbper;          /* coarse stage (model/nerf_training.py:311-314): per-point colour loss; 0 in the fine stage */
+  int32_t rgbper_slot;          /* its value is added to loss_out[rgbper_slot] (0: into the mse term; the coarse engine
+                                   keeps it apart in slot 6 so that PSNR can be formed from the mse alone) */
 } FgsFineLoss;
 int fgs_fine_loss(const FgsFineParams* p, const FgsFineLoss* l, fgs_stream_t stream);
 

@@ -194,7 +194,7 @@ def test_coarse_loss_and_gradients(case, request):
     torch.cuda.synchronize()
     loss = eng.ws["loss"].cpu().numpy()
     want_main = float(c.loss.detach())
-    assert abs(float(loss[:4].sum()) - want_main) <= 1e-4 * abs(want_main), (loss, want_main)
+    assert abs(float(loss[:4].sum() + loss[6]) - want_main) <= 1e-4 * abs(want_main), (loss, want_main)    # slot 6: rgbper
     assert abs(loss[4] - float(c.tv_smooth.detach())) <= 1e-4 * abs(float(c.tv_smooth.detach()))
     assert abs(loss[5] - float(c.tv_sdf.detach())) <= 1e-4 * abs(float(c.tv_sdf.detach()))
     m = c.m
@@ -280,3 +280,79 @@ def test_model_class_coarse_stage(cuda):
     assert _rel(got["rgb_marched"], want["rgb_marched"]) < 1e-4
     keys = list(model.state_dict().keys())
     assert "refnet.0.weight" in keys and "refnet.3.bias" in keys and not any(k.startswith("rgbnet") for k in keys)
+
+
+def test_coarse_checkpoint_round_trip(cuda, tmp_path):
+    """The reference's checkpoint format (model/nerf_training.py:522-531) for a stage='coarse' model: `refnet.{0,2.0,3}`
+    in nn.Linear shapes (the engine's zero-padding does not leak), groups k0 / sdf / refnet with sdf masked, and an
+    engine restored from it -- through torch.save -- holds the same parameters, Adam moments, step and rates."""
+    import make_coarse_golden as mk
+    from fgs_nerf_b200 import checkpoint, coarse, scene
+    N = 256
+    sc = scene.make_scene(G=40, mask_G=32, with_mlps=False)
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
+    eng = coarse.CoarseStepEngine(sc, mk.coarse_refnet(), N, cuda, cfg=dict(mk.COARSE_MODEL))
+    eng.set_nonempty_mask()
+    for gs in (3000, 3001):
+        eng.train_step(ro, rd, vd, tgt, gs)
+    eng.lr["sdf"] *= 0.2                                     # a decay_step_module entry (config coarse_train)
+    torch.cuda.synchronize()
+    ck = checkpoint.checkpoint_dict(eng, 3001)
+    sd = ck["model_state_dict"]
+    assert [tuple(sd[f"refnet.{i}.weight"].shape) for i in ("0", "2.0", "3")] == [(192, 90), (192, 192), (3, 192)]
+    assert not any(k.startswith("rgbnet") for k in sd) and ck["model_kwargs"]["stage"] == "coarse"
+    assert ck["model_kwargs"]["refnet_dim"] == 90
+    groups = ck["optimizer_state_dict"]["param_groups"]
+    assert [(g["name"], g["skip_zero_grad"], len(g["params"])) for g in groups] == [("k0", True, 1), ("sdf", True, 1), ("refnet", False, 6)]
+    assert tuple(ck["optimizer_state_dict"]["state"][2]["exp_avg"].shape) == (192, 90)
+    path = str(tmp_path / "coarse_last.tar")
+    checkpoint.save_checkpoint(eng, 3001, path)
+    eng2, start = checkpoint.coarse_engine_from_checkpoint(path, N, cuda)
+    assert start == 3001 and eng2.adam_step == 2 and eng2.lr == eng.lr
+    assert torch.equal(eng2.sdf, eng.sdf) and torch.equal(eng2.k0, eng.k0) and torch.equal(eng2.nonempty_mask, eng.nonempty_mask)
+    for i in range(3):
+        assert torch.equal(eng2.Wt[i], eng.Wt[i]) and torch.equal(eng2.Bt[i], eng.Bt[i])
+        assert torch.equal(eng2.adam["W"][i][0], eng.adam["W"][i][0]) and torch.equal(eng2.adam["B"][i][1], eng.adam["B"][i][1])
+    assert torch.equal(eng2.adam["sdf"][1], eng.adam["sdf"][1]) and torch.equal(eng2.adam["k0"][0], eng.adam["k0"][0])
+    # both continue: the third iteration agrees up to the float atomics of the scatters
+    before = eng.sdf.clone()
+    eng.train_step(ro, rd, vd, tgt, 3002)
+    eng2.train_step(ro, rd, vd, tgt, 3002)
+    torch.cuda.synchronize()
+    moved = (eng.sdf - before).abs()
+    assert float(moved.max()) > 0 and float((eng2.sdf - eng.sdf).abs().max()) < 0.05 * float(moved.max())
+
+
+def test_coarse_trainer_loop(cuda):
+    """training.CoarseTrainer: the reference's loop body for stage 'coarse' -- reference-style coarse_train dict (nested
+    tv_terms, weight_rgbper, ori_tv), lr decay + decay_step_module, pg_scale (grids resampled, fresh optimiser), the
+    coarse model's smooth_updates -- runs asynchronously and leaves finite parameters and a falling loss."""
+    import make_coarse_golden as mk
+    from fgs_nerf_b200 import coarse, scene, training
+    N, n_total = 256, 4096
+    sc = scene.make_scene(G=40, mask_G=32, with_mlps=False)
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=n_total, H=100, W=100, n_views=8)]
+    cfg_model = dict(mk.COARSE_MODEL, smooth_updates={4: dict(ksize=3, sigma=0.5)})
+    eng = coarse.CoarseStepEngine(sc, mk.coarse_refnet(), N, cuda, cfg=cfg_model)
+    eng.set_nonempty_mask()
+    cfg_train = dict(N_iters=100, N_rand=N, lrate_k0=0.1, lrate_sdf=0.1, lrate_refnet=1e-3, lrate_decay=20,
+                     ray_sampler="in_maskcache", weight_main=1.0, weight_entropy_last=1e-3, weight_rgbper=0.2,
+                     weight_tv_density=0.01, weight_tv_k0=0, sigmoid_rgb_loss=0.1, weight_orientation=1e-4, tv_every=1,
+                     tv_from=0, tv_end=40000, tv_dense_before=40000, voxel_inc=False, scale_ratio=1.5, pg_scale=[3],
+                     reset_iter=[], tv_terms=dict(sdf_tv=0.1, grad_norm=0, grad_tv=0, smooth_grad_tv=0.05), ori_tv=True,
+                     tv_updates={5: dict(sdf_tv=0.1, smooth_grad_tv=0.2)}, decay_step_module={2: dict(sdf=0.2)},
+                     skip_zero_grad_fields=["density", "k0", "sdf"])
+    tr = training.CoarseTrainer(eng, ro, rd, vd, tgt, cfg_train=cfg_train, start=0, rng=np.random.RandomState(5))
+    tr.run(2)
+    first = tr.stats()
+    assert tr.engine is eng and len(first["steps"]) == 2 and np.isfinite(first["loss"])
+    f = 0.1 ** (1 / 20000)
+    assert tr.engine.lr["sdf"] == pytest.approx(0.1 * f * f, rel=1e-12)
+    tr.run(1)                                                # pg_scale at 3: a new engine, fresh optimiser at the base rates
+    assert tr.engine is not eng and tr.engine.X > 40 and tr.engine.adam_step == 1
+    assert tr.engine.lr["sdf"] == pytest.approx(0.1 * f * 0.2, rel=1e-12)     # decay_step_module fired at the end of step 3
+    tr.run(5)
+    s = tr.stats()
+    assert tr.engine.smooth_ksize == 3 and tr.engine.train_cfg["smooth_grad_tv"] == 0.2
+    assert np.isfinite(s["loss"]) and np.isfinite(s["psnr"]) and s["terms"].shape[1] == 7
+    assert bool(torch.isfinite(tr.engine.sdf).all()) and bool(torch.isfinite(tr.engine.Wt[0]).all())
