@@ -146,7 +146,12 @@ def mid(cuda):
     return Case(cuda, G=96, mask_G=80, N=4096, step=3000)
 
 
-@pytest.mark.parametrize("case", ["small", "mid"])
+@pytest.fixture(scope="module")
+def bench_size(cuda):
+    return Case(cuda, G=116, mask_G=96, N=8192, step=3000)           # the shape `bench.py --stage coarse` measures
+
+
+@pytest.mark.parametrize("case", ["small", "mid", "bench_size"])
 def test_coarse_forward_ids_and_outputs(case, request):
     c = request.getfixturevalue(case)
     mine, want = c.mine, c.out
@@ -179,7 +184,7 @@ def test_coarse_forward_near_golden_fixture(small):
     assert float(np.abs(got - gold["out_rgb_marched"]).mean()) < 2e-2
 
 
-@pytest.mark.parametrize("case", ["small", "mid"])
+@pytest.mark.parametrize("case", ["small", "mid", "bench_size"])
 def test_coarse_loss_and_gradients(case, request):
     c = request.getfixturevalue(case)
     eng = c.eng

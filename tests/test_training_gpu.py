@@ -200,7 +200,10 @@ def test_trainer_second_iteration_against_oracle_step(cuda):
     for name, mine, lr in (("sdf", tr.engine.sdf, cfg["lrate_sdf"]), ("k0", tr.engine.k0, cfg["lrate_k0"]),
                            ("rgbnet.0.weight", tr.engine.weights[0], 1e-3), ("refnet.3.weight", tr.engine.weights[7], 1e-3)):
         frac = _frac_differing(mine, ref[name], before[name], lr)
-        assert frac < 2e-2, f"{name}: {frac:.5f} of the two-iteration updates differ from the oracle's"
+        print(f"  {name}: {frac:.6f} of the two-iteration updates differ from the oracle's")
+        # observed on a B200: sdf 6e-5 (entries whose gradient is rounding noise: Adam moves them by ~lr in a direction
+        # the last bit decides), k0 / MLP weights 0; the bound leaves an order of magnitude
+        assert frac < 1e-3, f"{name}: {frac:.5f} of the two-iteration updates differ from the oracle's"
     # the sdf step of iteration 2 used a tenth of the rate: |update| <= lr1 + 1.001 lr2 (Adam's bias-corrected ratio
     # is at most 1.001 at step 2), where two full-rate steps would reach 2 lr1
     lr1 = cfg["lrate_sdf"]                       # a fresh optimiser starts at the base rate (global_step=0)
