@@ -62,6 +62,8 @@ def main():
     ktable = "\n".join(k)
     summary = (f"Headline: **{M(c2['value'])} rays/s** resident ({c2['ms_per_step']:.3f} ms per 8192-ray step), "
                f"**{M(c2['e2e']['value'])} rays/s** end to end"
+               + (f" (host-fed loop with the next batch's upload and the previous step's loss read overlapped; "
+                  f"{M(c2['e2e']['serial_value'])} with nothing overlapped)" if c2['e2e'].get('serial_value') else "")
                + (f"; the reference's own arithmetic on the same GPU runs at {M(go['value'])} rays/s ({c2['value'] / go['value']:.1f}x slower)" if go.get("value") else "")
                + (f"; 8 GPUs: {M(n8['value'])} rays/s = {n8['value'] / c2['value']:.2f}x" if n8 else "") + ".")
     block = f"{summary}\n\n{cfg_table}\n\nPer-kernel roofline of the headline step:\n\n{ktable}\n"
