@@ -2,7 +2,8 @@
 (`lr`, `betas`, `eps`, `skip_zero_grad`), lazy state (`step`, `exp_avg`, `exp_avg_sq`) and
 `set_pervoxel_lr`; every update runs the sm_100a streaming kernels of csrc/adam.cu.  Dense groups of
 small tensors (the 16 MLP tensors) are batched into one multi-tensor launch instead of one launch
-per tensor."""
+per tensor.  Shared with the reference: the public surface (names, defaults, state keys) that its training loop and its
+checkpoints address; nothing else."""
 import ctypes as C
 
 import torch
@@ -12,52 +13,50 @@ from ._lib import check, lib, ptr, stream
 
 
 class MaskedAdam(torch.optim.Optimizer):
+    """What callers and checkpoints depend on is kept exactly: constructor signature and defaults, the `per_lr`
+    attribute, group keys and the state keys `step`, `exp_avg`, `exp_avg_sq` (in that order).  Everything else -- which
+    kernel runs for which tensor, the batching of small tensors -- is this implementation's."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.99), eps=1e-8):
-        if not 0.0 <= lr:
-            raise ValueError("Invalid learning rate: {}".format(lr))
-        if not 0.0 <= eps:
-            raise ValueError("Invalid epsilon value: {}".format(eps))
-        if not 0.0 <= betas[0] < 1.0:
-            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
-        if not 0.0 <= betas[1] < 1.0:
-            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
-        defaults = dict(lr=lr, betas=betas, eps=eps)
+        for what, value, ok in (("learning rate", lr, lr >= 0.0), ("epsilon value", eps, eps >= 0.0),
+                                ("beta parameter at index 0", betas[0], 0.0 <= betas[0] < 1.0),
+                                ("beta parameter at index 1", betas[1], 0.0 <= betas[1] < 1.0)):
+            if not ok:
+                raise ValueError(f"Invalid {what}: {value}")
         self.per_lr = None
-        super().__init__(params, defaults)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
 
     def set_pervoxel_lr(self, count):
         self.per_lr = count.float() / count.max()
 
+    def _moments(self, param):
+        """(exp_avg, exp_avg_sq, step) of `param`, created on first use, step already advanced."""
+        st = self.state[param]
+        if not st:
+            st.update(step=0, exp_avg=torch.zeros_like(param, memory_format=torch.preserve_format),
+                      exp_avg_sq=torch.zeros_like(param, memory_format=torch.preserve_format))
+        st['step'] += 1
+        return st['exp_avg'], st['exp_avg_sq'], st['step']
+
     @torch.no_grad()
     def step(self):
-        small = []   # (param, grad, m, v, step, lr, betas, eps) of dense tensors below 2^20 elements
+        small = []   # (param, grad, m, v, step, lr, beta1, beta2, eps) of dense tensors below 2^20 elements
         for group in self.param_groups:
-            lr = group['lr']
-            beta1, beta2 = group['betas']
-            eps = group['eps']
-            skip_zero_grad = group.get('skip_zero_grad', False)
+            lr, (beta1, beta2), eps = group['lr'], group['betas'], group['eps']
+            masked = group.get('skip_zero_grad', False)
             for param in group['params']:
-                if param.grad is None:
+                grad = param.grad
+                if grad is None:
                     continue
-                state = self.state[param]
-                if len(state) == 0:
-                    state['step'] = 0
-                    state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                    state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                state['step'] += 1
+                m, v, t = self._moments(param)
                 if self.per_lr is not None and param.shape == self.per_lr.shape:
-                    adam_upd_cuda.adam_upd_with_perlr(param, param.grad, state['exp_avg'], state['exp_avg_sq'],
-                                                      self.per_lr, state['step'], beta1, beta2, lr, eps)
-                elif skip_zero_grad:
-                    adam_upd_cuda.masked_adam_upd(param, param.grad, state['exp_avg'], state['exp_avg_sq'],
-                                                  state['step'], beta1, beta2, lr, eps)
-                elif param.numel() < (1 << 20) and param.is_contiguous() and param.grad.is_contiguous():
-                    small.append((param, param.grad, state['exp_avg'], state['exp_avg_sq'], state['step'], lr,
-                                  beta1, beta2, eps))
+                    adam_upd_cuda.adam_upd_with_perlr(param, grad, m, v, self.per_lr, t, beta1, beta2, lr, eps)
+                elif masked:
+                    adam_upd_cuda.masked_adam_upd(param, grad, m, v, t, beta1, beta2, lr, eps)
+                elif param.numel() < (1 << 20) and param.is_contiguous() and grad.is_contiguous():
+                    small.append((param, grad, m, v, t, lr, beta1, beta2, eps))
                 else:
-                    adam_upd_cuda.adam_upd(param, param.grad, state['exp_avg'], state['exp_avg_sq'],
-                                           state['step'], beta1, beta2, lr, eps)
+                    adam_upd_cuda.adam_upd(param, grad, m, v, t, beta1, beta2, lr, eps)
         # one launch per (betas, eps) family, up to 32 tensors each
         while small:
             b1, b2, eps = small[0][6:9]

@@ -11,6 +11,10 @@ DenseGrid.forward is differentiable w.r.t. the grid (what the reference gets fro
 both directions run fgs_grid_sample_fwd / fgs_grid_sample_bwd -- ATen's grid_sampler_3d arithmetic,
 bit-exact forward (tests/test_fine_gpu.py::test_grid_sample_matches_aten).  TensoRFGrid is not
 provided: no config of the reference instantiates it.
+
+What these classes share with the reference is its public surface only -- class / method / keyword names, the
+parameter `grid`, the buffers `mask`, `xyz2ijk_scale`, `xyz2ijk_shift` -- because the reference's callers, configs and
+checkpoints address them by those names; the bodies are written against this library's ops.
 """
 import torch
 import torch.nn as nn
@@ -92,31 +96,33 @@ class DenseGrid(nn.Module):
 
 
 class MaskGrid(nn.Module):
+    """Known-free-space lookup on a boolean occupancy grid (model/grid.py:253-287).  Kept exactly, because state_dicts
+    and callers name them: the constructor keywords and the buffers `mask`, `xyz2ijk_scale`, `xyz2ijk_shift` (registered
+    in that order); the lookup itself is fgs_maskcache_lookup."""
+
     def __init__(self, path=None, mask_cache_thres=None, mask=None, xyz_min=None, xyz_max=None):
         super().__init__()
-        if path is not None:
-            st = torch.load(path)
-            self.mask_cache_thres = mask_cache_thres
-            alpha = F.max_pool3d(st['model_state_dict']['alpha.grid'], kernel_size=3, padding=1, stride=1)
-            mask = (alpha >= self.mask_cache_thres).squeeze(0).squeeze(0)
-            xyz_min = torch.Tensor(st['model_kwargs']['xyz_min'])
-            xyz_max = torch.Tensor(st['model_kwargs']['xyz_max'])
+        if path is None:
+            occupied = mask.bool()
         else:
-            mask = mask.bool()
-            xyz_min = torch.Tensor(xyz_min)
-            xyz_max = torch.Tensor(xyz_max)
-        self.register_buffer('mask', mask)
-        xyz_len = xyz_max - xyz_min
-        self.register_buffer('xyz2ijk_scale', (torch.Tensor(list(mask.shape)) - 1) / xyz_len)
-        self.register_buffer('xyz2ijk_shift', -xyz_min * self.xyz2ijk_scale)
+            # checkpoint of an earlier stage: occupied where the 3^3 max-pooled alpha reaches the threshold
+            ckpt = torch.load(path)
+            self.mask_cache_thres = mask_cache_thres
+            pooled = F.max_pool3d(ckpt['model_state_dict']['alpha.grid'], kernel_size=3, padding=1, stride=1)
+            occupied = (pooled >= mask_cache_thres)[0, 0]
+            xyz_min, xyz_max = (ckpt['model_kwargs'][k] for k in ('xyz_min', 'xyz_max'))
+        lo, hi = torch.Tensor(xyz_min), torch.Tensor(xyz_max)
+        scale = (torch.Tensor(list(occupied.shape)) - 1) / (hi - lo)
+        self.register_buffer('mask', occupied)
+        self.register_buffer('xyz2ijk_scale', scale)
+        self.register_buffer('xyz2ijk_shift', -lo * scale)
 
     @torch.no_grad()
     def forward(self, xyz):
-        '''Skip known free space.  xyz: [..., 3] global coordinates.'''
-        shape = xyz.shape[:-1]
-        xyz = xyz.reshape(-1, 3).contiguous()
-        mask = render_utils_cuda.maskcache_lookup(self.mask, xyz, self.xyz2ijk_scale, self.xyz2ijk_shift)
-        return mask.reshape(shape)
+        """xyz [..., 3] world coordinates -> bool [...]: True where the point's nearest cell is occupied."""
+        pts = xyz.reshape(-1, 3).contiguous()
+        hit = render_utils_cuda.maskcache_lookup(self.mask, pts, self.xyz2ijk_scale, self.xyz2ijk_shift)
+        return hit.reshape(xyz.shape[:-1])
 
     def extra_repr(self):
         return f'mask.shape={list(self.mask.shape)}'
