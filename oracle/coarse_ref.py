@@ -40,6 +40,8 @@ class CoarseModel:
         self.smooth_weight = gaussian_3dconv_weight(cfg["smooth_ksize"], cfg["smooth_sigma"], dev) \
             if cfg.get("smooth_ksize", 0) > 0 else None
         self.nonempty_mask = None
+        self.stage = cfg.get("stage", "coarse")           # 'coarse' | 'geometry_searching' (model/nerf.py:47-50)
+        self.inc_mask = None                              # (mask bool [X,Y,Z], xyz2ijk_scale, xyz2ijk_shift) of a MaskGrid
 
     def params(self):
         out = [("sdf", self.sdf), ("k0", self.k0)]
@@ -49,10 +51,30 @@ class CoarseModel:
 
     @torch.no_grad()
     def set_nonempty_mask(self):
-        """model/nerf.py:339-353; in the coarse stage the SDF outside the mask is overwritten with 1."""
+        """model/nerf.py:339-353; in the coarse stage the SDF outside the mask is overwritten with 1.  The
+        geometry_searching stage has no MaskCache and no non-empty mask (:158-161)."""
+        if self.stage != "coarse":
+            return None
         R.FineModel.set_nonempty_mask(self)
         self.sdf[~self.nonempty_mask] = 1
         return self.nonempty_mask
+
+    @torch.no_grad()
+    def set_inc_mask(self, lower, upper):
+        """nerf.set_inc_mask (model/nerf.py:1078-1088) + MaskGrid.__init__ (model/grid.py:253-272): the voxels of the
+        unit-cube lattice inside [lower, upper] (Incremental Voxel Training), looked up with maskcache_lookup."""
+        X, Y, Z = (int(v) for v in self.sdf.shape[2:])
+        xyz = torch.stack(torch.meshgrid(torch.linspace(0, 1, X), torch.linspace(0, 1, Y), torch.linspace(0, 1, Z), indexing="ij"))
+        mask = (xyz[0] >= lower[0]) & (xyz[0] <= upper[0]) & (xyz[1] >= lower[1]) & (xyz[1] <= upper[1]) & \
+               (xyz[2] >= lower[2]) & (xyz[2] <= upper[2])
+        xyz_min, xyz_max = self.xyz_min.cpu(), self.xyz_max.cpu()
+        scale = (torch.Tensor(list(mask.shape)) - 1) / (xyz_max - xyz_min)
+        shift = -xyz_min * scale
+        dev = self.device
+        self.inc_mask = (mask.to(dev).contiguous(), scale.to(dev), shift.to(dev))
+
+    def unset_inc_mask(self):
+        self.inc_mask = None
 
 
 def gaussian_3dconv_weight(ksize, sigma, device):
@@ -80,7 +102,7 @@ def sample_grid(m, xyz, grid):
 
 def forward_coarse(m, native, rays_o, rays_d, viewdirs, global_step, near, stepsize, bg, render_depth=True,
                    render_grad=True, stages=None):
-    """model/nerf.py:943-1075 (stage 'coarse', inc_mask unset, use_viewdir)."""
+    """model/nerf.py:943-1075 (stages 'coarse' and 'geometry_searching', optional inc_mask, use_viewdir)."""
     A2W = R.make_alphas2weights(native)
     N = len(rays_o)
     # sample_ray_cuda (:700-732): far = 1e9, masked to the bbox
@@ -90,9 +112,14 @@ def forward_coarse(m, native, rays_o, rays_d, viewdirs, global_step, near, steps
     mask_inbbox = ~mask_outbbox
     ray_pts, ray_id, step_id = ray_pts[mask_inbbox], ray_id[mask_inbbox], step_id[mask_inbbox]
     viewdirs_pts = viewdirs[ray_id]
-    mask = R.mask_cache(m, ray_pts)                                   # :953-960
-    ray_pts, ray_id, viewdirs_pts, step_id = ray_pts[mask], ray_id[mask], viewdirs_pts[mask], step_id[mask]
-    mask_outbbox[~mask_outbbox] |= ~mask
+    if m.stage == "coarse":                                           # :952-960 (geometry_searching: no MaskCache)
+        mask = R.mask_cache(m, ray_pts)
+        ray_pts, ray_id, viewdirs_pts, step_id = ray_pts[mask], ray_id[mask], viewdirs_pts[mask], step_id[mask]
+        mask_outbbox[~mask_outbbox] |= ~mask
+    if m.inc_mask is not None:                                        # :962-967 Voxel Inc (MaskGrid.forward, grid.py:274-284)
+        imask, iscale, ishift = m.inc_mask
+        mask = native.maskcache_lookup(imask, ray_pts.reshape(-1, 3).contiguous(), iscale, ishift)
+        ray_pts, ray_id, viewdirs_pts, step_id = ray_pts[mask], ray_id[mask], viewdirs_pts[mask], step_id[mask]
     sdf_grid = smooth_conv(m, m.sdf) if m.smooth_weight is not None else m.sdf     # :969
     sdf = sample_grid(m, ray_pts, sdf_grid)                            # :971
     grad_grid = R.neus_sdf_gradient(m)                                 # :972, from the RAW sdf grid ('interpolate')

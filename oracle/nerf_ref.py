@@ -50,6 +50,9 @@ class CpuNative:
                                                     alphainv_last.numpy(), i_start.numpy(), i_end.numpy(),
                                                     n_rays, gw.contiguous().numpy(), gl.contiguous().numpy()))
 
+    def maskcache_lookup(self, mask, xyz, scale, shift):
+        return self._t(self.o.maskcache_lookup(mask.numpy(), xyz.numpy(), scale.numpy(), shift.numpy()))
+
     def adam(self, mode, param, grad, m, v, step, beta1, beta2, lr, eps):
         fn = self.o.masked_adam_upd if mode == "masked" else self.o.adam_upd
         p = param.detach().numpy()
@@ -79,6 +82,9 @@ class RefCudaNative:
     def alpha2weight_backward(self, alpha, weight, T, last, i_s, i_e, n_rays, gw, gl):
         return self.ru.alpha2weight_backward(alpha.detach(), weight, T, last, i_s, i_e, n_rays,
                                              gw.contiguous(), gl.contiguous())
+
+    def maskcache_lookup(self, mask, xyz, scale, shift):
+        return self.ru.maskcache_lookup(mask, xyz, scale, shift)
 
     def adam(self, mode, param, grad, m, v, step, beta1, beta2, lr, eps):
         fn = self.ad.masked_adam_upd if mode == "masked" else self.ad.adam_upd
