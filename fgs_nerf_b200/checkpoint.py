@@ -50,9 +50,10 @@ def model_state_dict(eng, global_step=None):
     for key, i in _mlp_items(eng):
         sd[key + ".weight"] = eng.weights[i].detach().clone().contiguous()
         sd[key + ".bias"] = (eng.biases[i] if hasattr(eng, "biases") else eng.Bt[i]).detach().clone()
-    sd["mask_cache.xyz_min"] = eng.mask_xyz_min.to(dev)
-    sd["mask_cache.xyz_max"] = eng.mask_xyz_max.to(dev)
-    sd["mask_cache.sdf_mask"] = eng.mask_grid.clone()
+    if eng.mask_grid is not None:                    # (the geometry_searching stage has no MaskCache)
+        sd["mask_cache.xyz_min"] = eng.mask_xyz_min.to(dev)
+        sd["mask_cache.xyz_max"] = eng.mask_xyz_max.to(dev)
+        sd["mask_cache.sdf_mask"] = eng.mask_grid.clone()
     # nerf.set_sdf_mask (model/nerf.py:181-186), what the NEXT stage's MaskCache reads (nerf.py:1199)
     sd["sdf_mask.grid"] = (eng.sdf.detach() < 0.5).float() * 1e-3
     return sd
@@ -73,6 +74,8 @@ def optimizer_state_dict(eng):
         for kind, i in per_group[name]:
             if i is None:
                 m, v = eng.adam[kind]
+                if kind == "k0" and m.shape[1] != eng.k0.shape[1]:       # (coarse stages: 12-channel storage of a narrower grid)
+                    m, v = m[:, :eng.k0.shape[1]], v[:, :eng.k0.shape[1]]
                 m, v = m.contiguous().clone(), v.contiguous().clone()
             elif kind == "W":       # (the engines store the layers zero-padded: cut back to nn.Linear's shape)
                 o, n_in = eng.weights[i].shape
@@ -98,7 +101,7 @@ def _coarse_model_kwargs(eng):
         "xyz_min": eng.xyz_min.cpu().numpy(), "xyz_max": eng.xyz_max.cpu().numpy(),
         "num_voxels": eng.num_voxels, "num_voxels_base": eng.num_voxels_base, "voxel_size": torch.tensor(float(eng.voxel_size)),
         "nearest": False, "k0_dim": c["k0_dim"], "grad_feat": (), "sdf_feat": (), "center_sdf": True,
-        "fast_color_thres": float(c["fast_color_thres"]), "stage": "coarse", "ref": True, "use_viewdir": True,
+        "fast_color_thres": float(c["fast_color_thres"]), "stage": eng.stage, "ref": True, "use_viewdir": True,
         "s_ratio": c["s_ratio"], "s_start": c["s_start"],
         "rgbnet_dim": rgb_dim, "rgbnet_width": c.get("rgbnet_width", 192), "rgbnet_depth": c.get("rgbnet_depth", 3),
         "refnet_dim": eng.in_dim, "refnet_width": c["refnet_width"], "refnet_depth": c["refnet_depth"],
@@ -219,7 +222,7 @@ def coarse_engine_from_checkpoint(ckpt, n_rays, device="cuda", model_cfg=None, t
         ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
     sd, mk = ckpt["model_state_dict"], ckpt.get("model_kwargs", {})
     cfg = dict(model_cfg if model_cfg is not None else COARSE_MODEL)
-    for k in ("k0_dim", "s_ratio", "s_start", "fast_color_thres", "refnet_width", "refnet_depth"):
+    for k in ("k0_dim", "s_ratio", "s_start", "fast_color_thres", "refnet_width", "refnet_depth", "stage"):
         if k in mk:
             cfg[k] = mk[k]
     for key, name in (("posfreq", "posbase_pe"), ("viewfreq", "viewbase_pe"), ("reffreq", "refbase_pe")):
@@ -229,9 +232,14 @@ def coarse_engine_from_checkpoint(ckpt, n_rays, device="cuda", model_cfg=None, t
     xyz_min, xyz_max = sd["xyz_min"].float().cpu(), sd["xyz_max"].float().cpu()
     voxel_size = float(mk["voxel_size"]) if "voxel_size" in mk else float(((xyz_max - xyz_min).prod() / sdf[0, 0].numel()).pow(1 / 3))
     refnet = [(sd[f"refnet.{i}.weight"].float(), sd[f"refnet.{i}.bias"].float()) for i in _LIN3]
+    cfg["k0_dim"] = int(k0.shape[1])
+    if "mask_cache.sdf_mask" in sd:
+        mg, mmin, mmax = sd["mask_cache.sdf_mask"].float(), sd["mask_cache.xyz_min"].float().cpu(), sd["mask_cache.xyz_max"].float().cpu()
+    else:                                            # geometry_searching: no MaskCache
+        cfg["stage"] = "geometry_searching"
+        mg, mmin, mmax = torch.zeros(1, 1, 2, 2, 2), xyz_min, xyz_max
     sc = Scene(G=int(sdf.shape[2]), xyz_min=xyz_min, xyz_max=xyz_max, voxel_size=voxel_size, sdf=sdf, k0=k0,
-               mask_grid=sd["mask_cache.sdf_mask"].float(), mask_xyz_min=sd["mask_cache.xyz_min"].float().cpu(),
-               mask_xyz_max=sd["mask_cache.xyz_max"].float().cpu(), mask_thres=cfg["mask_cache_thres"], cfg=cfg)
+               mask_grid=mg, mask_xyz_min=mmin, mask_xyz_max=mmax, mask_thres=cfg["mask_cache_thres"], cfg=cfg)
     eng = CoarseStepEngine(sc, refnet, n_rays, device, cfg=cfg, train_cfg=train_cfg, **kw)
     if "num_voxels" in mk:
         eng.num_voxels = mk["num_voxels"]
@@ -259,7 +267,7 @@ def coarse_engine_from_checkpoint(ckpt, n_rays, device="cuda", model_cfg=None, t
 
         for name in ("k0", "sdf"):
             e = st[ids[name][0]]
-            put(eng.adam[name][0], e["exp_avg"])
+            put(eng.adam[name][0], e["exp_avg"])             # (k0: into the first k0_dim channels of the 12-channel storage)
             put(eng.adam[name][1], e["exp_avg_sq"])
         for j in range(3):
             w, b = st[ids["refnet"][2 * j]], st[ids["refnet"][2 * j + 1]]

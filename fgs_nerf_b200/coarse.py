@@ -42,7 +42,7 @@ class FgsCoarse(C.Structure):
     _fields_ = [
         ("sdf_smooth", _fp), ("grad_grid", _fp), ("g_smooth", _fp), ("g_grad_grid", _fp),
         ("in_dim", C.c_int32), ("in_ld", C.c_int32),
-        ("pos_pe", C.c_int32), ("view_pe", C.c_int32), ("ref_pe", C.c_int32), ("pad_", C.c_int32),
+        ("pos_pe", C.c_int32), ("view_pe", C.c_int32), ("ref_pe", C.c_int32), ("k0_dim", C.c_int32),
     ]
 
 
@@ -55,6 +55,7 @@ _lib.declare("fgs_sdf_gradient_grid", _i, [_fp, _fp, _i, _i, _i, C.c_float, _fp]
 _lib.declare("fgs_sdf_gradient_grid_bwd", _i, [_fp, _fp, _i, _i, _i, C.c_float, _fp])
 _lib.declare("fgs_conv3d_replicate_bwd", _i, [_fp, _fp, _i, _i, _i, _fp, _i, _fp])
 _lib.declare("fgs_l1_tv_add_grad", _i, [_fp, _fp, _fp, _i, _i, _i, C.c_double, C.c_double, _fp, _fp])
+_lib.declare("fgs_l1_tv_unmasked_add_grad", _i, [_fp, _fp, _i, _i, _i, C.c_double, _fp, _fp, _fp])
 
 
 def sdf_gradient_grid(sdf, voxel_size):
@@ -132,8 +133,11 @@ class CoarseStepEngine(FineStepEngine):
         self.train_cfg = dict(COARSE_TRAIN)
         self.train_cfg.update(train_cfg or {})
         c = self.cfg
-        if c["k0_dim"] != K0_DIM:
-            raise NotImplementedError(f"coarse stage: k0_dim must be {K0_DIM} (got {c['k0_dim']})")
+        self.stage = c.get("stage", "coarse")
+        if self.stage not in ("coarse", "geometry_searching"):
+            raise NotImplementedError(f"CoarseStepEngine: stage {self.stage!r} (forward_coarse stages: coarse, geometry_searching)")
+        if not (0 < c["k0_dim"] <= K0_DIM):
+            raise NotImplementedError(f"coarse stages: k0_dim must be 1..{K0_DIM} (got {c['k0_dim']})")
         if c["refnet_depth"] != 3 or len(refnet) != 3:
             raise NotImplementedError("coarse stage: refnet_depth must be 3 (in -> width -> width -> 3)")
         self.n_rays = int(n_rays)
@@ -146,15 +150,25 @@ class CoarseStepEngine(FineStepEngine):
         self.mask_xyz_min, self.mask_xyz_max = scene.mask_xyz_min.clone().float(), scene.mask_xyz_max.clone().float()
         self.voxel_size = np.float32(scene.voxel_size)
         self.sdf = scene.sdf.to(dev, f32).contiguous().clone()
-        self.k0 = scene.k0.to(dev, f32).contiguous(memory_format=torch.channels_last_3d).clone()
-        self.mask_grid = scene.mask_grid.to(dev, f32).contiguous()
+        # the feature grid is stored with 12 channels-last channels whatever k0_dim is (the gather / scatter / brick-Adam
+        # kernels move three float4 per voxel); channels beyond k0_dim are 0 and stay 0 (their gradient is exactly 0, the
+        # masked Adam skips them): self.k0 / self.g_k0 are the [1, k0_dim, X, Y, Z] views the reference's names refer to
+        kd = int(c["k0_dim"])
+        if tuple(scene.k0.shape[1:2]) != (kd,):
+            raise RuntimeError(f"k0 grid has {scene.k0.shape[1]} channels, config says k0_dim {kd}")
+        self._k0_store = torch.zeros((1, K0_DIM) + tuple(scene.k0.shape[2:]), dtype=f32, device=dev).contiguous(
+            memory_format=torch.channels_last_3d)
+        self._k0_store[:, :kd] = scene.k0.to(dev, f32)
+        self.k0 = self._k0_store if kd == K0_DIM else self._k0_store[:, :kd]
+        # geometry_searching has no MaskCache (model/nerf.py:158-161): every in-bbox sample passes
+        self.mask_grid = scene.mask_grid.to(dev, f32).contiguous() if self.stage == "coarse" else None
         self.mask_thres = np.float32(c["mask_cache_thres"])
         self.fast_color_thres = np.float32(c["fast_color_thres"])
         X, Y, Z = self.sdf.shape[2:]
         self.X, self.Y, self.Z = X, Y, Z
         self.num_voxels = self.num_voxels_base = X * Y * Z
         self.width = int(c["refnet_width"])
-        self.in_dim = K0_DIM + (3 + 6 * c["posbase_pe"]) + (3 + 6 * c["refbase_pe"]) + 3 + (3 + 6 * c["viewbase_pe"])
+        self.in_dim = kd + (3 + 6 * c["posbase_pe"]) + (3 + 6 * c["refbase_pe"]) + 3 + (3 + 6 * c["viewbase_pe"])
         self.in_ld = (self.in_dim + 31) // 32 * 32
         w = self.width
         if not (0 < w <= WIDTH) or self.in_ld > 256:
@@ -173,7 +187,10 @@ class CoarseStepEngine(FineStepEngine):
             self.Bt.append(bt); self.biases.append(bt[:d[0]])
         # ---- gradients ----
         self.g_sdf = torch.zeros_like(self.sdf)
-        self.g_k0 = torch.zeros_like(self.k0)
+        self._g_k0_store = torch.zeros_like(self._k0_store)
+        self.g_k0 = self._g_k0_store if kd == K0_DIM else self._g_k0_store[:, :kd]
+        self.inc_mask = None
+        self._tv_sums = torch.zeros(2, dtype=torch.float64, device=dev)
         sizes = [t.numel() for t in self.Wt] + [t.numel() for t in self.Bt]
         offs = [0]
         for n in sizes:
@@ -246,7 +263,7 @@ class CoarseStepEngine(FineStepEngine):
         P, ws, c = self.P, self.ws, self.cfg
         P.n_rays = self.n_rays
         P.X, P.Y, P.Z = self.X, self.Y, self.Z
-        P.mX, P.mY, P.mZ = self.mask_grid.shape[2:]
+        P.mX, P.mY, P.mZ = self.mask_grid.shape[2:] if self.mask_grid is not None else (0, 0, 0)
         P.cap_words, P.cap_m1, P.cap_m2 = self.cap_words, self.cap_m1, self.cap_m2
         for k in range(3):
             P.xyz_min[k] = float(self.xyz_min[k]); P.xyz_max[k] = float(self.xyz_max[k])
@@ -257,19 +274,21 @@ class CoarseStepEngine(FineStepEngine):
         P.mask_thres = float(self.mask_thres)
         P.fast_color_thres = float(self.fast_color_thres)
         P.far_ = 1e9
-        P.sdf, P.k0, P.mask_grid = ptr(self.sdf), ptr(self.k0), ptr(self.mask_grid)
+        P.sdf, P.k0, P.mask_grid = ptr(self.sdf), ptr(self._k0_store), ptr(self.mask_grid)
         for slot, i in ((0, 0), (1, 1), (LAST, 2)):
             P.W[slot], P.B[slot] = ptr(self.Wt[i]), ptr(self.Bt[i])
             P.gW[slot], P.gB[slot] = ptr(self.gW[i]), ptr(self.gB[i])
-        P.g_sdf, P.g_k0 = ptr(self.g_sdf), ptr(self.g_k0)
+        P.g_sdf, P.g_k0 = ptr(self.g_sdf), ptr(self._g_k0_store)
         P.g_mlp_flat, P.g_mlp_floats = ptr(self.g_mlp_flat), self.g_mlp_flat.numel()
         for k in ("t_min", "t_max", "n_steps", "cnt1", "cnt2", "off1", "off2", "bits", "alphainv_last", "ray_id1",
                   "step_id1", "flag1", "sdf1", "grad1", "alpha1", "w1", "T1", "d_sdf1", "d_grad1", "d_w1", "idx1_of2",
                   "ray_id2", "X0", "H", "logit", "normal2", "rgb_marched", "sigmoid_rgb", "cum_weights", "depth",
                   "normal_marched", "counters", "dX0", "dlogit", "w_split", "hbits", "k0_brick_flags", "dZ", "dlogit_p"):
             setattr(P, k, ptr(ws[k]))
-        self._build_mask_occupancy()
+        if self.mask_grid is not None:
+            self._build_mask_occupancy()
         Cc = self.Cc
+        Cc.k0_dim = int(c["k0_dim"])
         # without a smoother (smooth_ksize 0) the SDF is sampled from the raw grid and its gradient lands in g_sdf directly
         Cc.sdf_smooth = ptr(self.sdf_smooth if self.smooth_ksize > 0 else self.sdf)
         Cc.g_smooth = ptr(self.g_smooth if self.smooth_ksize > 0 else self.g_sdf)
@@ -289,11 +308,62 @@ class CoarseStepEngine(FineStepEngine):
             self.Cc.g_smooth = ptr(self.g_smooth if ksize > 0 else self.g_sdf)
 
     def set_nonempty_mask(self):
-        """nerf._set_nonempty_mask (model/nerf.py:339-353): in the coarse stage the SDF outside the mask becomes 1."""
+        """nerf._set_nonempty_mask (model/nerf.py:339-353): in the coarse stage the SDF outside the mask becomes 1.
+        geometry_searching has neither a MaskCache nor a non-empty mask (:158-161)."""
+        if self.stage != "coarse":
+            self.nonempty_mask = None
+            return None
         m = super().set_nonempty_mask()
         with torch.no_grad():
             self.sdf[0, 0][~m] = 1
         return m
+
+    @torch.no_grad()
+    def set_inc_mask(self, lower, upper):
+        """nerf.set_inc_mask (model/nerf.py:1078-1088) + MaskGrid (grid.py:253-272): Incremental Voxel Training keeps only
+        the samples whose nearest voxel lies in the box [lower, upper] of the unit-cube lattice.  The three 1-D lattices
+        are torch.linspace(0, 1, n) evaluated on the CPU like the reference's (bit-identical comparisons), the box is
+        assembled on the device."""
+        if getattr(self, "_inc_lin", None) is None:
+            self._inc_lin = [torch.linspace(0, 1, n).to(self.device) for n in (self.X, self.Y, self.Z)]
+            ext = (self.xyz_max - self.xyz_min).float()
+            scale = (torch.Tensor([self.X, self.Y, self.Z]) - 1) / ext
+            shift = -self.xyz_min.float() * scale
+            for k in range(3):
+                self.P.inc_scale[k], self.P.inc_shift[k] = float(scale[k]), float(shift[k])
+            self.P.iX, self.P.iY, self.P.iZ = self.X, self.Y, self.Z
+        lo = torch.as_tensor(lower, dtype=torch.float32)
+        hi = torch.as_tensor(upper, dtype=torch.float32)
+        ax = [(l >= float(lo[k])) & (l <= float(hi[k])) for k, l in enumerate(self._inc_lin)]
+        self.inc_mask = (ax[0][:, None, None] & ax[1][None, :, None] & ax[2][None, None, :]).to(torch.uint8).contiguous()
+        self.P.inc_mask = ptr(self.inc_mask)
+
+    def unset_inc_mask(self):
+        self.inc_mask = None
+        self.P.inc_mask = None
+
+    @torch.no_grad()
+    def reset_refnet(self):
+        """nerf.reset_voxel_and_mlp (model/nerf.py:384-396; `reset_iter`): a freshly initialised refnet (nn.Linear's
+        default init from torch's global RNG, like the reference's constructor); the optimiser is the caller's business."""
+        import torch.nn as nn
+        w = self.width
+        for i, (n_in, n_out) in enumerate(((self.in_dim, w), (w, w), (w, 3))):
+            lin = nn.Linear(n_in, n_out)
+            self.Wt[i].zero_(); self.Bt[i].zero_()
+            self.weights[i].copy_(lin.weight.data.to(self.device))
+            self.biases[i].copy_(lin.bias.data.to(self.device))
+
+    @torch.no_grad()
+    def maskout_near_cam_vox(self, cam_o, near):
+        """nerf.maskout_near_cam_vox (model/nerf.py:355-367): sdf = 5 at the voxels closer than `near` to any camera."""
+        g = torch.stack(torch.meshgrid(
+            torch.linspace(float(self.xyz_min[0]), float(self.xyz_max[0]), self.X),
+            torch.linspace(float(self.xyz_min[1]), float(self.xyz_max[1]), self.Y),
+            torch.linspace(float(self.xyz_min[2]), float(self.xyz_max[2]), self.Z), indexing="ij"), -1).to(self.device)
+        nearest = torch.stack([(g.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1)
+                               for co in cam_o.to(self.device).split(100)]).amin(0)
+        self.sdf[0, 0][nearest <= near] = 5
 
     # -------------------------------------------------------------------------------------
     def forward(self, rays_o, rays_d, viewdirs, global_step=20000, near=2.0, bg=1.0, render_depth=False,
@@ -315,7 +385,7 @@ class CoarseStepEngine(FineStepEngine):
             with torch.cuda.device(self.device):
                 st = stream()
                 check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
-                check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
+                check(lib.fgs_memset_zero(ptr(self._g_k0_store), self._g_k0_store.numel() * 4, st))
                 check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
             self._grads_clean = True
 
@@ -348,9 +418,15 @@ class CoarseStepEngine(FineStepEngine):
     def sdf_l1_tv_add_grad(self):
         """ori_tv: weight_tv_density * density_total_variation(sdf_tv) (model/nerf_training.py:337-338, nerf.py:430-437)."""
         t = self.train_cfg
-        if self.nonempty_mask is None:
-            raise RuntimeError("the SDF TV of the coarse stage needs the non-empty mask (set_nonempty_mask)")
         w = t["weight_tv_density"] * t["sdf_tv"] / 2.0 / float(self.voxel_size)
+        if self.nonempty_mask is None:
+            if self.stage == "coarse":
+                raise RuntimeError("the SDF TV of the coarse stage needs the non-empty mask (set_nonempty_mask)")
+            # geometry_searching: total_variation(sdf) without a mask divides by sdf.sum() (model/nerf.py:1221)
+            with torch.cuda.device(self.device):
+                check(lib.fgs_l1_tv_unmasked_add_grad(ptr(self.sdf), ptr(self.g_sdf), self.X, self.Y, self.Z, float(w),
+                                                      ptr(self._tv_sums), self.ws["loss"].data_ptr() + 5 * 8, stream()))
+            return
         with torch.cuda.device(self.device):
             check(lib.fgs_l1_tv_add_grad(ptr(self.sdf), ptr(self.nonempty_mask), ptr(self.g_sdf), self.X, self.Y, self.Z,
                                          float(w), float(self.n_nonempty), self.ws["loss"].data_ptr() + 5 * 8, stream()))
@@ -366,7 +442,7 @@ class CoarseStepEngine(FineStepEngine):
         if self.adam:
             return
         z = torch.zeros_like
-        self.adam = {"sdf": (z(self.sdf), z(self.sdf)), "k0": (z(self.k0), z(self.k0)),
+        self.adam = {"sdf": (z(self.sdf), z(self.sdf)), "k0": (z(self._k0_store), z(self._k0_store)),
                      "W": [(z(w), z(w)) for w in self.Wt], "B": [(z(b), z(b)) for b in self.Bt]}
         n = 6
         self._mt = dict(
@@ -392,13 +468,13 @@ class CoarseStepEngine(FineStepEngine):
             check(lib.fgs_memset_zero(ptr(self.g_sdf), self.g_sdf.numel() * 4, st))
             m, v = self.adam["k0"]
             if self.sparse_k0 and "k0" in skip:
-                check(lib.fgs_adam_upd_brick_flags(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), ptr(self.ws["k0_brick_flags"]),
+                check(lib.fgs_adam_upd_brick_flags(ptr(self._k0_store), ptr(self._g_k0_store), ptr(m), ptr(v), ptr(self.ws["k0_brick_flags"]),
                                                    ptr(self.ws["k0_brick_ulist"]), self.X, self.Y, self.Z, K0_DIM, step, b1, b2,
                                                    self.lr["k0"] * lr_scale, eps, st))
             else:
-                check(lib.fgs_adam_upd(ptr(self.k0), ptr(self.g_k0), ptr(m), ptr(v), None, self.k0.numel(), step, b1, b2,
-                                       self.lr["k0"] * lr_scale, eps, 1 if "k0" in skip else 0, st))
-                check(lib.fgs_memset_zero(ptr(self.g_k0), self.g_k0.numel() * 4, st))
+                check(lib.fgs_adam_upd(ptr(self._k0_store), ptr(self._g_k0_store), ptr(m), ptr(v), None, self._k0_store.numel(),
+                                       step, b1, b2, self.lr["k0"] * lr_scale, eps, 1, st))   # (masked: the pad channels must stay 0)
+                check(lib.fgs_memset_zero(ptr(self._g_k0_store), self._g_k0_store.numel() * 4, st))
                 check(lib.fgs_memset_zero(ptr(self.ws["k0_brick_flags"]), self.ws["k0_brick_flags"].numel(), st))
             self._grads_clean = True
             n = 6
@@ -441,7 +517,8 @@ class CoarseStepEngine(FineStepEngine):
         voxel_size = (ext.prod() / num_voxels).pow(1 / 3)
         world_size = (ext / voxel_size).long().tolist()
         sc = Scene(G=int(world_size[0]), xyz_min=self.xyz_min, xyz_max=self.xyz_max, voxel_size=float(voxel_size),
-                   sdf=grid_resize(self.sdf, world_size), k0=grid_resize(self.k0, world_size), mask_grid=self.mask_grid,
+                   sdf=grid_resize(self.sdf, world_size), k0=grid_resize(self._k0_store, world_size)[:, :int(self.cfg["k0_dim"])],
+                   mask_grid=self.mask_grid if self.mask_grid is not None else torch.zeros(1, 1, 2, 2, 2),
                    mask_xyz_min=self.mask_xyz_min, mask_xyz_max=self.mask_xyz_max, mask_thres=float(self.mask_thres))
         refnet = [(w.clone(), b.clone()) for w, b in zip(self.weights, self.biases)]
         had_mask = self.nonempty_mask is not None

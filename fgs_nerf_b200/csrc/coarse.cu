@@ -48,7 +48,7 @@ struct RowMap {
 __host__ __device__ inline RowMap row_map(const FgsCoarse& C) {
   RowMap m;
   m.k0 = 0;
-  m.xyz = FGS_K0_DIM;
+  m.xyz = (C.k0_dim > 0 && C.k0_dim < FGS_K0_DIM) ? C.k0_dim : FGS_K0_DIM;
   m.ref = m.xyz + 3 + 6 * C.pos_pe;
   m.nrm = m.ref + 3 + 6 * C.ref_pe;
   m.view = m.nrm + 3;
@@ -213,9 +213,16 @@ coarse_feat_kernel(const __grid_constant__ FgsFineParams P, const __grid_constan
           a2 = fma4(__ldg(reinterpret_cast<const float4*>(v) + 2), t.w[c], a2);
         }
       }
-      st4(row + rm.k0, a0);
-      st4(row + rm.k0 + 4, a1);
-      st4(row + rm.k0 + 8, a2);
+      if (rm.xyz == FGS_K0_DIM) {
+        st4(row + rm.k0, a0);
+        st4(row + rm.k0 + 4, a1);
+        st4(row + rm.k0 + 8, a2);
+      } else {                                              // fewer feature channels: only they enter the row
+        const float a[FGS_K0_DIM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+        for (int ch = 0; ch < FGS_K0_DIM; ++ch)
+          if (ch < rm.xyz) row[rm.k0 + ch] = a[ch];
+      }
     } else if (task == kTaskPE) {
       const float rx[3] = {__fdiv_rn(__fsub_rn(q.px, g.mn[0]), g.ext[0]), __fdiv_rn(__fsub_rn(q.py, g.mn[1]), g.ext[1]),
                            __fdiv_rn(__fsub_rn(q.pz, g.mn[2]), g.ext[2])};
@@ -254,7 +261,15 @@ coarse_feat_bwd_kernel(const __grid_constant__ FgsFineParams P, const __grid_con
       float iw, ih, id;
       cont_index(g, q.px, q.py, q.pz, iw, ih, id);
       const Tri t = tri_setup(iw, ih, id);
-      const float4 d0 = ld4(drow + rm.k0), d1 = ld4(drow + rm.k0 + 4), d2 = ld4(drow + rm.k0 + 8);
+      float4 d0, d1, d2;
+      if (rm.xyz == FGS_K0_DIM) {
+        d0 = ld4(drow + rm.k0); d1 = ld4(drow + rm.k0 + 4); d2 = ld4(drow + rm.k0 + 8);
+      } else {                                              // the grid's pad channels receive exactly 0
+        float d[FGS_K0_DIM];
+#pragma unroll
+        for (int ch = 0; ch < FGS_K0_DIM; ++ch) d[ch] = ch < rm.xyz ? drow[rm.k0 + ch] : 0.f;
+        d0 = make_float4(d[0], d[1], d[2], d[3]); d1 = make_float4(d[4], d[5], d[6], d[7]); d2 = make_float4(d[8], d[9], d[10], d[11]);
+      }
       const int nbY = (g.Y + 3) >> 2, nbZ = (g.Z + 3) >> 2;
       int last_brick = -1;
 #pragma unroll
@@ -416,7 +431,8 @@ int check_coarse(const FgsFineParams* p, const FgsCoarse* c) {
   FGS_REQUIRE(c->sdf_smooth && c->grad_grid, "coarse grids are NULL");
   FGS_REQUIRE(c->pos_pe >= 0 && c->pos_pe <= 10 && c->view_pe >= 0 && c->view_pe <= 10 && c->ref_pe >= 0 && c->ref_pe <= 10,
               "encoding frequencies out of range (0..10)");
-  FGS_REQUIRE(c->in_dim == row_map(*c).dim, "in_dim does not match k0 12 + the three encodings + normal");
+  FGS_REQUIRE(c->k0_dim >= 0 && c->k0_dim <= FGS_K0_DIM, "k0_dim out of range (0 = 12)");
+  FGS_REQUIRE(c->in_dim == row_map(*c).dim, "in_dim does not match k0_dim + the three encodings + normal");
   FGS_REQUIRE(c->in_ld >= c->in_dim && (c->in_ld & 31) == 0 && c->in_ld <= 256, "in_ld must be a multiple of 32 in [in_dim, 256]");
   FGS_REQUIRE(p->w_split && p->hbits && p->X0 && p->H && p->logit, "MLP workspaces are NULL");
   return 0;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
   const int lane = lane_id();
   const GridGeo mg = make_geo(P.mask_xyz_min, P.mask_xyz_max, P.mX, P.mY, P.mZ);
   const float thres = P.mask_thres;
-  const uint32_t* __restrict__ occ = (thres > 0.f) ? P.mask_occ : nullptr;
+  const uint32_t* __restrict__ occ = (thres > 0.f && P.mask_grid != nullptr) ? P.mask_occ : nullptr;
   long long tot_steps = 0;
   int tot_m0 = 0;
   for (int ray = blockIdx.x * kWarps + (threadIdx.x >> 5); ray < P.n_rays; ray += gridDim.x * kWarps) {
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
       in = in && !((P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) |
                    (P.xyz_max[0] < px) | (P.xyz_max[1] < py) | (P.xyz_max[2] < pz));
       bool keep = false;
-      if (in) {
+      if (in && P.mask_grid == nullptr) keep = true;         // geometry_searching: no MaskCache
+      if (in && P.mask_grid != nullptr) {
         // MaskCache.forward, model/nerf.py:1202-1209
         float iw, ih, id;
         cont_index(mg, px, py, pz, iw, ih, id);
@@ -82,6 +83,14 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
           const Tri t = tri_setup(iw, ih, id);
           keep = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
         }
+      }
+      if (keep && P.inc_mask != nullptr) {
+        // Incremental Voxel Training: MaskGrid.forward = maskcache_lookup (render_utils_kernel.cu:374-392)
+        const int i = (int)roundf(__fmaf_rn(px, P.inc_scale[0], P.inc_shift[0]));
+        const int j = (int)roundf(__fmaf_rn(py, P.inc_scale[1], P.inc_shift[1]));
+        const int k = (int)roundf(__fmaf_rn(pz, P.inc_scale[2], P.inc_shift[2]));
+        keep = 0 <= i && i < P.iX && 0 <= j && j < P.iY && 0 <= k && k < P.iZ &&
+               P.inc_mask[((size_t)i * P.iY + j) * P.iZ + k] != 0;
       }
       const unsigned m0 = __ballot_sync(0xffffffffu, in);
       const unsigned word = __ballot_sync(0xffffffffu, keep);

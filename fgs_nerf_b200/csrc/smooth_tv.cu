@@ -314,6 +314,66 @@ l1_tv_kernel(const float* __restrict__ sdf, const unsigned char* __restrict__ ma
   }
 }
 
+// The unmasked branch of total_variation (model/nerf.py:1212-1221: `... / 3 / v.sum()`): pass 1 = S and sum(v)
+__global__ void __launch_bounds__(kBlock)
+l1_tv_sums_kernel(const float* __restrict__ sdf, int X, int Y, int Z, double* __restrict__ out2) {
+  const long long V = (long long)X * Y * Z;
+  const long long sj = Z, si = (long long)Z * Y;
+  double s_abs = 0., s_val = 0.;
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < V; idx += (long long)gridDim.x * kBlock) {
+    long long r = idx;
+    const int k = (int)(r % Z); r /= Z;
+    const int j = (int)(r % Y); r /= Y;
+    const int i = (int)r;
+    const float c = sdf[idx];
+    s_val += (double)c;
+    if (i + 1 < X) s_abs += (double)fabsf(sdf[idx + si] - c);
+    if (j + 1 < Y) s_abs += (double)fabsf(sdf[idx + sj] - c);
+    if (k + 1 < Z) s_abs += (double)fabsf(sdf[idx + 1] - c);
+  }
+  __shared__ double s[2][kBlock / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_abs += __shfl_xor_sync(0xffffffffu, s_abs, o);
+    s_val += __shfl_xor_sync(0xffffffffu, s_val, o);
+  }
+  if (lane_id() == 0) { s[0][threadIdx.x >> 5] = s_abs; s[1][threadIdx.x >> 5] = s_val; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.;
+    for (int w = 0; w < kBlock / 32; ++w) t += s[threadIdx.x][w];
+    atomicAdd(out2 + threadIdx.x, t);
+  }
+}
+
+// pass 2: d/dv [ w S / (3 sum) ] = w / (3 sum) * dS/dv - w S / (3 sum^2)
+__global__ void __launch_bounds__(kBlock)
+l1_tv_unmasked_grad_kernel(const float* __restrict__ sdf, float* __restrict__ g_sdf, int X, int Y, int Z, double weight,
+                           const double* __restrict__ sums, double* __restrict__ loss_out) {
+  const long long V = (long long)X * Y * Z;
+  const long long sj = Z, si = (long long)Z * Y;
+  const double S = sums[0], T = sums[1];
+  const float scale = (float)(weight / (3.0 * T));
+  const float shift = (float)(-weight * S / (3.0 * T * T));
+  if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(loss_out, weight * S / (3.0 * T));
+  for (long long idx = blockIdx.x * (long long)kBlock + threadIdx.x; idx < V; idx += (long long)gridDim.x * kBlock) {
+    long long r = idx;
+    const int k = (int)(r % Z); r /= Z;
+    const int j = (int)(r % Y); r /= Y;
+    const int i = (int)r;
+    const float c = sdf[idx];
+    float acc = 0.f;
+    auto sgn = [](float d) { return (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f); };
+    if (i + 1 < X) acc -= sgn(sdf[idx + si] - c);
+    if (i > 0) acc += sgn(c - sdf[idx - si]);
+    if (j + 1 < Y) acc -= sgn(sdf[idx + sj] - c);
+    if (j > 0) acc += sgn(c - sdf[idx - sj]);
+    if (k + 1 < Z) acc -= sgn(sdf[idx + 1] - c);
+    if (k > 0) acc += sgn(c - sdf[idx - 1]);
+    g_sdf[idx] += scale * acc + shift;
+  }
+}
+
 }  // namespace
 
 extern "C" int fgs_smooth_grad_tv_add_grad(const float* sdf, float* g_sdf, const uint8_t* nonempty,
@@ -385,5 +445,19 @@ extern "C" int fgs_l1_tv_add_grad(const float* sdf, const uint8_t* mask, float* 
   const long long V = (long long)X * Y * Z;
   const double s = weight / 3.0 / mask_count;
   l1_tv_kernel<<<fgs::stream_grid(V, kBlock, 8), kBlock, 0, st>>>(sdf, mask, g_sdf, X, Y, Z, (float)s, loss_out, s);
+  return fgs::check_launch("l1_tv_add_grad", st);
+}
+
+extern "C" int fgs_l1_tv_unmasked_add_grad(const float* sdf, float* g_sdf, int X, int Y, int Z, double weight, double* scratch2,
+                                           double* loss_out, fgs_stream_t stream) {
+  FGS_REQUIRE(sdf && g_sdf && scratch2 && X >= 2 && Y >= 2 && Z >= 2, "l1_tv_unmasked_add_grad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long V = (long long)X * Y * Z;
+  int rc = fgs::check_cuda(cudaMemsetAsync(scratch2, 0, 2 * sizeof(double), st), "l1_tv scratch memset");
+  if (rc) return rc;
+  const int grid = fgs::stream_grid(V, kBlock, 8);
+  l1_tv_sums_kernel<<<grid, kBlock, 0, st>>>(sdf, X, Y, Z, scratch2);
+  if ((rc = fgs::check_launch("l1_tv_add_grad", st))) return rc;
+  l1_tv_unmasked_grad_kernel<<<grid, kBlock, 0, st>>>(sdf, g_sdf, X, Y, Z, weight, scratch2, loss_out);
   return fgs::check_launch("l1_tv_add_grad", st);
 }

@@ -61,6 +61,8 @@ class FgsFineParams(C.Structure):
         ("dA", _fp), ("dB", _fp), ("dXR", _fp), ("dX0", _fp), ("dlogit", _fp), ("dlogit_p", _fp), ("dXRp", _fp),
         ("w_split", _fp), ("hbits", _fp), ("g_mlp_flat", _fp), ("g_mlp_floats", C.c_int64), ("k0_brick_flags", _fp),
         ("dZ", _fp), ("k0_vox_flags", _fp), ("mask_occ", _fp), ("sdf_brick_flags", _fp),
+        ("inc_mask", _fp), ("inc_scale", C.c_float * 3), ("inc_shift", C.c_float * 3),
+        ("iX", C.c_int32), ("iY", C.c_int32), ("iZ", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 

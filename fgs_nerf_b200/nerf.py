@@ -87,8 +87,8 @@ class nerf(nn.Module):
         import numpy as np
         from .engine import FineStepEngine
         from .scene import Scene
-        if stage == "coarse":
-            self._init_coarse(xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
+        if stage in ("coarse", "geometry_searching"):
+            self._init_coarse(stage, xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
                               fast_color_thres, k0_dim, ref, refnet_width, refnet_depth, posbase_pe, viewbase_pe, refbase_pe,
                               s_ratio, s_start, step_start, smooth_ksize, smooth_sigma, use_viewdir, stepsize, n_rays, device,
                               mask_cache, train_cfg)
@@ -144,7 +144,7 @@ class nerf(nn.Module):
         self.sdf = _GridView(lambda: self.engine.sdf)
         self.k0 = _GridView(lambda: self.engine.k0)
 
-    def _init_coarse(self, xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
+    def _init_coarse(self, stage, xyz_min, xyz_max, num_voxels, num_voxels_base, nearest, mask_cache_path, mask_cache_thres,
                      fast_color_thres, k0_dim, ref, refnet_width, refnet_depth, posbase_pe, viewbase_pe, refbase_pe, s_ratio,
                      s_start, step_start, smooth_ksize, smooth_sigma, use_viewdir, stepsize, n_rays, device, mask_cache,
                      train_cfg):
@@ -156,33 +156,38 @@ class nerf(nn.Module):
         bad = {}
         if not (ref and use_viewdir) or nearest:
             bad.update(ref=ref, use_viewdir=use_viewdir, nearest=nearest)
-        if k0_dim != 12 or refnet_depth != 3 or refnet_width > 256:
+        if not (0 < k0_dim <= 12) or refnet_depth != 3 or refnet_width > 256:
             bad.update(k0_dim=k0_dim, refnet_depth=refnet_depth, refnet_width=refnet_width)
         if bad:
-            raise NotImplementedError(f"fgs_b200.nerf(stage='coarse'): unsupported {bad}")
-        self.stage, self.ref, self.use_viewdir = "coarse", ref, use_viewdir
+            raise NotImplementedError(f"fgs_b200.nerf(stage={stage!r}): unsupported {bad}")
+        self.stage, self.ref, self.use_viewdir = stage, ref, use_viewdir
         xyz_min = torch.as_tensor(np.asarray(xyz_min), dtype=torch.float32)
         xyz_max = torch.as_tensor(np.asarray(xyz_max), dtype=torch.float32)
         voxel_size = ((xyz_max - xyz_min).prod() / num_voxels).pow(1 / 3)
         world_size = ((xyz_max - xyz_min) / voxel_size).long().tolist()
         x, y, z = np.mgrid[-1.0:1.0:world_size[0] * 1j, -1.0:1.0:world_size[1] * 1j, -1.0:1.0:world_size[2] * 1j]
-        sdf = torch.from_numpy((x ** 2 + y ** 2 + z ** 2) ** 0.5 - 1).float()[None, None, ...]       # ball init (:77-82)
+        # ball init (:77-82): the radius itself in the geometry_searching stage, radius - 1 otherwise
+        sdf = torch.from_numpy((x ** 2 + y ** 2 + z ** 2) ** 0.5 - (0 if stage == "geometry_searching" else 1)).float()[None, None, ...]
         k0 = torch.zeros([1, k0_dim, *world_size])
         dim = (3 + 3 * refbase_pe * 2) + k0_dim + (3 + 3 * posbase_pe * 2) + 3 + (3 + 3 * viewbase_pe * 2)   # :116-122
         ls = [nn.Linear(dim, refnet_width), nn.Linear(refnet_width, refnet_width), nn.Linear(refnet_width, 3)]
         refnet = [(l.weight.data.clone(), l.bias.data.clone()) for l in ls]
-        if mask_cache is None:
-            if mask_cache_path is None:
-                raise ValueError("the coarse stage needs the MaskCache of the earlier stage (mask_cache_path or mask_cache)")
-            mask_cache = MaskCache(path=mask_cache_path, mask_cache_thres=mask_cache_thres)
+        if stage == "geometry_searching":                     # no MaskCache, no non-empty mask (:158-161)
+            mask_cache = None
+            mgrid, mmin, mmax, mthres = torch.zeros(1, 1, 2, 2, 2), xyz_min, xyz_max, mask_cache_thres
+        else:
+            if mask_cache is None:
+                if mask_cache_path is None:
+                    raise ValueError("the coarse stage needs the MaskCache of the earlier stage (mask_cache_path or mask_cache)")
+                mask_cache = MaskCache(path=mask_cache_path, mask_cache_thres=mask_cache_thres)
+            mgrid, mmin, mmax, mthres = mask_cache.sdf_mask, mask_cache.xyz_min.cpu(), mask_cache.xyz_max.cpu(), mask_cache.mask_cache_thres
         self.mask_cache = mask_cache
-        cfg = dict(k0_dim=k0_dim, refnet_width=refnet_width, refnet_depth=refnet_depth, posbase_pe=posbase_pe,
+        cfg = dict(stage=stage, k0_dim=k0_dim, refnet_width=refnet_width, refnet_depth=refnet_depth, posbase_pe=posbase_pe,
                    viewbase_pe=viewbase_pe, refbase_pe=refbase_pe, smooth_ksize=smooth_ksize, smooth_sigma=smooth_sigma,
                    s_ratio=s_ratio, s_start=s_start, step_start=step_start, stepsize=stepsize,
-                   fast_color_thres=fast_color_thres, mask_cache_thres=mask_cache.mask_cache_thres)
+                   fast_color_thres=fast_color_thres, mask_cache_thres=mthres)
         sc = Scene(G=int(world_size[0]), xyz_min=xyz_min, xyz_max=xyz_max, voxel_size=float(voxel_size), sdf=sdf, k0=k0,
-                   mask_grid=mask_cache.sdf_mask, mask_xyz_min=mask_cache.xyz_min.cpu(), mask_xyz_max=mask_cache.xyz_max.cpu(),
-                   mask_thres=mask_cache.mask_cache_thres, cfg=cfg)
+                   mask_grid=mgrid, mask_xyz_min=mmin, mask_xyz_max=mmax, mask_thres=mthres, cfg=cfg)
         self.engine = CoarseStepEngine(sc, refnet, n_rays, device, cfg=cfg, train_cfg=train_cfg)
         self.engine.num_voxels = num_voxels
         self.engine.num_voxels_base = num_voxels_base or num_voxels
@@ -210,7 +215,16 @@ class nerf(nn.Module):
 
     @property
     def nonempty_mask(self):
-        return self.engine.nonempty_mask.reshape(self.engine.sdf.shape)
+        m = self.engine.nonempty_mask
+        return None if m is None else m.reshape(self.engine.sdf.shape)
+
+    def set_inc_mask(self, lower, upper):
+        """nerf.set_inc_mask (model/nerf.py:1078-1088), coarse stages only."""
+        self.engine.set_inc_mask(lower, upper)
+
+    def unset_inc_mask(self):
+        if hasattr(self.engine, "unset_inc_mask"):
+            self.engine.unset_inc_mask()
 
     @torch.no_grad()
     def forward(self, rays_o, rays_d, viewdirs, global_step=20000, **render_kwargs):
@@ -241,6 +255,11 @@ class nerf(nn.Module):
         mo = torch.ones(total, dtype=torch.bool, device=ns.device)
         if total > 0 and bool(real.any()):
             mo[(off[l1["ray_id"][real]] + l1["step_id"][real]).clamp_(0, total - 1)] = False
+        if getattr(eng, "inc_mask", None) is not None:
+            # Voxel Inc drops samples WITHOUT touching mask_outbbox (:962-967): take the bbox test from the sampling op
+            mo = render_utils_cuda.sample_pts_on_rays(ro[:n].contiguous(), rd[:n].contiguous(), eng.xyz_min.to(ro.device),
+                                                      eng.xyz_max.to(ro.device), render_kwargs.get("near", 2.0), 1e9,
+                                                      float(eng.P.stepdist))[1]
         out["mask_outbbox"] = mo
         if n == cap:
             return out

@@ -163,9 +163,9 @@ def flatten_coarse_train_cfg(cfg_train):
     t.setdefault("smooth_grad_tv", 0.0)
     if t.get("weight_tv_k0", 0) > 0 or t.get("grad_norm", 0) > 0 or t.get("grad_tv", 0) > 0:
         raise NotImplementedError("weight_tv_k0 / grad_norm / grad_tv are 0 in every shipped coarse config")
-    if t.get("voxel_inc", False) or t.get("pervoxel_lr", False) or t.get("reset_iter"):
-        raise NotImplementedError("voxel_inc / pervoxel_lr / reset_iter belong to the geometry_searching stage")
-    if t.get("ray_sampler", "in_maskcache") not in ("flatten", "in_maskcache"):
+    if t.get("pervoxel_lr", False):
+        raise NotImplementedError("pervoxel_lr is off in every shipped config")
+    if t.get("ray_sampler", "in_maskcache") not in ("flatten", "in_maskcache", "random"):
         raise NotImplementedError(f"ray_sampler {t['ray_sampler']!r}")
     return t
 
@@ -225,6 +225,8 @@ class FineTrainer:
         if gs in t.get("pg_scale", []):
             # model.scale_volume_grid(num_voxels * scale_ratio) + a fresh optimiser (nerf_training.py:244-254)
             self.engine = self.engine.scale_volume_grid(self.engine.num_voxels * t["scale_ratio"])
+            self._after_rescale(gs)
+        self._before_iteration(gs)
         eng = self.engine
         sel = next(self.sampler)
         lo, hi = self._shard
@@ -236,6 +238,12 @@ class FineTrainer:
         end_of_iteration_updates(t, eng.lr, gs, eng.train_cfg, eng.cfg)
         self._after_updates(gs)
         return gs
+
+    def _after_rescale(self, gs):
+        pass
+
+    def _before_iteration(self, gs):
+        pass
 
     def _after_updates(self, gs):
         if self.engine.cfg.get("smooth_updates"):
@@ -279,12 +287,42 @@ class FineTrainer:
 
 
 class CoarseTrainer(FineTrainer):
-    """scene_rep_reconstruction's iteration loop for stage 'coarse' (model/nerf_training.py:237-460 with `coarse_train` /
-    `coarse_model`): the same loop on a coarse.CoarseStepEngine -- batch sampler, one-launch gather, lr decay,
-    decay_step_module, tv_updates, s_updates, pg_scale (scale_volume_grid + a fresh optimiser) -- plus the coarse
-    model's `smooth_updates` (init_smooth_conv).  Single GPU."""
+    """scene_rep_reconstruction's iteration loop for the stages that run forward_coarse (model/nerf_training.py:237-460 with
+    `coarse_train` / `coarse_model` or `geometry_searching` / `geometry_searching_model`): the same loop on a
+    coarse.CoarseStepEngine -- batch sampler, one-launch gather, lr decay, decay_step_module, tv_updates, s_updates,
+    pg_scale (scale_volume_grid + a fresh optimiser) -- plus the coarse model's `smooth_updates` (init_smooth_conv) and,
+    for geometry_searching, Incremental Voxel Training (`voxel_inc`: the box of `set_inc_mask` grows over `inc_steps`
+    iterations, :201-214, :286-293) and `reset_iter` (a fresh refnet and the near-camera mask at a pg_scale step,
+    :249-252; pass the training cameras' origins as `cam_o`).  `ray_sampler='random'` draws pixels uniformly, which on
+    flattened rays is what the batch sampler's permutation stream does without replacement.  Single GPU."""
     _flatten = staticmethod(flatten_coarse_train_cfg)
     _stage = "coarse"
+
+    def __init__(self, engine, *rays, cam_o=None, maskout_near_cam_vox=True, **kw):
+        super().__init__(engine, *rays, **kw)
+        self._stage = engine.stage
+        self.cam_o, self.maskout = cam_o, maskout_near_cam_vox
+        t = self.cfg_train
+        if t.get("voxel_inc", False):
+            mid = [t["x_mid"], t["y_mid"], t["z_mid"]]
+            r = [t["x_init_ratio"], t["y_init_ratio"], t["z_init_ratio"]]
+            self._inc_lo0 = torch.tensor([m - q * m for m, q in zip(mid, r)])            # nerf_training.py:205-214
+            self._inc_hi0 = torch.tensor([m + q * (1 - m) for m, q in zip(mid, r)])
+
+    def _after_rescale(self, gs):
+        if gs in self.cfg_train.get("reset_iter", []):                 # nerf_training.py:249-252
+            self.engine.reset_refnet()
+            if self.maskout and self.cam_o is not None:
+                self.engine.maskout_near_cam_vox(self.cam_o, self.near)
+
+    def _before_iteration(self, gs):
+        t = self.cfg_train
+        if t.get("voxel_inc", False):                                  # nerf_training.py:286-293
+            if gs <= t["inc_steps"] or self.engine.inc_mask is None:   # (None: a pg_scale step has just replaced the engine)
+                w = min(gs * 1.0 / t["inc_steps"], 1.0)
+                self.engine.set_inc_mask(self._inc_lo0 - w * self._inc_lo0, self._inc_hi0 + w * (1 - self._inc_hi0))
+        elif self.engine.inc_mask is not None:
+            self.engine.unset_inc_mask()
 
     def _after_updates(self, gs):
         upd = self.engine.cfg.get("smooth_updates", {}).get(gs - 1)

@@ -145,6 +145,13 @@ typedef struct FgsFineParams {
   uint8_t *sdf_brick_flags; /* optional [ceil(X/4)*ceil(Y/4)*ceil(Z/4)]: set to 1 by the backward scatters for every 4^3
                         brick of the SDF grid that received a gradient (data-parallel exchange: g_sdf then travels as
                         packed bricks like g_k0 instead of as the dense grid); NULL = not recorded */
+  /* geometry_searching stage (model/nerf.py:962-967): mask_grid may be NULL (no MaskCache: every in-bbox sample passes),
+   * and inc_mask, when given, is the MaskGrid of Incremental Voxel Training -- a sample survives iff
+   * inc_mask[round(x * scale + shift)] != 0 (grid.py:274-284 = render_utils_cuda.maskcache_lookup) */
+  const uint8_t *inc_mask;      /* optional [iX][iY][iZ] bytes */
+  float inc_scale[3], inc_shift[3];
+  int32_t iX, iY, iZ;
+  int32_t pad2_;
 } FgsFineParams;
 
 /* words of FgsFineParams::mask_occ for an [mX][mY][mZ] mask grid, and the kernel that fills it (re-run whenever the
@@ -320,7 +327,9 @@ typedef struct FgsCoarse {
   float* g_grad_grid;        /* [3][X][Y][Z] gradient wrt grad_grid, accumulated into (caller zeroes)           */
   int32_t in_dim, in_ld;     /* refnet input width (90 / 102) and row length of X0 (% 32 == 0, 32..256)          */
   int32_t pos_pe, view_pe, ref_pe;   /* frequencies of the three encodings (5, 1, 5), each <= 10                 */
-  int32_t pad_;
+  int32_t k0_dim;            /* feature channels that enter the refnet row (0 = 12).  The k0 GRID always has 12
+                                channels-last channels; a model with fewer (geometry_searching: 6) keeps the rest at 0:
+                                their row columns do not exist, their gradient is exactly 0                          */
 } FgsCoarse;
 int64_t fgs_coarse_wsplit_floats(int in_ld);
 int fgs_coarse_forward(const FgsFineParams* p, const FgsCoarse* c, fgs_stream_t stream);
@@ -338,6 +347,12 @@ int fgs_conv3d_replicate_bwd(const float* g_out, float* g_in, int X, int Y, int 
  * reference's unmasked branch divides by sdf.sum(), which no config reaches (_set_nonempty_mask always runs). */
 int fgs_l1_tv_add_grad(const float* sdf, const uint8_t* mask, float* g_sdf, int X, int Y, int Z, double weight,
                        double mask_count, double* loss_out, fgs_stream_t stream);
+/* The unmasked branch of the same function (geometry_searching stage: no non-empty mask), as the reference writes it:
+ * loss = weight * S / 3 / sum(sdf), S = sum over the three axes of |sdf[v+e] - sdf[v]| -- the divisor is the SUM OF THE
+ * GRID (model/nerf.py:1221), so the gradient has a second, constant term -weight S / (3 sum^2).  Two launches: S and
+ * sum into scratch2 (2 device doubles, cleared here), then the gradient. */
+int fgs_l1_tv_unmasked_add_grad(const float* sdf, float* g_sdf, int X, int Y, int Z, double weight, double* scratch2,
+                                double* loss_out, fgs_stream_t stream);
 
 #ifdef __cplusplus
 }

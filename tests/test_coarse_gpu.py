@@ -84,21 +84,31 @@ def test_l1_tv_add_grad(cuda):
 
 # ---- the fused step -----------------------------------------------------------------------------------------------------
 class Case:
-    def __init__(self, cuda, G, mask_G, N, step):
-        import make_coarse_golden as mk            # model / loss settings of the golden fixture (no reference import)
+    def __init__(self, cuda, G, mask_G, N, step, stage="coarse"):
         from fgs_nerf_b200 import coarse, scene
         if not ref_ext.available():
             pytest.skip("oracle/_ref not built")
         native = R.RefCudaNative()
-        self.sc = scene.make_scene(G=G, mask_G=mask_G, with_mlps=False)
+        if stage == "coarse":
+            import make_coarse_golden as mk        # model / loss settings of the golden fixture (no reference import)
+            self.sc = scene.make_scene(G=G, mask_G=mask_G, with_mlps=False)
+            self.refnet = mk.coarse_refnet()
+            self.cfg, self.train = dict(mk.COARSE_MODEL), dict(mk.COARSE_TRAIN)
+            self.inc = None
+        else:                                       # geometry_searching: k0_dim 6, no MaskCache, an inc_mask box
+            import make_geometry_golden as mg
+            self.sc = scene.make_scene(G=G, mask_G=mask_G, with_mlps=False, cfg=dict(scene.FINE_MODEL, k0_dim=6))
+            self.refnet = mg.geometry_refnet()
+            self.cfg, self.train = dict(mg.GEOMETRY_MODEL), dict(mg.GEOMETRY_TRAIN)
+            self.inc = (mg.INC_LOWER, mg.INC_UPPER)
         self.rays = [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
-        self.refnet = mk.coarse_refnet()
-        self.cfg, self.train = dict(mk.COARSE_MODEL), dict(mk.COARSE_TRAIN)
         self.step, self.N = step, N
         ro, rd, vd, tgt = self.rays
         # ---- oracle ----
         self.m = m = Cr.CoarseModel(self.sc, self.refnet, self.cfg, device=cuda)
         m.set_nonempty_mask()
+        if self.inc:
+            m.set_inc_mask(*self.inc)
         self.stages = {}
         self.out = Cr.forward_coarse(m, native, ro, rd, vd, step, near=2.0, stepsize=0.5, bg=1.0, stages=self.stages)
         self.loss, self.tv_smooth, self.tv_sdf = Cr.coarse_loss(m, self.out, tgt, self.train)
@@ -108,6 +118,9 @@ class Case:
         tc.update(self.train)
         self.eng = eng = coarse.CoarseStepEngine(self.sc, self.refnet, N, cuda, cfg=self.cfg, train_cfg=tc)
         eng.set_nonempty_mask()
+        if self.inc:
+            eng.set_inc_mask(*self.inc)
+            assert torch.equal(eng.inc_mask.bool(), m.inc_mask[0])
         eng.forward(ro, rd, vd, step, near=2.0, bg=1.0, render_depth=True, render_grad=True)
         self.mine = eng.outputs()
         torch.cuda.synchronize()
@@ -151,7 +164,17 @@ def bench_size(cuda):
     return Case(cuda, G=116, mask_G=96, N=8192, step=3000)           # the shape `bench.py --stage coarse` measures
 
 
-@pytest.mark.parametrize("case", ["small", "mid", "bench_size"])
+@pytest.fixture(scope="module")
+def geometry(cuda):
+    return Case(cuda, G=40, mask_G=32, N=512, step=600, stage="geometry_searching")      # the geometry fixture's shape
+
+
+@pytest.fixture(scope="module")
+def geometry_mid(cuda):
+    return Case(cuda, G=120, mask_G=96, N=4096, step=600, stage="geometry_searching")    # config geometry_searching_model: 120^3
+
+
+@pytest.mark.parametrize("case", ["small", "mid", "bench_size", "geometry", "geometry_mid"])
 def test_coarse_forward_ids_and_outputs(case, request):
     c = request.getfixturevalue(case)
     mine, want = c.mine, c.out
@@ -184,7 +207,7 @@ def test_coarse_forward_near_golden_fixture(small):
     assert float(np.abs(got - gold["out_rgb_marched"]).mean()) < 2e-2
 
 
-@pytest.mark.parametrize("case", ["small", "mid", "bench_size"])
+@pytest.mark.parametrize("case", ["small", "mid", "bench_size", "geometry", "geometry_mid"])
 def test_coarse_loss_and_gradients(case, request):
     c = request.getfixturevalue(case)
     eng = c.eng
@@ -212,6 +235,7 @@ def test_coarse_loss_and_gradients(case, request):
         print(f"  {case} {k:6s} {l2:.3e} {mx:.3e}")
     for k, (a, b) in pairs.items():
         U.close_grad(a, b, k)
+    assert float(eng._g_k0_store[:, eng.k0.shape[1]:].abs().max() if eng.k0.shape[1] < 12 else 0.0) == 0.0   # pad channels of k0
     # gradients of the pad rows / columns are exactly zero (they must stay 0 under Adam)
     w, d = eng.width, eng.in_dim
     assert float(eng.gW[0][w:].abs().max()) == 0.0 and float(eng.gW[0][:, d:].abs().max()) == 0.0
@@ -361,3 +385,53 @@ def test_coarse_trainer_loop(cuda):
     assert tr.engine.smooth_ksize == 3 and tr.engine.train_cfg["smooth_grad_tv"] == 0.2
     assert np.isfinite(s["loss"]) and np.isfinite(s["psnr"]) and s["terms"].shape[1] == 7
     assert bool(torch.isfinite(tr.engine.sdf).all()) and bool(torch.isfinite(tr.engine.Wt[0]).all())
+
+
+def test_geometry_train_step_and_trainer(cuda):
+    """geometry_searching: a whole iteration moves every parameter inside the element-wise Adam bound (the unmasked SDF TV
+    with its sum(sdf) divisor included); CoarseTrainer runs the stage's loop -- voxel_inc box growing with the iteration,
+    pg_scale + reset_iter (fresh refnet) -- and the pad channels of the 12-channel k0 storage stay exactly 0."""
+    import make_geometry_golden as mg
+    from fgs_nerf_b200 import coarse, scene, training
+    c = Case(cuda, G=40, mask_G=32, N=512, step=600, stage="geometry_searching")
+    tc = dict(coarse.COARSE_TRAIN)
+    tc.update(c.train)
+    eng = coarse.CoarseStepEngine(c.sc, c.refnet, c.N, cuda, cfg=c.cfg, train_cfg=tc)
+    assert eng.set_nonempty_mask() is None
+    eng.set_inc_mask(*c.inc)
+    before = {"sdf": eng.sdf.clone(), "k0": eng.k0.clone(), "W0": eng.weights[0].clone()}
+    eng.train_step(*c.rays, c.step)
+    torch.cuda.synchronize()
+    eng.check_overflow()
+    m = c.m
+    for name, mine, g_ref, lr, masked in (("sdf", eng.sdf, m.sdf.grad, tc["lrate_sdf"], True), ("k0", eng.k0, m.k0.grad, tc["lrate_k0"], True),
+                                          ("W0", eng.weights[0], m.refnet[0][0].grad, tc["lrate_refnet"], False)):
+        bad = U.adam_first_step_violations(mine, before[name], g_ref, lr, masked=masked)
+        print(f"  geometry {name}: {bad} of {mine.numel()} first-step updates outside the element-wise bound")
+        assert bad == 0, (name, bad)
+    assert float(eng._k0_store[:, 6:].abs().max()) == 0.0
+    # the loop
+    n_total = 4096
+    ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=n_total, H=100, W=100, n_views=8)]
+    eng = coarse.CoarseStepEngine(c.sc, c.refnet, 256, cuda, cfg=c.cfg)
+    cfg_train = dict(N_iters=100, N_rand=256, lrate_k0=0.1, lrate_sdf=0.1, lrate_refnet=1e-3, lrate_decay=20, ray_sampler="random",
+                     weight_main=1, weight_entropy_last=1e-3, weight_rgbper=0.2, weight_tv_density=0.01, weight_tv_k0=0,
+                     sigmoid_rgb_loss=0.1, weight_orientation=1e-4, tv_every=1, tv_from=0, tv_end=40000, tv_dense_before=40000,
+                     voxel_inc=True, x_mid=0.5, y_mid=0.5, z_mid=0.5, x_init_ratio=0.6, y_init_ratio=0.6, z_init_ratio=0.6,
+                     inc_steps=4, scale_ratio=1.5, pg_scale=[3], reset_iter=[3],
+                     tv_terms=dict(sdf_tv=0.1, grad_norm=0, grad_tv=0, smooth_grad_tv=0.05), ori_tv=True, tv_updates={},
+                     decay_step_module={}, skip_zero_grad_fields=["density", "k0", "sdf"])
+    cam_o = torch.tensor([[0.0, 0.0, 4.0], [4.0, 0.0, 0.0]])
+    tr = training.CoarseTrainer(eng, ro, rd, vd, tgt, cfg_train=cfg_train, start=0, rng=np.random.RandomState(7), cam_o=cam_o, near=2.0)
+    tr.run(1)
+    n1 = int(tr.engine.inc_mask.sum())
+    tr.run(1)
+    assert int(tr.engine.inc_mask.sum()) > n1                      # the box grows
+    w0 = tr.engine.weights[0].clone()
+    tr.run(1)                                                        # pg_scale + reset_iter
+    assert tr.engine.X > 40 and tr.engine.inc_mask is not None and not torch.equal(tr.engine.weights[0], w0)
+    tr.run(3)
+    s_ = tr.stats()
+    assert int(tr.engine.inc_mask.min()) == 1                        # past inc_steps: the whole lattice
+    assert np.isfinite(s_["loss"]) and bool(torch.isfinite(tr.engine.sdf).all())
+    assert float(tr.engine._k0_store[:, 6:].abs().max()) == 0.0
