@@ -297,7 +297,7 @@ class nerf(nn.Module):
                     raise RuntimeError(f"{key}: checkpoint {tuple(sd[key].shape)} vs model {tuple(dst.shape)} "
                                        f"(scale_volume_grid first, as utils.load_checkpoint does)")
                 dst.copy_(sd[key].to(dst.device))
-        if self.stage == "coarse":
+        if self.stage in ("coarse", "geometry_searching"):
             from .checkpoint import _LIN3
             for j, idx in enumerate(_LIN3):
                 if f"refnet.{idx}.weight" in sd:

@@ -435,3 +435,44 @@ def test_geometry_train_step_and_trainer(cuda):
     assert int(tr.engine.inc_mask.min()) == 1                        # past inc_steps: the whole lattice
     assert np.isfinite(s_["loss"]) and bool(torch.isfinite(tr.engine.sdf).all())
     assert float(tr.engine._k0_store[:, 6:].abs().max()) == 0.0
+
+
+def test_model_class_geometry_stage(cuda, tmp_path):
+    """nerf.nerf(stage='geometry_searching') with config geometry_searching_model's keywords: forward with an inc_mask
+    (mask_outbbox is NOT touched by Voxel Inc, model/nerf.py:962-967), state_dict / checkpoint in the reference's
+    layout (k0.grid with 6 channels, no mask_cache.* keys), engine restored from the checkpoint."""
+    import make_geometry_golden as mg
+    from fgs_nerf_b200 import checkpoint, nerf as Nf, scene
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    c = mg.GEOMETRY_MODEL
+    sc = scene.make_scene(G=40, mask_G=32, with_mlps=False, cfg=dict(scene.FINE_MODEL, k0_dim=6))
+    model = Nf.nerf(xyz_min=sc.xyz_min.numpy(), xyz_max=sc.xyz_max.numpy(), num_voxels=40 ** 3, num_voxels_base=40 ** 3,
+                    mask_cache_path=None, mask_cache_thres=c["mask_cache_thres"], fast_color_thres=c["fast_color_thres"], k0_dim=6,
+                    ref=True, refnet_width=128, refnet_depth=3, posbase_pe=5, viewbase_pe=1, refbase_pe=3, smooth_ksize=5,
+                    smooth_sigma=0.8, s_ratio=50, s_start=0.2, stage="geometry_searching", use_viewdir=True, n_rays=512, device=cuda)
+    assert model.nonempty_mask is None and tuple(model.k0.grid.shape) == (1, 6, 40, 40, 40)
+    assert float(model.sdf.grid.min()) >= 0.0                       # ball init WITHOUT the -1 of the later stages
+    refnet = mg.geometry_refnet()
+    sd = {"sdf.grid": sc.sdf, "k0.grid": sc.k0}
+    for idx, (w, b) in zip(("0", "2.0", "3"), refnet):
+        sd[f"refnet.{idx}.weight"], sd[f"refnet.{idx}.bias"] = w, b
+    model.load_state_dict(sd)
+    model.set_inc_mask(mg.INC_LOWER, mg.INC_UPPER)
+    ro, rd, vd, _ = [t.to(cuda) for t in scene.make_rays(N=512, H=100, W=100, n_views=8)]
+    got = model(ro, rd, vd, global_step=600, near=2.0, far=6.0, stepsize=0.5, bg=1.0, render_depth=True, render_grad=True)
+    m = Cr.CoarseModel(sc, refnet, c, device=cuda, requires_grad=False)
+    m.set_inc_mask(mg.INC_LOWER, mg.INC_UPPER)
+    with torch.no_grad():
+        want = Cr.forward_coarse(m, R.RefCudaNative(), ro, rd, vd, 600, near=2.0, stepsize=0.5, bg=1.0)
+    assert torch.equal(got["ray_id"], want["ray_id"]) and torch.equal(got["mask_outbbox"], want["mask_outbbox"])
+    assert _rel(got["rgb_marched"], want["rgb_marched"]) < 1e-4
+    ck = checkpoint.checkpoint_dict(model.engine, 600)
+    keys = list(ck["model_state_dict"].keys())
+    assert tuple(ck["model_state_dict"]["k0.grid"].shape) == (1, 6, 40, 40, 40) and not any(k.startswith("mask_cache") for k in keys)
+    assert ck["model_kwargs"]["stage"] == "geometry_searching" and ck["model_kwargs"]["refnet_dim"] == 72
+    path = str(tmp_path / "geometry_last.tar")
+    checkpoint.save_checkpoint(model.engine, 600, path)
+    eng2, start = checkpoint.coarse_engine_from_checkpoint(path, 512, cuda)
+    assert start == 600 and eng2.stage == "geometry_searching" and eng2.mask_grid is None
+    assert torch.equal(eng2.k0, model.engine.k0) and torch.equal(eng2.weights[0], model.engine.weights[0])
