@@ -1,6 +1,8 @@
 """Coarse stage of the per-ray path: host side of the "coarse stage" section of include/fgs_b200_fine.h.
 
-`CoarseStepEngine` is the coarse-stage counterpart of engine.FineStepEngine:
+`CoarseStepEngine` is the counterpart of engine.FineStepEngine for the two stages that run nerf.forward_coarse --
+'coarse' and (cfg['stage'] = 'geometry_searching') the first stage of a run, which has no MaskCache, k0_dim 6 and the
+Incremental-Voxel-Training box `inc_mask`:
 
   forward()      nerf.forward_coarse                               model/nerf.py:943-1075
   train_step()   forward + loss (incl. weight_rgbper, ori_tv) + backward + MaskedAdam
