@@ -422,9 +422,9 @@ def run_ours(args):
             os.close(saved_stdout)
     if args.mode == "render":
         return run_render(args, world, rank, dev)
-    if args.stage == "coarse":
+    if args.stage in ("coarse", "geometry_searching"):
         if world > 1:
-            raise SystemExit("bench.py --stage coarse: the coarse stage runs on one GPU")
+            raise SystemExit("bench.py --stage coarse / geometry_searching: these stages run on one GPU")
         return run_coarse(args, dev)
     from fgs_nerf_b200 import _lib, engine, scene
 
@@ -612,8 +612,17 @@ def run_coarse(args, dev):
     import torch
     from fgs_nerf_b200 import _lib, coarse, scene
     N = args.rays
-    sc = scene.make_scene(G=args.grid, with_mlps=False)
-    eng = coarse.CoarseStepEngine(sc, coarse.make_refnet(), N, dev)
+    geometry = args.stage == "geometry_searching"
+    if geometry:
+        # the first stage of a run: no MaskCache, k0_dim 6, refnet 72-128-128-3, the voxel_inc box 60 % through its schedule
+        sc = scene.make_scene(G=args.grid, with_mlps=False, cfg=dict(scene.FINE_MODEL, k0_dim=6))
+        eng = coarse.CoarseStepEngine(sc, coarse.make_refnet(coarse.GEOMETRY_MODEL), N, dev, cfg=coarse.GEOMETRY_MODEL,
+                                      train_cfg=coarse.GEOMETRY_TRAIN)
+        w = 0.6
+        eng.set_inc_mask([0.2 - w * 0.2] * 3, [0.8 + w * 0.2] * 3)
+    else:
+        sc = scene.make_scene(G=args.grid, with_mlps=False)
+        eng = coarse.CoarseStepEngine(sc, coarse.make_refnet(), N, dev)
     eng.set_nonempty_mask()
     if args.freeze:
         eng.lr = {k: 0.0 for k in eng.lr}
@@ -670,11 +679,16 @@ def run_coarse(args, dev):
     line = {"metric": METRIC, "value": N * K / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
             "data": "synthetic",
-            "config": {"workload": f"shiny-blender COARSE-stage training step (forward_coarse + loss incl. weight_rgbper + bwd + "
-                                   f"smooth-grad TV + autograd SDF TV every step + masked Adam), {args.grid}^3 SDF + 12-ch k0 "
-                                   f"grid, 5^3 Gaussian SDF smoothing per forward, refnet 90-192-192-3, {N} rays/step, "
-                                   f"global_step {args.global_step}+",
-                       "stage": "coarse", "grid": args.grid, "rays_per_gpu": N, "frozen_trajectory": bool(args.freeze),
+            "config": {"workload": (f"shiny-blender GEOMETRY_SEARCHING-stage training step (forward_coarse without a MaskCache, "
+                                    f"voxel_inc box at 60 % of its schedule, loss incl. weight_rgbper + bwd + smooth-grad TV + "
+                                    f"unmasked autograd SDF TV every step + masked Adam), {args.grid}^3 SDF + 6-ch k0 grid, 5^3 "
+                                    f"Gaussian SDF smoothing per forward, refnet 72-128-128-3, {N} rays/step, global_step "
+                                    f"{args.global_step}+") if geometry else
+                                   (f"shiny-blender COARSE-stage training step (forward_coarse + loss incl. weight_rgbper + bwd + "
+                                    f"smooth-grad TV + autograd SDF TV every step + masked Adam), {args.grid}^3 SDF + 12-ch k0 "
+                                    f"grid, 5^3 Gaussian SDF smoothing per forward, refnet 90-192-192-3, {N} rays/step, "
+                                    f"global_step {args.global_step}+"),
+                       "stage": args.stage, "grid": args.grid, "rays_per_gpu": N, "frozen_trajectory": bool(args.freeze),
                        "l2_policy": f"k0 + grad + Adam state = 4 x {48 * V / 1e6:.0f} MB, larger than the 126 MB L2",
                        "samples_per_ray": {"total_len": cnt["total_len"] / N, "M1": cnt["M1"] / N, "M2": cnt["M2"] / N}},
             "clocks": clocks,
@@ -763,8 +777,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "render"])
-    ap.add_argument("--stage", default="fine", choices=["fine", "coarse"],
-                    help="coarse: one coarse-stage iteration (SURVEY 8f row 1; use --grid 116 --global-step 3000)")
+    ap.add_argument("--stage", default="fine", choices=["fine", "coarse", "geometry_searching"],
+                    help="coarse / geometry_searching: one iteration of that stage (SURVEY 8f row 1; use --grid 116 "
+                         "--global-step 3000 / --grid 120 --global-step 600)")
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (train) / chunk size (render)")
     ap.add_argument("--camera", default="blender", choices=["blender", "dtu"])

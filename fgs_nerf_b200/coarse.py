@@ -36,6 +36,12 @@ COARSE_TRAIN = dict(  # config/shiny_blender.py `coarse_train`
     sdf_tv=0.1, smooth_grad_tv=0.05, ori_tv=True, N_iters=15000,
     skip_zero_grad_fields=("density", "k0", "sdf"),
 )
+GEOMETRY_MODEL = dict(  # config/shiny_blender.py `geometry_searching_model`
+    stage="geometry_searching", k0_dim=6, refnet_width=128, refnet_depth=3, posbase_pe=5, viewbase_pe=1, refbase_pe=3,
+    smooth_ksize=5, smooth_sigma=0.8, s_ratio=50, s_start=0.2, step_start=0, stepsize=0.5,
+    fast_color_thres=1e-4, mask_cache_thres=1e-3,
+)
+GEOMETRY_TRAIN = dict(COARSE_TRAIN, N_iters=12000, lrate_density=0.1)    # config `geometry_searching` (same loss weights)
 LAST = MLP_LAYERS - 1          # slot of the refnet's output layer in FgsFineParams.W / B / gW / gB
 
 

@@ -51,6 +51,8 @@ def main():
     t.append(row("5 at 8 GPUs (chunks dealt round-robin, one all-gather per output)", c58, "r02_bench_cfg5_n8.json", per=" / image",
                  extra=f": {c58['value'] / c5['value']:.2f}x of 1 GPU" if c58 and c5 else ""))
     t.append(row(f"coarse stage (8f row 1): 116^3, 8192 rays, 1 GPU (M2/ray {co['config']['samples_per_ray']['M2']:.1f})" if co else "coarse", co, "r02_bench_coarse.json"))
+    ge = line("r02_bench_geometry.json")
+    t.append(row(f"geometry_searching stage (8f row 1): 120^3, 6-ch k0, 8192 rays, 1 GPU (no MaskCache: M2/ray {ge['config']['samples_per_ray']['M2']:.1f})" if ge else "geometry_searching", ge, "r02_bench_geometry.json"))
     cfg_table = "\n".join(t)
     k = ["| kernel | ms / step | share | bound | achieved | fraction of the measured peak | DRAM bytes / launch (ncu) |", "|---|---|---|---|---|---|---|"]
     for r in c2["kernels"]:

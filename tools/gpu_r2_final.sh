@@ -8,6 +8,7 @@ timeout 600 python bench.py > gpurun_out/r2_final_bench_cfg2.json 2> gpurun_out/
 timeout 300 python bench.py --grid 256 --camera dtu --no-cpu-baseline --no-gpu-oracle > gpurun_out/r2_final_bench_cfg3.json 2> gpurun_out/r2_final_bench_cfg3.err; echo "cfg3 rc=$?"
 timeout 300 python bench.py --mode render --grid 384 --steps 5 --warmup 2 > gpurun_out/r2_final_bench_cfg5_n1.json 2> gpurun_out/r2_final_bench_cfg5_n1.err; echo "cfg5 rc=$?"
 timeout 300 python bench.py --stage coarse --grid 116 --global-step 3000 > gpurun_out/r2_final_bench_coarse.json 2> gpurun_out/r2_final_bench_coarse.err; echo "coarse rc=$?"
+timeout 300 python bench.py --stage geometry_searching --grid 120 --global-step 600 > gpurun_out/r2_final_bench_geometry.json 2> gpurun_out/r2_final_bench_geometry.err; echo "geometry rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_bench_reference.json 2> gpurun_out/r2_final_bench_reference.err; echo "reference rc=$?"
 python - <<PY
 import json, glob
