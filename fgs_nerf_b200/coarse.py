@@ -51,6 +51,7 @@ class FgsCoarse(C.Structure):
         ("sdf_smooth", _fp), ("grad_grid", _fp), ("g_smooth", _fp), ("g_grad_grid", _fp),
         ("in_dim", C.c_int32), ("in_ld", C.c_int32),
         ("pos_pe", C.c_int32), ("view_pe", C.c_int32), ("ref_pe", C.c_int32), ("k0_dim", C.c_int32),
+        ("width", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -243,7 +244,7 @@ class CoarseStepEngine(FineStepEngine):
         ws["grad1"], ws["d_grad1"] = e(3, self.cap_m1), e(3, self.cap_m1)
         ws["idx1_of2"], ws["ray_id2"] = e(self.cap_m2, dt=i32), e(self.cap_m2, dt=i32)
         ws["X0"], ws["dX0"] = e(self.cap_m2, self.in_ld), e(self.cap_m2, self.in_ld)
-        ws["H"] = e(2, self.cap_m2, WIDTH)
+        ws["H"] = torch.zeros(2, self.cap_m2, WIDTH, dtype=f32, device=dev)    # (columns beyond the GEMMs' N are never written)
         ws["logit"], ws["normal2"], ws["dlogit"] = e(self.cap_m2, 4), e(self.cap_m2, 4), e(self.cap_m2, 4)
         ws["dZ"] = torch.zeros(2, self.cap_m2, WIDTH, dtype=f32, device=dev)      # bf16 hi / mid planes, zero-initialised
         ws["dlogit_p"] = torch.zeros(2, self.cap_m2, 8, dtype=torch.int16, device=dev)
@@ -297,6 +298,7 @@ class CoarseStepEngine(FineStepEngine):
             self._build_mask_occupancy()
         Cc = self.Cc
         Cc.k0_dim = int(c["k0_dim"])
+        Cc.width = int(self.width)
         # without a smoother (smooth_ksize 0) the SDF is sampled from the raw grid and its gradient lands in g_sdf directly
         Cc.sdf_smooth = ptr(self.sdf_smooth if self.smooth_ksize > 0 else self.sdf)
         Cc.g_smooth = ptr(self.g_smooth if self.smooth_ksize > 0 else self.g_sdf)

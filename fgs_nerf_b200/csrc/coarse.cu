@@ -435,8 +435,12 @@ int check_coarse(const FgsFineParams* p, const FgsCoarse* c) {
   FGS_REQUIRE(c->in_dim == row_map(*c).dim, "in_dim does not match k0_dim + the three encodings + normal");
   FGS_REQUIRE(c->in_ld >= c->in_dim && (c->in_ld & 31) == 0 && c->in_ld <= 256, "in_ld must be a multiple of 32 in [in_dim, 256]");
   FGS_REQUIRE(p->w_split && p->hbits && p->X0 && p->H && p->logit, "MLP workspaces are NULL");
+  FGS_REQUIRE(c->width >= 0 && c->width <= W, "refnet width out of range (0..256)");
   return 0;
 }
+
+// N / K extent of the hidden layers in the GEMMs: the width rounded up to whole 64-k slabs of the bf16 kernels
+int gemm_width(const FgsCoarse& C) { return C.width > 0 ? ((C.width + 63) & ~63) : W; }
 
 float* hidden(const FgsFineParams& P, int i) { return P.H + (size_t)i * P.cap_m2 * W; }
 uint32_t* hbits(const FgsFineParams& P, int i) { return P.hbits + (size_t)i * P.cap_m2 * 8; }
@@ -471,18 +475,19 @@ int fgs_coarse_forward(const FgsFineParams* p, const FgsCoarse* c, fgs_stream_t 
     jobs[2 * l + 1] = {Wl, P.w_split + L.thi[l], P.w_split + L.tlo[l], L.out[l], L.in_ld[l], L.in_ld[l], L.ldt[l], 1, 1};
   }
   if ((rc = weight_split_jobs(jobs, 6, st))) return rc;
-  auto fwd = [&](int l, const float* A, int lda, float* Cout, int ldc, int N, int relu, int hid) {
+  const int Wp = gemm_width(C);
+  auto fwd = [&](int l, const float* A, int lda, int K, float* Cout, int ldc, int N, int relu, int hid) {
     ChainStepHost s{};
-    s.A = A; s.lda = lda; s.K = L.in_ld[l];
+    s.A = A; s.lda = lda; s.K = K;
     s.Bh = P.w_split + L.hi[l]; s.Bl = P.w_split + L.lo[l]; s.ldb = L.in_ld[l];
     s.C = Cout; s.ldc = ldc; s.N = N; s.n0 = 0;
     s.bias = P.B[L.slot[l]]; s.relu = relu;
     s.bits_in = nullptr; s.bits_out = relu ? hbits(P, hid) : nullptr;
     return s;
   };
-  const ChainStepHost steps[3] = {fwd(0, P.X0, C.in_ld, hidden(P, 0), W, W, 1, 0),
-                                  fwd(1, hidden(P, 0), W, hidden(P, 1), W, W, 1, 1),
-                                  fwd(2, hidden(P, 1), W, P.logit, 4, 3, 0, -1)};
+  const ChainStepHost steps[3] = {fwd(0, P.X0, C.in_ld, C.in_ld, hidden(P, 0), W, Wp, 1, 0),
+                                  fwd(1, hidden(P, 0), W, Wp, hidden(P, 1), W, Wp, 1, 1),
+                                  fwd(2, hidden(P, 1), W, Wp, P.logit, 4, 3, 0, -1)};
   if ((rc = mlp_chain(steps, 3, P.cap_m2, P.counters + FGS_CNT_M2, st))) return rc;
   if (P.skip_composite) return 0;
   return launch_composite(P, nullptr, st);
@@ -516,10 +521,11 @@ int fgs_coarse_backward(const FgsFineParams* p, const FgsFineLoss* l, const FgsC
   };
   // backward-data chain (3xBF16): dlogit -> dZ1 (masked by relu'(H1)) -> dZ0 (relu'(H0)) -> dX0; bias gradients of
   // layers 1 and 0 are the column sums of dZ1 / dZ0 (the last layer's came from the compositing kernel)
+  const int Wp = gemm_width(C);
   const BwStepHost steps[3] = {
-      step(2, lg_hi, lg_mid, 8, 3, zhi(0), zmid(0), nullptr, 0, W, 1, P.gB[1]),
-      step(1, zhi(0), zmid(0), W, W, zhi(1), zmid(1), nullptr, 0, W, 0, P.gB[0]),
-      step(0, zhi(1), zmid(1), W, W, nullptr, nullptr, P.dX0, C.in_ld, C.in_ld, -1, nullptr)};
+      step(2, lg_hi, lg_mid, 8, 3, zhi(0), zmid(0), nullptr, 0, Wp, 1, P.gB[1]),
+      step(1, zhi(0), zmid(0), W, Wp, zhi(1), zmid(1), nullptr, 0, Wp, 0, P.gB[0]),
+      step(0, zhi(1), zmid(1), W, Wp, nullptr, nullptr, P.dX0, C.in_ld, C.in_ld, -1, nullptr)};
   if ((rc = mlp_bwd_planes(steps, 3, cap, m2, st))) return rc;
   coarse_feat_bwd_kernel<<<dim3(fgs::stream_grid(P.cap_m2, kBlock, 4), 2), kBlock, 0, st>>>(P, C, l->weight_orientation);
   if ((rc = fgs::check_launch("coarse feat_bwd", st))) return rc;
@@ -528,12 +534,12 @@ int fgs_coarse_backward(const FgsFineParams* p, const FgsFineLoss* l, const FgsC
   if ((rc = fgs::check_launch("coarse level1_bwd", st))) return rc;
   // weight gradients: dW_l = dZ_l^T X_l
   DwProblemHost dw[2];
-  dw[0] = DwProblemHost{nullptr, P.X0, P.gW[0], nullptr, W, C.in_ld, 0, C.in_ld, C.in_ld};
+  dw[0] = DwProblemHost{nullptr, P.X0, P.gW[0], nullptr, Wp, C.in_ld, 0, C.in_ld, C.in_ld};
   dw[0].Ahi = zhi(1); dw[0].Amid = zmid(1); dw[0].ldp = W;
-  dw[1] = DwProblemHost{nullptr, hidden(P, 0), P.gW[1], nullptr, W, W, 0, W, W};
+  dw[1] = DwProblemHost{nullptr, hidden(P, 0), P.gW[1], nullptr, Wp, Wp, 0, W, W};
   dw[1].Ahi = zhi(0); dw[1].Amid = zmid(0); dw[1].ldp = W;
   if ((rc = mlp_dw(dw, 2, cap, m2, st, true))) return rc;
-  return dw_small(3, W, cap, P.dlogit, 4, hidden(P, 1), W, P.gW[kLast], W, m2, st);
+  return dw_small(3, Wp, cap, P.dlogit, 4, hidden(P, 1), W, P.gW[kLast], W, m2, st);
 }
 
 }  // extern "C"

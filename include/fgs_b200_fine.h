@@ -330,6 +330,9 @@ typedef struct FgsCoarse {
   int32_t k0_dim;            /* feature channels that enter the refnet row (0 = 12).  The k0 GRID always has 12
                                 channels-last channels; a model with fewer (geometry_searching: 6) keeps the rest at 0:
                                 their row columns do not exist, their gradient is exactly 0                          */
+  int32_t width;             /* refnet hidden width (192 / 128; 0 = 256): the GEMMs run N / K = width rounded up to 64
+                                instead of the storage's 256 (tcgen05 time scales with N: 0.56x / 0.25x of the MMA work) */
+  int32_t pad_;
 } FgsCoarse;
 int64_t fgs_coarse_wsplit_floats(int in_ld);
 int fgs_coarse_forward(const FgsFineParams* p, const FgsCoarse* c, fgs_stream_t stream);
