@@ -435,6 +435,7 @@ def run_ours(args):
     eng.set_nonempty_mask()
     if args.dw_sm_reserve >= 0:
         eng.dw_sm_reserve = args.dw_sm_reserve
+    eng.use_graph = bool(args.graph) and world == 1
     if args.freeze:
         eng.lr = {k: 0.0 for k in eng.lr}
     cam = camera(args)
@@ -794,6 +795,7 @@ def main():
     ap.add_argument("--no-gpu-oracle", action="store_true")
     ap.add_argument("--dw-sm-reserve", type=int, default=-1,
                     help="N > 1: SMs the weight-gradient kernel leaves to the overlapped exchange (-1: the engine's default)")
+    ap.add_argument("--graph", type=int, default=1, help="1 (default): the single-GPU iteration is launched as one CUDA graph")
     ap.add_argument("--exchange", default="bricks", choices=["bricks", "voxels"],
                     help="granularity of the data-parallel k0 gradient exchange (N > 1)")
     args = ap.parse_args()

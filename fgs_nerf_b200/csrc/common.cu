@@ -31,9 +31,9 @@ int fgs_device_sm_count(int device, int* sm_count, int* cc_major, int* cc_minor)
 
 // ---- per-launch timing (bench.py / profiles): one cudaEvent per launch on the launching stream
 namespace fgs {
+bool g_prof_on = false;          // per-launch timing active (fgs_prof_begin .. fgs_prof_end)
 namespace {
 constexpr int kMaxEv = 16384;
-bool g_prof_on = false;
 int g_prof_n = 0, g_prof_created = 0;
 cudaEvent_t g_ev[kMaxEv];
 const char* g_ev_name[kMaxEv];

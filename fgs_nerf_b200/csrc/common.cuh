@@ -12,6 +12,7 @@ namespace fgs {
 
 extern thread_local char g_err[256];
 extern int64_t g_launches;
+extern bool g_prof_on;
 
 inline int fail_arg(const char* msg) {
   snprintf(g_err, sizeof(g_err), "fgs_b200: bad argument: %s", msg);

@@ -60,3 +60,61 @@ extern "C" int fgs_fine_train_step(const FgsFineParams* p, const FgsFineLoss* l,
     return rc;
   return 0;
 }
+
+// ---- the iteration as one CUDA graph ---------------------------------------------------------------------------------
+namespace {
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+};
+StepGraph g_step_graphs[64][4];          // [device][tv_smooth | tv_sdf << 1]
+}  // namespace
+
+extern "C" int fgs_fine_train_step_graph(const FgsFineParams* p, const FgsFineLoss* l, const FgsFineStep* s,
+                                         fgs_stream_t stream, int* used_graph) {
+  if (used_graph) *used_graph = 0;
+  FGS_REQUIRE(p && l && s, "train_step_graph: NULL descriptor");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  if (fgs::g_prof_on || st == nullptr || st == cudaStreamLegacy || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return fgs_fine_train_step(p, l, s, stream);
+  StepGraph& G = g_step_graphs[dev][(s->tv_smooth ? 1 : 0) | (s->tv_sdf ? 2 : 0)];
+  int rc = 0;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();                              // e.g. the caller is capturing this stream itself: join its capture
+    return fgs_fine_train_step(p, l, s, stream);
+  }
+  const int64_t launches_before = fgs::g_launches;
+  const int rc_step = fgs_fine_train_step(p, l, s, stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc_step) {                                     // the step's own error wins; the capture is void
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc_step;
+  }
+  if (e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    fgs::g_launches = launches_before;
+    return fgs_fine_train_step(p, l, s, stream);     // capture not possible here: enqueue directly
+  }
+  if (G.exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(G.exec, graph, &info) != cudaSuccess) {   // different topology (e.g. another row-range count)
+      cudaGetLastError();
+      cudaGraphExecDestroy(G.exec);
+      G.exec = nullptr;
+    }
+  }
+  if (!G.exec) {
+    e = cudaGraphInstantiate(&G.exec, graph, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      G.exec = nullptr;
+      return fgs::check_cuda(e, "graph instantiate");
+    }
+  }
+  cudaGraphDestroy(graph);
+  rc = fgs::check_cuda(cudaGraphLaunch(G.exec, st), "graph launch");
+  if (!rc && used_graph) *used_graph = 1;
+  return rc;
+}

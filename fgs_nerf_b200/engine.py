@@ -96,6 +96,7 @@ class FgsFineStep(C.Structure):
 _PP = C.POINTER(FgsFineParams)
 _LP = C.POINTER(FgsFineLoss)
 _lib.declare("fgs_fine_train_step", C.c_int, [_PP, _LP, C.POINTER(FgsFineStep), _fp])
+_lib.declare("fgs_fine_train_step_graph", C.c_int, [_PP, _LP, C.POINTER(FgsFineStep), _fp, C.POINTER(C.c_int)])
 _lib.declare("fgs_fine_forward", C.c_int, [_PP, _fp])
 _lib.declare("fgs_fine_loss", C.c_int, [_PP, _LP, _fp])
 _lib.declare("fgs_fine_backward", C.c_int, [_PP, _LP, _fp])
@@ -391,6 +392,9 @@ class FineStepEngine:
         self.exchange_sdf_bricks = 0
         self._side = None                  # side stream of the overlapped gradient exchange (data parallel)
         self.native_step = True            # single GPU: the iteration is one library call (fgs_fine_train_step)
+        self.use_graph = True              # ... launched as one CUDA graph (fgs_fine_train_step_graph): 1.055 -> 1.017 ms per step
+        self._graph_stream = None
+        self.graph_steps = 0
         self._S = None
         self.dw_sm_reserve = 8             # SMs the weight-gradient kernel leaves to the overlapped exchange (2 GPUs: 1.220 ms per step with 8, 1.255 with 16, 1.230 with 0)
         ws["counters"] = torch.zeros(NUM_COUNTERS, dtype=i32, device=dev)
@@ -956,7 +960,20 @@ class FineStepEngine:
             self._S_steps[i] = self._S_steps[MLP_LAYERS + i] = self.adam_step
         self.P.mlp_grads_zeroed = int(self._mlp_grads_clean)     # its Adam clears the MLP gradients it consumes
         with torch.cuda.device(self.device):
-            check(lib.fgs_fine_train_step(C.byref(self.P), C.byref(L), C.byref(S), stream()))
+            if self.use_graph and self.adam_step > 2:          # (the first iterations set function attributes, tensor maps ...)
+                # one CUDA graph per iteration, on the engine's own stream (capture is illegal on the legacy default stream)
+                cur = torch.cuda.current_stream(self.device)
+                if self._graph_stream is None:
+                    self._graph_stream = torch.cuda.Stream(device=self.device)
+                gs = self._graph_stream
+                gs.wait_stream(cur)
+                with torch.cuda.stream(gs):
+                    used = C.c_int(0)
+                    check(lib.fgs_fine_train_step_graph(C.byref(self.P), C.byref(L), C.byref(S), stream(), C.byref(used)))
+                    self.graph_steps += int(used.value)
+                cur.wait_stream(gs)
+            else:
+                check(lib.fgs_fine_train_step(C.byref(self.P), C.byref(L), C.byref(S), stream()))
         self._mlp_grads_clean = True
         self._grads_clean = True
         self._brick_list_ready = False

@@ -252,6 +252,15 @@ typedef struct FgsFineStep {
 
 int fgs_fine_train_step(const FgsFineParams* p, const FgsFineLoss* l, const FgsFineStep* s, fgs_stream_t stream);
 
+/* The same iteration launched as ONE CUDA graph: the call stream-captures fgs_fine_train_step (thread-local capture
+ * mode), updates the cached executable graph of the same shape in place (cudaGraphExecUpdate: the per-iteration scalars
+ * -- inv_s, Adam step, learning rates, ray pointers -- are kernel parameters of the captured nodes), and launches it.
+ * One executable graph per step shape (TV regularisers on / off) and device.  `stream` must not be the legacy default
+ * stream (capture is illegal there).  While per-launch timing is active (fgs_prof_begin) the iteration is enqueued
+ * directly instead.  *used_graph (may be NULL) reports which way it went. */
+int fgs_fine_train_step_graph(const FgsFineParams* p, const FgsFineLoss* l, const FgsFineStep* s, fgs_stream_t stream,
+                              int* used_graph);
+
 /* DenseGrid.forward / backward (model/grid.py:49-59) and MaskCache.forward (model/nerf.py:
  * 1202-1209) as stand-alone ops: ATen grid_sample arithmetic, any channel count.
  * channels_last: 0 = [C][X][Y][Z], 1 = [X][Y][Z][C].  out: [M][C].

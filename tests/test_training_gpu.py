@@ -484,3 +484,36 @@ def test_library_sequenced_step_equals_host_sequenced_step(cuda):
     a._S.sdf_m = None
     with pytest.raises(RuntimeError):
         a.train_step(ro, rd, vd, tgt, 5003)
+
+
+def test_graph_launched_step_equals_directly_enqueued_step(cuda):
+    """fgs_fine_train_step_graph (the iteration stream-captured and launched as ONE CUDA graph, its executable updated in
+    place every iteration) against the directly enqueued iteration: six iterations that alternate TV / non-TV steps
+    (two graph shapes) with changing learning rates and ray batches; parameters, Adam state and loss terms agree to the
+    rounding of the float atomics, and the graph path was really taken."""
+    from fgs_nerf_b200 import engine, scene
+    N = 192
+    sc = scene.make_scene(G=48, mask_G=40)
+    cfg = dict(scene.FINE_TRAIN, tv_every=2)
+    batches = [[t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8, offset=b * N)] for b in range(2)]
+    engs = []
+    for graph in (True, False):
+        e = engine.FineStepEngine(sc, N, cuda, train_cfg=cfg)
+        e.set_nonempty_mask()
+        e.use_graph = graph
+        losses = []
+        for i, gs in enumerate(range(5000, 5006)):
+            e.lr["sdf"] *= 0.9
+            e.train_step(*batches[i % 2], gs)
+            torch.cuda.synchronize()
+            losses.append(e.ws["loss"].cpu().numpy().copy())
+        e.check_overflow()
+        engs.append((e, np.stack(losses)))
+    (a, la), (b, lb) = engs
+    assert a.graph_steps >= 4 and b.graph_steps == 0           # (the first iterations warm up outside the graph)
+    assert a.adam_step == b.adam_step == 6
+    assert np.allclose(la[0], lb[0], rtol=1e-6, atol=1e-12) and np.allclose(la, lb, rtol=2e-3, atol=1e-7)
+    assert (la[::2, 4] > 0).all() and (la[1::2, 4] == 0).all()  # smooth TV on the even steps only
+    for name, x, y, before, lr in (("sdf", a.sdf, b.sdf, sc.sdf, 0.005), ("k0", a.k0, b.k0, sc.k0, 0.1),
+                                   ("W0", a.weights[0], b.weights[0], sc.rgbnet[0][0], 1e-3)):
+        assert _frac_differing(x, y, before.to(cuda), lr) < 1e-2, name
