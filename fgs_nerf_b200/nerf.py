@@ -66,16 +66,17 @@ class _GridView:
 
 class nerf(nn.Module):
     """The reference's scene model class (model/nerf.py:20-1075) on top of FineStepEngine (stage='fine') or
-    coarse.CoarseStepEngine (stage='coarse': forward_coarse, :943-1075; k0_dim 12, refnet in -> width -> width -> 3 with
-    width <= 256, any PE counts, Gaussian SDF smoothing): same
+    coarse.CoarseStepEngine (stage='coarse' | 'geometry_searching': forward_coarse, :943-1075; k0_dim 1..12, refnet
+    in -> width -> width -> 3 with width <= 256, any PE counts, Gaussian SDF smoothing; the first stage also without a
+    MaskCache and with the Incremental-Voxel-Training box, set_inc_mask / unset_inc_mask): same
     constructor keywords, `forward(rays_o, rays_d, viewdirs, global_step=..., **render_kwargs) -> dict` with the
     reference's keys (:922-939), `sdf.grid` / `k0.grid`, `state_dict()` in the reference's layout, `scale_volume_grid`,
     `extract_geometry`'s field.  What differs, stated loudly:
       * forward is inference only (no autograd graph): training is the fused `train_step` / training.FineTrainer
         (the reference's loss.backward() has no counterpart to hook into -- the backward is fused with the loss);
-      * only the fine-stage architecture the kernels are specialised for is accepted (k0_dim 12, 4 x 256 rgbnet and
-        refnet, PE 5 / 3 / 8, grad_feat = sdf_feat = (0.5, 1, 1.5, 2), ref, use_viewdir, no SDF smoothing); anything
-        else raises NotImplementedError (the 'geometry_searching' stage -- k0_dim 6, no MaskCache, voxel_inc -- is not built);
+      * stage='fine' accepts only the architecture its kernels are specialised for (k0_dim 12, 4 x 256 rgbnet and
+        refnet, PE 5 / 3 / 8, grad_feat = sdf_feat = (0.5, 1, 1.5, 2), ref, use_viewdir, no SDF smoothing) -- the
+        `fine_model` block of every shipped config; anything else raises NotImplementedError;
       * a batch may have at most `n_rays` rays (the workspace is allocated once); shorter batches are padded."""
 
     def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, nearest=False, mask_cache_path=None,
