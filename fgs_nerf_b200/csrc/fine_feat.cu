@@ -53,7 +53,10 @@ __device__ __forceinline__ float disp_of(int d) { return 0.5f * (float)(d + 1); 
 // backward: k0 scatter | - | reflection chain | (tap axis, displacement pair) x 6
 constexpr int kTaskK0 = 0, kTaskPE = 1, kTaskRefl = 2, kTaskTap0 = 3, kNumTasks = 7, kNumTasksBwd = 9;
 
-__global__ void __launch_bounds__(kBlock) feat_kernel(const __grid_constant__ FgsFineParams P, int only_task) {
+// (launch bound: 6 CTAs per SM = 80 registers instead of the 96 ptxas picks on its own: 46.6 -> 45.4 us on the headline
+// workload; 64 / 48 registers spill into the encoding tasks and gain nothing more, 101 registers lose 4 us --
+// profiles/r02_variant_sweep.jsonl.  The same sweep moved feat_bwd_kernel by less than its noise at every bound.)
+__global__ void __launch_bounds__(kBlock, 6) feat_kernel(const __grid_constant__ FgsFineParams P, int only_task) {
   const GridGeo g = make_geo(P.xyz_min, P.xyz_max, P.X, P.Y, P.Z);
   const int M2 = min(P.counters[FGS_CNT_M2], P.cap_m2);
   // blockIdx.y = which independent part of the row this CTA builds (uniform per CTA: no divergence).  With one

@@ -30,7 +30,15 @@ __device__ __forceinline__ void flag_overflow(int* counters, int bit) {
   atomicOr(counters + FGS_CNT_STICKY, bit);
 }
 
-__global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ FgsFineParams P) {
+// march_kernel, warp per ray, kMarchWords bitmap words (32 steps each) of the ray in flight: the steps of a ray are
+// independent, but a warp that finishes one word (occupancy word -> 8 mask gathers -> ballot) before it starts the next
+// pays two dependent memory latencies per word.  The occupancy loads of the words are issued together, then the gathers,
+// then the ballots in step order.  Measured on the headline workload (profiles/r02_variant_sweep.jsonl): 38.1 us with one
+// word at a time (64 registers) -> 34.9 us with two words at 40 registers (6 CTAs per SM); four words need > 64
+// registers or spill and are no faster (36.9 us), and no register bound alone moves the kernel (35.7-38.3 us).
+constexpr int kMarchWords = 2;
+__global__ void __launch_bounds__(kBlock, 6) march_kernel(const __grid_constant__ FgsFineParams P) {
+  constexpr int W = kMarchWords;
   const int lane = lane_id();
   const GridGeo mg = make_geo(P.mask_xyz_min, P.mask_xyz_max, P.mX, P.mY, P.mZ);
   const float thres = P.mask_thres;
@@ -55,50 +63,67 @@ __global__ void __launch_bounds__(kBlock) march_kernel(const __grid_constant__ F
     const Ray r = make_ray(o, d, is.t_min);
     int c1 = 0;
     const int words = (n + 31) >> 5;
-    for (int w = 0; w < words; ++w) {
-      const int step = w * 32 + lane;
-      bool in = step < n;
-      float px, py, pz;
-      ray_point(r, P.stepdist, step, px, py, pz);
-      // render_utils_kernel.cu:191-192
-      in = in && !((P.xyz_min[0] > px) | (P.xyz_min[1] > py) | (P.xyz_min[2] > pz) |
-                   (P.xyz_max[0] < px) | (P.xyz_max[1] < py) | (P.xyz_max[2] < pz));
-      bool keep = false;
-      if (in && P.mask_grid == nullptr) keep = true;         // geometry_searching: no MaskCache
-      if (in && P.mask_grid != nullptr) {
-        // MaskCache.forward, model/nerf.py:1202-1209
-        float iw, ih, id;
-        cont_index(mg, px, py, pz, iw, ih, id);
-        bool gather = true;
-        if (occ) {
-          // cell of the sample; all 8 corners zero -> the trilinear value is exactly 0 < thres (thres > 0 checked by the
-          // host): no gathers.  Cells outside the grid (a model bbox larger than the mask's) take the full path.
-          const int cx = (int)floorf(iw), cy = (int)floorf(ih), cz = (int)floorf(id);
-          if (cx >= 0 && cx < mg.Z - 1 && cy >= 0 && cy < mg.Y - 1 && cz >= 0 && cz < mg.X - 1) {
-            const unsigned cell = ((unsigned)cz * (unsigned)(mg.Y - 1) + (unsigned)cy) * (unsigned)(mg.Z - 1) + (unsigned)cx;
-            gather = (__ldg(occ + (cell >> 5)) >> (cell & 31)) & 1u;
+    for (int w0 = 0; w0 < words; w0 += W) {
+      bool in[W], keep[W], gather[W];
+      float px[W], py[W], pz[W], iw[W], ih[W], id[W];
+      int cell[W];
+      // 1. points, bbox test (render_utils_kernel.cu:191-192), MaskCache index, occupancy cell
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const int step = (w0 + u) * 32 + lane;
+        in[u] = step < n;
+        ray_point(r, P.stepdist, step, px[u], py[u], pz[u]);
+        in[u] = in[u] && !((P.xyz_min[0] > px[u]) | (P.xyz_min[1] > py[u]) | (P.xyz_min[2] > pz[u]) |
+                           (P.xyz_max[0] < px[u]) | (P.xyz_max[1] < py[u]) | (P.xyz_max[2] < pz[u]));
+        keep[u] = in[u] && P.mask_grid == nullptr;           // geometry_searching: no MaskCache
+        gather[u] = in[u] && P.mask_grid != nullptr;
+        cell[u] = -1;
+        iw[u] = ih[u] = id[u] = 0.f;
+        if (gather[u]) {
+          cont_index(mg, px[u], py[u], pz[u], iw[u], ih[u], id[u]);   // MaskCache.forward, model/nerf.py:1202-1209
+          if (occ) {
+            const int cx = (int)floorf(iw[u]), cy = (int)floorf(ih[u]), cz = (int)floorf(id[u]);
+            if (cx >= 0 && cx < mg.Z - 1 && cy >= 0 && cy < mg.Y - 1 && cz >= 0 && cz < mg.X - 1)
+              cell[u] = (int)(((unsigned)cz * (unsigned)(mg.Y - 1) + (unsigned)cy) * (unsigned)(mg.Z - 1) + (unsigned)cx);
           }
         }
-        if (gather) {
-          const Tri t = tri_setup(iw, ih, id);
-          keep = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
+      }
+      // 2. occupancy words (all 8 corners zero -> the trilinear value is exactly 0 < thres: no gathers)
+      uint32_t ow[W];
+#pragma unroll
+      for (int u = 0; u < W; ++u) ow[u] = (cell[u] >= 0) ? __ldg(occ + ((unsigned)cell[u] >> 5)) : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < W; ++u) gather[u] = gather[u] && ((ow[u] >> (cell[u] & 31)) & 1u);
+      // 3. the mask gathers
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        if (gather[u]) {
+          const Tri t = tri_setup(iw[u], ih[u], id[u]);
+          keep[u] = tri_sample1(P.mask_grid, t, mg.X, mg.Y, mg.Z) >= thres;
         }
       }
-      if (keep && P.inc_mask != nullptr) {
-        // Incremental Voxel Training: MaskGrid.forward = maskcache_lookup (render_utils_kernel.cu:374-392)
-        const int i = (int)roundf(__fmaf_rn(px, P.inc_scale[0], P.inc_shift[0]));
-        const int j = (int)roundf(__fmaf_rn(py, P.inc_scale[1], P.inc_shift[1]));
-        const int k = (int)roundf(__fmaf_rn(pz, P.inc_scale[2], P.inc_shift[2]));
-        keep = 0 <= i && i < P.iX && 0 <= j && j < P.iY && 0 <= k && k < P.iZ &&
-               P.inc_mask[((size_t)i * P.iY + j) * P.iZ + k] != 0;
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        if (keep[u] && P.inc_mask != nullptr) {
+          // Incremental Voxel Training: MaskGrid.forward = maskcache_lookup (render_utils_kernel.cu:374-392)
+          const int i = (int)roundf(__fmaf_rn(px[u], P.inc_scale[0], P.inc_shift[0]));
+          const int j = (int)roundf(__fmaf_rn(py[u], P.inc_scale[1], P.inc_shift[1]));
+          const int k = (int)roundf(__fmaf_rn(pz[u], P.inc_scale[2], P.inc_shift[2]));
+          keep[u] = 0 <= i && i < P.iX && 0 <= j && j < P.iY && 0 <= k && k < P.iZ &&
+                    P.inc_mask[((size_t)i * P.iY + j) * P.iZ + k] != 0;
+        }
       }
-      const unsigned m0 = __ballot_sync(0xffffffffu, in);
-      const unsigned word = __ballot_sync(0xffffffffu, keep);
-      if (lane == 0) {
-        P.bits[(size_t)ray * P.cap_words + w] = word;
-        tot_m0 += __popc(m0);
+      // 4. bitmap words in step order
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, in[u]);
+        const unsigned word = __ballot_sync(0xffffffffu, keep[u]);
+        if (lane == 0 && w0 + u < words) {
+          P.bits[(size_t)ray * P.cap_words + w0 + u] = word;
+          tot_m0 += __popc(m0);
+        }
+        c1 += __popc(word);
       }
-      c1 += __popc(word);
     }
     if (lane == 0) P.cnt1[ray] = c1;
   }

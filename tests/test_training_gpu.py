@@ -130,37 +130,43 @@ def test_trainer_equals_hand_issued_iterations(cuda):
     eng = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(scene.FINE_TRAIN))
     eng.set_nonempty_mask()
     tr = training.FineTrainer(eng, *rays, cfg_train=cfg, start=start, rng=np.random.RandomState(7))
-    assert tr.run(K) == start + K
-    st = tr.stats()
-    assert st["steps"] == [start + 1, start + 2, start + 3] and np.isfinite(st["psnr"]) and st["terms"].shape == (K, 5)
 
     ref_t = dict(cfg, tv_terms=dict(sdf_tv=cfg["sdf_tv"], smooth_grad_tv=cfg["smooth_grad_tv"]))
     sch = stage_ref.RefSchedule(ref_t)
     sch._fresh_optimizer(0)                            # create_optimizer_or_freeze_model(global_step=0), nerf_training.py:117
     eng2 = engine.FineStepEngine(sc, N, cuda, train_cfg=dict(cfg))
     eng2.set_nonempty_mask()
+    eng2._ensure_adam()
     gen = training.batch_indices_generator(n_total, N, rng=np.random.RandomState(7))
     losses = []
+    # the scatter-adds are float atomics, so two runs agree to rounding (amplified by Adam where a gradient is itself
+    # rounding noise), not bit for bit.  Lockstep: before every iteration the hand-issued engine takes over the
+    # trainer's parameters and Adam moments, so that one decision taken differently after a last-bit difference is not
+    # integrated over the following iterations (see test_graph_launched_step_equals_directly_enqueued_step).
     for i in range(K):
         gs = start + 1 + i
+        with torch.no_grad():
+            for x, y in zip(_engine_state(eng2), _engine_state(tr.engine)):
+                x.copy_(y)
+        before = {"sdf": eng2.sdf.clone(), "k0": eng2.k0.clone(), "W0": eng2.weights[0].clone(), "W7": eng2.weights[7].clone()}
+        assert tr.run(1) == gs
         sel = torch.from_numpy(next(gen)).to(cuda)
         ro, rd, vd, tgt = [r[sel].contiguous() for r in rays]
         eng2.lr = dict(sch.lr)
         eng2.train_step(ro, rd, vd, tgt, gs)
         torch.cuda.synchronize()
         losses.append(eng2.ws["loss"].cpu().numpy().copy())
+        for name, a, b in (("sdf", tr.engine.sdf, eng2.sdf), ("k0", tr.engine.k0, eng2.k0),
+                           ("W0", tr.engine.weights[0], eng2.weights[0]), ("W7", tr.engine.weights[7], eng2.weights[7])):
+            lr = {"sdf": sch.lr["sdf"], "k0": sch.lr["k0"], "W0": sch.lr["rgbnet"], "W7": sch.lr["refnet"]}[name]
+            frac = _frac_differing(a, b, before[name], lr)
+            assert frac < 1e-2, f"{name}: {frac:.5f} of the parameters differ after iteration {gs}"
         sch.iteration(gs)
+    st = tr.stats()
+    assert st["steps"] == [start + 1, start + 2, start + 3] and np.isfinite(st["psnr"]) and st["terms"].shape == (K, 5)
     assert tr.engine.lr == pytest.approx(sch.lr, rel=1e-13)
     assert sch.lr["sdf"] < 0.11 * sch.lr["k0"] * cfg["lrate_sdf"] / cfg["lrate_k0"]      # decay_step_module applied
-    # the scatter-adds are float atomics, so two runs agree to rounding (amplified by Adam where a gradient is
-    # itself rounding noise), not bit for bit: first iteration tight, later ones to 1e-3
-    assert np.allclose(st["terms"][0], losses[0], rtol=1e-6, atol=1e-12)
-    assert np.allclose(st["terms"], np.stack(losses), rtol=1e-3, atol=1e-7)
-    for name, a, b, lr in (("sdf", tr.engine.sdf, eng2.sdf, cfg["lrate_sdf"]), ("k0", tr.engine.k0, eng2.k0, cfg["lrate_k0"]),
-                           ("W0", tr.engine.weights[0], eng2.weights[0], 1e-3), ("W7", tr.engine.weights[7], eng2.weights[7], 1e-3)):
-        before = {"sdf": sc.sdf, "k0": sc.k0, "W0": sc.rgbnet[0][0], "W7": sc.refnet[3][0]}[name].to(cuda)
-        frac = _frac_differing(a, b, before, lr)
-        assert frac < 1e-2, f"{name}: {frac:.5f} of the parameters differ after {K} iterations"
+    assert np.allclose(st["terms"], np.stack(losses), rtol=1e-6, atol=1e-12)
 
 
 def test_trainer_second_iteration_against_oracle_step(cuda):
@@ -452,33 +458,36 @@ def test_checkpoint_layout_and_round_trip(cuda, tmp_path):
 
 def test_library_sequenced_step_equals_host_sequenced_step(cuda):
     """fgs_fine_train_step (one call per iteration) against the same iteration sequenced launch by launch from
-    Python: three iterations with both TV terms on, then the parameters, the Adam state and the loss terms agree to
-    the rounding of the float atomics."""
+    Python: three iterations with both TV terms on; parameters, Adam state and loss terms agree to the rounding of
+    the float atomics.  The engines run in lockstep (see the graph test below): same state in, same state out."""
     from fgs_nerf_b200 import engine, scene
     N = 192
     sc = scene.make_scene(G=48, mask_G=40)
     cfg = dict(scene.FINE_TRAIN, tv_every=1)
     ro, rd, vd, tgt = [t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8)]
-    engs = []
-    for native in (True, False):
-        e = engine.FineStepEngine(sc, N, cuda, train_cfg=cfg)
+    a, b = [engine.FineStepEngine(sc, N, cuda, train_cfg=cfg) for _ in range(2)]
+    for e, native in ((a, True), (b, False)):
         e.set_nonempty_mask()
         e.native_step = native
-        losses = []
-        for gs in (5000, 5001, 5002):
+        e.use_graph = False                                     # the graph launch has its own test
+        e._ensure_adam()
+    la, lb = [], []
+    for gs in (5000, 5001, 5002):
+        with torch.no_grad():
+            for x, y in zip(_engine_state(a), _engine_state(b)):
+                x.copy_(y)
+        before = [t.clone() for t in (b.sdf, b.k0, b.weights[0], b.Bt[7])]
+        for e, losses in ((a, la), (b, lb)):
             e.lr["sdf"] *= 0.9                                   # the per-group rates reach both drivers
             e.train_step(ro, rd, vd, tgt, gs)
             torch.cuda.synchronize()
             losses.append(e.ws["loss"].cpu().numpy().copy())
-        engs.append((e, np.stack(losses)))
-    (a, la), (b, lb) = engs
-    assert a.adam_step == b.adam_step == 3 and la[:, 4].min() > 0           # the smooth-TV term was computed
-    assert np.allclose(la[0], lb[0], rtol=1e-6, atol=1e-12) and np.allclose(la, lb, rtol=1e-3, atol=1e-7)
-    for name, x, y, before, lr in (("sdf", a.sdf, b.sdf, sc.sdf, 0.005), ("k0", a.k0, b.k0, sc.k0, 0.1),
-                                   ("W0", a.weights[0], b.weights[0], sc.rgbnet[0][0], 1e-3),
-                                   ("B7", a.Bt[7], b.Bt[7], sc.refnet[3][1], 1e-3)):
-        assert _frac_differing(x, y, before.to(cuda), lr) < 1e-2, name
-    assert float((a.adam["sdf"][1] - b.adam["sdf"][1]).abs().max()) <= 1e-3 * float(b.adam["sdf"][1].abs().max())
+        assert np.allclose(la[-1], lb[-1], rtol=1e-6, atol=1e-12), (gs, la[-1], lb[-1])
+        for name, x, y, x0, lr in (("sdf", a.sdf, b.sdf, before[0], b.lr["sdf"]), ("k0", a.k0, b.k0, before[1], 0.1),
+                                   ("W0", a.weights[0], b.weights[0], before[2], 1e-3), ("B7", a.Bt[7], b.Bt[7], before[3], 1e-3)):
+            assert _frac_differing(x, y, x0, lr) < 1e-2, (gs, name)
+        assert float((a.adam["sdf"][1] - b.adam["sdf"][1]).abs().max()) <= 1e-3 * float(b.adam["sdf"][1].abs().max())
+    assert a.adam_step == b.adam_step == 3 and np.stack(la)[:, 4].min() > 0           # the smooth-TV term was computed
     assert int(a.ws["k0_brick_flags"].sum()) == 0 and float(a.g_sdf.abs().max()) == 0.0   # cleared by the optimiser
     # argument errors come back as RuntimeError, like every other entry point
     a._S.sdf_m = None
@@ -486,34 +495,54 @@ def test_library_sequenced_step_equals_host_sequenced_step(cuda):
         a.train_step(ro, rd, vd, tgt, 5003)
 
 
+def _engine_state(e):
+    """Everything an iteration reads and writes: parameters and Adam moments (the gradients are clear between steps)."""
+    e._ensure_adam()
+    t = [e.sdf, e.k0] + list(e.Wt) + list(e.Bt) + list(e.adam["sdf"]) + list(e.adam["k0"])
+    for pair in e.adam["W"] + e.adam["B"]:
+        t += list(pair)
+    return t
+
+
 def test_graph_launched_step_equals_directly_enqueued_step(cuda):
     """fgs_fine_train_step_graph (the iteration stream-captured and launched as ONE CUDA graph, its executable updated in
     place every iteration) against the directly enqueued iteration: six iterations that alternate TV / non-TV steps
-    (two graph shapes) with changing learning rates and ray batches; parameters, Adam state and loss terms agree to the
-    rounding of the float atomics, and the graph path was really taken."""
+    (two graph shapes) with changing learning rates and ray batches, and the graph path was really taken.
+
+    The two engines run in LOCKSTEP: before every iteration the graph engine takes over the other's parameters and Adam
+    moments, so each comparison is `same state in -> same state out` and only that iteration's float-atomics order
+    differs.  (Free-running both for six iterations was measured flaky on hardware, 5 failures in 12 runs: with ~1000
+    MLP rows one ReLU / threshold decision taken differently after a last-bit difference changes every weight gradient
+    by ~1e-3, which Adam then integrates past any per-element bound -- a property of the trajectory, not of the graph.)"""
     from fgs_nerf_b200 import engine, scene
     N = 192
     sc = scene.make_scene(G=48, mask_G=40)
     cfg = dict(scene.FINE_TRAIN, tv_every=2)
     batches = [[t.to(cuda) for t in scene.make_rays(N=N, H=100, W=100, n_views=8, offset=b * N)] for b in range(2)]
-    engs = []
-    for graph in (True, False):
-        e = engine.FineStepEngine(sc, N, cuda, train_cfg=cfg)
+    a, b = [engine.FineStepEngine(sc, N, cuda, train_cfg=cfg) for _ in range(2)]
+    for e, graph in ((a, True), (b, False)):
         e.set_nonempty_mask()
         e.use_graph = graph
-        losses = []
-        for i, gs in enumerate(range(5000, 5006)):
+        e._ensure_adam()
+    la, lb = [], []
+    for i, gs in enumerate(range(5000, 5006)):
+        with torch.no_grad():
+            for x, y in zip(_engine_state(a), _engine_state(b)):
+                x.copy_(y)
+        before = [t.clone() for t in (b.sdf, b.k0, b.weights[0], b.Bt[7])]
+        for e, losses in ((a, la), (b, lb)):
             e.lr["sdf"] *= 0.9
             e.train_step(*batches[i % 2], gs)
             torch.cuda.synchronize()
             losses.append(e.ws["loss"].cpu().numpy().copy())
-        e.check_overflow()
-        engs.append((e, np.stack(losses)))
-    (a, la), (b, lb) = engs
+        assert np.allclose(la[-1], lb[-1], rtol=1e-6, atol=1e-12), (i, la[-1], lb[-1])
+        for name, x, y, x0, lr in (("sdf", a.sdf, b.sdf, before[0], b.lr["sdf"]), ("k0", a.k0, b.k0, before[1], 0.1),
+                                   ("W0", a.weights[0], b.weights[0], before[2], 1e-3), ("B7", a.Bt[7], b.Bt[7], before[3], 1e-3)):
+            assert _frac_differing(x, y, x0, lr) < 1e-2, (i, name)
+        assert float((a.adam["sdf"][1] - b.adam["sdf"][1]).abs().max()) <= 1e-3 * float(b.adam["sdf"][1].abs().max())
+    a.check_overflow()
+    b.check_overflow()
+    la, lb = np.stack(la), np.stack(lb)
     assert a.graph_steps >= 4 and b.graph_steps == 0           # (the first iterations warm up outside the graph)
     assert a.adam_step == b.adam_step == 6
-    assert np.allclose(la[0], lb[0], rtol=1e-6, atol=1e-12) and np.allclose(la, lb, rtol=2e-3, atol=1e-7)
     assert (la[::2, 4] > 0).all() and (la[1::2, 4] == 0).all()  # smooth TV on the even steps only
-    for name, x, y, before, lr in (("sdf", a.sdf, b.sdf, sc.sdf, 0.005), ("k0", a.k0, b.k0, sc.k0, 0.1),
-                                   ("W0", a.weights[0], b.weights[0], sc.rgbnet[0][0], 1e-3)):
-        assert _frac_differing(x, y, before.to(cuda), lr) < 1e-2, name
