@@ -31,7 +31,7 @@ def main():
     c2, c3, c5, co = line("r02_bench_cfg2.json"), line("r02_bench_cfg3.json"), line("r02_bench_cfg5_n1.json"), line("r02_bench_coarse.json")
     rf, n2, n8 = line("r02_bench_reference.json"), line("r02_bench_cfg2_n2.json"), line("r02_bench_cfg2_n8.json")
     c4, c58 = line("r02_bench_cfg4_n8.json"), line("r02_bench_cfg5_n8.json")
-    # the multi-GPU lines were taken one build earlier (before march_kernel / feat_kernel changed by ~4.5 us per step):
+    # the 8-GPU lines were taken one build earlier (before march_kernel / feat_kernel changed by ~4.5 us per step):
     # their ratios are formed against the single-GPU line of THAT build and visit
     c2s = line("r02_bench_cfg2_prev.json") or c2
     go, cb = c2.get("gpu_oracle") or {}, c2.get("cpu_baseline") or {}
@@ -47,8 +47,8 @@ def main():
                  f"2048-ray steps) | {M(cb['value'])} / {M(rf['value']) if rf else '--'} | -- | -- | same line / `r02_bench_reference.json` |")
     t.append(row(f"3: 256^3, DTU camera, 8192 rays, 1 GPU (M2/ray {c3['config']['samples_per_ray']['M2']:.1f})" if c3 else "3", c3, "r02_bench_cfg3.json"))
     t.append(row("2 at 2 GPUs (8192 rays per rank)", n2, "r02_bench_cfg2_n2.json",
-                 extra=f": {n2['value'] / c2s['value']:.2f}x of the 1-GPU line of the same build ({c2s['ms_per_step']:.3f} ms, `r02_bench_cfg2_prev.json`)" if n2 else ""))
-    t.append(row("2 at 8 GPUs", n8, "r02_bench_cfg2_n8.json", extra=f": {n8['value'] / c2s['value']:.2f}x of the 1-GPU line of the same build" if n8 else ""))
+                 extra=f": {n2['value'] / c2['value']:.2f}x of 1 GPU (both lines: final build)" if n2 else ""))
+    t.append(row("2 at 8 GPUs", n8, "r02_bench_cfg2_n8.json", extra=f": {n8['value'] / c2s['value']:.2f}x of the 1-GPU line of the same build and visit ({c2s['ms_per_step']:.3f} ms, `r02_bench_cfg2_prev.json`)" if n8 else ""))
     t.append(row("4: 256^3, 8192 rays per rank, 8 GPUs", c4, "r02_bench_cfg4_n8.json"))
     t.append(row("5: 384^3, 800 x 800 image (640 K rays, 79 chunks), 1 GPU, inference", c5, "r02_bench_cfg5_n1.json", per=" / image"))
     t.append(row("5 at 8 GPUs (chunks dealt round-robin, one all-gather per output)", c58, "r02_bench_cfg5_n8.json", per=" / image",
