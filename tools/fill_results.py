@@ -34,6 +34,7 @@ def main():
     # the 8-GPU lines were taken one build earlier (before march_kernel / feat_kernel changed by ~4.5 us per step):
     # their ratios are formed against the single-GPU line of THAT build and visit
     c2s = line("r02_bench_cfg2_prev.json") or c2
+    c5p = line("r02_bench_cfg5_n1_prev.json") or c5
     go, cb = c2.get("gpu_oracle") or {}, c2.get("cpu_baseline") or {}
     spr = c2["config"]["samples_per_ray"]
     t = ["| configuration | rays/s (`value`) | ms / step | end to end (`e2e`) | file |", "|---|---|---|---|---|"]
@@ -52,7 +53,8 @@ def main():
     t.append(row("4: 256^3, 8192 rays per rank, 8 GPUs", c4, "r02_bench_cfg4_n8.json"))
     t.append(row("5: 384^3, 800 x 800 image (640 K rays, 79 chunks), 1 GPU, inference", c5, "r02_bench_cfg5_n1.json", per=" / image"))
     t.append(row("5 at 8 GPUs (chunks dealt round-robin, one all-gather per output)", c58, "r02_bench_cfg5_n8.json", per=" / image",
-                 extra=f": {c58['value'] / c5['value']:.2f}x of 1 GPU" if c58 and c5 else ""))
+                 extra=(f": {c58['value'] / c5p['value']:.2f}x of the 1-GPU line of the same build and visit ({M(c5p['value'])}, `r02_bench_cfg5_n1_prev.json`)"
+                        if c58 and c5p else "")))
     t.append(row(f"coarse stage (8f row 1): 116^3, 8192 rays, 1 GPU (M2/ray {co['config']['samples_per_ray']['M2']:.1f})" if co else "coarse", co, "r02_bench_coarse.json"))
     ge = line("r02_bench_geometry.json")
     t.append(row(f"geometry_searching stage (8f row 1): 120^3, 6-ch k0, 8192 rays, 1 GPU (no MaskCache: M2/ray {ge['config']['samples_per_ray']['M2']:.1f})" if ge else "geometry_searching", ge, "r02_bench_geometry.json"))
