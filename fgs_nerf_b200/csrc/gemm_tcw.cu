@@ -163,22 +163,62 @@ struct SplitJobs {
   int n;
 };
 
+// One CTA (32 x 8 threads) per 32 x 32 tile of a job, four rows per thread: the reads are coalesced along the columns
+// of W; a straight job writes the same way, a transposed job goes through a padded shared-memory tile so that its
+// writes are coalesced along the rows of W (the first version indexed the flat element range with a division per
+// element and wrote the transposed bf16 planes as scattered 2-byte stores: 18 us per step for 7 MB).
 __global__ void __launch_bounds__(256) weight_split_kernel(const __grid_constant__ SplitJobs jobs) {
   const SplitJob& J = jobs.j[blockIdx.y];
-  const int total = J.rows * J.cols;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int r = i / J.cols, c = i - r * J.cols;
-    const float x = J.W[(size_t)r * J.ld + c];
-    const size_t o = J.transpose ? (size_t)c * J.ld_out + r : (size_t)r * J.ld_out + c;
-    if (J.bf16) {
-      const uint32_t h = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
-      const uint32_t m = __float_as_uint(x - __uint_as_float(h)) + 0x8000u;
-      reinterpret_cast<uint16_t*>(J.hi)[o] = (uint16_t)(h >> 16);
-      reinterpret_cast<uint16_t*>(J.lo)[o] = (uint16_t)(m >> 16);
-    } else {
-      const float h = rn_tf32(x), l = rn_tf32(x - h);
-      J.hi[o] = h;
-      J.lo[o] = l;
+  __shared__ uint32_t s_hi[32][33], s_lo[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_c = (J.cols + 31) >> 5, tiles_r = (J.rows + 31) >> 5;
+  for (int t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const int r0 = (t / tiles_c) << 5, c0 = (t - (t / tiles_c) * tiles_c) << 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + 8 * k, c = c0 + tx;
+      uint32_t h = 0, l = 0;
+      if (r < J.rows && c < J.cols) {
+        const float x = J.W[(size_t)r * J.ld + c];
+        if (J.bf16) {
+          h = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+          l = __float_as_uint(x - __uint_as_float(h)) + 0x8000u;
+        } else {
+          const float hf = rn_tf32(x);
+          h = __float_as_uint(hf);
+          l = __float_as_uint(rn_tf32(x - hf));
+        }
+        if (!J.transpose) {
+          const size_t o = (size_t)r * J.ld_out + c;
+          if (J.bf16) {
+            reinterpret_cast<uint16_t*>(J.hi)[o] = (uint16_t)(h >> 16);
+            reinterpret_cast<uint16_t*>(J.lo)[o] = (uint16_t)(l >> 16);
+          } else {
+            J.hi[o] = __uint_as_float(h);
+            J.lo[o] = __uint_as_float(l);
+          }
+        }
+      }
+      if (J.transpose) { s_hi[ty + 8 * k][tx] = h; s_lo[ty + 8 * k][tx] = l; }
+    }
+    if (J.transpose) {                                   // (uniform per CTA)
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;     // out[c][r]: consecutive lanes -> consecutive r
+        if (r < J.rows && c < J.cols) {
+          const uint32_t h = s_hi[tx][ty + 8 * k], l = s_lo[tx][ty + 8 * k];
+          const size_t o = (size_t)c * J.ld_out + r;
+          if (J.bf16) {
+            reinterpret_cast<uint16_t*>(J.hi)[o] = (uint16_t)(h >> 16);
+            reinterpret_cast<uint16_t*>(J.lo)[o] = (uint16_t)(l >> 16);
+          } else {
+            J.hi[o] = __uint_as_float(h);
+            J.lo[o] = __uint_as_float(l);
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -2281,7 +2321,9 @@ int weight_split_jobs(const SplitJobHost* jobs, int n, cudaStream_t st) {
     J.j[i].rows = jobs[i].rows; J.j[i].cols = jobs[i].cols; J.j[i].ld = jobs[i].ld;
     J.j[i].ld_out = jobs[i].ld_out; J.j[i].transpose = jobs[i].transpose; J.j[i].bf16 = jobs[i].bf16;
   }
-  weight_split_kernel<<<dim3(32, n), 256, 0, st>>>(J);
+  int tiles = 1;
+  for (int i = 0; i < n; ++i) tiles = max(tiles, ((jobs[i].rows + 31) / 32) * ((jobs[i].cols + 31) / 32));
+  weight_split_kernel<<<dim3(min(tiles, 4 * FGS_NUM_SMS), n), 256, 0, st>>>(J);
   return fgs::check_launch("weight_split", st);
 }
 
