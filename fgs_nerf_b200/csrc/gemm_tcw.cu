@@ -1944,7 +1944,9 @@ split_planes_kernel(const float* __restrict__ X, int ld, int rows, int cols, uin
 // A fp32 [K][lda] (lda >= 4, m < 4), B fp32 [K][ldb].  On the tensor-core kernel these problems cost as much as a
 // 256-out-feature layer (the MMA is 256 rows tall: 2 of 16 tiles, 12 % of the kernel, for 0.3 % of the FLOPs); here one
 // thread per input feature streams B once (coalesced rows) with the A row broadcast from shared memory.
-constexpr int kDwSmallRows = 64;
+// (16 rows per chunk: the grid is sized from the CAPACITY -- 592 CTAs -- while the row count lives on the device, so
+// with 64-row chunks 44 K rows were 693 chunks = two rounds with the second 17 % full; 16-row chunks balance to 6 %)
+constexpr int kDwSmallRows = 16;
 __global__ void __launch_bounds__(256)
 dw_small_kernel(const float* __restrict__ A, int lda, int M, const float* __restrict__ B, int ldb, int N,
                 float* __restrict__ C, int ldc, int K, const int* __restrict__ rows_dev) {
@@ -1953,27 +1955,22 @@ dw_small_kernel(const float* __restrict__ A, int lda, int M, const float* __rest
   const int n = blockIdx.y * 256 + threadIdx.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k0 = blockIdx.x * kDwSmallRows; k0 < K; k0 += gridDim.x * kDwSmallRows) {
-    __syncthreads();
+    // the chunk's 16 B rows first (independent loads, all in flight), THEN the A rows through shared memory: the A load's
+    // latency hides behind the B loads instead of in front of them
+    float b[kDwSmallRows];
+#pragma unroll
+    for (int j = 0; j < kDwSmallRows; ++j) b[j] = (n < N && k0 + j < K) ? __ldg(B + (size_t)(k0 + j) * ldb + n) : 0.f;
+    __syncthreads();                                   // the previous chunk's readers of s_a are done
     if (threadIdx.x < kDwSmallRows) {
       const int k = k0 + threadIdx.x;
       s_a[threadIdx.x] = k < K ? *reinterpret_cast<const float4*>(A + (size_t)k * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (n < N) {
-      // 16 independent row loads in flight per thread, then the FMAs (a loop with a run-time trip count left every
-      // load's latency exposed: 0.5 us per row)
-#pragma unroll 1
-      for (int r0 = 0; r0 < kDwSmallRows && k0 + r0 < K; r0 += 16) {
-        float b[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) b[j] = (k0 + r0 + j < K) ? __ldg(B + (size_t)(k0 + r0 + j) * ldb + n) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 a4 = s_a[r0 + j];
-          acc[0] = fmaf(a4.x, b[j], acc[0]); acc[1] = fmaf(a4.y, b[j], acc[1]);
-          acc[2] = fmaf(a4.z, b[j], acc[2]); acc[3] = fmaf(a4.w, b[j], acc[3]);
-        }
-      }
+    for (int j = 0; j < kDwSmallRows; ++j) {
+      const float4 a4 = s_a[j];
+      acc[0] = fmaf(a4.x, b[j], acc[0]); acc[1] = fmaf(a4.y, b[j], acc[1]);
+      acc[2] = fmaf(a4.z, b[j], acc[2]); acc[3] = fmaf(a4.w, b[j], acc[3]);
     }
   }
   if (n < N)
